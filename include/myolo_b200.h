@@ -1,0 +1,157 @@
+/* myolo_b200.h -- C ABI of libmyolo_sm100.so, the B200 (sm_100a) kernels behind the Mask-YOLO
+ * hot path (jianing-sun/Mask-YOLO @ 402dbd9).
+ *
+ * The reference has no FFI: its hot path is a Keras/TensorFlow graph (myolo/model.py) whose
+ * arithmetic runs inside TF ops.  Each entry point below replaces one TF-op call site of that
+ * graph (cited per function as myolo/model.py:LINE and the SURVEY.md section 2.3 kernel id).
+ * INTEGRATION.md shows the ctypes binding the Python host side uses.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in _host; fp32 unless stated;
+ *  - activations are NHWC, described by a myolo_view (strided: innermost C contiguous);
+ *  - conv kernels are HWIO ([tap][Cin][Cout]), depthwise [3][3][C], deconv [2][2][Cout][Cin];
+ *  - nothing allocates, nothing synchronises; work is enqueued on `stream` (a cudaStream_t);
+ *  - return value 0 on success, negative on error; myolo_last_error() describes the failure;
+ *  - the library refuses to run on anything but compute capability 10.x (no fallback).
+ */
+#ifndef MYOLO_B200_H_
+#define MYOLO_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* myolo_stream;            /* cudaStream_t */
+
+/* Strided NHWC view.  pixel (n,h,w) channel c lives at p[n*sn + h*sh + w*c_stride... ] with the
+ * pixel stride fixed to C:  addr = p + n*sn + h*sh + w*C + c.   Dense: sh=W*C, sn=H*W*C.
+ * "Padded-flat" (PF) tensors are the same struct with sh=(W+1)*C,
+ * sn=(H+1)*(W+1)*C and p pointing at pixel (0,0). */
+typedef struct {
+  float* p;
+  long long sn, sh;
+  int n, h, w, c;
+} myolo_view;
+
+enum { MYOLO_ACT_NONE = 0, MYOLO_ACT_RELU = 1, MYOLO_ACT_RELU6 = 2 };
+enum { MYOLO_OK = 0, MYOLO_ERR_ARG = -1, MYOLO_ERR_CUDA = -2, MYOLO_ERR_DEVICE = -3 };
+
+/* ---- library --------------------------------------------------------------------------- */
+int myolo_version(void);
+const char* myolo_last_error(void);
+/* 0 iff device `dev` is sm_100-class; otherwise MYOLO_ERR_DEVICE (no other target is supported). */
+int myolo_device_check(int dev);
+
+/* ---- K1: first conv, myolo/model.py:45-50 (ZeroPad(1,1) + Conv 3x3 s2 VALID, 3->Cout) ---- */
+int myolo_conv1_fwd(const float* x, const float* w, float* y, int B, int S, int Cout, myolo_stream stream);
+int myolo_conv1_wgrad(const float* x, const float* dy, float* dw, int B, int S, int Cout, myolo_stream stream);
+
+/* ---- K2: depthwise 3x3, myolo/model.py:68-77,256-268 (ZeroPad(1,1) + DepthwiseConv VALID) ---- */
+int myolo_dwconv3x3_fwd(const float* x, const float* w, float* y, int B, int H, int W, int C, int stride, myolo_stream stream);
+int myolo_dwconv3x3_bwd_data(const float* dy, const float* w, float* dx, int B, int H, int W, int C, int stride, myolo_stream stream);
+int myolo_dwconv3x3_bwd_filter(const float* x, const float* dy, float* dw, int B, int H, int W, int C, int stride, myolo_stream stream);
+
+/* ---- K3/K6/K8/K10: tap-GEMM family (pointwise 1x1, 3x3 SAME on padded-flat tiles, deconv) ----
+ * C[m,n] = epi( sum_t sum_k A[m + shift[t], k] * Bt[t][k][n] ),  m in [0,M)
+ *   A row-major, leading dim lda;  Bt = B + t*K*N row-major [K,N];  C row-major ldc.
+ *   epi: (+ bias[n]) -> (* scale[n] + shift_c[n]) -> act;   bias/scale may be NULL.
+ *   pf_w1>0: rows are a padded-flat tiling with (W+1)=pf_w1 and block pf_blk; pad rows are NOT
+ *   written (they stay zero).  accumulate!=0: C += result (no epilogue affine/act allowed).
+ * Replaces tf Conv2D call sites myolo/model.py:271, 688-706, 848 and keras_applications pw convs. */
+int myolo_gemm_taps(const float* A, long long lda, const float* B, float* C, long long ldc,
+                    long long M, int N, int K, int ntaps, const int* shifts_host,
+                    const float* bias, const float* scale, const float* shift_c, int act,
+                    int pf_w1, int pf_blk, int accumulate, myolo_stream stream);
+/* wgrad: dW[t][k][n] += sum_m A[m + shift[t], k] * D[m, n]   (fp32 atomics; dW pre-zeroed by caller)
+ * transpose_out!=0 stores dW as [t][n][k] instead. */
+int myolo_gemm_taps_wgrad(const float* A, long long lda, const float* D, long long ldd, float* dW,
+                          long long M, int N, int K, int ntaps, const int* shifts_host,
+                          int transpose_out, myolo_stream stream);
+/* out[t][c][r] = in[t][r][c]  (per-tap weight transpose for dgrad / deconv) */
+int myolo_transpose_taps(const float* in, float* out, int ntaps, int rows, int cols, myolo_stream stream);
+/* pointwise / 3x3 named wrappers (SURVEY 8b names) */
+int myolo_pwconv_fwd(const float* x, const float* w, float* y, long long M, int Cin, int Cout,
+                     const float* bias, myolo_stream stream);
+int myolo_pwconv_dgrad(const float* dy, const float* wT, float* dx, long long M, int Cin, int Cout, myolo_stream stream);
+int myolo_pwconv_wgrad(const float* x, const float* dy, float* dw, long long M, int Cin, int Cout, myolo_stream stream);
+/* 3x3 SAME conv on a padded-flat tensor: n_img tiles of H x W, rows = n_img*(H+1)*(W+1). x and y point at
+ * row 0 of the tiling (guards of >= W+2 zero rows must exist on both sides of x). */
+int myolo_conv3x3_fwd(const float* x, const float* w, float* y, int n_img, int H, int W, int Cin, int Cout,
+                      const float* bias, const float* scale, const float* shift_c, int act, myolo_stream stream);
+int myolo_conv3x3_dgrad(const float* dy, const float* wT, float* dx, int n_img, int H, int W, int Cin, int Cout, myolo_stream stream);
+int myolo_conv3x3_wgrad(const float* x, const float* dy, float* dw, int n_img, int H, int W, int Cin, int Cout, myolo_stream stream);
+
+/* ---- K4/K5/K9: batch norm + activation (Keras BatchNormalization eps 1e-3) ---- */
+/* mean[c], var[c] (biased) over all pixels of x; ws = 2*C doubles of scratch (zeroed inside). */
+int myolo_bn_stats(const myolo_view* x, float* mean, float* var, double* ws, myolo_stream stream);
+/* y = act(gamma*(x-mean)*rsqrt(var+eps)+beta) */
+int myolo_bn_apply(const myolo_view* x, const myolo_view* y, const float* mean, const float* var,
+                   const float* gamma, const float* beta, float eps, int act, myolo_stream stream);
+/* backward of act(BN(x)). train!=0: batch-statistics BN (mean/var are this batch's); else moving stats.
+ * dgamma/dbeta are OVERWRITTEN. ws = 2*C doubles. dx may alias dy. */
+int myolo_bn_bwd(const myolo_view* x, const myolo_view* dy, const myolo_view* dx, const float* mean, const float* var,
+                 const float* gamma, const float* beta, float eps, int act, int train,
+                 float* dgamma, float* dbeta, double* ws, myolo_stream stream);
+/* Keras moving-average update with TF zero-debias: biased -= (biased-value)*(1-momentum);
+ * moving = biased/(1-momentum^step). value = mean, or var*bessel*n/(n-(1+eps)) when is_var. */
+int myolo_bn_moving_update(const float* value, float* biased, float* moving, int C, float momentum, int step,
+                           int is_var, double n, float eps, myolo_stream stream);
+/* out[c] (=|+=) sum over pixels of x[.,c]  (bias gradients). ws = C doubles. */
+int myolo_colsum(const myolo_view* x, float* out, double* ws, myolo_stream stream);
+/* dst (=|+=) src over valid pixels (dense <-> padded-flat moves, gradient joins) */
+int myolo_view_copy(const myolo_view* src, const myolo_view* dst, int accumulate, myolo_stream stream);
+
+/* ---- K7: PyramidROIAlign, myolo/model.py:385-387 = tf.image.crop_and_resize(feat, boxes, idx, (P,P)) ----
+ * boxes[n_roi][4] are consumed as (y1,x1,y2,x2) exactly like the TF op; the reference passes
+ * (x1,y1,x2,y2) and so does the host side here.  roi n samples image n / rois_per_img. */
+int myolo_roialign_fwd(const myolo_view* feat, const float* boxes, int n_roi, int rois_per_img, int pool,
+                       const myolo_view* out, myolo_stream stream);
+int myolo_roialign_bwd(const myolo_view* dout, const float* boxes, int n_roi, int rois_per_img, int pool,
+                       const myolo_view* dfeat, myolo_stream stream);
+
+/* ---- K12: DecodeYOLOLayer / DetectionsLayer, myolo/model.py:1442-1473, 1493-1538 ---- */
+int myolo_yolo_decode(const float* y_pred, const float* anchors, float* boxes, float* detections /*nullable*/,
+                      int B, int GH, int GW, int NB, int NC, myolo_stream stream);
+
+/* ---- K13: DetectMaskTargetLayer, myolo/model.py:457-602 (+ norm_boxes_graph 1394-1408) ----
+ * gt_boxes are PIXEL (x1,y1,x2,y2) as fed to the model; normalisation happens inside.
+ * Outputs: rois [B,R,4], target_ids [B,R] int32, target_masks [B,R,MH,MW], n_pos [B] int32,
+ * roi_src [B,R] int32 (source proposal index, -1 for padding), roi_gt [B,R] int32 (matched GT, -1). */
+int myolo_detect_mask_targets(const float* proposals, const int* gt_class_ids, const float* gt_boxes,
+                              const unsigned char* gt_masks, int B, int R, int M, int S, int MH, int MW,
+                              float* rois, int* target_ids, float* target_masks, int* n_pos,
+                              int* roi_src, int* roi_gt, myolo_stream stream);
+
+/* ---- K10+K11: mask output, myolo/model.py:711-713.  y4 = deconv GEMM output rows [p][(a,b,co)]
+ * (padded-flat H x W tiles, pre-bias).  masks[n][2h+a][2w+b][k] = sigmoid(b1[k] + sum_co relu(y4+bd[co]) * w1[co][k]) */
+int myolo_mask_out_fwd(const float* y4, const float* bd, const float* w1, const float* b1, float* masks,
+                       int n_roi, int H, int W, int Cmid, int NC, myolo_stream stream);
+/* backward: dlogit [n][2H][2W][NC] -> dy4 (same layout as y4), dw1 [Cmid][NC] +=, db1 [NC] +=, dbd [Cmid] += */
+int myolo_mask_out_bwd(const float* y4, const float* bd, const float* w1, const float* dlogit,
+                       float* dy4, float* dw1, float* db1, float* dbd,
+                       int n_roi, int H, int W, int Cmid, int NC, myolo_stream stream);
+
+/* ---- K16: myolo_mask_loss_graph, myolo/model.py:718-754 (Keras binary_crossentropy) ----
+ * loss_out[0] = mean BCE over positive rois' class masks (0 if none). dlogit (pre-sigmoid gradient,
+ * scaled by loss_weight) is written for every element (zeros off the positive/class entries).
+ * ws: 2 doubles. */
+int myolo_mask_loss(const float* masks, const float* target_masks, const int* target_ids, int n_roi,
+                    int MH, int MW, int NC, float loss_weight, float* loss_out, float* dlogit /*nullable*/,
+                    double* ws, myolo_stream stream);
+
+/* ---- K15: yolo_custom_loss, myolo/model.py:86-242 ----
+ * scales = {OBJECT, NO_OBJECT, COORD, CLASS}; warmup!=0 selects the warm-up branch (196-207).
+ * loss_out[0..4] = total, xy, wh, conf, class. dy_pred (nullable) = d(loss_weight*total)/dy_pred. ws: 8 doubles. */
+int myolo_yolo_loss(const float* y_true, const float* y_pred, const float* true_boxes, const float* anchors,
+                    const float* class_weights, int B, int GH, int GW, int NB, int NC, int TB,
+                    const float* scales_host, int warmup, float loss_weight,
+                    float* loss_out, float* dy_pred, double* ws, myolo_stream stream);
+
+/* ---- K17: Keras Adam, myolo/model.py:1071-1075 ----  lr_t = lr*sqrt(1-b2^t)/(1-b1^t) computed by caller */
+int myolo_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr_t,
+                    float b1, float b2, float eps, float grad_scale, myolo_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MYOLO_B200_H_ */

@@ -1,0 +1,299 @@
+// bn.cu -- BatchNormalization (+ fused activation) forward/backward, per-channel reductions and
+// strided-view moves.  All HBM-bound: float4 channel vectors, 128 B per pixel per 8-thread group,
+// per-block smem reduction then ONE fp64 atomic per (block, channel) so the batch statistics are
+// reproducible to fp32 rounding.  Replaces TF FusedBatchNorm / FusedBatchNormGrad (K4, K9) and the
+// Relu / Relu6 nodes (K5); Keras semantics restated in SURVEY.md Q7.
+#include "common.cuh"
+
+namespace myolo {
+
+struct V {  // device copy of myolo_view
+  float* p;
+  long long sn, sh;
+  int n, h, w, c;
+};
+static inline V to_v(const myolo_view* v) { return V{v->p, v->sn, v->sh, v->n, v->h, v->w, v->c}; }
+
+__device__ __forceinline__ size_t pix_off(const V& v, long long pix) {
+  const int w = (int)(pix % v.w);
+  const long long t = pix / v.w;
+  const int h = (int)(t % v.h);
+  const long long n = t / v.h;
+  return (size_t)(n * v.sn + h * v.sh + (long long)w * v.c);
+}
+
+__device__ __forceinline__ float act_grad_mask(float y, int act) {
+  if (act == MYOLO_ACT_RELU) return y > 0.f ? 1.f : 0.f;
+  if (act == MYOLO_ACT_RELU6) return (y > 0.f && y < 6.f) ? 1.f : 0.f;
+  return 1.f;
+}
+
+// MODE 0: s0 += x                 MODE 1: s0 += (x-mean)^2
+// MODE 2: g = dy*act'(y); s0 += g; s1 += g*xhat
+template <int MODE>
+__global__ void __launch_bounds__(256)
+colreduce_kernel(V x, V dy, const float* __restrict__ mean, const float* __restrict__ var,
+                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int act,
+                 double* __restrict__ out0, double* __restrict__ out1, long long chunk) {
+  __shared__ float red[2][32][33];
+  const int tid = threadIdx.x;
+  const int cq = tid & 7, pg = tid >> 3;
+  const int c0 = blockIdx.y * 32 + cq * 4;
+  const long long total = (long long)x.n * x.h * x.w;
+  const long long p0 = blockIdx.x * chunk, p1 = min(total, p0 + chunk);
+  float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), rs = mu, ga = mu, be = mu;
+  if (MODE >= 1) mu = *reinterpret_cast<const float4*>(mean + c0);
+  if (MODE == 2) {
+    const float4 vv = *reinterpret_cast<const float4*>(var + c0);
+    rs = make_float4(1.f / sqrtf(vv.x + eps), 1.f / sqrtf(vv.y + eps), 1.f / sqrtf(vv.z + eps), 1.f / sqrtf(vv.w + eps));
+    ga = *reinterpret_cast<const float4*>(gamma + c0);
+    be = *reinterpret_cast<const float4*>(beta + c0);
+  }
+  float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+  for (long long p = p0 + pg; p < p1; p += 32) {
+    const float4 v = *reinterpret_cast<const float4*>(x.p + pix_off(x, p) + c0);
+    if (MODE == 0) {
+      s0.x += v.x; s0.y += v.y; s0.z += v.z; s0.w += v.w;
+    } else if (MODE == 1) {
+      const float a = v.x - mu.x, b = v.y - mu.y, c = v.z - mu.z, d = v.w - mu.w;
+      s0.x = fmaf(a, a, s0.x); s0.y = fmaf(b, b, s0.y); s0.z = fmaf(c, c, s0.z); s0.w = fmaf(d, d, s0.w);
+    } else {
+      const float4 g = *reinterpret_cast<const float4*>(dy.p + pix_off(dy, p) + c0);
+      const float xh0 = (v.x - mu.x) * rs.x, xh1 = (v.y - mu.y) * rs.y, xh2 = (v.z - mu.z) * rs.z, xh3 = (v.w - mu.w) * rs.w;
+      const float g0 = g.x * act_grad_mask(fmaf(xh0, ga.x, be.x), act);
+      const float g1 = g.y * act_grad_mask(fmaf(xh1, ga.y, be.y), act);
+      const float g2 = g.z * act_grad_mask(fmaf(xh2, ga.z, be.z), act);
+      const float g3 = g.w * act_grad_mask(fmaf(xh3, ga.w, be.w), act);
+      s0.x += g0; s0.y += g1; s0.z += g2; s0.w += g3;
+      s1.x = fmaf(g0, xh0, s1.x); s1.y = fmaf(g1, xh1, s1.y); s1.z = fmaf(g2, xh2, s1.z); s1.w = fmaf(g3, xh3, s1.w);
+    }
+  }
+  red[0][cq * 4 + 0][pg] = s0.x; red[0][cq * 4 + 1][pg] = s0.y; red[0][cq * 4 + 2][pg] = s0.z; red[0][cq * 4 + 3][pg] = s0.w;
+  if (MODE == 2) {
+    red[1][cq * 4 + 0][pg] = s1.x; red[1][cq * 4 + 1][pg] = s1.y; red[1][cq * 4 + 2][pg] = s1.z; red[1][cq * 4 + 3][pg] = s1.w;
+  }
+  __syncthreads();
+  const int nred = (MODE == 2) ? 64 : 32;
+  if (tid < nred) {
+    const int which = tid >> 5, c = tid & 31;
+    double s = 0.0;
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) s += (double)red[which][c][j];
+    atomicAdd((which ? out1 : out0) + blockIdx.y * 32 + c, s);
+  }
+}
+
+// arbitrary (small) C: one thread per channel, serial over pixels.  Only used for tiny tensors.
+__global__ void colsum_generic_kernel(V x, double* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= x.c) return;
+  const long long total = (long long)x.n * x.h * x.w;
+  double s = 0.0;
+  for (long long p = blockIdx.y; p < total; p += gridDim.y) s += (double)x.p[pix_off(x, p) + c];
+  atomicAdd(out + c, s);
+}
+
+__global__ void finalize_div_kernel(const double* __restrict__ s, float* __restrict__ out, int C, double inv, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) out[c] = (accumulate ? out[c] : 0.f) + (float)(s[c] * inv);
+}
+
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(V x, V y, const float* __restrict__ mean, const float* __restrict__ var,
+                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int act) {
+  const int C4 = x.c >> 2;
+  const long long total = (long long)x.n * x.h * x.w * C4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % C4) * 4;
+    const long long p = i / C4;
+    const float4 v = *reinterpret_cast<const float4*>(x.p + pix_off(x, p) + q);
+    const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + q));
+    const float4 vv = __ldg(reinterpret_cast<const float4*>(var + q));
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + q));
+    const float4 be = __ldg(reinterpret_cast<const float4*>(beta + q));
+    float4 o;
+    o.x = apply_act(fmaf((v.x - mu.x) * (1.f / sqrtf(vv.x + eps)), ga.x, be.x), act);
+    o.y = apply_act(fmaf((v.y - mu.y) * (1.f / sqrtf(vv.y + eps)), ga.y, be.y), act);
+    o.z = apply_act(fmaf((v.z - mu.z) * (1.f / sqrtf(vv.z + eps)), ga.z, be.z), act);
+    o.w = apply_act(fmaf((v.w - mu.w) * (1.f / sqrtf(vv.w + eps)), ga.w, be.w), act);
+    *reinterpret_cast<float4*>(y.p + pix_off(y, p) + q) = o;
+  }
+}
+
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ ws, float* __restrict__ dgamma, float* __restrict__ dbeta, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    dbeta[c] = (float)ws[c];
+    dgamma[c] = (float)ws[C + c];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_dx_kernel(V x, V dy, V dx, const float* __restrict__ mean, const float* __restrict__ var,
+                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int act, int train,
+                 const double* __restrict__ ws, double inv_count) {
+  const int C = x.c, C4 = C >> 2;
+  const long long total = (long long)x.n * x.h * x.w * C4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % C4) * 4;
+    const long long p = i / C4;
+    const float4 v = *reinterpret_cast<const float4*>(x.p + pix_off(x, p) + q);
+    const float4 g = *reinterpret_cast<const float4*>(dy.p + pix_off(dy, p) + q);
+    const float vin[4] = {v.x, v.y, v.z, v.w};
+    const float gin[4] = {g.x, g.y, g.z, g.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = q + j;
+      const float rs = 1.f / sqrtf(__ldg(var + c) + eps);
+      const float ga = __ldg(gamma + c);
+      const float xh = (vin[j] - __ldg(mean + c)) * rs;
+      const float gg = gin[j] * act_grad_mask(fmaf(xh, ga, __ldg(beta + c)), act);
+      if (train) {
+        const float m0 = (float)(ws[c] * inv_count), m1 = (float)(ws[C + c] * inv_count);
+        o[j] = ga * rs * (gg - m0 - xh * m1);
+      } else {
+        o[j] = ga * rs * gg;
+      }
+    }
+    *reinterpret_cast<float4*>(dx.p + pix_off(dx, p) + q) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+__global__ void bn_moving_update_kernel(const float* __restrict__ value, float* __restrict__ biased,
+                                        float* __restrict__ moving, int C, float momentum, float corr, float debias) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    const float v = value[c] * corr;
+    const float b = biased[c] - (biased[c] - v) * (1.f - momentum);
+    biased[c] = b;
+    moving[c] = b / debias;
+  }
+}
+
+__global__ void __launch_bounds__(256) view_copy_kernel(V src, V dst, int accumulate) {
+  const int C4 = src.c >> 2;
+  const long long total = (long long)src.n * src.h * src.w * C4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % C4) * 4;
+    const long long p = i / C4;
+    float4 v = *reinterpret_cast<const float4*>(src.p + pix_off(src, p) + q);
+    float4* d = reinterpret_cast<float4*>(dst.p + pix_off(dst, p) + q);
+    if (accumulate) {
+      const float4 o = *d;
+      v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+    }
+    *d = v;
+  }
+}
+
+static bool view_ok(const myolo_view* v) {
+  return v && v->p && v->n > 0 && v->h > 0 && v->w > 0 && v->c > 0 && (v->c % 4) == 0 && (v->sn % 4) == 0 && (v->sh % 4) == 0;
+}
+static bool same_shape(const myolo_view* a, const myolo_view* b) {
+  return a->n == b->n && a->h == b->h && a->w == b->w && a->c == b->c;
+}
+static void reduce_grid(long long total, int C, dim3* grid, long long* chunk) {
+  const int cg = C / 32;
+  long long nch = max(1LL, min(ceil_div(total, 64), (long long)(kNumSMs * 8) / cg + 1));
+  *chunk = ceil_div(total, nch);
+  nch = ceil_div(total, *chunk);
+  *grid = dim3((unsigned)nch, (unsigned)cg);
+}
+static int ew_blocks(long long total) { return (int)max(1LL, min(ceil_div(total, 256), (long long)kNumSMs * 16)); }
+
+}  // namespace myolo
+
+using namespace myolo;
+
+extern "C" int myolo_bn_stats(const myolo_view* x, float* mean, float* var, double* ws, myolo_stream stream) {
+  MYOLO_CHECK_ARG(view_ok(x) && mean && var && ws && (x->c % 32) == 0);
+  cudaStream_t st = as_stream(stream);
+  const int C = x->c;
+  const long long total = (long long)x->n * x->h * x->w;
+  dim3 grid;
+  long long chunk;
+  reduce_grid(total, C, &grid, &chunk);
+  V vx = to_v(x);
+  MYOLO_CUDA(cudaMemsetAsync(ws, 0, 2 * C * sizeof(double), st));
+  colreduce_kernel<0><<<grid, 256, 0, st>>>(vx, vx, nullptr, nullptr, nullptr, nullptr, 0.f, 0, ws, nullptr, chunk);
+  finalize_div_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, mean, C, 1.0 / (double)total, 0);
+  colreduce_kernel<1><<<grid, 256, 0, st>>>(vx, vx, mean, nullptr, nullptr, nullptr, 0.f, 0, ws + C, nullptr, chunk);
+  finalize_div_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws + C, var, C, 1.0 / (double)total, 0);
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
+}
+
+extern "C" int myolo_bn_apply(const myolo_view* x, const myolo_view* y, const float* mean, const float* var,
+                              const float* gamma, const float* beta, float eps, int act, myolo_stream stream) {
+  MYOLO_CHECK_ARG(view_ok(x) && view_ok(y) && same_shape(x, y) && mean && var && gamma && beta);
+  const long long total = (long long)x->n * x->h * x->w * (x->c / 4);
+  bn_apply_kernel<<<ew_blocks(total), 256, 0, as_stream(stream)>>>(to_v(x), to_v(y), mean, var, gamma, beta, eps, act);
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
+}
+
+extern "C" int myolo_bn_bwd(const myolo_view* x, const myolo_view* dy, const myolo_view* dx, const float* mean,
+                            const float* var, const float* gamma, const float* beta, float eps, int act, int train,
+                            float* dgamma, float* dbeta, double* ws, myolo_stream stream) {
+  MYOLO_CHECK_ARG(view_ok(x) && view_ok(dy) && view_ok(dx) && same_shape(x, dy) && same_shape(x, dx));
+  MYOLO_CHECK_ARG(mean && var && gamma && beta && dgamma && dbeta && ws && (x->c % 32) == 0);
+  cudaStream_t st = as_stream(stream);
+  const int C = x->c;
+  const long long total = (long long)x->n * x->h * x->w;
+  dim3 grid;
+  long long chunk;
+  reduce_grid(total, C, &grid, &chunk);
+  MYOLO_CUDA(cudaMemsetAsync(ws, 0, 2 * C * sizeof(double), st));
+  colreduce_kernel<2><<<grid, 256, 0, st>>>(to_v(x), to_v(dy), mean, var, gamma, beta, eps, act, ws, ws + C, chunk);
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, dgamma, dbeta, C);
+  bn_bwd_dx_kernel<<<ew_blocks(total * (C / 4)), 256, 0, st>>>(to_v(x), to_v(dy), to_v(dx), mean, var, gamma, beta, eps,
+                                                               act, train, ws, 1.0 / (double)total);
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
+}
+
+extern "C" int myolo_bn_moving_update(const float* value, float* biased, float* moving, int C, float momentum, int step,
+                                      int is_var, double n, float eps, myolo_stream stream) {
+  MYOLO_CHECK_ARG(value && biased && moving && C > 0 && step >= 1 && n > 0);
+  double corr = 1.0;
+  if (is_var) corr = (n / (n > 1 ? n - 1 : 1.0)) * (n / (n - (1.0 + (double)eps)));
+  double debias = 1.0;
+  {
+    double pw = 1.0;
+    for (int i = 0; i < step && pw > 1e-300; ++i) pw *= (double)momentum;
+    debias = 1.0 - pw;
+  }
+  bn_moving_update_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(value, biased, moving, C, momentum, (float)corr, (float)debias);
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
+}
+
+extern "C" int myolo_colsum(const myolo_view* x, float* out, double* ws, myolo_stream stream) {
+  MYOLO_CHECK_ARG(x && x->p && x->n > 0 && x->h > 0 && x->w > 0 && x->c > 0 && out && ws);
+  cudaStream_t st = as_stream(stream);
+  const int C = x->c;
+  const long long total = (long long)x->n * x->h * x->w;
+  MYOLO_CUDA(cudaMemsetAsync(ws, 0, C * sizeof(double), st));
+  V vx = to_v(x);
+  if ((C % 32) == 0 && (x->sn % 4) == 0 && (x->sh % 4) == 0) {
+    dim3 grid;
+    long long chunk;
+    reduce_grid(total, C, &grid, &chunk);
+    colreduce_kernel<0><<<grid, 256, 0, st>>>(vx, vx, nullptr, nullptr, nullptr, nullptr, 0.f, 0, ws, nullptr, chunk);
+  } else {
+    dim3 grid((C + 63) / 64, (unsigned)min(total, 256LL));
+    colsum_generic_kernel<<<grid, 64, 0, st>>>(vx, ws);
+  }
+  finalize_div_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, out, C, 1.0, 0);
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
+}
+
+extern "C" int myolo_view_copy(const myolo_view* src, const myolo_view* dst, int accumulate, myolo_stream stream) {
+  MYOLO_CHECK_ARG(view_ok(src) && view_ok(dst) && same_shape(src, dst));
+  const long long total = (long long)src->n * src->h * src->w * (src->c / 4);
+  view_copy_kernel<<<ew_blocks(total), 256, 0, as_stream(stream)>>>(to_v(src), to_v(dst), accumulate);
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
+}

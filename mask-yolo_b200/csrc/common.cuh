@@ -1,0 +1,68 @@
+// common.cuh -- shared helpers for libmyolo_sm100.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/myolo_b200.h"
+
+namespace myolo {
+
+void set_error(const char* fmt, ...);
+
+#define MYOLO_CHECK_ARG(cond)                                                          \
+  do {                                                                                 \
+    if (!(cond)) {                                                                     \
+      myolo::set_error("%s:%d: argument check failed: %s", __FILE__, __LINE__, #cond); \
+      return MYOLO_ERR_ARG;                                                            \
+    }                                                                                  \
+  } while (0)
+
+#define MYOLO_CHECK_LAUNCH()                                                              \
+  do {                                                                                    \
+    cudaError_t e__ = cudaGetLastError();                                                 \
+    if (e__ != cudaSuccess) {                                                             \
+      myolo::set_error("%s:%d: CUDA error: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+      return MYOLO_ERR_CUDA;                                                              \
+    }                                                                                     \
+  } while (0)
+
+#define MYOLO_CUDA(call)                                                                  \
+  do {                                                                                    \
+    cudaError_t e__ = (call);                                                             \
+    if (e__ != cudaSuccess) {                                                             \
+      myolo::set_error("%s:%d: CUDA error: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+      return MYOLO_ERR_CUDA;                                                              \
+    }                                                                                     \
+  } while (0)
+
+static inline cudaStream_t as_stream(myolo_stream s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline long long ceil_div(long long a, long long b) { return (a + b - 1) / b; }
+
+constexpr int kNumSMs = 148;  // B200
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == MYOLO_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == MYOLO_ACT_RELU6) return fminf(fmaxf(v, 0.f), 6.f);
+  return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// streaming 128-bit load that does not pollute L1 (data touched once)
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+
+}  // namespace myolo

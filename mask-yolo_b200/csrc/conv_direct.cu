@@ -1,0 +1,327 @@
+// conv_direct.cu -- HBM-bound direct convolutions: the 3->32 stem conv (K1) and the 14 depthwise
+// 3x3 layers (K2) of the truncated MobileNet backbone.  No tensor cores: 9 (or 27) MACs per
+// loaded element, so these are pure streaming kernels -- 128-bit channel-vector accesses, the
+// input halo tile staged once in shared memory, grid sized in (tile x channel-group x image).
+// Reference call sites: myolo/model.py:42-52 (conv_block) and 68-77 / 256-268
+// (keras_applications _depthwise_conv_block: ZeroPad(1,1) + DepthwiseConv2D 3x3 VALID stride s).
+#include "common.cuh"
+
+namespace myolo {
+
+// ------------------------------------------------------------------------------------------
+// depthwise 3x3 forward.  block = 256 threads = 32 pixel-slots x 8 channel-quads (32 channels).
+// tile = 8x8 outputs; input halo tile (7*S+3)^2 x 32ch staged in smem with float4 loads.
+// ------------------------------------------------------------------------------------------
+template <int S>
+__global__ void __launch_bounds__(256) dw_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                     float* __restrict__ y, int H, int W, int C, int Ho, int Wo,
+                                                     int ntx) {
+  constexpr int IT = 7 * S + 3;
+  __shared__ __align__(16) float tile[IT * IT * 32];
+  const int tid = threadIdx.x;
+  const int cq = tid & 7, pg = tid >> 3;
+  const int c0 = blockIdx.y * 32;
+  const int b = blockIdx.z;
+  const int oy0 = (blockIdx.x / ntx) * 8, ox0 = (blockIdx.x % ntx) * 8;
+  const int iy0 = oy0 * S - 1, ix0 = ox0 * S - 1;
+  const float* xb = x + (size_t)b * H * W * C + c0;
+  for (int i = tid; i < IT * IT * 8; i += 256) {
+    const int pix = i >> 3, q = i & 7;
+    const int gy = iy0 + pix / IT, gx = ix0 + pix % IT;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W)
+      v = __ldg(reinterpret_cast<const float4*>(xb + ((size_t)gy * W + gx) * C + q * 4));
+    *reinterpret_cast<float4*>(&tile[pix * 32 + q * 4]) = v;
+  }
+  float4 wr[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) wr[k] = __ldg(reinterpret_cast<const float4*>(w + (size_t)k * C + c0 + cq * 4));
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int o = pg + 32 * j;
+    const int oy = o >> 3, ox = o & 7;
+    if (oy0 + oy >= Ho || ox0 + ox >= Wo) continue;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const float4 v = *reinterpret_cast<const float4*>(&tile[((oy * S + ky) * IT + ox * S + kx) * 32 + cq * 4]);
+        const float4 ww = wr[ky * 3 + kx];
+        acc.x = fmaf(v.x, ww.x, acc.x);
+        acc.y = fmaf(v.y, ww.y, acc.y);
+        acc.z = fmaf(v.z, ww.z, acc.z);
+        acc.w = fmaf(v.w, ww.w, acc.w);
+      }
+    *reinterpret_cast<float4*>(y + (((size_t)b * Ho + oy0 + oy) * Wo + ox0 + ox) * C + c0 + cq * 4) = acc;
+  }
+}
+
+// depthwise backward w.r.t. input: gather form, one thread = one input pixel x 4 channels.
+template <int S>
+__global__ void __launch_bounds__(256) dw_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                                          float* __restrict__ dx, int B, int H, int W, int C, int Ho,
+                                                          int Wo) {
+  const int C4 = C >> 2;
+  const long long total = (long long)B * H * W * C4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % C4);
+    long long p = i / C4;
+    const int ix = (int)(p % W);
+    p /= W;
+    const int iy = (int)(p % H);
+    const int b = (int)(p / H);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int ty = iy + 1 - ky;
+      if (ty < 0 || (ty % S) != 0) continue;
+      const int oy = ty / S;
+      if (oy >= Ho) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int tx = ix + 1 - kx;
+        if (tx < 0 || (tx % S) != 0) continue;
+        const int ox = tx / S;
+        if (ox >= Wo) continue;
+        const float4 g = __ldg(reinterpret_cast<const float4*>(dy + (((size_t)b * Ho + oy) * Wo + ox) * C + q * 4));
+        const float4 ww = __ldg(reinterpret_cast<const float4*>(w + (size_t)(ky * 3 + kx) * C + q * 4));
+        acc.x = fmaf(g.x, ww.x, acc.x);
+        acc.y = fmaf(g.y, ww.y, acc.y);
+        acc.z = fmaf(g.z, ww.z, acc.z);
+        acc.w = fmaf(g.w, ww.w, acc.w);
+      }
+    }
+    *reinterpret_cast<float4*>(dx + (((size_t)b * H + iy) * W + ix) * C + q * 4) = acc;
+  }
+}
+
+// depthwise backward w.r.t. filter: per-block register accumulation over a pixel chunk, smem
+// reduction across the 32 pixel slots, one atomicAdd per (tap, channel) per block.
+template <int S>
+__global__ void __launch_bounds__(256) dw_bwd_filter_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                            float* __restrict__ dw, int B, int H, int W, int C, int Ho,
+                                                            int Wo, long long chunk) {
+  __shared__ float red[9 * 32 * 33];
+  const int tid = threadIdx.x;
+  const int cq = tid & 7, pg = tid >> 3;
+  const int c0 = blockIdx.y * 32 + cq * 4;
+  const long long total = (long long)B * Ho * Wo;
+  const long long p0 = blockIdx.x * chunk;
+  const long long p1 = min(total, p0 + chunk);
+  float4 acc[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long p = p0 + pg; p < p1; p += 32) {
+    const int ox = (int)(p % Wo);
+    const long long t = p / Wo;
+    const int oy = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    const float4 g = __ldg(reinterpret_cast<const float4*>(dy + (size_t)p * C + c0));
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = oy * S + ky - 1;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = ox * S + kx - 1;
+        if (ix < 0 || ix >= W) continue;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + (((size_t)b * H + iy) * W + ix) * C + c0));
+        float4& a = acc[ky * 3 + kx];
+        a.x = fmaf(v.x, g.x, a.x);
+        a.y = fmaf(v.y, g.y, a.y);
+        a.z = fmaf(v.z, g.z, a.z);
+        a.w = fmaf(v.w, g.w, a.w);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    float* r = &red[(k * 32 + cq * 4) * 33 + pg];
+    r[0] = acc[k].x;
+    r[33] = acc[k].y;
+    r[66] = acc[k].z;
+    r[99] = acc[k].w;
+  }
+  __syncthreads();
+  for (int i = tid; i < 9 * 32; i += 256) {
+    const float* r = &red[i * 33];
+    float s = 0.f;
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) s += r[j];
+    const int k = i / 32, c = i % 32;
+    atomicAdd(dw + (size_t)k * C + blockIdx.y * 32 + c, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// stem conv 3x3 s2 pad 1, Cin=3 -> Cout (K=27: too thin for MMA, HBM/L1 bound direct conv).
+// thread = one output pixel x 8 output channels; 864-float filter in smem.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        float* __restrict__ y, int B, int S, int Cout) {
+  extern __shared__ __align__(16) float ws[];  // [27][Cout]
+  for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) ws[i] = w[i];
+  __syncthreads();
+  const int So = S / 2;
+  const int octs = Cout >> 3;
+  const long long total = (long long)B * So * So * octs;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int o8 = (int)(i % octs);
+    long long p = i / octs;
+    const int ox = (int)(p % So);
+    p /= So;
+    const int oy = (int)(p % So);
+    const int b = (int)(p / So);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = oy * 2 + ky - 1;
+      if (iy < 0 || iy >= S) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = ox * 2 + kx - 1;
+        if (ix < 0 || ix >= S) continue;
+        const float* px = x + (((size_t)b * S + iy) * S + ix) * 3;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) {
+          const float v = __ldg(px + ci);
+          const float* wp = ws + ((ky * 3 + kx) * 3 + ci) * Cout + o8 * 8;
+          const float4 w0 = *reinterpret_cast<const float4*>(wp);
+          const float4 w1 = *reinterpret_cast<const float4*>(wp + 4);
+          acc[0] = fmaf(v, w0.x, acc[0]);
+          acc[1] = fmaf(v, w0.y, acc[1]);
+          acc[2] = fmaf(v, w0.z, acc[2]);
+          acc[3] = fmaf(v, w0.w, acc[3]);
+          acc[4] = fmaf(v, w1.x, acc[4]);
+          acc[5] = fmaf(v, w1.y, acc[5]);
+          acc[6] = fmaf(v, w1.z, acc[6]);
+          acc[7] = fmaf(v, w1.w, acc[7]);
+        }
+      }
+    }
+    float* py = y + (((size_t)b * So + oy) * So + ox) * Cout + o8 * 8;
+    *reinterpret_cast<float4*>(py) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    *reinterpret_cast<float4*>(py + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+}
+
+// stem conv wgrad (Cout == 32): lane = output channel, warp = pixel slot; the 27 input taps of a
+// pixel are warp-uniform broadcast loads.
+__global__ void __launch_bounds__(256) conv1_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                          float* __restrict__ dw, int B, int S, long long chunk) {
+  __shared__ float red[8 * 27 * 32];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const int So = S / 2;
+  const long long total = (long long)B * So * So;
+  const long long p0 = blockIdx.x * chunk, p1 = min(total, p0 + chunk);
+  float acc[27];
+#pragma unroll
+  for (int i = 0; i < 27; ++i) acc[i] = 0.f;
+  for (long long p = p0 + wp; p < p1; p += 8) {
+    const int ox = (int)(p % So);
+    const long long t = p / So;
+    const int oy = (int)(t % So);
+    const int b = (int)(t / So);
+    const float g = __ldg(dy + (size_t)p * 32 + lane);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = oy * 2 + ky - 1;
+      if (iy < 0 || iy >= S) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = ox * 2 + kx - 1;
+        if (ix < 0 || ix >= S) continue;
+        const float* px = x + (((size_t)b * S + iy) * S + ix) * 3;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) acc[(ky * 3 + kx) * 3 + ci] = fmaf(__ldg(px + ci), g, acc[(ky * 3 + kx) * 3 + ci]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 27; ++i) red[(wp * 27 + i) * 32 + lane] = acc[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < 27 * 32; i += 256) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += red[j * 27 * 32 + i];
+    atomicAdd(dw + i, s);
+  }
+}
+
+}  // namespace myolo
+
+using namespace myolo;
+
+extern "C" int myolo_conv1_fwd(const float* x, const float* w, float* y, int B, int S, int Cout, myolo_stream stream) {
+  MYOLO_CHECK_ARG(x && w && y && B > 0 && S > 0 && (S % 2) == 0 && Cout > 0 && (Cout % 8) == 0 && Cout <= 128);
+  const long long total = (long long)B * (S / 2) * (S / 2) * (Cout / 8);
+  const int blocks = (int)min(ceil_div(total, 256), (long long)kNumSMs * 16);
+  conv1_fwd_kernel<<<blocks, 256, 27 * Cout * sizeof(float), as_stream(stream)>>>(x, w, y, B, S, Cout);
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
+}
+
+extern "C" int myolo_conv1_wgrad(const float* x, const float* dy, float* dw, int B, int S, int Cout, myolo_stream stream) {
+  MYOLO_CHECK_ARG(x && dy && dw && B > 0 && S > 0 && (S % 2) == 0);
+  MYOLO_CHECK_ARG(Cout == 32);
+  const long long total = (long long)B * (S / 2) * (S / 2);
+  const int blocks = (int)min(ceil_div(total, 64), (long long)kNumSMs * 4);
+  const long long chunk = ceil_div(total, blocks);
+  MYOLO_CUDA(cudaMemsetAsync(dw, 0, 27 * 32 * sizeof(float), as_stream(stream)));
+  conv1_wgrad_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x, dy, dw, B, S, chunk);
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
+}
+
+static inline int dw_out(int n, int s) { return (n + 2 - 3) / s + 1; }
+
+extern "C" int myolo_dwconv3x3_fwd(const float* x, const float* w, float* y, int B, int H, int W, int C, int stride,
+                                   myolo_stream stream) {
+  MYOLO_CHECK_ARG(x && w && y && B > 0 && H > 0 && W > 0 && C > 0 && (C % 32) == 0 && (stride == 1 || stride == 2));
+  const int Ho = dw_out(H, stride), Wo = dw_out(W, stride);
+  const int ntx = (Wo + 7) / 8, nty = (Ho + 7) / 8;
+  dim3 grid(ntx * nty, C / 32, B);
+  if (stride == 1)
+    dw_fwd_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(x, w, y, H, W, C, Ho, Wo, ntx);
+  else
+    dw_fwd_kernel<2><<<grid, 256, 0, as_stream(stream)>>>(x, w, y, H, W, C, Ho, Wo, ntx);
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
+}
+
+extern "C" int myolo_dwconv3x3_bwd_data(const float* dy, const float* w, float* dx, int B, int H, int W, int C,
+                                        int stride, myolo_stream stream) {
+  MYOLO_CHECK_ARG(dy && w && dx && B > 0 && H > 0 && W > 0 && C > 0 && (C % 4) == 0 && (stride == 1 || stride == 2));
+  const int Ho = dw_out(H, stride), Wo = dw_out(W, stride);
+  const long long total = (long long)B * H * W * (C / 4);
+  const int blocks = (int)min(ceil_div(total, 256), (long long)kNumSMs * 32);
+  if (stride == 1)
+    dw_bwd_data_kernel<1><<<blocks, 256, 0, as_stream(stream)>>>(dy, w, dx, B, H, W, C, Ho, Wo);
+  else
+    dw_bwd_data_kernel<2><<<blocks, 256, 0, as_stream(stream)>>>(dy, w, dx, B, H, W, C, Ho, Wo);
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
+}
+
+extern "C" int myolo_dwconv3x3_bwd_filter(const float* x, const float* dy, float* dw, int B, int H, int W, int C,
+                                          int stride, myolo_stream stream) {
+  MYOLO_CHECK_ARG(x && dy && dw && B > 0 && H > 0 && W > 0 && C > 0 && (C % 32) == 0 && (stride == 1 || stride == 2));
+  const int Ho = dw_out(H, stride), Wo = dw_out(W, stride);
+  const long long total = (long long)B * Ho * Wo;
+  const int cgroups = C / 32;
+  long long nchunks = max(1LL, min(ceil_div(total, 64), (long long)(kNumSMs * 4) / cgroups + 1));
+  const long long chunk = ceil_div(total, nchunks);
+  nchunks = ceil_div(total, chunk);
+  MYOLO_CUDA(cudaMemsetAsync(dw, 0, (size_t)9 * C * sizeof(float), as_stream(stream)));
+  dim3 grid((unsigned)nchunks, cgroups);
+  if (stride == 1)
+    dw_bwd_filter_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(x, dy, dw, B, H, W, C, Ho, Wo, chunk);
+  else
+    dw_bwd_filter_kernel<2><<<grid, 256, 0, as_stream(stream)>>>(x, dy, dw, B, H, W, C, Ho, Wo, chunk);
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
+}

@@ -1,0 +1,131 @@
+// roialign.cu -- PyramidROIAlign (K7): tf.image.crop_and_resize(feature, boxes, box_idx, (P,P),
+// bilinear, extrapolation 0) forward and its image gradient (CropAndResizeGradImage).
+// Reference: myolo/model.py:327-410 (crop at 385-387; every ROI maps to pyramid level 0, the
+// final top-k re-sort is the identity).  TF 1.x kernel semantics restated in SURVEY.md Q3.
+//
+// HBM-bound gather: one warp per (roi, output row); per sample 4 coalesced channel-vector reads
+// (C*4 bytes each, served from L2 after first touch: the whole feature map is B*F*F*C*4 bytes)
+// and one C*4-byte streaming write.  Coordinates are computed with explicitly rounded fp32 ops in
+// the reference's order so the sample positions are bit-identical to the CPU oracle.
+#include "common.cuh"
+#include "crop.cuh"
+
+namespace myolo {
+
+struct V {
+  float* p;
+  long long sn, sh;
+  int n, h, w, c;
+};
+static inline V to_v(const myolo_view* v) { return V{v->p, v->sn, v->sh, v->n, v->h, v->w, v->c}; }
+
+__global__ void __launch_bounds__(256)
+roialign_fwd_kernel(V feat, const float* __restrict__ boxes, int n_roi, int rois_per_img, int pool, V out) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int C4 = feat.c >> 2;
+  const long long items = (long long)n_roi * pool;
+  for (long long it = warp; it < items; it += nwarps) {
+    const int r = (int)(it / pool), y = (int)(it % pool);
+    const float4 bx = __ldg(reinterpret_cast<const float4*>(boxes) + r);  // consumed as (y1,x1,y2,x2)
+    const int b = r / rois_per_img;
+    const Sample sy = crop_coord(bx.x, bx.z, y, pool, feat.h);
+    const float* fb = feat.p + (size_t)b * feat.sn;
+    float* orow = out.p + (size_t)r * out.sn + (size_t)y * out.sh;
+    for (int x = 0; x < pool; ++x) {
+      const Sample sx = crop_coord(bx.y, bx.w, x, pool, feat.w);
+      float4* op = reinterpret_cast<float4*>(orow + (size_t)x * out.c);
+      if (!(sy.valid && sx.valid)) {
+        for (int q = lane; q < C4; q += 32) op[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        continue;
+      }
+      const float4* tl = reinterpret_cast<const float4*>(fb + (size_t)sy.lo * feat.sh + (size_t)sx.lo * feat.c);
+      const float4* tr = reinterpret_cast<const float4*>(fb + (size_t)sy.lo * feat.sh + (size_t)sx.hi * feat.c);
+      const float4* bl = reinterpret_cast<const float4*>(fb + (size_t)sy.hi * feat.sh + (size_t)sx.lo * feat.c);
+      const float4* br = reinterpret_cast<const float4*>(fb + (size_t)sy.hi * feat.sh + (size_t)sx.hi * feat.c);
+      for (int q = lane; q < C4; q += 32) {
+        const float4 a = __ldg(tl + q), bq = __ldg(tr + q), c = __ldg(bl + q), d = __ldg(br + q);
+        float4 o;
+        o.x = lerp_rn(lerp_rn(a.x, bq.x, sx.lerp), lerp_rn(c.x, d.x, sx.lerp), sy.lerp);
+        o.y = lerp_rn(lerp_rn(a.y, bq.y, sx.lerp), lerp_rn(c.y, d.y, sx.lerp), sy.lerp);
+        o.z = lerp_rn(lerp_rn(a.z, bq.z, sx.lerp), lerp_rn(c.z, d.z, sx.lerp), sy.lerp);
+        o.w = lerp_rn(lerp_rn(a.w, bq.w, sx.lerp), lerp_rn(c.w, d.w, sx.lerp), sy.lerp);
+        op[q] = o;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void red_add4(float* p, float4 v) {
+  atomicAdd(reinterpret_cast<float4*>(p), v);  // sm_90+: 128-bit vector reduction
+}
+
+__global__ void __launch_bounds__(256)
+roialign_bwd_kernel(V dout, const float* __restrict__ boxes, int n_roi, int rois_per_img, int pool, V dfeat) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int C4 = dfeat.c >> 2;
+  const long long items = (long long)n_roi * pool;
+  for (long long it = warp; it < items; it += nwarps) {
+    const int r = (int)(it / pool), y = (int)(it % pool);
+    const float4 bx = __ldg(reinterpret_cast<const float4*>(boxes) + r);
+    const int b = r / rois_per_img;
+    const Sample sy = crop_coord(bx.x, bx.z, y, pool, dfeat.h);
+    if (!sy.valid) continue;
+    float* fb = dfeat.p + (size_t)b * dfeat.sn;
+    const float* grow = dout.p + (size_t)r * dout.sn + (size_t)y * dout.sh;
+    for (int x = 0; x < pool; ++x) {
+      const Sample sx = crop_coord(bx.y, bx.w, x, pool, dfeat.w);
+      if (!sx.valid) continue;
+      const float4* gp = reinterpret_cast<const float4*>(grow + (size_t)x * dout.c);
+      float* tl = fb + (size_t)sy.lo * dfeat.sh + (size_t)sx.lo * dfeat.c;
+      float* tr = fb + (size_t)sy.lo * dfeat.sh + (size_t)sx.hi * dfeat.c;
+      float* bl = fb + (size_t)sy.hi * dfeat.sh + (size_t)sx.lo * dfeat.c;
+      float* br = fb + (size_t)sy.hi * dfeat.sh + (size_t)sx.hi * dfeat.c;
+      const float wt = 1.f - sy.lerp, wb = sy.lerp, wl = 1.f - sx.lerp, wr = sx.lerp;
+      for (int q = lane; q < C4; q += 32) {
+        const float4 g = gp[q];
+        const float4 dt = make_float4(wt * g.x, wt * g.y, wt * g.z, wt * g.w);
+        const float4 db = make_float4(wb * g.x, wb * g.y, wb * g.z, wb * g.w);
+        red_add4(tl + q * 4, make_float4(wl * dt.x, wl * dt.y, wl * dt.z, wl * dt.w));
+        red_add4(tr + q * 4, make_float4(wr * dt.x, wr * dt.y, wr * dt.z, wr * dt.w));
+        red_add4(bl + q * 4, make_float4(wl * db.x, wl * db.y, wl * db.z, wl * db.w));
+        red_add4(br + q * 4, make_float4(wr * db.x, wr * db.y, wr * db.z, wr * db.w));
+      }
+    }
+  }
+}
+
+static bool view_ok(const myolo_view* v) {
+  return v && v->p && v->n > 0 && v->h > 0 && v->w > 0 && v->c > 0 && (v->c % 4) == 0 && (v->sn % 4) == 0 && (v->sh % 4) == 0;
+}
+
+}  // namespace myolo
+
+using namespace myolo;
+
+extern "C" int myolo_roialign_fwd(const myolo_view* feat, const float* boxes, int n_roi, int rois_per_img, int pool,
+                                  const myolo_view* out, myolo_stream stream) {
+  MYOLO_CHECK_ARG(view_ok(feat) && view_ok(out) && boxes && n_roi > 0 && rois_per_img > 0 && pool > 0);
+  MYOLO_CHECK_ARG(out->n == n_roi && out->h == pool && out->w == pool && out->c == feat->c);
+  MYOLO_CHECK_ARG((n_roi + rois_per_img - 1) / rois_per_img <= feat->n);
+  const long long items = (long long)n_roi * pool;
+  const int blocks = (int)max(1LL, min(ceil_div(items, 8), (long long)kNumSMs * 8));
+  roialign_fwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(to_v(feat), boxes, n_roi, rois_per_img, pool, to_v(out));
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
+}
+
+extern "C" int myolo_roialign_bwd(const myolo_view* dout, const float* boxes, int n_roi, int rois_per_img, int pool,
+                                  const myolo_view* dfeat, myolo_stream stream) {
+  MYOLO_CHECK_ARG(view_ok(dfeat) && view_ok(dout) && boxes && n_roi > 0 && rois_per_img > 0 && pool > 0);
+  MYOLO_CHECK_ARG(dout->n == n_roi && dout->h == pool && dout->w == pool && dout->c == dfeat->c);
+  MYOLO_CHECK_ARG((n_roi + rois_per_img - 1) / rois_per_img <= dfeat->n);
+  const long long items = (long long)n_roi * pool;
+  const int blocks = (int)max(1LL, min(ceil_div(items, 8), (long long)kNumSMs * 8));
+  roialign_bwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(to_v(dout), boxes, n_roi, rois_per_img, pool, to_v(dfeat));
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
+}
