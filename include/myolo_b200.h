@@ -33,7 +33,9 @@ typedef struct {
   int n, h, w, c;
 } myolo_view;
 
-enum { MYOLO_ACT_NONE = 0, MYOLO_ACT_RELU = 1, MYOLO_ACT_RELU6 = 2 };
+enum { MYOLO_ACT_NONE = 0, MYOLO_ACT_RELU = 1, MYOLO_ACT_RELU6 = 2,
+       /* OR-able flag on any `act` argument: round the stored result to tf32 (operand of a tcgen05 GEMM) */
+       MYOLO_ROUND_TF32 = 0x100 };
 enum { MYOLO_OK = 0, MYOLO_ERR_ARG = -1, MYOLO_ERR_CUDA = -2, MYOLO_ERR_DEVICE = -3 };
 
 /* ---- library --------------------------------------------------------------------------- */
@@ -47,38 +49,69 @@ int myolo_conv1_fwd(const float* x, const float* w, float* y, int B, int S, int 
 int myolo_conv1_wgrad(const float* x, const float* dy, float* dw, int B, int S, int Cout, myolo_stream stream);
 
 /* ---- K2: depthwise 3x3, myolo/model.py:68-77,256-268 (ZeroPad(1,1) + DepthwiseConv VALID) ---- */
-int myolo_dwconv3x3_fwd(const float* x, const float* w, float* y, int B, int H, int W, int C, int stride, myolo_stream stream);
+/* x is a strided view (dense or padded-flat); y, dy, dx are dense NHWC. */
+int myolo_dwconv3x3_fwd(const myolo_view* x, const float* w, float* y, int stride, myolo_stream stream);
 int myolo_dwconv3x3_bwd_data(const float* dy, const float* w, float* dx, int B, int H, int W, int C, int stride, myolo_stream stream);
-int myolo_dwconv3x3_bwd_filter(const float* x, const float* dy, float* dw, int B, int H, int W, int C, int stride, myolo_stream stream);
+int myolo_dwconv3x3_bwd_filter(const myolo_view* x, const float* dy, float* dw, int stride, myolo_stream stream);
 
 /* ---- K3/K6/K8/K10: tap-GEMM family (pointwise 1x1, 3x3 SAME on padded-flat tiles, deconv) ----
- * C[m,n] = epi( sum_t sum_k A[m + shift[t], k] * Bt[t][k][n] ),  m in [0,M)
- *   A row-major, leading dim lda;  Bt = B + t*K*N row-major [K,N];  C row-major ldc.
+ * C[m,n] = epi( sum_t sum_k A[m + shift[t], k] * Bt[t][n][k] ),  m in [0,M)
+ *   A row-major [rows][K], leading dim lda;  Bt = per-tap [N][K] (K contiguous: the tensor-core
+ *   "K-major" operand form);  C row-major, leading dim ldc.
  *   epi: (+ bias[n]) -> (* scale[n] + shift_c[n]) -> act;   bias/scale may be NULL.
  *   pf_w1>0: rows are a padded-flat tiling with (W+1)=pf_w1 and block pf_blk; pad rows are NOT
  *   written (they stay zero).  accumulate!=0: C += result (no epilogue affine/act allowed).
- * Replaces tf Conv2D call sites myolo/model.py:271, 688-706, 848 and keras_applications pw convs. */
-int myolo_gemm_taps(const float* A, long long lda, const float* B, float* C, long long ldc,
+ *   Rows m+shift outside [0,M) read as zero on the tcgen05 path (TMA fill); the fp32 path reads
+ *   memory there, so padded-flat buffers carry >= W+2 zero guard rows on both sides.
+ * Precision mode (process-wide): MYOLO_PREC_FP32 = exact fp32 FFMA kernel; MYOLO_PREC_TF32 =
+ * tcgen05.mma kind::tf32 with fp32 accumulation in TMEM when the shape qualifies
+ * (K % 32 == 0, N % 32 == 0), else the fp32 kernel.
+ * Replaces tf Conv2D call sites myolo/model.py:271, 688-713, 848 and keras_applications pw convs. */
+enum { MYOLO_PREC_FP32 = 0, MYOLO_PREC_TF32 = 1 };
+int myolo_set_precision(int mode);
+int myolo_get_precision(void);
+int myolo_gemm_taps(const float* A, long long lda, const float* Bt, float* C, long long ldc,
                     long long M, int N, int K, int ntaps, const int* shifts_host,
                     const float* bias, const float* scale, const float* shift_c, int act,
                     int pf_w1, int pf_blk, int accumulate, myolo_stream stream);
 /* wgrad: dW[t][k][n] += sum_m A[m + shift[t], k] * D[m, n]   (fp32 atomics; dW pre-zeroed by caller)
- * transpose_out!=0 stores dW as [t][n][k] instead. */
+ * transpose_out!=0 stores dW as [t][n][k] instead.  TF32 mode uses tcgen05 with both operands
+ * MN-major when K % 128 == 0 and N % 32 == 0. */
 int myolo_gemm_taps_wgrad(const float* A, long long lda, const float* D, long long ldd, float* dW,
                           long long M, int N, int K, int ntaps, const int* shifts_host,
                           int transpose_out, myolo_stream stream);
-/* out[t][c][r] = in[t][r][c]  (per-tap weight transpose for dgrad / deconv) */
-int myolo_transpose_taps(const float* in, float* out, int ntaps, int rows, int cols, myolo_stream stream);
-/* pointwise / 3x3 named wrappers (SURVEY 8b names) */
-int myolo_pwconv_fwd(const float* x, const float* w, float* y, long long M, int Cin, int Cout,
+/* the two implementations, callable directly (tests, benchmarks) */
+int myolo_gemm_taps_ffma(const float* A, long long lda, const float* Bt, float* C, long long ldc,
+                         long long M, int N, int K, int ntaps, const int* shifts_host,
+                         const float* bias, const float* scale, const float* shift_c, int act,
+                         int pf_w1, int pf_blk, int accumulate, myolo_stream stream);
+int myolo_gemm_taps_tc(const float* A, long long lda, const float* Bt, float* C, long long ldc,
+                       long long M, int N, int K, int ntaps, const int* shifts_host,
+                       const float* bias, const float* scale, const float* shift_c, int act,
+                       int pf_w1, int pf_blk, int accumulate, myolo_stream stream);
+int myolo_gemm_taps_tc_supported(long long lda, long long ldc, long long M, int N, int K, int ntaps, int accumulate);
+int myolo_gemm_taps_wgrad_ffma(const float* A, long long lda, const float* D, long long ldd, float* dW,
+                               long long M, int N, int K, int ntaps, const int* shifts_host,
+                               int transpose_out, myolo_stream stream);
+int myolo_gemm_taps_wgrad_tc(const float* A, long long lda, const float* D, long long ldd, float* dW,
+                             long long M, int N, int K, int ntaps, const int* shifts_host,
+                             int transpose_out, myolo_stream stream);
+int myolo_gemm_taps_wgrad_tc_supported(long long lda, long long ldd, long long M, int N, int K, int ntaps);
+/* weight staging: out[t][c][r] = f(in[t][r][c]) when transpose!=0, else out = f(in);
+ * f rounds to tf32 (round-to-nearest) when round_tf32!=0.  in != out. */
+int myolo_prep_weights(const float* in, float* out, int ntaps, int rows, int cols, int transpose,
+                       int round_tf32, myolo_stream stream);
+/* pointwise / 3x3 named wrappers (SURVEY 8b names).  w = HWIO kernel [t][Cin][Cout]; wt = its
+ * per-tap transpose [t][Cout][Cin] (myolo_prep_weights). */
+int myolo_pwconv_fwd(const float* x, const float* wt, float* y, long long M, int Cin, int Cout,
                      const float* bias, myolo_stream stream);
-int myolo_pwconv_dgrad(const float* dy, const float* wT, float* dx, long long M, int Cin, int Cout, myolo_stream stream);
+int myolo_pwconv_dgrad(const float* dy, const float* w, float* dx, long long M, int Cin, int Cout, myolo_stream stream);
 int myolo_pwconv_wgrad(const float* x, const float* dy, float* dw, long long M, int Cin, int Cout, myolo_stream stream);
 /* 3x3 SAME conv on a padded-flat tensor: n_img tiles of H x W, rows = n_img*(H+1)*(W+1). x and y point at
  * row 0 of the tiling (guards of >= W+2 zero rows must exist on both sides of x). */
-int myolo_conv3x3_fwd(const float* x, const float* w, float* y, int n_img, int H, int W, int Cin, int Cout,
+int myolo_conv3x3_fwd(const float* x, const float* wt, float* y, int n_img, int H, int W, int Cin, int Cout,
                       const float* bias, const float* scale, const float* shift_c, int act, myolo_stream stream);
-int myolo_conv3x3_dgrad(const float* dy, const float* wT, float* dx, int n_img, int H, int W, int Cin, int Cout, myolo_stream stream);
+int myolo_conv3x3_dgrad(const float* dy, const float* w, float* dx, int n_img, int H, int W, int Cin, int Cout, myolo_stream stream);
 int myolo_conv3x3_wgrad(const float* x, const float* dy, float* dw, int n_img, int H, int W, int Cin, int Cout, myolo_stream stream);
 
 /* ---- K4/K5/K9: batch norm + activation (Keras BatchNormalization eps 1e-3) ---- */
@@ -98,14 +131,16 @@ int myolo_bn_moving_update(const float* value, float* biased, float* moving, int
                            int is_var, double n, float eps, myolo_stream stream);
 /* out[c] (=|+=) sum over pixels of x[.,c]  (bias gradients). ws = C doubles. */
 int myolo_colsum(const myolo_view* x, float* out, double* ws, myolo_stream stream);
-/* dst (=|+=) src over valid pixels (dense <-> padded-flat moves, gradient joins) */
+/* dst (=|+=) src over valid pixels (dense <-> padded-flat moves, gradient joins).
+ * accumulate bit 0: dst += src; bit 1: round the stored value to tf32. */
 int myolo_view_copy(const myolo_view* src, const myolo_view* dst, int accumulate, myolo_stream stream);
 
 /* ---- K7: PyramidROIAlign, myolo/model.py:385-387 = tf.image.crop_and_resize(feat, boxes, idx, (P,P)) ----
  * boxes[n_roi][4] are consumed as (y1,x1,y2,x2) exactly like the TF op; the reference passes
- * (x1,y1,x2,y2) and so does the host side here.  roi n samples image n / rois_per_img. */
+ * (x1,y1,x2,y2) and so does the host side here.  roi n samples image n / rois_per_img.
+ * round_tf32!=0 rounds the pooled values to tf32 (they are the A operand of mask conv1). */
 int myolo_roialign_fwd(const myolo_view* feat, const float* boxes, int n_roi, int rois_per_img, int pool,
-                       const myolo_view* out, myolo_stream stream);
+                       const myolo_view* out, int round_tf32, myolo_stream stream);
 int myolo_roialign_bwd(const myolo_view* dout, const float* boxes, int n_roi, int rois_per_img, int pool,
                        const myolo_view* dfeat, myolo_stream stream);
 

@@ -23,8 +23,9 @@ __device__ __forceinline__ size_t pix_off(const V& v, long long pix) {
 }
 
 __device__ __forceinline__ float act_grad_mask(float y, int act) {
-  if (act == MYOLO_ACT_RELU) return y > 0.f ? 1.f : 0.f;
-  if (act == MYOLO_ACT_RELU6) return (y > 0.f && y < 6.f) ? 1.f : 0.f;
+  const int a = act & 0xff;
+  if (a == MYOLO_ACT_RELU) return y > 0.f ? 1.f : 0.f;
+  if (a == MYOLO_ACT_RELU6) return (y > 0.f && y < 6.f) ? 1.f : 0.f;
   return 1.f;
 }
 
@@ -156,6 +157,10 @@ bn_bwd_dx_kernel(V x, V dy, V dx, const float* __restrict__ mean, const float* _
         o[j] = ga * rs * gg;
       }
     }
+    if (act & MYOLO_ROUND_TF32) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = round_tf32(o[j]);
+    }
     *reinterpret_cast<float4*>(dx.p + pix_off(dx, p) + q) = make_float4(o[0], o[1], o[2], o[3]);
   }
 }
@@ -179,10 +184,11 @@ __global__ void __launch_bounds__(256) view_copy_kernel(V src, V dst, int accumu
     const long long p = i / C4;
     float4 v = *reinterpret_cast<const float4*>(src.p + pix_off(src, p) + q);
     float4* d = reinterpret_cast<float4*>(dst.p + pix_off(dst, p) + q);
-    if (accumulate) {
+    if (accumulate & 1) {
       const float4 o = *d;
       v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
     }
+    if (accumulate & 2) v = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
     *d = v;
   }
 }

@@ -40,9 +40,21 @@ static inline long long ceil_div(long long a, long long b) { return (a + b - 1) 
 
 constexpr int kNumSMs = 148;  // B200
 
+// round-to-nearest fp32 -> tf32 (10-bit mantissa, low 13 bits zero).  tcgen05 kind::tf32 reads fp32
+// words and ignores the low mantissa bits, so producers of tensor-core operands round here to keep
+// the error unbiased.
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// `act` carries the activation in its low byte and MYOLO_ROUND_TF32 as a flag bit.
 __device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == MYOLO_ACT_RELU) return fmaxf(v, 0.f);
-  if (act == MYOLO_ACT_RELU6) return fminf(fmaxf(v, 0.f), 6.f);
+  const int a = act & 0xff;
+  if (a == MYOLO_ACT_RELU) v = fmaxf(v, 0.f);
+  else if (a == MYOLO_ACT_RELU6) v = fminf(fmaxf(v, 0.f), 6.f);
+  if (act & MYOLO_ROUND_TF32) v = round_tf32(v);
   return v;
 }
 

@@ -15,7 +15,7 @@ namespace myolo {
 template <int S>
 __global__ void __launch_bounds__(256) dw_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                      float* __restrict__ y, int H, int W, int C, int Ho, int Wo,
-                                                     int ntx) {
+                                                     int ntx, long long xsn, long long xsh) {
   constexpr int IT = 7 * S + 3;
   __shared__ __align__(16) float tile[IT * IT * 32];
   const int tid = threadIdx.x;
@@ -24,13 +24,13 @@ __global__ void __launch_bounds__(256) dw_fwd_kernel(const float* __restrict__ x
   const int b = blockIdx.z;
   const int oy0 = (blockIdx.x / ntx) * 8, ox0 = (blockIdx.x % ntx) * 8;
   const int iy0 = oy0 * S - 1, ix0 = ox0 * S - 1;
-  const float* xb = x + (size_t)b * H * W * C + c0;
+  const float* xb = x + (size_t)b * xsn + c0;
   for (int i = tid; i < IT * IT * 8; i += 256) {
     const int pix = i >> 3, q = i & 7;
     const int gy = iy0 + pix / IT, gx = ix0 + pix % IT;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (gy >= 0 && gy < H && gx >= 0 && gx < W)
-      v = __ldg(reinterpret_cast<const float4*>(xb + ((size_t)gy * W + gx) * C + q * 4));
+      v = __ldg(reinterpret_cast<const float4*>(xb + (size_t)gy * xsh + (size_t)gx * C + q * 4));
     *reinterpret_cast<float4*>(&tile[pix * 32 + q * 4]) = v;
   }
   float4 wr[9];
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(256) dw_bwd_data_kernel(const float* __restric
 template <int S>
 __global__ void __launch_bounds__(256) dw_bwd_filter_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                             float* __restrict__ dw, int B, int H, int W, int C, int Ho,
-                                                            int Wo, long long chunk) {
+                                                            int Wo, long long chunk, long long xsn, long long xsh) {
   __shared__ float red[9 * 32 * 33];
   const int tid = threadIdx.x;
   const int cq = tid & 7, pg = tid >> 3;
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(256) dw_bwd_filter_kernel(const float* __restr
       for (int kx = 0; kx < 3; ++kx) {
         const int ix = ox * S + kx - 1;
         if (ix < 0 || ix >= W) continue;
-        const float4 v = __ldg(reinterpret_cast<const float4*>(x + (((size_t)b * H + iy) * W + ix) * C + c0));
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + (size_t)b * xsn + (size_t)iy * xsh + (size_t)ix * C + c0));
         float4& a = acc[ky * 3 + kx];
         a.x = fmaf(v.x, g.x, a.x);
         a.y = fmaf(v.y, g.y, a.y);
@@ -279,16 +279,21 @@ extern "C" int myolo_conv1_wgrad(const float* x, const float* dy, float* dw, int
 
 static inline int dw_out(int n, int s) { return (n + 2 - 3) / s + 1; }
 
-extern "C" int myolo_dwconv3x3_fwd(const float* x, const float* w, float* y, int B, int H, int W, int C, int stride,
-                                   myolo_stream stream) {
-  MYOLO_CHECK_ARG(x && w && y && B > 0 && H > 0 && W > 0 && C > 0 && (C % 32) == 0 && (stride == 1 || stride == 2));
+static bool dw_view_ok(const myolo_view* v) {
+  return v && v->p && v->n > 0 && v->h > 0 && v->w > 0 && v->c > 0 && (v->c % 32) == 0 && (v->sn % 4) == 0 && (v->sh % 4) == 0;
+}
+
+extern "C" int myolo_dwconv3x3_fwd(const myolo_view* xv, const float* w, float* y, int stride, myolo_stream stream) {
+  MYOLO_CHECK_ARG(dw_view_ok(xv) && w && y && (stride == 1 || stride == 2));
+  const float* x = xv->p;
+  const int B = xv->n, H = xv->h, W = xv->w, C = xv->c;
   const int Ho = dw_out(H, stride), Wo = dw_out(W, stride);
   const int ntx = (Wo + 7) / 8, nty = (Ho + 7) / 8;
   dim3 grid(ntx * nty, C / 32, B);
   if (stride == 1)
-    dw_fwd_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(x, w, y, H, W, C, Ho, Wo, ntx);
+    dw_fwd_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(x, w, y, H, W, C, Ho, Wo, ntx, xv->sn, xv->sh);
   else
-    dw_fwd_kernel<2><<<grid, 256, 0, as_stream(stream)>>>(x, w, y, H, W, C, Ho, Wo, ntx);
+    dw_fwd_kernel<2><<<grid, 256, 0, as_stream(stream)>>>(x, w, y, H, W, C, Ho, Wo, ntx, xv->sn, xv->sh);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }
@@ -307,9 +312,11 @@ extern "C" int myolo_dwconv3x3_bwd_data(const float* dy, const float* w, float* 
   return MYOLO_OK;
 }
 
-extern "C" int myolo_dwconv3x3_bwd_filter(const float* x, const float* dy, float* dw, int B, int H, int W, int C,
-                                          int stride, myolo_stream stream) {
-  MYOLO_CHECK_ARG(x && dy && dw && B > 0 && H > 0 && W > 0 && C > 0 && (C % 32) == 0 && (stride == 1 || stride == 2));
+extern "C" int myolo_dwconv3x3_bwd_filter(const myolo_view* xv, const float* dy, float* dw, int stride,
+                                          myolo_stream stream) {
+  MYOLO_CHECK_ARG(dw_view_ok(xv) && dy && dw && (stride == 1 || stride == 2));
+  const float* x = xv->p;
+  const int B = xv->n, H = xv->h, W = xv->w, C = xv->c;
   const int Ho = dw_out(H, stride), Wo = dw_out(W, stride);
   const long long total = (long long)B * Ho * Wo;
   const int cgroups = C / 32;
@@ -319,9 +326,9 @@ extern "C" int myolo_dwconv3x3_bwd_filter(const float* x, const float* dy, float
   MYOLO_CUDA(cudaMemsetAsync(dw, 0, (size_t)9 * C * sizeof(float), as_stream(stream)));
   dim3 grid((unsigned)nchunks, cgroups);
   if (stride == 1)
-    dw_bwd_filter_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(x, dy, dw, B, H, W, C, Ho, Wo, chunk);
+    dw_bwd_filter_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(x, dy, dw, B, H, W, C, Ho, Wo, chunk, xv->sn, xv->sh);
   else
-    dw_bwd_filter_kernel<2><<<grid, 256, 0, as_stream(stream)>>>(x, dy, dw, B, H, W, C, Ho, Wo, chunk);
+    dw_bwd_filter_kernel<2><<<grid, 256, 0, as_stream(stream)>>>(x, dy, dw, B, H, W, C, Ho, Wo, chunk, xv->sn, xv->sh);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }

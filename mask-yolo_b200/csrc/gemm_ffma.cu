@@ -1,6 +1,6 @@
 // gemm_ffma.cu -- fp32 CUDA-core tap-GEMM family (exact-fp32 path).
 //
-//   forward / dgrad :  C[m,n] = epi( sum_t sum_k A[m + shift_t, k] * B_t[k, n] )
+//   forward / dgrad :  C[m,n] = epi( sum_t sum_k A[m + shift_t, k] * Bt[t][n][k] )
 //   wgrad           :  dW_t[k,n] += sum_m A[m + shift_t, k] * D[m, n]
 //
 // A "tap" is one (dy,dx) offset of a 3x3 SAME convolution evaluated on a padded-flat tensor
@@ -38,10 +38,10 @@ sgemm_taps_kernel(const float* __restrict__ A, long long lda, const float* __res
   const long long m0 = (long long)blockIdx.x * BM;
   const int n0 = blockIdx.y * BN;
   const bool nvec = ((N & 3) == 0);
-  // load assignments
-  const int ar = tid >> 1, akq = (tid & 1) * 4;    // A: row ar, k offset akq..akq+3
-  const int bk = tid >> 5, bnq = (tid & 31) * 4;   // B: k row bk, n offset bnq..bnq+3
+  // load assignments: A row ar / Bt row ar (output channel n0+ar), k offset akq..akq+3
+  const int ar = tid >> 1, akq = (tid & 1) * 4;
   const bool arow_ok = (m0 + ar) < M;
+  const bool brow_ok = (n0 + ar) < N;
   const int kiters = K / BK;
   const int total = ntaps * kiters;
 
@@ -57,22 +57,18 @@ sgemm_taps_kernel(const float* __restrict__ A, long long lda, const float* __res
     const int k0 = (it - t * kiters) * BK;
     ra = make_float4(0.f, 0.f, 0.f, 0.f);
     if (arow_ok) ra = __ldg(reinterpret_cast<const float4*>(A + (m0 + ar + sh.s[t]) * lda + k0 + akq));
-    const float* bp = B + ((size_t)t * K + k0 + bk) * N + n0 + bnq;
-    if (nvec && n0 + bnq + 3 < N) {
-      rb = __ldg(reinterpret_cast<const float4*>(bp));
-    } else {
-      rb.x = (n0 + bnq + 0 < N) ? __ldg(bp + 0) : 0.f;
-      rb.y = (n0 + bnq + 1 < N) ? __ldg(bp + 1) : 0.f;
-      rb.z = (n0 + bnq + 2 < N) ? __ldg(bp + 2) : 0.f;
-      rb.w = (n0 + bnq + 3 < N) ? __ldg(bp + 3) : 0.f;
-    }
+    rb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (brow_ok) rb = __ldg(reinterpret_cast<const float4*>(B + ((size_t)t * N + n0 + ar) * K + k0 + akq));
   };
   auto sstore = [&](int buf) {
     As[buf][akq + 0][ar] = ra.x;
     As[buf][akq + 1][ar] = ra.y;
     As[buf][akq + 2][ar] = ra.z;
     As[buf][akq + 3][ar] = ra.w;
-    *reinterpret_cast<float4*>(&Bs[buf][bk][bnq]) = rb;
+    Bs[buf][akq + 0][ar] = rb.x;
+    Bs[buf][akq + 1][ar] = rb.y;
+    Bs[buf][akq + 2][ar] = rb.z;
+    Bs[buf][akq + 3][ar] = rb.w;
   };
 
   gload(0);
@@ -237,23 +233,6 @@ sgemm_taps_wgrad_kernel(const float* __restrict__ A, long long lda, const float*
   }
 }
 
-__global__ void transpose_taps_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
-  __shared__ float t[32][33];
-  const float* ip = in + (size_t)blockIdx.z * rows * cols;
-  float* op = out + (size_t)blockIdx.z * rows * cols;
-  const int c = blockIdx.x * 32 + threadIdx.x;
-  for (int j = threadIdx.y; j < 32; j += 8) {
-    const int r = blockIdx.y * 32 + j;
-    t[j][threadIdx.x] = (r < rows && c < cols) ? ip[(size_t)r * cols + c] : 0.f;
-  }
-  __syncthreads();
-  const int r2 = blockIdx.y * 32 + threadIdx.x;
-  for (int j = threadIdx.y; j < 32; j += 8) {
-    const int c2 = blockIdx.x * 32 + j;
-    if (r2 < rows && c2 < cols) op[(size_t)c2 * rows + r2] = t[threadIdx.x][j];
-  }
-}
-
 }  // namespace myolo
 
 using namespace myolo;
@@ -265,7 +244,7 @@ extern "C" int myolo_gemm_taps_ffma(const float* A, long long lda, const float* 
   MYOLO_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0 && (K % BK) == 0 && (lda % 4) == 0);
   MYOLO_CHECK_ARG(ntaps >= 1 && ntaps <= 16);
   MYOLO_CHECK_ARG((scale == nullptr) == (shift_c == nullptr));
-  MYOLO_CHECK_ARG(!(accumulate && (scale || act != MYOLO_ACT_NONE)));
+  MYOLO_CHECK_ARG(!(accumulate && (scale || (act & 0xff) != MYOLO_ACT_NONE)));
   MYOLO_CHECK_ARG(pf_w1 <= 0 || pf_blk > 0);
   TapShifts sh;
   for (int t = 0; t < 16; ++t) sh.s[t] = (shifts_host && t < ntaps) ? shifts_host[t] : 0;
@@ -276,7 +255,7 @@ extern "C" int myolo_gemm_taps_ffma(const float* A, long long lda, const float* 
   return MYOLO_OK;
 }
 
-extern "C" int myolo_gemm_taps_wgrad(const float* A, long long lda, const float* D, long long ldd, float* dW,
+extern "C" int myolo_gemm_taps_wgrad_ffma(const float* A, long long lda, const float* D, long long ldd, float* dW,
                                      long long M, int N, int K, int ntaps, const int* shifts_host, int transpose_out,
                                      myolo_stream stream) {
   MYOLO_CHECK_ARG(A && D && dW && M > 0 && N > 0 && K > 0 && (K % 4) == 0 && (lda % 4) == 0);
@@ -291,14 +270,6 @@ extern "C" int myolo_gemm_taps_wgrad(const float* A, long long lda, const float*
   dim3 grid((unsigned)nsplit, (unsigned)(ntk * ntn), (unsigned)ntaps);
   sgemm_taps_wgrad_kernel<<<grid, 256, 0, as_stream(stream)>>>(A, lda, D, ldd, dW, M, N, K, sh, chunk, ntn,
                                                                transpose_out);
-  MYOLO_CHECK_LAUNCH();
-  return MYOLO_OK;
-}
-
-extern "C" int myolo_transpose_taps(const float* in, float* out, int ntaps, int rows, int cols, myolo_stream stream) {
-  MYOLO_CHECK_ARG(in && out && ntaps > 0 && rows > 0 && cols > 0);
-  dim3 grid((cols + 31) / 32, (rows + 31) / 32, ntaps), block(32, 8);
-  transpose_taps_kernel<<<grid, block, 0, as_stream(stream)>>>(in, out, rows, cols);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }

@@ -1,0 +1,592 @@
+// gemm_tcgen05.cu -- tensor-core tap-GEMM family for sm_100a: TMA -> 128B-swizzled shared memory ->
+// tcgen05.mma (kind::tf32, fp32 accumulate in TMEM) -> tcgen05.ld epilogue.
+//
+//   forward / dgrad : C[m,n] = epi( sum_t sum_k A[m + shift_t, k] * Bt[t][n][k] )        (tc_gemm_kernel)
+//   wgrad           : dW[t][k][n] += sum_m A[m + shift_t, k] * D[m, n]                   (tc_wgrad_kernel)
+//
+// These replace the Conv2D / Conv2DBackpropInput / Conv2DBackpropFilter call sites of the reference
+// graph (myolo/model.py:271, 688-713, 848 and the keras_applications pointwise convs, SURVEY K3/K6/
+// K8/K10).  A 3x3 SAME convolution on a padded-flat tensor is nine row-shifted
+// GEMMs accumulated in one TMEM tile: the shift is just the TMA row coordinate, out-of-range rows
+// are zero-filled by TMA, so there is no im2col buffer and no halo logic.
+//
+// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer
+// (one lane), warps 2..5 = epilogue (TMEM lane quarter = warp % 4).  smem ring of `stages` slots,
+// full/empty mbarriers, tcgen05.commit releases a slot when the MMAs that read it retire.
+//
+// Operand layouts in shared memory
+//   forward/dgrad: A and Bt are K-major: a TMA box of 32 fp32 (=128 B, one swizzle atom) x rows.
+//                  UMMA descriptor: SWIZZLE_128B, SBO = 1024 B (8 rows), k-step of 8 tf32 = +32 B.
+//   wgrad:         both operands are MN-major (the reduction index is the row index): boxes of
+//                  32 channels x 32 rows; LBO = 4096 B between 32-channel chunks, SBO = 1024 B
+//                  between 8-row groups, k-step of 8 rows = +1024 B.
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
+#include "common.cuh"
+
+namespace myolo {
+namespace tc {
+
+struct TapShifts {
+  int s[16];
+};
+
+constexpr int BM = 128;  // UMMA M: rows (fwd) / A-channels (wgrad) per CTA
+constexpr int BK = 32;   // fp32 per k-block = 128 bytes = one swizzle atom
+constexpr int kThreads = 192;
+constexpr long long kWatchdogCycles = 6000000000LL;  // ~3 s: turns a protocol bug into a trap, not a hang
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  long long t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (spin == 256) t0 = clock64();
+    if (spin > 256 && (spin & 255) == 0 && clock64() - t0 > kWatchdogCycles) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// arrives on `bar` once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+      "%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout): start>>4 [0,14),
+// LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
+// layout: 2 = SWIZZLE_128B (16-byte chunks), 1 = SWIZZLE_128B_BASE32B (32-byte chunks; the only
+// layout the hardware accepts for MN-major 32-bit operands).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint64_t layout = 2) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         (1ull << 46) | (layout << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10),
+// a_major bit 15, b_major bit 16 (1 = MN-major), N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ bool pf_valid(long long m, int pf_w1, int pf_blk) {
+  if (pf_w1 <= 0) return true;
+  const int r = (int)(m % pf_blk);
+  return (r / pf_w1) >= 1 && (r % pf_w1) >= 1;
+}
+
+struct Epi {
+  const float* bias;
+  const float* scale;
+  const float* shift;
+  int act, pf_w1, pf_blk, accumulate;
+};
+
+// ------------------------------------------------------------------------------------------
+// forward / dgrad kernel: one 128 x BN output tile per CTA
+// ------------------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(kThreads)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C,
+               long long ldc, long long M, int N, int K, int ntaps, TapShifts sh, Epi ep, int stages) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * 8 + 1];
+  __shared__ uint32_t tmem_slot;
+  constexpr uint32_t kABytes = BM * BK * 4, kBBytes = BN * BK * 4, kStage = kABytes + kBBytes;
+  constexpr uint32_t kCols = BN < 32 ? 32 : BN;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long m0 = (long long)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int kblocks = K / BK;
+  const int total = ntaps * kblocks;
+  const uint32_t bar0 = smem_u32(bars);
+  auto full = [&](int s) { return bar0 + 8u * s; };
+  auto empty = [&](int s) { return bar0 + 8u * (8 + s); };
+  const uint32_t tfull = bar0 + 8u * 16;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(full(s), 1);
+      mbar_init(empty(s), 1);
+    }
+    mbar_init(tfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), kCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int t = 0; t < ntaps; ++t) {
+        const int arow = (int)(m0 + sh.s[t]);
+        const int brow = t * N + n0;
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const int s = it % stages;
+          const uint32_t ph = (uint32_t)(it / stages) & 1u;
+          mbar_wait(empty(s), ph ^ 1u);
+          mbar_expect_tx(full(s), kStage);
+          const uint32_t sa = base + (uint32_t)s * kStage;
+          tma_load_2d(sa, &tmA, full(s), kb * BK, arow);
+          tma_load_2d(sa + kABytes, &tmB, full(s), kb * BK, brow);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN, 0, 0);
+      for (int it = 0; it < total; ++it) {
+        const int s = it % stages;
+        const uint32_t ph = (uint32_t)(it / stages) & 1u;
+        mbar_wait(full(s), ph);
+        tc_fence_after();
+        const uint32_t sa = base + (uint32_t)s * kStage;
+        const uint64_t da = make_desc(sa, 16, 1024);
+        const uint64_t db = make_desc(sa + kABytes, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k)
+          umma_tf32(tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it | k) != 0 ? 1u : 0u);
+        umma_commit(empty(s));
+      }
+      umma_commit(tfull);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const long long m = m0 + row;
+    const bool valid = (m < M) && pf_valid(m, ep.pf_w1, ep.pf_blk);
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+    float* crow = C + m * ldc + n0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      float v[32];
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int n = n0 + c0 + j + e;
+            float t = v[j + e];
+            if (ep.bias) t += __ldg(ep.bias + n);
+            if (ep.scale) t = fmaf(t, __ldg(ep.scale + n), __ldg(ep.shift + n));
+            o[e] = apply_act(t, ep.act);
+          }
+          float4* dst = reinterpret_cast<float4*>(crow + c0 + j);
+          float4 r = make_float4(o[0], o[1], o[2], o[3]);
+          if (ep.accumulate) {
+            const float4 old = *dst;
+            r.x += old.x; r.y += old.y; r.z += old.z; r.w += old.w;
+          }
+          *dst = r;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, kCols);
+}
+
+// ------------------------------------------------------------------------------------------
+// wgrad kernel: CTA = (row chunk, 128 A-channels x BN D-channels, tap); reduction over rows.
+// ------------------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(kThreads)
+tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmD,
+                float* __restrict__ dW, long long M, int N, int K, TapShifts sh, long long chunk, int ntn,
+                int transpose_out, int stages) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * 8 + 1];
+  __shared__ uint32_t tmem_slot;
+  constexpr int RB = 32;  // rows per stage
+  constexpr uint32_t kBox = 32 * RB * 4;  // one 32-channel x 32-row box = 4 KB
+  constexpr uint32_t kABytes = (BM / 32) * kBox, kDBytes = (BN / 32) * kBox, kStage = kABytes + kDBytes;
+  constexpr uint32_t kCols = BN < 32 ? 32 : BN;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tap = blockIdx.z;
+  const int k0 = (blockIdx.y / ntn) * BM;
+  const int n0 = (blockIdx.y % ntn) * BN;
+  const long long mbeg = (long long)blockIdx.x * chunk;
+  const long long mend = min(M, mbeg + chunk);
+  const int total = (int)((mend - mbeg + RB - 1) / RB);  // chunk is a multiple of RB; rows >= M are TMA zero fill
+  const uint32_t bar0 = smem_u32(bars);
+  auto full = [&](int s) { return bar0 + 8u * s; };
+  auto empty = [&](int s) { return bar0 + 8u * (8 + s); };
+  const uint32_t tfull = bar0 + 8u * 16;
+  if (total <= 0) return;  // uniform per CTA
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmD);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(full(s), 1);
+      mbar_init(empty(s), 1);
+    }
+    mbar_init(tfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), kCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int shift = sh.s[tap];
+      for (int it = 0; it < total; ++it) {
+        const int s = it % stages;
+        const uint32_t ph = (uint32_t)(it / stages) & 1u;
+        mbar_wait(empty(s), ph ^ 1u);
+        mbar_expect_tx(full(s), kStage);
+        const uint32_t sa = base + (uint32_t)s * kStage;
+        const int row = (int)(mbeg + (long long)it * RB);
+#pragma unroll
+        for (int j = 0; j < BM / 32; ++j) tma_load_2d(sa + j * kBox, &tmA, full(s), k0 + 32 * j, row + shift);
+#pragma unroll
+        for (int j = 0; j < BN / 32; ++j) tma_load_2d(sa + kABytes + j * kBox, &tmD, full(s), n0 + 32 * j, row);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN, 1, 1);
+      for (int it = 0; it < total; ++it) {
+        const int s = it % stages;
+        const uint32_t ph = (uint32_t)(it / stages) & 1u;
+        mbar_wait(full(s), ph);
+        tc_fence_after();
+        const uint32_t sa = base + (uint32_t)s * kStage;
+        // MN-major tf32: 128B_BASE32B atoms of 4 reduction rows x 128 B; LBO = next 32-channel box,
+        // SBO = next 4-row group (512 B); one K=8 MMA spans two atoms = 1024 B.
+        const uint64_t da = make_desc(sa, kBox, 512, 1);
+        const uint64_t db = make_desc(sa + kABytes, kBox, 512, 1);
+#pragma unroll
+        for (int k = 0; k < RB / 8; ++k)
+          umma_tf32(tmem, da + (uint64_t)(k * 64), db + (uint64_t)(k * 64), idesc, (it | k) != 0 ? 1u : 0u);
+        umma_commit(empty(s));
+      }
+      umma_commit(tfull);
+    }
+  } else {
+    const int q = warp & 3;
+    const int k = k0 + q * 32 + lane;
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+    float* W = dW + (size_t)tap * K * N;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      float v[32];
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      if (k < K) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int n = n0 + c0 + j;
+          if (transpose_out)
+            atomicAdd(W + (size_t)n * K + k, v[j]);
+          else
+            atomicAdd(W + (size_t)k * N + n, v[j]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, kCols);
+}
+
+// out[t][c][r] = f(in[t][r][c]) (transpose) or out = f(in); f = optional tf32 rounding
+__global__ void prep_weights_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols,
+                                    int transpose, int round) {
+  __shared__ float t[32][33];
+  const float* ip = in + (size_t)blockIdx.z * rows * cols;
+  float* op = out + (size_t)blockIdx.z * rows * cols;
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int r = blockIdx.y * 32 + j;
+    float v = (r < rows && c < cols) ? ip[(size_t)r * cols + c] : 0.f;
+    if (round) v = round_tf32(v);
+    if (!transpose) {
+      if (r < rows && c < cols) op[(size_t)r * cols + c] = v;
+    } else {
+      t[j][threadIdx.x] = v;
+    }
+  }
+  if (!transpose) return;
+  __syncthreads();
+  const int r2 = blockIdx.y * 32 + threadIdx.x;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int c2 = blockIdx.x * 32 + j;
+    if (r2 < rows && c2 < cols) op[(size_t)c2 * rows + r2] = t[threadIdx.x][j];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: tensor-map construction (driver entry point fetched at run time) + cache
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* p;
+  long long rows, pitch;
+  int cols, box_rows, atom32;
+  bool operator==(const MapKey& o) const {
+    return p == o.p && rows == o.rows && pitch == o.pitch && cols == o.cols && box_rows == o.box_rows &&
+           atom32 == o.atom32;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = std::hash<const void*>()(k.p);
+    h ^= std::hash<long long>()(k.rows * 1315423911LL + k.pitch) + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2);
+    h ^= std::hash<long long>()(((long long)k.cols << 20) ^ (k.box_rows << 1) ^ k.atom32) + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2);
+    return h;
+  }
+};
+
+// 2D fp32 tensor [rows][cols] with row pitch `pitch` elements; box = 32 columns x box_rows rows, 128B swizzle
+// atom32 != 0 selects the 32-byte-chunk flavour of the 128B swizzle (MN-major tf32 operands).
+static int get_map(const float* p, long long rows, int cols, long long pitch, int box_rows, CUtensorMap* out,
+                   int atom32 = 0) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key{p, rows, pitch, cols, box_rows, atom32};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return MYOLO_OK;
+    }
+  }
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return MYOLO_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)pitch * sizeof(float)};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) for [%lld x %d] pitch %lld box_rows %d", (int)r, rows, cols, pitch, box_rows);
+    return MYOLO_ERR_CUDA;
+  }
+  {
+    std::lock_guard<std::mutex> g(mu);
+    if (cache.size() > 4096) cache.clear();
+    cache[key] = m;
+  }
+  *out = m;
+  return MYOLO_OK;
+}
+
+static int pick_bn(int N) {
+  if (N % 256 == 0) return 256;
+  if (N % 128 == 0) return 128;
+  if (N % 64 == 0) return 64;
+  if (N % 32 == 0) return 32;
+  return 0;
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, float* C, long long ldc, long long M, int N, int K,
+                       int ntaps, const TapShifts& sh, const Epi& ep, cudaStream_t st) {
+  const int total = ntaps * (K / BK);
+  const int stages = total < 4 ? total : 4;
+  const size_t smem = (size_t)stages * (BM + BN) * BK * 4 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MYOLO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (BM + BN) * BK * 4 + 1024));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)ceil_div(M, BM), (unsigned)(N / BN));
+  tc_gemm_kernel<BN><<<grid, kThreads, smem, st>>>(ta, tb, C, ldc, M, N, K, ntaps, sh, ep, stages);
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
+}
+
+template <int BN>
+static int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& td, float* dW, long long M, int N, int K, int ntaps,
+                        const TapShifts& sh, int transpose_out, cudaStream_t st) {
+  const int ntk = K / BM, ntn = N / BN;
+  const long long tiles = (long long)ntk * ntn * ntaps;
+  long long nsplit = max(1LL, min(ceil_div(M, 32 * 8), (long long)kNumSMs / tiles));
+  if (nsplit < 1) nsplit = 1;
+  long long chunk = ceil_div(ceil_div(M, nsplit), 32) * 32;
+  nsplit = ceil_div(M, chunk);
+  const int stages = 4;
+  const size_t smem = (size_t)stages * (BM + BN) * BK * 4 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MYOLO_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)nsplit, (unsigned)(ntk * ntn), (unsigned)ntaps);
+  tc_wgrad_kernel<BN><<<grid, kThreads, smem, st>>>(ta, td, dW, M, N, K, sh, chunk, ntn, transpose_out, stages);
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
+}
+
+}  // namespace tc
+}  // namespace myolo
+
+using namespace myolo;
+using namespace myolo::tc;
+
+static bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+
+extern "C" int myolo_gemm_taps_tc_supported(long long lda, long long ldc, long long M, int N, int K, int ntaps,
+                                            int accumulate) {
+  (void)accumulate;
+  return M >= 1 && M < (1LL << 31) - 4096 && (K % BK) == 0 && pick_bn(N) != 0 && (lda % 4) == 0 && (ldc % 4) == 0 &&
+         ntaps >= 1 && ntaps <= 16 && (long long)ntaps * N < (1LL << 31);
+}
+
+extern "C" int myolo_gemm_taps_tc(const float* A, long long lda, const float* Bt, float* C, long long ldc, long long M,
+                                  int N, int K, int ntaps, const int* shifts_host, const float* bias,
+                                  const float* scale, const float* shift_c, int act, int pf_w1, int pf_blk,
+                                  int accumulate, myolo_stream stream) {
+  MYOLO_CHECK_ARG(A && Bt && C && aligned16(A) && aligned16(Bt) && aligned16(C));
+  MYOLO_CHECK_ARG(myolo_gemm_taps_tc_supported(lda, ldc, M, N, K, ntaps, accumulate));
+  MYOLO_CHECK_ARG((scale == nullptr) == (shift_c == nullptr));
+  MYOLO_CHECK_ARG(!(accumulate && (scale || (act & 0xff) != MYOLO_ACT_NONE)));
+  MYOLO_CHECK_ARG(pf_w1 <= 0 || pf_blk > 0);
+  TapShifts sh;
+  for (int t = 0; t < 16; ++t) sh.s[t] = (shifts_host && t < ntaps) ? shifts_host[t] : 0;
+  const int bn = pick_bn(N);
+  CUtensorMap ta, tb;
+  int rc = get_map(A, M, K, lda, BM, &ta);
+  if (rc) return rc;
+  rc = get_map(Bt, (long long)ntaps * N, K, K, bn, &tb);
+  if (rc) return rc;
+  Epi ep{bias, scale, shift_c, act, pf_w1, pf_blk, accumulate};
+  cudaStream_t st = as_stream(stream);
+  switch (bn) {
+    case 256: return launch_gemm<256>(ta, tb, C, ldc, M, N, K, ntaps, sh, ep, st);
+    case 128: return launch_gemm<128>(ta, tb, C, ldc, M, N, K, ntaps, sh, ep, st);
+    case 64: return launch_gemm<64>(ta, tb, C, ldc, M, N, K, ntaps, sh, ep, st);
+    default: return launch_gemm<32>(ta, tb, C, ldc, M, N, K, ntaps, sh, ep, st);
+  }
+}
+
+extern "C" int myolo_gemm_taps_wgrad_tc_supported(long long lda, long long ldd, long long M, int N, int K, int ntaps) {
+  return M >= 32 && M < (1LL << 31) - 4096 && (K % BM) == 0 && pick_bn(N) != 0 && (lda % 4) == 0 && (ldd % 4) == 0 &&
+         ntaps >= 1 && ntaps <= 16;
+}
+
+extern "C" int myolo_gemm_taps_wgrad_tc(const float* A, long long lda, const float* D, long long ldd, float* dW,
+                                        long long M, int N, int K, int ntaps, const int* shifts_host,
+                                        int transpose_out, myolo_stream stream) {
+  MYOLO_CHECK_ARG(A && D && dW && aligned16(A) && aligned16(D));
+  MYOLO_CHECK_ARG(myolo_gemm_taps_wgrad_tc_supported(lda, ldd, M, N, K, ntaps));
+  TapShifts sh;
+  for (int t = 0; t < 16; ++t) sh.s[t] = (shifts_host && t < ntaps) ? shifts_host[t] : 0;
+  const int bn = pick_bn(N);
+  CUtensorMap ta, td;
+  int rc = get_map(A, M, K, lda, 32, &ta, 1);
+  if (rc) return rc;
+  rc = get_map(D, M, N, ldd, 32, &td, 1);
+  if (rc) return rc;
+  cudaStream_t st = as_stream(stream);
+  switch (bn) {
+    case 256: return launch_wgrad<256>(ta, td, dW, M, N, K, ntaps, sh, transpose_out, st);
+    case 128: return launch_wgrad<128>(ta, td, dW, M, N, K, ntaps, sh, transpose_out, st);
+    case 64: return launch_wgrad<64>(ta, td, dW, M, N, K, ntaps, sh, transpose_out, st);
+    default: return launch_wgrad<32>(ta, td, dW, M, N, K, ntaps, sh, transpose_out, st);
+  }
+}
+
+extern "C" int myolo_prep_weights(const float* in, float* out, int ntaps, int rows, int cols, int transpose,
+                                  int round_tf32, myolo_stream stream) {
+  MYOLO_CHECK_ARG(in && out && in != out && ntaps > 0 && rows > 0 && cols > 0);
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32, ntaps), block(32, 8);
+  prep_weights_kernel<<<grid, block, 0, as_stream(stream)>>>(in, out, rows, cols, transpose, round_tf32);
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
+}

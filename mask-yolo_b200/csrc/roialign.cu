@@ -20,7 +20,7 @@ struct V {
 static inline V to_v(const myolo_view* v) { return V{v->p, v->sn, v->sh, v->n, v->h, v->w, v->c}; }
 
 __global__ void __launch_bounds__(256)
-roialign_fwd_kernel(V feat, const float* __restrict__ boxes, int n_roi, int rois_per_img, int pool, V out) {
+roialign_fwd_kernel(V feat, const float* __restrict__ boxes, int n_roi, int rois_per_img, int pool, V out, int rnd) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -51,6 +51,7 @@ roialign_fwd_kernel(V feat, const float* __restrict__ boxes, int n_roi, int rois
         o.y = lerp_rn(lerp_rn(a.y, bq.y, sx.lerp), lerp_rn(c.y, d.y, sx.lerp), sy.lerp);
         o.z = lerp_rn(lerp_rn(a.z, bq.z, sx.lerp), lerp_rn(c.z, d.z, sx.lerp), sy.lerp);
         o.w = lerp_rn(lerp_rn(a.w, bq.w, sx.lerp), lerp_rn(c.w, d.w, sx.lerp), sy.lerp);
+        if (rnd) o = make_float4(round_tf32(o.x), round_tf32(o.y), round_tf32(o.z), round_tf32(o.w));
         op[q] = o;
       }
     }
@@ -107,13 +108,13 @@ static bool view_ok(const myolo_view* v) {
 using namespace myolo;
 
 extern "C" int myolo_roialign_fwd(const myolo_view* feat, const float* boxes, int n_roi, int rois_per_img, int pool,
-                                  const myolo_view* out, myolo_stream stream) {
+                                  const myolo_view* out, int round_tf32, myolo_stream stream) {
   MYOLO_CHECK_ARG(view_ok(feat) && view_ok(out) && boxes && n_roi > 0 && rois_per_img > 0 && pool > 0);
   MYOLO_CHECK_ARG(out->n == n_roi && out->h == pool && out->w == pool && out->c == feat->c);
   MYOLO_CHECK_ARG((n_roi + rois_per_img - 1) / rois_per_img <= feat->n);
   const long long items = (long long)n_roi * pool;
   const int blocks = (int)max(1LL, min(ceil_div(items, 8), (long long)kNumSMs * 8));
-  roialign_fwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(to_v(feat), boxes, n_roi, rois_per_img, pool, to_v(out));
+  roialign_fwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(to_v(feat), boxes, n_roi, rois_per_img, pool, to_v(out), round_tf32);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }

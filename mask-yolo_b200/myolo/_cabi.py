@@ -1,0 +1,140 @@
+"""ctypes binding of libmyolo_sm100.so (the C ABI declared in include/myolo_b200.h).
+
+The prototypes are parsed from the header itself, so the header is the single source of truth for
+the boundary.  There is no CPU or library fallback: if the shared library is missing, or the
+device is not an sm_100-class GPU, every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PKG_ROOT = os.path.dirname(_HERE)                      # mask-yolo_b200/
+REPO_ROOT = os.path.dirname(PKG_ROOT)
+HEADER = os.path.join(REPO_ROOT, "include", "myolo_b200.h")
+LIB_PATH = os.path.join(PKG_ROOT, "lib", "libmyolo_sm100.so")
+
+ACT_NONE, ACT_RELU, ACT_RELU6 = 0, 1, 2
+ROUND_TF32 = 0x100
+PREC_FP32, PREC_TF32 = 0, 1
+
+
+class View(ctypes.Structure):
+    """myolo_view: strided NHWC view (innermost C contiguous, pixel stride = C)."""
+    _fields_ = [("p", ctypes.c_void_p), ("sn", ctypes.c_longlong), ("sh", ctypes.c_longlong),
+                ("n", ctypes.c_int), ("h", ctypes.c_int), ("w", ctypes.c_int), ("c", ctypes.c_int)]
+
+
+_CTYPE = {
+    "int": ctypes.c_int, "long long": ctypes.c_longlong, "float": ctypes.c_float, "double": ctypes.c_double,
+    "myolo_stream": ctypes.c_void_p,
+}
+
+
+def parse_header(path: str = HEADER):
+    """Returns {name: (restype, [(ctype, argname), ...])} for every prototype in the header."""
+    src = open(path).read()
+    src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"(const\s+char\s*\*|int)\s+(myolo_\w+)\s*\(([^)]*)\)\s*;", src):
+        ret, name, args = m.group(1), m.group(2), m.group(3).strip()
+        restype = ctypes.c_char_p if "char" in ret else ctypes.c_int
+        argl = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = " ".join(a.split())
+                if "*" in a:
+                    argl.append((ctypes.c_void_p, a.split("*")[-1].strip()))
+                else:
+                    typ, an = a.rsplit(" ", 1)
+                    argl.append((_CTYPE[typ.replace("const ", "").strip()], an))
+        protos[name] = (restype, argl)
+    return protos
+
+
+class MyoloError(RuntimeError):
+    pass
+
+
+_lock = threading.Lock()
+_lib = None
+_protos = None
+
+
+def lib():
+    """Loads the library once.  Raises if it has not been built (python __graft_entry__.py build)."""
+    global _lib, _protos
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise MyoloError(f"{LIB_PATH} not found: build it with `make -C {PKG_ROOT}/csrc` "
+                             "(there is no CPU fallback for the Mask-YOLO hot path)")
+        l = ctypes.CDLL(LIB_PATH)
+        _protos = parse_header()
+        for name, (restype, argl) in _protos.items():
+            fn = getattr(l, name)          # AttributeError if the header declares a missing symbol
+            fn.restype = restype
+            fn.argtypes = [t for t, _ in argl]
+        _lib = l
+    return _lib
+
+
+def _conv(x):
+    if x is None:
+        return None
+    if hasattr(x, "data_ptr"):             # torch tensor
+        if not x.is_cuda:
+            raise MyoloError("device pointer argument is a CPU tensor (no CPU path exists)")
+        if not x.is_contiguous():
+            raise MyoloError("tensor arguments must be contiguous")
+        return x.data_ptr()
+    if isinstance(x, View):
+        return ctypes.addressof(x)
+    if isinstance(x, ctypes.Array):
+        return ctypes.addressof(x)
+    return x
+
+
+def call(name: str, *args):
+    """Invoke a C-ABI entry point; tensors -> device pointers; nonzero status -> MyoloError."""
+    l = lib()
+    fn = getattr(l, name)
+    keep = args                             # keep Views / arrays alive across the call
+    rc = fn(*[_conv(a) for a in args])
+    del keep
+    if rc != 0:
+        raise MyoloError(f"{name} failed ({rc}): {l.myolo_last_error().decode()}")
+    return rc
+
+
+def view(t, n, h, w, c, sn=None, sh=None, offset=0):
+    """View over tensor `t` starting `offset` elements in; dense unless strides are given."""
+    sh = w * c if sh is None else sh
+    sn = h * sh if sn is None else sn
+    return View(t.data_ptr() + 4 * offset, sn, sh, n, h, w, c)
+
+
+def device_check(dev: int = 0):
+    call("myolo_device_check", dev)
+
+
+def set_precision(mode: int):
+    call("myolo_set_precision", mode)
+
+
+def get_precision() -> int:
+    return lib().myolo_get_precision()
+
+
+def int_array(vals):
+    return (ctypes.c_int * len(vals))(*vals)
+
+
+def float_array(vals):
+    return (ctypes.c_float * len(vals))(*vals)

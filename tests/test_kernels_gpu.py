@@ -1,0 +1,487 @@
+"""Per-kernel parity: every C-ABI entry point of libmyolo_sm100.so against the CPU oracle
+(oracle/myolo_oracle.py) on the same seeded inputs.  Index / mask-target / ROI-selection work is
+compared bit-exactly; fp32 arithmetic within the tolerance written next to each check; the
+tcgen05 (tf32-operand) kernels within 2e-3 of the output scale (tf32 has a 10-bit mantissa)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import myolo_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def C():
+    from myolo import _cabi
+    _cabi.device_check(0)
+    return _cabi
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def cuda(t):
+    return t.contiguous().cuda()
+
+
+def close(a, b, tol, what=""):
+    a = a.detach().float().cpu()
+    b = b.detach().float().cpu()
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    scale = max(b.abs().max().item(), 1e-6)
+    err = (a - b).abs().max().item() / scale
+    assert err <= tol, f"{what}: rel-to-max err {err:.3e} > {tol}"
+
+
+# ----------------------------------------------------------------------------- K2 depthwise
+@pytest.mark.parametrize("B,H,W,Cc,s", [(2, 16, 16, 32, 1), (2, 16, 16, 64, 2), (1, 13, 11, 32, 1), (3, 14, 14, 96, 2),
+                                        (2, 7, 7, 128, 1)])
+def test_dwconv(C, B, H, W, Cc, s):
+    torch.manual_seed(0)
+    x = torch.randn(B, H, W, Cc)
+    w = torch.randn(3, 3, Cc, 1)
+    xr = x.clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    y = O.depthwise3x3_nhwc(xr, wr, s)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    xd, wd, dyd = cuda(x), cuda(w.reshape(3, 3, Cc)), cuda(dy)
+    yd = torch.empty(y.shape, device="cuda")
+    C.call("myolo_dwconv3x3_fwd", C.view(xd, B, H, W, Cc), wd, yd, s, stream())
+    close(yd, y, 1e-6, "dw fwd")
+    dxd = torch.empty_like(xd)
+    C.call("myolo_dwconv3x3_bwd_data", dyd, wd, dxd, B, H, W, Cc, s, stream())
+    close(dxd, xr.grad, 1e-6, "dw bwd data")
+    dwd = torch.empty(3, 3, Cc, device="cuda")
+    C.call("myolo_dwconv3x3_bwd_filter", C.view(xd, B, H, W, Cc), dyd, dwd, s, stream())
+    close(dwd, wr.grad.reshape(3, 3, Cc), 2e-6, "dw bwd filter")
+
+
+# ----------------------------------------------------------------------------- K1 stem conv
+def test_conv1(C):
+    torch.manual_seed(1)
+    B, S = 2, 32
+    x = torch.rand(B, S, S, 3)
+    w = (torch.randn(3, 3, 3, 32) * 0.2).requires_grad_(True)
+    y = O.conv2d_nhwc(x, w, stride=2, pad=1)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    xd, wd = cuda(x), cuda(w.detach())
+    yd = torch.empty(y.shape, device="cuda")
+    C.call("myolo_conv1_fwd", xd, wd, yd, B, S, 32, stream())
+    close(yd, y, 1e-6, "conv1 fwd")
+    dwd = torch.empty(3, 3, 3, 32, device="cuda")
+    C.call("myolo_conv1_wgrad", xd, cuda(dy), dwd, B, S, 32, stream())
+    close(dwd, w.grad, 2e-6, "conv1 wgrad")
+
+
+# ----------------------------------------------------------------------------- K4 batch norm
+@pytest.mark.parametrize("act", [0, 1, 2])
+@pytest.mark.parametrize("train", [1, 0])
+def test_bn(C, act, train):
+    torch.manual_seed(2)
+    B, H, W, Cc = 3, 9, 7, 64
+    x = (torch.randn(B, H, W, Cc) * 2 + 0.5).requires_grad_(True)
+    g = (torch.rand(Cc) + 0.5).requires_grad_(True)
+    b = (torch.randn(Cc) * 0.3).requires_grad_(True)
+    mm, mv = torch.randn(Cc) * 0.1, torch.rand(Cc) + 0.5
+    if train:
+        y, mean, var, n = O.bn_train(x, g, b)
+    else:
+        y, mean, var = O.bn_infer(x, g, b, mm, mv), mm, mv
+    fa = {0: lambda t: t, 1: torch.relu, 2: O.relu6}[act]
+    ya = fa(y)
+    dy = torch.randn_like(ya)
+    ya.backward(dy)
+    xd, gd, bd = cuda(x.detach()), cuda(g.detach()), cuda(b.detach())
+    meand, vard = torch.empty(Cc, device="cuda"), torch.empty(Cc, device="cuda")
+    ws = torch.zeros(2 * Cc, dtype=torch.float64, device="cuda")
+    xv = C.view(xd, B, H, W, Cc)
+    if train:
+        C.call("myolo_bn_stats", xv, meand, vard, ws, stream())
+        close(meand, mean, 1e-6, "bn mean")
+        close(vard, var, 1e-5, "bn var")
+    else:
+        meand, vard = cuda(mm), cuda(mv)
+    yd = torch.empty_like(xd)
+    C.call("myolo_bn_apply", xv, C.view(yd, B, H, W, Cc), meand, vard, gd, bd, 1e-3, act, stream())
+    close(yd, ya, 2e-6, "bn apply")
+    dxd = torch.empty_like(xd)
+    dg, db = torch.empty(Cc, device="cuda"), torch.empty(Cc, device="cuda")
+    dyd = cuda(dy)
+    C.call("myolo_bn_bwd", xv, C.view(dyd, B, H, W, Cc), C.view(dxd, B, H, W, Cc), meand, vard, gd, bd, 1e-3, act, train,
+           dg, db, ws, stream())
+    close(dxd, x.grad, 2e-5, "bn dx")
+    close(dg, g.grad, 2e-5, "bn dgamma")
+    close(db, b.grad, 2e-5, "bn dbeta")
+
+
+def test_bn_moving_update_and_colsum(C):
+    torch.manual_seed(3)
+    Cc, n = 32, 5 * 7 * 7
+    val = torch.rand(Cc) + 0.1
+    biased = torch.zeros(Cc)
+    bd, md = cuda(biased), torch.empty(Cc, device="cuda")
+    exp_b = biased.clone()
+    for step in (1, 2, 3):
+        C.call("myolo_bn_moving_update", cuda(val), bd, md, Cc, 0.99, step, 1, float(n), 1e-3, stream())
+        v = O.moving_update_value(val, n)
+        exp_b = exp_b - (exp_b - v) * (1 - 0.99)
+        close(md, exp_b / (1 - 0.99 ** step), 2e-5, "moving var")
+    x = torch.randn(4, 5, 6, 64)
+    out = torch.empty(64, device="cuda")
+    ws = torch.zeros(64, dtype=torch.float64, device="cuda")
+    xd = cuda(x)
+    C.call("myolo_colsum", C.view(xd, 4, 5, 6, 64), out, ws, stream())
+    close(out, x.sum((0, 1, 2)), 1e-5, "colsum")
+    x5 = torch.randn(4, 5, 6, 20)
+    out5 = torch.empty(20, device="cuda")
+    x5d = cuda(x5)
+    C.call("myolo_colsum", C.view(x5d, 4, 5, 6, 20), out5, ws, stream())
+    close(out5, x5.sum((0, 1, 2)), 1e-5, "colsum generic")
+
+
+# ----------------------------------------------------------------------------- K7 ROIAlign
+def _boxes(n, seed):
+    g = torch.Generator().manual_seed(seed)
+    c = torch.rand(n, 2, generator=g)
+    wh = torch.rand(n, 2, generator=g) * 0.6
+    b = torch.cat([c - wh / 2, c + wh / 2], 1)        # some fall outside [0,1] -> extrapolation
+    b[0] = torch.tensor([0.0, 0.0, 0.0, 0.0])          # zero-padded roi
+    b[1] = torch.tensor([0.0, 0.0, 1.0, 1.0])
+    b[2] = torch.tensor([0.2, 0.3, 0.2, 0.9])          # degenerate
+    b[3] = torch.tensor([-0.5, 0.1, 1.5, 0.8])
+    return b
+
+
+def test_roialign(C):
+    torch.manual_seed(4)
+    B, Fh, Cc, R, P = 2, 12, 64, 9, 14
+    feat = torch.randn(B, Fh, Fh, Cc).requires_grad_(True)
+    boxes = _boxes(B * R, 5)
+    idx = torch.arange(B).repeat_interleave(R)
+    out = O.crop_and_resize(feat, boxes, idx, P, P)
+    dout = torch.randn_like(out)
+    out.backward(dout)
+    fd, bd = cuda(feat.detach()), cuda(boxes)
+    od = torch.empty(B * R, P, P, Cc, device="cuda")
+    C.call("myolo_roialign_fwd", C.view(fd, B, Fh, Fh, Cc), bd, B * R, R, P, C.view(od, B * R, P, P, Cc), 0, stream())
+    assert torch.equal(od.cpu(), out.detach()), "ROIAlign forward must be bit-exact vs the oracle"
+    dfd = torch.zeros_like(fd)
+    dod = cuda(dout)
+    C.call("myolo_roialign_bwd", C.view(dod, B * R, P, P, Cc), bd, B * R, R, P, C.view(dfd, B, Fh, Fh, Cc), stream())
+    close(dfd, feat.grad, 1e-5, "roialign bwd")
+
+
+# ----------------------------------------------------------------------------- tap-GEMM family
+def _prep(C, w, ntaps, rows, cols, transpose, rnd=0):
+    out = torch.empty(ntaps, cols if transpose else rows, rows if transpose else cols, device="cuda")
+    C.call("myolo_prep_weights", w, out, ntaps, rows, cols, transpose, rnd, stream())
+    return out
+
+
+@pytest.mark.parametrize("impl,tol", [("ffma", 2e-6), ("tc", 2e-3)])
+@pytest.mark.parametrize("M,K,N", [(300, 64, 64), (1000, 32, 128), (257, 256, 512), (64, 1024, 32), (4100, 128, 256)])
+def test_gemm_pointwise(C, impl, tol, M, K, N):
+    torch.manual_seed(6)
+    A = torch.randn(M, K)
+    W = torch.randn(K, N) / K ** 0.5
+    bias = torch.randn(N)
+    ref = torch.relu(A.double() @ W.double() + bias.double()).float()
+    Ad, Wd = cuda(A), cuda(W)
+    Wt = _prep(C, Wd, 1, K, N, 1)
+    assert torch.equal(Wt[0].cpu(), W.t().contiguous())
+    out = torch.full((M, N), 7.0, device="cuda")
+    C.call(f"myolo_gemm_taps_{impl}", Ad, K, Wt, out, N, M, N, K, 1, None, cuda(bias), None, None, C.ACT_RELU, 0, 0, 0,
+           stream())
+    close(out, ref, tol, f"pointwise {impl}")
+    # dgrad form + accumulate
+    dY = torch.randn(M, N)
+    base = torch.randn(M, K)
+    dX = cuda(base)
+    C.call(f"myolo_gemm_taps_{impl}", cuda(dY), N, Wd, dX, K, M, K, N, 1, None, None, None, None, 0, 0, 0, 1, stream())
+    close(dX, (base.double() + dY.double() @ W.double().t()).float(), tol, f"dgrad {impl}")
+
+
+@pytest.mark.parametrize("impl,tol", [("ffma", 3e-6), ("tc", 2e-3)])
+@pytest.mark.parametrize("n,H,W,Ci,Co", [(3, 14, 14, 64, 64), (2, 7, 9, 32, 128), (5, 14, 14, 256, 256)])
+def test_conv3x3_pf(C, impl, tol, n, H, W, Ci, Co):
+    from myolo.pf import PF, conv3x3_shifts
+    torch.manual_seed(7)
+    x = torch.randn(n, H, W, Ci)
+    w = (torch.randn(3, 3, Ci, Co) / (9 * Ci) ** 0.5).requires_grad_(True)
+    bias = torch.randn(Co)
+    xr = x.clone().requires_grad_(True)
+    y = O.conv2d_nhwc(xr, w, 1, 1) + bias
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    px = PF(n, H, W, Ci).load_dense(cuda(x))
+    py = PF(n, H, W, Co)
+    wd = cuda(w.detach().reshape(9, Ci, Co))
+    wt = _prep(C, wd, 9, Ci, Co, 1)
+    sh = C.int_array(conv3x3_shifts(W))
+    M = px.M
+    C.call(f"myolo_gemm_taps_{impl}", px.rows, Ci, wt, py.rows, Co, M, Co, Ci, 9, sh, cuda(bias), None, None, 0, W + 1,
+           (H + 1) * (W + 1), 0, stream())
+    close(py.dense(), y, tol, f"conv3x3 fwd {impl}")
+    full = py.rows.view(n, H + 1, W + 1, Co)
+    assert full[:, 0].abs().max().item() == 0 and full[:, :, 0].abs().max().item() == 0, "pad rows must stay zero"
+    # dgrad
+    pdy = PF(n, H, W, Co).load_dense(cuda(dy))
+    pdx = PF(n, H, W, Ci)
+    shn = C.int_array(conv3x3_shifts(W, negate=True))
+    C.call(f"myolo_gemm_taps_{impl}", pdy.rows, Co, wd, pdx.rows, Ci, M, Ci, Co, 9, shn, None, None, None, 0, W + 1,
+           (H + 1) * (W + 1), 0, stream())
+    close(pdx.dense(), xr.grad, tol, f"conv3x3 dgrad {impl}")
+    # wgrad
+    dw = torch.zeros(9, Ci, Co, device="cuda")
+    C.call(f"myolo_gemm_taps_wgrad_{impl}" if impl == "ffma" or Ci % 128 == 0 else "myolo_gemm_taps_wgrad_ffma",
+           px.rows, Ci, pdy.rows, Co, dw, M, Co, Ci, 9, sh, 0, stream())
+    close(dw, w.grad.reshape(9, Ci, Co), tol, f"conv3x3 wgrad {impl}")
+    dwt = torch.zeros(9, Co, Ci, device="cuda")
+    C.call(f"myolo_gemm_taps_wgrad_{impl}" if impl == "ffma" or Ci % 128 == 0 else "myolo_gemm_taps_wgrad_ffma",
+           px.rows, Ci, pdy.rows, Co, dwt, M, Co, Ci, 9, sh, 1, stream())
+    close(dwt, w.grad.reshape(9, Ci, Co).transpose(1, 2), tol, f"conv3x3 wgrad^T {impl}")
+
+
+def test_named_conv_wrappers(C):
+    """myolo_pwconv_* / myolo_conv3x3_* in both precision modes."""
+    from myolo.pf import PF
+    torch.manual_seed(8)
+    M, Ci, Co = 777, 128, 64
+    x, w, dy = torch.randn(M, Ci), torch.randn(Ci, Co) / Ci ** 0.5, torch.randn(M, Co)
+    for mode, tol in ((C.PREC_FP32, 3e-6), (C.PREC_TF32, 2e-3)):
+        C.set_precision(mode)
+        try:
+            wd = cuda(w)
+            wt = _prep(C, wd, 1, Ci, Co, 1)
+            y = torch.empty(M, Co, device="cuda")
+            C.call("myolo_pwconv_fwd", cuda(x), wt, y, M, Ci, Co, None, stream())
+            close(y, x @ w, tol, "pwconv fwd")
+            dx = torch.empty(M, Ci, device="cuda")
+            C.call("myolo_pwconv_dgrad", cuda(dy), wd, dx, M, Ci, Co, stream())
+            close(dx, dy @ w.t(), tol, "pwconv dgrad")
+            dw = torch.empty(Ci, Co, device="cuda")
+            C.call("myolo_pwconv_wgrad", cuda(x), cuda(dy), dw, M, Ci, Co, stream())
+            close(dw, x.t() @ dy, tol, "pwconv wgrad")
+            n, H, W = 4, 14, 14
+            xi = torch.randn(n, H, W, Ci)
+            k = torch.randn(3, 3, Ci, Co) / (9 * Ci) ** 0.5
+            px, py = PF(n, H, W, Ci).load_dense(cuda(xi)), PF(n, H, W, Co)
+            kt = _prep(C, cuda(k.reshape(9, Ci, Co)), 9, Ci, Co, 1)
+            C.call("myolo_conv3x3_fwd", px.rows, kt, py.rows, n, H, W, Ci, Co, None, None, None, 0, stream())
+            close(py.dense(), O.conv2d_nhwc(xi, k, 1, 1), tol, "conv3x3 fwd wrapper")
+        finally:
+            C.set_precision(C.PREC_FP32)
+
+
+# ----------------------------------------------------------------------------- K10/K11 mask tail
+def test_mask_out(C):
+    from myolo.pf import PF
+    torch.manual_seed(9)
+    n, H, W, Cm, NC = 3, 14, 14, 256, 4
+    a4 = torch.randn(n, H, W, Cm)
+    kd = (torch.randn(2, 2, Cm, Cm) / Cm ** 0.5).requires_grad_(True)       # [a,b,co,ci]
+    bd = (torch.randn(Cm) * 0.1).requires_grad_(True)
+    w1 = (torch.randn(Cm, NC) / Cm ** 0.5).requires_grad_(True)
+    b1 = (torch.randn(NC) * 0.1).requires_grad_(True)
+    a4r = a4.clone().requires_grad_(True)
+    y = F.conv_transpose2d(a4r.permute(0, 3, 1, 2), kd.permute(3, 2, 0, 1), stride=2).permute(0, 2, 3, 1)
+    h = torch.relu(y + bd)
+    logit = h @ w1 + b1
+    masks = torch.sigmoid(logit)
+    dlogit = torch.zeros_like(logit)
+    dlogit[0, :, :, 2] = torch.randn(2 * H, 2 * W)
+    dlogit[2, :, :, 1] = torch.randn(2 * H, 2 * W)
+    logit.backward(dlogit)
+    pa = PF(n, H, W, Cm).load_dense(cuda(a4))
+    y4 = PF(n, H, W, 4 * Cm)
+    kdd = cuda(kd.detach().reshape(4 * Cm, Cm))
+    C.call("myolo_gemm_taps_ffma", pa.rows, Cm, kdd, y4.rows, 4 * Cm, pa.M, 4 * Cm, Cm, 1, None, None, None, None, 0,
+           W + 1, (H + 1) * (W + 1), 0, stream())
+    md = torch.empty(n, 2 * H, 2 * W, NC, device="cuda")
+    C.call("myolo_mask_out_fwd", y4.rows, cuda(bd.detach()), cuda(w1.detach()), cuda(b1.detach()), md, n, H, W, Cm, NC, stream())
+    close(md, masks, 5e-6, "mask_out fwd")
+    dy4 = PF(n, H, W, 4 * Cm)
+    dw1, db1, dbd = torch.zeros(Cm, NC, device="cuda"), torch.zeros(NC, device="cuda"), torch.zeros(Cm, device="cuda")
+    C.call("myolo_mask_out_bwd", y4.rows, cuda(bd.detach()), cuda(w1.detach()), cuda(dlogit), dy4.rows, dw1, db1, dbd,
+           n, H, W, Cm, NC, stream())
+    close(dw1, w1.grad, 2e-5, "dw1")
+    close(db1, b1.grad, 2e-5, "db1")
+    close(dbd, bd.grad, 2e-5, "dbd")
+    # dy4 -> da4 (dgrad GEMM, Bt = Kd^T per (a,b,co) -> [ci][(a,b,co)]) and dKd (wgrad, transposed output)
+    kdt = _prep(C, kdd, 1, 4 * Cm, Cm, 1)                                   # [Cm][4Cm]
+    da = PF(n, H, W, Cm)
+    C.call("myolo_gemm_taps_ffma", dy4.rows, 4 * Cm, kdt, da.rows, Cm, pa.M, Cm, 4 * Cm, 1, None, None, None, None, 0,
+           W + 1, (H + 1) * (W + 1), 0, stream())
+    close(da.dense(), a4r.grad, 2e-5, "deconv dgrad")
+    dkd = torch.zeros(4 * Cm, Cm, device="cuda")
+    C.call("myolo_gemm_taps_wgrad_ffma", pa.rows, Cm, dy4.rows, 4 * Cm, dkd, pa.M, 4 * Cm, Cm, 1, None, 1, stream())
+    close(dkd, kd.grad.reshape(4 * Cm, Cm), 2e-5, "deconv wgrad")
+
+
+# ----------------------------------------------------------------------------- K12 decode
+CFG = dict(GRID_H=7, GRID_W=7, N_BOX=3, NUM_CLASSES=4, ANCHORS=[0.6, 0.9, 1.5, 1.4, 2.5, 2.8], TRAIN_ROIS_PER_IMAGE=147,
+           MASK_SHAPE=[28, 28], MASK_POOL_SIZE=14, COORD_SCALE=1.0, NO_OBJECT_SCALE=1.0, OBJECT_SCALE=5.0,
+           CLASS_SCALE=1.0, CLASS_WEIGHTS=np.ones(4, dtype="float32"), WARM_UP_BATCHES=0, TRUE_BOX_BUFFER=15)
+
+
+def test_yolo_decode(C):
+    torch.manual_seed(10)
+    B = 3
+    yp = torch.randn(B, 7, 7, 3, 9)
+    boxes = O.decode_yolo(yp, CFG)
+    det = O.detections_layer(yp, CFG)
+    bd, dd = torch.empty(B, 147, 4, device="cuda"), torch.empty(B, 147, 6, device="cuda")
+    C.call("myolo_yolo_decode", cuda(yp), cuda(torch.tensor(CFG["ANCHORS"])), bd, dd, B, 7, 7, 3, 4, stream())
+    close(bd, boxes, 2e-6, "decode boxes")
+    close(dd[..., :5], det[..., :5], 2e-6, "detections")
+    assert torch.equal(dd[..., 5].cpu(), det[..., 5])
+
+
+# ----------------------------------------------------------------------------- K13 targets
+def _shapes_batch(B, S, M, seed):
+    """Synthetic GT: axis-aligned rectangles / discs with pixel boxes (x1,y1,x2,y2), x2/y2 exclusive."""
+    rng = np.random.RandomState(seed)
+    ids = np.zeros((B, M), np.int32)
+    boxes = np.zeros((B, M, 4), np.float32)
+    masks = np.zeros((B, S, S, M), np.uint8)
+    yy, xx = np.mgrid[0:S, 0:S]
+    for b in range(B):
+        for m in range(rng.randint(1, 4)):
+            cx, cy = rng.randint(20, S - 20, 2)
+            r = rng.randint(8, S // 4)
+            if rng.rand() < 0.5:
+                mk = (np.abs(xx - cx) <= r) & (np.abs(yy - cy) <= r)
+            else:
+                mk = (xx - cx) ** 2 + (yy - cy) ** 2 <= r * r
+            masks[b, :, :, m] = mk
+            ys, xs = np.where(mk)
+            boxes[b, m] = [xs.min(), ys.min(), xs.max() + 1, ys.max() + 1]
+            ids[b, m] = rng.randint(1, 4)
+    return ids, boxes, masks
+
+
+def _proposals_near(boxes_px, S, R, seed):
+    rng = np.random.RandomState(seed)
+    B = boxes_px.shape[0]
+    props = rng.rand(B, R, 4).astype(np.float32)
+    props[..., 2:] = props[..., :2] + rng.rand(B, R, 2).astype(np.float32) * 0.5
+    for b in range(B):
+        for j in range(0, R, 3):                       # every third proposal is a jittered GT box
+            g = boxes_px[b, rng.randint(0, 3)]
+            if g[2] <= g[0]:
+                continue
+            props[b, j] = g / S + rng.randn(4).astype(np.float32) * 0.02
+    props[0, 5] = np.nan                               # NaN proposal -> neither pos nor neg
+    return props
+
+
+def test_detect_mask_targets_bit_exact(C):
+    B, S, M, R = 4, 128, 10, 48
+    ids, boxes, masks = _shapes_batch(B, S, M, 11)
+    props = _proposals_near(boxes, S, R, 12)
+    cfg = dict(CFG, TRAIN_ROIS_PER_IMAGE=R)
+    gtb = O.norm_boxes_graph(torch.tensor(boxes), S, S)
+    rois, tids, tm = O.detect_mask_targets(torch.tensor(props), torch.tensor(ids), gtb, torch.tensor(masks).bool(), cfg)
+    rd = torch.empty(B, R, 4, device="cuda")
+    td = torch.empty(B, R, dtype=torch.int32, device="cuda")
+    md = torch.empty(B, R, 28, 28, device="cuda")
+    npos = torch.empty(B, dtype=torch.int32, device="cuda")
+    src = torch.empty(B, R, dtype=torch.int32, device="cuda")
+    rgt = torch.empty(B, R, dtype=torch.int32, device="cuda")
+    C.call("myolo_detect_mask_targets", cuda(torch.tensor(props)), cuda(torch.tensor(ids)), cuda(torch.tensor(boxes)),
+           cuda(torch.tensor(masks)), B, R, M, S, 28, 28, rd, td, md, npos, src, rgt, stream())
+    assert (tids > 0).sum() > 10, "test should exercise positives"
+    assert torch.equal(td.cpu(), tids), "target class ids must be bit-exact"
+    assert torch.equal(rd.cpu().view(torch.int32), rois.view(torch.int32)), "roi selection/order must be bit-exact"
+    assert torch.equal(md.cpu(), tm), "mask targets must be bit-exact"
+    assert torch.equal(npos.cpu().long(), (tids > 0).sum(1))
+
+
+# ----------------------------------------------------------------------------- K15 / K16 losses
+def _yolo_inputs(B, seed):
+    rng = np.random.RandomState(seed)
+    G, NB, NC, TB = 7, 3, 4, 15
+    yt = np.zeros((B, G, G, NB, 5 + NC), np.float32)
+    tb = np.zeros((B, 1, 1, 1, TB, 4), np.float32)
+    for b in range(B):
+        for k in range(rng.randint(1, 4)):
+            cx, cy = rng.rand(2) * G
+            w, h = rng.rand(2) * 3 + 0.3
+            a = rng.randint(NB)
+            yt[b, int(cy), int(cx), a, :5] = [cx, cy, w, h, 1]
+            yt[b, int(cy), int(cx), a, 5 + rng.randint(1, NC)] = 1
+            tb[b, 0, 0, 0, k] = [cx, cy, w, h]
+    yp = rng.randn(B, G, G, NB, 5 + NC).astype(np.float32)
+    return torch.tensor(yt), torch.tensor(yp), torch.tensor(tb)
+
+
+@pytest.mark.parametrize("warm", [0, 1])
+def test_yolo_loss(C, warm):
+    B = 4
+    yt, yp, tb = _yolo_inputs(B, 13)
+    cfg = dict(CFG, WARM_UP_BATCHES=10 if warm else 0)
+    ypr = yp.clone().requires_grad_(True)
+    loss = O.yolo_custom_loss(yt, ypr, tb, cfg, seen=1.0)
+    loss.backward()
+    lo = torch.empty(5, device="cuda")
+    dyp = torch.empty_like(yp, device="cuda")
+    ws = torch.zeros(8, dtype=torch.float64, device="cuda")
+    sc = C.float_array([cfg["OBJECT_SCALE"], cfg["NO_OBJECT_SCALE"], cfg["COORD_SCALE"], cfg["CLASS_SCALE"]])
+    C.call("myolo_yolo_loss", cuda(yt), cuda(yp), cuda(tb.reshape(B, 15, 4)), cuda(torch.tensor(cfg["ANCHORS"])),
+           cuda(torch.tensor(cfg["CLASS_WEIGHTS"])), B, 7, 7, 3, 4, 15, sc, warm, 1.0, lo, dyp, ws, stream())
+    assert abs(lo[0].item() - loss.item()) <= 1e-5 * max(1.0, abs(loss.item())), (lo[0].item(), loss.item())
+    close(dyp, ypr.grad, 2e-5, "yolo loss grad")
+
+
+def test_mask_loss(C):
+    torch.manual_seed(14)
+    n, NC = 12, 4
+    logits = torch.randn(n, 28, 28, NC) * 3
+    logits[0, 0, 0, :] = 40.0                          # saturated -> clip region
+    lr = logits.clone().requires_grad_(True)
+    masks = torch.sigmoid(lr)
+    tm = (torch.rand(n, 28, 28) > 0.5).float()
+    ids = torch.tensor([2, 0, 1, 0, 3, 0, 0, 1, 0, 0, 2, 0], dtype=torch.int32)
+    loss = O.myolo_mask_loss_graph(tm[None], ids[None], masks[None])
+    loss.backward()
+    lo = torch.empty(1, device="cuda")
+    dl = torch.empty(n, 28, 28, NC, device="cuda")
+    ws = torch.zeros(2, dtype=torch.float64, device="cuda")
+    C.call("myolo_mask_loss", cuda(masks.detach()), cuda(tm), cuda(ids), n, 28, 28, NC, 1.0, lo, dl, ws, stream())
+    assert abs(lo.item() - loss.item()) <= 2e-6 * max(1.0, loss.item())
+    close(dl, lr.grad, 5e-5, "mask loss dlogit")
+    ids0 = torch.zeros(n, dtype=torch.int32)
+    C.call("myolo_mask_loss", cuda(masks.detach()), cuda(tm), cuda(ids0), n, 28, 28, NC, 1.0, lo, dl, ws, stream())
+    assert lo.item() == 0.0 and dl.abs().max().item() == 0.0
+
+
+# ----------------------------------------------------------------------------- K17 Adam
+def test_adam(C):
+    torch.manual_seed(15)
+    n = 1003
+    p, g = torch.randn(n), torch.randn(n)
+    m, v = torch.zeros(n), torch.zeros(n)
+    pd, md, vd = cuda(p), cuda(m), cuda(v)
+    for t in (1, 2, 3):
+        lr_t = 1e-3 * (1 - 0.999 ** t) ** 0.5 / (1 - 0.9 ** t)
+        m = 0.9 * m + 0.1 * g
+        v = 0.999 * v + 0.001 * g * g
+        p = p - lr_t * m / (v.sqrt() + 1e-8)
+        C.call("myolo_adam_step", pd, cuda(g), md, vd, n, lr_t, 0.9, 0.999, 1e-8, 1.0, stream())
+    close(pd, p, 1e-6, "adam")
+
+
+def test_error_paths(C):
+    """Reference-style error behaviour: bad arguments raise, the message names the failed check."""
+    x = torch.zeros(1, 4, 4, 30, device="cuda")
+    with pytest.raises(C.MyoloError, match="argument check failed"):
+        C.call("myolo_dwconv3x3_fwd", C.view(x, 1, 4, 4, 30), x, x, 1, stream())
+    with pytest.raises(C.MyoloError):
+        C.call("myolo_conv1_fwd", torch.zeros(4), x, x, 1, 4, 32, stream())   # CPU tensor: no CPU path
