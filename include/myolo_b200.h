@@ -61,8 +61,9 @@ int myolo_dwconv3x3_bwd_filter(const myolo_view* x, const float* dy, float* dw, 
  *   epi: (+ bias[n]) -> (* scale[n] + shift_c[n]) -> act;   bias/scale may be NULL.
  *   pf_w1>0: rows are a padded-flat tiling with (W+1)=pf_w1 and block pf_blk; pad rows are NOT
  *   written (they stay zero).  accumulate!=0: C += result (no epilogue affine/act allowed).
- *   Rows m+shift outside [0,M) read as zero on the tcgen05 path (TMA fill); the fp32 path reads
- *   memory there, so padded-flat buffers carry >= W+2 zero guard rows on both sides.
+ *   Rows m+shift < 0 read as zero on the tcgen05 path (TMA fill); rows past M are read from memory
+ *   on both paths (and below 0 on the fp32 path), so padded-flat buffers carry >= W+2 zero guard
+ *   rows on both sides.  ntaps <= 32.
  * Precision mode (process-wide): MYOLO_PREC_FP32 = exact fp32 FFMA kernel; MYOLO_PREC_TF32 =
  * tcgen05.mma kind::tf32 with fp32 accumulation in TMEM when the shape qualifies
  * (K % 32 == 0, N % 32 == 0), else the fp32 kernel.
@@ -98,7 +99,9 @@ int myolo_gemm_taps_wgrad_tc(const float* A, long long lda, const float* D, long
                              int transpose_out, myolo_stream stream);
 int myolo_gemm_taps_wgrad_tc_supported(long long lda, long long ldd, long long M, int N, int K, int ntaps);
 /* weight staging: out[t][c][r] = f(in[t][r][c]) when transpose!=0, else out = f(in);
- * f rounds to tf32 (round-to-nearest) when round_tf32!=0.  in != out. */
+ * f rounds to tf32 (round-to-nearest) when round_tf32==1.  round_tf32==2 writes THREE stacked copies
+ * [hi | hi | lo] (hi = rna_tf32(v), lo = rna_tf32(v-hi)), each ntaps*rows*cols floats: the B operands of
+ * the 3xTF32 tap triple (A_hi,B_hi), (A_lo,B_hi), (A_hi,B_lo).  in != out. */
 int myolo_prep_weights(const float* in, float* out, int ntaps, int rows, int cols, int transpose,
                        int round_tf32, myolo_stream stream);
 /* pointwise / 3x3 named wrappers (SURVEY 8b names).  w = HWIO kernel [t][Cin][Cout]; wt = its
@@ -120,6 +123,13 @@ int myolo_bn_stats(const myolo_view* x, float* mean, float* var, double* ws, myo
 /* y = act(gamma*(x-mean)*rsqrt(var+eps)+beta) */
 int myolo_bn_apply(const myolo_view* x, const myolo_view* y, const float* mean, const float* var,
                    const float* gamma, const float* beta, float eps, int act, myolo_stream stream);
+/* same, but the result v is stored as the operand pair of a 3xTF32 GEMM: y_hi = rna_tf32(v),
+ * y_lo = rna_tf32(v - y_hi) (A*B ~= Ah*Bh + Al*Bh + Ah*Bl recovers fp32-grade accuracy on tcgen05). */
+int myolo_bn_apply_split(const myolo_view* x, const myolo_view* y_hi, const myolo_view* y_lo, const float* mean,
+                         const float* var, const float* gamma, const float* beta, float eps, int act,
+                         myolo_stream stream);
+/* hi = rna_tf32(src), lo = rna_tf32(src - hi), elementwise over equal-shape views. */
+int myolo_split_tf32(const myolo_view* src, const myolo_view* hi, const myolo_view* lo, myolo_stream stream);
 /* backward of act(BN(x)). train!=0: batch-statistics BN (mean/var are this batch's); else moving stats.
  * dgamma/dbeta are OVERWRITTEN. ws = 2*C doubles. dx may alias dy. */
 int myolo_bn_bwd(const myolo_view* x, const myolo_view* dy, const myolo_view* dx, const float* mean, const float* var,

@@ -99,8 +99,10 @@ __global__ void finalize_div_kernel(const double* __restrict__ s, float* __restr
   if (c < C) out[c] = (accumulate ? out[c] : 0.f) + (float)(s[c] * inv);
 }
 
+// SPLIT: y receives hi = rna_tf32(v) and ylo receives rna_tf32(v - hi) (operand pair of a 3xTF32 GEMM)
+template <bool SPLIT>
 __global__ void __launch_bounds__(256)
-bn_apply_kernel(V x, V y, const float* __restrict__ mean, const float* __restrict__ var,
+bn_apply_kernel(V x, V y, V ylo, const float* __restrict__ mean, const float* __restrict__ var,
                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int act) {
   const int C4 = x.c >> 2;
   const long long total = (long long)x.n * x.h * x.w * C4;
@@ -117,7 +119,28 @@ bn_apply_kernel(V x, V y, const float* __restrict__ mean, const float* __restric
     o.y = apply_act(fmaf((v.y - mu.y) * (1.f / sqrtf(vv.y + eps)), ga.y, be.y), act);
     o.z = apply_act(fmaf((v.z - mu.z) * (1.f / sqrtf(vv.z + eps)), ga.z, be.z), act);
     o.w = apply_act(fmaf((v.w - mu.w) * (1.f / sqrtf(vv.w + eps)), ga.w, be.w), act);
-    *reinterpret_cast<float4*>(y.p + pix_off(y, p) + q) = o;
+    if (SPLIT) {
+      const float4 hi = make_float4(round_tf32(o.x), round_tf32(o.y), round_tf32(o.z), round_tf32(o.w));
+      *reinterpret_cast<float4*>(y.p + pix_off(y, p) + q) = hi;
+      *reinterpret_cast<float4*>(ylo.p + pix_off(ylo, p) + q) =
+          make_float4(round_tf32(o.x - hi.x), round_tf32(o.y - hi.y), round_tf32(o.z - hi.z), round_tf32(o.w - hi.w));
+    } else {
+      *reinterpret_cast<float4*>(y.p + pix_off(y, p) + q) = o;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) split_tf32_kernel(V src, V hi, V lo) {
+  const int C4 = src.c >> 2;
+  const long long total = (long long)src.n * src.h * src.w * C4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % C4) * 4;
+    const long long p = i / C4;
+    const float4 v = *reinterpret_cast<const float4*>(src.p + pix_off(src, p) + q);
+    const float4 h = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+    *reinterpret_cast<float4*>(hi.p + pix_off(hi, p) + q) = h;
+    *reinterpret_cast<float4*>(lo.p + pix_off(lo, p) + q) =
+        make_float4(round_tf32(v.x - h.x), round_tf32(v.y - h.y), round_tf32(v.z - h.z), round_tf32(v.w - h.w));
   }
 }
 
@@ -234,7 +257,26 @@ extern "C" int myolo_bn_apply(const myolo_view* x, const myolo_view* y, const fl
                               const float* gamma, const float* beta, float eps, int act, myolo_stream stream) {
   MYOLO_CHECK_ARG(view_ok(x) && view_ok(y) && same_shape(x, y) && mean && var && gamma && beta);
   const long long total = (long long)x->n * x->h * x->w * (x->c / 4);
-  bn_apply_kernel<<<ew_blocks(total), 256, 0, as_stream(stream)>>>(to_v(x), to_v(y), mean, var, gamma, beta, eps, act);
+  bn_apply_kernel<false><<<ew_blocks(total), 256, 0, as_stream(stream)>>>(to_v(x), to_v(y), to_v(y), mean, var, gamma, beta, eps, act);
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
+}
+
+extern "C" int myolo_bn_apply_split(const myolo_view* x, const myolo_view* y_hi, const myolo_view* y_lo, const float* mean,
+                                    const float* var, const float* gamma, const float* beta, float eps, int act,
+                                    myolo_stream stream) {
+  MYOLO_CHECK_ARG(view_ok(x) && view_ok(y_hi) && view_ok(y_lo) && same_shape(x, y_hi) && same_shape(x, y_lo));
+  MYOLO_CHECK_ARG(mean && var && gamma && beta);
+  const long long total = (long long)x->n * x->h * x->w * (x->c / 4);
+  bn_apply_kernel<true><<<ew_blocks(total), 256, 0, as_stream(stream)>>>(to_v(x), to_v(y_hi), to_v(y_lo), mean, var, gamma, beta, eps, act);
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
+}
+
+extern "C" int myolo_split_tf32(const myolo_view* src, const myolo_view* hi, const myolo_view* lo, myolo_stream stream) {
+  MYOLO_CHECK_ARG(view_ok(src) && view_ok(hi) && view_ok(lo) && same_shape(src, hi) && same_shape(src, lo));
+  const long long total = (long long)src->n * src->h * src->w * (src->c / 4);
+  split_tf32_kernel<<<ew_blocks(total), 256, 0, as_stream(stream)>>>(to_v(src), to_v(hi), to_v(lo));
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }

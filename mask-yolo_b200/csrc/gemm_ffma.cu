@@ -15,7 +15,7 @@
 namespace myolo {
 
 struct TapShifts {
-  int s[16];
+  int s[32];
 };
 
 constexpr int BM = 128, BN = 128, BK = 8;
@@ -42,8 +42,11 @@ sgemm_taps_kernel(const float* __restrict__ A, long long lda, const float* __res
   const int ar = tid >> 1, akq = (tid & 1) * 4;
   const bool arow_ok = (m0 + ar) < M;
   const bool brow_ok = (n0 + ar) < N;
-  const int kiters = K / BK;
+  const int kiters = (K + BK - 1) / BK;
   const int total = ntaps * kiters;
+  // fast path: 128-bit loads need 16-byte aligned rows and a K that is a multiple of the k-tile
+  const bool avec = ((lda & 3) == 0) && ((K & (BK - 1)) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+  const bool bvec = ((K & (BK - 1)) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
 
   float acc[8][8];
 #pragma unroll
@@ -56,9 +59,31 @@ sgemm_taps_kernel(const float* __restrict__ A, long long lda, const float* __res
     const int t = it / kiters;
     const int k0 = (it - t * kiters) * BK;
     ra = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (arow_ok) ra = __ldg(reinterpret_cast<const float4*>(A + (m0 + ar + sh.s[t]) * lda + k0 + akq));
+    if (arow_ok) {
+      const float* ap = A + (m0 + ar + sh.s[t]) * lda + k0 + akq;
+      if (avec) {
+        ra = __ldg(reinterpret_cast<const float4*>(ap));
+      } else {
+        const int kk = k0 + akq;
+        ra.x = (kk + 0 < K) ? __ldg(ap + 0) : 0.f;
+        ra.y = (kk + 1 < K) ? __ldg(ap + 1) : 0.f;
+        ra.z = (kk + 2 < K) ? __ldg(ap + 2) : 0.f;
+        ra.w = (kk + 3 < K) ? __ldg(ap + 3) : 0.f;
+      }
+    }
     rb = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (brow_ok) rb = __ldg(reinterpret_cast<const float4*>(B + ((size_t)t * N + n0 + ar) * K + k0 + akq));
+    if (brow_ok) {
+      const float* bp = B + ((size_t)t * N + n0 + ar) * K + k0 + akq;
+      if (bvec) {
+        rb = __ldg(reinterpret_cast<const float4*>(bp));
+      } else {
+        const int kk = k0 + akq;
+        rb.x = (kk + 0 < K) ? __ldg(bp + 0) : 0.f;
+        rb.y = (kk + 1 < K) ? __ldg(bp + 1) : 0.f;
+        rb.z = (kk + 2 < K) ? __ldg(bp + 2) : 0.f;
+        rb.w = (kk + 3 < K) ? __ldg(bp + 3) : 0.f;
+      }
+    }
   };
   auto sstore = [&](int buf) {
     As[buf][akq + 0][ar] = ra.x;
@@ -241,13 +266,13 @@ extern "C" int myolo_gemm_taps_ffma(const float* A, long long lda, const float* 
                                     int N, int K, int ntaps, const int* shifts_host, const float* bias,
                                     const float* scale, const float* shift_c, int act, int pf_w1, int pf_blk,
                                     int accumulate, myolo_stream stream) {
-  MYOLO_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0 && (K % BK) == 0 && (lda % 4) == 0);
-  MYOLO_CHECK_ARG(ntaps >= 1 && ntaps <= 16);
+  MYOLO_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0 && lda >= K);
+  MYOLO_CHECK_ARG(ntaps >= 1 && ntaps <= 32);
   MYOLO_CHECK_ARG((scale == nullptr) == (shift_c == nullptr));
   MYOLO_CHECK_ARG(!(accumulate && (scale || (act & 0xff) != MYOLO_ACT_NONE)));
   MYOLO_CHECK_ARG(pf_w1 <= 0 || pf_blk > 0);
   TapShifts sh;
-  for (int t = 0; t < 16; ++t) sh.s[t] = (shifts_host && t < ntaps) ? shifts_host[t] : 0;
+  for (int t = 0; t < 32; ++t) sh.s[t] = (shifts_host && t < ntaps) ? shifts_host[t] : 0;
   dim3 grid((unsigned)ceil_div(M, BM), (unsigned)ceil_div(N, BN));
   sgemm_taps_kernel<<<grid, 256, 0, as_stream(stream)>>>(A, lda, B, C, ldc, M, N, K, ntaps, sh, bias, scale, shift_c,
                                                          act, pf_w1, pf_blk, accumulate);
@@ -259,9 +284,9 @@ extern "C" int myolo_gemm_taps_wgrad_ffma(const float* A, long long lda, const f
                                      long long M, int N, int K, int ntaps, const int* shifts_host, int transpose_out,
                                      myolo_stream stream) {
   MYOLO_CHECK_ARG(A && D && dW && M > 0 && N > 0 && K > 0 && (K % 4) == 0 && (lda % 4) == 0);
-  MYOLO_CHECK_ARG(ntaps >= 1 && ntaps <= 16);
+  MYOLO_CHECK_ARG(ntaps >= 1 && ntaps <= 32);
   TapShifts sh;
-  for (int t = 0; t < 16; ++t) sh.s[t] = (shifts_host && t < ntaps) ? shifts_host[t] : 0;
+  for (int t = 0; t < 32; ++t) sh.s[t] = (shifts_host && t < ntaps) ? shifts_host[t] : 0;
   const int ntk = (int)ceil_div(K, BM), ntn = (int)ceil_div(N, BN);
   const long long tiles = (long long)ntk * ntn * ntaps;
   long long nsplit = max(1LL, min(ceil_div(M, 256), (long long)(kNumSMs * 4) / tiles + 1));

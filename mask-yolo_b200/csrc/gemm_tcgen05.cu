@@ -29,7 +29,7 @@ namespace myolo {
 namespace tc {
 
 struct TapShifts {
-  int s[16];
+  int s[32];
 };
 
 constexpr int BM = 128;  // UMMA M: rows (fwd) / A-channels (wgrad) per CTA
@@ -361,8 +361,10 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 // out[t][c][r] = f(in[t][r][c]) (transpose) or out = f(in); f = optional tf32 rounding
+// round == 2: split staging for the 3xTF32 forward (hi = rna(v), lo = rna(v - hi)); three stacked
+// copies [hi | hi | lo], each `total` floats, matching the tap triple (A_hi,B_hi) (A_lo,B_hi) (A_hi,B_lo).
 __global__ void prep_weights_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols,
-                                    int transpose, int round) {
+                                    int transpose, int round, size_t total) {
   __shared__ float t[32][33];
   const float* ip = in + (size_t)blockIdx.z * rows * cols;
   float* op = out + (size_t)blockIdx.z * rows * cols;
@@ -370,9 +372,18 @@ __global__ void prep_weights_kernel(const float* __restrict__ in, float* __restr
   for (int j = threadIdx.y; j < 32; j += 8) {
     const int r = blockIdx.y * 32 + j;
     float v = (r < rows && c < cols) ? ip[(size_t)r * cols + c] : 0.f;
-    if (round) v = round_tf32(v);
+    if (round == 1) v = round_tf32(v);
     if (!transpose) {
-      if (r < rows && c < cols) op[(size_t)r * cols + c] = v;
+      if (r < rows && c < cols) {
+        if (round == 2) {
+          const float hi = round_tf32(v);
+          op[(size_t)r * cols + c] = hi;
+          op[total + (size_t)r * cols + c] = hi;
+          op[2 * total + (size_t)r * cols + c] = round_tf32(v - hi);
+        } else {
+          op[(size_t)r * cols + c] = v;
+        }
+      }
     } else {
       t[j][threadIdx.x] = v;
     }
@@ -382,7 +393,17 @@ __global__ void prep_weights_kernel(const float* __restrict__ in, float* __restr
   const int r2 = blockIdx.y * 32 + threadIdx.x;
   for (int j = threadIdx.y; j < 32; j += 8) {
     const int c2 = blockIdx.x * 32 + j;
-    if (r2 < rows && c2 < cols) op[(size_t)c2 * rows + r2] = t[threadIdx.x][j];
+    if (r2 < rows && c2 < cols) {
+      const float v = t[threadIdx.x][j];
+      if (round == 2) {
+        const float hi = round_tf32(v);
+        op[(size_t)c2 * rows + r2] = hi;
+        op[total + (size_t)c2 * rows + r2] = hi;
+        op[2 * total + (size_t)c2 * rows + r2] = round_tf32(v - hi);
+      } else {
+        op[(size_t)c2 * rows + r2] = v;
+      }
+    }
   }
 }
 
@@ -525,7 +546,7 @@ extern "C" int myolo_gemm_taps_tc_supported(long long lda, long long ldc, long l
                                             int accumulate) {
   (void)accumulate;
   return M >= 1 && M < (1LL << 31) - 4096 && (K % BK) == 0 && pick_bn(N) != 0 && (lda % 4) == 0 && (ldc % 4) == 0 &&
-         ntaps >= 1 && ntaps <= 16 && (long long)ntaps * N < (1LL << 31);
+         ntaps >= 1 && ntaps <= 32 && (long long)ntaps * N < (1LL << 31);
 }
 
 extern "C" int myolo_gemm_taps_tc(const float* A, long long lda, const float* Bt, float* C, long long ldc, long long M,
@@ -538,10 +559,14 @@ extern "C" int myolo_gemm_taps_tc(const float* A, long long lda, const float* Bt
   MYOLO_CHECK_ARG(!(accumulate && (scale || (act & 0xff) != MYOLO_ACT_NONE)));
   MYOLO_CHECK_ARG(pf_w1 <= 0 || pf_blk > 0);
   TapShifts sh;
-  for (int t = 0; t < 16; ++t) sh.s[t] = (shifts_host && t < ntaps) ? shifts_host[t] : 0;
+  for (int t = 0; t < 32; ++t) sh.s[t] = (shifts_host && t < ntaps) ? shifts_host[t] : 0;
   const int bn = pick_bn(N);
   CUtensorMap ta, tb;
-  int rc = get_map(A, M, K, lda, BM, &ta);
+  // rows below 0 are TMA zero fill; rows past M are real memory (zero guard rows of a padded-flat
+  // tensor, or the low-part copy of a split operand), so the map extends over the largest shift
+  long long a_rows = M;
+  for (int t = 0; t < ntaps; ++t) a_rows = max(a_rows, M + (long long)sh.s[t]);
+  int rc = get_map(A, a_rows, K, lda, BM, &ta);
   if (rc) return rc;
   rc = get_map(Bt, (long long)ntaps * N, K, K, bn, &tb);
   if (rc) return rc;
@@ -557,7 +582,7 @@ extern "C" int myolo_gemm_taps_tc(const float* A, long long lda, const float* Bt
 
 extern "C" int myolo_gemm_taps_wgrad_tc_supported(long long lda, long long ldd, long long M, int N, int K, int ntaps) {
   return M >= 32 && M < (1LL << 31) - 4096 && (K % BM) == 0 && pick_bn(N) != 0 && (lda % 4) == 0 && (ldd % 4) == 0 &&
-         ntaps >= 1 && ntaps <= 16;
+         ntaps >= 1 && ntaps <= 32;
 }
 
 extern "C" int myolo_gemm_taps_wgrad_tc(const float* A, long long lda, const float* D, long long ldd, float* dW,
@@ -566,7 +591,7 @@ extern "C" int myolo_gemm_taps_wgrad_tc(const float* A, long long lda, const flo
   MYOLO_CHECK_ARG(A && D && dW && aligned16(A) && aligned16(D));
   MYOLO_CHECK_ARG(myolo_gemm_taps_wgrad_tc_supported(lda, ldd, M, N, K, ntaps));
   TapShifts sh;
-  for (int t = 0; t < 16; ++t) sh.s[t] = (shifts_host && t < ntaps) ? shifts_host[t] : 0;
+  for (int t = 0; t < 32; ++t) sh.s[t] = (shifts_host && t < ntaps) ? shifts_host[t] : 0;
   const int bn = pick_bn(N);
   CUtensorMap ta, td;
   int rc = get_map(A, M, K, lda, 32, &ta, 1);
@@ -584,9 +609,10 @@ extern "C" int myolo_gemm_taps_wgrad_tc(const float* A, long long lda, const flo
 
 extern "C" int myolo_prep_weights(const float* in, float* out, int ntaps, int rows, int cols, int transpose,
                                   int round_tf32, myolo_stream stream) {
-  MYOLO_CHECK_ARG(in && out && in != out && ntaps > 0 && rows > 0 && cols > 0);
+  MYOLO_CHECK_ARG(in && out && in != out && ntaps > 0 && rows > 0 && cols > 0 && round_tf32 >= 0 && round_tf32 <= 2);
   dim3 grid((cols + 31) / 32, (rows + 31) / 32, ntaps), block(32, 8);
-  prep_weights_kernel<<<grid, block, 0, as_stream(stream)>>>(in, out, rows, cols, transpose, round_tf32);
+  prep_weights_kernel<<<grid, block, 0, as_stream(stream)>>>(in, out, rows, cols, transpose, round_tf32,
+                                                             (size_t)ntaps * rows * cols);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }

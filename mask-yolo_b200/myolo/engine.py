@@ -1,0 +1,570 @@
+"""Executor of the Mask-YOLO hot path on one B200: forward, backward, Adam and the Keras BN
+moving-average update, entirely through the C ABI of libmyolo_sm100.so (include/myolo_b200.h).
+
+This replaces what the reference delegates to one `tf.Session.run(train_op)` per batch
+(myolo/model.py:1047-1059 -> the graph wired in MaskYOLO.build, 787-941).  PyTorch is used for
+device memory and streams only; no torch operator computes anything on the hot path and there is
+no CPU fallback (the C-ABI loader raises when the library or an sm_100 device is missing).
+
+Data layout in HBM: activations fp32 NHWC; every tensor that feeds a 3x3
+tensor-core convolution lives in the padded-flat (PF) layout of myolo/pf.py; parameters, gradients
+and the two Adam moments are four flat fp32 buffers with identical offsets (one fused Adam launch,
+one NCCL all-reduce), keyed by the Keras variable names of the reference graph.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import _cabi as C
+from .pf import PF, conv3x3_shifts
+
+BN_EPS = 1e-3        # Keras BatchNormalization default (graph fixture: epsilon 0.001)
+BN_MOMENTUM = 0.99
+
+# (block id, Cin, Cout, stride): myolo/model.py:68-77 (backbone) and 256-268 (yolo branch)
+BACKBONE_BLOCKS = [(1, 32, 64, 1), (2, 64, 64, 2), (3, 64, 128, 1), (4, 128, 256, 2), (5, 256, 256, 1), (6, 256, 512, 1)]
+YOLO_BLOCKS = [(7, 512, 512, 2), (8, 512, 512, 1), (9, 512, 512, 1), (10, 512, 512, 1), (11, 512, 512, 1),
+               (12, 512, 512, 1), (13, 512, 1024, 2), (14, 1024, 1024, 1)]
+MASK_C = 256          # TOP_FEATURE_MAP_DEPTH (config.py:91) == mask head width (model.py:688-711)
+
+
+def param_specs(nb: int, nc: int):
+    """[(keras variable name, shape, trainable)] in flat-buffer order: backbone, yolo branch, then
+    feature_map + mask head LAST (their gradients are complete first in the backward pass, so the
+    tail of the flat gradient buffer can be all-reduced while the backbone is still running)."""
+    sp = [("conv1/kernel", (3, 3, 3, 32), True)]
+
+    def bn(name, c):
+        return [(f"{name}/gamma", (c,), True), (f"{name}/beta", (c,), True),
+                (f"{name}/moving_mean", (c,), False), (f"{name}/moving_variance", (c,), False)]
+
+    sp += bn("conv1_bn", 32)
+    for k, ci, co, _ in BACKBONE_BLOCKS + YOLO_BLOCKS:
+        sp.append((f"conv_dw_{k}/depthwise_kernel", (3, 3, ci, 1), True))
+        sp += bn(f"conv_dw_{k}_bn", ci)
+        sp.append((f"conv_pw_{k}/kernel", (1, 1, ci, co), True))
+        sp += bn(f"conv_pw_{k}_bn", co)
+    sp += [("conv_23/kernel", (1, 1, 1024, nb * (5 + nc)), True), ("conv_23/bias", (nb * (5 + nc),), True)]
+    sp += [("feature_map/kernel", (3, 3, 512, MASK_C), True), ("feature_map/bias", (MASK_C,), True)]
+    for i in (1, 2, 3, 4):
+        sp += [(f"myolo_mask_conv{i}/kernel", (3, 3, MASK_C, MASK_C), True), (f"myolo_mask_conv{i}/bias", (MASK_C,), True)]
+        sp += bn(f"myolo_mask_bn{i}", MASK_C)
+    sp += [("myolo_mask_deconv/kernel", (2, 2, MASK_C, MASK_C), True), ("myolo_mask_deconv/bias", (MASK_C,), True)]
+    sp += [("myolo_mask/kernel", (1, 1, MASK_C, nc), True), ("myolo_mask/bias", (nc,), True)]
+    return sp
+
+
+def init_params(nb: int, nc: int, seed: int = 0, kind: str = "keras") -> Dict[str, torch.Tensor]:
+    """CPU fp32 parameter dict keyed by Keras names.  kind='keras': the Keras defaults the reference
+    relies on (glorot_uniform kernels, zero biases, BN gamma 1 / beta 0 / mean 0 / var 1).
+    kind='trained_like': same kernels with perturbed BN statistics and affine terms so that moving
+    statistics, biases and the inference-mode mask BNs are numerically exercised."""
+    g = torch.Generator().manual_seed(seed)
+    P = OrderedDict()
+    for name, shape, _ in param_specs(nb, nc):
+        leaf = name.rsplit("/", 1)[1]
+        if leaf in ("kernel", "depthwise_kernel"):
+            rf = shape[0] * shape[1]
+            fan_in, fan_out = rf * shape[2], rf * shape[3]
+            lim = math.sqrt(6.0 / (fan_in + fan_out))
+            P[name] = (torch.rand(shape, generator=g) * 2 - 1) * lim
+        elif leaf in ("gamma", "moving_variance"):
+            P[name] = torch.ones(shape)
+        else:
+            P[name] = torch.zeros(shape)
+        if kind == "trained_like":
+            if leaf == "gamma":
+                P[name] = 0.8 + 0.4 * torch.rand(shape, generator=g)
+            elif leaf == "beta":
+                P[name] = 0.2 * torch.randn(shape, generator=g)
+            elif leaf == "moving_mean":
+                P[name] = 0.1 * torch.randn(shape, generator=g)
+            elif leaf == "moving_variance":
+                P[name] = 0.6 + 0.8 * torch.rand(shape, generator=g)
+            elif leaf == "bias":
+                P[name] = 0.05 * torch.randn(shape, generator=g)
+    return P
+
+
+class _BN:
+    """One BatchNormalization layer: views into the flat buffers + batch/moving statistics."""
+    __slots__ = ("name", "c", "gamma", "beta", "dgamma", "dbeta", "mmean", "mvar", "bmean", "bvar", "mean", "var", "step")
+
+
+class Engine:
+    """Owns every device buffer of one replica and runs the step.  `cfg` is a plain dict (built by
+    myolo.model from a Config instance, SURVEY Q1 rules applied): S, G, NB, NC, TB, MAXGT, R,
+    ANCHORS, POOL, MASK_SHAPE, OBJECT/NO_OBJECT/COORD/CLASS scales, CLASS_WEIGHTS, WARM_UP_BATCHES,
+    LOSS_WEIGHTS."""
+
+    def __init__(self, cfg: dict, batch: int, mode: str = "training", precision: str = "tf32", device: int = 0,
+                 params: Optional[Dict[str, torch.Tensor]] = None, seed: int = 0):
+        assert mode in ("training", "inference", "yolo")
+        if not torch.cuda.is_available():
+            raise C.MyoloError("the Mask-YOLO hot path needs an sm_100 (B200) GPU; there is no CPU fallback")
+        C.device_check(device)
+        self.cfg, self.B, self.mode = cfg, batch, mode
+        self.dev = torch.device("cuda", device)
+        torch.cuda.set_device(self.dev)
+        self.set_precision(precision)
+        S, G = cfg["S"], cfg["G"]
+        if S % 32 != 0 or G != S // 32:
+            raise Exception("Image size must be dividable by 32 to adapt with YOLO framework. "
+                            "For example, use 224, 256, 288, 320, 356, ... etc. ")   # model.py:791-794
+        self.NB, self.NC, self.TB, self.R = cfg["NB"], cfg["NC"], cfg["TB"], cfg["G"] * cfg["G"] * cfg["NB"]
+        self.with_mask = mode != "yolo"
+        self._frozen = False
+        self._shift_cache = {}
+        self.t = 0                     # Adam iteration
+        self.seen = 0                  # yolo_custom_loss `seen` counter (model.py:95, 197)
+        self._alloc_params(params if params is not None else init_params(self.NB, self.NC, seed))
+        self._alloc_acts()
+        self.refresh_weights()
+
+    # ------------------------------------------------------------------ parameters
+    def set_precision(self, precision: str):
+        """fp32      : exact-fp32 CUDA-core GEMMs everywhere (parity configuration);
+        tf32      : tcgen05 kind::tf32 everywhere, single pass (fastest, ~1e-3 relative per layer);
+        tf32x3    : tcgen05 everywhere; the FORWARD GEMMs of backbone / yolo branch / feature_map run
+                    as 3xTF32 (operands split hi+lo, A*B ~= Ah*Bh + Al*Bh + Ah*Bl: fp32-grade
+                    outputs), mask head and every backward GEMM single-pass tf32;
+        tf32x3_all: as tf32x3, with the mask-head forward convolutions in 3xTF32 as well."""
+        assert precision in ("fp32", "tf32", "tf32x3", "tf32x3_all")
+        self.precision = precision
+        self.tc = precision != "fp32"
+        self.x3 = precision in ("tf32x3", "tf32x3_all")
+        self.x3m = precision == "tf32x3_all"
+        self.rnd = C.ROUND_TF32 if self.tc else 0
+        C.set_precision(C.PREC_TF32 if self.tc else C.PREC_FP32)
+
+    def _alloc_params(self, P):
+        specs = param_specs(self.NB, self.NC)
+        self.specs = specs
+        off, self.offs = 0, OrderedDict()
+        for name, shape, tr in specs:
+            if tr:
+                n = int(np.prod(shape))
+                self.offs[name] = (off, n, shape)
+                off += (n + 3) // 4 * 4                       # 16-byte aligned slices
+        self.n_flat = off
+        z = lambda: torch.zeros(off, dtype=torch.float32, device=self.dev)
+        self.params, self.grads, self.adam_m, self.adam_v = z(), z(), z(), z()
+        self.p, self.g = {}, {}
+        for name, (o, n, shape) in self.offs.items():
+            self.p[name] = self.params[o:o + n].view(shape)
+            self.g[name] = self.grads[o:o + n].view(shape)
+        self.trainable_mask = torch.ones(off, dtype=torch.float32, device=self.dev)
+        self.stats = {name: torch.zeros(shape, dtype=torch.float32, device=self.dev) for name, shape, tr in specs if not tr}
+        self.bn: Dict[str, _BN] = {}
+        for name, shape, tr in specs:
+            if name.endswith("/gamma"):
+                b = _BN()
+                b.name, b.c = name[:-6], shape[0]
+                b.gamma, b.beta = self.p[b.name + "/gamma"], self.p[b.name + "/beta"]
+                b.dgamma, b.dbeta = self.g[b.name + "/gamma"], self.g[b.name + "/beta"]
+                b.mmean, b.mvar = self.stats[b.name + "/moving_mean"], self.stats[b.name + "/moving_variance"]
+                b.bmean = torch.zeros(b.c, device=self.dev)     # zero-debiased accumulators ("biased")
+                b.bvar = torch.zeros(b.c, device=self.dev)
+                b.mean = torch.zeros(b.c, device=self.dev)      # this batch's statistics
+                b.var = torch.zeros(b.c, device=self.dev)
+                b.step = 0
+                self.bn[b.name] = b
+        # boundary of the "late" bucket (feature_map + mask head) inside the flat buffers
+        self.tail_off = self.offs["feature_map/kernel"][0]
+        self.load_params(P)
+        # GEMM-side weight copies: per-tap transposed ([t][Cout][Cin], K-major B operand of the forward)
+        self.wt = {}
+        for name, (o, n, shape) in self.offs.items():
+            if name.endswith("/kernel") and name != "conv1/kernel":
+                self.wt[name] = torch.zeros(n * (3 if self._is_x3(name) else 1), dtype=torch.float32, device=self.dev)
+        self.ws = torch.zeros(4096, dtype=torch.float64, device=self.dev)
+        self.anchors = torch.tensor(self.cfg["ANCHORS"], dtype=torch.float32, device=self.dev)
+        self.class_w = torch.tensor(np.asarray(self.cfg["CLASS_WEIGHTS"], dtype=np.float32), device=self.dev)
+        self.scales = C.float_array([self.cfg["OBJECT_SCALE"], self.cfg["NO_OBJECT_SCALE"], self.cfg["COORD_SCALE"],
+                                     self.cfg["CLASS_SCALE"]])
+
+    def _is_x3(self, name: str) -> bool:
+        """Does the forward GEMM of this kernel run as 3xTF32?"""
+        if name.startswith("myolo_mask_conv"):
+            return self.x3m
+        if name.startswith("myolo_mask") or name == "conv_23/kernel":
+            return False            # deconv: single pass; conv_23 (N=45) and the 1x1 mask conv are CUDA-core fp32
+        return self.x3
+
+    def load_params(self, P: Dict[str, torch.Tensor], strict: bool = True):
+        for name, shape, tr in self.specs:
+            if name not in P:
+                if strict:
+                    raise KeyError(name)
+                continue
+            src = torch.as_tensor(P[name], dtype=torch.float32).reshape(shape)
+            (self.p[name] if tr else self.stats[name]).copy_(src)
+        if hasattr(self, "wt"):
+            self.refresh_weights()
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        out = OrderedDict()
+        for name, shape, tr in self.specs:
+            out[name] = (self.p[name] if tr else self.stats[name]).detach().cpu().clone()
+        return out
+
+    def grad_dict(self) -> Dict[str, torch.Tensor]:
+        return OrderedDict((n, self.g[n].detach().cpu().clone()) for n in self.offs)
+
+    def set_trainable(self, predicate):
+        """predicate(keras variable name) -> bool.  Frozen variables keep zero Adam updates."""
+        self.trainable_mask.zero_()
+        self._frozen = False
+        for name, (o, n, _) in self.offs.items():
+            if predicate(name):
+                self.trainable_mask[o:o + n] = 1.0
+            else:
+                self._frozen = True
+
+    def refresh_weights(self):
+        """Re-stage the transposed (and, in tf32 mode, rounded) GEMM weight operands after an update."""
+        st = self._st()
+        for name, buf in self.wt.items():
+            rnd = 2 if self._is_x3(name) else (1 if self.tc else 0)
+            if name == "conv_23/kernel":
+                rnd = 0         # N = N_BOX*(5+NC) is not a tensor-core shape: always the exact CUDA-core kernel
+            shape = self.offs[name][2]
+            if name == "myolo_mask_deconv/kernel":
+                # Keras [2,2,Cout,Cin] is already the forward Bt ([N=4*Cout][K=Cin]); stage its
+                # transpose [Cin][4*Cout] for the dgrad GEMM.
+                C.call("myolo_prep_weights", self.p[name], buf, 1, 4 * shape[2], shape[3], 1, rnd, st)
+            else:
+                taps = shape[0] * shape[1]
+                C.call("myolo_prep_weights", self.p[name], buf, taps, shape[2], shape[3], 1, rnd, st)
+
+    # ------------------------------------------------------------------ activations
+    def _alloc_acts(self):
+        B, S, dev = self.B, self.cfg["S"], self.dev
+        f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+        A = {}
+        H = S // 2
+        A["y0"], A["a0"] = f(B, H, H, 32), f(B, H, H, 32)
+        self.geo = {}
+        maxel = B * H * H * 32
+        for k, ci, co, s in BACKBONE_BLOCKS + YOLO_BLOCKS:
+            Ho = (H - 1) // s + 1
+            self.geo[k] = (H, Ho, ci, co, s)
+            A[f"yd{k}"] = f(B, Ho, Ho, ci)
+            # pointwise-GEMM operand; in 3xTF32 mode [0] = tf32 high part, [1] = low part
+            A[f"ad{k}"] = f(2, B, Ho, Ho, ci) if self.x3 else f(B, Ho, Ho, ci)
+            A[f"yp{k}"] = f(B, Ho, Ho, co)
+            if k == 6 and self.with_mask:
+                self.c4 = PF(B, Ho, Ho, co, device=dev, split=self.x3)   # C4 feeds the 3x3 feature_map conv
+                if self.x3:
+                    A["ap6"] = f(B, Ho, Ho, co)                   # full-precision C4 for the depthwise consumer
+            else:
+                A[f"ap{k}"] = f(B, Ho, Ho, co)
+            maxel = max(maxel, B * H * H * ci, B * Ho * Ho * co)
+            H = Ho
+        self.F = self.geo[6][1]
+        G, NB, NC, R = self.cfg["G"], self.NB, self.NC, self.R
+        assert H == G
+        A["yolo"] = f(B, G, G, NB * (5 + NC))
+        A["proposals"] = f(B, R, 4)
+        A["detections"] = f(B, R, 6)
+        self.loss_yolo = torch.zeros(5, device=dev)
+        self.loss_mask = torch.zeros(1, device=dev)
+        if self.mode != "inference":
+            A["dyolo"] = f(B, G, G, NB * (5 + NC))
+            self.gx, self.gy = f(maxel), f(maxel)                 # backbone gradient ping-pong
+        if self.with_mask:
+            F_, P_ = self.F, self.cfg["POOL"]
+            n = B * R
+            self.n_roi = n
+            self.feat = PF(B, F_, F_, MASK_C, device=dev)
+            self.x0 = PF(n, P_, P_, MASK_C, device=dev, split=self.x3m)
+            self.my = [None] + [PF(n, P_, P_, MASK_C, device=dev) for _ in range(4)]
+            self.ma = [self.x0] + [PF(n, P_, P_, MASK_C, device=dev, split=self.x3m and i < 4) for i in range(1, 5)]
+            self.y4d = PF(n, P_, P_, 4 * MASK_C, device=dev)
+            mh, mw = self.cfg["MASK_SHAPE"]
+            assert (mh, mw) == (2 * P_, 2 * P_)
+            A["masks"] = f(n, mh, mw, NC)
+            if self.mode == "training":
+                A["rois"] = f(B, R, 4)
+                self.target_ids = torch.zeros(B, R, dtype=torch.int32, device=dev)
+                A["target_masks"] = f(B, R, mh, mw)
+                self.n_pos = torch.zeros(B, dtype=torch.int32, device=dev)
+                self.roi_src = torch.zeros(B, R, dtype=torch.int32, device=dev)
+                self.roi_gt = torch.zeros(B, R, dtype=torch.int32, device=dev)
+                A["dlogit"] = f(n, mh, mw, NC)
+                self.dy4d = PF(n, P_, P_, 4 * MASK_C, device=dev)
+                self.mg = [PF(n, P_, P_, MASK_C, device=dev) for _ in range(2)]
+                self.dfeat = PF(B, F_, F_, MASK_C, device=dev)
+                self.dc4 = PF(B, F_, F_, 512, device=dev)
+        self.A = A
+
+    # ------------------------------------------------------------------ small helpers
+    def _st(self):
+        return torch.cuda.current_stream().cuda_stream
+
+    @staticmethod
+    def _v(t):
+        n, h, w, c = t.shape
+        return C.view(t, n, h, w, c)
+
+    def _bn_fwd(self, name, xv, yv, act, training, n_pix, yv_lo=None):
+        b, st = self.bn[name], self._st()
+        if training:
+            C.call("myolo_bn_stats", xv, b.mean, b.var, self.ws, st)
+            self._bn_touched.append((b, n_pix))
+            mean, var = b.mean, b.var
+        else:
+            mean, var = b.mmean, b.mvar
+        if yv_lo is None:
+            C.call("myolo_bn_apply", xv, yv, mean, var, b.gamma, b.beta, BN_EPS, act, st)
+        else:
+            C.call("myolo_bn_apply_split", xv, yv, yv_lo, mean, var, b.gamma, b.beta, BN_EPS, act & 0xff, st)
+
+    def _gemm_fwd(self, a_rows, lo_off, name, out_rows, M, N, K, shifts, bias, pf_w1, pf_blk):
+        """Forward conv GEMM through the tap-GEMM entry point; 3xTF32 = the tap list tripled over the
+        (A_hi,B_hi) (A_lo,B_hi) (A_hi,B_lo) operand pairs (lo_off = row distance hi -> lo)."""
+        base = list(shifts) if shifts is not None else [0]
+        if self._is_x3(name):
+            sh = base + [v + lo_off for v in base] + base
+        else:
+            sh = base
+        key = (name, tuple(sh))
+        arr = self._shift_cache.get(key)
+        if arr is None:
+            arr = self._shift_cache[key] = C.int_array(sh)
+        C.call("myolo_gemm_taps", a_rows, K, self.wt[name], out_rows, N, M, N, K, len(sh), arr, bias, None, None,
+               C.ACT_NONE, pf_w1, pf_blk, 0, self._st())
+
+    def _bn_bwd(self, name, xv, dyv, act, training):
+        b = self.bn[name]
+        mean, var = (b.mean, b.var) if training else (b.mmean, b.mvar)
+        C.call("myolo_bn_bwd", xv, dyv, dyv, mean, var, b.gamma, b.beta, BN_EPS, act, 1 if training else 0,
+               b.dgamma, b.dbeta, self.ws, self._st())
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, image: torch.Tensor, training: Optional[bool] = None):
+        """image [B,S,S,3] fp32 on the device, values in 0..1 (BatchGenerator divides by 255).
+        Backbone + feature_map + yolo branch + decode (model.py:844-874, 922-926)."""
+        training = (self.mode != "inference") if training is None else training
+        A, B, st = self.A, self.B, self._st()
+        S = self.cfg["S"]
+        assert tuple(image.shape) == (B, S, S, 3) and image.is_cuda and image.dtype == torch.float32
+        self._bn_touched: List = []
+        self._image = image
+        relu6 = C.ACT_RELU6
+        # conv_block (model.py:42-52)
+        C.call("myolo_conv1_fwd", image, self.p["conv1/kernel"], A["y0"], B, S, 32, st)
+        self._bn_fwd("conv1_bn", self._v(A["y0"]), self._v(A["a0"]), relu6, training, B * (S // 2) ** 2)
+        xin_view = self._v(A["a0"])
+        for k, ci, co, s in BACKBONE_BLOCKS + YOLO_BLOCKS:
+            Hi, Ho, _, _, _ = self.geo[k]
+            npix = B * Ho * Ho
+            # _depthwise_conv_block: ZeroPad(1,1) + depthwise 3x3 VALID stride s -> BN -> ReLU6
+            C.call("myolo_dwconv3x3_fwd", xin_view, self.p[f"conv_dw_{k}/depthwise_kernel"], A[f"yd{k}"], s, st)
+            ad = A[f"ad{k}"]
+            if self.x3:
+                self._bn_fwd(f"conv_dw_{k}_bn", self._v(A[f"yd{k}"]), self._v(ad[0]), relu6, training, npix, self._v(ad[1]))
+            else:
+                self._bn_fwd(f"conv_dw_{k}_bn", self._v(A[f"yd{k}"]), self._v(ad), relu6 | self.rnd, training, npix)
+            # pointwise 1x1 -> BN -> ReLU6
+            self._gemm_fwd(ad, npix, f"conv_pw_{k}/kernel", A[f"yp{k}"], npix, co, ci, None, None, 0, 0)
+            if k == 6 and self.with_mask:
+                if self.x3:
+                    out_view = self._v(A["ap6"])
+                    self._bn_fwd(f"conv_pw_{k}_bn", self._v(A[f"yp{k}"]), out_view, relu6, training, npix)
+                    C.call("myolo_split_tf32", out_view, self.c4.view(), self.c4.view(lo=True), st)
+                else:
+                    out_view = self.c4.view()
+                    self._bn_fwd(f"conv_pw_{k}_bn", self._v(A[f"yp{k}"]), out_view, relu6 | self.rnd, training, npix)
+            else:
+                out_view = self._v(A[f"ap{k}"])
+                self._bn_fwd(f"conv_pw_{k}_bn", self._v(A[f"yp{k}"]), out_view, relu6, training, npix)
+            xin_view = out_view
+            if k == 6 and self.with_mask:
+                # myolo_feature_maps = Conv2D(256, 3x3, SAME)(C4) + bias   (model.py:848)
+                F_ = self.F
+                self._gemm_fwd(self.c4.rows, self.c4.lo_off, "feature_map/kernel", self.feat.rows, self.c4.M, MASK_C, 512,
+                               conv3x3_shifts(F_), self.p["feature_map/bias"], F_ + 1, (F_ + 1) * (F_ + 1))
+        G, NB, NC = self.cfg["G"], self.NB, self.NC
+        # conv_23 (model.py:271) + reshape [B,G,G,NB,5+NC] (273): a pure view of the NHWC result
+        C.call("myolo_gemm_taps_ffma", A["ap14"], 1024, self.wt["conv_23/kernel"], A["yolo"], NB * (5 + NC), B * G * G,
+               NB * (5 + NC), 1024, 1, None, self.p["conv_23/bias"], None, None, C.ACT_NONE, 0, 0, 0, st)
+        # DecodeYOLOLayer / DetectionsLayer (model.py:1442-1473, 1493-1538)
+        C.call("myolo_yolo_decode", A["yolo"], self.anchors, A["proposals"], A["detections"], B, G, G, NB, NC, st)
+        return A["yolo"].view(B, G, G, NB, 5 + NC)
+
+    def mask_head(self, rois: torch.Tensor, training: bool):
+        """build_mask_graph (model.py:668-715) on rois [B,R,4] (x1,y1,x2,y2, passed to ROIAlign as-is:
+        SURVEY Q2).  bn1 follows the learning phase, bn2..4 always use moving statistics."""
+        A, st, n = self.A, self._st(), self.n_roi
+        P_ = self.cfg["POOL"]
+        npix = n * P_ * P_
+        C.call("myolo_roialign_fwd", self.feat.view(), rois, n, self.R, P_, self.x0.view(),
+               1 if (self.rnd and not self.x3m) else 0, st)
+        if self.x3m:
+            C.call("myolo_split_tf32", self.x0.view(), self.x0.view(), self.x0.view(lo=True), st)
+        sh3 = conv3x3_shifts(P_)
+        for i in (1, 2, 3, 4):
+            a_in = self.ma[i - 1]
+            self._gemm_fwd(a_in.rows, a_in.lo_off, f"myolo_mask_conv{i}/kernel", self.my[i].rows, a_in.M, MASK_C, MASK_C,
+                           sh3, self.p[f"myolo_mask_conv{i}/bias"], P_ + 1, (P_ + 1) * (P_ + 1))
+            lo = self.ma[i].view(lo=True) if self.ma[i].rows_lo is not None else None
+            self._bn_fwd(f"myolo_mask_bn{i}", self.my[i].view(), self.ma[i].view(), C.ACT_RELU | self.rnd,
+                         training and i == 1, npix, lo)
+        # Conv2DTranspose 2x2 s2 as one GEMM [rows,256] x [256, 4*256]; bias/ReLU/1x1/sigmoid in mask_out
+        a4 = self.ma[4]
+        C.call("myolo_gemm_taps", a4.rows, MASK_C, self.p["myolo_mask_deconv/kernel"], self.y4d.rows, 4 * MASK_C, a4.M,
+               4 * MASK_C, MASK_C, 1, None, None, None, None, C.ACT_NONE, P_ + 1, (P_ + 1) * (P_ + 1), 0, st)
+        C.call("myolo_mask_out_fwd", self.y4d.rows, self.p["myolo_mask_deconv/bias"], self.p["myolo_mask/kernel"],
+               self.p["myolo_mask/bias"], A["masks"], n, P_, P_, MASK_C, self.NC, st)
+        mh, mw = self.cfg["MASK_SHAPE"]
+        return A["masks"].view(self.B, self.R, mh, mw, self.NC)
+
+    def forward_inference(self, image):
+        """mode='inference' graph (model.py:922-936) -> [yolo_output, detections, myolo_mask]."""
+        yolo = self.forward(image, training=False)
+        det = self.A["detections"]
+        # detection_boxes = detections[..., :4] (model.py:927) == the decoded proposals buffer
+        masks = self.mask_head(self.A["proposals"], training=False) if self.with_mask else None
+        return yolo, det, masks
+
+    def forward_training(self, inputs):
+        """mode='training' graph (model.py:844-901); inputs as BatchGenerator yields them:
+        [image, true_boxes [B,1,1,1,TB,4], yolo_target [B,G,G,NB,5+NC], gt_class_ids [B,M] i32,
+        gt_boxes [B,M,4] px (x1,y1,x2,y2), gt_masks [B,S,S,M] bool] -- device tensors."""
+        image, true_boxes, yolo_target = inputs[0], inputs[1], inputs[2]
+        A, B, st, cfg = self.A, self.B, self._st(), self.cfg
+        G, NB, NC, TB, R = cfg["G"], self.NB, self.NC, self.TB, self.R
+        yolo = self.forward(image, training=True)
+        self.seen += 1
+        warm = 1 if self.seen < cfg.get("WARM_UP_BATCHES", 0) else 0
+        lw = cfg.get("LOSS_WEIGHTS", {})
+        assert true_boxes.dtype == torch.float32 and yolo_target.dtype == torch.float32
+        C.call("myolo_yolo_loss", yolo_target, A["yolo"], true_boxes, self.anchors, self.class_w, B, G, G, NB, NC, TB,
+               self.scales, warm, float(lw.get("yolo_sum_loss", 1.0)), self.loss_yolo, A["dyolo"], self.ws, st)
+        out = dict(yolo_output=yolo, yolo_proposals=A["proposals"], yolo_sum_loss=self.loss_yolo[0])
+        if self.with_mask:
+            gt_ids, gt_boxes, gt_masks = inputs[3], inputs[4], inputs[5]
+            M = gt_ids.shape[1]
+            mh, mw = cfg["MASK_SHAPE"]
+            assert gt_ids.dtype == torch.int32 and gt_boxes.dtype == torch.float32 and gt_masks.dtype in (torch.uint8, torch.bool)
+            C.call("myolo_detect_mask_targets", A["proposals"], gt_ids, gt_boxes, gt_masks, B, R, M, cfg["S"], mh, mw,
+                   A["rois"], self.target_ids, A["target_masks"], self.n_pos, self.roi_src, self.roi_gt, st)
+            masks = self.mask_head(A["rois"], training=True)
+            C.call("myolo_mask_loss", A["masks"], A["target_masks"], self.target_ids, self.n_roi, mh, mw, NC,
+                   float(lw.get("myolo_mask_loss", 1.0)), self.loss_mask, A["dlogit"], self.ws, st)
+            out.update(output_rois=A["rois"], myolo_mask=masks, mask_loss=self.loss_mask[0],
+                       target_class_ids=self.target_ids, target_mask=A["target_masks"])
+        return out
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, on_tail_ready=None):
+        """Gradients of LOSS_WEIGHTS-weighted (yolo_sum_loss + mask_loss) w.r.t. every trainable
+        variable, into the flat gradient buffer.  `on_tail_ready()` is invoked once the
+        feature_map + mask-head slice [tail_off:] is final (hook for the overlapped all-reduce)."""
+        A, B, st = self.A, self.B, self._st()
+        self.grads.zero_()
+        relu6 = C.ACT_RELU6
+        if self.with_mask:
+            self._backward_mask()
+        if on_tail_ready is not None:
+            on_tail_ready()
+        G, NB, NC = self.cfg["G"], self.NB, self.NC
+        ny = NB * (5 + NC)
+        # conv_23
+        dy = A["dyolo"]
+        C.call("myolo_colsum", self._v(dy), self.g["conv_23/bias"], self.ws, st)
+        C.call("myolo_pwconv_wgrad", A["ap14"], dy, self.g["conv_23/kernel"], B * G * G, 1024, ny, st)
+        gx, gy = self.gx, self.gy
+        C.call("myolo_pwconv_dgrad", dy, self.p["conv_23/kernel"], gx, B * G * G, 1024, ny, st)
+        for k, ci, co, s in reversed(BACKBONE_BLOCKS + YOLO_BLOCKS):
+            Hi, Ho, _, _, _ = self.geo[k]
+            npix = B * Ho * Ho
+            if k == 6 and self.with_mask:
+                # join the feature_map branch: d(C4) += dgrad of the 3x3 conv (padded-flat -> dense)
+                C.call("myolo_view_copy", self.dc4.view(), C.view(gx, B, Ho, Ho, co), 1, st)
+            d_ap = C.view(gx, B, Ho, Ho, co)
+            self._bn_bwd(f"conv_pw_{k}_bn", self._v(A[f"yp{k}"]), d_ap, relu6, True)
+            ad_hi = A[f"ad{k}"][0] if self.x3 else A[f"ad{k}"]
+            C.call("myolo_pwconv_wgrad", ad_hi, gx, self.g[f"conv_pw_{k}/kernel"], npix, ci, co, st)
+            C.call("myolo_pwconv_dgrad", gx, self.p[f"conv_pw_{k}/kernel"], gy, npix, ci, co, st)
+            d_ad = C.view(gy, B, Ho, Ho, ci)
+            self._bn_bwd(f"conv_dw_{k}_bn", self._v(A[f"yd{k}"]), d_ad, relu6, True)
+            if k == 1:
+                xin = self._v(A["a0"])
+            elif k == 7 and self.with_mask and not self.x3:
+                xin = self.c4.view()
+            else:
+                xin = self._v(A[f"ap{k - 1}"])
+            C.call("myolo_dwconv3x3_bwd_filter", xin, gy, self.g[f"conv_dw_{k}/depthwise_kernel"], s, st)
+            C.call("myolo_dwconv3x3_bwd_data", gy, self.p[f"conv_dw_{k}/depthwise_kernel"], gx, B, Hi, Hi, ci, s, st)
+        S = self.cfg["S"]
+        H0 = S // 2
+        self._bn_bwd("conv1_bn", self._v(A["y0"]), C.view(gx, B, H0, H0, 32), relu6, True)
+        C.call("myolo_conv1_wgrad", self._image, gx, self.g["conv1/kernel"], B, S, 32, st)
+
+    def _backward_mask(self):
+        A, st, n = self.A, self._st(), self.n_roi
+        P_, B, F_ = self.cfg["POOL"], self.B, self.F
+        pfw, pfb = P_ + 1, (P_ + 1) * (P_ + 1)
+        a4 = self.ma[4]
+        C.call("myolo_mask_out_bwd", self.y4d.rows, self.p["myolo_mask_deconv/bias"], self.p["myolo_mask/kernel"],
+               A["dlogit"], self.dy4d.rows, self.g["myolo_mask/kernel"], self.g["myolo_mask/bias"],
+               self.g["myolo_mask_deconv/bias"], n, P_, P_, MASK_C, self.NC, st)
+        # deconv: dKd[(a,b,co)][ci] = sum_p dy4[p][(a,b,co)] a4[p][ci]  (transposed wgrad output = Keras layout)
+        C.call("myolo_gemm_taps_wgrad", a4.rows, MASK_C, self.dy4d.rows, 4 * MASK_C, self.g["myolo_mask_deconv/kernel"],
+               a4.M, 4 * MASK_C, MASK_C, 1, None, 1, st)
+        g0, g1 = self.mg
+        C.call("myolo_gemm_taps", self.dy4d.rows, 4 * MASK_C, self.wt["myolo_mask_deconv/kernel"], g0.rows, MASK_C, a4.M,
+               MASK_C, 4 * MASK_C, 1, None, None, None, None, C.ACT_NONE, pfw, pfb, 0, st)
+        for i in (4, 3, 2, 1):
+            self._bn_bwd(f"myolo_mask_bn{i}", self.my[i].view(), g0.view(), C.ACT_RELU | self.rnd, i == 1)
+            C.call("myolo_colsum", g0.view(), self.g[f"myolo_mask_conv{i}/bias"], self.ws, st)
+            C.call("myolo_conv3x3_wgrad", self.ma[i - 1].rows, g0.rows, self.g[f"myolo_mask_conv{i}/kernel"], n, P_, P_,
+                   MASK_C, MASK_C, st)
+            C.call("myolo_conv3x3_dgrad", g0.rows, self.p[f"myolo_mask_conv{i}/kernel"], g1.rows, n, P_, P_, MASK_C,
+                   MASK_C, st)
+            g0, g1 = g1, g0
+        # CropAndResizeGradImage into the feature-map gradient
+        self.dfeat.storage.zero_()
+        C.call("myolo_roialign_bwd", g0.view(), A["rois"], n, self.R, P_, self.dfeat.view(), st)
+        C.call("myolo_colsum", self.dfeat.view(), self.g["feature_map/bias"], self.ws, st)
+        C.call("myolo_conv3x3_wgrad", self.c4.rows, self.dfeat.rows, self.g["feature_map/kernel"], B, F_, F_, 512, MASK_C, st)
+        C.call("myolo_conv3x3_dgrad", self.dfeat.rows, self.p["feature_map/kernel"], self.dc4.rows, B, F_, F_, 512, MASK_C, st)
+
+    # ------------------------------------------------------------------ optimizer
+    def apply_updates(self, lr: float = 1e-3, grad_scale: float = 1.0):
+        """Keras Adam (model.py:1071-1075: lr, beta_1 0.9, beta_2 0.999, epsilon 1e-8, no decay) over
+        the flat buffers, then the Keras BN moving-average update (momentum 0.99, TF zero-debias)."""
+        st = self._st()
+        self.t += 1
+        b1, b2 = 0.9, 0.999
+        lr_t = lr * math.sqrt(1.0 - b2 ** self.t) / (1.0 - b1 ** self.t)
+        if self._frozen:
+            self.grads.mul_(self.trainable_mask)        # set_trainable(): frozen variables get no update
+        C.call("myolo_adam_step", self.params, self.grads, self.adam_m, self.adam_v, self.n_flat, lr_t, b1, b2, 1e-8,
+               grad_scale, st)
+        for b, npix in self._bn_touched:
+            b.step += 1
+            C.call("myolo_bn_moving_update", b.mean, b.bmean, b.mmean, b.c, BN_MOMENTUM, b.step, 0, float(npix), BN_EPS, st)
+            C.call("myolo_bn_moving_update", b.var, b.bvar, b.mvar, b.c, BN_MOMENTUM, b.step, 1, float(npix), BN_EPS, st)
+        self._bn_touched = []
+        self.refresh_weights()
+
+    def train_step(self, inputs, lr: float = 1e-3, allreduce=None):
+        """One fit step.  `allreduce(flat_grads, lo, hi)` (optional) sums gradient slices across
+        replicas; it is called for the tail bucket as soon as it is ready and for the head at the end."""
+        out = self.forward_training(inputs)
+        if allreduce is None:
+            self.backward()
+            scale = 1.0
+        else:
+            self.backward(on_tail_ready=lambda: allreduce(self.grads, self.tail_off, self.n_flat))
+            scale = allreduce(self.grads, 0, self.tail_off)
+        self.apply_updates(lr, scale if scale is not None else 1.0)
+        return out

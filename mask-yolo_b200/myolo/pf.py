@@ -24,11 +24,14 @@ def guard_rows(W: int) -> int:
 class PF:
     """Owns a zero-initialised PF buffer.  .rows is the [M, C] matrix (M = n*(H+1)*(W+1))."""
 
-    def __init__(self, n, H, W, C, device="cuda", storage=None):
+    def __init__(self, n, H, W, C, device="cuda", storage=None, split=False):
+        """split=True allocates a second copy (the tf32 low part of a 3xTF32 operand) `lo_off` rows
+        after the first, separated by zero guard rows: [guard | rows | guard | rows_lo | guard]."""
         self.n, self.H, self.W, self.C = n, H, W, C
         self.M = n * (H + 1) * (W + 1)
         g = guard_rows(W)
-        total = (self.M + 2 * g) * C
+        copies = 2 if split else 1
+        total = (copies * (self.M + g) + g) * C
         if storage is None:
             storage = torch.zeros(total, dtype=torch.float32, device=device)
         else:
@@ -36,12 +39,15 @@ class PF:
             storage = storage[:total]
         self.storage = storage
         self.rows = storage[g * C:(g + self.M) * C].view(self.M, C)
+        self.lo_off = self.M + g if split else 0
+        self.rows_lo = storage[(g + self.lo_off) * C:(g + self.lo_off + self.M) * C].view(self.M, C) if split else None
 
-    def view(self) -> _cabi.View:
+    def view(self, lo=False) -> _cabi.View:
         """C-ABI view of the valid pixels: pixel (0,0) of tile 0 sits (W+1)+1 rows in."""
         W, H, C = self.W, self.H, self.C
         off = ((W + 1) + 1) * C
-        return _cabi.View(self.rows.data_ptr() + 4 * off, (H + 1) * (W + 1) * C, (W + 1) * C, self.n, H, W, C)
+        base = (self.rows_lo if lo else self.rows).data_ptr()
+        return _cabi.View(base + 4 * off, (H + 1) * (W + 1) * C, (W + 1) * C, self.n, H, W, C)
 
     def valid(self) -> torch.Tensor:
         """[n,H,W,C] strided torch view of the valid pixels (no copy)."""

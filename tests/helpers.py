@@ -1,0 +1,82 @@
+"""Shared builders for the model-level parity tests, smoke() and bench.py's cpu_baseline leg:
+synthetic Shapes-like batches in the exact format BatchGenerator yields, and the
+oracle-side config dict."""
+import numpy as np
+import torch
+
+
+def engine_cfg(S=64, NB=3, NC=4, TB=5, anchors=None, maxgt=4):
+    G = S // 32
+    anchors = anchors if anchors is not None else [0.5, 0.6, 0.9, 0.8, 1.2, 1.3, 1.6, 1.5, 0.4, 1.0][:2 * NB]
+    return dict(S=S, G=G, NB=NB, NC=NC, TB=TB, MAXGT=maxgt, R=G * G * NB, ANCHORS=list(anchors), POOL=14,
+                MASK_SHAPE=[28, 28], OBJECT_SCALE=5.0, NO_OBJECT_SCALE=1.0, COORD_SCALE=1.0, CLASS_SCALE=1.0,
+                CLASS_WEIGHTS=np.ones(NC, dtype="float32"), WARM_UP_BATCHES=0,
+                LOSS_WEIGHTS={"yolo_sum_loss": 1.0, "myolo_mask_loss": 1.0})
+
+
+def oracle_cfg(c):
+    return dict(GRID_H=c["G"], GRID_W=c["G"], N_BOX=c["NB"], NUM_CLASSES=c["NC"], ANCHORS=c["ANCHORS"],
+                TRAIN_ROIS_PER_IMAGE=c["R"], MASK_SHAPE=c["MASK_SHAPE"], MASK_POOL_SIZE=c["POOL"],
+                COORD_SCALE=c["COORD_SCALE"], NO_OBJECT_SCALE=c["NO_OBJECT_SCALE"], OBJECT_SCALE=c["OBJECT_SCALE"],
+                CLASS_SCALE=c["CLASS_SCALE"], CLASS_WEIGHTS=c["CLASS_WEIGHTS"], WARM_UP_BATCHES=c["WARM_UP_BATCHES"],
+                TRUE_BOX_BUFFER=c["TB"], LOSS_WEIGHTS=c["LOSS_WEIGHTS"])
+
+
+def batch_from_boxes(c, B, image, boxes_norm, seed):
+    """Training inputs whose GT instances are ellipses inscribed in the given normalised boxes
+    (list per image of (x1,y1,x2,y2)); the YOLO target / true-box buffer are encoded like
+    BatchGenerator.__getitem__ does (myolo_utils.py:769-820)."""
+    rng = np.random.RandomState(seed)
+    S, G, NB, NC, TB, M = c["S"], c["G"], c["NB"], c["NC"], c["TB"], c["MAXGT"]
+    ids = np.zeros((B, M), np.int32)
+    gtb = np.zeros((B, M, 4), np.float32)
+    masks = np.zeros((B, S, S, M), np.uint8)
+    yt = np.zeros((B, G, G, NB, 5 + NC), np.float32)
+    tb = np.zeros((B, 1, 1, 1, TB, 4), np.float32)
+    yy, xx = np.mgrid[0:S, 0:S]
+    anc = np.asarray(c["ANCHORS"], np.float32).reshape(NB, 2)
+    for b in range(B):
+        for m, bx in enumerate(boxes_norm[b][:M]):
+            x1, y1, x2, y2 = [float(np.clip(v, 0.0, 1.0)) * (S - 1) for v in bx]
+            x1, y1, x2, y2 = int(round(x1)), int(round(y1)), int(round(x2)) + 1, int(round(y2)) + 1
+            if x2 - x1 < 3 or y2 - y1 < 3:
+                continue
+            cx, cy, rx, ry = (x1 + x2 - 1) / 2.0, (y1 + y2 - 1) / 2.0, (x2 - x1) / 2.0, (y2 - y1) / 2.0
+            mk = ((xx - cx) / rx) ** 2 + ((yy - cy) / ry) ** 2 <= 1.0
+            mk[y1, x1:x2] = True; mk[y2 - 1, x1:x2] = True; mk[y1:y2, x1] = True; mk[y1:y2, x2 - 1] = True
+            masks[b, :, :, m] = mk
+            gtb[b, m] = [x1, y1, x2, y2]
+            cls = rng.randint(1, NC)
+            ids[b, m] = cls
+            gcx, gcy = 0.5 * (x1 + x2) / (S / G), 0.5 * (y1 + y2) / (S / G)
+            gw, gh = (x2 - x1) / (S / G), (y2 - y1) / (S / G)
+            gx_, gy_ = int(gcx), int(gcy)
+            if gx_ < G and gy_ < G:
+                inter = np.minimum(anc[:, 0], gw) * np.minimum(anc[:, 1], gh)
+                iou = inter / (anc[:, 0] * anc[:, 1] + gw * gh - inter)
+                a = int(np.argmax(iou))
+                yt[b, gy_, gx_, a, :5] = [gcx, gcy, gw, gh, 1.0]
+                yt[b, gy_, gx_, a, 5:] = 0
+                yt[b, gy_, gx_, a, 5 + cls] = 1
+                tb[b, 0, 0, 0, m % TB] = [gcx, gcy, gw, gh]
+    return [torch.as_tensor(image), torch.tensor(tb), torch.tensor(yt), torch.tensor(ids), torch.tensor(gtb),
+            torch.tensor(masks)]
+
+
+def random_boxes(B, n, seed):
+    rng = np.random.RandomState(seed)
+    out = []
+    for b in range(B):
+        c = rng.rand(n, 2) * 0.6 + 0.2
+        wh = rng.rand(n, 2) * 0.3 + 0.15
+        out.append(np.concatenate([c - wh / 2, c + wh / 2], 1).tolist())
+    return out
+
+
+def to_oracle_inputs(inputs):
+    image, tb, yt, ids, gtb, masks = inputs
+    return [image, tb, yt, ids, gtb, masks.bool()]
+
+
+def to_device(inputs, dev="cuda"):
+    return [t.contiguous().to(dev) for t in inputs]
