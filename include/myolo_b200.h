@@ -160,10 +160,12 @@ int myolo_yolo_decode(const float* y_pred, const float* anchors, float* boxes, f
 
 /* ---- K13: DetectMaskTargetLayer, myolo/model.py:457-602 (+ norm_boxes_graph 1394-1408) ----
  * gt_boxes are PIXEL (x1,y1,x2,y2) as fed to the model; normalisation happens inside.
+ * gt_class_ids [B,M], gt_boxes [B,M,4] (M = TRUE_BOX_BUFFER columns as BatchGenerator pads them),
+ * gt_masks [B,S,S,MM] bytes (MM = MAX_GT_INSTANCES channels).
  * Outputs: rois [B,R,4], target_ids [B,R] int32, target_masks [B,R,MH,MW], n_pos [B] int32,
  * roi_src [B,R] int32 (source proposal index, -1 for padding), roi_gt [B,R] int32 (matched GT, -1). */
 int myolo_detect_mask_targets(const float* proposals, const int* gt_class_ids, const float* gt_boxes,
-                              const unsigned char* gt_masks, int B, int R, int M, int S, int MH, int MW,
+                              const unsigned char* gt_masks, int B, int R, int M, int MM, int S, int MH, int MW,
                               float* rois, int* target_ids, float* target_masks, int* n_pos,
                               int* roi_src, int* roi_gt, myolo_stream stream);
 

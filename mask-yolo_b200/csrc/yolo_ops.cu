@@ -156,6 +156,7 @@ detect_targets_kernel(const float* __restrict__ proposals, const int* __restrict
 __global__ void mask_targets_kernel(const float* __restrict__ rois, const int* __restrict__ roi_gt,
                                     const int* __restrict__ n_pos, const unsigned char* __restrict__ gt_masks, int R,
                                     int M, int S, int MH, int MW, float* __restrict__ out) {
+  // M here = number of mask channels (MAX_GT_INSTANCES); a matched GT index beyond it has no mask
   const int j = blockIdx.x, b = blockIdx.y;
   const int t = threadIdx.x;
   if (t >= MH * MW) return;
@@ -167,7 +168,7 @@ __global__ void mask_targets_kernel(const float* __restrict__ rois, const int* _
   const Sample sy = crop_coord(bx.y, bx.w, y, MH, S);
   const Sample sx = crop_coord(bx.x, bx.z, x, MW, S);
   float v = 0.f;
-  if (sy.valid && sx.valid) {
+  if (sy.valid && sx.valid && g >= 0 && g < M) {
     const unsigned char* mb = gt_masks + (size_t)b * S * S * M + g;
     const float tl = mb[((size_t)sy.lo * S + sx.lo) * M] ? 1.f : 0.f;
     const float tr = mb[((size_t)sy.lo * S + sx.hi) * M] ? 1.f : 0.f;
@@ -442,18 +443,18 @@ extern "C" int myolo_yolo_decode(const float* y_pred, const float* anchors, floa
 }
 
 extern "C" int myolo_detect_mask_targets(const float* proposals, const int* gt_class_ids, const float* gt_boxes,
-                                         const unsigned char* gt_masks, int B, int R, int M, int S, int MH, int MW,
+                                         const unsigned char* gt_masks, int B, int R, int M, int MM, int S, int MH, int MW,
                                          float* rois, int* target_ids, float* target_masks, int* n_pos, int* roi_src,
                                          int* roi_gt, myolo_stream stream) {
   MYOLO_CHECK_ARG(proposals && gt_class_ids && gt_boxes && gt_masks && rois && target_ids && target_masks && n_pos && roi_src && roi_gt);
-  MYOLO_CHECK_ARG(B > 0 && R > 0 && M > 0 && M <= kMaxGT && S > 1 && MH > 0 && MW > 0 && MH * MW <= 1024);
+  MYOLO_CHECK_ARG(B > 0 && R > 0 && M > 0 && M <= kMaxGT && MM > 0 && S > 1 && MH > 0 && MW > 0 && MH * MW <= 1024);
   const size_t smem = (size_t)3 * R * sizeof(int);
   MYOLO_CHECK_ARG(smem <= 40 * 1024);
   cudaStream_t st = as_stream(stream);
   detect_targets_kernel<<<B, 256, smem, st>>>(proposals, gt_class_ids, gt_boxes, R, M, S, rois, target_ids, n_pos, roi_src, roi_gt);
   dim3 grid(R, B);
   const int threads = ((MH * MW + 31) / 32) * 32;
-  mask_targets_kernel<<<grid, threads, 0, st>>>(rois, roi_gt, n_pos, gt_masks, R, M, S, MH, MW, target_masks);
+  mask_targets_kernel<<<grid, threads, 0, st>>>(rois, roi_gt, n_pos, gt_masks, R, MM, S, MH, MW, target_masks);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }

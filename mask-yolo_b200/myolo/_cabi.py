@@ -101,10 +101,21 @@ def _conv(x):
     return x
 
 
+# device kernels launched per entry point (anything not listed launches exactly one); bench.py reports
+# the sum over the timed region as `gpu_launches`
+KERNELS_PER_CALL = {"myolo_bn_stats": 4, "myolo_bn_bwd": 3, "myolo_colsum": 2, "myolo_detect_mask_targets": 2,
+                    "myolo_mask_loss": 3, "myolo_yolo_loss": 3, "myolo_version": 0, "myolo_last_error": 0,
+                    "myolo_device_check": 0, "myolo_set_precision": 0, "myolo_get_precision": 0,
+                    "myolo_gemm_taps_tc_supported": 0, "myolo_gemm_taps_wgrad_tc_supported": 0}
+launch_count = 0
+
+
 def call(name: str, *args):
     """Invoke a C-ABI entry point; tensors -> device pointers; nonzero status -> MyoloError."""
+    global launch_count
     l = lib()
     fn = getattr(l, name)
+    launch_count += KERNELS_PER_CALL.get(name, 1)
     keep = args                             # keep Views / arrays alive across the call
     rc = fn(*[_conv(a) for a in args])
     del keep

@@ -120,6 +120,7 @@ class Engine:
         self.with_mask = mode != "yolo"
         self._frozen = False
         self._shift_cache = {}
+        self.kernel_events = None      # bench.py: list collecting (start, end) CUDA events of the dominant kernel
         self.t = 0                     # Adam iteration
         self.seen = 0                  # yolo_custom_loss `seen` counter (model.py:95, 197)
         self._alloc_params(params if params is not None else init_params(self.NB, self.NC, seed))
@@ -337,8 +338,15 @@ class Engine:
         arr = self._shift_cache.get(key)
         if arr is None:
             arr = self._shift_cache[key] = C.int_array(sh)
+        timed = self.kernel_events is not None and name.startswith("myolo_mask_conv")
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         C.call("myolo_gemm_taps", a_rows, K, self.wt[name], out_rows, N, M, N, K, len(sh), arr, bias, None, None,
                C.ACT_NONE, pf_w1, pf_blk, 0, self._st())
+        if timed:
+            e1.record()
+            self.kernel_events.append((e0, e1))
 
     def _bn_bwd(self, name, xv, dyv, act, training):
         b = self.bn[name]
@@ -453,7 +461,8 @@ class Engine:
             M = gt_ids.shape[1]
             mh, mw = cfg["MASK_SHAPE"]
             assert gt_ids.dtype == torch.int32 and gt_boxes.dtype == torch.float32 and gt_masks.dtype in (torch.uint8, torch.bool)
-            C.call("myolo_detect_mask_targets", A["proposals"], gt_ids, gt_boxes, gt_masks, B, R, M, cfg["S"], mh, mw,
+            C.call("myolo_detect_mask_targets", A["proposals"], gt_ids, gt_boxes, gt_masks, B, R, M, gt_masks.shape[3],
+                   cfg["S"], mh, mw,
                    A["rois"], self.target_ids, A["target_masks"], self.n_pos, self.roi_src, self.roi_gt, st)
             masks = self.mask_head(A["rois"], training=True)
             C.call("myolo_mask_loss", A["masks"], A["target_masks"], self.target_ids, self.n_roi, mh, mw, NC,

@@ -1,0 +1,472 @@
+"""Mask-YOLO model API on the B200 engine.
+
+Same public surface as the reference's myolo/model.py -- `MaskYOLO(mode, config, model_dir,
+yolo_pretrain_dir, yolo_trainable)` with `.keras_model`, `.train`, `.compile`, `.set_trainable`,
+`.load_weights`, `.infer_yolo`, `.detect`, `.decode_masks`, and the module-level layer/graph names
+(`PyramidROIAlign`, `DetectMaskTargetLayer`, `DecodeYOLOLayer`, `DetectionsLayer`,
+`yolo_custom_loss`, `myolo_mask_loss_graph`, ...) -- but nothing here builds a Keras graph: every
+name is an operator over device tensors that calls the hand-written sm_100a kernels through the C
+ABI (include/myolo_b200.h), and `MaskYOLO` drives `myolo.engine.Engine`, which owns all HBM buffers.
+There is no CPU path: constructing a model without an sm_100 GPU raises.
+"""
+from __future__ import annotations
+
+import datetime
+import os
+import re
+import time
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import _cabi as C
+from . import myolo_utils as mutils
+from .config import Config, resolve
+from .engine import Engine, init_params, param_specs, MASK_C
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32(t):
+    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# operators (reference: the Keras layers / graph functions of myolo/model.py)
+# ------------------------------------------------------------------------------------------------
+def relu6(x):
+    """model.py:38-39.  Elementwise utility (the engine fuses ReLU6 into its BN-apply kernel)."""
+    return torch.clamp(x, 0.0, 6.0)
+
+
+def norm_boxes_graph(boxes, shape):
+    """Pixel (x1,y1,x2,y2) -> normalised: (box - [0,0,1,1]) / ([s0,s1,s0,s1] - 1)  (model.py:1394-1408)."""
+    s0, s1 = float(shape[0]), float(shape[1])
+    scale = torch.tensor([s0, s1, s0, s1], dtype=boxes.dtype, device=boxes.device) - 1.0
+    shift = torch.tensor([0.0, 0.0, 1.0, 1.0], dtype=boxes.dtype, device=boxes.device)
+    return (boxes - shift) / scale
+
+
+def trim_zeros_graph(boxes, name=None):
+    """Drop all-zero rows; returns (boxes, keep mask)  (model.py:1411-1420)."""
+    keep = boxes.abs().sum(1) != 0
+    return boxes[keep], keep
+
+
+def overlaps_graph(boxes1, boxes2):
+    """IoU matrix [N1, N2] of (x1,y1,x2,y2) boxes  (model.py:420-454)."""
+    a, b = boxes1[:, None, :], boxes2[None, :, :]
+    iw = (torch.minimum(a[..., 2], b[..., 2]) - torch.maximum(a[..., 0], b[..., 0])).clamp(min=0)
+    ih = (torch.minimum(a[..., 3], b[..., 3]) - torch.maximum(a[..., 1], b[..., 1])).clamp(min=0)
+    inter = iw * ih
+    union = (a[..., 3] - a[..., 1]) * (a[..., 2] - a[..., 0]) + (b[..., 3] - b[..., 1]) * (b[..., 2] - b[..., 0]) - inter
+    return inter / union
+
+
+class _Layer(object):
+    def __call__(self, inputs):
+        return self.call(inputs)
+
+
+class DecodeYOLOLayer(_Layer):
+    """yolo_output [B,G,G,NB,5+NC] -> proposals [B, G*G*NB, (x1,y1,x2,y2)] normalised  (model.py:1429-1476)."""
+
+    def __init__(self, name=None, config=None, **kwargs):
+        self.name, self.cfg = name, resolve(config)
+
+    def call(self, inputs):
+        y = _f32(inputs[0] if isinstance(inputs, (list, tuple)) else inputs)
+        B, G, NB, NC = y.shape[0], self.cfg["G"], self.cfg["NB"], self.cfg["NC"]
+        out = torch.empty(B, G * G * NB, 4, device=y.device)
+        anchors = torch.tensor(self.cfg["ANCHORS"], dtype=torch.float32, device=y.device)
+        C.call("myolo_yolo_decode", y, anchors, out, None, B, G, G, NB, NC, _stream())
+        return out
+
+    def compute_output_shape(self, input_shape):
+        return (None, self.cfg["R"], 4)
+
+
+class DetectionsLayer(_Layer):
+    """yolo_output -> [B, R, (x1,y1,x2,y2, sigmoid(conf), argmax class)]  (model.py:1479-1541)."""
+
+    def __init__(self, name=None, config=None, **kwargs):
+        self.name, self.cfg = name, resolve(config)
+
+    def call(self, inputs):
+        y = _f32(inputs[0] if isinstance(inputs, (list, tuple)) else inputs)
+        B, G, NB, NC = y.shape[0], self.cfg["G"], self.cfg["NB"], self.cfg["NC"]
+        det = torch.empty(B, G * G * NB, 6, device=y.device)
+        anchors = torch.tensor(self.cfg["ANCHORS"], dtype=torch.float32, device=y.device)
+        C.call("myolo_yolo_decode", y, anchors, None, det, B, G, G, NB, NC, _stream())
+        return det
+
+    def compute_output_shape(self, input_shape):
+        return (None, self.cfg["R"], 6)
+
+
+class PyramidROIAlign(_Layer):
+    """Single-level ROIAlign = crop_and_resize(feature_map, boxes, box->image index, pool_shape)
+    (model.py:299-413).  boxes [B,R,4] are handed to the sampler as they are, i.e. (x1,y1,x2,y2) read
+    as (y1,x1,y2,x2) -- the reference's behaviour.  Returns [B,R,P,P,C]."""
+
+    def __init__(self, pool_shape, **kwargs):
+        self.pool_shape = tuple(pool_shape)
+        assert self.pool_shape[0] == self.pool_shape[1]
+
+    def call(self, inputs):
+        boxes, feat = _f32(inputs[0]), _f32(inputs[1])
+        B, R = boxes.shape[0], boxes.shape[1]
+        Fh, Fw, Cc = feat.shape[1], feat.shape[2], feat.shape[3]
+        P = self.pool_shape[0]
+        out = torch.empty(B * R, P, P, Cc, device=feat.device)
+        C.call("myolo_roialign_fwd", C.view(feat, B, Fh, Fw, Cc), boxes, B * R, R, P, C.view(out, B * R, P, P, Cc), 0,
+               _stream())
+        return out.view(B, R, P, P, Cc)
+
+    def compute_output_shape(self, input_shape):
+        return input_shape[0][:2] + self.pool_shape + (input_shape[1][-1],)
+
+
+class DetectMaskTargetLayer(_Layer):
+    """proposals + ground truth -> (rois, target_class_ids, None, target_mask)  (model.py:605-661,
+    detect_mask_target_graph 457-602).  gt_boxes are PIXEL (x1,y1,x2,y2) as the model input carries
+    them: norm_boxes_graph (model.py:819-820) is fused into the kernel."""
+
+    def __init__(self, config, **kwargs):
+        self.config, self.cfg = config, resolve(config)
+
+    def call(self, inputs):
+        props, ids, boxes, masks = inputs
+        props, boxes = _f32(props), _f32(boxes)
+        ids = ids.int().contiguous()
+        masks = masks.to(torch.uint8).contiguous()
+        B, R = props.shape[0], props.shape[1]
+        mh, mw = self.cfg["MASK_SHAPE"]
+        dev = props.device
+        rois = torch.empty(B, R, 4, device=dev)
+        tids = torch.empty(B, R, dtype=torch.int32, device=dev)
+        tmask = torch.empty(B, R, mh, mw, device=dev)
+        scratch = [torch.empty(B, dtype=torch.int32, device=dev)] + [torch.empty(B, R, dtype=torch.int32, device=dev) for _ in range(2)]
+        C.call("myolo_detect_mask_targets", props, ids, boxes, masks, B, R, ids.shape[1], masks.shape[3], self.cfg["S"],
+               mh, mw, rois, tids, tmask, scratch[0], scratch[1], scratch[2], _stream())
+        return [rois, tids, None, tmask]
+
+
+def detect_mask_target_graph(proposals, gt_class_ids, gt_boxes, gt_masks, config):
+    """One image (model.py:457-602): thin wrapper over the batched kernel."""
+    r = DetectMaskTargetLayer(config).call([proposals[None], gt_class_ids[None], gt_boxes[None], gt_masks[None]])
+    return r[0][0], r[1][0], None, r[3][0]
+
+
+def yolo_custom_loss(y_true, y_pred, true_boxes, config=None):
+    """YOLOv2 loss of model.py:86-242 (xy + wh + conf + class), scalar device tensor."""
+    cfg = resolve(config if config is not None else Config())
+    y_true, y_pred, tb = _f32(y_true), _f32(y_pred), _f32(true_boxes)
+    B, G, NB, NC, TB = y_pred.shape[0], cfg["G"], cfg["NB"], cfg["NC"], cfg["TB"]
+    dev = y_pred.device
+    out = torch.empty(5, device=dev)
+    ws = torch.zeros(8, dtype=torch.float64, device=dev)
+    sc = C.float_array([cfg["OBJECT_SCALE"], cfg["NO_OBJECT_SCALE"], cfg["COORD_SCALE"], cfg["CLASS_SCALE"]])
+    C.call("myolo_yolo_loss", y_true, y_pred, tb, torch.tensor(cfg["ANCHORS"], dtype=torch.float32, device=dev),
+           torch.tensor(cfg["CLASS_WEIGHTS"], device=dev), B, G, G, NB, NC, TB, sc, 0, 1.0, out, None, ws, _stream())
+    return out[0]
+
+
+def myolo_mask_loss_graph(target_masks, target_class_ids, pred_masks):
+    """Binary cross-entropy over the positive ROIs' class-specific masks (model.py:718-754)."""
+    pm = _f32(pred_masks)
+    n = pm.shape[0] * pm.shape[1]
+    mh, mw, nc = pm.shape[2], pm.shape[3], pm.shape[4]
+    out = torch.empty(1, device=pm.device)
+    ws = torch.zeros(2, dtype=torch.float64, device=pm.device)
+    C.call("myolo_mask_loss", pm, _f32(target_masks), target_class_ids.int().contiguous(), n, mh, mw, nc, 1.0, out, None,
+           ws, _stream())
+    return out[0]
+
+
+def conv_block(engine, inputs):
+    """model.py:42-52 on the engine's parameters: first conv + BN + ReLU6 (inference-mode BN)."""
+    engine.forward(inputs, training=False)
+    return engine.A["a0"]
+
+
+def mobilenet_graph(engine, input_image, training=False):
+    """Truncated MobileNet-v1 backbone -> C4 [B,S/8,S/8,512]  (model.py:55-79)."""
+    engine.forward(input_image, training=training)
+    return engine.c4.dense() if engine.with_mask and not engine.x3 else engine.A["ap6"]
+
+
+def yolo_branch_graph(engine, input_image, training=False):
+    """Backbone + YOLO branch -> [B,G,G,NB,5+NC]  (model.py:249-278)."""
+    return engine.forward(input_image, training=training)
+
+
+def build_yolo_model(config, depth=None, batch=None):
+    """The nested 'yolo_model' of the reference (model.py:281-292) as an engine in mode 'yolo'."""
+    return Engine(resolve(config), batch or config.BATCH_SIZE, "yolo")
+
+
+def build_mask_graph(engine, rois, training=False):
+    """Mask head on [B,R,4] rois -> [B,R,28,28,NC] sigmoid masks  (model.py:668-715).  Uses the
+    feature map left in the engine by the preceding backbone pass."""
+    return engine.mask_head(_f32(rois), training)
+
+
+# ------------------------------------------------------------------------------------------------
+# keras_model-like handle
+# ------------------------------------------------------------------------------------------------
+class _ModelHandle(object):
+    """What `MaskYOLO.keras_model` exposes: predict / train_on_batch / test_on_batch / summary /
+    get_weights-by-name, over the engine."""
+
+    def __init__(self, owner: "MaskYOLO"):
+        self._o = owner
+        self.metrics_names = ["loss", "yolo_sum_loss", "myolo_mask_loss"] if owner.mode == "training" else ["loss", "yolo_sum_loss"]
+        self.name = {"training": "mask+yolo", "yolo": "only_yolo", "inference": "mask_yolo_inference"}[owner.mode]
+
+    def predict(self, inputs, batch_size=None, verbose=0):
+        return self._o._predict(inputs)
+
+    def train_on_batch(self, inputs, targets=None):
+        return self._o._train_on_batch(inputs)
+
+    def test_on_batch(self, inputs, targets=None):
+        return self._o._train_on_batch(inputs, update=False)
+
+    def summary(self):
+        lines = ["Model: %s" % self.name]
+        total = trainable = 0
+        for name, shape, tr in self._o.engine.specs:
+            n = int(np.prod(shape))
+            total += n
+            trainable += n if tr else 0
+            lines.append("  %-40s %-20s %10d%s" % (name, tuple(shape), n, "" if tr else "  (non-trainable)"))
+        lines.append("Total params: %d  Trainable: %d  Non-trainable: %d" % (total, trainable, total - trainable))
+        return "\n".join(lines)
+
+    def get_weights(self):
+        return self._o.engine.state_dict()
+
+    def save_weights(self, path):
+        torch.save(self._o.engine.state_dict(), path)
+
+    def load_weights(self, path, by_name=False):
+        self._o.load_weights(path, by_name=by_name)
+
+
+# ------------------------------------------------------------------------------------------------
+# MaskYOLO
+# ------------------------------------------------------------------------------------------------
+class MaskYOLO:
+    """MobileNet backbone + YOLOv2 head + Mask R-CNN-style mask branch (model.py:761-1391)."""
+
+    def __init__(self, mode, config, model_dir=None, yolo_pretrain_dir=None, yolo_trainable=True,
+                 precision: Optional[str] = None, device: int = 0, seed: int = 0):
+        assert mode in ['training', 'inference', 'yolo']
+        self.mode = mode
+        self.config = config
+        self.model_dir = model_dir
+        self.yolo_pretrain_dir = yolo_pretrain_dir
+        self.yolo_trainable = yolo_trainable
+        self.precision = precision or os.environ.get("MYOLO_PRECISION", "tf32x3")
+        self.device, self.seed = device, seed
+        self.learning_rate = getattr(config, "LEARNING_RATE", 1e-3)
+        self.allreduce = None                    # set by myolo.ddp.attach() for data-parallel training
+        self.keras_model = self.build(mode=mode, config=config)
+        self.epoch = 0
+
+    # ---- construction
+    def build(self, mode, config):
+        assert mode in ['training', 'inference', 'yolo']
+        w, h = config.IMAGE_SHAPE[:2]
+        if w % 32 != 0 or h % 32 != 0:
+            raise Exception("Image size must be dividable by 32 to adapt with YOLO framework. "
+                            "For example, use 224, 256, 288, 320, 356, ... etc. ")
+        self.cfg = resolve(config)
+        batch = int(config.BATCH_SIZE) if mode != "inference" else int(getattr(config, "BATCH_SIZE", 1))
+        self.engine = Engine(self.cfg, batch, mode, self.precision, self.device, seed=self.seed)
+        self._stage_bufs = None
+        if self.yolo_pretrain_dir is not None:
+            self.load_weights(self.yolo_pretrain_dir, by_name=True)
+            if not self.yolo_trainable:           # model.py:854-868: freeze the pretrained yolo branch
+                self.engine.set_trainable(lambda n: n.startswith(("feature_map", "myolo_mask")))
+        return _ModelHandle(self)
+
+    # ---- host <-> device staging (pinned buffers, one async copy per input)
+    def _stage(self, inputs: List[np.ndarray]):
+        want = [torch.float32, torch.float32, torch.float32, torch.int32, torch.float32, torch.uint8]
+        if self._stage_bufs is None or any(tuple(b[0].shape) != tuple(np.shape(x)) for b, x in zip(self._stage_bufs, inputs)) \
+                or len(self._stage_bufs) != len(inputs):
+            self._stage_bufs = []
+            for x, dt in zip(inputs, want):
+                host = torch.empty(tuple(np.shape(x)), dtype=dt).pin_memory()
+                self._stage_bufs.append((host, torch.empty_like(host, device=self.engine.dev)))
+        out, nbytes = [], 0
+        for (host, devt), x in zip(self._stage_bufs, inputs):
+            if isinstance(x, torch.Tensor):
+                host.copy_(x)
+            else:
+                host.copy_(torch.from_numpy(np.ascontiguousarray(x)))
+            devt.copy_(host, non_blocking=True)
+            nbytes += host.numel() * host.element_size()
+            out.append(devt)
+        self.last_h2d_bytes = nbytes
+        return out
+
+    def _train_on_batch(self, inputs, update=True, lr=None):
+        dev_inputs = self._stage(inputs)
+        eng = self.engine
+        if update:
+            out = eng.train_step(dev_inputs, lr if lr is not None else self.learning_rate, self.allreduce)
+        else:
+            out = eng.forward_training(dev_inputs)
+        res = [out["yolo_sum_loss"]] + ([out["mask_loss"]] if "mask_loss" in out else [])
+        vals = torch.stack(res).cpu().tolist()           # device -> host read of the step's losses
+        self.last_d2h_bytes = 4 * len(vals)
+        lw = self.cfg["LOSS_WEIGHTS"]
+        total = vals[0] * lw.get("yolo_sum_loss", 1.0) + (vals[1] * lw.get("myolo_mask_loss", 1.0) if len(vals) > 1 else 0.0)
+        self.last_outputs = out
+        return [total] + vals
+
+    def _predict(self, inputs):
+        image = inputs[0] if isinstance(inputs, (list, tuple)) else inputs
+        img = torch.as_tensor(np.ascontiguousarray(image), dtype=torch.float32).pin_memory().to(self.engine.dev, non_blocking=True)
+        eng = self.engine
+        if self.mode == "inference":
+            yolo, det, masks = eng.forward_inference(img)
+            return [yolo.cpu().numpy(), det.cpu().numpy(), masks.cpu().numpy()]
+        yolo = eng.forward(img, training=False)
+        return [yolo.cpu().numpy()]
+
+    # ---- training API
+    def compile(self, learning_rate, momentum=None):
+        """Adam(lr, beta_1 0.9, beta_2 0.999, epsilon 1e-8) over LOSS_WEIGHTS-weighted losses
+        (model.py:1062-1118).  `momentum` is accepted and unused, as in the reference."""
+        self.learning_rate = float(learning_rate)
+
+    def set_trainable(self, layer_regex, keras_model=None, indent=0, verbose=1):
+        """Train only the layers whose Keras name fully matches layer_regex (model.py:1120-1155)."""
+        rx = re.compile(layer_regex)
+        self.engine.set_trainable(lambda name: bool(rx.fullmatch(name.split("/")[0])))
+
+    def load_weights(self, filepath, by_name=False, exclude=None):
+        """Load a checkpoint written by this package (torch.save of {keras variable name: tensor}, or an
+        .npz with the same keys).  by_name tolerates missing variables; `exclude` drops layers by name
+        (model.py:1157-1196 semantics; HDF5 needs h5py, which this build does not depend on)."""
+        if str(filepath).endswith(".npz"):
+            sd = {k: torch.from_numpy(v) for k, v in np.load(filepath).items()}
+        elif str(filepath).endswith((".h5", ".hdf5")):
+            raise ImportError("Keras HDF5 checkpoints need h5py; convert to .npz keyed by variable name")
+        else:
+            sd = torch.load(filepath, map_location="cpu")
+        if exclude:
+            sd = {k: v for k, v in sd.items() if k.split("/")[0] not in set(exclude)}
+        self.engine.load_params(sd, strict=not (by_name or exclude))
+
+    def train(self, train_dataset, val_dataset, learning_rate, epochs, layers, augmentation=None, custom_callbacks=None,
+              no_augmentation_sources=None, max_cached=(50, 6), verbose=1):
+        """fit loop of model.py:943-1060: caches the first 50 / 6 images of the datasets, builds the
+        BatchGenerators, trains `layers` with Adam and writes './saved_model_<Mon DD-HH-MM>.pt' after
+        every epoch.  Returns the per-epoch history dict."""
+        layer_regex = {"all": ".*"}
+        layers = layer_regex.get(layers, layers)
+        cfg = self.config
+        n_tr = min(max_cached[0], len(train_dataset.image_ids))
+        n_va = min(max_cached[1], len(val_dataset.image_ids)) if val_dataset is not None else 0
+        train_info = [list(mutils.load_image_gt(train_dataset, cfg, i, use_mini_mask=cfg.USE_MINI_MASK)) for i in range(n_tr)]
+        val_info = [list(mutils.load_image_gt(val_dataset, cfg, i, use_mini_mask=cfg.USE_MINI_MASK)) for i in range(n_va)]
+        gen_mode = "yolo" if self.mode == "yolo" else "training"
+        train_gen = mutils.BatchGenerator(train_info, cfg, mode=gen_mode, shuffle=True, jitter=False, norm=True)
+        val_gen = mutils.BatchGenerator(val_info, cfg, mode=gen_mode, shuffle=True, jitter=False, norm=True) if n_va else None
+        self.set_trainable(layers)
+        self.compile(learning_rate, getattr(cfg, "LEARNING_MOMENTUM", 0.9))
+        stamp = datetime.datetime.now().strftime("%b %d-%H-%M")
+        ckpt = os.path.join(self.model_dir or ".", "saved_model_" + stamp + ".pt")
+        history = {"loss": [], "yolo_sum_loss": [], "myolo_mask_loss": [], "val_loss": []}
+        B = self.engine.B
+        for ep in range(self.epoch, epochs):
+            t0, acc, nb = time.time(), np.zeros(3), 0
+            for i in range(len(train_gen)):
+                inputs, _ = train_gen[i]
+                if inputs[0].shape[0] != B:
+                    continue
+                vals = self._train_on_batch(inputs)
+                acc[:len(vals)] += vals
+                nb += 1
+            acc /= max(nb, 1)
+            vloss = float("nan")
+            if val_gen is not None:
+                vs = [self._train_on_batch(val_gen[i][0], update=False)[0] for i in range(len(val_gen)) if val_gen[i][0][0].shape[0] == B]
+                vloss = float(np.mean(vs)) if vs else float("nan")
+            for k, v in zip(("loss", "yolo_sum_loss", "myolo_mask_loss"), acc):
+                history[k].append(float(v))
+            history["val_loss"].append(vloss)
+            if verbose:
+                print("Epoch %d/%d - %.1fs - loss: %.4f - yolo_sum_loss: %.4f - myolo_mask_loss: %.4f - val_loss: %.4f"
+                      % (ep + 1, epochs, time.time() - t0, acc[0], acc[1], acc[2], vloss))
+            torch.save(self.engine.state_dict(), ckpt)
+            train_gen.on_epoch_end()
+        self.epoch = max(self.epoch, epochs)
+        return history
+
+    # ---- inference API
+    def infer_yolo(self, image, weights_dir=None, save_path=None, display=False):
+        """YOLO-only inference on one uint8 image (model.py:1198-1236): returns the decoded BoundBox
+        list after the numpy NMS of decode_one_yolo_output."""
+        assert image.dtype == np.uint8 and list(image.shape) == list(self.config.IMAGE_SHAPE)
+        if weights_dir is not None:
+            self.load_weights(weights_dir)
+        x = (image / 255.)[None].astype(np.float32)
+        netout = self._predict_b1(x)[0][0]
+        return mutils.decode_one_yolo_output(netout, self.cfg["ANCHORS"], nms_threshold=0.3, obj_threshold=0.3,
+                                             nb_class=self.cfg["NC"])
+
+    def _predict_b1(self, x):
+        if self.engine.B != 1:
+            if getattr(self, "_eng1", None) is None:
+                mode = "inference" if self.mode != "yolo" else "yolo"
+                self._eng1 = Engine(self.cfg, 1, mode, self.precision, self.device, params=self.engine.state_dict())
+            else:
+                self._eng1.load_params(self.engine.state_dict())
+            eng = self._eng1
+        else:
+            eng = self.engine
+        img = torch.from_numpy(x).to(eng.dev)
+        if eng.with_mask:
+            yolo, det, masks = eng.forward_inference(img)
+            return [yolo.cpu().numpy(), det.cpu().numpy(), masks.cpu().numpy()]
+        return [eng.forward(img, training=False).cpu().numpy()]
+
+    def detect(self, image, weights_dir=None, save_path=None, cs_threshold=0.35, display=False):
+        """Full inference on one uint8 image (model.py:1238-1328).  Returns a dict with 'rois'
+        (x1,y1,x2,y2 pixels), 'class_ids', 'scores' and boolean 'masks' [H,W,N] for the detections that
+        survive the confidence threshold and NMB; the reference's debugging overrides (hard-coded
+        indices 1306, fixed 224 scale 1307) are not reproduced."""
+        assert self.mode == "inference", "Create model in inference mode."
+        assert image.dtype == np.uint8 and list(image.shape) == list(self.config.IMAGE_SHAPE)
+        if weights_dir is not None:
+            self.load_weights(weights_dir)
+        x = (image / 255.)[None].astype(np.float32)
+        yolo, det, masks = self._predict_b1(x)
+        det, masks = det[0], masks[0]
+        order = np.argsort(det[:, 4])[::-1][:10]
+        order = [i for i in order if det[i, 4] >= cs_threshold]
+        S = self.cfg["S"]
+        keep = [order[j] for j in mutils.NMB(det[order, :4], det[order, 4])] if order else []
+        boxes = np.clip(np.round(det[keep, :4] * S), 0, S).astype(np.int32) if keep else np.zeros((0, 4), np.int32)
+        full = self.decode_masks(det[keep], masks[keep], image.shape) if keep else np.zeros(image.shape[:2] + (0,), bool)
+        return {"rois": boxes, "class_ids": det[keep, 5].astype(np.int32) if keep else np.zeros((0,), np.int32),
+                "scores": det[keep, 4] if keep else np.zeros((0,), np.float32), "masks": full}
+
+    def decode_masks(self, detections, myolo_mask, image_shape):
+        """Class-specific 28x28 masks -> full-size boolean masks pasted at their boxes (model.py:1330-1391)."""
+        S = self.cfg["S"]
+        out = []
+        for d, m in zip(detections, myolo_mask):
+            cls = int(d[5])
+            box = np.round(d[:4] * S).astype(np.int32)
+            out.append(mutils.unmold_mask(m[:, :, cls], box, image_shape))
+        return np.stack(out, -1) if out else np.zeros(tuple(image_shape[:2]) + (0,), bool)

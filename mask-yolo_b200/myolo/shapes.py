@@ -1,0 +1,120 @@
+"""Synthetic Shapes data (squares, circles, triangles on a random background), the workload of
+example/shapes/dataset_shapes.py:53-204 restated with numpy rasterisation so that the benchmark
+and the tests can generate it anywhere (no cv2 / mrcnn dependency, seeded `random.Random`).
+
+ShapesConfig mirrors dataset_shapes.py:14-50.  ShapesDataset follows the mrcnn Dataset protocol
+(load_image / load_mask / image_ids), so load_image_gt and BatchGenerator consume it unchanged."""
+import math
+import random
+
+import numpy as np
+
+from mrcnn import utils
+from .config import Config
+
+
+class ShapesConfig(Config):
+    NAME = "shapes"
+    LABELS = ['background', 'square', 'circle', 'triangle']
+    GPU_COUNT = 0
+    IMAGES_PER_GPU = 8
+    BATCH_SIZE = 16
+    NUM_CLASSES = 1 + 3
+    IMAGE_MIN_DIM = 224
+    IMAGE_MAX_DIM = 224
+    ANCHORS = [1.27273, 1.277385, 2.47446, 2.56253, 4.03843, 4.07434]
+    N_BOX = 3                                   # = len(ANCHORS)//2: what the shipped TF graph was built with
+    TRUE_BOX_BUFFER = 15
+    MAX_GT_INSTANCES = 15                       # gt ids/boxes (TRUE_BOX_BUFFER wide) and gt masks must agree (model.py:487-493)
+    CLASS_WEIGHTS = np.ones(NUM_CLASSES, dtype='float32')
+    TRAIN_ROIS_PER_IMAGE = Config.GRID_H * Config.GRID_W * N_BOX
+    USE_MINI_MASK = False
+
+
+class ShapesDataset(utils.Dataset):
+    def __init__(self, seed=None):
+        super().__init__()
+        self.rng = random.Random(seed)
+
+    def load_shapes(self, count, height, width):
+        self.add_class("shapes", 1, "square")
+        self.add_class("shapes", 2, "circle")
+        self.add_class("shapes", 3, "triangle")
+        for i in range(count):
+            bg_color, shapes = self.random_image(height, width)
+            self.add_image("shapes", image_id=i, path=None, width=width, height=height, bg_color=bg_color, shapes=shapes)
+
+    def image_reference(self, image_id):
+        info = self.image_info[image_id]
+        return info["shapes"] if info["source"] == "shapes" else super().image_reference(image_id)
+
+    @staticmethod
+    def _raster(shape, dims, h, w):
+        x, y, s = dims
+        yy, xx = np.mgrid[0:h, 0:w]
+        if shape == "square":
+            return (np.abs(xx - x) <= s) & (np.abs(yy - y) <= s)
+        if shape == "circle":
+            return (xx - x) ** 2 + (yy - y) ** 2 <= s * s
+        # triangle with apex (x, y-s) and base corners (x -+ s/sin60, y+s)
+        half = s / math.sin(math.radians(60))
+        t = (yy - (y - s)) / (2.0 * s)
+        return (t >= 0) & (t <= 1) & (np.abs(xx - x) <= half * t)
+
+    def load_image(self, image_id):
+        info = self.image_info[image_id]
+        img = np.ones([info["height"], info["width"], 3], dtype=np.uint8) * np.array(info["bg_color"], dtype=np.uint8).reshape(1, 1, 3)
+        for shape, color, dims in info["shapes"]:
+            img[self._raster(shape, dims, info["height"], info["width"])] = color
+        return img
+
+    def load_mask(self, image_id):
+        info = self.image_info[image_id]
+        shapes = info["shapes"]
+        h, w = info["height"], info["width"]
+        mask = np.zeros([h, w, len(shapes)], dtype=np.uint8)
+        for i, (shape, _, dims) in enumerate(shapes):
+            mask[:, :, i] = self._raster(shape, dims, h, w)
+        occlusion = np.logical_not(mask[:, :, -1]).astype(np.uint8) if shapes else None
+        for i in range(len(shapes) - 2, -1, -1):      # later shapes occlude earlier ones
+            mask[:, :, i] = mask[:, :, i] * occlusion
+            occlusion = np.logical_and(occlusion, np.logical_not(mask[:, :, i]))
+        class_ids = np.array([self.class_names.index(s[0]) for s in shapes], dtype=np.int32)
+        return mask.astype(bool), class_ids
+
+    def random_shape(self, height, width):
+        shape = self.rng.choice(["square", "circle", "triangle"])
+        color = tuple(self.rng.randint(0, 255) for _ in range(3))
+        buffer = 20
+        y = self.rng.randint(buffer, height - buffer - 1)
+        x = self.rng.randint(buffer, width - buffer - 1)
+        s = self.rng.randint(buffer, max(buffer, height // 4))
+        return shape, color, (x, y, s)
+
+    def random_image(self, height, width):
+        bg_color = [self.rng.randint(0, 255) for _ in range(3)]
+        shapes, boxes = [], []
+        for _ in range(self.rng.randint(1, 4)):
+            shape, color, dims = self.random_shape(height, width)
+            shapes.append((shape, color, dims))
+            x, y, s = dims
+            boxes.append([y - s, x - s, y + s, x + s])
+        keep = utils.non_max_suppression(np.array(boxes), np.arange(len(shapes)), 0.3)
+        return bg_color, [s for i, s in enumerate(shapes) if i in keep]
+
+
+def make_batches(config, n_batches, seed=1234, mode="training"):
+    """`n_batches` BatchGenerator outputs (lists of numpy arrays) of synthetic Shapes at the config's
+    IMAGE_SHAPE / BATCH_SIZE -- the benchmark's and smoke test's input source."""
+    from . import myolo_utils as mutils
+    S = int(config.IMAGE_SHAPE[0])
+    ds = ShapesDataset(seed)
+    ds.load_shapes(n_batches * config.BATCH_SIZE, S, S)
+    ds.prepare()
+    info = [list(mutils.load_image_gt(ds, config, i, use_mini_mask=False)) for i in ds.image_ids]
+    state = np.random.get_state()
+    np.random.seed(seed)
+    gen = mutils.BatchGenerator(info, config, mode=mode, shuffle=False, norm=True)
+    out = [gen[i][0] for i in range(len(gen))]
+    np.random.set_state(state)
+    return out

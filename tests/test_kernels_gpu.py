@@ -396,7 +396,7 @@ def test_detect_mask_targets_bit_exact(C):
     src = torch.empty(B, R, dtype=torch.int32, device="cuda")
     rgt = torch.empty(B, R, dtype=torch.int32, device="cuda")
     C.call("myolo_detect_mask_targets", cuda(torch.tensor(props)), cuda(torch.tensor(ids)), cuda(torch.tensor(boxes)),
-           cuda(torch.tensor(masks)), B, R, M, S, 28, 28, rd, td, md, npos, src, rgt, stream())
+           cuda(torch.tensor(masks)), B, R, M, M, S, 28, 28, rd, td, md, npos, src, rgt, stream())
     assert (tids > 0).sum() > 10, "test should exercise positives"
     assert torch.equal(td.cpu(), tids), "target class ids must be bit-exact"
     assert torch.equal(rd.cpu().view(torch.int32), rois.view(torch.int32)), "roi selection/order must be bit-exact"
