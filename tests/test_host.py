@@ -1,0 +1,117 @@
+"""Host-side mirror of the reference interface: Config resolution, the BatchGenerator /
+data_generator target encoding, box helpers, the Shapes dataset and the mrcnn shim."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from myolo import myolo_utils as mutils
+from myolo.config import Config, resolve
+from myolo.shapes import ShapesConfig, ShapesDataset, make_batches
+
+
+def test_resolve_repairs_inconsistent_inherited_fields():
+    class Broken(Config):                       # what example/shapes/dataset_shapes.py does at HEAD
+        NUM_CLASSES = 4
+        ANCHORS = [1.27273, 1.277385, 2.47446, 2.56253, 4.03843, 4.07434]
+        BATCH_SIZE = 16
+    c = resolve(Broken())
+    assert (c["NB"], c["NC"], c["R"], c["G"]) == (3, 4, 147, 7)
+    assert c["CLASS_WEIGHTS"].shape == (4,) and len(c["ANCHORS"]) == 6
+
+    class Big(Config):
+        IMAGE_SHAPE = [416, 416, 3]
+    assert resolve(Big())["G"] == 13 and resolve(Big())["R"] == 13 * 13 * 5
+    assert Config().TRAIN_ROIS_PER_IMAGE == 245 and Config.MASK_SHAPE == [28, 28]
+
+
+def test_extract_bboxes_and_iou_helpers():
+    m = np.zeros((10, 12, 3), bool)
+    m[2:5, 3:9, 0] = True
+    m[7, 11, 1] = True
+    b = mutils.extract_bboxes(m)
+    assert b.tolist() == [[3, 2, 9, 5], [11, 7, 12, 8], [0, 0, 0, 0]] and b.dtype == np.int32
+    a, c = mutils.BoundBox(0, 0, 2, 2), mutils.BoundBox(1, 1, 3, 3)
+    assert abs(mutils.bbox_iou(a, c) - 1 / 7) < 1e-12
+    assert mutils.bbox_iou(a, mutils.BoundBox(5, 5, 6, 6)) == 0
+    assert mutils._interval_overlap([0, 2], [1, 5]) == 1 and mutils._interval_overlap([3, 4], [0, 1]) == 0
+    assert mutils.NMB(np.array([[0, 0, 10, 10], [1, 1, 10, 10], [20, 20, 30, 30]]), np.array([0.9, 0.8, 0.7])) == [0, 2]
+
+
+def test_batch_generator_encoding():
+    cfg = ShapesConfig()
+    cfg.BATCH_SIZE = 2
+    S = 224
+    img = np.full((S, S, 3), 128, np.uint8)
+    mask = np.zeros((S, S, 1), bool)
+    mask[64:128, 32:96, 0] = True                      # box (32,64,96,128): centre (64,96) px = (2.0, 3.0) cells
+    info = [[img, np.array([2], np.int32), mutils.extract_bboxes(mask), mask] for _ in range(3)]
+    gen = mutils.BatchGenerator(info, cfg, mode="training", shuffle=False, norm=True)
+    assert len(gen) == 2 and gen.size() == 3
+    (images, tb, yt, ids, boxes, masks), outs = gen[1]           # last batch is filled up from the previous image
+    assert outs == [] and images.shape == (2, S, S, 3) and images.dtype == np.float32
+    assert abs(images.max() - 128 / 255.) < 1e-6
+    assert tb.shape == (2, 1, 1, 1, 15, 4) and yt.shape == (2, 7, 7, 3, 9)
+    assert ids.shape == (2, 15) and boxes.shape == (2, 15, 4) and boxes.dtype == np.int32 and masks.dtype == bool
+    cell = yt[0, 3, 2]                                   # [gy=3, gx=2]
+    a = int(np.argmax(cell[:, 4]))
+    assert cell[a, :5].tolist() == [2.0, 3.0, 2.0, 2.0, 1.0] and cell[a, 5 + 2] == 1 and cell[:, 4].sum() == 1
+    assert a == 1                                        # 2x2-cell box best matches anchor 2.47x2.56
+    assert tb[0, 0, 0, 0, 0].tolist() == [2.0, 3.0, 2.0, 2.0] and ids[0, 0] == 2
+    y3 = mutils.BatchGenerator(info, cfg, mode="yolo", shuffle=False, norm=True)[0][0]
+    assert len(y3) == 3
+
+
+def test_shapes_dataset_and_data_generator():
+    ds = ShapesDataset(seed=3)
+    ds.load_shapes(6, 128, 128)
+    ds.prepare()
+    assert ds.num_classes == 4 and ds.class_names == ["BG", "square", "circle", "triangle"]
+    img = ds.load_image(0)
+    mask, cls = ds.load_mask(0)
+    assert img.shape == (128, 128, 3) and img.dtype == np.uint8 and mask.shape[:2] == (128, 128) and mask.shape[2] == len(cls)
+    assert ((mask.sum(-1)) <= 1).all()                  # occlusion handling: instance masks never overlap
+
+    class C128(ShapesConfig):
+        IMAGE_SHAPE = [128, 128, 3]
+        GRID_H = GRID_W = 4
+    g = mutils.data_generator(ds, C128(), shuffle=False, batch_size=2)
+    (images, tb, yt), _ = next(g)
+    assert images.shape == (2, 128, 128, 3) and yt.shape == (2, 4, 4, 3, 9) and yt[..., 4].sum() >= 2
+    b = make_batches(C128(), 1, seed=5)
+    assert len(b) == 1 and b[0][5].shape == (16, 128, 128, 15)
+    b2 = make_batches(C128(), 1, seed=5)
+    assert all(np.array_equal(x, y) for x, y in zip(b[0], b2[0]))       # seeded -> reproducible
+
+
+def test_decode_one_yolo_output_and_unmold():
+    netout = np.full((2, 2, 1, 7), -8.0)
+    netout[1, 0, 0] = [0, 0, 0, 0, 8.0, 9.0, -9.0]
+    boxes = mutils.decode_one_yolo_output(netout, [1.0, 1.0], obj_threshold=0.3, nb_class=2)
+    assert len(boxes) == 1 and boxes[0].get_label() == 0
+    assert abs(boxes[0].xmin - (0.25 - 0.25)) < 1e-9 and abs(boxes[0].ymax - (0.75 + 0.25)) < 1e-9
+    full = mutils.unmold_mask(np.ones((28, 28), np.float32), [10, 20, 30, 50], (64, 64, 3))
+    assert full.sum() == 20 * 30 and full[20:50, 10:30].all()
+
+
+def test_mrcnn_shim_and_reference_example_imports():
+    from mrcnn import utils
+    keep = utils.non_max_suppression(np.array([[0, 0, 10, 10], [0, 0, 9, 10], [20, 20, 30, 30]]), np.array([0.5, 0.9, 0.1]), 0.3)
+    assert keep.tolist() == [1, 2]
+    ex = "/root/reference/example/shapes"
+    if not os.path.isdir(ex):
+        pytest.skip("reference checkout not present on this box")
+    sys.path.insert(0, ex)
+    try:
+        import dataset_shapes                       # the reference's own file, unmodified
+        cfg = dataset_shapes.ShapesConfig()
+        ds = dataset_shapes.ShapesDataset()
+        ds.load_shapes(2, 224, 224)
+        ds.prepare()
+        image, cls, bbox, mask = mutils.load_image_gt(ds, cfg, 0)
+        assert image.shape == (224, 224, 3) and bbox.shape[1] == 4 and mask.shape[-1] == len(cls)
+        assert resolve(cfg)["NB"] == 3
+    finally:
+        sys.path.remove(ex)
+        sys.modules.pop("dataset_shapes", None)
