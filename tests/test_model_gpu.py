@@ -111,7 +111,7 @@ def test_train_step_matches_oracle(precision):
     rows.sort(reverse=True)
     print(f"[{precision}] gradient rel-L2 error (engine, oracle32) worst first: {rows[:6]}")
     for e_eng, e_o32, k in rows:
-        assert e_eng <= (4 * e_o32 + 2e-5 if exact else max(3e-2, 4 * e_o32)), (k, e_eng, e_o32)
+        assert e_eng <= (4 * e_o32 + 2e-4 if exact else max(3e-2, 4 * e_o32)), (k, e_eng, e_o32)
     kref = g64["myolo_mask_conv1/kernel"].abs().max().item()
     assert ge["myolo_mask_conv1/bias"].abs().max().item() <= 1e-3 * kref
     # ---- updated variables: BN moving averages and Adam's first step (|delta| = lr where g != 0)
@@ -171,4 +171,4 @@ def test_yolo_mode_and_second_step():
     errs = sorted(((_l2(ge[k], g_o[k]), _l2(g_32[k], g_o[k]), k) for k in g_o), reverse=True)
     print(f"[yolo mode] gradient rel-L2 errors vs fp64 (engine, oracle32), worst first: {errs[:6]}")
     for e_eng, e_o32, k in errs:
-        assert e_eng <= 4 * e_o32 + 2e-5, (k, e_eng, e_o32)
+        assert e_eng <= 4 * e_o32 + 2e-4, (k, e_eng, e_o32)
