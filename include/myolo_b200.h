@@ -135,6 +135,16 @@ int myolo_split_tf32(const myolo_view* src, const myolo_view* hi, const myolo_vi
 int myolo_bn_bwd(const myolo_view* x, const myolo_view* dy, const myolo_view* dx, const float* mean, const float* var,
                  const float* gamma, const float* beta, float eps, int act, int train,
                  float* dgamma, float* dbeta, double* ws, myolo_stream stream);
+/* scale = gamma*rsqrt(var+eps), shift = beta - mean*scale: fixed-statistics BN (myolo_mask_bn2..4, model.py:695-708)
+ * folded into the producing conv's epilogue through the scale / shift_c arguments of myolo_gemm_taps. */
+int myolo_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                  float* scale, float* shift, int C, myolo_stream stream);
+/* backward of a = act(BN_fixed_stats(conv + bias)) from the OUTPUT a only (the pre-BN tensor is never
+ * stored): dx = dy*act'(a)*gamma*rs (may alias dy), dgamma/dbeta OVERWRITTEN, dbias (nullable) =
+ * gamma*rs*dbeta = gradient of the conv bias.  ws = 2*C doubles. */
+int myolo_bn_act_bwd_from_output(const myolo_view* a, const myolo_view* dy, const myolo_view* dx, const float* gamma,
+                                 const float* beta, const float* var, float eps, int act, float* dgamma, float* dbeta,
+                                 float* dbias, double* ws, myolo_stream stream);
 /* Keras moving-average update with TF zero-debias: biased -= (biased-value)*(1-momentum);
  * moving = biased/(1-momentum^step). value = mean, or var*bessel*n/(n-(1+eps)) when is_var. */
 int myolo_bn_moving_update(const float* value, float* biased, float* moving, int C, float momentum, int step,

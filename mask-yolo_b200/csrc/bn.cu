@@ -216,6 +216,90 @@ __global__ void __launch_bounds__(256) view_copy_kernel(V src, V dst, int accumu
   }
 }
 
+// scale = gamma * rsqrt(var + eps), shift = beta - mean * scale: inference-mode BN folded into the
+// producing GEMM's epilogue (myolo_gemm_taps scale/shift_c arguments).
+__global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                               float* __restrict__ scale, float* __restrict__ shift, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    const float s = gamma[c] * (1.f / sqrtf(var[c] + eps));
+    scale[c] = s;
+    shift[c] = fmaf(-mean[c], s, beta[c]);
+  }
+}
+
+// Backward of a = act(gamma * xhat + beta) with FIXED (moving) statistics, computed from the
+// OUTPUT a alone: where the activation passes, gamma * xhat = a - beta.  One pass: reads a and dy,
+// writes dx = dy * act'(a) * gamma * rs, accumulates dbeta = sum dy*act' and dgamma = sum dy*act'*xhat.
+__global__ void __launch_bounds__(256)
+bn_act_bwd_from_output_kernel(V a, V dy, V dx, const float* __restrict__ gamma, const float* __restrict__ beta,
+                              const float* __restrict__ var, float eps, int act, double* __restrict__ out0,
+                              double* __restrict__ out1, long long chunk) {
+  __shared__ float red[2][32][33];
+  const int tid = threadIdx.x;
+  const int cq = tid & 7, pg = tid >> 3;
+  const int c0 = blockIdx.y * 32 + cq * 4;
+  const long long total = (long long)a.n * a.h * a.w;
+  const long long p0 = blockIdx.x * chunk, p1 = min(total, p0 + chunk);
+  const float4 ga = *reinterpret_cast<const float4*>(gamma + c0);
+  const float4 be = *reinterpret_cast<const float4*>(beta + c0);
+  const float4 vv = *reinterpret_cast<const float4*>(var + c0);
+  const float gav[4] = {ga.x, ga.y, ga.z, ga.w}, bev[4] = {be.x, be.y, be.z, be.w};
+  const float vvv[4] = {vv.x, vv.y, vv.z, vv.w};
+  float sc[4], ig[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    sc[j] = gav[j] * (1.f / sqrtf(vvv[j] + eps));
+    ig[j] = 1.f / (fabsf(gav[j]) < 1e-20f ? copysignf(1e-20f, gav[j]) : gav[j]);
+  }
+  float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+  const int aa = act & 0xff;
+  for (long long p = p0 + pg; p < p1; p += 32) {
+    const float4 av = *reinterpret_cast<const float4*>(a.p + pix_off(a, p) + c0);
+    const float4 gv = *reinterpret_cast<const float4*>(dy.p + pix_off(dy, p) + c0);
+    const float ain[4] = {av.x, av.y, av.z, av.w}, gin[4] = {gv.x, gv.y, gv.z, gv.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      bool pass = true;
+      if (aa == MYOLO_ACT_RELU) pass = ain[j] > 0.f;
+      else if (aa == MYOLO_ACT_RELU6) pass = ain[j] > 0.f && ain[j] < 6.f;
+      const float g = pass ? gin[j] : 0.f;
+      s0[j] += g;
+      s1[j] = fmaf(g, (ain[j] - bev[j]) * ig[j], s1[j]);
+      o[j] = g * sc[j];
+      if (act & MYOLO_ROUND_TF32) o[j] = round_tf32(o[j]);
+    }
+    *reinterpret_cast<float4*>(dx.p + pix_off(dx, p) + c0) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    red[0][cq * 4 + j][pg] = s0[j];
+    red[1][cq * 4 + j][pg] = s1[j];
+  }
+  __syncthreads();
+  if (tid < 64) {
+    const int which = tid >> 5, c = tid & 31;
+    double s = 0.0;
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) s += (double)red[which][c][j];
+    atomicAdd((which ? out1 : out0) + blockIdx.y * 32 + c, s);
+  }
+}
+
+__global__ void bn_act_bwd_finalize_kernel(const double* __restrict__ ws, const float* __restrict__ gamma,
+                                           const float* __restrict__ var, float eps, float* __restrict__ dgamma,
+                                           float* __restrict__ dbeta, float* __restrict__ dbias, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    dbeta[c] = (float)ws[c];
+    dgamma[c] = (float)ws[C + c];
+    // d(pre-BN)/sum: the conv bias sits before the (fixed-statistics) BN, so dbias = gamma*rs*dbeta
+    if (dbias) dbias[c] = (float)(ws[c] * (double)(gamma[c] * (1.f / sqrtf(var[c] + eps))));
+  }
+}
+
 static bool view_ok(const myolo_view* v) {
   return v && v->p && v->n > 0 && v->h > 0 && v->w > 0 && v->c > 0 && (v->c % 4) == 0 && (v->sn % 4) == 0 && (v->sh % 4) == 0;
 }
@@ -342,6 +426,32 @@ extern "C" int myolo_view_copy(const myolo_view* src, const myolo_view* dst, int
   MYOLO_CHECK_ARG(view_ok(src) && view_ok(dst) && same_shape(src, dst));
   const long long total = (long long)src->n * src->h * src->w * (src->c / 4);
   view_copy_kernel<<<ew_blocks(total), 256, 0, as_stream(stream)>>>(to_v(src), to_v(dst), accumulate);
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
+}
+
+extern "C" int myolo_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                             float* scale, float* shift, int C, myolo_stream stream) {
+  MYOLO_CHECK_ARG(gamma && beta && mean && var && scale && shift && C > 0);
+  bn_fold_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(gamma, beta, mean, var, eps, scale, shift, C);
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
+}
+
+extern "C" int myolo_bn_act_bwd_from_output(const myolo_view* a, const myolo_view* dy, const myolo_view* dx,
+                                            const float* gamma, const float* beta, const float* var, float eps, int act,
+                                            float* dgamma, float* dbeta, float* dbias, double* ws, myolo_stream stream) {
+  MYOLO_CHECK_ARG(view_ok(a) && view_ok(dy) && view_ok(dx) && same_shape(a, dy) && same_shape(a, dx));
+  MYOLO_CHECK_ARG(gamma && beta && var && dgamma && dbeta && ws && (a->c % 32) == 0);
+  cudaStream_t st = as_stream(stream);
+  const int C = a->c;
+  const long long total = (long long)a->n * a->h * a->w;
+  dim3 grid;
+  long long chunk;
+  reduce_grid(total, C, &grid, &chunk);
+  MYOLO_CUDA(cudaMemsetAsync(ws, 0, 2 * C * sizeof(double), st));
+  bn_act_bwd_from_output_kernel<<<grid, 256, 0, st>>>(to_v(a), to_v(dy), to_v(dx), gamma, beta, var, eps, act, ws, ws + C, chunk);
+  bn_act_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, gamma, var, eps, dgamma, dbeta, dbias, C);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }

@@ -23,8 +23,8 @@ __global__ void __launch_bounds__(256)
 mask_out_fwd_kernel(const float* __restrict__ y4, const float* __restrict__ bd, const float* __restrict__ w1,
                     const float* __restrict__ b1, float* __restrict__ masks, int n_roi, int H, int W, int Cmid,
                     int NC) {
-  extern __shared__ float sm[];  // w1 [Cmid][NC], b1 [NC]
-  for (int i = threadIdx.x; i < Cmid * NC; i += blockDim.x) sm[i] = w1[i];
+  extern __shared__ __align__(16) float sm[];  // w1 TRANSPOSED [NC][Cmid] (conflict-free float4 reads), b1 [NC]
+  for (int i = threadIdx.x; i < Cmid * NC; i += blockDim.x) sm[(i % NC) * Cmid + i / NC] = w1[i];
   for (int i = threadIdx.x; i < NC; i += blockDim.x) sm[Cmid * NC + i] = b1[i];
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -59,12 +59,15 @@ mask_out_fwd_kernel(const float* __restrict__ y4, const float* __restrict__ bd, 
     float* out = masks + ((((size_t)n * 2 * H + 2 * h + a) * 2 * W) + 2 * w + b) * NC;
     for (int k = 0; k < NC; ++k) {
       float s = 0.f;
+      const float4* wk = reinterpret_cast<const float4*>(sm + (size_t)k * Cmid);
 #pragma unroll
       for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int co = (j * 32 + lane) * 4 + e;
-          if (j < nq) s = fmaf(v[4 * j + e], sm[co * NC + k], s);
+        if (j < nq) {
+          const float4 ww = wk[j * 32 + lane];
+          s = fmaf(v[4 * j + 0], ww.x, s);
+          s = fmaf(v[4 * j + 1], ww.y, s);
+          s = fmaf(v[4 * j + 2], ww.z, s);
+          s = fmaf(v[4 * j + 3], ww.w, s);
         }
       s = warp_sum(s);
       if (lane == (k & 31)) out[k] = 1.f / (1.f + expf(-(s + sm[Cmid * NC + k])));
@@ -82,8 +85,8 @@ mask_out_bwd_kernel(const float* __restrict__ y4, const float* __restrict__ bd, 
   float* s_w1 = sm;
   float* a_w1 = sm + Cmid * NC;
   float* a_b1 = a_w1 + Cmid * NC;
-  for (int i = threadIdx.x; i < Cmid * NC; i += blockDim.x) {
-    s_w1[i] = w1[i];
+  for (int i = threadIdx.x; i < Cmid * NC; i += blockDim.x) {  // both TRANSPOSED: [NC][Cmid]
+    s_w1[(i % NC) * Cmid + i / NC] = w1[i];
     a_w1[i] = 0.f;
   }
   for (int i = threadIdx.x; i < NC; i += blockDim.x) a_b1[i] = 0.f;
@@ -144,8 +147,8 @@ mask_out_bwd_kernel(const float* __restrict__ y4, const float* __restrict__ bd, 
           for (int e = 0; e < 4; ++e) {
             if (j < nq) {
               const int co = (j * 32 + lane) * 4 + e;
-              d[4 * j + e] = fmaf(gv, s_w1[co * NC + k], d[4 * j + e]);
-              atomicAdd(a_w1 + co * NC + k, hv[4 * j + e] * gv);
+              d[4 * j + e] = fmaf(gv, s_w1[k * Cmid + co], d[4 * j + e]);
+              atomicAdd(a_w1 + k * Cmid + co, hv[4 * j + e] * gv);
             }
           }
       }
@@ -171,8 +174,10 @@ mask_out_bwd_kernel(const float* __restrict__ y4, const float* __restrict__ bd, 
         if (j < nq && dbd_acc[4 * j + e] != 0.f) atomicAdd(dbd + (j * 32 + lane) * 4 + e, dbd_acc[4 * j + e]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < Cmid * NC; i += blockDim.x)
-    if (a_w1[i] != 0.f) atomicAdd(dw1 + i, a_w1[i]);
+  for (int i = threadIdx.x; i < Cmid * NC; i += blockDim.x) {
+    const float v = a_w1[(i % NC) * Cmid + i / NC];
+    if (v != 0.f) atomicAdd(dw1 + i, v);
+  }
   for (int i = threadIdx.x; i < NC; i += blockDim.x)
     if (a_b1[i] != 0.f) atomicAdd(db1 + i, a_b1[i]);
 }

@@ -284,7 +284,11 @@ class Engine:
             self.n_roi = n
             self.feat = PF(B, F_, F_, MASK_C, device=dev)
             self.x0 = PF(n, P_, P_, MASK_C, device=dev, split=self.x3m)
-            self.my = [None] + [PF(n, P_, P_, MASK_C, device=dev) for _ in range(4)]
+            # pre-BN conv outputs: only conv1 (batch-statistics BN) needs one; conv2..4 fold their
+            # fixed-statistics BN + ReLU into the GEMM epilogue (unless the 3xTF32 mask mode splits them)
+            self.my = [None] + [PF(n, P_, P_, MASK_C, device=dev) if (i == 1 or self.x3m) else None for i in range(1, 5)]
+            self.bn_scale = torch.zeros(4, MASK_C, device=dev)
+            self.bn_shift = torch.zeros(4, MASK_C, device=dev)
             self.ma = [self.x0] + [PF(n, P_, P_, MASK_C, device=dev, split=self.x3m and i < 4) for i in range(1, 5)]
             self.y4d = PF(n, P_, P_, 4 * MASK_C, device=dev)
             mh, mw = self.cfg["MASK_SHAPE"]
@@ -326,7 +330,8 @@ class Engine:
         else:
             C.call("myolo_bn_apply_split", xv, yv, yv_lo, mean, var, b.gamma, b.beta, BN_EPS, act & 0xff, st)
 
-    def _gemm_fwd(self, a_rows, lo_off, name, out_rows, M, N, K, shifts, bias, pf_w1, pf_blk):
+    def _gemm_fwd(self, a_rows, lo_off, name, out_rows, M, N, K, shifts, bias, pf_w1, pf_blk, scale=None, shift=None,
+                  act=0):
         """Forward conv GEMM through the tap-GEMM entry point; 3xTF32 = the tap list tripled over the
         (A_hi,B_hi) (A_lo,B_hi) (A_hi,B_lo) operand pairs (lo_off = row distance hi -> lo)."""
         base = list(shifts) if shifts is not None else [0]
@@ -342,8 +347,8 @@ class Engine:
         if timed:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        C.call("myolo_gemm_taps", a_rows, K, self.wt[name], out_rows, N, M, N, K, len(sh), arr, bias, None, None,
-               C.ACT_NONE, pf_w1, pf_blk, 0, self._st())
+        C.call("myolo_gemm_taps", a_rows, K, self.wt[name], out_rows, N, M, N, K, len(sh), arr, bias, scale, shift,
+               act, pf_w1, pf_blk, 0, self._st())
         if timed:
             e1.record()
             self.kernel_events.append((e0, e1))
@@ -417,13 +422,25 @@ class Engine:
         if self.x3m:
             C.call("myolo_split_tf32", self.x0.view(), self.x0.view(), self.x0.view(lo=True), st)
         sh3 = conv3x3_shifts(P_)
+        self._mask_fused = [False] * 5
         for i in (1, 2, 3, 4):
             a_in = self.ma[i - 1]
-            self._gemm_fwd(a_in.rows, a_in.lo_off, f"myolo_mask_conv{i}/kernel", self.my[i].rows, a_in.M, MASK_C, MASK_C,
-                           sh3, self.p[f"myolo_mask_conv{i}/bias"], P_ + 1, (P_ + 1) * (P_ + 1))
-            lo = self.ma[i].view(lo=True) if self.ma[i].rows_lo is not None else None
-            self._bn_fwd(f"myolo_mask_bn{i}", self.my[i].view(), self.ma[i].view(), C.ACT_RELU | self.rnd,
-                         training and i == 1, npix, lo)
+            batch_stats = training and i == 1
+            if batch_stats or self.x3m:
+                self._gemm_fwd(a_in.rows, a_in.lo_off, f"myolo_mask_conv{i}/kernel", self.my[i].rows, a_in.M, MASK_C, MASK_C,
+                               sh3, self.p[f"myolo_mask_conv{i}/bias"], P_ + 1, (P_ + 1) * (P_ + 1))
+                lo = self.ma[i].view(lo=True) if self.ma[i].rows_lo is not None else None
+                self._bn_fwd(f"myolo_mask_bn{i}", self.my[i].view(), self.ma[i].view(), C.ACT_RELU | self.rnd,
+                             batch_stats, npix, lo)
+            else:
+                # fixed-statistics BN + ReLU folded into the conv epilogue: a_i = relu((conv+bias)*scale + shift)
+                b = self.bn[f"myolo_mask_bn{i}"]
+                C.call("myolo_bn_fold", b.gamma, b.beta, b.mmean, b.mvar, BN_EPS, self.bn_scale[i - 1], self.bn_shift[i - 1],
+                       MASK_C, st)
+                self._gemm_fwd(a_in.rows, a_in.lo_off, f"myolo_mask_conv{i}/kernel", self.ma[i].rows, a_in.M, MASK_C, MASK_C,
+                               sh3, self.p[f"myolo_mask_conv{i}/bias"], P_ + 1, (P_ + 1) * (P_ + 1),
+                               self.bn_scale[i - 1], self.bn_shift[i - 1], C.ACT_RELU | self.rnd)
+                self._mask_fused[i] = True
         # Conv2DTranspose 2x2 s2 as one GEMM [rows,256] x [256, 4*256]; bias/ReLU/1x1/sigmoid in mask_out
         a4 = self.ma[4]
         C.call("myolo_gemm_taps", a4.rows, MASK_C, self.p["myolo_mask_deconv/kernel"], self.y4d.rows, 4 * MASK_C, a4.M,
@@ -532,8 +549,14 @@ class Engine:
         C.call("myolo_gemm_taps", self.dy4d.rows, 4 * MASK_C, self.wt["myolo_mask_deconv/kernel"], g0.rows, MASK_C, a4.M,
                MASK_C, 4 * MASK_C, 1, None, None, None, None, C.ACT_NONE, pfw, pfb, 0, st)
         for i in (4, 3, 2, 1):
-            self._bn_bwd(f"myolo_mask_bn{i}", self.my[i].view(), g0.view(), C.ACT_RELU | self.rnd, i == 1)
-            C.call("myolo_colsum", g0.view(), self.g[f"myolo_mask_conv{i}/bias"], self.ws, st)
+            if self._mask_fused[i]:
+                b = self.bn[f"myolo_mask_bn{i}"]
+                C.call("myolo_bn_act_bwd_from_output", self.ma[i].view(), g0.view(), g0.view(), b.gamma, b.beta, b.mvar, BN_EPS,
+                       C.ACT_RELU | self.rnd, b.dgamma, b.dbeta, self.g[f"myolo_mask_conv{i}/bias"], self.ws, st)
+            else:
+                self._bn_bwd(f"myolo_mask_bn{i}", self.my[i].view(), g0.view(), C.ACT_RELU | self.rnd, i == 1)
+                if i != 1:      # conv1's bias feeds a batch-statistics BN: its gradient is identically zero
+                    C.call("myolo_colsum", g0.view(), self.g[f"myolo_mask_conv{i}/bias"], self.ws, st)
             C.call("myolo_conv3x3_wgrad", self.ma[i - 1].rows, g0.rows, self.g[f"myolo_mask_conv{i}/kernel"], n, P_, P_,
                    MASK_C, MASK_C, st)
             C.call("myolo_conv3x3_dgrad", g0.rows, self.p[f"myolo_mask_conv{i}/kernel"], g1.rows, n, P_, P_, MASK_C,

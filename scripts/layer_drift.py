@@ -20,7 +20,7 @@ for prec in ("fp32", mode):
     d = {k: (v[0] + v[1] if (k.startswith("ad") and v.dim() == 5) else v.clone()) for k, v in eng.A.items()}
     d["c4"] = eng.c4.dense(); d["feat"] = eng.feat.dense(); d["x0"] = eng.x0.dense()
     for i in (1, 2, 3, 4):
-        d[f"my{i}"] = eng.my[i].dense(); d[f"ma{i}"] = eng.ma[i].dense()
+        d[f"ma{i}"] = eng.ma[i].dense()
     snap[prec] = d
     del eng
 for k in snap["fp32"]:
