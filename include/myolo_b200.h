@@ -91,6 +91,15 @@ int myolo_gemm_taps_tc(const float* A, long long lda, const float* Bt, float* C,
                        const float* bias, const float* scale, const float* shift_c, int act,
                        int pf_w1, int pf_blk, int accumulate, myolo_stream stream);
 int myolo_gemm_taps_tc_supported(long long lda, long long ldc, long long M, int N, int K, int ntaps, int accumulate);
+/* persistent multi-tap variant with shared-memory reuse of the A rows across taps (conv_win_tcgen05.cu):
+ * N == 256, 2 <= ntaps, every |shift| <= 16 (3x3 conv on padded-flat tiles up to 14 wide); A must carry
+ * >= 16 zero guard rows after row M.  myolo_gemm_taps picks it automatically in TF32 mode. */
+int myolo_gemm_taps_win(const float* A, long long lda, const float* Bt, float* C, long long ldc,
+                        long long M, int N, int K, int ntaps, const int* shifts_host,
+                        const float* bias, const float* scale, const float* shift_c, int act,
+                        int pf_w1, int pf_blk, int accumulate, myolo_stream stream);
+int myolo_gemm_taps_win_supported(long long lda, long long ldc, long long M, int N, int K, int ntaps,
+                                  const int* shifts_host, int accumulate);
 int myolo_gemm_taps_wgrad_ffma(const float* A, long long lda, const float* D, long long ldd, float* dW,
                                long long M, int N, int K, int ntaps, const int* shifts_host,
                                int transpose_out, myolo_stream stream);

@@ -1,0 +1,272 @@
+// conv_win_tcgen05.cu -- multi-tap (3x3) convolution on padded-flat tensors as ONE persistent
+// tcgen05 kernel with shared-memory reuse of the A operand across taps.
+//
+//   C[m, n] = epi( sum_t sum_k A[m + shift_t, k] * Bt[t][n][k] ),   |shift_t| <= 16, N = 256
+//
+// Why: with fp32 operands a 128x256 tile needs 48 KB of L2->smem traffic per 2.1 MFLOP and the
+// one-tile-per-CTA kernel (gemm_tcgen05.cu) is bound by L2 bandwidth (ncu: lts 52 %, tensor pipe
+// 38 %).  The nine taps of a 3x3 conv read the SAME activation rows shifted by at most W+2 rows, so
+// this kernel loads one window of 256+32 rows per 32-channel k-block (36 KB) and addresses all nine
+// taps inside it by moving the UMMA descriptor start by whole 128-byte rows (measured on B200: the
+// 128B swizzle is a function of the absolute shared-memory address, so a row-shifted start needs no
+// base_offset); the weights stream through a 4-stage ring and feed TWO 128-row accumulators
+// (512 TMEM columns), halving their traffic per output row.  L2 traffic per output row drops 2.6x.
+//
+// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 =
+// epilogue.  Persistent: CTA i processes tiles i, i+grid, ...; the producer keeps prefetching the
+// next tile's operands while the epilogue drains TMEM.
+// Replaces the Conv2D / Conv2DBackpropInput call sites of the mask head (myolo/model.py:688-706).
+#include "tc_common.cuh"
+
+namespace myolo {
+namespace tc {
+
+constexpr int WBM = 256, WHALO = 16;
+constexpr int WROWS = WBM + 2 * WHALO;          // 288 window rows
+constexpr int WBOX = WROWS / 2;                 // TMA box rows (<= 256)
+constexpr uint32_t kWinBytes = WROWS * 128;     // 36864
+constexpr uint32_t kWBRing = 6 * 16384;         // weight ring: 6 stages x 128 channels or 3 stages x 256 channels
+constexpr uint32_t kWStageOut = 4 * 2 * 4096;   // per-epilogue-warp double-buffered 32x32 fp32 staging (TMA store)
+constexpr uint32_t kWEpiVec = 2 * 1024 * 4;     // folded epilogue scale / shift, up to 1024 output channels
+constexpr uint32_t kWinSmem = 2 * kWinBytes + kWBRing + kWStageOut + kWEpiVec + 1024;
+
+// Work item = (256-row tile, WBN-column slice).  Two 128-row accumulators share every weight stage.
+//   WBN = 256: 512 TMEM columns, single TMEM stage (epilogue exposed, ~8 % of an item) -- the fastest
+//              variant: per 128x256x8 MMA the tensor core reads 12 KB of operands from shared memory
+//              in 128 cycles (96 B/clk of the 128 B/clk budget);
+//   WBN = 128: two TMEM stages (epilogue overlapped) but 8 KB per 64-cycle MMA = 128 B/clk: measured
+//              1.75 ms vs the 256-wide variant on the 4704-ROI mask conv (shared-memory bound).
+template <int WBN>
+__global__ void __launch_bounds__(kThreads)
+tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const __grid_constant__ CUtensorMap tmC, long long M, int N, int K, int ntaps, TapShifts sh, Epi ep,
+                   int nitems, int dbg) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr uint32_t kWBBytes = WBN * 128;
+  constexpr int kWBStages = kWBRing / kWBBytes;
+  constexpr uint32_t TS = WBN == 128 ? 2 : 1;     // TMEM stages
+  __shared__ __align__(8) uint64_t bars[2 + 2 + kWBStages * 2 + 4];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t awin0 = base, bst0 = base + 2 * kWinBytes, stg0 = bst0 + kWBStages * kWBBytes;
+  float* evec = reinterpret_cast<float*>(smem_raw + (stg0 + kWStageOut - smem_u32(smem_raw)));  // [scale N | shift N]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kblocks = K / BK;
+  const int nh = N / WBN;
+  const uint32_t bar0 = smem_u32(bars);
+  auto a_full = [&](int i) { return bar0 + 8u * i; };
+  auto a_empty = [&](int i) { return bar0 + 8u * (2 + i); };
+  auto b_full = [&](int i) { return bar0 + 8u * (4 + i); };
+  auto b_empty = [&](int i) { return bar0 + 8u * (4 + kWBStages + i); };
+  auto t_full = [&](int i) { return bar0 + 8u * (4 + 2 * kWBStages + i); };
+  auto t_empty = [&](int i) { return bar0 + 8u * (6 + 2 * kWBStages + i); };
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(a_full(i), 1);
+      mbar_init(a_empty(i), 1);
+      mbar_init(t_full(i), 1);
+      mbar_init(t_empty(i), 4);  // one arrival per epilogue warp
+    }
+    for (int i = 0; i < kWBStages; ++i) {
+      mbar_init(b_full(i), 1);
+      mbar_init(b_empty(i), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // epilogue constants, folded:  act((acc + bias) * scale + shift) = act(acc * S + T)
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const float sc = ep.scale ? __ldg(ep.scale + n) : 1.f;
+    const float b = ep.bias ? __ldg(ep.bias + n) : 0.f;
+    evec[n] = sc;
+    evec[N + n] = ep.scale ? fmaf(b, sc, __ldg(ep.shift + n)) : b;
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t a_it = 0, b_it = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int tile = item / nh, half = item - tile * nh;
+        const int row0 = tile * WBM - WHALO;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          const uint32_t ab = a_it & 1u;
+          mbar_wait(a_empty(ab), ((a_it >> 1) & 1u) ^ 1u);
+          const uint32_t wa = awin0 + ab * kWinBytes;
+          mbar_expect_tx(a_full(ab), kWinBytes);
+          tma_load_2d(wa, &tmA, a_full(ab), kb * BK, row0);
+          tma_load_2d(wa + WBOX * 128, &tmA, a_full(ab), kb * BK, row0 + WBOX);
+          ++a_it;
+          for (int t = 0; t < ntaps; ++t, ++b_it) {
+            const uint32_t s = b_it % kWBStages;
+            mbar_wait(b_empty(s), ((b_it / kWBStages) & 1u) ^ 1u);
+            mbar_expect_tx(b_full(s), kWBBytes);
+            tma_load_2d(bst0 + s * kWBBytes, &tmB, b_full(s), kb * BK, t * N + half * WBN);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(128, WBN, 0, 0);
+      uint32_t a_it = 0, b_it = 0, it = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+        const uint32_t ts = it % TS;
+        mbar_wait(t_empty(ts), ((it / TS) & 1u) ^ 1u);  // the epilogue that last used this TMEM stage has drained it
+        tc_fence_after();
+        const uint32_t tacc = tmem + ts * 256u;
+        for (int kb = 0; kb < kblocks; ++kb, ++a_it) {
+          const uint32_t ab = a_it & 1u;
+          mbar_wait(a_full(ab), (a_it >> 1) & 1u);
+          tc_fence_after();
+          const uint32_t wa = awin0 + ab * kWinBytes;
+          for (int t = 0; t < ntaps; ++t, ++b_it) {
+            const uint32_t s = b_it % kWBStages;
+            mbar_wait(b_full(s), (b_it / kWBStages) & 1u);
+            tc_fence_after();
+            const uint32_t row = (uint32_t)(WHALO + sh.s[t]);
+            const uint64_t db = make_desc(bst0 + s * kWBBytes, 16, 1024);
+#pragma unroll
+            for (int acc = 0; acc < 2; ++acc) {
+              // row-shifted start inside the swizzled window: the 128B swizzle is a function of the
+              // absolute smem address, so no base_offset is needed (verified on B200)
+              const uint64_t da = make_desc(wa + (row + 128u * acc) * 128u, 16, 1024);
+#pragma unroll
+              for (int k = 0; k < BK / 8; ++k)
+                umma_tf32(tacc + (uint32_t)WBN * acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                          (kb | t | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(b_empty(s));
+          }
+          umma_commit(a_empty(ab));
+        }
+        umma_commit(t_full(ts));
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const uint32_t sbuf0 = stg0 + (uint32_t)q * 8192u;
+    const uint32_t evs = smem_u32(evec);
+    const int actk = ep.act & 0xff;
+    const bool rnd = (ep.act & MYOLO_ROUND_TF32) != 0;
+    uint32_t it = 0, nst = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+      const int tile = item / nh, half = item - tile * nh;
+      const uint32_t ts = it % TS;
+      mbar_wait(t_full(ts), (it / TS) & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int acc = 0; acc < 2; ++acc) {
+        const int mrow0 = tile * WBM + acc * 128 + q * 32;
+        const long long m = (long long)mrow0 + lane;
+        const bool valid = (m < M) && pf_valid(m, ep.pf_w1, ep.pf_blk);
+#pragma unroll 1
+        for (int c0 = 0; c0 < WBN; c0 += 32, ++nst) {
+          float v[32];
+          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ts * 256u + (uint32_t)(acc * WBN + c0), v);
+          const uint32_t sbuf = sbuf0 + (nst & 1u) * 4096u;
+          // the store issued two chunks ago (same buffer) must have finished reading shared memory
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          __syncwarp();
+          const int n0 = half * WBN + c0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 sc, sf;
+            asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(sc.x), "=f"(sc.y), "=f"(sc.z), "=f"(sc.w) : "r"(evs + 4u * (n0 + 4 * j)));
+            asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(sf.x), "=f"(sf.y), "=f"(sf.z), "=f"(sf.w) : "r"(evs + 4u * (N + n0 + 4 * j)));
+            float o[4] = {fmaf(v[4 * j], sc.x, sf.x), fmaf(v[4 * j + 1], sc.y, sf.y), fmaf(v[4 * j + 2], sc.z, sf.z),
+                          fmaf(v[4 * j + 3], sc.w, sf.w)};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (actk == MYOLO_ACT_RELU) o[e] = fmaxf(o[e], 0.f);
+              else if (actk == MYOLO_ACT_RELU6) o[e] = fminf(fmaxf(o[e], 0.f), 6.f);
+              if (rnd) o[e] = round_tf32(o[e]);
+              if (!valid) o[e] = 0.f;   // padded-flat pad rows stay zero
+            }
+            const uint32_t addr = sbuf + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]));
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0 && mrow0 < M && !(dbg & 4)) tma_store_2d(&tmC, sbuf, n0, mrow0);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_empty(ts));
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace tc
+}  // namespace myolo
+
+using namespace myolo;
+using namespace myolo::tc;
+
+static int win_bn(int N) { return (N % 256) == 0 ? 256 : 128; }
+
+extern "C" int myolo_gemm_taps_win_supported(long long lda, long long ldc, long long M, int N, int K, int ntaps,
+                                             const int* shifts_host, int accumulate) {
+  if (!(M >= 1 && M < (1LL << 31) - 4096 && N >= 128 && (N % 128) == 0 && N <= 1024 && K >= BK && (K % BK) == 0 && (lda % 4) == 0 && (ldc % 4) == 0 &&
+        ntaps >= 2 && ntaps <= 32 && shifts_host && !accumulate))
+    return 0;
+  for (int t = 0; t < ntaps; ++t)
+    if (shifts_host[t] < -WHALO || shifts_host[t] > WHALO) return 0;
+  return 1;
+}
+
+extern "C" int myolo_gemm_taps_win(const float* A, long long lda, const float* Bt, float* C, long long ldc, long long M,
+                                   int N, int K, int ntaps, const int* shifts_host, const float* bias, const float* scale,
+                                   const float* shift_c, int act, int pf_w1, int pf_blk, int accumulate,
+                                   myolo_stream stream) {
+  MYOLO_CHECK_ARG(A && Bt && C && ((((uintptr_t)A | (uintptr_t)Bt | (uintptr_t)C) & 15) == 0));
+  MYOLO_CHECK_ARG(myolo_gemm_taps_win_supported(lda, ldc, M, N, K, ntaps, shifts_host, accumulate));
+  MYOLO_CHECK_ARG((scale == nullptr) == (shift_c == nullptr));
+  MYOLO_CHECK_ARG(!(accumulate && (scale || (act & 0xff) != MYOLO_ACT_NONE)));
+  MYOLO_CHECK_ARG(pf_w1 <= 0 || pf_blk > 0);
+  TapShifts sh;
+  for (int t = 0; t < 32; ++t) sh.s[t] = t < ntaps ? shifts_host[t] : 0;
+  CUtensorMap ta, tb;
+  // rows in [M, M+16) are the zero guard rows of the padded-flat tensor; everything else out of range
+  // (negative rows, the tail of the last tile) is TMA zero fill
+  int rc = get_map(A, M + WHALO, K, lda, WBOX, &ta);
+  if (rc) return rc;
+  static int bo_mode = -1;
+  if (bo_mode < 0) {
+    const char* e = getenv("MYOLO_WIN_BO");
+    bo_mode = e ? atoi(e) : 0;  // experiment switches: 4 = skip the global stores, 8 = force the 128-column variant
+  }
+  const int wbn = (bo_mode & 8) ? 128 : win_bn(N);
+  rc = get_map(Bt, (long long)ntaps * N, K, K, wbn, &tb);
+  if (rc) return rc;
+  CUtensorMap tc_;
+  rc = get_map(C, M, N, ldc, 32, &tc_);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MYOLO_CUDA(cudaFuncSetAttribute(tc_conv_win_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinSmem));
+    MYOLO_CUDA(cudaFuncSetAttribute(tc_conv_win_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinSmem));
+    attr_set = true;
+  }
+  const int nitems = (int)ceil_div(M, WBM) * (N / wbn);
+  const int grid = nitems < kNumSMs ? nitems : kNumSMs;
+  Epi ep{bias, scale, shift_c, act, pf_w1, pf_blk, accumulate};
+  if (wbn == 256)
+    tc_conv_win_kernel<256><<<grid, kThreads, kWinSmem, as_stream(stream)>>>(ta, tb, tc_, M, N, K, ntaps, sh, ep, nitems, bo_mode);
+  else
+    tc_conv_win_kernel<128><<<grid, kThreads, kWinSmem, as_stream(stream)>>>(ta, tb, tc_, M, N, K, ntaps, sh, ep, nitems, bo_mode);
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
+}

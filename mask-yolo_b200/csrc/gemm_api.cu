@@ -2,6 +2,7 @@
 // myolo_gemm_taps / myolo_gemm_taps_wgrad pick the tcgen05 kernel (gemm_tcgen05.cu) when the
 // library is in TF32 mode and the shape qualifies, otherwise the exact-fp32 CUDA-core kernel
 // (gemm_ffma.cu).  Both are sm_100a device code; there is no host or library fallback.
+#include <stdlib.h>
 #include "common.cuh"
 
 extern "C" int myolo_gemm_taps_ffma(const float* A, long long lda, const float* Bt, float* C, long long ldc,
@@ -21,8 +22,22 @@ extern "C" int myolo_gemm_taps_wgrad_tc(const float* A, long long lda, const flo
                                         int transpose_out, myolo_stream stream);
 extern "C" int myolo_gemm_taps_wgrad_tc_supported(long long lda, long long ldd, long long M, int N, int K, int ntaps);
 
+extern "C" int myolo_gemm_taps_win(const float* A, long long lda, const float* Bt, float* C, long long ldc, long long M,
+                                   int N, int K, int ntaps, const int* shifts_host, const float* bias, const float* scale,
+                                   const float* shift_c, int act, int pf_w1, int pf_blk, int accumulate, myolo_stream stream);
+extern "C" int myolo_gemm_taps_win_supported(long long lda, long long ldc, long long M, int N, int K, int ntaps,
+                                             const int* shifts_host, int accumulate);
+
 namespace myolo {
 static int g_precision = MYOLO_PREC_FP32;
+static int use_win() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MYOLO_NO_WIN");
+    v = (e && atoi(e)) ? 0 : 1;
+  }
+  return v;
+}
 }
 
 extern "C" int myolo_set_precision(int mode) {
@@ -36,6 +51,10 @@ extern "C" int myolo_gemm_taps(const float* A, long long lda, const float* Bt, f
                                int N, int K, int ntaps, const int* shifts_host, const float* bias, const float* scale,
                                const float* shift_c, int act, int pf_w1, int pf_blk, int accumulate,
                                myolo_stream stream) {
+  if (myolo::g_precision == MYOLO_PREC_TF32 && myolo::use_win() &&
+      myolo_gemm_taps_win_supported(lda, ldc, M, N, K, ntaps, shifts_host, accumulate))
+    return myolo_gemm_taps_win(A, lda, Bt, C, ldc, M, N, K, ntaps, shifts_host, bias, scale, shift_c, act, pf_w1, pf_blk,
+                               accumulate, stream);
   if (myolo::g_precision == MYOLO_PREC_TF32 && myolo_gemm_taps_tc_supported(lda, ldc, M, N, K, ntaps, accumulate))
     return myolo_gemm_taps_tc(A, lda, Bt, C, ldc, M, N, K, ntaps, shifts_host, bias, scale, shift_c, act, pf_w1, pf_blk,
                               accumulate, stream);

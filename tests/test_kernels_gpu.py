@@ -485,3 +485,34 @@ def test_error_paths(C):
         C.call("myolo_dwconv3x3_fwd", C.view(x, 1, 4, 4, 30), x, x, 1, stream())
     with pytest.raises(C.MyoloError):
         C.call("myolo_conv1_fwd", torch.zeros(4), x, x, 1, 4, 32, stream())   # CPU tensor: no CPU path
+
+
+@pytest.mark.parametrize("n,H,W,Ci", [(40, 14, 14, 256), (3, 14, 14, 64), (300, 14, 14, 256), (17, 7, 9, 128)])
+def test_conv3x3_window_kernel(C, n, H, W, Ci):
+    """Persistent windowed tcgen05 conv (conv_win_tcgen05.cu) vs the exact CUDA-core kernel: forward
+    with the fused bias/BN/ReLU epilogue, and the dgrad form (negated shifts)."""
+    from myolo.pf import PF, conv3x3_shifts
+    torch.manual_seed(20)
+    Co = 256
+    px = PF(n, H, W, Ci)
+    px.valid().normal_()
+    w = torch.randn(9, Ci, Co, device="cuda") / (9 * Ci) ** 0.5
+    wt = _prep(C, w, 9, Ci, Co, 1)
+    bias, scale, shift = (torch.randn(Co, device="cuda") * 0.1, torch.rand(Co, device="cuda") + 0.5,
+                          torch.randn(Co, device="cuda") * 0.1)
+    sh = C.int_array(conv3x3_shifts(W))
+    args = (Co, Ci, 9, sh, bias, scale, shift, C.ACT_RELU, W + 1, (H + 1) * (W + 1), 0, stream())
+    ref, out = PF(n, H, W, Co), PF(n, H, W, Co)
+    C.call("myolo_gemm_taps_ffma", px.rows, Ci, wt, ref.rows, Co, px.M, *args)
+    assert C.lib().myolo_gemm_taps_win_supported(Ci, Co, px.M, Co, Ci, 9, ctypes.addressof(sh), 0) == 1
+    C.call("myolo_gemm_taps_win", px.rows, Ci, wt, out.rows, Co, px.M, *args)
+    close(out.rows, ref.rows, 2e-3, "windowed conv fwd")
+    assert out.storage[:px.C].abs().max().item() == 0
+    # dgrad form: A = dy [M, 256], Bt = w[t] as [N=Ci? no: N must be 256] -> use square case only
+    if Ci == 256:
+        shn = C.int_array(conv3x3_shifts(W, negate=True))
+        a2 = (Co, Ci, 9, shn, None, None, None, 0, W + 1, (H + 1) * (W + 1), 0, stream())
+        r2, o2 = PF(n, H, W, Ci), PF(n, H, W, Ci)
+        C.call("myolo_gemm_taps_ffma", ref.rows, Co, w, r2.rows, Ci, px.M, *a2)
+        C.call("myolo_gemm_taps_win", ref.rows, Co, w, o2.rows, Ci, px.M, *a2)
+        close(o2.rows, r2.rows, 2e-3, "windowed conv dgrad")
