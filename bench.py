@@ -240,10 +240,10 @@ def main():
         ach = flops / (avg_ms * 1e-3) / 1e12
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("tc_gemm_mask_conv_bytes_per_launch")
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("mask_conv_fwd_dram_bytes_per_launch")
         except Exception:
             pass
-        roof = {"kernel": "tc_gemm_kernel<256> (mask-head 3x3 conv forward, 9-tap tcgen05 kind::tf32)", "bound": "tensor", "achieved": ach,
+        roof = {"kernel": "tc_conv_win_kernel<256> (mask-head 3x3 conv forward, persistent 9-tap tcgen05 kind::tf32)", "bound": "tensor", "achieved": ach,
                 "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"],
                 "traffic": traffic, "avg_launch_ms": avg_ms, "launches_timed": len(durs), "algorithmic_flops_per_launch": flops,
                 "peak_source": pk_src + " bf16 sustained (tf32 runs at half the bf16 tensor rate: nominal 1.1 vs 2.25 PFLOP/s)",
