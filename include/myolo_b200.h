@@ -192,6 +192,13 @@ int myolo_detect_mask_targets(const float* proposals, const int* gt_class_ids, c
  * (padded-flat H x W tiles, pre-bias).  masks[n][2h+a][2w+b][k] = sigmoid(b1[k] + sum_co relu(y4+bd[co]) * w1[co][k]) */
 int myolo_mask_out_fwd(const float* y4, const float* bd, const float* w1, const float* b1, float* masks,
                        int n_roi, int H, int W, int Cmid, int NC, myolo_stream stream);
+/* K10+K11 fused (tcgen05): deconv GEMM a4 [rows,Cmid] x kd [4*Cmid][Cmid] with the whole mask tail in the
+ * epilogue -> masks.  y4 rows are written ONLY for rois with target_ids > 0 (the rows myolo_mask_out_bwd
+ * reads); target_ids may be NULL (inference: nothing is written to y4).  Cmid == 256, NC <= 7. */
+int myolo_deconv_mask_fwd(const float* a4, const float* kd, const float* bd, const float* w1, const float* b1,
+                          float* masks, const int* target_ids, float* y4, int n_roi, int H, int W, int Cmid, int NC,
+                          myolo_stream stream);
+int myolo_deconv_mask_fwd_supported(int Cmid, int NC);
 /* backward: dlogit [n][2H][2W][NC] -> dy4 (same layout as y4), dw1 [Cmid][NC] +=, db1 [NC] +=, dbd [Cmid] += */
 int myolo_mask_out_bwd(const float* y4, const float* bd, const float* w1, const float* dlogit,
                        float* dy4, float* dw1, float* db1, float* dbd,

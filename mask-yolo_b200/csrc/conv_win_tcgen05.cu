@@ -36,11 +36,26 @@ constexpr uint32_t kWinSmem = 2 * kWinBytes + kWBRing + kWStageOut + kWEpiVec + 
 //              in 128 cycles (96 B/clk of the 128 B/clk budget);
 //   WBN = 128: two TMEM stages (epilogue overlapped) but 8 KB per 64-cycle MMA = 128 B/clk: measured
 //              1.75 ms vs the 256-wide variant on the 4704-ROI mask conv (shared-memory bound).
+// Fused tail of the mask head (model.py:711-713) for the deconv GEMM: the 256 columns of an item are
+// the output channels of ONE sub-pixel (a,b) of the 2x2 stride-2 transposed conv, so the epilogue can
+// finish the network in registers: h = relu(acc + bd), logits = h . w1 + b1, sigmoid, pixel-shuffled
+// store of NC floats.  The [rows, 4*256] deconv activation is written only for rows of POSITIVE rois
+// (the only rows the backward pass ever reads; nothing is skipped arithmetically).
+struct MaskTail {
+  const float* bd;    // [256] deconv bias
+  const float* w1;    // [256][NC] 1x1 kernel
+  const float* b1;    // [NC]
+  float* masks;       // [n_roi][2H][2W][NC]; nullptr = ordinary epilogue
+  const int* ids;     // [n_roi] target class ids (>0 = positive) or nullptr
+  float* y4;          // [rows][4*256] pre-bias deconv output (positive rois only)
+  int H, W, NC;
+};
+
 template <int WBN>
 __global__ void __launch_bounds__(kThreads)
 tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmC, long long M, int N, int K, int ntaps, TapShifts sh, Epi ep,
-                   int nitems, int dbg) {
+                   MaskTail mt, int nitems, int dbg) {
   extern __shared__ uint8_t smem_raw[];
   constexpr uint32_t kWBBytes = WBN * 128;
   constexpr int kWBStages = kWBRing / kWBBytes;
@@ -78,11 +93,16 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // epilogue constants, folded:  act((acc + bias) * scale + shift) = act(acc * S + T)
-  for (int n = threadIdx.x; n < N; n += blockDim.x) {
-    const float sc = ep.scale ? __ldg(ep.scale + n) : 1.f;
-    const float b = ep.bias ? __ldg(ep.bias + n) : 0.f;
-    evec[n] = sc;
-    evec[N + n] = ep.scale ? fmaf(b, sc, __ldg(ep.shift + n)) : b;
+  if (mt.masks) {   // mask tail: evec = [bd 256 | w1 transposed NC x 256]
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) evec[i] = __ldg(mt.bd + i);
+    for (int i = threadIdx.x; i < 256 * mt.NC; i += blockDim.x) evec[256 + (i % mt.NC) * 256 + i / mt.NC] = __ldg(mt.w1 + i);
+  } else {
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+      const float sc = ep.scale ? __ldg(ep.scale + n) : 1.f;
+      const float b = ep.bias ? __ldg(ep.bias + n) : 0.f;
+      evec[n] = sc;
+      evec[N + n] = ep.scale ? fmaf(b, sc, __ldg(ep.shift + n)) : b;
+    }
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), 512);
   tc_fence_before();
@@ -162,6 +182,60 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const uint32_t ts = it % TS;
       mbar_wait(t_full(ts), (it / TS) & 1u);
       tc_fence_after();
+      if (WBN == 256 && mt.masks) {
+#pragma unroll 1
+        for (int acc = 0; acc < 2; ++acc) {
+          const long long m = (long long)tile * WBM + acc * 128 + q * 32 + lane;
+          const bool valid = (m < M) && pf_valid(m, ep.pf_w1, ep.pf_blk);
+          int roi = 0, hh = 0, ww = 0;
+          bool pos = false;
+          if (valid) {
+            roi = (int)(m / ep.pf_blk);
+            const int r = (int)(m - (long long)roi * ep.pf_blk);
+            hh = r / ep.pf_w1 - 1;
+            ww = r % ep.pf_w1 - 1;
+            pos = mt.ids && __ldg(mt.ids + roi) > 0;
+          }
+          float lg[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) lg[k] = 0.f;
+#pragma unroll 1
+          for (int c0 = 0; c0 < 256; c0 += 32) {
+            float v[32];
+            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + c0), v);
+            if (pos) {
+              float4* yp = reinterpret_cast<float4*>(mt.y4 + (size_t)m * N + half * 256 + c0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) yp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 b4;
+              asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(evs + 4u * (c0 + 4 * j)));
+              const float h0 = fmaxf(v[4 * j] + b4.x, 0.f), h1 = fmaxf(v[4 * j + 1] + b4.y, 0.f);
+              const float h2 = fmaxf(v[4 * j + 2] + b4.z, 0.f), h3 = fmaxf(v[4 * j + 3] + b4.w, 0.f);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                if (k < mt.NC) {
+                  float4 w4;
+                  asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(w4.x), "=f"(w4.y), "=f"(w4.z), "=f"(w4.w) : "r"(evs + 4u * (256 + k * 256 + c0 + 4 * j)));
+                  lg[k] = fmaf(h0, w4.x, lg[k]);
+                  lg[k] = fmaf(h1, w4.y, lg[k]);
+                  lg[k] = fmaf(h2, w4.z, lg[k]);
+                  lg[k] = fmaf(h3, w4.w, lg[k]);
+                }
+              }
+            }
+          }
+          if (valid) {
+            const int a = half >> 1, b = half & 1;
+            float* out = mt.masks + ((((size_t)roi * 2 * mt.H + 2 * hh + a) * 2 * mt.W) + 2 * ww + b) * mt.NC;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (k < mt.NC) out[k] = 1.f / (1.f + expf(-(lg[k] + __ldg(mt.b1 + k))));
+          }
+        }
+      } else
 #pragma unroll 1
       for (int acc = 0; acc < 2; ++acc) {
         const int mrow0 = tile * WBM + acc * 128 + q * 32;
@@ -220,35 +294,38 @@ static int win_bn(int N) { return (N % 256) == 0 ? 256 : 128; }
 extern "C" int myolo_gemm_taps_win_supported(long long lda, long long ldc, long long M, int N, int K, int ntaps,
                                              const int* shifts_host, int accumulate) {
   if (!(M >= 1 && M < (1LL << 31) - 4096 && N >= 128 && (N % 128) == 0 && N <= 1024 && K >= BK && (K % BK) == 0 && (lda % 4) == 0 && (ldc % 4) == 0 &&
-        ntaps >= 2 && ntaps <= 32 && shifts_host && !accumulate))
+        ntaps >= 1 && ntaps <= 32 && !accumulate))
     return 0;
+  if (!shifts_host) return ntaps == 1 && M >= 4096;   // plain GEMM: worth it only for large M (persistent 256-row tiles)
   for (int t = 0; t < ntaps; ++t)
     if (shifts_host[t] < -WHALO || shifts_host[t] > WHALO) return 0;
+  if (ntaps == 1 && M < 4096) return 0;
   return 1;
 }
 
-extern "C" int myolo_gemm_taps_win(const float* A, long long lda, const float* Bt, float* C, long long ldc, long long M,
-                                   int N, int K, int ntaps, const int* shifts_host, const float* bias, const float* scale,
-                                   const float* shift_c, int act, int pf_w1, int pf_blk, int accumulate,
-                                   myolo_stream stream) {
+static int launch_win(const float* A, long long lda, const float* Bt, float* C, long long ldc, long long M, int N, int K,
+                      int ntaps, const int* shifts_host, const float* bias, const float* scale, const float* shift_c,
+                      int act, int pf_w1, int pf_blk, int accumulate, const MaskTail& mt, myolo_stream stream) {
   MYOLO_CHECK_ARG(A && Bt && C && ((((uintptr_t)A | (uintptr_t)Bt | (uintptr_t)C) & 15) == 0));
   MYOLO_CHECK_ARG(myolo_gemm_taps_win_supported(lda, ldc, M, N, K, ntaps, shifts_host, accumulate));
   MYOLO_CHECK_ARG((scale == nullptr) == (shift_c == nullptr));
   MYOLO_CHECK_ARG(!(accumulate && (scale || (act & 0xff) != MYOLO_ACT_NONE)));
   MYOLO_CHECK_ARG(pf_w1 <= 0 || pf_blk > 0);
   TapShifts sh;
-  for (int t = 0; t < 32; ++t) sh.s[t] = t < ntaps ? shifts_host[t] : 0;
+  for (int t = 0; t < 32; ++t) sh.s[t] = (shifts_host && t < ntaps) ? shifts_host[t] : 0;
   CUtensorMap ta, tb;
-  // rows in [M, M+16) are the zero guard rows of the padded-flat tensor; everything else out of range
-  // (negative rows, the tail of the last tile) is TMA zero fill
-  int rc = get_map(A, M + WHALO, K, lda, WBOX, &ta);
+  // rows in [M, M + max shift) are the zero guard rows of the padded-flat tensor; everything else out of
+  // range (negative rows, the tail of the last tile) is TMA zero fill
+  int maxs = 0;
+  for (int t = 0; t < ntaps; ++t) maxs = sh.s[t] > maxs ? sh.s[t] : maxs;
+  int rc = get_map(A, M + maxs, K, lda, WBOX, &ta);
   if (rc) return rc;
   static int bo_mode = -1;
   if (bo_mode < 0) {
     const char* e = getenv("MYOLO_WIN_BO");
     bo_mode = e ? atoi(e) : 0;  // experiment switches: 4 = skip the global stores, 8 = force the 128-column variant
   }
-  const int wbn = (bo_mode & 8) ? 128 : win_bn(N);
+  const int wbn = ((bo_mode & 8) && !mt.masks) ? 128 : win_bn(N);
   rc = get_map(Bt, (long long)ntaps * N, K, K, wbn, &tb);
   if (rc) return rc;
   CUtensorMap tc_;
@@ -264,9 +341,31 @@ extern "C" int myolo_gemm_taps_win(const float* A, long long lda, const float* B
   const int grid = nitems < kNumSMs ? nitems : kNumSMs;
   Epi ep{bias, scale, shift_c, act, pf_w1, pf_blk, accumulate};
   if (wbn == 256)
-    tc_conv_win_kernel<256><<<grid, kThreads, kWinSmem, as_stream(stream)>>>(ta, tb, tc_, M, N, K, ntaps, sh, ep, nitems, bo_mode);
+    tc_conv_win_kernel<256><<<grid, kThreads, kWinSmem, as_stream(stream)>>>(ta, tb, tc_, M, N, K, ntaps, sh, ep, mt, nitems, bo_mode);
   else
-    tc_conv_win_kernel<128><<<grid, kThreads, kWinSmem, as_stream(stream)>>>(ta, tb, tc_, M, N, K, ntaps, sh, ep, nitems, bo_mode);
+    tc_conv_win_kernel<128><<<grid, kThreads, kWinSmem, as_stream(stream)>>>(ta, tb, tc_, M, N, K, ntaps, sh, ep, mt, nitems, bo_mode);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
+}
+
+extern "C" int myolo_gemm_taps_win(const float* A, long long lda, const float* Bt, float* C, long long ldc, long long M,
+                                   int N, int K, int ntaps, const int* shifts_host, const float* bias, const float* scale,
+                                   const float* shift_c, int act, int pf_w1, int pf_blk, int accumulate,
+                                   myolo_stream stream) {
+  MaskTail mt{};
+  return launch_win(A, lda, Bt, C, ldc, M, N, K, ntaps, shifts_host, bias, scale, shift_c, act, pf_w1, pf_blk, accumulate,
+                    mt, stream);
+}
+
+extern "C" int myolo_deconv_mask_fwd_supported(int Cmid, int NC) { return Cmid == 256 && NC >= 1 && NC <= 7; }
+
+extern "C" int myolo_deconv_mask_fwd(const float* a4, const float* kd, const float* bd, const float* w1, const float* b1,
+                                     float* masks, const int* target_ids, float* y4, int n_roi, int H, int W, int Cmid,
+                                     int NC, myolo_stream stream) {
+  MYOLO_CHECK_ARG(a4 && kd && bd && w1 && b1 && masks && y4 && n_roi > 0 && H > 0 && W > 0);
+  MYOLO_CHECK_ARG(myolo_deconv_mask_fwd_supported(Cmid, NC));
+  MaskTail mt{bd, w1, b1, masks, target_ids, y4, H, W, NC};
+  const long long M = (long long)n_roi * (H + 1) * (W + 1);
+  return launch_win(a4, Cmid, kd, y4, 4 * Cmid, M, 4 * Cmid, Cmid, 1, nullptr, nullptr, nullptr, nullptr, MYOLO_ACT_NONE,
+                    W + 1, (H + 1) * (W + 1), 0, mt, stream);
 }

@@ -443,10 +443,18 @@ class Engine:
                 self._mask_fused[i] = True
         # Conv2DTranspose 2x2 s2 as one GEMM [rows,256] x [256, 4*256]; bias/ReLU/1x1/sigmoid in mask_out
         a4 = self.ma[4]
-        C.call("myolo_gemm_taps", a4.rows, MASK_C, self.p["myolo_mask_deconv/kernel"], self.y4d.rows, 4 * MASK_C, a4.M,
-               4 * MASK_C, MASK_C, 1, None, None, None, None, C.ACT_NONE, P_ + 1, (P_ + 1) * (P_ + 1), 0, st)
-        C.call("myolo_mask_out_fwd", self.y4d.rows, self.p["myolo_mask_deconv/bias"], self.p["myolo_mask/kernel"],
-               self.p["myolo_mask/bias"], A["masks"], n, P_, P_, MASK_C, self.NC, st)
+        if self.tc and C.lib().myolo_deconv_mask_fwd_supported(MASK_C, self.NC):
+            # one tcgen05 kernel: deconv GEMM + bias + ReLU + 1x1 conv + sigmoid; the deconv activation is
+            # kept only for positive rois (all the backward pass reads)
+            ids = self.target_ids if (training and self.mode == "training") else None
+            C.call("myolo_deconv_mask_fwd", a4.rows, self.p["myolo_mask_deconv/kernel"], self.p["myolo_mask_deconv/bias"],
+                   self.p["myolo_mask/kernel"], self.p["myolo_mask/bias"], A["masks"], ids, self.y4d.rows, n, P_, P_,
+                   MASK_C, self.NC, st)
+        else:
+            C.call("myolo_gemm_taps", a4.rows, MASK_C, self.p["myolo_mask_deconv/kernel"], self.y4d.rows, 4 * MASK_C, a4.M,
+                   4 * MASK_C, MASK_C, 1, None, None, None, None, C.ACT_NONE, P_ + 1, (P_ + 1) * (P_ + 1), 0, st)
+            C.call("myolo_mask_out_fwd", self.y4d.rows, self.p["myolo_mask_deconv/bias"], self.p["myolo_mask/kernel"],
+                   self.p["myolo_mask/bias"], A["masks"], n, P_, P_, MASK_C, self.NC, st)
         mh, mw = self.cfg["MASK_SHAPE"]
         return A["masks"].view(self.B, self.R, mh, mw, self.NC)
 

@@ -516,3 +516,32 @@ def test_conv3x3_window_kernel(C, n, H, W, Ci):
         C.call("myolo_gemm_taps_ffma", ref.rows, Co, w, r2.rows, Ci, px.M, *a2)
         C.call("myolo_gemm_taps_win", ref.rows, Co, w, o2.rows, Ci, px.M, *a2)
         close(o2.rows, r2.rows, 2e-3, "windowed conv dgrad")
+
+
+def test_deconv_mask_fused(C):
+    """tcgen05 deconv GEMM with the mask tail in its epilogue vs the unfused exact path."""
+    from myolo.pf import PF
+    torch.manual_seed(21)
+    n, H, W, Cm, NC = 37, 14, 14, 256, 4
+    pa = PF(n, H, W, Cm)
+    pa.valid().normal_()
+    kd = torch.randn(4 * Cm, Cm, device="cuda") / Cm ** 0.5
+    bd, w1, b1 = torch.randn(Cm, device="cuda") * 0.1, torch.randn(Cm, NC, device="cuda") / Cm ** 0.5, torch.randn(NC, device="cuda") * 0.1
+    ids = torch.zeros(n, dtype=torch.int32, device="cuda")
+    ids[[0, 5, 36]] = torch.tensor([1, 3, 2], dtype=torch.int32, device="cuda")
+    y_ref = PF(n, H, W, 4 * Cm)
+    C.call("myolo_gemm_taps_ffma", pa.rows, Cm, kd, y_ref.rows, 4 * Cm, pa.M, 4 * Cm, Cm, 1, None, None, None, None, 0,
+           W + 1, (H + 1) * (W + 1), 0, stream())
+    m_ref = torch.empty(n, 2 * H, 2 * W, NC, device="cuda")
+    C.call("myolo_mask_out_fwd", y_ref.rows, bd, w1, b1, m_ref, n, H, W, Cm, NC, stream())
+    y4 = PF(n, H, W, 4 * Cm)
+    m = torch.full((n, 2 * H, 2 * W, NC), -1.0, device="cuda")
+    assert C.lib().myolo_deconv_mask_fwd_supported(Cm, NC) == 1
+    C.call("myolo_deconv_mask_fwd", pa.rows, kd, bd, w1, b1, m, ids, y4.rows, n, H, W, Cm, NC, stream())
+    close(m, m_ref, 1e-3, "fused masks")
+    yv, rv = y4.valid(), y_ref.valid()
+    for r in range(n):
+        if ids[r] > 0:
+            close(yv[r], rv[r], 2e-3, "y4 of a positive roi")
+        else:
+            assert yv[r].abs().max().item() == 0, "y4 rows of non-positive rois are not written"
