@@ -7,19 +7,41 @@
 
 namespace myolo {
 
-struct V {  // device copy of myolo_view
+// Division by a runtime constant as multiply-high + add + shift (Granlund-Montgomery round-up form;
+// exact for dividends below 2^31).  The 64-bit div/mod chains these replaced made every elementwise
+// BN kernel ALU-bound at ~3 TB/s.
+struct FastDiv {
+  uint32_t mul, shr, d;
+};
+static inline FastDiv make_fd(uint32_t d) {
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;
+  const uint64_t m = ((1ull << 32) * ((1ull << l) - d)) / d + 1;
+  return FastDiv{(uint32_t)m, l, d};
+}
+__device__ __forceinline__ uint32_t fd_div(uint32_t n, const FastDiv& f) { return (__umulhi(f.mul, n) + n) >> f.shr; }
+
+struct V {  // device copy of myolo_view + precomputed divisors
   float* p;
   long long sn, sh;
   int n, h, w, c;
+  FastDiv fw, fh, fc4;
+  int dense;  // pixels are contiguous: offset = pixel * c
 };
-static inline V to_v(const myolo_view* v) { return V{v->p, v->sn, v->sh, v->n, v->h, v->w, v->c}; }
+static inline V to_v(const myolo_view* v) {
+  const int dense = (v->sh == (long long)v->w * v->c) && (v->sn == (long long)v->h * v->sh);
+  return V{v->p, v->sn, v->sh, v->n, v->h, v->w, v->c, make_fd((uint32_t)v->w), make_fd((uint32_t)v->h),
+           make_fd((uint32_t)(v->c / 4 > 0 ? v->c / 4 : 1)), dense};
+}
 
 __device__ __forceinline__ size_t pix_off(const V& v, long long pix) {
-  const int w = (int)(pix % v.w);
-  const long long t = pix / v.w;
-  const int h = (int)(t % v.h);
-  const long long n = t / v.h;
-  return (size_t)(n * v.sn + h * v.sh + (long long)w * v.c);
+  if (v.dense) return (size_t)pix * (size_t)v.c;
+  const uint32_t p = (uint32_t)pix;
+  const uint32_t t = fd_div(p, v.fw);
+  const uint32_t w = p - t * (uint32_t)v.w;
+  const uint32_t n = fd_div(t, v.fh);
+  const uint32_t h = t - n * (uint32_t)v.h;
+  return (size_t)((long long)n * v.sn + (long long)h * v.sh + (long long)w * v.c);
 }
 
 __device__ __forceinline__ float act_grad_mask(float y, int act) {
@@ -105,10 +127,12 @@ __global__ void __launch_bounds__(256)
 bn_apply_kernel(V x, V y, V ylo, const float* __restrict__ mean, const float* __restrict__ var,
                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int act) {
   const int C4 = x.c >> 2;
+  const FastDiv x_fc4 = x.fc4;
   const long long total = (long long)x.n * x.h * x.w * C4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int q = (int)(i % C4) * 4;
-    const long long p = i / C4;
+    const uint32_t pp = fd_div((uint32_t)i, x_fc4);
+    const int q = (int)((uint32_t)i - pp * (uint32_t)C4) * 4;
+    const long long p = pp;
     const float4 v = *reinterpret_cast<const float4*>(x.p + pix_off(x, p) + q);
     const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + q));
     const float4 vv = __ldg(reinterpret_cast<const float4*>(var + q));
@@ -132,10 +156,12 @@ bn_apply_kernel(V x, V y, V ylo, const float* __restrict__ mean, const float* __
 
 __global__ void __launch_bounds__(256) split_tf32_kernel(V src, V hi, V lo) {
   const int C4 = src.c >> 2;
+  const FastDiv x_fc4 = src.fc4;
   const long long total = (long long)src.n * src.h * src.w * C4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int q = (int)(i % C4) * 4;
-    const long long p = i / C4;
+    const uint32_t pp = fd_div((uint32_t)i, x_fc4);
+    const int q = (int)((uint32_t)i - pp * (uint32_t)C4) * 4;
+    const long long p = pp;
     const float4 v = *reinterpret_cast<const float4*>(src.p + pix_off(src, p) + q);
     const float4 h = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
     *reinterpret_cast<float4*>(hi.p + pix_off(hi, p) + q) = h;
@@ -157,10 +183,12 @@ bn_bwd_dx_kernel(V x, V dy, V dx, const float* __restrict__ mean, const float* _
                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int act, int train,
                  const double* __restrict__ ws, double inv_count) {
   const int C = x.c, C4 = C >> 2;
+  const FastDiv x_fc4 = x.fc4;
   const long long total = (long long)x.n * x.h * x.w * C4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int q = (int)(i % C4) * 4;
-    const long long p = i / C4;
+    const uint32_t pp = fd_div((uint32_t)i, x_fc4);
+    const int q = (int)((uint32_t)i - pp * (uint32_t)C4) * 4;
+    const long long p = pp;
     const float4 v = *reinterpret_cast<const float4*>(x.p + pix_off(x, p) + q);
     const float4 g = *reinterpret_cast<const float4*>(dy.p + pix_off(dy, p) + q);
     const float vin[4] = {v.x, v.y, v.z, v.w};
@@ -201,10 +229,12 @@ __global__ void bn_moving_update_kernel(const float* __restrict__ value, float* 
 
 __global__ void __launch_bounds__(256) view_copy_kernel(V src, V dst, int accumulate) {
   const int C4 = src.c >> 2;
+  const FastDiv x_fc4 = src.fc4;
   const long long total = (long long)src.n * src.h * src.w * C4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int q = (int)(i % C4) * 4;
-    const long long p = i / C4;
+    const uint32_t pp = fd_div((uint32_t)i, x_fc4);
+    const int q = (int)((uint32_t)i - pp * (uint32_t)C4) * 4;
+    const long long p = pp;
     float4 v = *reinterpret_cast<const float4*>(src.p + pix_off(src, p) + q);
     float4* d = reinterpret_cast<float4*>(dst.p + pix_off(dst, p) + q);
     if (accumulate & 1) {

@@ -21,14 +21,16 @@
 namespace myolo {
 namespace tc {
 
-constexpr int WBM = 256, WHALO = 16;
-constexpr int WROWS = WBM + 2 * WHALO;          // 288 window rows
-constexpr int WBOX = WROWS / 2;                 // TMA box rows (<= 256)
-constexpr uint32_t kWinBytes = WROWS * 128;     // 36864
-constexpr uint32_t kWBRing = 6 * 16384;         // weight ring: 6 stages x 128 channels or 3 stages x 256 channels
+constexpr int WHALO = 16;
 constexpr uint32_t kWStageOut = 4 * 2 * 4096;   // per-epilogue-warp double-buffered 32x32 fp32 staging (TMA store)
 constexpr uint32_t kWEpiVec = 2 * 1024 * 4;     // folded epilogue scale / shift, up to 1024 output channels
-constexpr uint32_t kWinSmem = 2 * kWinBytes + kWBRing + kWStageOut + kWEpiVec + 1024;
+// NACC = 128-row accumulators per work item.  Window = 128*NACC + 32 rows; weight ring 128 KB (NACC 1) / 96 KB (NACC 2)
+__host__ __device__ constexpr int win_rows(int nacc) { return 128 * nacc + 2 * WHALO; }
+__host__ __device__ constexpr int win_box(int nacc) { return nacc == 1 ? win_rows(1) : win_rows(2) / 2; }
+__host__ __device__ constexpr uint32_t win_ring(int nacc) { return nacc == 1 ? 131072u : 98304u; }
+__host__ __device__ constexpr uint32_t win_smem(int nacc) {
+  return 2u * win_rows(nacc) * 128u + win_ring(nacc) + kWStageOut + kWEpiVec + 1024u;
+}
 
 // Work item = (256-row tile, WBN-column slice).  Two 128-row accumulators share every weight stage.
 //   WBN = 256: 512 TMEM columns, single TMEM stage (epilogue exposed, ~8 % of an item) -- the fastest
@@ -51,15 +53,18 @@ struct MaskTail {
   int H, W, NC;
 };
 
-template <int WBN>
+template <int WBN, int NACC>
 __global__ void __launch_bounds__(kThreads)
 tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmC, long long M, int N, int K, int ntaps, TapShifts sh, Epi ep,
                    MaskTail mt, int nitems, int dbg) {
   extern __shared__ uint8_t smem_raw[];
+  constexpr int WBM = 128 * NACC, WROWS = win_rows(NACC), WBOX = win_box(NACC);
+  constexpr uint32_t kWinBytes = WROWS * 128;
   constexpr uint32_t kWBBytes = WBN * 128;
-  constexpr int kWBStages = kWBRing / kWBBytes;
-  constexpr uint32_t TS = WBN == 128 ? 2 : 1;     // TMEM stages
+  constexpr int kWBStages = win_ring(NACC) / kWBBytes;
+  constexpr uint32_t TS = (WBN * NACC <= 256) ? 2 : 1;     // TMEM stages (epilogue overlapped when 2)
+  constexpr uint32_t TSTRIDE = WBN * NACC;                  // TMEM columns per stage
   __shared__ __align__(8) uint64_t bars[2 + 2 + kWBStages * 2 + 4];
   __shared__ uint32_t tmem_slot;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -122,7 +127,7 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const uint32_t wa = awin0 + ab * kWinBytes;
           mbar_expect_tx(a_full(ab), kWinBytes);
           tma_load_2d(wa, &tmA, a_full(ab), kb * BK, row0);
-          tma_load_2d(wa + WBOX * 128, &tmA, a_full(ab), kb * BK, row0 + WBOX);
+          if (NACC == 2) tma_load_2d(wa + WBOX * 128, &tmA, a_full(ab), kb * BK, row0 + WBOX);
           ++a_it;
           for (int t = 0; t < ntaps; ++t, ++b_it) {
             const uint32_t s = b_it % kWBStages;
@@ -141,7 +146,7 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const uint32_t ts = it % TS;
         mbar_wait(t_empty(ts), ((it / TS) & 1u) ^ 1u);  // the epilogue that last used this TMEM stage has drained it
         tc_fence_after();
-        const uint32_t tacc = tmem + ts * 256u;
+        const uint32_t tacc = tmem + ts * TSTRIDE;
         for (int kb = 0; kb < kblocks; ++kb, ++a_it) {
           const uint32_t ab = a_it & 1u;
           mbar_wait(a_full(ab), (a_it >> 1) & 1u);
@@ -154,7 +159,7 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const uint32_t row = (uint32_t)(WHALO + sh.s[t]);
             const uint64_t db = make_desc(bst0 + s * kWBBytes, 16, 1024);
 #pragma unroll
-            for (int acc = 0; acc < 2; ++acc) {
+            for (int acc = 0; acc < NACC; ++acc) {
               // row-shifted start inside the swizzled window: the 128B swizzle is a function of the
               // absolute smem address, so no base_offset is needed (verified on B200)
               const uint64_t da = make_desc(wa + (row + 128u * acc) * 128u, 16, 1024);
@@ -184,7 +189,7 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       tc_fence_after();
       if (WBN == 256 && mt.masks) {
 #pragma unroll 1
-        for (int acc = 0; acc < 2; ++acc) {
+        for (int acc = 0; acc < NACC; ++acc) {
           const long long m = (long long)tile * WBM + acc * 128 + q * 32 + lane;
           const bool valid = (m < M) && pf_valid(m, ep.pf_w1, ep.pf_blk);
           int roi = 0, hh = 0, ww = 0;
@@ -202,7 +207,7 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll 1
           for (int c0 = 0; c0 < 256; c0 += 32) {
             float v[32];
-            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + c0), v);
+            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ts * TSTRIDE + (uint32_t)(acc * 256 + c0), v);
             if (pos) {
               float4* yp = reinterpret_cast<float4*>(mt.y4 + (size_t)m * N + half * 256 + c0);
 #pragma unroll
@@ -237,14 +242,14 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
       } else
 #pragma unroll 1
-      for (int acc = 0; acc < 2; ++acc) {
+      for (int acc = 0; acc < NACC; ++acc) {
         const int mrow0 = tile * WBM + acc * 128 + q * 32;
         const long long m = (long long)mrow0 + lane;
         const bool valid = (m < M) && pf_valid(m, ep.pf_w1, ep.pf_blk);
 #pragma unroll 1
         for (int c0 = 0; c0 < WBN; c0 += 32, ++nst) {
           float v[32];
-          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ts * 256u + (uint32_t)(acc * WBN + c0), v);
+          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ts * TSTRIDE + (uint32_t)(acc * WBN + c0), v);
           const uint32_t sbuf = sbuf0 + (nst & 1u) * 4096u;
           // the store issued two chunks ago (same buffer) must have finished reading shared memory
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -289,7 +294,6 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 using namespace myolo;
 using namespace myolo::tc;
 
-static int win_bn(int N) { return (N % 256) == 0 ? 256 : 128; }
 
 extern "C" int myolo_gemm_taps_win_supported(long long lda, long long ldc, long long M, int N, int K, int ntaps,
                                              const int* shifts_host, int accumulate) {
@@ -318,14 +322,17 @@ static int launch_win(const float* A, long long lda, const float* Bt, float* C, 
   // range (negative rows, the tail of the last tile) is TMA zero fill
   int maxs = 0;
   for (int t = 0; t < ntaps; ++t) maxs = sh.s[t] > maxs ? sh.s[t] : maxs;
-  int rc = get_map(A, M + maxs, K, lda, WBOX, &ta);
-  if (rc) return rc;
   static int bo_mode = -1;
   if (bo_mode < 0) {
     const char* e = getenv("MYOLO_WIN_BO");
-    bo_mode = e ? atoi(e) : 0;  // experiment switches: 4 = skip the global stores, 8 = force the 128-column variant
+    bo_mode = e ? atoi(e) : 0;  // experiment switches: 4 = skip the global stores, 8 = 128-column slices, 16 = two accumulators
   }
-  const int wbn = ((bo_mode & 8) && !mt.masks) ? 128 : win_bn(N);
+  const int wbn = (((bo_mode & 8) && !mt.masks) || (N % 256) != 0) ? 128 : 256;
+  // one accumulator + two TMEM stages (epilogue overlapped with the next item's main loop) is the default;
+  // the two-accumulator variant halves the weight traffic from L2 but exposes its epilogue
+  const int nacc = (bo_mode & 16) ? 2 : 1;
+  int rc = get_map(A, M + maxs, K, lda, win_box(nacc), &ta);
+  if (rc) return rc;
   rc = get_map(Bt, (long long)ntaps * N, K, K, wbn, &tb);
   if (rc) return rc;
   CUtensorMap tc_;
@@ -333,17 +340,23 @@ static int launch_win(const float* A, long long lda, const float* Bt, float* C, 
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    MYOLO_CUDA(cudaFuncSetAttribute(tc_conv_win_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinSmem));
-    MYOLO_CUDA(cudaFuncSetAttribute(tc_conv_win_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinSmem));
+    MYOLO_CUDA(cudaFuncSetAttribute(tc_conv_win_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem(1)));
+    MYOLO_CUDA(cudaFuncSetAttribute(tc_conv_win_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem(1)));
+    MYOLO_CUDA(cudaFuncSetAttribute(tc_conv_win_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem(2)));
+    MYOLO_CUDA(cudaFuncSetAttribute(tc_conv_win_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem(2)));
     attr_set = true;
   }
-  const int nitems = (int)ceil_div(M, WBM) * (N / wbn);
+  const int nitems = (int)ceil_div(M, 128 * nacc) * (N / wbn);
   const int grid = nitems < kNumSMs ? nitems : kNumSMs;
   Epi ep{bias, scale, shift_c, act, pf_w1, pf_blk, accumulate};
-  if (wbn == 256)
-    tc_conv_win_kernel<256><<<grid, kThreads, kWinSmem, as_stream(stream)>>>(ta, tb, tc_, M, N, K, ntaps, sh, ep, mt, nitems, bo_mode);
-  else
-    tc_conv_win_kernel<128><<<grid, kThreads, kWinSmem, as_stream(stream)>>>(ta, tb, tc_, M, N, K, ntaps, sh, ep, mt, nitems, bo_mode);
+  cudaStream_t st = as_stream(stream);
+#define MYOLO_WIN_LAUNCH(BN_, NA_) \
+  tc_conv_win_kernel<BN_, NA_><<<grid, kThreads, win_smem(NA_), st>>>(ta, tb, tc_, M, N, K, ntaps, sh, ep, mt, nitems, bo_mode)
+  if (wbn == 256 && nacc == 1) MYOLO_WIN_LAUNCH(256, 1);
+  else if (wbn == 256) MYOLO_WIN_LAUNCH(256, 2);
+  else if (nacc == 1) MYOLO_WIN_LAUNCH(128, 1);
+  else MYOLO_WIN_LAUNCH(128, 2);
+#undef MYOLO_WIN_LAUNCH
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }

@@ -144,7 +144,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------
 // wgrad kernel: CTA = (row chunk, 128 A-channels x BN D-channels, tap); reduction over rows.
 // ------------------------------------------------------------------------------------------
-template <int BN>
+// NACC accumulators of 128 A-channels each share every D stage (halves the D traffic per FLOP).
+template <int BN, int NACC>
 __global__ void __launch_bounds__(kThreads)
 tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmD,
                 float* __restrict__ dW, long long M, int N, int K, TapShifts sh, long long chunk, int ntn,
@@ -154,12 +155,13 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __shared__ uint32_t tmem_slot;
   constexpr int RB = 32;  // rows per stage
   constexpr uint32_t kBox = 32 * RB * 4;  // one 32-channel x 32-row box = 4 KB
-  constexpr uint32_t kABytes = (BM / 32) * kBox, kDBytes = (BN / 32) * kBox, kStage = kABytes + kDBytes;
-  constexpr uint32_t kCols = BN < 32 ? 32 : BN;
+  constexpr int AM = BM * NACC;  // A-channels per CTA
+  constexpr uint32_t kABytes = (AM / 32) * kBox, kDBytes = (BN / 32) * kBox, kStage = kABytes + kDBytes;
+  constexpr uint32_t kCols = (BN * NACC) < 32 ? 32 : BN * NACC;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tap = blockIdx.z;
-  const int k0 = (blockIdx.y / ntn) * BM;
+  const int k0 = (blockIdx.y / ntn) * AM;
   const int n0 = (blockIdx.y % ntn) * BN;
   const long long mbeg = (long long)blockIdx.x * chunk;
   const long long mend = min(M, mbeg + chunk);
@@ -197,7 +199,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint32_t sa = base + (uint32_t)s * kStage;
         const int row = (int)(mbeg + (long long)it * RB);
 #pragma unroll
-        for (int j = 0; j < BM / 32; ++j) tma_load_2d(sa + j * kBox, &tmA, full(s), k0 + 32 * j, row + shift);
+        for (int j = 0; j < AM / 32; ++j) tma_load_2d(sa + j * kBox, &tmA, full(s), k0 + 32 * j, row + shift);
 #pragma unroll
         for (int j = 0; j < BN / 32; ++j) tma_load_2d(sa + kABytes + j * kBox, &tmD, full(s), n0 + 32 * j, row);
       }
@@ -213,25 +215,30 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint32_t sa = base + (uint32_t)s * kStage;
         // MN-major tf32: 128B_BASE32B atoms of 4 reduction rows x 128 B; LBO = next 32-channel box,
         // SBO = next 4-row group (512 B); one K=8 MMA spans two atoms = 1024 B.
-        const uint64_t da = make_desc(sa, kBox, 512, 1);
         const uint64_t db = make_desc(sa + kABytes, kBox, 512, 1);
 #pragma unroll
-        for (int k = 0; k < RB / 8; ++k)
-          umma_tf32(tmem, da + (uint64_t)(k * 64), db + (uint64_t)(k * 64), idesc, (it | k) != 0 ? 1u : 0u);
+        for (int acc = 0; acc < NACC; ++acc) {
+          const uint64_t da = make_desc(sa + acc * (BM / 32) * kBox, kBox, 512, 1);
+#pragma unroll
+          for (int k = 0; k < RB / 8; ++k)
+            umma_tf32(tmem + (uint32_t)(acc * BN), da + (uint64_t)(k * 64), db + (uint64_t)(k * 64), idesc,
+                      (it | k) != 0 ? 1u : 0u);
+        }
         umma_commit(empty(s));
       }
       umma_commit(tfull);
     }
   } else {
     const int q = warp & 3;
-    const int k = k0 + q * 32 + lane;
     mbar_wait(tfull, 0);
     tc_fence_after();
     float* W = dW + (size_t)tap * K * N;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int cc = 0; cc < NACC * BN; cc += 32) {
+      const int acc = cc / BN, c0 = cc - acc * BN;
+      const int k = k0 + acc * BM + q * 32 + lane;
       float v[32];
-      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v);
       if (k < K) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -400,24 +407,36 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, float* C, l
   return MYOLO_OK;
 }
 
+template <int BN, int NACC>
+static int launch_wgrad_n(const CUtensorMap& ta, const CUtensorMap& td, float* dW, long long M, int N, int K, int ntaps,
+                          const TapShifts& sh, int transpose_out, cudaStream_t st);
+
 template <int BN>
 static int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& td, float* dW, long long M, int N, int K, int ntaps,
                         const TapShifts& sh, int transpose_out, cudaStream_t st) {
-  const int ntk = K / BM, ntn = N / BN;
+  if (BN * 2 <= 512 && (K % (2 * BM)) == 0) return launch_wgrad_n<BN, (BN * 2 <= 512 ? 2 : 1)>(ta, td, dW, M, N, K, ntaps, sh, transpose_out, st);
+  return launch_wgrad_n<BN, 1>(ta, td, dW, M, N, K, ntaps, sh, transpose_out, st);
+}
+
+template <int BN, int NACC>
+static int launch_wgrad_n(const CUtensorMap& ta, const CUtensorMap& td, float* dW, long long M, int N, int K, int ntaps,
+                          const TapShifts& sh, int transpose_out, cudaStream_t st) {
+  const int ntk = K / (BM * NACC), ntn = N / BN;
   const long long tiles = (long long)ntk * ntn * ntaps;
   long long nsplit = max(1LL, min(ceil_div(M, 32 * 8), (long long)kNumSMs / tiles));
   if (nsplit < 1) nsplit = 1;
   long long chunk = ceil_div(ceil_div(M, nsplit), 32) * 32;
   nsplit = ceil_div(M, chunk);
-  const int stages = 4;
-  const size_t smem = (size_t)stages * (BM + BN) * BK * 4 + 1024;
+  const size_t per_stage = (size_t)(BM * NACC + BN) * BK * 4;
+  const int stages = per_stage * 4 + 1024 <= 220 * 1024 ? 4 : 3;
+  const size_t smem = (size_t)stages * per_stage + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    MYOLO_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MYOLO_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<BN, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   dim3 grid((unsigned)nsplit, (unsigned)(ntk * ntn), (unsigned)ntaps);
-  tc_wgrad_kernel<BN><<<grid, kThreads, smem, st>>>(ta, td, dW, M, N, K, sh, chunk, ntn, transpose_out, stages);
+  tc_wgrad_kernel<BN, NACC><<<grid, kThreads, smem, st>>>(ta, td, dW, M, N, K, sh, chunk, ntn, transpose_out, stages);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }
