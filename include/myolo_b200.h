@@ -140,7 +140,7 @@ int myolo_bn_apply_split(const myolo_view* x, const myolo_view* y_hi, const myol
 /* hi = rna_tf32(src), lo = rna_tf32(src - hi), elementwise over equal-shape views. */
 int myolo_split_tf32(const myolo_view* src, const myolo_view* hi, const myolo_view* lo, myolo_stream stream);
 /* backward of act(BN(x)). train!=0: batch-statistics BN (mean/var are this batch's); else moving stats.
- * dgamma/dbeta are OVERWRITTEN. ws = 2*C doubles. dx may alias dy. */
+ * dgamma/dbeta are OVERWRITTEN. ws = 4*C doubles. dx may alias dy. */
 int myolo_bn_bwd(const myolo_view* x, const myolo_view* dy, const myolo_view* dx, const float* mean, const float* var,
                  const float* gamma, const float* beta, float eps, int act, int train,
                  float* dgamma, float* dbeta, double* ws, myolo_stream stream);

@@ -170,18 +170,26 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(V src, V hi, V lo) {
   }
 }
 
-__global__ void bn_bwd_finalize_kernel(const double* __restrict__ ws, float* __restrict__ dgamma, float* __restrict__ dbeta, int C) {
+// also folds the per-channel constants of the dx pass into a float table behind the sums:
+// coef[0][c] = rs, coef[1][c] = gamma*rs, coef[2][c] = mean(g), coef[3][c] = mean(g*xhat)
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ ws, float* __restrict__ dgamma, float* __restrict__ dbeta, int C,
+                                       const float* __restrict__ var, const float* __restrict__ gamma, float eps,
+                                       double inv_count, int train, float* __restrict__ coef) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) {
     dbeta[c] = (float)ws[c];
     dgamma[c] = (float)ws[C + c];
+    const float rs = 1.f / sqrtf(var[c] + eps);
+    coef[c] = rs;
+    coef[C + c] = gamma[c] * rs;
+    coef[2 * C + c] = train ? (float)(ws[c] * inv_count) : 0.f;
+    coef[3 * C + c] = train ? (float)(ws[C + c] * inv_count) : 0.f;
   }
 }
 
 __global__ void __launch_bounds__(256)
-bn_bwd_dx_kernel(V x, V dy, V dx, const float* __restrict__ mean, const float* __restrict__ var,
-                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int act, int train,
-                 const double* __restrict__ ws, double inv_count) {
+bn_bwd_dx_kernel(V x, V dy, V dx, const float* __restrict__ mean, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, int act, const float* __restrict__ coef) {
   const int C = x.c, C4 = C >> 2;
   const FastDiv x_fc4 = x.fc4;
   const long long total = (long long)x.n * x.h * x.w * C4;
@@ -191,26 +199,24 @@ bn_bwd_dx_kernel(V x, V dy, V dx, const float* __restrict__ mean, const float* _
     const long long p = pp;
     const float4 v = *reinterpret_cast<const float4*>(x.p + pix_off(x, p) + q);
     const float4 g = *reinterpret_cast<const float4*>(dy.p + pix_off(dy, p) + q);
-    const float vin[4] = {v.x, v.y, v.z, v.w};
-    const float gin[4] = {g.x, g.y, g.z, g.w};
+    const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + q));
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + q));
+    const float4 be = __ldg(reinterpret_cast<const float4*>(beta + q));
+    const float4 rs = __ldg(reinterpret_cast<const float4*>(coef + q));
+    const float4 k1 = __ldg(reinterpret_cast<const float4*>(coef + C + q));
+    const float4 m0 = __ldg(reinterpret_cast<const float4*>(coef + 2 * C + q));
+    const float4 m1 = __ldg(reinterpret_cast<const float4*>(coef + 3 * C + q));
+    const float vin[4] = {v.x, v.y, v.z, v.w}, gin[4] = {g.x, g.y, g.z, g.w};
+    const float mua[4] = {mu.x, mu.y, mu.z, mu.w}, gaa[4] = {ga.x, ga.y, ga.z, ga.w}, bea[4] = {be.x, be.y, be.z, be.w};
+    const float rsa[4] = {rs.x, rs.y, rs.z, rs.w}, k1a[4] = {k1.x, k1.y, k1.z, k1.w};
+    const float m0a[4] = {m0.x, m0.y, m0.z, m0.w}, m1a[4] = {m1.x, m1.y, m1.z, m1.w};
     float o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int c = q + j;
-      const float rs = 1.f / sqrtf(__ldg(var + c) + eps);
-      const float ga = __ldg(gamma + c);
-      const float xh = (vin[j] - __ldg(mean + c)) * rs;
-      const float gg = gin[j] * act_grad_mask(fmaf(xh, ga, __ldg(beta + c)), act);
-      if (train) {
-        const float m0 = (float)(ws[c] * inv_count), m1 = (float)(ws[C + c] * inv_count);
-        o[j] = ga * rs * (gg - m0 - xh * m1);
-      } else {
-        o[j] = ga * rs * gg;
-      }
-    }
-    if (act & MYOLO_ROUND_TF32) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) o[j] = round_tf32(o[j]);
+      const float xh = (vin[j] - mua[j]) * rsa[j];
+      const float gg = gin[j] * act_grad_mask(fmaf(xh, gaa[j], bea[j]), act);
+      o[j] = k1a[j] * (gg - m0a[j] - xh * m1a[j]);     // inference-mode BN: m0 = m1 = 0
+      if (act & MYOLO_ROUND_TF32) o[j] = round_tf32(o[j]);
     }
     *reinterpret_cast<float4*>(dx.p + pix_off(dx, p) + q) = make_float4(o[0], o[1], o[2], o[3]);
   }
@@ -408,9 +414,9 @@ extern "C" int myolo_bn_bwd(const myolo_view* x, const myolo_view* dy, const myo
   reduce_grid(total, C, &grid, &chunk);
   MYOLO_CUDA(cudaMemsetAsync(ws, 0, 2 * C * sizeof(double), st));
   colreduce_kernel<2><<<grid, 256, 0, st>>>(to_v(x), to_v(dy), mean, var, gamma, beta, eps, act, ws, ws + C, chunk);
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, dgamma, dbeta, C);
-  bn_bwd_dx_kernel<<<ew_blocks(total * (C / 4)), 256, 0, st>>>(to_v(x), to_v(dy), to_v(dx), mean, var, gamma, beta, eps,
-                                                               act, train, ws, 1.0 / (double)total);
+  float* coef = reinterpret_cast<float*>(ws + 2 * C);   // 4*C floats behind the 2*C sums (ws holds >= 4*C doubles)
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, dgamma, dbeta, C, var, gamma, eps, 1.0 / (double)total, train, coef);
+  bn_bwd_dx_kernel<<<ew_blocks(total * (C / 4)), 256, 0, st>>>(to_v(x), to_v(dy), to_v(dx), mean, gamma, beta, act, coef);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }

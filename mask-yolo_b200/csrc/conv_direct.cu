@@ -63,15 +63,15 @@ template <int S>
 __global__ void __launch_bounds__(256) dw_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ w,
                                                           float* __restrict__ dx, int B, int H, int W, int C, int Ho,
                                                           int Wo) {
-  const int C4 = C >> 2;
-  const long long total = (long long)B * H * W * C4;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+  const unsigned C4 = C >> 2;
+  const unsigned total = (unsigned)B * H * W * C4;   // < 2^31 (checked by the caller): 32-bit index math
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int q = (int)(i % C4);
-    long long p = i / C4;
-    const int ix = (int)(p % W);
-    p /= W;
-    const int iy = (int)(p % H);
-    const int b = (int)(p / H);
+    unsigned p = i / C4;
+    const int ix = (int)(p % (unsigned)W);
+    p /= (unsigned)W;
+    const int iy = (int)(p % (unsigned)H);
+    const int b = (int)(p / (unsigned)H);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
@@ -114,10 +114,11 @@ __global__ void __launch_bounds__(256) dw_bwd_filter_kernel(const float* __restr
 #pragma unroll
   for (int k = 0; k < 9; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (long long p = p0 + pg; p < p1; p += 32) {
-    const int ox = (int)(p % Wo);
-    const long long t = p / Wo;
-    const int oy = (int)(t % Ho);
-    const int b = (int)(t / Ho);
+    const unsigned pu = (unsigned)p;
+    const int ox = (int)(pu % (unsigned)Wo);
+    const unsigned t = pu / (unsigned)Wo;
+    const int oy = (int)(t % (unsigned)Ho);
+    const int b = (int)(t / (unsigned)Ho);
     const float4 g = __ldg(reinterpret_cast<const float4*>(dy + (size_t)p * C + c0));
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
@@ -166,14 +167,14 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict_
   __syncthreads();
   const int So = S / 2;
   const int octs = Cout >> 3;
-  const long long total = (long long)B * So * So * octs;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int o8 = (int)(i % octs);
-    long long p = i / octs;
-    const int ox = (int)(p % So);
-    p /= So;
-    const int oy = (int)(p % So);
-    const int b = (int)(p / So);
+  const unsigned total = (unsigned)B * So * So * octs;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int o8 = (int)(i % (unsigned)octs);
+    unsigned p = i / (unsigned)octs;
+    const int ox = (int)(p % (unsigned)So);
+    p /= (unsigned)So;
+    const int oy = (int)(p % (unsigned)So);
+    const int b = (int)(p / (unsigned)So);
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
@@ -258,6 +259,7 @@ using namespace myolo;
 
 extern "C" int myolo_conv1_fwd(const float* x, const float* w, float* y, int B, int S, int Cout, myolo_stream stream) {
   MYOLO_CHECK_ARG(x && w && y && B > 0 && S > 0 && (S % 2) == 0 && Cout > 0 && (Cout % 8) == 0 && Cout <= 128);
+  MYOLO_CHECK_ARG((long long)B * (S / 2) * (S / 2) * (Cout / 8) < (1LL << 31));
   const long long total = (long long)B * (S / 2) * (S / 2) * (Cout / 8);
   const int blocks = (int)min(ceil_div(total, 256), (long long)kNumSMs * 16);
   conv1_fwd_kernel<<<blocks, 256, 27 * Cout * sizeof(float), as_stream(stream)>>>(x, w, y, B, S, Cout);
@@ -301,6 +303,7 @@ extern "C" int myolo_dwconv3x3_fwd(const myolo_view* xv, const float* w, float* 
 extern "C" int myolo_dwconv3x3_bwd_data(const float* dy, const float* w, float* dx, int B, int H, int W, int C,
                                         int stride, myolo_stream stream) {
   MYOLO_CHECK_ARG(dy && w && dx && B > 0 && H > 0 && W > 0 && C > 0 && (C % 4) == 0 && (stride == 1 || stride == 2));
+  MYOLO_CHECK_ARG((long long)B * H * W * (C / 4) < (1LL << 31));
   const int Ho = dw_out(H, stride), Wo = dw_out(W, stride);
   const long long total = (long long)B * H * W * (C / 4);
   const int blocks = (int)min(ceil_div(total, 256), (long long)kNumSMs * 32);

@@ -151,7 +151,9 @@ class Engine:
             if tr:
                 n = int(np.prod(shape))
                 self.offs[name] = (off, n, shape)
-                off += (n + 3) // 4 * 4                       # 16-byte aligned slices
+                off += (n + 63) // 64 * 64                    # 256-byte aligned slices: kernels read weights in
+                                                              # place through TMA (dgrad B operand); a slice that
+                                                              # straddles 128-byte lines costs 2x L2 requests
         self.n_flat = off
         z = lambda: torch.zeros(off, dtype=torch.float32, device=self.dev)
         self.params, self.grads, self.adam_m, self.adam_v = z(), z(), z(), z()

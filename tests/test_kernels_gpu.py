@@ -100,7 +100,7 @@ def test_bn(C, act, train):
     ya.backward(dy)
     xd, gd, bd = cuda(x.detach()), cuda(g.detach()), cuda(b.detach())
     meand, vard = torch.empty(Cc, device="cuda"), torch.empty(Cc, device="cuda")
-    ws = torch.zeros(2 * Cc, dtype=torch.float64, device="cuda")
+    ws = torch.zeros(4 * Cc, dtype=torch.float64, device="cuda")
     xv = C.view(xd, B, H, W, Cc)
     if train:
         C.call("myolo_bn_stats", xv, meand, vard, ws, stream())
