@@ -22,12 +22,12 @@ namespace myolo {
 namespace tc {
 
 constexpr int WHALO = 16;
-constexpr uint32_t kWStageOut = 4 * 2 * 4096;   // per-epilogue-warp double-buffered 32x32 fp32 staging (TMA store)
+constexpr uint32_t kWStageOut = 4 * 4096;       // per-epilogue-warp 32x32 fp32 staging buffer for the TMA store
 constexpr uint32_t kWEpiVec = 2 * 1024 * 4;     // folded epilogue scale / shift, up to 1024 output channels
-// NACC = 128-row accumulators per work item.  Window = 128*NACC + 32 rows; weight ring 128 KB (NACC 1) / 96 KB (NACC 2)
+// NACC = 128-row accumulators per work item.  Window = 128*NACC + 32 rows; weight ring 160 KB (NACC 1) / 128 KB (NACC 2)
 __host__ __device__ constexpr int win_rows(int nacc) { return 128 * nacc + 2 * WHALO; }
 __host__ __device__ constexpr int win_box(int nacc) { return nacc == 1 ? win_rows(1) : win_rows(2) / 2; }
-__host__ __device__ constexpr uint32_t win_ring(int nacc) { return nacc == 1 ? 131072u : 98304u; }
+__host__ __device__ constexpr uint32_t win_ring(int nacc) { return nacc == 1 ? 163840u : 131072u; }
 __host__ __device__ constexpr uint32_t win_smem(int nacc) {
   return 2u * win_rows(nacc) * 128u + win_ring(nacc) + kWStageOut + kWEpiVec + 1024u;
 }
@@ -177,7 +177,7 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
   } else {
     const int q = warp & 3;
-    const uint32_t sbuf0 = stg0 + (uint32_t)q * 8192u;
+    const uint32_t sbuf0 = stg0 + (uint32_t)q * 4096u;
     const uint32_t evs = smem_u32(evec);
     const int actk = ep.act & 0xff;
     const bool rnd = (ep.act & MYOLO_ROUND_TF32) != 0;
@@ -250,9 +250,10 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int c0 = 0; c0 < WBN; c0 += 32, ++nst) {
           float v[32];
           tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ts * TSTRIDE + (uint32_t)(acc * WBN + c0), v);
-          const uint32_t sbuf = sbuf0 + (nst & 1u) * 4096u;
-          // the store issued two chunks ago (same buffer) must have finished reading shared memory
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          const uint32_t sbuf = sbuf0;
+          // the previous store must have finished reading the staging buffer (the shared memory a second
+          // buffer would take is worth more as a fifth weight stage)
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           __syncwarp();
           const int n0 = half * WBN + c0;
 #pragma unroll

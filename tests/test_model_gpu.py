@@ -185,3 +185,43 @@ def test_yolo_mode_and_second_step():
     errs = sorted(((_l2(ge[k], g_o[k]), _l2(g_32[k], g_o[k]), k) for k in g_o), reverse=True)
     print(f"[yolo mode] gradient rel-L2 errors vs fp64 (engine, oracle32), worst first: {errs[:6]}")
     _check_grad_errors(errs, exact=True)
+
+
+def _engine_pair_case(S, B, NB, NC, seed):
+    from myolo.engine import init_params
+    anchors = [1.27, 1.31, 1.95, 1.85, 2.40, 2.72, 3.20, 3.32, 5.06, 5.05][:2 * NB]
+    c = Hh.engine_cfg(S=S, NB=NB, NC=NC, TB=10, anchors=anchors, maxgt=10)
+    P = init_params(NB, NC, seed, "trained_like")
+    g = torch.Generator().manual_seed(seed)
+    image = torch.rand(B, S, S, 3, generator=g)
+    inputs = Hh.batch_from_boxes(c, B, image, Hh.random_boxes(B, 6, seed + 1), seed + 2)
+    return c, P, inputs
+
+
+@pytest.mark.parametrize("S,B,NB,NC", [(416, 2, 5, 2), (640, 1, 5, 81)])
+def test_large_configs_tensor_core_path_matches_exact_fp32_path(S, B, NB, NC):
+    """BASELINE configs[2] (416x416, dense ROIs, R=845) and configs[4] (640x640, 80 classes, R=2000)
+    at reduced batch: the tcgen05 path (tf32x3) against the exact CUDA-core path of the same engine
+    (the CPU oracle needs minutes at these sizes; fp32 engine == oracle is established at 128x128)."""
+    from myolo.engine import Engine
+    c, P, inputs = _engine_pair_case(S, B, NB, NC, 400 + S)
+    dev_in = Hh.to_device(inputs)
+    outs = {}
+    for prec in ("fp32", "tf32x3"):
+        eng = Engine(c, B, "training", prec, params=P)
+        o = eng.train_step(dev_in, lr=1e-3)
+        torch.cuda.synchronize()
+        outs[prec] = {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in o.items()}
+        outs[prec]["grads"] = eng.grad_dict()
+        del eng
+        torch.cuda.empty_cache()
+    a, b = outs["fp32"], outs["tf32x3"]
+    assert a["myolo_mask"].shape == (B, c["R"], 28, 28, NC)
+    for k in ("yolo_sum_loss", "mask_loss"):
+        assert torch.isfinite(a[k]) and abs(a[k].item() - b[k].item()) <= 3e-3 * max(1.0, abs(a[k].item())), k
+    assert _abs(b["yolo_proposals"], a["yolo_proposals"]) <= 1e-3
+    assert torch.equal(a["target_class_ids"], b["target_class_ids"])
+    bad = ((a["myolo_mask"] - b["myolo_mask"]).abs() > 1e-3).float().mean().item()
+    assert bad <= 1e-3, bad                       # masks: see smoke() on ROIs that straddle the feature-map border
+    rows = [(_l2(b["grads"][k], a["grads"][k]), k) for k in a["grads"] if a["grads"][k].abs().max() > 0 and k != "myolo_mask_conv1/bias"]
+    assert max(rows)[0] <= 8e-2 and sorted(rows)[len(rows) // 2][0] <= 2e-2, max(rows)
