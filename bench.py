@@ -29,8 +29,8 @@ METRIC = "images/sec fwd+bwd @224x224 Shapes"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="per-GPU batch")
     ap.add_argument("--size", type=int, default=224)
@@ -179,7 +179,9 @@ def main():
     dev_batches = []
     for hb in host_batches:
         staged = model._stage(hb)
+        torch.cuda.synchronize()
         dev_batches.append([t.clone() for t in staged])
+    eng.inputs_ready = None
     torch.cuda.synchronize()
     B, K, W = args.batch, args.steps, args.warmup
 

@@ -120,6 +120,7 @@ class Engine:
         self.with_mask = mode != "yolo"
         self._frozen = False
         self._shift_cache = {}
+        self.inputs_ready = None       # optional CUDA event: inputs[1:] of forward_training are complete
         self.kernel_events = None      # bench.py: list collecting (start, end) CUDA events of the dominant kernel
         self.t = 0                     # Adam iteration
         self.seen = 0                  # yolo_custom_loss `seen` counter (model.py:95, 197)
@@ -476,6 +477,9 @@ class Engine:
         A, B, st, cfg = self.A, self.B, self._st(), self.cfg
         G, NB, NC, TB, R = cfg["G"], self.NB, self.NC, self.TB, self.R
         yolo = self.forward(image, training=True)
+        if self.inputs_ready is not None:      # ground-truth tensors still in flight on the caller's copy stream
+            torch.cuda.current_stream().wait_event(self.inputs_ready)
+            self.inputs_ready = None
         self.seen += 1
         warm = 1 if self.seen < cfg.get("WARM_UP_BATCHES", 0) else 0
         lw = cfg.get("LOSS_WEIGHTS", {})

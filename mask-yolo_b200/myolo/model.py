@@ -304,15 +304,30 @@ class MaskYOLO:
             for x, dt in zip(inputs, want):
                 host = torch.empty(tuple(np.shape(x)), dtype=dt).pin_memory()
                 self._stage_bufs.append((host, torch.empty_like(host, device=self.engine.dev)))
+        # copies run on a side stream in consumption order: the step starts as soon as the IMAGE has
+        # landed; the ground-truth tensors (two thirds of the bytes) arrive under the backbone forward and
+        # are awaited right before the first kernel that reads them (Engine.inputs_ready)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.engine.dev)
+        main = torch.cuda.current_stream(self.engine.dev)
+        self._copy_stream.wait_stream(main)               # the previous step no longer reads the device buffers
         out, nbytes = [], 0
-        for (host, devt), x in zip(self._stage_bufs, inputs):
-            if isinstance(x, torch.Tensor):
-                host.copy_(x)
-            else:
-                host.copy_(torch.from_numpy(np.ascontiguousarray(x)))
-            devt.copy_(host, non_blocking=True)
-            nbytes += host.numel() * host.element_size()
-            out.append(devt)
+        with torch.cuda.stream(self._copy_stream):
+            for k, ((host, devt), x) in enumerate(zip(self._stage_bufs, inputs)):
+                if isinstance(x, torch.Tensor):
+                    host.copy_(x)
+                else:
+                    host.copy_(torch.from_numpy(np.ascontiguousarray(x)))
+                devt.copy_(host, non_blocking=True)
+                if k == 0:
+                    ev_img = torch.cuda.Event()
+                    ev_img.record(self._copy_stream)
+                nbytes += host.numel() * host.element_size()
+                out.append(devt)
+            ev_all = torch.cuda.Event()
+            ev_all.record(self._copy_stream)
+        main.wait_event(ev_img)
+        self.engine.inputs_ready = ev_all
         self.last_h2d_bytes = nbytes
         return out
 
