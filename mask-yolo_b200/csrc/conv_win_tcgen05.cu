@@ -53,7 +53,11 @@ struct MaskTail {
   int H, W, NC;
 };
 
-template <int WBN, int NACC>
+// CG = 2: the work item is shared by a CTA pair (cluster of two, cta_group::2): M = 256 rows per MMA, each
+// CTA holds 128 of them (its own activation window and TMEM accumulator) and HALF of every weight stage,
+// which halves the L2->SM fill per FLOP -- the limiter of the single-CTA variant (measured: 1.27 ms with
+// the loads removed vs 1.60 ms with them; per-SM fill rate 66 B/clk needed vs ~64 B/clk available).
+template <int WBN, int NACC, int CG>
 __global__ void __launch_bounds__(kThreads)
 tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmC, long long M, int N, int K, int ntaps, TapShifts sh, Epi ep,
@@ -61,8 +65,11 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   constexpr int WBM = 128 * NACC, WROWS = win_rows(NACC), WBOX = win_box(NACC);
   constexpr uint32_t kWinBytes = WROWS * 128;
-  constexpr uint32_t kWBBytes = WBN * 128;
+  constexpr uint32_t kWBBytes = (WBN / CG) * 128;          // this CTA's share of one weight stage
   constexpr int kWBStages = win_ring(NACC) / kWBBytes;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const int cid = blockIdx.x / CG, ncl = gridDim.x / CG;   // work is distributed over clusters
   constexpr uint32_t TS = (WBN * NACC <= 256) ? 2 : 1;     // TMEM stages (epilogue overlapped when 2)
   constexpr uint32_t TSTRIDE = WBN * NACC;                  // TMEM columns per stage
   __shared__ __align__(8) uint64_t bars[2 + 2 + kWBStages * 2 + 4];
@@ -89,7 +96,7 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       mbar_init(a_full(i), 1);
       mbar_init(a_empty(i), 1);
       mbar_init(t_full(i), 1);
-      mbar_init(t_empty(i), 4);  // one arrival per epilogue warp
+      mbar_init(t_empty(i), 4 * CG);  // one arrival per epilogue warp (of both CTAs of a pair)
     }
     for (int i = 0; i < kWBStages; ++i) {
       mbar_init(b_full(i), 1);
@@ -109,40 +116,60 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       evec[N + n] = ep.scale ? fmaf(b, sc, __ldg(ep.shift + n)) : b;
     }
   }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), 512);
+  if (warp == 1) {
+    if (CG == 2) tmem_alloc_2sm(smem_u32(&tmem_slot), 512);
+    else tmem_alloc(smem_u32(&tmem_slot), 512);
+  }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();   // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t a_it = 0, b_it = 0;
-      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      for (int item = cid; item < nitems; item += ncl) {
         const int tile = item / nh, half = item - tile * nh;
-        const int row0 = tile * WBM - WHALO;
+        const int row0 = tile * (WBM * CG) + (int)rank * WBM - WHALO;
         for (int kb = 0; kb < kblocks; ++kb) {
           const uint32_t ab = a_it & 1u;
           mbar_wait(a_empty(ab), ((a_it >> 1) & 1u) ^ 1u);
           const uint32_t wa = awin0 + ab * kWinBytes;
-          mbar_expect_tx(a_full(ab), kWinBytes);
-          tma_load_2d(wa, &tmA, a_full(ab), kb * BK, row0);
-          if (NACC == 2) tma_load_2d(wa + WBOX * 128, &tmA, a_full(ab), kb * BK, row0 + WBOX);
+          if (CG == 2) {
+            // both CTAs' loads complete on the LEADER's barrier, which expects the bytes of the pair
+            if (leader) mbar_expect_tx(a_full(ab), 2 * kWinBytes);
+            tma_load_2d_2sm(wa, &tmA, mapa_rank(a_full(ab), 0), kb * BK, row0);
+          } else if (dbg & 2) {
+            mbar_arrive(a_full(ab));
+          } else {
+            mbar_expect_tx(a_full(ab), kWinBytes);
+            tma_load_2d(wa, &tmA, a_full(ab), kb * BK, row0);
+            if (NACC == 2) tma_load_2d(wa + WBOX * 128, &tmA, a_full(ab), kb * BK, row0 + WBOX);
+          }
           ++a_it;
           for (int t = 0; t < ntaps; ++t, ++b_it) {
             const uint32_t s = b_it % kWBStages;
             mbar_wait(b_empty(s), ((b_it / kWBStages) & 1u) ^ 1u);
-            mbar_expect_tx(b_full(s), kWBBytes);
-            tma_load_2d(bst0 + s * kWBBytes, &tmB, b_full(s), kb * BK, t * N + half * WBN);
+            if (CG == 2) {
+              if (leader) mbar_expect_tx(b_full(s), 2 * kWBBytes);
+              tma_load_2d_2sm(bst0 + s * kWBBytes, &tmB, mapa_rank(b_full(s), 0), kb * BK,
+                              t * N + half * WBN + (int)rank * (WBN / 2));
+            } else if (dbg & 2) {
+              mbar_arrive(b_full(s));
+            } else {
+              mbar_expect_tx(b_full(s), kWBBytes);
+              tma_load_2d(bst0 + s * kWBBytes, &tmB, b_full(s), kb * BK, t * N + half * WBN);
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(128, WBN, 0, 0);
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc(128 * CG, WBN, 0, 0);
       uint32_t a_it = 0, b_it = 0, it = 0;
-      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+      for (int item = cid; item < nitems; item += ncl, ++it) {
         const uint32_t ts = it % TS;
         mbar_wait(t_empty(ts), ((it / TS) & 1u) ^ 1u);  // the epilogue that last used this TMEM stage has drained it
         tc_fence_after();
@@ -164,15 +191,20 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               // absolute smem address, so no base_offset is needed (verified on B200)
               const uint64_t da = make_desc(wa + (row + 128u * acc) * 128u, 16, 1024);
 #pragma unroll
-              for (int k = 0; k < BK / 8; ++k)
-                umma_tf32(tacc + (uint32_t)WBN * acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
-                          (kb | t | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < BK / 8; ++k) {
+                if (CG == 2)
+                  umma_tf32_2sm(tacc + (uint32_t)WBN * acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                                (kb | t | k) != 0 ? 1u : 0u);
+                else
+                  umma_tf32(tacc + (uint32_t)WBN * acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                            (kb | t | k) != 0 ? 1u : 0u);
+              }
             }
-            umma_commit(b_empty(s));
+            if (CG == 2) umma_commit_2sm(b_empty(s)); else umma_commit(b_empty(s));
           }
-          umma_commit(a_empty(ab));
+          if (CG == 2) umma_commit_2sm(a_empty(ab)); else umma_commit(a_empty(ab));
         }
-        umma_commit(t_full(ts));
+        if (CG == 2) umma_commit_2sm(t_full(ts)); else umma_commit(t_full(ts));
       }
     }
   } else {
@@ -182,8 +214,9 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int actk = ep.act & 0xff;
     const bool rnd = (ep.act & MYOLO_ROUND_TF32) != 0;
     uint32_t it = 0, nst = 0;
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
-      const int tile = item / nh, half = item - tile * nh;
+    for (int item = cid; item < nitems; item += ncl, ++it) {
+      const int half = item % nh;
+      const int tile = (item / nh) * CG + (int)rank;      // this CTA's 128*NACC-row tile
       const uint32_t ts = it % TS;
       mbar_wait(t_full(ts), (it / TS) & 1u);
       tc_fence_after();
@@ -280,13 +313,20 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(t_empty(ts));
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(mapa_rank(t_empty(ts), 0));   // the leader's MMA thread owns the TMEM hand-back
+        else mbar_arrive(t_empty(ts));
+      }
     }
     if (lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 512);
+  if (CG == 2) cluster_sync_all();   // no CTA of the pair may free TMEM / exit while the other still uses it
+  if (warp == 1) {
+    if (CG == 2) tmem_dealloc_2sm(tmem, 512);
+    else tmem_dealloc(tmem, 512);
+  }
 }
 
 }  // namespace tc
@@ -326,33 +366,70 @@ static int launch_win(const float* A, long long lda, const float* Bt, float* C, 
   static int bo_mode = -1;
   if (bo_mode < 0) {
     const char* e = getenv("MYOLO_WIN_BO");
-    bo_mode = e ? atoi(e) : 0;  // experiment switches: 4 = skip the global stores, 8 = 128-column slices, 16 = two accumulators
+    bo_mode = e ? atoi(e) : 0;  // experiment switches: 2 = no TMA loads, 4 = skip the global stores, 8 = 128-column slices, 16 = two accumulators, 32 = no CTA pairs
   }
   const int wbn = (((bo_mode & 8) && !mt.masks) || (N % 256) != 0) ? 128 : 256;
   // one accumulator + two TMEM stages (epilogue overlapped with the next item's main loop) is the default;
   // the two-accumulator variant halves the weight traffic from L2 but exposes its epilogue
   const int nacc = (bo_mode & 16) ? 2 : 1;
+  // CTA-pair variant (cta_group::2): 256-column slices, one accumulator per CTA; MYOLO_WIN_BO & 32 disables it
+  const int cg = (wbn == 256 && nacc == 1 && !(bo_mode & 32) && !(bo_mode & 2)) ? 2 : 1;
   int rc = get_map(A, M + maxs, K, lda, win_box(nacc), &ta);
   if (rc) return rc;
-  rc = get_map(Bt, (long long)ntaps * N, K, K, wbn, &tb);
+  rc = get_map(Bt, (long long)ntaps * N, K, K, wbn / cg, &tb);
   if (rc) return rc;
   CUtensorMap tc_;
   rc = get_map(C, M, N, ldc, 32, &tc_);
   if (rc) return rc;
   static bool attr_set = false;
+  static int max_clusters = 0;
   if (!attr_set) {
-    MYOLO_CUDA(cudaFuncSetAttribute(tc_conv_win_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem(1)));
-    MYOLO_CUDA(cudaFuncSetAttribute(tc_conv_win_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem(1)));
-    MYOLO_CUDA(cudaFuncSetAttribute(tc_conv_win_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem(2)));
-    MYOLO_CUDA(cudaFuncSetAttribute(tc_conv_win_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem(2)));
+    MYOLO_CUDA(cudaFuncSetAttribute(tc_conv_win_kernel<128, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem(1)));
+    MYOLO_CUDA(cudaFuncSetAttribute(tc_conv_win_kernel<256, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem(1)));
+    MYOLO_CUDA(cudaFuncSetAttribute(tc_conv_win_kernel<128, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem(2)));
+    MYOLO_CUDA(cudaFuncSetAttribute(tc_conv_win_kernel<256, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem(2)));
+    MYOLO_CUDA(cudaFuncSetAttribute(tc_conv_win_kernel<256, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem(1)));
+    {   // how many CTA pairs fit at once (GPCs with an odd SM count leave SMs unpaired)
+      cudaLaunchConfig_t q = {};
+      q.gridDim = dim3(kNumSMs);
+      q.blockDim = dim3(kThreads);
+      q.dynamicSmemBytes = win_smem(1);
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      q.attrs = at;
+      q.numAttrs = 1;
+      if (cudaOccupancyMaxActiveClusters(&max_clusters, tc_conv_win_kernel<256, 1, 2>, &q) != cudaSuccess) max_clusters = 0;
+      (void)cudaGetLastError();
+    }
     attr_set = true;
+  }
+  Epi ep{bias, scale, shift_c, act, pf_w1, pf_blk, accumulate};
+  cudaStream_t st = as_stream(stream);
+  if (cg == 2 && max_clusters > 0) {
+    const int nitems = (int)ceil_div(M, 256) * (N / wbn);
+    const int ncl = nitems < max_clusters ? nitems : max_clusters;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * ncl);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = win_smem(1);
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    MYOLO_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_win_kernel<256, 1, 2>, ta, tb, tc_, M, N, K, ntaps, sh, ep, mt, nitems, bo_mode));
+    return MYOLO_OK;
+  }
+  if (cg == 2) {   // no pair fits (should not happen on B200): rebuild the weight map for the single-CTA box
+    rc = get_map(Bt, (long long)ntaps * N, K, K, wbn, &tb);
+    if (rc) return rc;
   }
   const int nitems = (int)ceil_div(M, 128 * nacc) * (N / wbn);
   const int grid = nitems < kNumSMs ? nitems : kNumSMs;
-  Epi ep{bias, scale, shift_c, act, pf_w1, pf_blk, accumulate};
-  cudaStream_t st = as_stream(stream);
 #define MYOLO_WIN_LAUNCH(BN_, NA_) \
-  tc_conv_win_kernel<BN_, NA_><<<grid, kThreads, win_smem(NA_), st>>>(ta, tb, tc_, M, N, K, ntaps, sh, ep, mt, nitems, bo_mode)
+  tc_conv_win_kernel<BN_, NA_, 1><<<grid, kThreads, win_smem(NA_), st>>>(ta, tb, tc_, M, N, K, ntaps, sh, ep, mt, nitems, bo_mode)
   if (wbn == 256 && nacc == 1) MYOLO_WIN_LAUNCH(256, 1);
   else if (wbn == 256) MYOLO_WIN_LAUNCH(256, 2);
   else if (nacc == 1) MYOLO_WIN_LAUNCH(128, 1);
