@@ -246,22 +246,42 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
               for (int j = 0; j < 8; ++j) yp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             }
+            // h = relu(acc + bd): the 8 bias vectors are fetched as one batch of independent LDS.128 ...
+            {
+              float4 b4[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 b4;
-              asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(evs + 4u * (c0 + 4 * j)));
-              const float h0 = fmaxf(v[4 * j] + b4.x, 0.f), h1 = fmaxf(v[4 * j + 1] + b4.y, 0.f);
-              const float h2 = fmaxf(v[4 * j + 2] + b4.z, 0.f), h3 = fmaxf(v[4 * j + 3] + b4.w, 0.f);
+              for (int j = 0; j < 8; ++j)
+                asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b4[j].x), "=f"(b4[j].y), "=f"(b4[j].z), "=f"(b4[j].w) : "r"(evs + 4u * (c0 + 4 * j)));
 #pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                if (k < mt.NC) {
-                  float4 w4;
-                  asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(w4.x), "=f"(w4.y), "=f"(w4.z), "=f"(w4.w) : "r"(evs + 4u * (256 + k * 256 + c0 + 4 * j)));
-                  lg[k] = fmaf(h0, w4.x, lg[k]);
-                  lg[k] = fmaf(h1, w4.y, lg[k]);
-                  lg[k] = fmaf(h2, w4.z, lg[k]);
-                  lg[k] = fmaf(h3, w4.w, lg[k]);
+              for (int j = 0; j < 8; ++j) {
+                v[4 * j] = fmaxf(v[4 * j] + b4[j].x, 0.f);
+                v[4 * j + 1] = fmaxf(v[4 * j + 1] + b4[j].y, 0.f);
+                v[4 * j + 2] = fmaxf(v[4 * j + 2] + b4[j].z, 0.f);
+                v[4 * j + 3] = fmaxf(v[4 * j + 3] + b4[j].w, 0.f);
+              }
+            }
+            // ... and so are the 32 weights of each class (the one-load-then-four-FMAs form of this loop was
+            // bound by shared-memory latency: 62 % of the kernel's stall samples)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              if (k < mt.NC) {
+                float4 w4[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(w4[j].x), "=f"(w4[j].y), "=f"(w4[j].z), "=f"(w4[j].w) : "r"(evs + 4u * (256 + k * 256 + c0 + 4 * j)));
+                float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) {
+                  s0 = fmaf(v[4 * j], w4[j].x, s0);
+                  s0 = fmaf(v[4 * j + 1], w4[j].y, s0);
+                  s0 = fmaf(v[4 * j + 2], w4[j].z, s0);
+                  s0 = fmaf(v[4 * j + 3], w4[j].w, s0);
+                  s1 = fmaf(v[4 * j + 4], w4[j + 1].x, s1);
+                  s1 = fmaf(v[4 * j + 5], w4[j + 1].y, s1);
+                  s1 = fmaf(v[4 * j + 6], w4[j + 1].z, s1);
+                  s1 = fmaf(v[4 * j + 7], w4[j + 1].w, s1);
                 }
+                lg[k] += s0 + s1;
               }
             }
           }

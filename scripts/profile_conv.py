@@ -18,8 +18,19 @@ w = torch.randn(9, 256, 256, device="cuda") / 48
 bias = torch.zeros(256, device="cuda")
 dw = torch.zeros(9, 256, 256, device="cuda")
 flops = 2.0 * n * 196 * 2304 * 256
+NC = 4
+y4 = PF(n, 14, 14, 1024) if which == "deconv" else None
+kd = torch.randn(1024, 256, device="cuda") / 16 if which == "deconv" else None
+w1 = torch.randn(256, NC, device="cuda") / 16
+b1 = torch.zeros(NC, device="cuda")
+masks = torch.empty(n, 28, 28, NC, device="cuda") if which == "deconv" else None
+ids = torch.zeros(n, dtype=torch.int32, device="cuda")
+if which == "deconv":
+    flops = 2.0 * n * 196 * 256 * 1024
 def run():
-    if which == "fwd":
+    if which == "deconv":
+        C.call("myolo_deconv_mask_fwd", x.rows, kd, bias, w1, b1, masks, ids, y4.rows, n, 14, 14, 256, NC, st)
+    elif which == "fwd":
         C.call("myolo_conv3x3_fwd", x.rows, w, y.rows, n, 14, 14, 256, 256, bias, None, None, 0, st)
     elif which == "wgrad":
         C.call("myolo_conv3x3_wgrad", x.rows, y.rows, dw, n, 14, 14, 256, 256, st)
