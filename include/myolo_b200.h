@@ -126,8 +126,11 @@ int myolo_conv3x3_fwd(const float* x, const float* wt, float* y, int n_img, int 
 int myolo_conv3x3_dgrad(const float* dy, const float* w, float* dx, int n_img, int H, int W, int Cin, int Cout, myolo_stream stream);
 int myolo_conv3x3_wgrad(const float* x, const float* dy, float* dw, int n_img, int H, int W, int Cin, int Cout, myolo_stream stream);
 
-/* ---- K4/K5/K9: batch norm + activation (Keras BatchNormalization eps 1e-3) ---- */
-/* mean[c], var[c] (biased) over all pixels of x; ws = 2*C doubles of scratch (zeroed inside). */
+/* ---- K4/K5/K9: batch norm + activation (Keras BatchNormalization eps 1e-3) ----
+ * Workspace `ws` of every entry point in this block: MYOLO_BN_WS_DOUBLES doubles (C <= 1024), ZERO before the
+ * first call; the reductions finalize and reset their sums and tickets themselves (one launch each). */
+#define MYOLO_BN_WS_DOUBLES 4112
+/* mean[c], var[c] (biased) over all pixels of x, single pass (sum and sum of squares in fp64). */
 int myolo_bn_stats(const myolo_view* x, float* mean, float* var, double* ws, myolo_stream stream);
 /* y = act(gamma*(x-mean)*rsqrt(var+eps)+beta) */
 int myolo_bn_apply(const myolo_view* x, const myolo_view* y, const float* mean, const float* var,
@@ -140,7 +143,7 @@ int myolo_bn_apply_split(const myolo_view* x, const myolo_view* y_hi, const myol
 /* hi = rna_tf32(src), lo = rna_tf32(src - hi), elementwise over equal-shape views. */
 int myolo_split_tf32(const myolo_view* src, const myolo_view* hi, const myolo_view* lo, myolo_stream stream);
 /* backward of act(BN(x)). train!=0: batch-statistics BN (mean/var are this batch's); else moving stats.
- * dgamma/dbeta are OVERWRITTEN. ws = 4*C doubles. dx may alias dy. */
+ * dgamma/dbeta are OVERWRITTEN. dx may alias dy. */
 int myolo_bn_bwd(const myolo_view* x, const myolo_view* dy, const myolo_view* dx, const float* mean, const float* var,
                  const float* gamma, const float* beta, float eps, int act, int train,
                  float* dgamma, float* dbeta, double* ws, myolo_stream stream);
@@ -150,7 +153,7 @@ int myolo_bn_fold(const float* gamma, const float* beta, const float* mean, cons
                   float* scale, float* shift, int C, myolo_stream stream);
 /* backward of a = act(BN_fixed_stats(conv + bias)) from the OUTPUT a only (the pre-BN tensor is never
  * stored): dx = dy*act'(a)*gamma*rs (may alias dy), dgamma/dbeta OVERWRITTEN, dbias (nullable) =
- * gamma*rs*dbeta = gradient of the conv bias.  ws = 2*C doubles. */
+ * gamma*rs*dbeta = gradient of the conv bias. */
 int myolo_bn_act_bwd_from_output(const myolo_view* a, const myolo_view* dy, const myolo_view* dx, const float* gamma,
                                  const float* beta, const float* var, float eps, int act, float* dgamma, float* dbeta,
                                  float* dbias, double* ws, myolo_stream stream);
@@ -158,7 +161,11 @@ int myolo_bn_act_bwd_from_output(const myolo_view* a, const myolo_view* dy, cons
  * moving = biased/(1-momentum^step). value = mean, or var*bessel*n/(n-(1+eps)) when is_var. */
 int myolo_bn_moving_update(const float* value, float* biased, float* moving, int C, float momentum, int step,
                            int is_var, double n, float eps, myolo_stream stream);
-/* out[c] (=|+=) sum over pixels of x[.,c]  (bias gradients). ws = C doubles. */
+/* the same update for many (layer, statistic) pairs in ONE launch.  items_dev: device array of n_items records
+ * { const float* value; float* biased; float* moving; int C; float corr; } (32 bytes each, corr = 1 for means,
+ * bessel * n/(n-(1+eps)) for variances); every item shares the step count. */
+int myolo_bn_moving_update_batch(const void* items_dev, int n_items, float momentum, int step, myolo_stream stream);
+/* out[c] = sum over pixels of x[.,c]  (bias gradients). */
 int myolo_colsum(const myolo_view* x, float* out, double* ws, myolo_stream stream);
 /* dst (=|+=) src over valid pixels (dense <-> padded-flat moves, gradient joins).
  * accumulate bit 0: dst += src; bit 1: round the stored value to tf32. */

@@ -53,12 +53,30 @@ __device__ __forceinline__ float act_grad_mask(float y, int act) {
 
 // MODE 0: s0 += x                 MODE 1: s0 += (x-mean)^2
 // MODE 2: g = dy*act'(y); s0 += g; s1 += g*xhat
+// MODE 3: s0 += x; s1 += x^2   (single-pass batch statistics)
+//
+// Every reduction ends with the "last block finalizes" pattern: blocks add their partial sums to the fp64
+// workspace with atomics, take a ticket, and the block that draws the last ticket of its channel group
+// turns the sums into the result (mean/var, dgamma/dbeta + the dx coefficient table, plain column sums)
+// and ZEROES sums and ticket again.  One launch instead of memset + reduce + finalize (x2 for the
+// statistics); the workspace must be zero before the first call and is zero after every call.
+struct Fin {
+  float* o0;          // MODE 0: column sums | MODE 2: dbeta | MODE 3: mean
+  float* o1;          //                       MODE 2: dgamma | MODE 3: var
+  float* coef;        // MODE 2: [rs | gamma*rs | mean(g) | mean(g*xhat)] x C   (nullable)
+  int* ticket;        // one counter per 32-channel group
+  double inv_count;   // 1 / pixels
+  int train;          // MODE 2: batch-statistics BN (mean terms) or fixed statistics
+  int C;
+};
+
 template <int MODE>
 __global__ void __launch_bounds__(256)
 colreduce_kernel(V x, V dy, const float* __restrict__ mean, const float* __restrict__ var,
                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int act,
-                 double* __restrict__ out0, double* __restrict__ out1, long long chunk) {
+                 double* __restrict__ out0, double* __restrict__ out1, long long chunk, Fin fin) {
   __shared__ float red[2][32][33];
+  __shared__ int s_last;
   const int tid = threadIdx.x;
   const int cq = tid & 7, pg = tid >> 3;
   const int c0 = blockIdx.y * 32 + cq * 4;
@@ -80,6 +98,9 @@ colreduce_kernel(V x, V dy, const float* __restrict__ mean, const float* __restr
     } else if (MODE == 1) {
       const float a = v.x - mu.x, b = v.y - mu.y, c = v.z - mu.z, d = v.w - mu.w;
       s0.x = fmaf(a, a, s0.x); s0.y = fmaf(b, b, s0.y); s0.z = fmaf(c, c, s0.z); s0.w = fmaf(d, d, s0.w);
+    } else if (MODE == 3) {
+      s0.x += v.x; s0.y += v.y; s0.z += v.z; s0.w += v.w;
+      s1.x = fmaf(v.x, v.x, s1.x); s1.y = fmaf(v.y, v.y, s1.y); s1.z = fmaf(v.z, v.z, s1.z); s1.w = fmaf(v.w, v.w, s1.w);
     } else {
       const float4 g = *reinterpret_cast<const float4*>(dy.p + pix_off(dy, p) + c0);
       const float xh0 = (v.x - mu.x) * rs.x, xh1 = (v.y - mu.y) * rs.y, xh2 = (v.z - mu.z) * rs.z, xh3 = (v.w - mu.w) * rs.w;
@@ -92,11 +113,11 @@ colreduce_kernel(V x, V dy, const float* __restrict__ mean, const float* __restr
     }
   }
   red[0][cq * 4 + 0][pg] = s0.x; red[0][cq * 4 + 1][pg] = s0.y; red[0][cq * 4 + 2][pg] = s0.z; red[0][cq * 4 + 3][pg] = s0.w;
-  if (MODE == 2) {
+  if (MODE >= 2) {
     red[1][cq * 4 + 0][pg] = s1.x; red[1][cq * 4 + 1][pg] = s1.y; red[1][cq * 4 + 2][pg] = s1.z; red[1][cq * 4 + 3][pg] = s1.w;
   }
   __syncthreads();
-  const int nred = (MODE == 2) ? 64 : 32;
+  const int nred = (MODE >= 2) ? 64 : 32;
   if (tid < nred) {
     const int which = tid >> 5, c = tid & 31;
     double s = 0.0;
@@ -104,6 +125,39 @@ colreduce_kernel(V x, V dy, const float* __restrict__ mean, const float* __restr
     for (int j = 0; j < 32; ++j) s += (double)red[which][c][j];
     atomicAdd((which ? out1 : out0) + blockIdx.y * 32 + c, s);
   }
+  if (fin.ticket == nullptr) return;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(fin.ticket + blockIdx.y, 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (tid < 32) {
+    const int c = blockIdx.y * 32 + tid;
+    const double S0 = *(volatile double*)(out0 + c);
+    const double S1 = (MODE >= 2) ? *(volatile double*)(out1 + c) : 0.0;
+    if (MODE == 0) {
+      fin.o0[c] = (float)S0;
+    } else if (MODE == 3) {
+      const double m = S0 * fin.inv_count;
+      const double vv = S1 * fin.inv_count - m * m;
+      fin.o0[c] = (float)m;
+      fin.o1[c] = (float)(vv > 0.0 ? vv : 0.0);
+    } else if (MODE == 2) {
+      fin.o0[c] = (float)S0;
+      fin.o1[c] = (float)S1;
+      if (fin.coef) {
+        const float r = 1.f / sqrtf(var[c] + eps);
+        fin.coef[c] = r;
+        fin.coef[fin.C + c] = gamma[c] * r;
+        fin.coef[2 * fin.C + c] = fin.train ? (float)(S0 * fin.inv_count) : 0.f;
+        fin.coef[3 * fin.C + c] = fin.train ? (float)(S1 * fin.inv_count) : 0.f;
+      }
+    }
+    out0[c] = 0.0;
+    if (MODE >= 2) out1[c] = 0.0;
+  }
+  if (tid == 0) fin.ticket[blockIdx.y] = 0;
 }
 
 // arbitrary (small) C: one thread per channel, serial over pixels.  Only used for tiny tensors.
@@ -116,9 +170,12 @@ __global__ void colsum_generic_kernel(V x, double* __restrict__ out) {
   atomicAdd(out + c, s);
 }
 
-__global__ void finalize_div_kernel(const double* __restrict__ s, float* __restrict__ out, int C, double inv, int accumulate) {
+__global__ void finalize_div_kernel(double* __restrict__ s, float* __restrict__ out, int C, double inv, int accumulate) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < C) out[c] = (accumulate ? out[c] : 0.f) + (float)(s[c] * inv);
+  if (c < C) {
+    out[c] = (accumulate ? out[c] : 0.f) + (float)(s[c] * inv);
+    s[c] = 0.0;   // workspace invariant: zero after every call
+  }
 }
 
 // SPLIT: y receives hi = rna_tf32(v) and ylo receives rna_tf32(v - hi) (operand pair of a 3xTF32 GEMM)
@@ -170,23 +227,6 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(V src, V hi, V lo) {
   }
 }
 
-// also folds the per-channel constants of the dx pass into a float table behind the sums:
-// coef[0][c] = rs, coef[1][c] = gamma*rs, coef[2][c] = mean(g), coef[3][c] = mean(g*xhat)
-__global__ void bn_bwd_finalize_kernel(const double* __restrict__ ws, float* __restrict__ dgamma, float* __restrict__ dbeta, int C,
-                                       const float* __restrict__ var, const float* __restrict__ gamma, float eps,
-                                       double inv_count, int train, float* __restrict__ coef) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < C) {
-    dbeta[c] = (float)ws[c];
-    dgamma[c] = (float)ws[C + c];
-    const float rs = 1.f / sqrtf(var[c] + eps);
-    coef[c] = rs;
-    coef[C + c] = gamma[c] * rs;
-    coef[2 * C + c] = train ? (float)(ws[c] * inv_count) : 0.f;
-    coef[3 * C + c] = train ? (float)(ws[C + c] * inv_count) : 0.f;
-  }
-}
-
 __global__ void __launch_bounds__(256)
 bn_bwd_dx_kernel(V x, V dy, V dx, const float* __restrict__ mean, const float* __restrict__ gamma,
                  const float* __restrict__ beta, int act, const float* __restrict__ coef) {
@@ -233,6 +273,24 @@ __global__ void bn_moving_update_kernel(const float* __restrict__ value, float* 
   }
 }
 
+// all BN layers of the model in one launch: block = one (layer, statistic) item
+struct MovingItem {
+  const float* value;
+  float* biased;
+  float* moving;
+  int C;
+  float corr;
+};
+__global__ void bn_moving_update_batch_kernel(const MovingItem* __restrict__ items, float momentum, float debias) {
+  const MovingItem it = items[blockIdx.x];
+  for (int c = threadIdx.x; c < it.C; c += blockDim.x) {
+    const float v = it.value[c] * it.corr;
+    const float b = it.biased[c] - (it.biased[c] - v) * (1.f - momentum);
+    it.biased[c] = b;
+    it.moving[c] = b / debias;
+  }
+}
+
 __global__ void __launch_bounds__(256) view_copy_kernel(V src, V dst, int accumulate) {
   const int C4 = src.c >> 2;
   const FastDiv x_fc4 = src.fc4;
@@ -271,8 +329,10 @@ __global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __r
 __global__ void __launch_bounds__(256)
 bn_act_bwd_from_output_kernel(V a, V dy, V dx, const float* __restrict__ gamma, const float* __restrict__ beta,
                               const float* __restrict__ var, float eps, int act, double* __restrict__ out0,
-                              double* __restrict__ out1, long long chunk) {
+                              double* __restrict__ out1, long long chunk, float* __restrict__ dgamma,
+                              float* __restrict__ dbeta, float* __restrict__ dbias, int* __restrict__ ticket) {
   __shared__ float red[2][32][33];
+  __shared__ int s_last;
   const int tid = threadIdx.x;
   const int cq = tid & 7, pg = tid >> 3;
   const int c0 = blockIdx.y * 32 + cq * 4;
@@ -322,18 +382,23 @@ bn_act_bwd_from_output_kernel(V a, V dy, V dx, const float* __restrict__ gamma, 
     for (int j = 0; j < 32; ++j) s += (double)red[which][c][j];
     atomicAdd((which ? out1 : out0) + blockIdx.y * 32 + c, s);
   }
-}
-
-__global__ void bn_act_bwd_finalize_kernel(const double* __restrict__ ws, const float* __restrict__ gamma,
-                                           const float* __restrict__ var, float eps, float* __restrict__ dgamma,
-                                           float* __restrict__ dbeta, float* __restrict__ dbias, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < C) {
-    dbeta[c] = (float)ws[c];
-    dgamma[c] = (float)ws[C + c];
-    // d(pre-BN)/sum: the conv bias sits before the (fixed-statistics) BN, so dbias = gamma*rs*dbeta
-    if (dbias) dbias[c] = (float)(ws[c] * (double)(gamma[c] * (1.f / sqrtf(var[c] + eps))));
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(ticket + blockIdx.y, 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (tid < 32) {
+    const int c = blockIdx.y * 32 + tid;
+    const double S0 = *(volatile double*)(out0 + c), S1 = *(volatile double*)(out1 + c);
+    dbeta[c] = (float)S0;
+    dgamma[c] = (float)S1;
+    // the conv bias sits before the (fixed-statistics) BN, so dbias = gamma*rs*dbeta
+    if (dbias) dbias[c] = (float)(S0 * (double)(gamma[c] * (1.f / sqrtf(var[c] + eps))));
+    out0[c] = 0.0;
+    out1[c] = 0.0;
   }
+  if (tid == 0) ticket[blockIdx.y] = 0;
 }
 
 static bool view_ok(const myolo_view* v) {
@@ -349,6 +414,10 @@ static void reduce_grid(long long total, int C, dim3* grid, long long* chunk) {
   nch = ceil_div(total, *chunk);
   *grid = dim3((unsigned)nch, (unsigned)cg);
 }
+// workspace layout (doubles), FIXED so that calls with different C never see each other's leftovers:
+//   [0,16) int tickets | [16, 16+2048) sums (2*C used, zero between calls) | [2064, 4112) float coefficient table
+constexpr int kWsMaxC = 1024, kWsSums = 16, kWsCoef = 16 + 2 * kWsMaxC;
+static int* ws_ticket(double* ws, int) { return reinterpret_cast<int*>(ws); }
 static int ew_blocks(long long total) { return (int)max(1LL, min(ceil_div(total, 256), (long long)kNumSMs * 16)); }
 
 }  // namespace myolo
@@ -356,7 +425,7 @@ static int ew_blocks(long long total) { return (int)max(1LL, min(ceil_div(total,
 using namespace myolo;
 
 extern "C" int myolo_bn_stats(const myolo_view* x, float* mean, float* var, double* ws, myolo_stream stream) {
-  MYOLO_CHECK_ARG(view_ok(x) && mean && var && ws && (x->c % 32) == 0);
+  MYOLO_CHECK_ARG(view_ok(x) && mean && var && ws && (x->c % 32) == 0 && x->c <= kWsMaxC);
   cudaStream_t st = as_stream(stream);
   const int C = x->c;
   const long long total = (long long)x->n * x->h * x->w;
@@ -364,11 +433,9 @@ extern "C" int myolo_bn_stats(const myolo_view* x, float* mean, float* var, doub
   long long chunk;
   reduce_grid(total, C, &grid, &chunk);
   V vx = to_v(x);
-  MYOLO_CUDA(cudaMemsetAsync(ws, 0, 2 * C * sizeof(double), st));
-  colreduce_kernel<0><<<grid, 256, 0, st>>>(vx, vx, nullptr, nullptr, nullptr, nullptr, 0.f, 0, ws, nullptr, chunk);
-  finalize_div_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, mean, C, 1.0 / (double)total, 0);
-  colreduce_kernel<1><<<grid, 256, 0, st>>>(vx, vx, mean, nullptr, nullptr, nullptr, 0.f, 0, ws + C, nullptr, chunk);
-  finalize_div_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws + C, var, C, 1.0 / (double)total, 0);
+  // single pass: sum and sum of squares in fp64 (per-thread fp32 partials over <= chunk/32 pixels)
+  Fin fin{mean, var, nullptr, ws_ticket(ws, C), 1.0 / (double)total, 1, C};
+  colreduce_kernel<3><<<grid, 256, 0, st>>>(vx, vx, nullptr, nullptr, nullptr, nullptr, 0.f, 0, ws + kWsSums, ws + kWsSums + C, chunk, fin);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }
@@ -405,17 +472,16 @@ extern "C" int myolo_bn_bwd(const myolo_view* x, const myolo_view* dy, const myo
                             const float* var, const float* gamma, const float* beta, float eps, int act, int train,
                             float* dgamma, float* dbeta, double* ws, myolo_stream stream) {
   MYOLO_CHECK_ARG(view_ok(x) && view_ok(dy) && view_ok(dx) && same_shape(x, dy) && same_shape(x, dx));
-  MYOLO_CHECK_ARG(mean && var && gamma && beta && dgamma && dbeta && ws && (x->c % 32) == 0);
+  MYOLO_CHECK_ARG(mean && var && gamma && beta && dgamma && dbeta && ws && (x->c % 32) == 0 && x->c <= kWsMaxC);
   cudaStream_t st = as_stream(stream);
   const int C = x->c;
   const long long total = (long long)x->n * x->h * x->w;
   dim3 grid;
   long long chunk;
   reduce_grid(total, C, &grid, &chunk);
-  MYOLO_CUDA(cudaMemsetAsync(ws, 0, 2 * C * sizeof(double), st));
-  colreduce_kernel<2><<<grid, 256, 0, st>>>(to_v(x), to_v(dy), mean, var, gamma, beta, eps, act, ws, ws + C, chunk);
-  float* coef = reinterpret_cast<float*>(ws + 2 * C);   // 4*C floats behind the 2*C sums (ws holds >= 4*C doubles)
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, dgamma, dbeta, C, var, gamma, eps, 1.0 / (double)total, train, coef);
+  float* coef = reinterpret_cast<float*>(ws + kWsCoef);   // 4*C floats
+  Fin fin{dbeta, dgamma, coef, ws_ticket(ws, C), 1.0 / (double)total, train, C};
+  colreduce_kernel<2><<<grid, 256, 0, st>>>(to_v(x), to_v(dy), mean, var, gamma, beta, eps, act, ws + kWsSums, ws + kWsSums + C, chunk, fin);
   bn_bwd_dx_kernel<<<ew_blocks(total * (C / 4)), 256, 0, st>>>(to_v(x), to_v(dy), to_v(dx), mean, gamma, beta, act, coef);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
@@ -438,22 +504,22 @@ extern "C" int myolo_bn_moving_update(const float* value, float* biased, float* 
 }
 
 extern "C" int myolo_colsum(const myolo_view* x, float* out, double* ws, myolo_stream stream) {
-  MYOLO_CHECK_ARG(x && x->p && x->n > 0 && x->h > 0 && x->w > 0 && x->c > 0 && out && ws);
+  MYOLO_CHECK_ARG(x && x->p && x->n > 0 && x->h > 0 && x->w > 0 && x->c > 0 && x->c <= 2 * kWsMaxC && out && ws);
   cudaStream_t st = as_stream(stream);
   const int C = x->c;
   const long long total = (long long)x->n * x->h * x->w;
-  MYOLO_CUDA(cudaMemsetAsync(ws, 0, C * sizeof(double), st));
   V vx = to_v(x);
   if ((C % 32) == 0 && (x->sn % 4) == 0 && (x->sh % 4) == 0) {
     dim3 grid;
     long long chunk;
     reduce_grid(total, C, &grid, &chunk);
-    colreduce_kernel<0><<<grid, 256, 0, st>>>(vx, vx, nullptr, nullptr, nullptr, nullptr, 0.f, 0, ws, nullptr, chunk);
+    Fin fin{out, nullptr, nullptr, ws_ticket(ws, C), 1.0, 0, C};
+    colreduce_kernel<0><<<grid, 256, 0, st>>>(vx, vx, nullptr, nullptr, nullptr, nullptr, 0.f, 0, ws + kWsSums, nullptr, chunk, fin);
   } else {
     dim3 grid((C + 63) / 64, (unsigned)min(total, 256LL));
-    colsum_generic_kernel<<<grid, 64, 0, st>>>(vx, ws);
+    colsum_generic_kernel<<<grid, 64, 0, st>>>(vx, ws + kWsSums);
+    finalize_div_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws + kWsSums, out, C, 1.0, 0);
   }
-  finalize_div_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, out, C, 1.0, 0);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }
@@ -478,16 +544,25 @@ extern "C" int myolo_bn_act_bwd_from_output(const myolo_view* a, const myolo_vie
                                             const float* gamma, const float* beta, const float* var, float eps, int act,
                                             float* dgamma, float* dbeta, float* dbias, double* ws, myolo_stream stream) {
   MYOLO_CHECK_ARG(view_ok(a) && view_ok(dy) && view_ok(dx) && same_shape(a, dy) && same_shape(a, dx));
-  MYOLO_CHECK_ARG(gamma && beta && var && dgamma && dbeta && ws && (a->c % 32) == 0);
+  MYOLO_CHECK_ARG(gamma && beta && var && dgamma && dbeta && ws && (a->c % 32) == 0 && a->c <= kWsMaxC);
   cudaStream_t st = as_stream(stream);
   const int C = a->c;
   const long long total = (long long)a->n * a->h * a->w;
   dim3 grid;
   long long chunk;
   reduce_grid(total, C, &grid, &chunk);
-  MYOLO_CUDA(cudaMemsetAsync(ws, 0, 2 * C * sizeof(double), st));
-  bn_act_bwd_from_output_kernel<<<grid, 256, 0, st>>>(to_v(a), to_v(dy), to_v(dx), gamma, beta, var, eps, act, ws, ws + C, chunk);
-  bn_act_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, gamma, var, eps, dgamma, dbeta, dbias, C);
+  bn_act_bwd_from_output_kernel<<<grid, 256, 0, st>>>(to_v(a), to_v(dy), to_v(dx), gamma, beta, var, eps, act, ws + kWsSums, ws + kWsSums + C, chunk,
+                                                      dgamma, dbeta, dbias, ws_ticket(ws, C));
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
+}
+
+extern "C" int myolo_bn_moving_update_batch(const void* items_dev, int n_items, float momentum, int step, myolo_stream stream) {
+  MYOLO_CHECK_ARG(items_dev && n_items > 0 && step >= 1);
+  double pw = 1.0;
+  for (int i = 0; i < step && pw > 1e-300; ++i) pw *= (double)momentum;
+  bn_moving_update_batch_kernel<<<n_items, 256, 0, as_stream(stream)>>>(reinterpret_cast<const MovingItem*>(items_dev), momentum,
+                                                                         (float)(1.0 - pw));
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }

@@ -119,6 +119,7 @@ class Engine:
         self.NB, self.NC, self.TB, self.R = cfg["NB"], cfg["NC"], cfg["TB"], cfg["G"] * cfg["G"] * cfg["NB"]
         self.with_mask = mode != "yolo"
         self._frozen = False
+        self._moving_key = None
         self._shift_cache = {}
         self.inputs_ready = None       # optional CUDA event: inputs[1:] of forward_training are complete
         self.kernel_events = None      # bench.py: list collecting (start, end) CUDA events of the dominant kernel
@@ -186,7 +187,8 @@ class Engine:
         for name, (o, n, shape) in self.offs.items():
             if name.endswith("/kernel") and name != "conv1/kernel":
                 self.wt[name] = torch.zeros(n * (3 if self._is_x3(name) else 1), dtype=torch.float32, device=self.dev)
-        self.ws = torch.zeros(4096, dtype=torch.float64, device=self.dev)
+        self.ws = torch.zeros(8192, dtype=torch.float64, device=self.dev)       # BN family: zero between calls
+        self.ws_loss = torch.zeros(16, dtype=torch.float64, device=self.dev)
         self.anchors = torch.tensor(self.cfg["ANCHORS"], dtype=torch.float32, device=self.dev)
         self.class_w = torch.tensor(np.asarray(self.cfg["CLASS_WEIGHTS"], dtype=np.float32), device=self.dev)
         self.scales = C.float_array([self.cfg["OBJECT_SCALE"], self.cfg["NO_OBJECT_SCALE"], self.cfg["COORD_SCALE"],
@@ -485,7 +487,7 @@ class Engine:
         lw = cfg.get("LOSS_WEIGHTS", {})
         assert true_boxes.dtype == torch.float32 and yolo_target.dtype == torch.float32
         C.call("myolo_yolo_loss", yolo_target, A["yolo"], true_boxes, self.anchors, self.class_w, B, G, G, NB, NC, TB,
-               self.scales, warm, float(lw.get("yolo_sum_loss", 1.0)), self.loss_yolo, A["dyolo"], self.ws, st)
+               self.scales, warm, float(lw.get("yolo_sum_loss", 1.0)), self.loss_yolo, A["dyolo"], self.ws_loss, st)
         out = dict(yolo_output=yolo, yolo_proposals=A["proposals"], yolo_sum_loss=self.loss_yolo[0])
         if self.with_mask:
             gt_ids, gt_boxes, gt_masks = inputs[3], inputs[4], inputs[5]
@@ -497,7 +499,7 @@ class Engine:
                    A["rois"], self.target_ids, A["target_masks"], self.n_pos, self.roi_src, self.roi_gt, st)
             masks = self.mask_head(A["rois"], training=True)
             C.call("myolo_mask_loss", A["masks"], A["target_masks"], self.target_ids, self.n_roi, mh, mw, NC,
-                   float(lw.get("myolo_mask_loss", 1.0)), self.loss_mask, A["dlogit"], self.ws, st)
+                   float(lw.get("myolo_mask_loss", 1.0)), self.loss_mask, A["dlogit"], self.ws_loss, st)
             out.update(output_rois=A["rois"], myolo_mask=masks, mask_loss=self.loss_mask[0],
                        target_class_ids=self.target_ids, target_mask=A["target_masks"])
         return out
@@ -595,10 +597,26 @@ class Engine:
             self.grads.mul_(self.trainable_mask)        # set_trainable(): frozen variables get no update
         C.call("myolo_adam_step", self.params, self.grads, self.adam_m, self.adam_v, self.n_flat, lr_t, b1, b2, 1e-8,
                grad_scale, st)
-        for b, npix in self._bn_touched:
-            b.step += 1
-            C.call("myolo_bn_moving_update", b.mean, b.bmean, b.mmean, b.c, BN_MOMENTUM, b.step, 0, float(npix), BN_EPS, st)
-            C.call("myolo_bn_moving_update", b.var, b.bvar, b.mvar, b.c, BN_MOMENTUM, b.step, 1, float(npix), BN_EPS, st)
+        if self._bn_touched:
+            # one launch for every (layer, statistic): the record table is rebuilt only when the set of
+            # batch-statistics layers changes (it never does within a run)
+            key = tuple(id(b) for b, _ in self._bn_touched)
+            if self._moving_key != key:
+                import struct
+                steps = {b.step for b, _ in self._bn_touched}
+                assert len(steps) == 1, "batched moving-average update needs a common step count"
+                rec = b""
+                for b, npix in self._bn_touched:
+                    n = float(npix)
+                    corr = (n / max(n - 1.0, 1.0)) * (n / (n - (1.0 + BN_EPS)))
+                    rec += struct.pack("<QQQif", b.mean.data_ptr(), b.bmean.data_ptr(), b.mmean.data_ptr(), b.c, 1.0)
+                    rec += struct.pack("<QQQif", b.var.data_ptr(), b.bvar.data_ptr(), b.mvar.data_ptr(), b.c, corr)
+                self._moving_table = torch.frombuffer(bytearray(rec), dtype=torch.uint8).to(self.dev)
+                self._moving_key, self._moving_n = key, 2 * len(self._bn_touched)
+            for b, _ in self._bn_touched:
+                b.step += 1
+            C.call("myolo_bn_moving_update_batch", self._moving_table, self._moving_n, BN_MOMENTUM,
+                   self._bn_touched[0][0].step, st)
         self._bn_touched = []
         self.refresh_weights()
 

@@ -100,7 +100,7 @@ def test_bn(C, act, train):
     ya.backward(dy)
     xd, gd, bd = cuda(x.detach()), cuda(g.detach()), cuda(b.detach())
     meand, vard = torch.empty(Cc, device="cuda"), torch.empty(Cc, device="cuda")
-    ws = torch.zeros(4 * Cc, dtype=torch.float64, device="cuda")
+    ws = torch.zeros(4112, dtype=torch.float64, device="cuda")
     xv = C.view(xd, B, H, W, Cc)
     if train:
         C.call("myolo_bn_stats", xv, meand, vard, ws, stream())
@@ -135,7 +135,7 @@ def test_bn_moving_update_and_colsum(C):
         close(md, exp_b / (1 - 0.99 ** step), 2e-5, "moving var")
     x = torch.randn(4, 5, 6, 64)
     out = torch.empty(64, device="cuda")
-    ws = torch.zeros(64, dtype=torch.float64, device="cuda")
+    ws = torch.zeros(4112, dtype=torch.float64, device="cuda")
     xd = cuda(x)
     C.call("myolo_colsum", C.view(xd, 4, 5, 6, 64), out, ws, stream())
     close(out, x.sum((0, 1, 2)), 1e-5, "colsum")
