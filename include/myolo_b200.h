@@ -227,6 +227,18 @@ int myolo_yolo_loss(const float* y_true, const float* y_pred, const float* true_
                     const float* scales_host, int warmup, float loss_weight,
                     float* loss_out, float* dy_pred, double* ws, myolo_stream stream);
 
+/* ---- inference post-processing, myolo/model.py:1290-1304 + 1330-1391 (myolo_utils.py:88-113 NMB, 883-912 unmold_mask) ----
+ * per image: the top_k detections by confidence that reach cs_threshold, greedy suppression (a box survives
+ * if IoU < nms_threshold against every kept box), then each survivor's class mask resized (bilinear, pixel
+ * centres aligned) to its pixel box, thresholded at 0.5 and pasted into an S x S byte image.
+ * detections [B,R,6] = DetectionsLayer output; masks [B,R,MH,MW,NC] (nullable together with out_masks).
+ * out_index [B,top_k] (detection index or -1), out_boxes [B,top_k,4] int32 pixels (x1,y1,x2,y2) clipped to
+ * [0,S], out_class / out_score [B,top_k], out_count [B], out_masks [B,top_k,S,S] bytes.  top_k <= 32. */
+int myolo_detect_postprocess(const float* detections, const float* masks, int B, int R, int NC, int S, int MH, int MW,
+                             int top_k, float cs_threshold, float nms_threshold, int* out_index, int* out_boxes,
+                             int* out_class, float* out_score, int* out_count, unsigned char* out_masks,
+                             myolo_stream stream);
+
 /* ---- K17: Keras Adam, myolo/model.py:1071-1075 ----  lr_t = lr*sqrt(1-b2^t)/(1-b1^t) computed by caller */
 int myolo_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr_t,
                     float b1, float b2, float eps, float grad_scale, myolo_stream stream);

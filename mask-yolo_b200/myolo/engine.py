@@ -471,6 +471,20 @@ class Engine:
         masks = self.mask_head(self.A["proposals"], training=False) if self.with_mask else None
         return yolo, det, masks
 
+    def postprocess(self, top_k: int = 10, cs_threshold: float = 0.35, nms_threshold: float = 0.5):
+        """Device-side tail of MaskYOLO.detect (model.py:1290-1304, 1330-1391) on the detections / masks left by
+        forward_inference: top-k by confidence, threshold, NMB, mask paste.  Returns device tensors
+        (index [B,K], boxes [B,K,4] int32 px, class [B,K], score [B,K], count [B], masks [B,K,S,S] uint8)."""
+        B, R, S, dev = self.B, self.R, self.cfg["S"], self.dev
+        mh, mw = self.cfg["MASK_SHAPE"]
+        i32 = lambda *sh: torch.empty(sh, dtype=torch.int32, device=dev)
+        idx, boxes, cls, cnt = i32(B, top_k), i32(B, top_k, 4), i32(B, top_k), i32(B)
+        score = torch.empty(B, top_k, dtype=torch.float32, device=dev)
+        pm = torch.empty(B, top_k, S, S, dtype=torch.uint8, device=dev) if self.with_mask else None
+        C.call("myolo_detect_postprocess", self.A["detections"], self.A["masks"] if self.with_mask else None, B, R, self.NC, S,
+               mh, mw, top_k, float(cs_threshold), float(nms_threshold), idx, boxes, cls, score, cnt, pm, self._st())
+        return idx, boxes, cls, score, cnt, pm
+
     def forward_training(self, inputs):
         """mode='training' graph (model.py:844-901); inputs as BatchGenerator yields them:
         [image, true_boxes [B,1,1,1,TB,4], yolo_target [B,G,G,NB,5+NC], gt_class_ids [B,M] i32,

@@ -439,42 +439,42 @@ class MaskYOLO:
         return mutils.decode_one_yolo_output(netout, self.cfg["ANCHORS"], nms_threshold=0.3, obj_threshold=0.3,
                                              nb_class=self.cfg["NC"])
 
-    def _predict_b1(self, x):
-        if self.engine.B != 1:
-            if getattr(self, "_eng1", None) is None:
-                mode = "inference" if self.mode != "yolo" else "yolo"
-                self._eng1 = Engine(self.cfg, 1, mode, self.precision, self.device, params=self.engine.state_dict())
-            else:
-                self._eng1.load_params(self.engine.state_dict())
-            eng = self._eng1
+    def _engine_b1(self):
+        """Batch-1 engine sharing this model's weights (detect / infer_yolo run one image at a time)."""
+        if self.engine.B == 1:
+            return self.engine
+        if getattr(self, "_eng1", None) is None:
+            mode = "inference" if self.mode != "yolo" else "yolo"
+            self._eng1 = Engine(self.cfg, 1, mode, self.precision, self.device, params=self.engine.state_dict())
         else:
-            eng = self.engine
+            self._eng1.load_params(self.engine.state_dict())
+        return self._eng1
+
+    def _predict_b1(self, x):
+        eng = self._engine_b1()
         img = torch.from_numpy(x).to(eng.dev)
         if eng.with_mask:
             yolo, det, masks = eng.forward_inference(img)
             return [yolo.cpu().numpy(), det.cpu().numpy(), masks.cpu().numpy()]
         return [eng.forward(img, training=False).cpu().numpy()]
 
-    def detect(self, image, weights_dir=None, save_path=None, cs_threshold=0.35, display=False):
-        """Full inference on one uint8 image (model.py:1238-1328).  Returns a dict with 'rois'
-        (x1,y1,x2,y2 pixels), 'class_ids', 'scores' and boolean 'masks' [H,W,N] for the detections that
-        survive the confidence threshold and NMB; the reference's debugging overrides (hard-coded
-        indices 1306, fixed 224 scale 1307) are not reproduced."""
+    def detect(self, image, weights_dir=None, save_path=None, cs_threshold=0.35, display=False, top_k=10):
+        """Full inference on one uint8 image (model.py:1238-1328), end to end on the GPU: network, top-10 by
+        confidence, confidence threshold, NMB and mask paste (myolo_detect_postprocess).  Returns a dict with
+        'rois' (x1,y1,x2,y2 pixels), 'class_ids', 'scores' and boolean 'masks' [H,W,N].  The reference's
+        debugging overrides (hard-coded indices 1306, fixed 224 scale 1307) are not reproduced."""
         assert self.mode == "inference", "Create model in inference mode."
         assert image.dtype == np.uint8 and list(image.shape) == list(self.config.IMAGE_SHAPE)
         if weights_dir is not None:
             self.load_weights(weights_dir)
-        x = (image / 255.)[None].astype(np.float32)
-        yolo, det, masks = self._predict_b1(x)
-        det, masks = det[0], masks[0]
-        order = np.argsort(det[:, 4])[::-1][:10]
-        order = [i for i in order if det[i, 4] >= cs_threshold]
-        S = self.cfg["S"]
-        keep = [order[j] for j in mutils.NMB(det[order, :4], det[order, 4])] if order else []
-        boxes = np.clip(np.round(det[keep, :4] * S), 0, S).astype(np.int32) if keep else np.zeros((0, 4), np.int32)
-        full = self.decode_masks(det[keep], masks[keep], image.shape) if keep else np.zeros(image.shape[:2] + (0,), bool)
-        return {"rois": boxes, "class_ids": det[keep, 5].astype(np.int32) if keep else np.zeros((0,), np.int32),
-                "scores": det[keep, 4] if keep else np.zeros((0,), np.float32), "masks": full}
+        eng = self._engine_b1()
+        x = torch.from_numpy((image / 255.)[None].astype(np.float32)).to(eng.dev)
+        eng.forward_inference(x)
+        idx, boxes, cls, score, cnt, pm = eng.postprocess(top_k=top_k, cs_threshold=cs_threshold, nms_threshold=0.5)
+        n = int(cnt[0].item())
+        masks = pm[0, :n].permute(1, 2, 0).bool().cpu().numpy() if n else np.zeros(tuple(image.shape[:2]) + (0,), bool)
+        return {"rois": boxes[0, :n].cpu().numpy(), "class_ids": cls[0, :n].cpu().numpy(),
+                "scores": score[0, :n].cpu().numpy(), "masks": masks}
 
     def decode_masks(self, detections, myolo_mask, image_shape):
         """Class-specific 28x28 masks -> full-size boolean masks pasted at their boxes (model.py:1330-1391)."""

@@ -29,12 +29,13 @@ def test_train_loop_checkpoint_and_reload(tmp_path):
     tr, va = ShapesDataset(seed=1), ShapesDataset(seed=2)
     tr.load_shapes(12, 128, 128); tr.prepare()
     va.load_shapes(4, 128, 128); va.prepare()
+    np.random.seed(0)                          # BatchGenerator shuffles with the global numpy RNG
     model = MaskYOLO(mode="training", config=cfg, model_dir=str(tmp_path))
     assert model.keras_model.metrics_names == ["loss", "yolo_sum_loss", "myolo_mask_loss"]
     assert "Total params" in model.keras_model.summary()
-    hist = model.train(tr, va, learning_rate=cfg.LEARNING_RATE, epochs=2, layers="all", verbose=0)
-    assert len(hist["loss"]) == 2 and all(np.isfinite(hist["loss"])) and np.isfinite(hist["val_loss"][-1])
-    assert hist["loss"][1] < hist["loss"][0] * 1.5            # training does not blow up
+    hist = model.train(tr, va, learning_rate=cfg.LEARNING_RATE, epochs=12, layers="all", verbose=0)
+    assert len(hist["loss"]) == 12 and all(np.isfinite(hist["loss"])) and np.isfinite(hist["val_loss"][-1])
+    assert min(hist["loss"][-3:]) < 0.5 * hist["loss"][0], hist["loss"]     # 36 Adam steps: the loss comes down
     ckpts = glob.glob(os.path.join(str(tmp_path), "saved_model_*.pt"))
     assert len(ckpts) == 1
     sd = model.engine.state_dict()

@@ -545,3 +545,45 @@ def test_deconv_mask_fused(C):
             close(yv[r], rv[r], 2e-3, "y4 of a positive roi")
         else:
             assert yv[r].abs().max().item() == 0, "y4 rows of non-positive rois are not written"
+
+
+def test_detect_postprocess_matches_numpy_pipeline(C):
+    """Device top-k / threshold / NMB / mask paste against the host functions that restate
+    myolo_utils.NMB (88-113) and unmold_mask (883-912)."""
+    from myolo import myolo_utils as mu
+    rng = np.random.RandomState(30)
+    B, R, NC, S, K = 3, 147, 4, 224, 10
+    det = np.zeros((B, R, 6), np.float32)
+    c = rng.rand(B, R, 2) * 0.8 + 0.1
+    wh = rng.rand(B, R, 2) * 0.4 + 0.05
+    det[..., 0:2], det[..., 2:4] = c - wh / 2, c + wh / 2
+    det[:, :20, :4] = det[:, 20:40, :4] + rng.randn(B, 20, 4).astype(np.float32) * 0.01     # near-duplicates -> suppression
+    det[..., 4] = rng.permutation(B * R).reshape(B, R) / float(B * R)                        # distinct scores
+    det[..., 5] = rng.randint(0, NC, (B, R))
+    masks = rng.rand(B, R, 28, 28, NC).astype(np.float32)
+    thr = 0.9
+    dd, md = cuda(torch.tensor(det)), cuda(torch.tensor(masks))
+    i32 = lambda *sh: torch.empty(sh, dtype=torch.int32, device="cuda")
+    idx, boxes, cls, cnt = i32(B, K), i32(B, K, 4), i32(B, K), i32(B)
+    score = torch.empty(B, K, device="cuda")
+    pm = torch.empty(B, K, S, S, dtype=torch.uint8, device="cuda")
+    C.call("myolo_detect_postprocess", dd, md, B, R, NC, S, 28, 28, K, thr, 0.5, idx, boxes, cls, score, cnt, pm, stream())
+    total_px = mism = 0
+    for b in range(B):
+        order = np.argsort(det[b, :, 4])[::-1][:K]
+        order = [i for i in order if det[b, i, 4] >= thr]
+        keep = [order[j] for j in mu.NMB(det[b, order, :4], det[b, order, 4])] if order else []
+        n = int(cnt[b].item())
+        assert idx[b, :n].cpu().tolist() == [int(k) for k in keep], (b, idx[b].cpu().tolist(), keep)
+        assert (idx[b, n:] == -1).all()
+        exp_boxes = np.clip(np.round(det[b, keep, :4] * S), 0, S).astype(np.int32)
+        assert np.array_equal(boxes[b, :n].cpu().numpy(), exp_boxes)
+        assert cls[b, :n].cpu().tolist() == [int(det[b, k, 5]) for k in keep]
+        for j, k in enumerate(keep):
+            box = np.round(det[b, k, :4] * S).astype(np.int32)
+            ref = mu.unmold_mask(masks[b, k, :, :, int(det[b, k, 5])], box, (S, S, 3))
+            got = pm[b, j].bool().cpu().numpy()
+            total_px += ref.sum()
+            mism += (ref != got).sum()
+        assert pm[b, n:].sum().item() == 0
+    assert total_px > 1000 and mism <= 2e-3 * total_px, (mism, total_px)     # cv2 vs device rounding at exactly 0.5
