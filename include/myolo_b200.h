@@ -157,6 +157,19 @@ int myolo_bn_fold(const float* gamma, const float* beta, const float* mean, cons
 int myolo_bn_act_bwd_from_output(const myolo_view* a, const myolo_view* dy, const myolo_view* dx, const float* gamma,
                                  const float* beta, const float* var, float eps, int act, float* dgamma, float* dbeta,
                                  float* dbias, double* ws, myolo_stream stream);
+/* dgrad GEMM with the backward of the PREVIOUS layer's fixed-statistics BN + activation fused into its epilogue
+ * (tcgen05 persistent kernel, N == 256): the GEMM result is d(a); the kernel reads a_out ([M][N], same rows as C),
+ * stores C = d(a)*act'(a)*gamma*rs and reduces dbeta / dgamma / dbias -- what myolo_gemm_taps followed by
+ * myolo_bn_act_bwd_from_output computes, without the three extra passes over the gradient tensor.
+ * ws: the BN workspace (MYOLO_BN_WS_DOUBLES, zero before and after). */
+int myolo_gemm_taps_bnbwd(const float* A, long long lda, const float* Bt, float* C, long long ldc, long long M,
+                          int N, int K, int ntaps, const int* shifts_host, int pf_w1, int pf_blk,
+                          const float* a_out, const float* gamma, const float* beta, const float* var, float eps,
+                          int act, float* dgamma, float* dbeta, float* dbias, double* ws, myolo_stream stream);
+int myolo_gemm_taps_bnbwd_supported(long long lda, long long ldc, long long M, int N, int K, int ntaps,
+                                    const int* shifts_host);
+int myolo_bn_epi_finalize(double* sums, const float* gamma, const float* var, float eps, float* dgamma,
+                          float* dbeta, float* dbias, int C, myolo_stream stream);
 /* Keras moving-average update with TF zero-debias: biased -= (biased-value)*(1-momentum);
  * moving = biased/(1-momentum^step). value = mean, or var*bessel*n/(n-(1+eps)) when is_var. */
 int myolo_bn_moving_update(const float* value, float* biased, float* moving, int C, float momentum, int step,

@@ -566,3 +566,28 @@ extern "C" int myolo_bn_moving_update_batch(const void* items_dev, int n_items, 
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }
+
+namespace myolo {
+__global__ void bn_epi_finalize_kernel(double* __restrict__ sums, const float* __restrict__ gamma, const float* __restrict__ var,
+                                       float eps, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
+                                       int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    const double S0 = sums[c], S1 = sums[C + c];
+    dbeta[c] = (float)S0;
+    dgamma[c] = (float)S1;
+    if (dbias) dbias[c] = (float)(S0 * (double)(gamma[c] * (1.f / sqrtf(var[c] + eps))));
+    sums[c] = 0.0;
+    sums[C + c] = 0.0;
+  }
+}
+}  // namespace myolo
+
+// finishes the column sums a GEMM epilogue accumulated (myolo_gemm_taps_bnbwd) and zeroes them again
+extern "C" int myolo_bn_epi_finalize(double* sums, const float* gamma, const float* var, float eps, float* dgamma,
+                                     float* dbeta, float* dbias, int C, myolo_stream stream) {
+  MYOLO_CHECK_ARG(sums && gamma && var && dgamma && dbeta && C > 0);
+  myolo::bn_epi_finalize_kernel<<<(C + 127) / 128, 128, 0, myolo::as_stream(stream)>>>(sums, gamma, var, eps, dgamma, dbeta, dbias, C);
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
+}

@@ -22,14 +22,15 @@ namespace myolo {
 namespace tc {
 
 constexpr int WHALO = 16;
-constexpr uint32_t kWStageOut = 4 * 4096;       // per-epilogue-warp 32x32 fp32 staging buffer for the TMA store
+constexpr uint32_t kWStageOut = 2 * 4 * 4096;   // per-epilogue-warp 32x32 fp32 staging buffers: TMA-store tile + BN-backward side tile
+constexpr uint32_t kWColAcc = 2 * 256 * 4;       // per-CTA column-sum accumulators of the fused BN backward
 constexpr uint32_t kWEpiVec = 2 * 1024 * 4;     // folded epilogue scale / shift, up to 1024 output channels
-// NACC = 128-row accumulators per work item.  Window = 128*NACC + 32 rows; weight ring 160 KB (NACC 1) / 128 KB (NACC 2)
+// NACC = 128-row accumulators per work item.  Window = 128*NACC + 32 rows; weight ring 128 KB (NACC 1) / 96 KB (NACC 2)
 __host__ __device__ constexpr int win_rows(int nacc) { return 128 * nacc + 2 * WHALO; }
 __host__ __device__ constexpr int win_box(int nacc) { return nacc == 1 ? win_rows(1) : win_rows(2) / 2; }
-__host__ __device__ constexpr uint32_t win_ring(int nacc) { return nacc == 1 ? 163840u : 131072u; }
+__host__ __device__ constexpr uint32_t win_ring(int nacc) { return nacc == 1 ? 131072u : 98304u; }
 __host__ __device__ constexpr uint32_t win_smem(int nacc) {
-  return 2u * win_rows(nacc) * 128u + win_ring(nacc) + kWStageOut + kWEpiVec + 1024u;
+  return 2u * win_rows(nacc) * 128u + win_ring(nacc) + kWStageOut + kWColAcc + kWEpiVec + 1024u;
 }
 
 // Work item = (256-row tile, WBN-column slice).  Two 128-row accumulators share every weight stage.
@@ -76,7 +77,8 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   __shared__ uint32_t tmem_slot;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t awin0 = base, bst0 = base + 2 * kWinBytes, stg0 = bst0 + kWBStages * kWBBytes;
-  float* evec = reinterpret_cast<float*>(smem_raw + (stg0 + kWStageOut - smem_u32(smem_raw)));  // [scale N | shift N]
+  float* colacc = reinterpret_cast<float*>(smem_raw + (stg0 + kWStageOut - smem_u32(smem_raw)));          // [2][256]
+  float* evec = reinterpret_cast<float*>(smem_raw + (stg0 + kWStageOut + kWColAcc - smem_u32(smem_raw)));  // [scale N | shift N]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kblocks = K / BK;
   const int nh = N / WBN;
@@ -108,6 +110,14 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (mt.masks) {   // mask tail: evec = [bd 256 | w1 transposed NC x 256]
     for (int i = threadIdx.x; i < 256; i += blockDim.x) evec[i] = __ldg(mt.bd + i);
     for (int i = threadIdx.x; i < 256 * mt.NC; i += blockDim.x) evec[256 + (i % mt.NC) * 256 + i / mt.NC] = __ldg(mt.w1 + i);
+  } else if (ep.bn_a) {   // fused BN backward: evec = [gamma*rs | beta | 1/gamma], column accumulators zeroed
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+      const float ga = __ldg(ep.bn_gamma + n);
+      evec[n] = ga * (1.f / sqrtf(__ldg(ep.bn_var + n) + ep.bn_eps));
+      evec[N + n] = __ldg(ep.bn_beta + n);
+      evec[2 * N + n] = 1.f / (fabsf(ga) < 1e-20f ? copysignf(1e-20f, ga) : ga);
+    }
+    for (int n = threadIdx.x; n < 512; n += blockDim.x) colacc[n] = 0.f;
   } else {
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
       const float sc = ep.scale ? __ldg(ep.scale + n) : 1.f;
@@ -309,6 +319,51 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           __syncwarp();
           const int n0 = half * WBN + c0;
+          if (ep.bn_a) {
+            // ---- fused BN(+ReLU) backward.  v = d(a) for this thread's row; a is read in place.
+            const uint32_t sbuf2 = sbuf + 4u * 4096u;
+            const float4* arow = reinterpret_cast<const float4*>(ep.bn_a + (size_t)m * N + n0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 av = make_float4(0.f, 0.f, 0.f, 0.f), be, ig;
+              if (valid) av = __ldg(arow + j);
+              asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(be.x), "=f"(be.y), "=f"(be.z), "=f"(be.w) : "r"(evs + 4u * (N + n0 + 4 * j)));
+              asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(ig.x), "=f"(ig.y), "=f"(ig.z), "=f"(ig.w) : "r"(evs + 4u * (2 * N + n0 + 4 * j)));
+              const float aa[4] = {av.x, av.y, av.z, av.w}, bb[4] = {be.x, be.y, be.z, be.w}, gg[4] = {ig.x, ig.y, ig.z, ig.w};
+              float g[4], t[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                bool pass = valid;
+                if (actk == MYOLO_ACT_RELU) pass = pass && aa[e] > 0.f;
+                else if (actk == MYOLO_ACT_RELU6) pass = pass && aa[e] > 0.f && aa[e] < 6.f;
+                g[e] = pass ? v[4 * j + e] : 0.f;
+                t[e] = g[e] * (aa[e] - bb[e]) * gg[e];
+              }
+              const uint32_t off = (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sbuf + off), "f"(g[0]), "f"(g[1]), "f"(g[2]), "f"(g[3]));
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sbuf2 + off), "f"(t[0]), "f"(t[1]), "f"(t[2]), "f"(t[3]));
+            }
+            __syncwarp();
+            // column pass: lane = column.  sums of g (dbeta) and g*xhat (dgamma); g is scaled in place to d(pre-BN)
+            {
+              const float scl = evec[n0 + lane];
+              float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+              for (int r = 0; r < 32; ++r) {
+                const uint32_t off = (uint32_t)r * 128u + (uint32_t)((((uint32_t)lane >> 2) ^ (uint32_t)(r & 7)) << 4) + ((uint32_t)lane & 3u) * 4u;
+                float gv, tv;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(gv) : "r"(sbuf + off));
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(tv) : "r"(sbuf2 + off));
+                s0 += gv;
+                s1 += tv;
+                float o = gv * scl;
+                if (rnd) o = round_tf32(o);
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(sbuf + off), "f"(o));
+              }
+              atomicAdd(colacc + n0 + lane, s0);
+              atomicAdd(colacc + 256 + n0 + lane, s1);
+            }
+          } else
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float4 sc, sf;
@@ -342,6 +397,12 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
+  if (ep.bn_a) {   // one fp64 atomic per (CTA, column, statistic)
+    for (int n = threadIdx.x; n < 2 * N; n += blockDim.x) {
+      const float vsum = colacc[(n / N) * 256 + (n % N)];
+      if (vsum != 0.f) atomicAdd(ep.bn_ws + n, (double)vsum);
+    }
+  }
   if (CG == 2) cluster_sync_all();   // no CTA of the pair may free TMEM / exit while the other still uses it
   if (warp == 1) {
     if (CG == 2) tmem_dealloc_2sm(tmem, 512);
@@ -368,9 +429,19 @@ extern "C" int myolo_gemm_taps_win_supported(long long lda, long long ldc, long 
   return 1;
 }
 
+struct BnBwd {   // host-side bundle of the fused BN-backward epilogue arguments (all null = off)
+  const float* a;
+  const float* gamma;
+  const float* beta;
+  const float* var;
+  double* ws;
+  float eps;
+};
+
 static int launch_win(const float* A, long long lda, const float* Bt, float* C, long long ldc, long long M, int N, int K,
                       int ntaps, const int* shifts_host, const float* bias, const float* scale, const float* shift_c,
-                      int act, int pf_w1, int pf_blk, int accumulate, const MaskTail& mt, myolo_stream stream) {
+                      int act, int pf_w1, int pf_blk, int accumulate, const MaskTail& mt, myolo_stream stream,
+                      const BnBwd& bnb = BnBwd{}) {
   MYOLO_CHECK_ARG(A && Bt && C && ((((uintptr_t)A | (uintptr_t)Bt | (uintptr_t)C) & 15) == 0));
   MYOLO_CHECK_ARG(myolo_gemm_taps_win_supported(lda, ldc, M, N, K, ntaps, shifts_host, accumulate));
   MYOLO_CHECK_ARG((scale == nullptr) == (shift_c == nullptr));
@@ -424,7 +495,7 @@ static int launch_win(const float* A, long long lda, const float* Bt, float* C, 
     }
     attr_set = true;
   }
-  Epi ep{bias, scale, shift_c, act, pf_w1, pf_blk, accumulate};
+  Epi ep{bias, scale, shift_c, act, pf_w1, pf_blk, accumulate, bnb.a, bnb.gamma, bnb.beta, bnb.var, bnb.ws, bnb.eps};
   cudaStream_t st = as_stream(stream);
   if (cg == 2 && max_clusters > 0) {
     const int nitems = (int)ceil_div(M, 256) * (N / wbn);
@@ -479,4 +550,26 @@ extern "C" int myolo_deconv_mask_fwd(const float* a4, const float* kd, const flo
   const long long M = (long long)n_roi * (H + 1) * (W + 1);
   return launch_win(a4, Cmid, kd, y4, 4 * Cmid, M, 4 * Cmid, Cmid, 1, nullptr, nullptr, nullptr, nullptr, MYOLO_ACT_NONE,
                     W + 1, (H + 1) * (W + 1), 0, mt, stream);
+}
+
+extern "C" int myolo_bn_epi_finalize(double* sums, const float* gamma, const float* var, float eps, float* dgamma,
+                                     float* dbeta, float* dbias, int C, myolo_stream stream);
+
+extern "C" int myolo_gemm_taps_bnbwd_supported(long long lda, long long ldc, long long M, int N, int K, int ntaps,
+                                               const int* shifts_host) {
+  return N == 256 && ldc == N && myolo_gemm_taps_win_supported(lda, ldc, M, N, K, ntaps, shifts_host, 0);
+}
+
+extern "C" int myolo_gemm_taps_bnbwd(const float* A, long long lda, const float* Bt, float* C, long long ldc, long long M,
+                                     int N, int K, int ntaps, const int* shifts_host, int pf_w1, int pf_blk,
+                                     const float* a_out, const float* gamma, const float* beta, const float* var, float eps,
+                                     int act, float* dgamma, float* dbeta, float* dbias, double* ws, myolo_stream stream) {
+  MYOLO_CHECK_ARG(a_out && gamma && beta && var && dgamma && dbeta && ws);
+  MYOLO_CHECK_ARG(myolo_gemm_taps_bnbwd_supported(lda, ldc, M, N, K, ntaps, shifts_host));
+  MaskTail mt{};
+  BnBwd bnb{a_out, gamma, beta, var, ws + 16, eps};       // sums live behind the ticket words of the BN workspace
+  int rc = launch_win(A, lda, Bt, C, ldc, M, N, K, ntaps, shifts_host, nullptr, nullptr, nullptr, act, pf_w1, pf_blk, 0, mt,
+                      stream, bnb);
+  if (rc) return rc;
+  return myolo_bn_epi_finalize(ws + 16, gamma, var, eps, dgamma, dbeta, dbias, N, stream);
 }

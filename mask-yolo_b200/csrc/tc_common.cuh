@@ -120,6 +120,14 @@ struct Epi {
   const float* scale;
   const float* shift;
   int act, pf_w1, pf_blk, accumulate;
+  // fused backward of a = act(BN_fixed_stats(.)) (conv_win kernel only): the GEMM result is d(a); the epilogue
+  // reads a, writes d(pre-BN) = d(a)*act'(a)*gamma*rs and accumulates dbeta / dgamma column sums into bn_ws
+  const float* bn_a;      // [M][N] activation the gradient belongs to (same row layout as C); nullptr = off
+  const float* bn_gamma;
+  const float* bn_beta;
+  const float* bn_var;
+  double* bn_ws;          // [2][N] fp64 sums (zero before, finalized + zeroed by myolo_gemm_taps_bnbwd)
+  float bn_eps;
 };
 
 

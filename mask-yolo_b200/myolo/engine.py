@@ -120,6 +120,7 @@ class Engine:
         self.with_mask = mode != "yolo"
         self._frozen = False
         self._moving_key = None
+        self._neg_shifts = C.int_array(conv3x3_shifts(cfg["POOL"], negate=True))
         self._shift_cache = {}
         self.inputs_ready = None       # optional CUDA event: inputs[1:] of forward_training are complete
         self.kernel_events = None      # bench.py: list collecting (start, end) CUDA events of the dominant kernel
@@ -576,21 +577,40 @@ class Engine:
         C.call("myolo_gemm_taps_wgrad", a4.rows, MASK_C, self.dy4d.rows, 4 * MASK_C, self.g["myolo_mask_deconv/kernel"],
                a4.M, 4 * MASK_C, MASK_C, 1, None, 1, st)
         g0, g1 = self.mg
-        C.call("myolo_gemm_taps", self.dy4d.rows, 4 * MASK_C, self.wt["myolo_mask_deconv/kernel"], g0.rows, MASK_C, a4.M,
-               MASK_C, 4 * MASK_C, 1, None, None, None, None, C.ACT_NONE, pfw, pfb, 0, st)
-        for i in (4, 3, 2, 1):
-            if self._mask_fused[i]:
-                b = self.bn[f"myolo_mask_bn{i}"]
-                C.call("myolo_bn_act_bwd_from_output", self.ma[i].view(), g0.view(), g0.view(), b.gamma, b.beta, b.mvar, BN_EPS,
-                       C.ACT_RELU | self.rnd, b.dgamma, b.dbeta, self.g[f"myolo_mask_conv{i}/bias"], self.ws, st)
+        M = a4.M
+        shn = self._neg_shifts
+
+        def fusable(i):      # BN_i backward can ride in the epilogue of the GEMM that produces d(a_i)
+            return i >= 2 and self._mask_fused[i] and self.tc and M >= 4096 and MASK_C == 256
+
+        def dgrad(src_rows, lda, bt, dst_rows, K, ntaps, shifts, bn_layer):
+            """d(a_bn_layer) = GEMM(src); with bn_layer set, its fixed-statistics BN + ReLU backward is fused into
+            the epilogue (dst = d(pre-BN), dgamma / dbeta / conv-bias gradients reduced on the fly)."""
+            if bn_layer:
+                b = self.bn[f"myolo_mask_bn{bn_layer}"]
+                C.call("myolo_gemm_taps_bnbwd", src_rows, lda, bt, dst_rows, MASK_C, M, MASK_C, K, ntaps, shifts, pfw, pfb,
+                       self.ma[bn_layer].rows, b.gamma, b.beta, b.mvar, BN_EPS, C.ACT_RELU | self.rnd, b.dgamma, b.dbeta,
+                       self.g[f"myolo_mask_conv{bn_layer}/bias"], self.ws, st)
             else:
-                self._bn_bwd(f"myolo_mask_bn{i}", self.my[i].view(), g0.view(), C.ACT_RELU | self.rnd, i == 1)
-                if i != 1:      # conv1's bias feeds a batch-statistics BN: its gradient is identically zero
-                    C.call("myolo_colsum", g0.view(), self.g[f"myolo_mask_conv{i}/bias"], self.ws, st)
+                C.call("myolo_gemm_taps", src_rows, lda, bt, dst_rows, MASK_C, M, MASK_C, K, ntaps, shifts, None, None, None,
+                       C.ACT_NONE, pfw, pfb, 0, st)
+
+        bn_done = fusable(4)
+        dgrad(self.dy4d.rows, 4 * MASK_C, self.wt["myolo_mask_deconv/kernel"], g0.rows, 4 * MASK_C, 1, None, 4 if bn_done else 0)
+        for i in (4, 3, 2, 1):
+            if not bn_done:
+                if self._mask_fused[i]:
+                    b = self.bn[f"myolo_mask_bn{i}"]
+                    C.call("myolo_bn_act_bwd_from_output", self.ma[i].view(), g0.view(), g0.view(), b.gamma, b.beta, b.mvar,
+                           BN_EPS, C.ACT_RELU | self.rnd, b.dgamma, b.dbeta, self.g[f"myolo_mask_conv{i}/bias"], self.ws, st)
+                else:
+                    self._bn_bwd(f"myolo_mask_bn{i}", self.my[i].view(), g0.view(), C.ACT_RELU | self.rnd, i == 1)
+                    if i != 1:      # conv1's bias feeds a batch-statistics BN: its gradient is identically zero
+                        C.call("myolo_colsum", g0.view(), self.g[f"myolo_mask_conv{i}/bias"], self.ws, st)
             C.call("myolo_conv3x3_wgrad", self.ma[i - 1].rows, g0.rows, self.g[f"myolo_mask_conv{i}/kernel"], n, P_, P_,
                    MASK_C, MASK_C, st)
-            C.call("myolo_conv3x3_dgrad", g0.rows, self.p[f"myolo_mask_conv{i}/kernel"], g1.rows, n, P_, P_, MASK_C,
-                   MASK_C, st)
+            bn_done = i >= 2 and fusable(i - 1)
+            dgrad(g0.rows, MASK_C, self.p[f"myolo_mask_conv{i}/kernel"], g1.rows, MASK_C, 9, shn, (i - 1) if bn_done else 0)
             g0, g1 = g1, g0
         # CropAndResizeGradImage into the feature-map gradient
         self.dfeat.storage.zero_()

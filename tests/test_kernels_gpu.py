@@ -587,3 +587,37 @@ def test_detect_postprocess_matches_numpy_pipeline(C):
             mism += (ref != got).sum()
         assert pm[b, n:].sum().item() == 0
     assert total_px > 1000 and mism <= 2e-3 * total_px, (mism, total_px)     # cv2 vs device rounding at exactly 0.5
+
+
+def test_dgrad_with_fused_bn_backward(C):
+    """myolo_gemm_taps_bnbwd (dgrad GEMM + BN/ReLU backward in the epilogue) against the exact two-step path:
+    CUDA-core dgrad followed by myolo_bn_act_bwd_from_output."""
+    from myolo.pf import PF, conv3x3_shifts
+    torch.manual_seed(22)
+    n, H, W, Cc = 40, 14, 14, 256
+    g_in = PF(n, H, W, Cc)
+    g_in.valid().normal_()
+    a_out = PF(n, H, W, Cc)
+    a_out.valid().copy_(torch.relu(torch.randn(n, H, W, Cc, device="cuda")))
+    w = torch.randn(9, Cc, Cc, device="cuda") / (9 * Cc) ** 0.5
+    gamma, beta = torch.rand(Cc, device="cuda") + 0.5, torch.randn(Cc, device="cuda") * 0.1
+    var = torch.rand(Cc, device="cuda") + 0.5
+    shn = C.int_array(conv3x3_shifts(W, negate=True))
+    pfw, pfb, M = W + 1, (H + 1) * (W + 1), g_in.M
+    ws = torch.zeros(4112, dtype=torch.float64, device="cuda")
+    ref = PF(n, H, W, Cc)
+    C.call("myolo_gemm_taps_ffma", g_in.rows, Cc, w, ref.rows, Cc, M, Cc, Cc, 9, shn, None, None, None, 0, pfw, pfb, 0, stream())
+    dg_r, db_r, dbias_r = (torch.empty(Cc, device="cuda") for _ in range(3))
+    C.call("myolo_bn_act_bwd_from_output", a_out.view(), ref.view(), ref.view(), gamma, beta, var, 1e-3, C.ACT_RELU, dg_r, db_r,
+           dbias_r, ws, stream())
+    out = PF(n, H, W, Cc)
+    dg, db, dbias = (torch.empty(Cc, device="cuda") for _ in range(3))
+    assert C.lib().myolo_gemm_taps_bnbwd_supported(Cc, Cc, M, Cc, Cc, 9, ctypes.addressof(shn)) == 1
+    C.call("myolo_gemm_taps_bnbwd", g_in.rows, Cc, w, out.rows, Cc, M, Cc, Cc, 9, shn, pfw, pfb, a_out.rows, gamma, beta, var,
+           1e-3, C.ACT_RELU, dg, db, dbias, ws, stream())
+    close(out.rows, ref.rows, 2e-3, "fused d(pre-BN)")
+    close(db, db_r, 2e-3, "fused dbeta")
+    close(dg, dg_r, 2e-3, "fused dgamma")
+    close(dbias, dbias_r, 2e-3, "fused dbias")
+    assert ws.abs().max().item() == 0, "BN workspace must be left zero"
+    assert out.storage[:Cc].abs().max().item() == 0 and out.rows.view(n, H + 1, W + 1, Cc)[:, 0].abs().max().item() == 0
