@@ -106,7 +106,7 @@ def oracle_step_fn(cfg, batch_np, nimg):
     P = init_params(c["NB"], c["NC"], 0, "trained_like")
     x = [torch.from_numpy(np.ascontiguousarray(batch_np[0][:nimg])), torch.from_numpy(batch_np[1][:nimg]).float(),
          torch.from_numpy(batch_np[2][:nimg]).float(), torch.from_numpy(batch_np[3][:nimg]),
-         torch.from_numpy(batch_np[4][:nimg]).float(), torch.from_numpy(batch_np[5][:nimg])]
+         torch.from_numpy(batch_np[4][:nimg]).float(), torch.from_numpy(batch_np[5][:nimg]).bool()]
     opt = {}
     return lambda: O.train_step(P, opt, x, oc, lr=1e-3)
 
@@ -215,6 +215,8 @@ def main():
     # ---- end to end through the public API: host numpy batch -> pinned -> H2D -> step -> D2H losses
     e2e = None
     if not args.no_e2e:
+        torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))
+        host_batches = [model.pin_inputs(hb) for hb in host_batches]     # the inputs live in pinned host memory
         for i in range(2):
             model.keras_model.train_on_batch(host_batches[i % pool])
         barrier()
@@ -254,7 +256,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        step = oracle_step_fn(cfg, host_batches[0], 2)
+        step = oracle_step_fn(cfg, [t.numpy() if torch.is_tensor(t) else t for t in host_batches[0]], 2)
         step()
         t0 = time.perf_counter(); n = 0
         while n < 3 and time.perf_counter() - t0 < 20:

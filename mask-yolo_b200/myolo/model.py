@@ -314,7 +314,9 @@ class MaskYOLO:
         out, nbytes = [], 0
         with torch.cuda.stream(self._copy_stream):
             for k, ((host, devt), x) in enumerate(zip(self._stage_bufs, inputs)):
-                if isinstance(x, torch.Tensor):
+                if isinstance(x, torch.Tensor) and x.is_pinned() and x.dtype == host.dtype and x.is_contiguous():
+                    host = x                              # already pinned and typed (pin_inputs): no host-side copy
+                elif isinstance(x, torch.Tensor):
                     host.copy_(x)
                 else:
                     host.copy_(torch.from_numpy(np.ascontiguousarray(x)))
@@ -329,6 +331,18 @@ class MaskYOLO:
         main.wait_event(ev_img)
         self.engine.inputs_ready = ev_all
         self.last_h2d_bytes = nbytes
+        return out
+
+    @staticmethod
+    def pin_inputs(inputs):
+        """BatchGenerator output (numpy) -> page-locked torch tensors in the dtypes the engine consumes; a data
+        loader that produces these lets train_on_batch skip its staging copy."""
+        want = [torch.float32, torch.float32, torch.float32, torch.int32, torch.float32, torch.uint8]
+        out = []
+        for x, dt in zip(inputs, want):
+            t = torch.empty(tuple(np.shape(x)), dtype=dt).pin_memory()
+            t.copy_(torch.from_numpy(np.ascontiguousarray(x)))
+            out.append(t)
         return out
 
     def _train_on_batch(self, inputs, update=True, lr=None):

@@ -225,3 +225,42 @@ def test_large_configs_tensor_core_path_matches_exact_fp32_path(S, B, NB, NC):
     assert bad <= 1e-3, bad                       # masks: see smoke() on ROIs that straddle the feature-map border
     rows = [(_l2(b["grads"][k], a["grads"][k]), k) for k in a["grads"] if a["grads"][k].abs().max() > 0 and k != "myolo_mask_conv1/bias"]
     assert max(rows)[0] <= 8e-2 and sorted(rows)[len(rows) // 2][0] <= 2e-2, max(rows)
+
+
+def test_edge_cases_no_ground_truth_and_nan_free():
+    """Ragged / empty inputs the reference graph tolerates: an image without any instance (all GT
+    rows are zero padding), and a batch without a single positive ROI (mask loss exactly 0, no mask-head
+    gradient).  Exact-fp32 engine against the fp32 oracle."""
+    from myolo.engine import Engine, init_params
+    S, B = 96, 3
+    c = Hh.engine_cfg(S=S)
+    oc = Hh.oracle_cfg(c)
+    P = init_params(c["NB"], c["NC"], 7, "trained_like")
+    img = torch.rand(B, S, S, 3, generator=torch.Generator().manual_seed(8))
+    boxes = Hh.random_boxes(B, 2, 9)
+    boxes[1] = []                                        # image 1: no instances at all
+    inputs = Hh.batch_from_boxes(c, B, img, boxes, 10)
+    assert inputs[3][1].abs().sum() == 0 and inputs[5][1].sum() == 0
+    Po = {k: v.clone() for k, v in P.items()}
+    out_o, g_o = O.train_step(Po, {}, Hh.to_oracle_inputs(inputs), oc, lr=1e-3)
+    eng = Engine(c, B, "training", "fp32", params=P)
+    out_e = eng.train_step(Hh.to_device(inputs), lr=1e-3)
+    torch.cuda.synchronize()
+    assert torch.equal(out_e["target_class_ids"].cpu(), out_o["target_class_ids"])
+    assert (out_e["target_class_ids"][1] == 0).all()
+    assert _abs(out_e["output_rois"], out_o["output_rois"]) <= 2e-4
+    assert _abs(out_e["myolo_mask"], out_o["myolo_mask"]) <= 2e-4
+    for k in ("yolo_sum_loss", "mask_loss"):
+        assert abs(out_e[k].item() - out_o[k].item()) <= 2e-4 * max(1.0, abs(out_o[k].item())), k
+    for t in eng.state_dict().values():
+        assert torch.isfinite(t).all()
+    # no positives anywhere: random GT far from every proposal
+    inputs2 = Hh.batch_from_boxes(c, B, img, [[] for _ in range(B)], 11)
+    eng2 = Engine(c, B, "training", "tf32x3", params=P)
+    out2 = eng2.train_step(Hh.to_device(inputs2), lr=1e-3)
+    torch.cuda.synchronize()
+    assert out2["mask_loss"].item() == 0.0 and int(eng2.n_pos.sum().item()) == 0
+    g2 = eng2.grad_dict()
+    assert g2["myolo_mask_conv3/kernel"].abs().max().item() == 0 and g2["feature_map/kernel"].abs().max().item() == 0
+    assert g2["conv_pw_3/kernel"].abs().max().item() > 0          # the yolo loss still trains the backbone
+    assert all(torch.isfinite(v).all() for v in g2.values())
