@@ -252,6 +252,15 @@ int myolo_detect_postprocess(const float* detections, const float* masks, int B,
                              int* out_class, float* out_score, int* out_count, unsigned char* out_masks,
                              myolo_stream stream);
 
+/* ---- target encoding on the device (host loops of myolo_utils.py:247-271 extract_bboxes and 769-820 BatchGenerator) ----
+ * boxes[b][m] = (x1,y1,x2,y2) of mask column m of gt_masks [B,S,S,M] bytes, x2/y2 exclusive, zeros for an empty mask. */
+int myolo_extract_bboxes(const unsigned char* gt_masks, int B, int S, int M, int* boxes, myolo_stream stream);
+/* yolo_target [B,G,G,NB,5+NC] and true_boxes [B,TB,4] (both zero-filled first) from padded int32 gt arrays
+ * [B,M] / [B,M,4] (rows with class id 0 are padding): centre and size in grid units, the cell holding the centre,
+ * the anchor with the best IoU against (0,0,w,h) (first maximum wins), later instances overwrite earlier ones. */
+int myolo_encode_yolo_targets(const int* gt_class_ids, const int* gt_boxes, int B, int M, int S, int G, int NB, int NC,
+                              int TB, const float* anchors, float* yolo_target, float* true_boxes, myolo_stream stream);
+
 /* ---- K17: Keras Adam, myolo/model.py:1071-1075 ----  lr_t = lr*sqrt(1-b2^t)/(1-b1^t) computed by caller */
 int myolo_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr_t,
                     float b1, float b2, float eps, float grad_scale, myolo_stream stream);

@@ -154,3 +154,109 @@ extern "C" int myolo_detect_postprocess(const float* detections, const float* ma
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// the host loops of BatchGenerator.__getitem__ (myolo_utils.py:769-820) and
+// extract_bboxes (247-271) on the device.
+// ------------------------------------------------------------------------------------------------
+namespace myolo {
+
+// one block per (instance, image): bounding box of a [S,S,M] byte mask column, x2/y2 exclusive
+__global__ void __launch_bounds__(256)
+extract_bboxes_kernel(const unsigned char* __restrict__ masks, int S, int M, int* __restrict__ boxes) {
+  const int m = blockIdx.x, b = blockIdx.y;
+  const unsigned char* P = masks + (size_t)b * S * S * M + m;
+  int x1 = S, y1 = S, x2 = -1, y2 = -1;
+  for (int i = threadIdx.x; i < S * S; i += blockDim.x) {
+    if (P[(size_t)i * M]) {
+      const int y = i / S, x = i - y * S;
+      x1 = min(x1, x); x2 = max(x2, x);
+      y1 = min(y1, y); y2 = max(y2, y);
+    }
+  }
+  __shared__ int r[4][8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    x1 = min(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+    y1 = min(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+    x2 = max(x2, __shfl_xor_sync(0xffffffffu, x2, o));
+    y2 = max(y2, __shfl_xor_sync(0xffffffffu, y2, o));
+  }
+  const int wp = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { r[0][wp] = x1; r[1][wp] = y1; r[2][wp] = x2; r[3][wp] = y2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) {
+      x1 = min(x1, r[0][w]); y1 = min(y1, r[1][w]);
+      x2 = max(x2, r[2][w]); y2 = max(y2, r[3][w]);
+    }
+    int* o = boxes + ((size_t)b * M + m) * 4;
+    if (x2 < 0) { o[0] = o[1] = o[2] = o[3] = 0; }         // empty mask -> zero box
+    else { o[0] = x1; o[1] = y1; o[2] = x2 + 1; o[3] = y2 + 1; }
+  }
+}
+
+// one thread per image, instances in order (a later instance overwrites an earlier one in the same
+// cell/anchor; the true-box buffer is a ring), exactly like the host loop.
+__global__ void encode_yolo_targets_kernel(const int* __restrict__ ids, const int* __restrict__ boxes, int B, int M, int S,
+                                           int G, int NB, int NC, int TB, const float* __restrict__ anchors,
+                                           float* __restrict__ yolo_target, float* __restrict__ true_boxes) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int D = 5 + NC;
+  float* Y = yolo_target + (size_t)b * G * G * NB * D;
+  float* T = true_boxes + (size_t)b * TB * 4;
+  const double cell = (double)S / (double)G;
+  int slot = 0;
+  for (int i = 0; i < M; ++i) {
+    const int cls = ids[(size_t)b * M + i];
+    if (cls <= 0) continue;                                  // zero padding of the [B, TRUE_BOX_BUFFER] arrays
+    const int* q = boxes + ((size_t)b * M + i) * 4;
+    const double cx = 0.5 * (q[0] + q[2]) / cell, cy = 0.5 * (q[1] + q[3]) / cell;
+    const int gx = (int)floor(cx), gy = (int)floor(cy);
+    if (gx < G && gy < G) {
+      const double w = (q[2] - q[0]) / cell, h = (q[3] - q[1]) / cell;
+      int best = -1;
+      double best_iou = -1.0;
+      for (int a = 0; a < NB; ++a) {                         // bbox_iou((0,0,w,h), (0,0,aw,ah)); first maximum wins
+        const double aw = (double)anchors[2 * a], ah = (double)anchors[2 * a + 1];
+        const double iw = (aw < 0.0) ? 0.0 : fmin(w, aw), ih = (ah < 0.0) ? 0.0 : fmin(h, ah);
+        const double inter = iw * ih;
+        const double iou = inter / (w * h + aw * ah - inter);
+        if (best_iou < iou) { best = a; best_iou = iou; }
+      }
+      if (best >= 0 && cls < NC) {
+        float* y = Y + (((size_t)gy * G + gx) * NB + best) * D;
+        y[0] = (float)cx; y[1] = (float)cy; y[2] = (float)w; y[3] = (float)h; y[4] = 1.f;
+        y[5 + cls] = 1.f;
+        float* t = T + (size_t)slot * 4;
+        t[0] = (float)cx; t[1] = (float)cy; t[2] = (float)w; t[3] = (float)h;
+        slot = (slot + 1) % TB;
+      }
+    }
+  }
+}
+
+}  // namespace myolo
+
+extern "C" int myolo_extract_bboxes(const unsigned char* gt_masks, int B, int S, int M, int* boxes, myolo_stream stream) {
+  MYOLO_CHECK_ARG(gt_masks && boxes && B > 0 && S > 0 && M > 0);
+  dim3 grid(M, B);
+  myolo::extract_bboxes_kernel<<<grid, 256, 0, myolo::as_stream(stream)>>>(gt_masks, S, M, boxes);
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
+}
+
+extern "C" int myolo_encode_yolo_targets(const int* gt_class_ids, const int* gt_boxes, int B, int M, int S, int G, int NB,
+                                         int NC, int TB, const float* anchors, float* yolo_target, float* true_boxes,
+                                         myolo_stream stream) {
+  MYOLO_CHECK_ARG(gt_class_ids && gt_boxes && anchors && yolo_target && true_boxes);
+  MYOLO_CHECK_ARG(B > 0 && M > 0 && S > 0 && G > 0 && NB > 0 && NC > 0 && TB > 0);
+  cudaStream_t st = myolo::as_stream(stream);
+  MYOLO_CUDA(cudaMemsetAsync(yolo_target, 0, (size_t)B * G * G * NB * (5 + NC) * sizeof(float), st));
+  MYOLO_CUDA(cudaMemsetAsync(true_boxes, 0, (size_t)B * TB * 4 * sizeof(float), st));
+  myolo::encode_yolo_targets_kernel<<<(B + 63) / 64, 64, 0, st>>>(gt_class_ids, gt_boxes, B, M, S, G, NB, NC, TB, anchors,
+                                                                  yolo_target, true_boxes);
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
+}

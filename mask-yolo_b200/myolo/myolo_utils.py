@@ -303,6 +303,31 @@ def data_generator(dataset, config, shuffle=True, augment=False, augmentation=No
                 raise
 
 
+def encode_targets_device(config, gt_class_ids, gt_boxes, gt_masks=None):
+    """Device-side version of the per-batch target construction of BatchGenerator.__getitem__ (769-820):
+    padded int32 gt arrays [B,TB] / [B,TB,4] on the GPU -> (true_boxes [B,1,1,1,TB,4], yolo_target
+    [B,GH,GW,NB,5+NC]) fp32 on the GPU.  With gt_boxes=None the boxes are first extracted from gt_masks
+    [B,S,S,M] (extract_bboxes, 247-271)."""
+    import torch
+    from . import _cabi as C
+    from .config import resolve
+    c = resolve(config)
+    st = torch.cuda.current_stream().cuda_stream
+    ids = gt_class_ids.int().contiguous()
+    B, M = ids.shape
+    if gt_boxes is None:
+        gm = gt_masks.to(torch.uint8).contiguous()
+        assert gm.shape[3] == M
+        gt_boxes = torch.empty(B, M, 4, dtype=torch.int32, device=ids.device)
+        C.call("myolo_extract_bboxes", gm, B, c["S"], M, gt_boxes, st)
+    boxes = gt_boxes.int().contiguous()
+    yt = torch.empty(B, c["G"], c["G"], c["NB"], 5 + c["NC"], device=ids.device)
+    tb = torch.empty(B, 1, 1, 1, c["TB"], 4, device=ids.device)
+    anchors = torch.tensor(c["ANCHORS"], dtype=torch.float32, device=ids.device)
+    C.call("myolo_encode_yolo_targets", ids, boxes, B, M, c["S"], c["G"], c["NB"], c["NC"], c["TB"], anchors, yt, tb, st)
+    return tb, yt, boxes
+
+
 def batch_slice(inputs, graph_fn, batch_size, names=None):
     """Apply graph_fn to each batch slice and stack the results (myolo_utils.py:929-963).  Kept for API
     compatibility with torch tensors / numpy arrays; the engine's target kernel is batched natively."""

@@ -621,3 +621,19 @@ def test_dgrad_with_fused_bn_backward(C):
     close(dbias, dbias_r, 2e-3, "fused dbias")
     assert ws.abs().max().item() == 0, "BN workspace must be left zero"
     assert out.storage[:Cc].abs().max().item() == 0 and out.rows.view(n, H + 1, W + 1, Cc)[:, 0].abs().max().item() == 0
+
+
+def test_target_encoding_on_device_matches_batch_generator(C):
+    """myolo_extract_bboxes / myolo_encode_yolo_targets against the host BatchGenerator (bit-exact)."""
+    from myolo import myolo_utils as mu
+    from myolo.shapes import ShapesConfig, make_batches
+
+    class Cfg(ShapesConfig):
+        BATCH_SIZE = 8
+    cfg = Cfg()
+    images, tb, yt, ids, boxes, masks = make_batches(cfg, 1, seed=77)[0]
+    assert (ids > 0).sum() >= 8
+    tb_d, yt_d, boxes_d = mu.encode_targets_device(cfg, torch.tensor(ids).cuda(), None, torch.tensor(masks).cuda())
+    assert np.array_equal(boxes_d.cpu().numpy(), boxes), "extract_bboxes"
+    assert np.array_equal(yt_d.cpu().numpy(), yt.astype(np.float32)), "yolo_target"
+    assert np.array_equal(tb_d.cpu().numpy(), tb.astype(np.float32)), "true_boxes"
