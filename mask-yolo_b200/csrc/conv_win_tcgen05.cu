@@ -1,21 +1,30 @@
-// conv_win_tcgen05.cu -- multi-tap (3x3) convolution on padded-flat tensors as ONE persistent
-// tcgen05 kernel with shared-memory reuse of the A operand across taps.
+// conv_win_tcgen05.cu -- multi-tap (3x3) convolutions and large plain GEMMs on padded-flat tensors as ONE
+// persistent tcgen05 kernel with shared-memory reuse of the A operand across taps.
 //
-//   C[m, n] = epi( sum_t sum_k A[m + shift_t, k] * Bt[t][n][k] ),   |shift_t| <= 16, N = 256
+//   C[m, n] = epi( sum_t sum_k A[m + shift_t, k] * Bt[t][n][k] ),   |shift_t| <= 16, N % 128 == 0
 //
-// Why: with fp32 operands a 128x256 tile needs 48 KB of L2->smem traffic per 2.1 MFLOP and the
-// one-tile-per-CTA kernel (gemm_tcgen05.cu) is bound by L2 bandwidth (ncu: lts 52 %, tensor pipe
-// 38 %).  The nine taps of a 3x3 conv read the SAME activation rows shifted by at most W+2 rows, so
-// this kernel loads one window of 256+32 rows per 32-channel k-block (36 KB) and addresses all nine
-// taps inside it by moving the UMMA descriptor start by whole 128-byte rows (measured on B200: the
-// 128B swizzle is a function of the absolute shared-memory address, so a row-shifted start needs no
-// base_offset); the weights stream through a 4-stage ring and feed TWO 128-row accumulators
-// (512 TMEM columns), halving their traffic per output row.  L2 traffic per output row drops 2.6x.
+// Why: with fp32 (tf32) operands a 128x256 output tile needs 48 KB of L2->shared-memory traffic per 2.1 MFLOP,
+// and the one-tile-per-CTA kernel (gemm_tcgen05.cu) ran at 38 % tensor-pipe utilisation.  The nine taps of a
+// 3x3 conv read the SAME activation rows shifted by at most W+2 rows, so this kernel loads one window of
+// 128+32 rows per 32-channel k-block and addresses all nine taps inside it by moving the UMMA descriptor start
+// by whole 128-byte rows (measured on B200: the 128B swizzle is a function of the absolute shared-memory
+// address, so a row-shifted start needs no base_offset).  Default configuration (template <256, 1, 2>):
+//   * CTA pair (cluster of 2, cta_group::2): one 256-row MMA spans both SMs; each CTA holds its own 128 rows
+//     (window + TMEM accumulator) and HALF of every weight stage -> L2->SM fill per FLOP halves;
+//   * 8-stage weight ring (16 KB per CTA per stage), double-buffered activation window;
+//   * two TMEM stages: the epilogue of item i overlaps the main loop of item i+1;
+//   * epilogue through swizzled shared-memory staging + TMA tensor stores (a thread owns one output ROW;
+//     storing rows straight to global memory cost as much as the whole main loop).
+// Fused epilogues: bias / folded fixed-statistics BN / activation (forward convs); the backward of the previous
+// layer's BN + ReLU with its dgamma / dbeta column sums (dgrad, myolo_gemm_taps_bnbwd); the whole mask tail
+// (deconv bias + ReLU + 1x1 conv + sigmoid, myolo_deconv_mask_fwd).
 //
-// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 =
-// epilogue.  Persistent: CTA i processes tiles i, i+grid, ...; the producer keeps prefetching the
-// next tile's operands while the epilogue drains TMEM.
-// Replaces the Conv2D / Conv2DBackpropInput call sites of the mask head (myolo/model.py:688-706).
+// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (leader CTA only),
+// warps 2..5 = epilogue.  Persistent: cluster i processes items i, i+n_clusters, ...
+// Replaces the Conv2D / Conv2DBackpropInput / Conv2DTranspose call sites of the mask head
+// (myolo/model.py:688-713) and the large pointwise GEMMs of the backbone.
+// MYOLO_WIN_BO (experiment switches, default 0): 2 no TMA loads, 4 no global stores, 8 128-column slices,
+// 16 two accumulators per CTA, 32 single-CTA instead of CTA pairs.
 #include "tc_common.cuh"
 
 namespace myolo {

@@ -637,3 +637,52 @@ def test_target_encoding_on_device_matches_batch_generator(C):
     assert np.array_equal(boxes_d.cpu().numpy(), boxes), "extract_bboxes"
     assert np.array_equal(yt_d.cpu().numpy(), yt.astype(np.float32)), "yolo_target"
     assert np.array_equal(tb_d.cpu().numpy(), tb.astype(np.float32)), "true_boxes"
+
+
+def test_staging_helpers_split_fold_copy_and_batched_moving_update(C):
+    """The small layout / precision staging entry points: tf32 hi/lo split (3xTF32 operands), BN folding,
+    strided view copy (dense <-> padded-flat, accumulate, tf32 rounding) and the batched moving-average update."""
+    import struct
+    from myolo.pf import PF
+    torch.manual_seed(23)
+    n, H, W, Cc = 3, 6, 5, 32
+    x = torch.randn(n, H, W, Cc, device="cuda")
+    hi, lo = torch.empty_like(x), torch.empty_like(x)
+    xv = C.view(x, n, H, W, Cc)
+    C.call("myolo_split_tf32", xv, C.view(hi, n, H, W, Cc), C.view(lo, n, H, W, Cc), stream())
+    assert (hi.view(torch.int32) & 0x1FFF).abs().max().item() == 0 and (lo.view(torch.int32) & 0x1FFF).abs().max().item() == 0
+    assert ((hi + lo) - x).abs().max().item() <= 2 ** -21 * x.abs().max().item()        # hi+lo recovers ~22 mantissa bits
+    # split BN apply == split of the plain BN apply
+    g, b = torch.rand(Cc, device="cuda") + 0.5, torch.randn(Cc, device="cuda") * 0.1
+    mean, var = torch.randn(Cc, device="cuda") * 0.1, torch.rand(Cc, device="cuda") + 0.5
+    y = torch.empty_like(x)
+    C.call("myolo_bn_apply", xv, C.view(y, n, H, W, Cc), mean, var, g, b, 1e-3, C.ACT_RELU6, stream())
+    yh, yl = torch.empty_like(x), torch.empty_like(x)
+    C.call("myolo_bn_apply_split", xv, C.view(yh, n, H, W, Cc), C.view(yl, n, H, W, Cc), mean, var, g, b, 1e-3, C.ACT_RELU6, stream())
+    assert ((yh + yl) - y).abs().max().item() <= 2 ** -20 * max(y.abs().max().item(), 1.0)
+    # fold: scale/shift reproduce the BN affine map
+    sc, sh = torch.empty(Cc, device="cuda"), torch.empty(Cc, device="cuda")
+    C.call("myolo_bn_fold", g, b, mean, var, 1e-3, sc, sh, Cc, stream())
+    close(x * sc + sh, (x - mean) * torch.rsqrt(var + 1e-3) * g + b, 2e-6, "bn fold")
+    # view copy: dense -> padded-flat, then accumulate back
+    pf = PF(n, H, W, Cc)
+    C.call("myolo_view_copy", xv, pf.view(), 0, stream())
+    assert torch.equal(pf.dense(), x) and pf.rows.view(n, H + 1, W + 1, Cc)[:, 0].abs().max().item() == 0
+    acc = x.clone()
+    C.call("myolo_view_copy", pf.view(), C.view(acc, n, H, W, Cc), 1, stream())
+    assert torch.equal(acc, 2 * x)
+    # batched moving update == per-layer update
+    val = [torch.rand(Cc, device="cuda") + 0.1 for _ in range(2)]
+    bi = [torch.zeros(Cc, device="cuda") for _ in range(4)]
+    mo = [torch.zeros(Cc, device="cuda") for _ in range(4)]
+    npix = 77.0
+    corr = (npix / (npix - 1)) * (npix / (npix - (1 + 1e-3)))
+    rec = struct.pack("<QQQif", val[0].data_ptr(), bi[0].data_ptr(), mo[0].data_ptr(), Cc, 1.0) + \
+        struct.pack("<QQQif", val[1].data_ptr(), bi[1].data_ptr(), mo[1].data_ptr(), Cc, corr)
+    table = torch.frombuffer(bytearray(rec), dtype=torch.uint8).cuda()
+    for step in (1, 2):
+        C.call("myolo_bn_moving_update_batch", table, 2, 0.99, step, stream())
+        C.call("myolo_bn_moving_update", val[0], bi[2], mo[2], Cc, 0.99, step, 0, npix, 1e-3, stream())
+        C.call("myolo_bn_moving_update", val[1], bi[3], mo[3], Cc, 0.99, step, 1, npix, 1e-3, stream())
+        close(mo[0], mo[2], 1e-6, "batched moving mean")
+        close(mo[1], mo[3], 1e-6, "batched moving var")
