@@ -421,7 +421,7 @@ static int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& td, float* dW,
 template <int BN, int NACC>
 static int launch_wgrad_n(const CUtensorMap& ta, const CUtensorMap& td, float* dW, long long M, int N, int K, int ntaps,
                           const TapShifts& sh, int transpose_out, cudaStream_t st) {
-  const int ntk = K / (BM * NACC), ntn = N / BN;
+  const int ntk = (K + BM * NACC - 1) / (BM * NACC), ntn = N / BN;
   const long long tiles = (long long)ntk * ntn * ntaps;
   long long nsplit = max(1LL, min(ceil_div(M, 32 * 8), (long long)kNumSMs / tiles));
   if (nsplit < 1) nsplit = 1;
@@ -488,7 +488,9 @@ extern "C" int myolo_gemm_taps_tc(const float* A, long long lda, const float* Bt
 }
 
 extern "C" int myolo_gemm_taps_wgrad_tc_supported(long long lda, long long ldd, long long M, int N, int K, int ntaps) {
-  return M >= 32 && M < (1LL << 31) - 4096 && (K % BM) == 0 && pick_bn(N) != 0 && (lda % 4) == 0 && (ldd % 4) == 0 &&
+  // K (A channels) only needs whole 32-channel TMA boxes: channels past K inside the last 128-channel tile are
+  // out-of-bounds boxes (zero fill) and their accumulator rows are never stored
+  return M >= 32 && M < (1LL << 31) - 4096 && (K % 32) == 0 && pick_bn(N) != 0 && (lda % 4) == 0 && (ldd % 4) == 0 &&
          ntaps >= 1 && ntaps <= 32;
 }
 

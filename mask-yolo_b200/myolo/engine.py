@@ -452,7 +452,7 @@ class Engine:
         if self.tc and C.lib().myolo_deconv_mask_fwd_supported(MASK_C, self.NC):
             # one tcgen05 kernel: deconv GEMM + bias + ReLU + 1x1 conv + sigmoid; the deconv activation is
             # kept only for positive rois (all the backward pass reads)
-            ids = self.target_ids if (training and self.mode == "training") else None
+            ids = self.target_ids if self.mode == "training" else None
             C.call("myolo_deconv_mask_fwd", a4.rows, self.p["myolo_mask_deconv/kernel"], self.p["myolo_mask_deconv/bias"],
                    self.p["myolo_mask/kernel"], self.p["myolo_mask/bias"], A["masks"], ids, self.y4d.rows, n, P_, P_,
                    MASK_C, self.NC, st)
@@ -486,14 +486,15 @@ class Engine:
                mh, mw, top_k, float(cs_threshold), float(nms_threshold), idx, boxes, cls, score, cnt, pm, self._st())
         return idx, boxes, cls, score, cnt, pm
 
-    def forward_training(self, inputs):
-        """mode='training' graph (model.py:844-901); inputs as BatchGenerator yields them:
+    def forward_training(self, inputs, learning_phase: bool = True):
+        """mode='training' graph (model.py:844-901); learning_phase=False evaluates the same graph the way Keras
+        validates (every BN on its moving statistics).  inputs as BatchGenerator yields them:
         [image, true_boxes [B,1,1,1,TB,4], yolo_target [B,G,G,NB,5+NC], gt_class_ids [B,M] i32,
         gt_boxes [B,M,4] px (x1,y1,x2,y2), gt_masks [B,S,S,M] bool] -- device tensors."""
         image, true_boxes, yolo_target = inputs[0], inputs[1], inputs[2]
         A, B, st, cfg = self.A, self.B, self._st(), self.cfg
         G, NB, NC, TB, R = cfg["G"], self.NB, self.NC, self.TB, self.R
-        yolo = self.forward(image, training=True)
+        yolo = self.forward(image, training=learning_phase)
         if self.inputs_ready is not None:      # ground-truth tensors still in flight on the caller's copy stream
             torch.cuda.current_stream().wait_event(self.inputs_ready)
             self.inputs_ready = None
@@ -512,7 +513,7 @@ class Engine:
             C.call("myolo_detect_mask_targets", A["proposals"], gt_ids, gt_boxes, gt_masks, B, R, M, gt_masks.shape[3],
                    cfg["S"], mh, mw,
                    A["rois"], self.target_ids, A["target_masks"], self.n_pos, self.roi_src, self.roi_gt, st)
-            masks = self.mask_head(A["rois"], training=True)
+            masks = self.mask_head(A["rois"], training=learning_phase)
             C.call("myolo_mask_loss", A["masks"], A["target_masks"], self.target_ids, self.n_roi, mh, mw, NC,
                    float(lw.get("myolo_mask_loss", 1.0)), self.loss_mask, A["dlogit"], self.ws_loss, st)
             out.update(output_rois=A["rois"], myolo_mask=masks, mask_loss=self.loss_mask[0],

@@ -351,7 +351,7 @@ class MaskYOLO:
         if update:
             out = eng.train_step(dev_inputs, lr if lr is not None else self.learning_rate, self.allreduce)
         else:
-            out = eng.forward_training(dev_inputs)
+            out = eng.forward_training(dev_inputs, learning_phase=False)     # Keras validates with learning phase 0
         res = [out["yolo_sum_loss"]] + ([out["mask_loss"]] if "mask_loss" in out else [])
         vals = torch.stack(res).cpu().tolist()           # device -> host read of the step's losses
         self.last_d2h_bytes = 4 * len(vals)

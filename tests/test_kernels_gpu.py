@@ -240,11 +240,11 @@ def test_conv3x3_pf(C, impl, tol, n, H, W, Ci, Co):
     close(pdx.dense(), xr.grad, tol, f"conv3x3 dgrad {impl}")
     # wgrad
     dw = torch.zeros(9, Ci, Co, device="cuda")
-    C.call(f"myolo_gemm_taps_wgrad_{impl}" if impl == "ffma" or Ci % 128 == 0 else "myolo_gemm_taps_wgrad_ffma",
+    C.call(f"myolo_gemm_taps_wgrad_{impl}",      # tcgen05 path: Ci only needs whole 32-channel boxes
            px.rows, Ci, pdy.rows, Co, dw, M, Co, Ci, 9, sh, 0, stream())
     close(dw, w.grad.reshape(9, Ci, Co), tol, f"conv3x3 wgrad {impl}")
     dwt = torch.zeros(9, Co, Ci, device="cuda")
-    C.call(f"myolo_gemm_taps_wgrad_{impl}" if impl == "ffma" or Ci % 128 == 0 else "myolo_gemm_taps_wgrad_ffma",
+    C.call(f"myolo_gemm_taps_wgrad_{impl}",      # tcgen05 path: Ci only needs whole 32-channel boxes
            px.rows, Ci, pdy.rows, Co, dwt, M, Co, Ci, 9, sh, 1, stream())
     close(dwt, w.grad.reshape(9, Ci, Co).transpose(1, 2), tol, f"conv3x3 wgrad^T {impl}")
 
