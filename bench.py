@@ -247,10 +247,13 @@ def main():
             traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("mask_conv_fwd_dram_bytes_per_launch")
         except Exception:
             pass
-        roof = {"kernel": "tc_conv_win_kernel<256> (mask-head 3x3 conv forward, persistent 9-tap tcgen05 kind::tf32)", "bound": "tensor", "achieved": ach,
+        h16 = args.precision == "h16"
+        roof = {"kernel": "tc_conv_win_kernel<256> (mask-head 3x3 conv forward, persistent 9-tap tcgen05 kind::%s, CTA pairs)" % ("f16" if h16 else "tf32"),
+                "bound": "tensor", "achieved": ach,
                 "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"],
                 "traffic": traffic, "avg_launch_ms": avg_ms, "launches_timed": len(durs), "algorithmic_flops_per_launch": flops,
-                "peak_source": pk_src + " bf16 sustained (tf32 runs at half the bf16 tensor rate: nominal 1.1 vs 2.25 PFLOP/s)",
+                "peak_source": pk_src + (" bf16 sustained (kind::f16 runs at the bf16 rate)" if h16 else
+                                         " bf16 sustained (tf32 runs at half the bf16 tensor rate: nominal 1.1 vs 2.25 PFLOP/s)"),
                 "step_share": sum(durs) / ms.item()}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -268,7 +271,8 @@ def main():
         fl = cpu_flops_per_image(c)
         line = {"metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "tf32" if args.precision != "fp32" else "f32", "data": "synthetic",
+                "dtype": {"fp32": "f32", "h16": "f16 operands (mask head) / 3xtf32 (backbone), f32 accumulate"}.get(args.precision, "tf32"),
+                "data": "synthetic",
                 "config": {"workload": f"Shapes {args.size}x{args.size} batch {B}/GPU, MobileNet+YOLO+ROIAlign+mask fwd+bwd+Adam",
                            "global_batch": B * world, "N_BOX": c["NB"], "NUM_CLASSES": c["NC"], "rois_per_image": c["R"],
                            "precision": args.precision, "positive_rois_last_step": npos, "parallelism": f"dp{world}",

@@ -193,6 +193,45 @@ int myolo_roialign_fwd(const myolo_view* feat, const float* boxes, int n_roi, in
 int myolo_roialign_bwd(const myolo_view* dout, const float* boxes, int n_roi, int rois_per_img, int pool,
                        const myolo_view* dfeat, myolo_stream stream);
 
+/* ---- half-operand (tcgen05 kind::f16) variants of the mask-head path, myolo/model.py:688-713 ----
+ * The mask head is 98.8 % of the FLOPs.  tcgen05 has no fp32 MMA; kind::tf32 keeps 10 explicit mantissa bits, IEEE half
+ * keeps the same 10 at TWICE the tensor rate and half the operand bytes.  In the "h16" precision mode the mask-head
+ * activations, staged weights and (loss-scaled) gradients are stored as IEEE half, every accumulation stays fp32 in
+ * TMEM, and every epilogue (bias, BN, ReLU, sigmoid, column sums) stays fp32.  `const void*` / `void*` arguments
+ * below are device pointers to IEEE-half data; half myolo_views use the same struct with p pointing at half data
+ * and sn / sh counted in ELEMENTS.  Conversions are round-to-nearest-even, saturating at +-65504. */
+/* out[t][c][r] = half(in[t][r][c]) when transpose != 0, else out = half(in) (weight staging, see myolo_prep_weights) */
+int myolo_prep_weights_h(const float* in, void* out_half, int ntaps, int rows, int cols, int transpose, myolo_stream stream);
+/* myolo_gemm_taps on the persistent CTA-pair kernel with half A / Bt.  Outputs: C (fp32, nullable) and Ch (half,
+ * nullable), at least one.  When both are stored, C holds the half-rounded values.  acc_scale (nullable): DEVICE scalar
+ * multiplied into the accumulator before the epilogue (un-scaling of loss-scaled gradients).  N % 256 == 0, K % 64 == 0,
+ * ntaps >= 2 with |shift| <= 16, or a plain GEMM with M >= 4096. */
+int myolo_gemm_taps_h(const void* A, long long lda, const void* Bt, float* C, long long ldc, void* Ch, long long ldch,
+                      long long M, int N, int K, int ntaps, const int* shifts_host, const float* bias,
+                      const float* scale, const float* shift_c, int act, int pf_w1, int pf_blk,
+                      const float* acc_scale, myolo_stream stream);
+int myolo_gemm_taps_h_supported(long long lda, long long M, int N, int K, int ntaps, const int* shifts_host);
+/* myolo_deconv_mask_fwd with half a4 [rows][Cmid] and half kd [4*Cmid][Cmid] (masks, y4 stay fp32). */
+int myolo_deconv_mask_fwd_h(const void* a4, const void* kd, const float* bd, const float* w1, const float* b1,
+                            float* masks, const int* target_ids, float* y4, int n_roi, int H, int W, int Cmid, int NC,
+                            myolo_stream stream);
+/* myolo_gemm_taps_bnbwd with half A / Bt / a_out; the result goes to C (fp32, nullable) and / or Ch (half, nullable),
+ * both [M][N] with pitch ldc.  grad_unscale (nullable): DEVICE scalar applied to dgamma / dbeta / dbias (the incoming
+ * gradient carries a loss scale; the stored d(pre-BN) keeps it). */
+int myolo_gemm_taps_bnbwd_h(const void* A, long long lda, const void* Bt, float* C, void* Ch, long long ldc,
+                            long long M, int N, int K, int ntaps, const int* shifts_host, int pf_w1, int pf_blk,
+                            const void* a_out, const float* gamma, const float* beta, const float* var, float eps,
+                            int act, float* dgamma, float* dbeta, float* dbias, double* ws,
+                            const float* grad_unscale, myolo_stream stream);
+int myolo_bn_epi_finalize_s(double* sums, const float* gamma, const float* var, float eps, float* dgamma,
+                            float* dbeta, float* dbias, int C, const float* unscale, myolo_stream stream);
+/* myolo_roialign_fwd with the pooled values stored as half (out_half) and, when out != NULL, also as fp32. */
+int myolo_roialign_fwd_h(const myolo_view* feat, const float* boxes, int n_roi, int rois_per_img, int pool,
+                         const myolo_view* out, const myolo_view* out_half, myolo_stream stream);
+/* myolo_bn_apply with the result stored as half (y_half) and, when y != NULL, as fp32 holding the same rounded values. */
+int myolo_bn_apply_h(const myolo_view* x, const myolo_view* y, const myolo_view* y_half, const float* mean,
+                     const float* var, const float* gamma, const float* beta, float eps, int act, myolo_stream stream);
+
 /* ---- K12: DecodeYOLOLayer / DetectionsLayer, myolo/model.py:1442-1473, 1493-1538 ---- */
 int myolo_yolo_decode(const float* y_pred, const float* anchors, float* boxes, float* detections /*nullable*/,
                       int B, int GH, int GW, int NB, int NC, myolo_stream stream);

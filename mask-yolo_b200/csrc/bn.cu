@@ -211,6 +211,49 @@ bn_apply_kernel(V x, V y, V ylo, const float* __restrict__ mean, const float* __
   }
 }
 
+__device__ __forceinline__ uint32_t pack_half2_sat(float lo, float hi) {
+  uint16_t a, b;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(a) : "f"(lo));
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(b) : "f"(hi));
+  return (uint32_t)a | ((uint32_t)b << 16);
+}
+__device__ __forceinline__ float half_bits_to_float(uint32_t h) {
+  float r;
+  asm("cvt.f32.f16 %0, %1;" : "=f"(r) : "h"((uint16_t)h));
+  return r;
+}
+
+// BN + activation with the result stored as IEEE half (yh, operand of a kind::f16 GEMM) and, when y.p is not
+// null, as fp32 holding the SAME half-rounded values (what the backward pass reads).
+__global__ void __launch_bounds__(256)
+bn_apply_h_kernel(V x, V y, V yh, const float* __restrict__ mean, const float* __restrict__ var,
+                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int act) {
+  const int C4 = x.c >> 2;
+  const FastDiv x_fc4 = x.fc4;
+  const long long total = (long long)x.n * x.h * x.w * C4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const uint32_t pp = fd_div((uint32_t)i, x_fc4);
+    const int q = (int)((uint32_t)i - pp * (uint32_t)C4) * 4;
+    const long long p = pp;
+    const float4 v = *reinterpret_cast<const float4*>(x.p + pix_off(x, p) + q);
+    const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + q));
+    const float4 vv = __ldg(reinterpret_cast<const float4*>(var + q));
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + q));
+    const float4 be = __ldg(reinterpret_cast<const float4*>(beta + q));
+    float4 o;
+    o.x = apply_act(fmaf((v.x - mu.x) * (1.f / sqrtf(vv.x + eps)), ga.x, be.x), act & 0xff);
+    o.y = apply_act(fmaf((v.y - mu.y) * (1.f / sqrtf(vv.y + eps)), ga.y, be.y), act & 0xff);
+    o.z = apply_act(fmaf((v.z - mu.z) * (1.f / sqrtf(vv.z + eps)), ga.z, be.z), act & 0xff);
+    o.w = apply_act(fmaf((v.w - mu.w) * (1.f / sqrtf(vv.w + eps)), ga.w, be.w), act & 0xff);
+    const uint32_t p0 = pack_half2_sat(o.x, o.y), p1 = pack_half2_sat(o.z, o.w);
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(yh.p) + pix_off(yh, p) + q) = make_uint2(p0, p1);
+    if (y.p)
+      *reinterpret_cast<float4*>(y.p + pix_off(y, p) + q) =
+          make_float4(half_bits_to_float(p0 & 0xffffu), half_bits_to_float(p0 >> 16), half_bits_to_float(p1 & 0xffffu),
+                      half_bits_to_float(p1 >> 16));
+  }
+}
+
 __global__ void __launch_bounds__(256) split_tf32_kernel(V src, V hi, V lo) {
   const int C4 = src.c >> 2;
   const FastDiv x_fc4 = src.fc4;
@@ -460,6 +503,19 @@ extern "C" int myolo_bn_apply_split(const myolo_view* x, const myolo_view* y_hi,
   return MYOLO_OK;
 }
 
+extern "C" int myolo_bn_apply_h(const myolo_view* x, const myolo_view* y, const myolo_view* y_half, const float* mean,
+                                const float* var, const float* gamma, const float* beta, float eps, int act,
+                                myolo_stream stream) {
+  MYOLO_CHECK_ARG(view_ok(x) && view_ok(y_half) && same_shape(x, y_half) && (!y || (view_ok(y) && same_shape(x, y))));
+  MYOLO_CHECK_ARG(mean && var && gamma && beta && ((uintptr_t)y_half->p & 7) == 0);
+  const long long total = (long long)x->n * x->h * x->w * (x->c / 4);
+  V vy = y ? to_v(y) : to_v(x);
+  if (!y) vy.p = nullptr;
+  bn_apply_h_kernel<<<ew_blocks(total), 256, 0, as_stream(stream)>>>(to_v(x), vy, to_v(y_half), mean, var, gamma, beta, eps, act);
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
+}
+
 extern "C" int myolo_split_tf32(const myolo_view* src, const myolo_view* hi, const myolo_view* lo, myolo_stream stream) {
   MYOLO_CHECK_ARG(view_ok(src) && view_ok(hi) && view_ok(lo) && same_shape(src, hi) && same_shape(src, lo));
   const long long total = (long long)src->n * src->h * src->w * (src->c / 4);
@@ -570,10 +626,11 @@ extern "C" int myolo_bn_moving_update_batch(const void* items_dev, int n_items, 
 namespace myolo {
 __global__ void bn_epi_finalize_kernel(double* __restrict__ sums, const float* __restrict__ gamma, const float* __restrict__ var,
                                        float eps, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
-                                       int C) {
+                                       int C, const float* __restrict__ unscale) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) {
-    const double S0 = sums[c], S1 = sums[C + c];
+    const double us = unscale ? (double)__ldg(unscale) : 1.0;   // the gradient tensor carried a loss scale
+    const double S0 = sums[c] * us, S1 = sums[C + c] * us;
     dbeta[c] = (float)S0;
     dgamma[c] = (float)S1;
     if (dbias) dbias[c] = (float)(S0 * (double)(gamma[c] * (1.f / sqrtf(var[c] + eps))));
@@ -584,10 +641,14 @@ __global__ void bn_epi_finalize_kernel(double* __restrict__ sums, const float* _
 }  // namespace myolo
 
 // finishes the column sums a GEMM epilogue accumulated (myolo_gemm_taps_bnbwd) and zeroes them again
-extern "C" int myolo_bn_epi_finalize(double* sums, const float* gamma, const float* var, float eps, float* dgamma,
-                                     float* dbeta, float* dbias, int C, myolo_stream stream) {
+extern "C" int myolo_bn_epi_finalize_s(double* sums, const float* gamma, const float* var, float eps, float* dgamma,
+                                       float* dbeta, float* dbias, int C, const float* unscale, myolo_stream stream) {
   MYOLO_CHECK_ARG(sums && gamma && var && dgamma && dbeta && C > 0);
-  myolo::bn_epi_finalize_kernel<<<(C + 127) / 128, 128, 0, myolo::as_stream(stream)>>>(sums, gamma, var, eps, dgamma, dbeta, dbias, C);
+  myolo::bn_epi_finalize_kernel<<<(C + 127) / 128, 128, 0, myolo::as_stream(stream)>>>(sums, gamma, var, eps, dgamma, dbeta, dbias, C, unscale);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
+}
+extern "C" int myolo_bn_epi_finalize(double* sums, const float* gamma, const float* var, float eps, float* dgamma,
+                                     float* dbeta, float* dbias, int C, myolo_stream stream) {
+  return myolo_bn_epi_finalize_s(sums, gamma, var, eps, dgamma, dbeta, dbias, C, nullptr, stream);
 }

@@ -34,12 +34,13 @@ constexpr int WHALO = 16;
 constexpr uint32_t kWStageOut = 2 * 4 * 4096;   // per-epilogue-warp 32x32 fp32 staging buffers: TMA-store tile + BN-backward side tile
 constexpr uint32_t kWColAcc = 2 * 256 * 4;       // per-CTA column-sum accumulators of the fused BN backward
 constexpr uint32_t kWEpiVec = 2 * 1024 * 4;     // folded epilogue scale / shift, up to 1024 output channels
+constexpr uint32_t kWStageHalf = 4 * 2048;      // per-epilogue-warp 32x32 half staging tile (64B-swizzled TMA-store box)
 // NACC = 128-row accumulators per work item.  Window = 128*NACC + 32 rows; weight ring 128 KB (NACC 1) / 96 KB (NACC 2)
 __host__ __device__ constexpr int win_rows(int nacc) { return 128 * nacc + 2 * WHALO; }
 __host__ __device__ constexpr int win_box(int nacc) { return nacc == 1 ? win_rows(1) : win_rows(2) / 2; }
 __host__ __device__ constexpr uint32_t win_ring(int nacc) { return nacc == 1 ? 131072u : 98304u; }
 __host__ __device__ constexpr uint32_t win_smem(int nacc) {
-  return 2u * win_rows(nacc) * 128u + win_ring(nacc) + kWStageOut + kWColAcc + kWEpiVec + 1024u;
+  return 2u * win_rows(nacc) * 128u + win_ring(nacc) + kWStageOut + kWColAcc + kWEpiVec + kWStageHalf + 1024u;
 }
 
 // Work item = (256-row tile, WBN-column slice).  Two 128-row accumulators share every weight stage.
@@ -67,11 +68,15 @@ struct MaskTail {
 // CTA holds 128 of them (its own activation window and TMEM accumulator) and HALF of every weight stage,
 // which halves the L2->SM fill per FLOP -- the limiter of the single-CTA variant (measured: 1.27 ms with
 // the loads removed vs 1.60 ms with them; per-SM fill rate 66 B/clk needed vs ~64 B/clk available).
-template <int WBN, int NACC, int CG>
+// EL = bytes per operand element: 4 = fp32 words read as tf32 (kind::tf32), 2 = IEEE half (kind::f16, twice the
+// tensor rate and half the operand bytes; a k-block is still 128 bytes = 64 channels, so the window / ring /
+// descriptor geometry is identical).  With EL = 2 the epilogue can store the result as half (tmCh, 64B-swizzled
+// 32x32 tiles) next to or instead of the fp32 tile, and the fused BN backward reads its activation as half.
+template <int WBN, int NACC, int CG, int EL = 4>
 __global__ void __launch_bounds__(kThreads)
 tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   const __grid_constant__ CUtensorMap tmC, long long M, int N, int K, int ntaps, TapShifts sh, Epi ep,
-                   MaskTail mt, int nitems, int dbg) {
+                   const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmCh, long long M, int N,
+                   int K, int ntaps, TapShifts sh, Epi ep, MaskTail mt, int nitems, int dbg) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int WBM = 128 * NACC, WROWS = win_rows(NACC), WBOX = win_box(NACC);
   constexpr uint32_t kWinBytes = WROWS * 128;
@@ -88,8 +93,10 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const uint32_t awin0 = base, bst0 = base + 2 * kWinBytes, stg0 = bst0 + kWBStages * kWBBytes;
   float* colacc = reinterpret_cast<float*>(smem_raw + (stg0 + kWStageOut - smem_u32(smem_raw)));          // [2][256]
   float* evec = reinterpret_cast<float*>(smem_raw + (stg0 + kWStageOut + kWColAcc - smem_u32(smem_raw)));  // [scale N | shift N]
+  const uint32_t stgh0 = stg0 + kWStageOut + kWColAcc + kWEpiVec;   // half staging tiles (1024-byte aligned)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kblocks = K / BK;
+  constexpr int KEL = 128 / EL;                             // channels per 128-byte k-block
+  const int kblocks = K / KEL;
   const int nh = N / WBN;
   const uint32_t bar0 = smem_u32(bars);
   auto a_full = [&](int i) { return bar0 + 8u * i; };
@@ -103,6 +110,7 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmC);
+    if (EL == 2) tma_prefetch_desc(&tmCh);
     for (int i = 0; i < 2; ++i) {
       mbar_init(a_full(i), 1);
       mbar_init(a_empty(i), 1);
@@ -116,6 +124,7 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // epilogue constants, folded:  act((acc + bias) * scale + shift) = act(acc * S + T)
+  const float accs = ep.acc_scale ? __ldg(ep.acc_scale) : 1.f;
   if (mt.masks) {   // mask tail: evec = [bd 256 | w1 transposed NC x 256]
     for (int i = threadIdx.x; i < 256; i += blockDim.x) evec[i] = __ldg(mt.bd + i);
     for (int i = threadIdx.x; i < 256 * mt.NC; i += blockDim.x) evec[256 + (i % mt.NC) * 256 + i / mt.NC] = __ldg(mt.w1 + i);
@@ -131,7 +140,7 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
       const float sc = ep.scale ? __ldg(ep.scale + n) : 1.f;
       const float b = ep.bias ? __ldg(ep.bias + n) : 0.f;
-      evec[n] = sc;
+      evec[n] = sc * accs;
       evec[N + n] = ep.scale ? fmaf(b, sc, __ldg(ep.shift + n)) : b;
     }
   }
@@ -158,13 +167,13 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           if (CG == 2) {
             // both CTAs' loads complete on the LEADER's barrier, which expects the bytes of the pair
             if (leader) mbar_expect_tx(a_full(ab), 2 * kWinBytes);
-            tma_load_2d_2sm(wa, &tmA, mapa_rank(a_full(ab), 0), kb * BK, row0);
+            tma_load_2d_2sm(wa, &tmA, mapa_rank(a_full(ab), 0), kb * KEL, row0);
           } else if (dbg & 2) {
             mbar_arrive(a_full(ab));
           } else {
             mbar_expect_tx(a_full(ab), kWinBytes);
-            tma_load_2d(wa, &tmA, a_full(ab), kb * BK, row0);
-            if (NACC == 2) tma_load_2d(wa + WBOX * 128, &tmA, a_full(ab), kb * BK, row0 + WBOX);
+            tma_load_2d(wa, &tmA, a_full(ab), kb * KEL, row0);
+            if (NACC == 2) tma_load_2d(wa + WBOX * 128, &tmA, a_full(ab), kb * KEL, row0 + WBOX);
           }
           ++a_it;
           for (int t = 0; t < ntaps; ++t, ++b_it) {
@@ -172,13 +181,13 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             mbar_wait(b_empty(s), ((b_it / kWBStages) & 1u) ^ 1u);
             if (CG == 2) {
               if (leader) mbar_expect_tx(b_full(s), 2 * kWBBytes);
-              tma_load_2d_2sm(bst0 + s * kWBBytes, &tmB, mapa_rank(b_full(s), 0), kb * BK,
+              tma_load_2d_2sm(bst0 + s * kWBBytes, &tmB, mapa_rank(b_full(s), 0), kb * KEL,
                               t * N + half * WBN + (int)rank * (WBN / 2));
             } else if (dbg & 2) {
               mbar_arrive(b_full(s));
             } else {
               mbar_expect_tx(b_full(s), kWBBytes);
-              tma_load_2d(bst0 + s * kWBBytes, &tmB, b_full(s), kb * BK, t * N + half * WBN);
+              tma_load_2d(bst0 + s * kWBBytes, &tmB, b_full(s), kb * KEL, t * N + half * WBN);
             }
           }
         }
@@ -186,7 +195,7 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
   } else if (warp == 1) {
     if (lane == 0 && leader) {
-      constexpr uint32_t idesc = make_idesc(128 * CG, WBN, 0, 0);
+      constexpr uint32_t idesc = EL == 2 ? make_idesc_f16(128 * CG, WBN, 0, 0) : make_idesc(128 * CG, WBN, 0, 0);
       uint32_t a_it = 0, b_it = 0, it = 0;
       for (int item = cid; item < nitems; item += ncl, ++it) {
         const uint32_t ts = it % TS;
@@ -210,13 +219,16 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               // absolute smem address, so no base_offset is needed (verified on B200)
               const uint64_t da = make_desc(wa + (row + 128u * acc) * 128u, 16, 1024);
 #pragma unroll
-              for (int k = 0; k < BK / 8; ++k) {
-                if (CG == 2)
-                  umma_tf32_2sm(tacc + (uint32_t)WBN * acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
-                                (kb | t | k) != 0 ? 1u : 0u);
-                else
-                  umma_tf32(tacc + (uint32_t)WBN * acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
-                            (kb | t | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < 4; ++k) {   // one MMA per 32 bytes of K: 8 tf32 or 16 half
+                const uint32_t accf = (kb | t | k) != 0 ? 1u : 0u;
+                const uint32_t td = tacc + (uint32_t)WBN * acc;
+                if (EL == 2) {
+                  if (CG == 2) umma_f16_2sm(td, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, accf);
+                  else umma_f16(td, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, accf);
+                } else {
+                  if (CG == 2) umma_tf32_2sm(td, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, accf);
+                  else umma_tf32(td, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, accf);
+                }
               }
             }
             if (CG == 2) umma_commit_2sm(b_empty(s)); else umma_commit(b_empty(s));
@@ -229,6 +241,8 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   } else {
     const int q = warp & 3;
     const uint32_t sbuf0 = stg0 + (uint32_t)q * 4096u;
+    const uint32_t sbufh = stgh0 + (uint32_t)q * 2048u;
+    const bool st_f32 = !(EL == 2 && ep.no_f32), st_h = EL == 2 && ep.has_h;
     const uint32_t evs = smem_u32(evec);
     const int actk = ep.act & 0xff;
     const bool rnd = (ep.act & MYOLO_ROUND_TF32) != 0;
@@ -332,10 +346,20 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             // ---- fused BN(+ReLU) backward.  v = d(a) for this thread's row; a is read in place.
             const uint32_t sbuf2 = sbuf + 4u * 4096u;
             const float4* arow = reinterpret_cast<const float4*>(ep.bn_a + (size_t)m * N + n0);
+            const uint4* arow_h = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(ep.bn_a_h) + (size_t)m * N + n0);
+            uint4 ah[4];
+            if (EL == 2) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) ah[j] = valid ? __ldg(arow_h + j) : make_uint4(0u, 0u, 0u, 0u);
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               float4 av = make_float4(0.f, 0.f, 0.f, 0.f), be, ig;
-              if (valid) av = __ldg(arow + j);
+              if (EL == 2) {
+                const uint32_t w0 = (j & 1) ? ah[j >> 1].z : ah[j >> 1].x, w1 = (j & 1) ? ah[j >> 1].w : ah[j >> 1].y;
+                av = make_float4(h2f((uint16_t)(w0 & 0xffffu)), h2f((uint16_t)(w0 >> 16)), h2f((uint16_t)(w1 & 0xffffu)),
+                                 h2f((uint16_t)(w1 >> 16)));
+              } else if (valid) av = __ldg(arow + j);
               asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(be.x), "=f"(be.y), "=f"(be.z), "=f"(be.w) : "r"(evs + 4u * (N + n0 + 4 * j)));
               asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(ig.x), "=f"(ig.y), "=f"(ig.z), "=f"(ig.w) : "r"(evs + 4u * (2 * N + n0 + 4 * j)));
               const float aa[4] = {av.x, av.y, av.z, av.w}, bb[4] = {be.x, be.y, be.z, be.w}, gg[4] = {ig.x, ig.y, ig.z, ig.w};
@@ -367,6 +391,13 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 s1 += tv;
                 float o = gv * scl;
                 if (rnd) o = round_tf32(o);
+                if (st_h) {
+                  const uint16_t hv = f2h_sat(o);
+                  o = h2f(hv);
+                  const uint32_t hoff = (uint32_t)r * 64u + (uint32_t)((((uint32_t)lane >> 3) ^ (((uint32_t)r >> 1) & 3u)) << 4) +
+                                        ((uint32_t)lane & 7u) * 2u;
+                  asm volatile("st.shared.b16 [%0], %1;" ::"r"(sbufh + hoff), "h"(hv));
+                }
                 asm volatile("st.shared.f32 [%0], %1;" ::"r"(sbuf + off), "f"(o));
               }
               atomicAdd(colacc + n0 + lane, s0);
@@ -387,12 +418,29 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               if (rnd) o[e] = round_tf32(o[e]);
               if (!valid) o[e] = 0.f;   // padded-flat pad rows stay zero
             }
-            const uint32_t addr = sbuf + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]));
+            if (st_h) {   // the half copy; v[] keeps the packed words until the 16-byte chunk is complete
+              const uint32_t p0 = pack_h2(o[0], o[1]), p1 = pack_h2(o[2], o[3]);
+              o[0] = h2f((uint16_t)(p0 & 0xffffu)); o[1] = h2f((uint16_t)(p0 >> 16));
+              o[2] = h2f((uint16_t)(p1 & 0xffffu)); o[3] = h2f((uint16_t)(p1 >> 16));
+              v[4 * j] = __uint_as_float(p0);
+              v[4 * j + 1] = __uint_as_float(p1);
+              if (j & 1) {
+                const uint32_t haddr = sbufh + (uint32_t)lane * 64u + (uint32_t)((((uint32_t)j >> 1) ^ (((uint32_t)lane >> 1) & 3u)) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(haddr), "r"(__float_as_uint(v[4 * j - 4])),
+                             "r"(__float_as_uint(v[4 * j - 3])), "r"(p0), "r"(p1));
+              }
+            }
+            if (st_f32) {
+              const uint32_t addr = sbuf + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]));
+            }
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
-          if (lane == 0 && mrow0 < M && !(dbg & 4)) tma_store_2d(&tmC, sbuf, n0, mrow0);
+          if (lane == 0 && mrow0 < M && !(dbg & 4)) {
+            if (st_f32) tma_store_2d(&tmC, sbuf, n0, mrow0);
+            if (st_h) tma_store_2d(&tmCh, sbufh, n0, mrow0);
+          }
         }
       }
       tc_fence_before();
@@ -447,12 +495,28 @@ struct BnBwd {   // host-side bundle of the fused BN-backward epilogue arguments
   float eps;
 };
 
+// half-operand launch options: A / Bt (and bnb.a) are IEEE half; Ch = half output [M][N] pitch ldch (nullable);
+// no_f32 skips the fp32 output C; acc_scale = device scalar folded into the accumulator
+struct HalfIO {
+  int on;
+  void* Ch;
+  long long ldch;
+  int no_f32;
+  const float* acc_scale;
+};
+
 static int launch_win(const float* A, long long lda, const float* Bt, float* C, long long ldc, long long M, int N, int K,
                       int ntaps, const int* shifts_host, const float* bias, const float* scale, const float* shift_c,
                       int act, int pf_w1, int pf_blk, int accumulate, const MaskTail& mt, myolo_stream stream,
-                      const BnBwd& bnb = BnBwd{}) {
-  MYOLO_CHECK_ARG(A && Bt && C && ((((uintptr_t)A | (uintptr_t)Bt | (uintptr_t)C) & 15) == 0));
+                      const BnBwd& bnb = BnBwd{}, const HalfIO& hio = HalfIO{}) {
+  MYOLO_CHECK_ARG(A && Bt && ((((uintptr_t)A | (uintptr_t)Bt | (uintptr_t)C) & 15) == 0));
+  MYOLO_CHECK_ARG(C || (hio.on && hio.no_f32));
   MYOLO_CHECK_ARG(myolo_gemm_taps_win_supported(lda, ldc, M, N, K, ntaps, shifts_host, accumulate));
+  if (hio.on) {
+    MYOLO_CHECK_ARG((K % 64) == 0 && (lda % 8) == 0 && (N % 256) == 0 && !(act & MYOLO_ROUND_TF32));
+    MYOLO_CHECK_ARG(!hio.Ch || ((hio.ldch % 8) == 0 && ((uintptr_t)hio.Ch & 15) == 0));
+    MYOLO_CHECK_ARG(hio.Ch || !hio.no_f32 || mt.masks);
+  }
   MYOLO_CHECK_ARG((scale == nullptr) == (shift_c == nullptr));
   MYOLO_CHECK_ARG(!(accumulate && (scale || (act & 0xff) != MYOLO_ACT_NONE)));
   MYOLO_CHECK_ARG(pf_w1 <= 0 || pf_blk > 0);
@@ -474,13 +538,35 @@ static int launch_win(const float* A, long long lda, const float* Bt, float* C, 
   const int nacc = (bo_mode & 16) ? 2 : 1;
   // CTA-pair variant (cta_group::2): 256-column slices, one accumulator per CTA; MYOLO_WIN_BO & 32 disables it
   const int cg = (wbn == 256 && nacc == 1 && !(bo_mode & 32) && !(bo_mode & 2)) ? 2 : 1;
-  int rc = get_map(A, M + maxs, K, lda, win_box(nacc), &ta);
-  if (rc) return rc;
-  rc = get_map(Bt, (long long)ntaps * N, K, K, wbn / cg, &tb);
-  if (rc) return rc;
-  CUtensorMap tc_;
-  rc = get_map(C, M, N, ldc, 32, &tc_);
-  if (rc) return rc;
+  int rc;
+  CUtensorMap tc_, tch;
+  if (hio.on) {
+    MYOLO_CHECK_ARG(wbn == 256 && cg == 2);
+    rc = get_map_h(A, M + maxs, K, lda, win_box(nacc), 64, &ta);
+    if (rc) return rc;
+    rc = get_map_h(Bt, (long long)ntaps * N, K, K, wbn / cg, 64, &tb);
+    if (rc) return rc;
+    if (!hio.no_f32) {
+      rc = get_map(C, M, N, ldc, 32, &tc_);
+      if (rc) return rc;
+    } else {
+      tc_ = ta;   // never dereferenced
+    }
+    if (hio.Ch) {
+      rc = get_map_h(hio.Ch, M, N, hio.ldch, 32, 32, &tch);
+      if (rc) return rc;
+    } else {
+      tch = ta;
+    }
+  } else {
+    rc = get_map(A, M + maxs, K, lda, win_box(nacc), &ta);
+    if (rc) return rc;
+    rc = get_map(Bt, (long long)ntaps * N, K, K, wbn / cg, &tb);
+    if (rc) return rc;
+    rc = get_map(C, M, N, ldc, 32, &tc_);
+    if (rc) return rc;
+    tch = tc_;
+  }
   static bool attr_set = false;
   static int max_clusters = 0;
   if (!attr_set) {
@@ -489,6 +575,7 @@ static int launch_win(const float* A, long long lda, const float* Bt, float* C, 
     MYOLO_CUDA(cudaFuncSetAttribute(tc_conv_win_kernel<128, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem(2)));
     MYOLO_CUDA(cudaFuncSetAttribute(tc_conv_win_kernel<256, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem(2)));
     MYOLO_CUDA(cudaFuncSetAttribute(tc_conv_win_kernel<256, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem(1)));
+    MYOLO_CUDA(cudaFuncSetAttribute(tc_conv_win_kernel<256, 1, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem(1)));
     {   // how many CTA pairs fit at once (GPCs with an odd SM count leave SMs unpaired)
       cudaLaunchConfig_t q = {};
       q.gridDim = dim3(kNumSMs);
@@ -504,7 +591,8 @@ static int launch_win(const float* A, long long lda, const float* Bt, float* C, 
     }
     attr_set = true;
   }
-  Epi ep{bias, scale, shift_c, act, pf_w1, pf_blk, accumulate, bnb.a, bnb.gamma, bnb.beta, bnb.var, bnb.ws, bnb.eps};
+  Epi ep{bias, scale, shift_c, act, pf_w1, pf_blk, accumulate, bnb.a, bnb.gamma, bnb.beta, bnb.var, bnb.ws, bnb.eps,
+         hio.on ? (const void*)bnb.a : nullptr, hio.on ? hio.no_f32 : 0, (hio.on && hio.Ch) ? 1 : 0, hio.acc_scale};
   cudaStream_t st = as_stream(stream);
   if (cg == 2 && max_clusters > 0) {
     const int nitems = (int)ceil_div(M, 256) * (N / wbn);
@@ -519,8 +607,15 @@ static int launch_win(const float* A, long long lda, const float* Bt, float* C, 
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    MYOLO_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_win_kernel<256, 1, 2>, ta, tb, tc_, M, N, K, ntaps, sh, ep, mt, nitems, bo_mode));
+    if (hio.on)
+      MYOLO_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_win_kernel<256, 1, 2, 2>, ta, tb, tc_, tch, M, N, K, ntaps, sh, ep, mt, nitems, bo_mode));
+    else
+      MYOLO_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_win_kernel<256, 1, 2>, ta, tb, tc_, tch, M, N, K, ntaps, sh, ep, mt, nitems, bo_mode));
     return MYOLO_OK;
+  }
+  if (hio.on) {
+    set_error("half-operand conv kernel needs CTA pairs (cudaOccupancyMaxActiveClusters returned 0)");
+    return MYOLO_ERR_CUDA;
   }
   if (cg == 2) {   // no pair fits (should not happen on B200): rebuild the weight map for the single-CTA box
     rc = get_map(Bt, (long long)ntaps * N, K, K, wbn, &tb);
@@ -529,7 +624,7 @@ static int launch_win(const float* A, long long lda, const float* Bt, float* C, 
   const int nitems = (int)ceil_div(M, 128 * nacc) * (N / wbn);
   const int grid = nitems < kNumSMs ? nitems : kNumSMs;
 #define MYOLO_WIN_LAUNCH(BN_, NA_) \
-  tc_conv_win_kernel<BN_, NA_, 1><<<grid, kThreads, win_smem(NA_), st>>>(ta, tb, tc_, M, N, K, ntaps, sh, ep, mt, nitems, bo_mode)
+  tc_conv_win_kernel<BN_, NA_, 1><<<grid, kThreads, win_smem(NA_), st>>>(ta, tb, tc_, tch, M, N, K, ntaps, sh, ep, mt, nitems, bo_mode)
   if (wbn == 256 && nacc == 1) MYOLO_WIN_LAUNCH(256, 1);
   else if (wbn == 256) MYOLO_WIN_LAUNCH(256, 2);
   else if (nacc == 1) MYOLO_WIN_LAUNCH(128, 1);
@@ -581,4 +676,55 @@ extern "C" int myolo_gemm_taps_bnbwd(const float* A, long long lda, const float*
                       stream, bnb);
   if (rc) return rc;
   return myolo_bn_epi_finalize(ws + 16, gamma, var, eps, dgamma, dbeta, dbias, N, stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// half-operand (kind::f16) entry points: same kernel, IEEE-half A / Bt, fp32 accumulation in TMEM
+// ------------------------------------------------------------------------------------------
+extern "C" int myolo_gemm_taps_h_supported(long long lda, long long M, int N, int K, int ntaps, const int* shifts_host) {
+  return (N % 256) == 0 && (K % 64) == 0 && (lda % 8) == 0 && myolo_gemm_taps_win_supported(lda, N, M, N, K, ntaps, shifts_host, 0);
+}
+
+extern "C" int myolo_gemm_taps_h(const void* A, long long lda, const void* Bt, float* C, long long ldc, void* Ch,
+                                 long long ldch, long long M, int N, int K, int ntaps, const int* shifts_host,
+                                 const float* bias, const float* scale, const float* shift_c, int act, int pf_w1, int pf_blk,
+                                 const float* acc_scale, myolo_stream stream) {
+  MYOLO_CHECK_ARG(C || Ch);
+  MYOLO_CHECK_ARG(myolo_gemm_taps_h_supported(lda, M, N, K, ntaps, shifts_host));
+  MaskTail mt{};
+  HalfIO hio{1, Ch, ldch, C ? 0 : 1, acc_scale};
+  return launch_win(reinterpret_cast<const float*>(A), lda, reinterpret_cast<const float*>(Bt), C, C ? ldc : N, M, N, K, ntaps,
+                    shifts_host, bias, scale, shift_c, act, pf_w1, pf_blk, 0, mt, stream, BnBwd{}, hio);
+}
+
+extern "C" int myolo_deconv_mask_fwd_h(const void* a4, const void* kd, const float* bd, const float* w1, const float* b1,
+                                       float* masks, const int* target_ids, float* y4, int n_roi, int H, int W, int Cmid,
+                                       int NC, myolo_stream stream) {
+  MYOLO_CHECK_ARG(a4 && kd && bd && w1 && b1 && masks && y4 && n_roi > 0 && H > 0 && W > 0);
+  MYOLO_CHECK_ARG(myolo_deconv_mask_fwd_supported(Cmid, NC));
+  MaskTail mt{bd, w1, b1, masks, target_ids, y4, H, W, NC};
+  const long long M = (long long)n_roi * (H + 1) * (W + 1);
+  HalfIO hio{1, nullptr, 0, 1, nullptr};
+  return launch_win(reinterpret_cast<const float*>(a4), Cmid, reinterpret_cast<const float*>(kd), y4, 4 * Cmid, M, 4 * Cmid,
+                    Cmid, 1, nullptr, nullptr, nullptr, nullptr, MYOLO_ACT_NONE, W + 1, (H + 1) * (W + 1), 0, mt, stream,
+                    BnBwd{}, hio);
+}
+
+extern "C" int myolo_bn_epi_finalize_s(double* sums, const float* gamma, const float* var, float eps, float* dgamma,
+                                       float* dbeta, float* dbias, int C, const float* unscale, myolo_stream stream);
+
+extern "C" int myolo_gemm_taps_bnbwd_h(const void* A, long long lda, const void* Bt, float* C, void* Ch, long long ldc,
+                                       long long M, int N, int K, int ntaps, const int* shifts_host, int pf_w1, int pf_blk,
+                                       const void* a_out, const float* gamma, const float* beta, const float* var, float eps,
+                                       int act, float* dgamma, float* dbeta, float* dbias, double* ws,
+                                       const float* grad_unscale, myolo_stream stream) {
+  MYOLO_CHECK_ARG(a_out && gamma && beta && var && dgamma && dbeta && ws && (C || Ch));
+  MYOLO_CHECK_ARG(N == 256 && ldc == N && myolo_gemm_taps_h_supported(lda, M, N, K, ntaps, shifts_host));
+  MaskTail mt{};
+  BnBwd bnb{reinterpret_cast<const float*>(a_out), gamma, beta, var, ws + 16, eps};
+  HalfIO hio{1, Ch, ldc, C ? 0 : 1, nullptr};
+  int rc = launch_win(reinterpret_cast<const float*>(A), lda, reinterpret_cast<const float*>(Bt), C, ldc, M, N, K, ntaps,
+                      shifts_host, nullptr, nullptr, nullptr, act, pf_w1, pf_blk, 0, mt, stream, bnb, hio);
+  if (rc) return rc;
+  return myolo_bn_epi_finalize_s(ws + 16, gamma, var, eps, dgamma, dbeta, dbias, N, grad_unscale, stream);
 }

@@ -382,6 +382,50 @@ int get_map(const float* p, long long rows, int cols, long long pitch, int box_r
   return MYOLO_OK;
 }
 
+// IEEE-half flavour (operands and outputs of the kind::f16 kernels).
+int get_map_h(const void* p, long long rows, int cols, long long pitch, int box_rows, int box_cols, CUtensorMap* out) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key{p, rows, pitch, cols, box_rows, 1000 + box_cols};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return MYOLO_OK;
+    }
+  }
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return MYOLO_ERR_CUDA;
+  }
+  if ((box_cols != 64 && box_cols != 32) || (pitch % 8) != 0 || ((uintptr_t)p & 15) != 0) {
+    set_error("get_map_h: unsupported half map (box_cols %d, pitch %lld)", box_cols, pitch);
+    return MYOLO_ERR_ARG;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)pitch * 2u};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(p), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (half) failed (%d) for [%lld x %d] pitch %lld box %d x %d", (int)r, rows, cols, pitch,
+              box_rows, box_cols);
+    return MYOLO_ERR_CUDA;
+  }
+  {
+    std::lock_guard<std::mutex> g(mu);
+    if (cache.size() > 4096) cache.clear();
+    cache[key] = m;
+  }
+  *out = m;
+  return MYOLO_OK;
+}
+
 static int pick_bn(int N) {
   if (N % 256 == 0) return 256;
   if (N % 128 == 0) return 128;
@@ -514,6 +558,44 @@ extern "C" int myolo_gemm_taps_wgrad_tc(const float* A, long long lda, const flo
     case 64: return launch_wgrad<64>(ta, td, dW, M, N, K, ntaps, sh, transpose_out, st);
     default: return launch_wgrad<32>(ta, td, dW, M, N, K, ntaps, sh, transpose_out, st);
   }
+}
+
+namespace myolo {
+namespace tc {
+// half staging of a weight block: out[t][c][r] = half(in[t][r][c]) (transpose) or out = half(in)
+__global__ void prep_weights_h_kernel(const float* __restrict__ in, uint16_t* __restrict__ out, int rows, int cols,
+                                      int transpose) {
+  __shared__ float t[32][33];
+  const float* ip = in + (size_t)blockIdx.z * rows * cols;
+  uint16_t* op = out + (size_t)blockIdx.z * rows * cols;
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int r = blockIdx.y * 32 + j;
+    const float v = (r < rows && c < cols) ? ip[(size_t)r * cols + c] : 0.f;
+    if (!transpose) {
+      if (r < rows && c < cols) op[(size_t)r * cols + c] = f2h_sat(v);
+    } else {
+      t[j][threadIdx.x] = v;
+    }
+  }
+  if (!transpose) return;
+  __syncthreads();
+  const int r2 = blockIdx.y * 32 + threadIdx.x;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int c2 = blockIdx.x * 32 + j;
+    if (r2 < rows && c2 < cols) op[(size_t)c2 * rows + r2] = f2h_sat(t[threadIdx.x][j]);
+  }
+}
+}  // namespace tc
+}  // namespace myolo
+
+extern "C" int myolo_prep_weights_h(const float* in, void* out_half, int ntaps, int rows, int cols, int transpose,
+                                    myolo_stream stream) {
+  MYOLO_CHECK_ARG(in && out_half && (const void*)in != out_half && ntaps > 0 && rows > 0 && cols > 0);
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32, ntaps), block(32, 8);
+  prep_weights_h_kernel<<<grid, block, 0, as_stream(stream)>>>(in, reinterpret_cast<uint16_t*>(out_half), rows, cols, transpose);
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
 }
 
 extern "C" int myolo_prep_weights(const float* in, float* out, int ntaps, int rows, int cols, int transpose,

@@ -19,8 +19,18 @@ struct V {
 };
 static inline V to_v(const myolo_view* v) { return V{v->p, v->sn, v->sh, v->n, v->h, v->w, v->c}; }
 
+__device__ __forceinline__ uint32_t pack_half2_sat(float lo, float hi) {
+  uint16_t a, b;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(a) : "f"(lo));
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(b) : "f"(hi));
+  return (uint32_t)a | ((uint32_t)b << 16);
+}
+
+// HALF: the pooled values are (also) stored as IEEE half into `outh` (operand of the kind::f16 mask conv1);
+// out.p may then be null.
+template <bool HALF>
 __global__ void __launch_bounds__(256)
-roialign_fwd_kernel(V feat, const float* __restrict__ boxes, int n_roi, int rois_per_img, int pool, V out, int rnd) {
+roialign_fwd_kernel(V feat, const float* __restrict__ boxes, int n_roi, int rois_per_img, int pool, V out, int rnd, V outh) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -32,12 +42,17 @@ roialign_fwd_kernel(V feat, const float* __restrict__ boxes, int n_roi, int rois
     const int b = r / rois_per_img;
     const Sample sy = crop_coord(bx.x, bx.z, y, pool, feat.h);
     const float* fb = feat.p + (size_t)b * feat.sn;
-    float* orow = out.p + (size_t)r * out.sn + (size_t)y * out.sh;
+    float* orow = out.p ? out.p + (size_t)r * out.sn + (size_t)y * out.sh : nullptr;
+    uint16_t* hrow = HALF ? reinterpret_cast<uint16_t*>(outh.p) + (size_t)r * outh.sn + (size_t)y * outh.sh : nullptr;
     for (int x = 0; x < pool; ++x) {
       const Sample sx = crop_coord(bx.y, bx.w, x, pool, feat.w);
       float4* op = reinterpret_cast<float4*>(orow + (size_t)x * out.c);
+      uint2* hp = reinterpret_cast<uint2*>(hrow + (size_t)x * feat.c);
       if (!(sy.valid && sx.valid)) {
-        for (int q = lane; q < C4; q += 32) op[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = lane; q < C4; q += 32) {
+          if (orow) op[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (HALF) hp[q] = make_uint2(0u, 0u);
+        }
         continue;
       }
       const float4* tl = reinterpret_cast<const float4*>(fb + (size_t)sy.lo * feat.sh + (size_t)sx.lo * feat.c);
@@ -52,7 +67,8 @@ roialign_fwd_kernel(V feat, const float* __restrict__ boxes, int n_roi, int rois
         o.z = lerp_rn(lerp_rn(a.z, bq.z, sx.lerp), lerp_rn(c.z, d.z, sx.lerp), sy.lerp);
         o.w = lerp_rn(lerp_rn(a.w, bq.w, sx.lerp), lerp_rn(c.w, d.w, sx.lerp), sy.lerp);
         if (rnd) o = make_float4(round_tf32(o.x), round_tf32(o.y), round_tf32(o.z), round_tf32(o.w));
-        op[q] = o;
+        if (orow) op[q] = o;
+        if (HALF) hp[q] = make_uint2(pack_half2_sat(o.x, o.y), pack_half2_sat(o.z, o.w));
       }
     }
   }
@@ -114,7 +130,21 @@ extern "C" int myolo_roialign_fwd(const myolo_view* feat, const float* boxes, in
   MYOLO_CHECK_ARG((n_roi + rois_per_img - 1) / rois_per_img <= feat->n);
   const long long items = (long long)n_roi * pool;
   const int blocks = (int)max(1LL, min(ceil_div(items, 8), (long long)kNumSMs * 8));
-  roialign_fwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(to_v(feat), boxes, n_roi, rois_per_img, pool, to_v(out), round_tf32);
+  roialign_fwd_kernel<false><<<blocks, 256, 0, as_stream(stream)>>>(to_v(feat), boxes, n_roi, rois_per_img, pool, to_v(out), round_tf32, to_v(out));
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
+}
+
+extern "C" int myolo_roialign_fwd_h(const myolo_view* feat, const float* boxes, int n_roi, int rois_per_img, int pool,
+                                    const myolo_view* out, const myolo_view* out_half, myolo_stream stream) {
+  MYOLO_CHECK_ARG(view_ok(feat) && view_ok(out_half) && (!out || view_ok(out)) && boxes && n_roi > 0 && rois_per_img > 0 && pool > 0);
+  MYOLO_CHECK_ARG(out_half->n == n_roi && out_half->h == pool && out_half->w == pool && out_half->c == feat->c);
+  MYOLO_CHECK_ARG(!out || (out->n == n_roi && out->h == pool && out->w == pool && out->c == feat->c));
+  MYOLO_CHECK_ARG((n_roi + rois_per_img - 1) / rois_per_img <= feat->n && ((uintptr_t)out_half->p & 7) == 0);
+  const long long items = (long long)n_roi * pool;
+  const int blocks = (int)max(1LL, min(ceil_div(items, 8), (long long)kNumSMs * 8));
+  V vo = out ? to_v(out) : V{nullptr, 0, 0, n_roi, pool, pool, feat->c};
+  roialign_fwd_kernel<true><<<blocks, 256, 0, as_stream(stream)>>>(to_v(feat), boxes, n_roi, rois_per_img, pool, vo, 0, to_v(out_half));
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }

@@ -109,6 +109,20 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// kind::f16 instruction descriptor: IEEE half operands (a_format = b_format = 0), fp32 accumulate.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
 __device__ __forceinline__ bool pf_valid(long long m, int pf_w1, int pf_blk) {
   if (pf_w1 <= 0) return true;
   const int r = (int)(m % pf_blk);
@@ -128,6 +142,12 @@ struct Epi {
   const float* bn_var;
   double* bn_ws;          // [2][N] fp64 sums (zero before, finalized + zeroed by myolo_gemm_taps_bnbwd)
   float bn_eps;
+  // half-operand (kind::f16) variants of the conv_win kernel
+  const void* bn_a_h;     // the same activation stored as IEEE half (replaces bn_a)
+  int no_f32;             // do not store the fp32 result C
+  int has_h;              // store the result as half through the second output map (the fp32 copy, when also
+                          // stored, is the half-rounded value so both consumers see the same numbers)
+  const float* acc_scale; // device scalar multiplied into the accumulator before the epilogue (nullable)
 };
 
 
@@ -182,6 +202,29 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
       : "memory");
 }
 
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
+// fp32 -> IEEE half, round to nearest even, saturating to +-65504 (a gradient or activation that leaves the
+// half range clamps instead of turning the whole tensor into inf/nan)
+__device__ __forceinline__ uint16_t f2h_sat(float x) {
+  uint16_t r;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float h2f(uint16_t h) {
+  float r;
+  asm("cvt.f32.f16 %0, %1;" : "=f"(r) : "h"(h));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) { return (uint32_t)f2h_sat(lo) | ((uint32_t)f2h_sat(hi) << 16); }
+
 // ---- epilogue: 32x32 fp32 chunk (one TMEM lane quarter x 32 columns) -> global memory through a
 // per-warp 4 KB staging buffer and a TMA tensor store.  A thread owns one output ROW; writing rows
 // straight to global memory is a 1 KB-strided 16-byte scatter (measured: the stores cost as much as
@@ -219,6 +262,9 @@ __device__ __forceinline__ void epi_stage_row(const float* v, const Epi& ep, int
 // 2D fp32 tensor map [rows][cols], row pitch `pitch` elements, box = 32 columns x box_rows rows, 128B swizzle
 // (atom32: the 32-byte-chunk flavour for MN-major tf32 operands).  Cached per (pointer, shape).
 int get_map(const float* p, long long rows, int cols, long long pitch, int box_rows, CUtensorMap* out, int atom32 = 0);
+// 2D IEEE-half tensor map [rows][cols], row pitch `pitch` elements (multiple of 8).  box_cols = 64 -> 128B swizzle
+// (tcgen05 operand tiles); box_cols = 32 -> 64B swizzle (epilogue store tiles of 32 columns).
+int get_map_h(const void* p, long long rows, int cols, long long pitch, int box_rows, int box_cols, CUtensorMap* out);
 
 }  // namespace tc
 }  // namespace myolo

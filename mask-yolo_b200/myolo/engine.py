@@ -137,12 +137,16 @@ class Engine:
         tf32x3    : tcgen05 everywhere; the FORWARD GEMMs of backbone / yolo branch / feature_map run
                     as 3xTF32 (operands split hi+lo, A*B ~= Ah*Bh + Al*Bh + Ah*Bl: fp32-grade
                     outputs), mask head and every backward GEMM single-pass tf32;
-        tf32x3_all: as tf32x3, with the mask-head forward convolutions in 3xTF32 as well."""
-        assert precision in ("fp32", "tf32", "tf32x3", "tf32x3_all")
+        tf32x3_all: as tf32x3, with the mask-head forward convolutions in 3xTF32 as well;
+        h16       : as tf32x3, with the mask head (98.8 % of the FLOPs) on tcgen05 kind::f16: activations and
+                    staged weights stored as IEEE half (the same 10 explicit mantissa bits tf32 keeps, at
+                    twice the tensor rate and half the bytes), fp32 accumulation and fp32 epilogues."""
+        assert precision in ("fp32", "tf32", "tf32x3", "tf32x3_all", "h16")
         self.precision = precision
         self.tc = precision != "fp32"
-        self.x3 = precision in ("tf32x3", "tf32x3_all")
+        self.x3 = precision in ("tf32x3", "tf32x3_all", "h16")
         self.x3m = precision == "tf32x3_all"
+        self.h16 = precision == "h16"
         self.rnd = C.ROUND_TF32 if self.tc else 0
         C.set_precision(C.PREC_TF32 if self.tc else C.PREC_FP32)
 
@@ -188,6 +192,13 @@ class Engine:
         for name, (o, n, shape) in self.offs.items():
             if name.endswith("/kernel") and name != "conv1/kernel":
                 self.wt[name] = torch.zeros(n * (3 if self._is_x3(name) else 1), dtype=torch.float32, device=self.dev)
+        # "h16": IEEE-half staging of the mask-head weights.  fwd = per-tap transposed [t][Cout][Cin] (deconv: the
+        # Keras layout is already [4*Cout][Cin]).
+        self.wth = {}
+        if self.h16:
+            for name, (o, n, shape) in self.offs.items():
+                if name.startswith("myolo_mask_conv") and name.endswith("/kernel") or name == "myolo_mask_deconv/kernel":
+                    self.wth[name] = torch.zeros(n, dtype=torch.float16, device=self.dev)
         self.ws = torch.zeros(8192, dtype=torch.float64, device=self.dev)       # BN family: zero between calls
         self.ws_loss = torch.zeros(16, dtype=torch.float64, device=self.dev)
         self.anchors = torch.tensor(self.cfg["ANCHORS"], dtype=torch.float32, device=self.dev)
@@ -248,6 +259,12 @@ class Engine:
             else:
                 taps = shape[0] * shape[1]
                 C.call("myolo_prep_weights", self.p[name], buf, taps, shape[2], shape[3], 1, rnd, st)
+        for name, buf in self.wth.items():
+            shape = self.offs[name][2]
+            if name == "myolo_mask_deconv/kernel":
+                C.call("myolo_prep_weights_h", self.p[name], buf, 1, 4 * shape[2], shape[3], 0, st)
+            else:
+                C.call("myolo_prep_weights_h", self.p[name], buf, shape[0] * shape[1], shape[2], shape[3], 1, st)
 
     # ------------------------------------------------------------------ activations
     def _alloc_acts(self):
@@ -297,6 +314,8 @@ class Engine:
             self.bn_shift = torch.zeros(4, MASK_C, device=dev)
             self.ma = [self.x0] + [PF(n, P_, P_, MASK_C, device=dev, split=self.x3m and i < 4) for i in range(1, 5)]
             self.y4d = PF(n, P_, P_, 4 * MASK_C, device=dev)
+            if self.h16:     # half copies of the conv operands x0, a1..a4
+                self.mah = [PF(n, P_, P_, MASK_C, device=dev, dtype=torch.float16) for _ in range(5)]
             mh, mw = self.cfg["MASK_SHAPE"]
             assert (mh, mw) == (2 * P_, 2 * P_)
             A["masks"] = f(n, mh, mw, NC)
@@ -423,6 +442,8 @@ class Engine:
         A, st, n = self.A, self._st(), self.n_roi
         P_ = self.cfg["POOL"]
         npix = n * P_ * P_
+        if self.h16:
+            return self._mask_head_h16(rois, training)
         C.call("myolo_roialign_fwd", self.feat.view(), rois, n, self.R, P_, self.x0.view(),
                1 if (self.rnd and not self.x3m) else 0, st)
         if self.x3m:
@@ -459,6 +480,61 @@ class Engine:
         else:
             C.call("myolo_gemm_taps", a4.rows, MASK_C, self.p["myolo_mask_deconv/kernel"], self.y4d.rows, 4 * MASK_C, a4.M,
                    4 * MASK_C, MASK_C, 1, None, None, None, None, C.ACT_NONE, P_ + 1, (P_ + 1) * (P_ + 1), 0, st)
+            C.call("myolo_mask_out_fwd", self.y4d.rows, self.p["myolo_mask_deconv/bias"], self.p["myolo_mask/kernel"],
+                   self.p["myolo_mask/bias"], A["masks"], n, P_, P_, MASK_C, self.NC, st)
+        mh, mw = self.cfg["MASK_SHAPE"]
+        return A["masks"].view(self.B, self.R, mh, mw, self.NC)
+
+    def _mask_head_h16(self, rois: torch.Tensor, training: bool):
+        """mask_head on tcgen05 kind::f16: every conv reads IEEE-half activations / weights, accumulates in fp32 and
+        stores its result as half for the next conv and as fp32 (the same rounded values) for the backward pass."""
+        A, st, n = self.A, self._st(), self.n_roi
+        P_ = self.cfg["POOL"]
+        npix = n * P_ * P_
+        pfw, pfb = P_ + 1, (P_ + 1) * (P_ + 1)
+        C.call("myolo_roialign_fwd_h", self.feat.view(), rois, n, self.R, P_, self.x0.view(), self.mah[0].view(), st)
+        key = ("h16", P_)
+        sh3 = self._shift_cache.get(key)
+        if sh3 is None:
+            sh3 = self._shift_cache[key] = C.int_array(conv3x3_shifts(P_))
+        self._mask_fused = [False] * 5
+        M = self.x0.M
+        for i in (1, 2, 3, 4):
+            name = f"myolo_mask_conv{i}/kernel"
+            a_in = self.mah[i - 1]
+            timed = self.kernel_events is not None
+            if timed:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            if training and i == 1:
+                # batch-statistics BN: the pre-BN tensor is kept in fp32 (statistics, backward)
+                C.call("myolo_gemm_taps_h", a_in.rows, MASK_C, self.wth[name], self.my[1].rows, MASK_C, None, 0, M, MASK_C, MASK_C,
+                       9, sh3, self.p[f"myolo_mask_conv{i}/bias"], None, None, C.ACT_NONE, pfw, pfb, None, st)
+            else:
+                b = self.bn[f"myolo_mask_bn{i}"]
+                C.call("myolo_bn_fold", b.gamma, b.beta, b.mmean, b.mvar, BN_EPS, self.bn_scale[i - 1], self.bn_shift[i - 1],
+                       MASK_C, st)
+                C.call("myolo_gemm_taps_h", a_in.rows, MASK_C, self.wth[name], self.ma[i].rows, MASK_C, self.mah[i].rows, MASK_C,
+                       M, MASK_C, MASK_C, 9, sh3, self.p[f"myolo_mask_conv{i}/bias"], self.bn_scale[i - 1],
+                       self.bn_shift[i - 1], C.ACT_RELU, pfw, pfb, None, st)
+                self._mask_fused[i] = True
+            if timed:
+                e1.record()
+                self.kernel_events.append((e0, e1))
+            if training and i == 1:
+                b = self.bn["myolo_mask_bn1"]
+                C.call("myolo_bn_stats", self.my[1].view(), b.mean, b.var, self.ws, st)
+                self._bn_touched.append((b, npix))
+                C.call("myolo_bn_apply_h", self.my[1].view(), self.ma[1].view(), self.mah[1].view(), b.mean, b.var, b.gamma,
+                       b.beta, BN_EPS, C.ACT_RELU, st)
+        if C.lib().myolo_deconv_mask_fwd_supported(MASK_C, self.NC):
+            ids = self.target_ids if self.mode == "training" else None
+            C.call("myolo_deconv_mask_fwd_h", self.mah[4].rows, self.wth["myolo_mask_deconv/kernel"], self.p["myolo_mask_deconv/bias"],
+                   self.p["myolo_mask/kernel"], self.p["myolo_mask/bias"], A["masks"], ids, self.y4d.rows, n, P_, P_,
+                   MASK_C, self.NC, st)
+        else:       # many classes (NC > 7): deconv GEMM to y4, then the mask tail as its own kernel
+            C.call("myolo_gemm_taps_h", self.mah[4].rows, MASK_C, self.wth["myolo_mask_deconv/kernel"], self.y4d.rows, 4 * MASK_C,
+                   None, 0, M, 4 * MASK_C, MASK_C, 1, None, None, None, None, C.ACT_NONE, pfw, pfb, None, st)
             C.call("myolo_mask_out_fwd", self.y4d.rows, self.p["myolo_mask_deconv/bias"], self.p["myolo_mask/kernel"],
                    self.p["myolo_mask/bias"], A["masks"], n, P_, P_, MASK_C, self.NC, st)
         mh, mw = self.cfg["MASK_SHAPE"]

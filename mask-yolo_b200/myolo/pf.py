@@ -24,7 +24,7 @@ def guard_rows(W: int) -> int:
 class PF:
     """Owns a zero-initialised PF buffer.  .rows is the [M, C] matrix (M = n*(H+1)*(W+1))."""
 
-    def __init__(self, n, H, W, C, device="cuda", storage=None, split=False):
+    def __init__(self, n, H, W, C, device="cuda", storage=None, split=False, dtype=torch.float32):
         """split=True allocates a second copy (the tf32 low part of a 3xTF32 operand) `lo_off` rows
         after the first, separated by zero guard rows: [guard | rows | guard | rows_lo | guard]."""
         self.n, self.H, self.W, self.C = n, H, W, C
@@ -32,8 +32,9 @@ class PF:
         g = guard_rows(W)
         copies = 2 if split else 1
         total = (copies * (self.M + g) + g) * C
+        self.esize = torch.empty(0, dtype=dtype).element_size()      # 4 (fp32) or 2 (IEEE half, "h16" mask head)
         if storage is None:
-            storage = torch.zeros(total, dtype=torch.float32, device=device)
+            storage = torch.zeros(total, dtype=dtype, device=device)
         else:
             assert storage.numel() >= total
             storage = storage[:total]
@@ -47,7 +48,7 @@ class PF:
         W, H, C = self.W, self.H, self.C
         off = ((W + 1) + 1) * C
         base = (self.rows_lo if lo else self.rows).data_ptr()
-        return _cabi.View(base + 4 * off, (H + 1) * (W + 1) * C, (W + 1) * C, self.n, H, W, C)
+        return _cabi.View(base + self.esize * off, (H + 1) * (W + 1) * C, (W + 1) * C, self.n, H, W, C)
 
     def valid(self) -> torch.Tensor:
         """[n,H,W,C] strided torch view of the valid pixels (no copy)."""

@@ -1,0 +1,215 @@
+"""Per-kernel parity of the half-operand (tcgen05 kind::f16) mask-head kernels.
+
+Inputs are drawn so that every operand is exactly representable in IEEE half; the exact CUDA-core kernels
+(already checked against the oracle in test_kernels_gpu.py) then compute the same products in fp32, so the
+fp32 outputs of the half-operand kernels must agree to accumulation-order rounding and the half outputs to
+one half ulp (2^-11 relative) of it.  ROIAlign's and BN's half outputs are compared bit-exactly with the
+round-to-nearest-even conversion of the oracle-checked fp32 result."""
+import ctypes
+
+import pytest
+import torch
+
+from oracle import myolo_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def C():
+    from myolo import _cabi
+    _cabi.device_check(0)
+    return _cabi
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def hq(t):
+    """values exactly representable in half, kept in fp32"""
+    return t.half().float()
+
+
+def close(a, b, tol, what=""):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    scale = max(b.abs().max().item(), 1e-6)
+    err = (a - b).abs().max().item() / scale
+    assert err <= tol, f"{what}: rel-to-max err {err:.3e} > {tol}"
+
+
+def half_pf(pf32):
+    """half twin of a fp32 padded-flat tensor (same geometry, converted storage)"""
+    from myolo.pf import PF
+    h = PF(pf32.n, pf32.H, pf32.W, pf32.C, dtype=torch.float16)
+    h.rows.copy_(pf32.rows)
+    return h
+
+
+def test_prep_weights_h(C):
+    torch.manual_seed(1)
+    w = torch.randn(9, 64, 96, device="cuda")
+    out = torch.empty(9, 96, 64, dtype=torch.float16, device="cuda")
+    C.call("myolo_prep_weights_h", w, out, 9, 64, 96, 1, stream())
+    assert torch.equal(out, w.transpose(1, 2).contiguous().half())
+    out2 = torch.empty(9, 64, 96, dtype=torch.float16, device="cuda")
+    C.call("myolo_prep_weights_h", w * 1e5, out2, 9, 64, 96, 0, stream())
+    assert torch.equal(out2, (w * 1e5).clamp(-65504, 65504).half()), "conversion saturates instead of producing inf"
+
+
+@pytest.mark.parametrize("n,H,W", [(40, 14, 14), (300, 14, 14), (19, 7, 9)])
+def test_conv3x3_half_operands(C, n, H, W):
+    """forward conv with the folded bias/BN/ReLU epilogue, fp32 + half outputs; then the dgrad form with a
+    device-side accumulator scale."""
+    from myolo.pf import PF, conv3x3_shifts
+    torch.manual_seed(30)
+    Ci = Co = 256
+    px = PF(n, H, W, Ci)
+    px.valid().copy_(hq(torch.randn(n, H, W, Ci, device="cuda")))
+    w = hq(torch.randn(9, Ci, Co, device="cuda") / (9 * Ci) ** 0.5)
+    wt = torch.empty(9 * Ci * Co, device="cuda")
+    C.call("myolo_prep_weights", w, wt, 9, Ci, Co, 1, 0, stream())
+    wth = torch.empty(9 * Ci * Co, dtype=torch.float16, device="cuda")
+    C.call("myolo_prep_weights_h", w, wth, 9, Ci, Co, 1, stream())
+    bias, scale, shift = (torch.randn(Co, device="cuda") * 0.1, torch.rand(Co, device="cuda") + 0.5,
+                          torch.randn(Co, device="cuda") * 0.1)
+    sh = C.int_array(conv3x3_shifts(W))
+    pfw, pfb, M = W + 1, (H + 1) * (W + 1), px.M
+    ref = PF(n, H, W, Co)
+    C.call("myolo_gemm_taps_ffma", px.rows, Ci, wt, ref.rows, Co, M, Co, Ci, 9, sh, bias, scale, shift, C.ACT_RELU, pfw, pfb, 0, stream())
+    assert C.lib().myolo_gemm_taps_h_supported(Ci, M, Co, Ci, 9, ctypes.addressof(sh)) == 1
+    xh = half_pf(px)
+    out, outh = PF(n, H, W, Co), PF(n, H, W, Co, dtype=torch.float16)
+    C.call("myolo_gemm_taps_h", xh.rows, Ci, wth, out.rows, Co, outh.rows, Co, M, Co, Ci, 9, sh, bias, scale, shift, C.ACT_RELU,
+           pfw, pfb, None, stream())
+    torch.cuda.synchronize()
+    close(out.rows, ref.rows, 6e-4, "half-operand conv, fp32 output")
+    assert torch.equal(outh.rows.float(), out.rows), "the fp32 copy holds exactly the half-rounded values"
+    # element-wise: within one half ulp of the exact result (plus accumulation-order noise)
+    err = (out.rows - ref.rows).abs()
+    assert (err <= ref.rows.abs() * 2.0 ** -10 + 1e-5).all()
+    assert outh.storage[:Co].abs().max().item() == 0 and outh.rows.view(n, H + 1, W + 1, Co)[:, 0].abs().max().item() == 0
+    assert outh.rows.view(n, H + 1, W + 1, Co)[:, :, 0].abs().max().item() == 0, "pad pixels stay zero"
+    # half output only
+    only_h = PF(n, H, W, Co, dtype=torch.float16)
+    C.call("myolo_gemm_taps_h", xh.rows, Ci, wth, None, 0, only_h.rows, Co, M, Co, Ci, 9, sh, bias, scale, shift, C.ACT_RELU,
+           pfw, pfb, None, stream())
+    assert torch.equal(only_h.rows, outh.rows)
+    # dgrad form (negated shifts, un-transposed weights), fp32 output scaled by a device scalar
+    shn = C.int_array(conv3x3_shifts(W, negate=True))
+    wh = w.half()
+    r2 = PF(n, H, W, Ci)
+    C.call("myolo_gemm_taps_ffma", ref.rows, Co, w, r2.rows, Ci, M, Ci, Co, 9, shn, None, None, None, 0, pfw, pfb, 0, stream())
+    gh = half_pf(ref)
+    r2h, g32 = PF(n, H, W, Ci), PF(n, H, W, Co)
+    g32.rows.copy_(gh.rows)
+    C.call("myolo_gemm_taps_ffma", g32.rows, Co, w, r2h.rows, Ci, M, Ci, Co, 9, shn, None, None, None, 0, pfw, pfb, 0, stream())
+    sc = torch.tensor([0.25], device="cuda")
+    o2 = PF(n, H, W, Ci)
+    C.call("myolo_gemm_taps_h", gh.rows, Co, wh, o2.rows, Ci, None, 0, M, Ci, Co, 9, shn, None, None, None, 0, pfw, pfb, sc, stream())
+    close(o2.rows * 4.0, r2h.rows, 2e-5, "half-operand dgrad with accumulator scale")
+
+
+def test_deconv_mask_tail_half_operands(C):
+    from myolo.pf import PF
+    torch.manual_seed(31)
+    n, H, W, Cm, NC = 37, 14, 14, 256, 4
+    pa = PF(n, H, W, Cm)
+    pa.valid().copy_(hq(torch.randn(n, H, W, Cm, device="cuda")))
+    kd = hq(torch.randn(4 * Cm, Cm, device="cuda") / Cm ** 0.5)
+    bd, w1, b1 = torch.randn(Cm, device="cuda") * 0.1, torch.randn(Cm, NC, device="cuda") / Cm ** 0.5, torch.randn(NC, device="cuda") * 0.1
+    ids = torch.zeros(n, dtype=torch.int32, device="cuda")
+    ids[[0, 5, 36]] = torch.tensor([1, 3, 2], dtype=torch.int32, device="cuda")
+    y_ref = PF(n, H, W, 4 * Cm)
+    C.call("myolo_gemm_taps_ffma", pa.rows, Cm, kd, y_ref.rows, 4 * Cm, pa.M, 4 * Cm, Cm, 1, None, None, None, None, 0,
+           W + 1, (H + 1) * (W + 1), 0, stream())
+    m_ref = torch.empty(n, 2 * H, 2 * W, NC, device="cuda")
+    C.call("myolo_mask_out_fwd", y_ref.rows, bd, w1, b1, m_ref, n, H, W, Cm, NC, stream())
+    y4 = PF(n, H, W, 4 * Cm)
+    m = torch.full((n, 2 * H, 2 * W, NC), -1.0, device="cuda")
+    C.call("myolo_deconv_mask_fwd_h", half_pf(pa).rows, kd.half(), bd, w1, b1, m, ids, y4.rows, n, H, W, Cm, NC, stream())
+    close(m, m_ref, 2e-5, "masks of the half-operand deconv + tail")
+    yv, rv = y4.valid(), y_ref.valid()
+    for r in range(n):
+        if ids[r] > 0:
+            close(yv[r], rv[r], 2e-5, "y4 of a positive roi")
+        else:
+            assert yv[r].abs().max().item() == 0
+
+
+def test_dgrad_with_fused_bn_backward_half(C):
+    """myolo_gemm_taps_bnbwd_h against the exact two-step path on the same (half-representable) tensors; the
+    incoming gradient carries a loss scale of 64 that the reduced dgamma / dbeta / dbias must not."""
+    from myolo.pf import PF, conv3x3_shifts
+    torch.manual_seed(32)
+    n, H, W, Cc = 40, 14, 14, 256
+    S = 64.0
+    g_true = PF(n, H, W, Cc)
+    g_true.valid().copy_(hq(torch.randn(n, H, W, Cc, device="cuda")))
+    a_out = PF(n, H, W, Cc)
+    a_out.valid().copy_(hq(torch.relu(torch.randn(n, H, W, Cc, device="cuda"))))
+    w = hq(torch.randn(9, Cc, Cc, device="cuda") / (9 * Cc) ** 0.5)
+    gamma, beta = torch.rand(Cc, device="cuda") + 0.5, torch.randn(Cc, device="cuda") * 0.1
+    var = torch.rand(Cc, device="cuda") + 0.5
+    shn = C.int_array(conv3x3_shifts(W, negate=True))
+    pfw, pfb, M = W + 1, (H + 1) * (W + 1), g_true.M
+    ws = torch.zeros(4112, dtype=torch.float64, device="cuda")
+    ref = PF(n, H, W, Cc)
+    C.call("myolo_gemm_taps_ffma", g_true.rows, Cc, w, ref.rows, Cc, M, Cc, Cc, 9, shn, None, None, None, 0, pfw, pfb, 0, stream())
+    dg_r, db_r, dbias_r = (torch.empty(Cc, device="cuda") for _ in range(3))
+    C.call("myolo_bn_act_bwd_from_output", a_out.view(), ref.view(), ref.view(), gamma, beta, var, 1e-3, C.ACT_RELU, dg_r, db_r,
+           dbias_r, ws, stream())
+    g_scaled = PF(n, H, W, Cc, dtype=torch.float16)
+    g_scaled.rows.copy_(g_true.rows * S)
+    out32, outh = PF(n, H, W, Cc), PF(n, H, W, Cc, dtype=torch.float16)
+    dg, db, dbias = (torch.empty(Cc, device="cuda") for _ in range(3))
+    unscale = torch.tensor([1.0 / S], device="cuda")
+    C.call("myolo_gemm_taps_bnbwd_h", g_scaled.rows, Cc, w.half(), out32.rows, outh.rows, Cc, M, Cc, Cc, 9, shn, pfw, pfb,
+           half_pf(a_out).rows, gamma, beta, var, 1e-3, C.ACT_RELU, dg, db, dbias, ws, unscale, stream())
+    torch.cuda.synchronize()
+    close(out32.rows / S, ref.rows, 6e-4, "fused d(pre-BN), fp32 copy")
+    assert torch.equal(outh.rows.float(), out32.rows)
+    close(db, db_r, 1e-4, "fused dbeta")
+    close(dg, dg_r, 1e-4, "fused dgamma")
+    close(dbias, dbias_r, 1e-4, "fused dbias")
+    assert ws.abs().max().item() == 0, "BN workspace must be left zero"
+    assert outh.storage[:Cc].abs().max().item() == 0 and outh.rows.view(n, H + 1, W + 1, Cc)[:, 0].abs().max().item() == 0
+    # half output only
+    only_h = PF(n, H, W, Cc, dtype=torch.float16)
+    C.call("myolo_gemm_taps_bnbwd_h", g_scaled.rows, Cc, w.half(), None, only_h.rows, Cc, M, Cc, Cc, 9, shn, pfw, pfb,
+           half_pf(a_out).rows, gamma, beta, var, 1e-3, C.ACT_RELU, dg, db, dbias, ws, unscale, stream())
+    assert torch.equal(only_h.rows, outh.rows)
+
+
+def test_roialign_and_bn_half_outputs(C):
+    from myolo.pf import PF
+    torch.manual_seed(33)
+    B, Fh, Cc, R, P = 2, 12, 64, 9, 14
+    feat = torch.randn(B, Fh, Fh, Cc)
+    g = torch.Generator().manual_seed(5)
+    c = torch.rand(B * R, 2, generator=g)
+    wh = torch.rand(B * R, 2, generator=g) * 0.6
+    boxes = torch.cat([c - wh / 2, c + wh / 2], 1)
+    boxes[0] = 0.0
+    boxes[1] = torch.tensor([-0.5, 0.1, 1.5, 0.8])
+    idx = torch.arange(B).repeat_interleave(R)
+    ref = O.crop_and_resize(feat, boxes, idx, P, P)
+    fd, bd = feat.cuda(), boxes.cuda()
+    o32, oh = PF(B * R, P, P, Cc), PF(B * R, P, P, Cc, dtype=torch.float16)
+    C.call("myolo_roialign_fwd_h", C.view(fd, B, Fh, Fh, Cc), bd, B * R, R, P, o32.view(), oh.view(), stream())
+    assert torch.equal(o32.valid().cpu(), ref), "fp32 ROIAlign output stays bit-exact vs the oracle"
+    assert torch.equal(oh.valid().cpu(), ref.half()), "half output = round-to-nearest-even of it"
+    oh2 = PF(B * R, P, P, Cc, dtype=torch.float16)
+    C.call("myolo_roialign_fwd_h", C.view(fd, B, Fh, Fh, Cc), bd, B * R, R, P, None, oh2.view(), stream())
+    assert torch.equal(oh2.rows, oh.rows)
+    # BN + ReLU with half / half-rounded fp32 outputs vs myolo_bn_apply
+    x = PF(5, P, P, Cc)
+    x.valid().normal_()
+    mean, var = torch.randn(Cc, device="cuda") * 0.1, torch.rand(Cc, device="cuda") + 0.5
+    gamma, beta = torch.rand(Cc, device="cuda") + 0.5, torch.randn(Cc, device="cuda") * 0.1
+    y_ref, y32, yh = PF(5, P, P, Cc), PF(5, P, P, Cc), PF(5, P, P, Cc, dtype=torch.float16)
+    C.call("myolo_bn_apply", x.view(), y_ref.view(), mean, var, gamma, beta, 1e-3, C.ACT_RELU, stream())
+    C.call("myolo_bn_apply_h", x.view(), y32.view(), yh.view(), mean, var, gamma, beta, 1e-3, C.ACT_RELU, stream())
+    assert torch.equal(yh.rows, y_ref.rows.half())
+    assert torch.equal(y32.rows, y_ref.rows.half().float())

@@ -86,7 +86,7 @@ def _reference(S, B, seed):
     return _REF[key]
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32x3", "tf32x3_all", "tf32"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3", "tf32x3_all", "h16", "tf32"])
 def test_train_step_matches_oracle(precision):
     from myolo.engine import Engine
     S, B = 128, 6
@@ -99,7 +99,7 @@ def test_train_step_matches_oracle(precision):
     torch.cuda.synchronize()
     exact = precision == "fp32"
     # ---- network outputs: boxes, class scores (yolo_output), rois, 28x28 masks
-    tol_out = {"fp32": 2e-4, "tf32x3": 1e-3, "tf32x3_all": 1e-3, "tf32": 0.5}[precision]
+    tol_out = {"fp32": 2e-4, "tf32x3": 1e-3, "tf32x3_all": 1e-3, "h16": 1e-3, "tf32": 0.5}[precision]
     errs = {k: _abs(out_e[k], out64[k].float()) for k in ("yolo_proposals", "yolo_output", "output_rois", "myolo_mask")}
     print(f"[{precision}] max abs output errors vs fp64 oracle: {errs}")
     same_sel = torch.equal(out_e["target_class_ids"].cpu(), out64["target_class_ids"])
@@ -110,7 +110,7 @@ def test_train_step_matches_oracle(precision):
     assert (tm_e != tm_o).float().mean().item() <= (1e-4 if precision != "tf32" else 2e-2), "mask targets"
     for k, e in errs.items():
         assert e <= tol_out, (k, e)
-    ltol = {"fp32": 2e-4, "tf32x3": 3e-3, "tf32x3_all": 3e-3, "tf32": 5e-2}[precision]
+    ltol = {"fp32": 2e-4, "tf32x3": 3e-3, "tf32x3_all": 3e-3, "h16": 3e-3, "tf32": 5e-2}[precision]
     for k in ("yolo_sum_loss", "mask_loss"):
         lo, le = out64[k].item(), out_e[k].item()
         assert abs(lo - le) <= ltol * max(1.0, abs(lo)), (k, lo, le)
@@ -144,7 +144,7 @@ def test_inference_matches_oracle():
     c, oc, P, inputs = _case(S, B, 200)
     with torch.no_grad():
         ref = O.forward_inference(P, inputs[0], oc)
-    for precision, tol in (("fp32", 2e-4), ("tf32x3_all", 1e-3), ("tf32x3", 1e-3)):
+    for precision, tol in (("fp32", 2e-4), ("tf32x3_all", 1e-3), ("tf32x3", 1e-3), ("h16", 1e-3)):
         eng = Engine(c, B, "inference", precision, params=P)
         yolo, det, masks = eng.forward_inference(inputs[0].cuda())
         torch.cuda.synchronize()
@@ -207,7 +207,7 @@ def test_large_configs_tensor_core_path_matches_exact_fp32_path(S, B, NB, NC):
     c, P, inputs = _engine_pair_case(S, B, NB, NC, 400 + S)
     dev_in = Hh.to_device(inputs)
     outs = {}
-    for prec in ("fp32", "tf32x3"):
+    for prec in ("fp32", "tf32x3", "h16"):
         eng = Engine(c, B, "training", prec, params=P)
         o = eng.train_step(dev_in, lr=1e-3)
         torch.cuda.synchronize()
@@ -215,7 +215,11 @@ def test_large_configs_tensor_core_path_matches_exact_fp32_path(S, B, NB, NC):
         outs[prec]["grads"] = eng.grad_dict()
         del eng
         torch.cuda.empty_cache()
-    a, b = outs["fp32"], outs["tf32x3"]
+    _compare_to_exact(outs["fp32"], outs["tf32x3"], B, c, NC)
+    _compare_to_exact(outs["fp32"], outs["h16"], B, c, NC)
+
+
+def _compare_to_exact(a, b, B, c, NC):
     assert a["myolo_mask"].shape == (B, c["R"], 28, 28, NC)
     for k in ("yolo_sum_loss", "mask_loss"):
         assert torch.isfinite(a[k]) and abs(a[k].item() - b[k].item()) <= 3e-3 * max(1.0, abs(a[k].item())), k
@@ -256,11 +260,12 @@ def test_edge_cases_no_ground_truth_and_nan_free():
         assert torch.isfinite(t).all()
     # no positives anywhere: random GT far from every proposal
     inputs2 = Hh.batch_from_boxes(c, B, img, [[] for _ in range(B)], 11)
-    eng2 = Engine(c, B, "training", "tf32x3", params=P)
-    out2 = eng2.train_step(Hh.to_device(inputs2), lr=1e-3)
-    torch.cuda.synchronize()
-    assert out2["mask_loss"].item() == 0.0 and int(eng2.n_pos.sum().item()) == 0
-    g2 = eng2.grad_dict()
-    assert g2["myolo_mask_conv3/kernel"].abs().max().item() == 0 and g2["feature_map/kernel"].abs().max().item() == 0
-    assert g2["conv_pw_3/kernel"].abs().max().item() > 0          # the yolo loss still trains the backbone
-    assert all(torch.isfinite(v).all() for v in g2.values())
+    for prec in ("tf32x3", "h16"):
+        eng2 = Engine(c, B, "training", prec, params=P)
+        out2 = eng2.train_step(Hh.to_device(inputs2), lr=1e-3)
+        torch.cuda.synchronize()
+        assert out2["mask_loss"].item() == 0.0 and int(eng2.n_pos.sum().item()) == 0
+        g2 = eng2.grad_dict()
+        assert g2["myolo_mask_conv3/kernel"].abs().max().item() == 0 and g2["feature_map/kernel"].abs().max().item() == 0
+        assert g2["conv_pw_3/kernel"].abs().max().item() > 0          # the yolo loss still trains the backbone
+        assert all(torch.isfinite(v).all() for v in g2.values())
