@@ -232,6 +232,28 @@ int myolo_roialign_fwd_h(const myolo_view* feat, const float* boxes, int n_roi, 
 int myolo_bn_apply_h(const myolo_view* x, const myolo_view* y, const myolo_view* y_half, const float* mean,
                      const float* var, const float* gamma, const float* beta, float eps, int act, myolo_stream stream);
 
+/* -- backward of the mask head in the "h16" mode.  Gradients are stored as half multiplied by a power-of-two loss
+ * scale S that lives on the DEVICE: gs = {S, 1/S, scratch}, computed per step by myolo_grad_scale from max|dlogit| so
+ * that the scaled gradient peaks in [8, 16) (no host synchronisation; S = 1 for an all-zero gradient).  Every
+ * parameter gradient is un-scaled where it is reduced (out_scale / grad_unscale = gs + 1), so the flat gradient
+ * buffer, Adam and the all-reduce never see S. */
+int myolo_grad_scale(const float* g, long long n, float* gs, myolo_stream stream);
+/* myolo_mask_out_bwd with dy4 stored as half * (*gscale); dw1 / db1 / dbd are unscaled. */
+int myolo_mask_out_bwd_h(const float* y4, const float* bd, const float* w1, const float* dlogit, void* dy4_half,
+                         float* dw1, float* db1, float* dbd, int n_roi, int H, int W, int Cmid, int NC,
+                         const float* gscale, myolo_stream stream);
+/* myolo_gemm_taps_wgrad with half A [rows][K] and half D [rows][N] (both MN-major operands of tcgen05 kind::f16):
+ * dW[t][k][n] += (*out_scale) * sum_m A[m + shift[t], k] * D[m, n]  (fp32 atomics; out_scale nullable = 1).
+ * K % 64 == 0, N % 64 == 0, lda % 8 == 0, ldd % 8 == 0. */
+int myolo_gemm_taps_wgrad_h(const void* A, long long lda, const void* D, long long ldd, float* dW, long long M,
+                            int N, int K, int ntaps, const int* shifts_host, int transpose_out,
+                            const float* out_scale, myolo_stream stream);
+int myolo_gemm_taps_wgrad_h_supported(long long lda, long long ldd, long long M, int N, int K, int ntaps);
+/* myolo_bn_bwd (fp32 x, fp32 UNSCALED dy) whose dx is stored as half * (*out_scale) in the half view dx_half. */
+int myolo_bn_bwd_h(const myolo_view* x, const myolo_view* dy, const myolo_view* dx_half, const float* mean,
+                   const float* var, const float* gamma, const float* beta, float eps, int act, int train,
+                   float* dgamma, float* dbeta, double* ws, const float* out_scale, myolo_stream stream);
+
 /* ---- K12: DecodeYOLOLayer / DetectionsLayer, myolo/model.py:1442-1473, 1493-1538 ---- */
 int myolo_yolo_decode(const float* y_pred, const float* anchors, float* boxes, float* detections /*nullable*/,
                       int B, int GH, int GW, int NB, int NC, myolo_stream stream);

@@ -270,9 +270,12 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(V src, V hi, V lo) {
   }
 }
 
+// HALF: dx is an IEEE-half view and receives dx * (*oscale) (loss-scaled operand of the kind::f16 GEMMs)
+template <bool HALF>
 __global__ void __launch_bounds__(256)
 bn_bwd_dx_kernel(V x, V dy, V dx, const float* __restrict__ mean, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, int act, const float* __restrict__ coef) {
+                 const float* __restrict__ beta, int act, const float* __restrict__ coef, const float* __restrict__ oscale) {
+  const float os = (HALF && oscale) ? __ldg(oscale) : 1.f;
   const int C = x.c, C4 = C >> 2;
   const FastDiv x_fc4 = x.fc4;
   const long long total = (long long)x.n * x.h * x.w * C4;
@@ -301,7 +304,11 @@ bn_bwd_dx_kernel(V x, V dy, V dx, const float* __restrict__ mean, const float* _
       o[j] = k1a[j] * (gg - m0a[j] - xh * m1a[j]);     // inference-mode BN: m0 = m1 = 0
       if (act & MYOLO_ROUND_TF32) o[j] = round_tf32(o[j]);
     }
-    *reinterpret_cast<float4*>(dx.p + pix_off(dx, p) + q) = make_float4(o[0], o[1], o[2], o[3]);
+    if (HALF)
+      *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(dx.p) + pix_off(dx, p) + q) =
+          make_uint2(pack_half2_sat(o[0] * os, o[1] * os), pack_half2_sat(o[2] * os, o[3] * os));
+    else
+      *reinterpret_cast<float4*>(dx.p + pix_off(dx, p) + q) = make_float4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -538,7 +545,27 @@ extern "C" int myolo_bn_bwd(const myolo_view* x, const myolo_view* dy, const myo
   float* coef = reinterpret_cast<float*>(ws + kWsCoef);   // 4*C floats
   Fin fin{dbeta, dgamma, coef, ws_ticket(ws, C), 1.0 / (double)total, train, C};
   colreduce_kernel<2><<<grid, 256, 0, st>>>(to_v(x), to_v(dy), mean, var, gamma, beta, eps, act, ws + kWsSums, ws + kWsSums + C, chunk, fin);
-  bn_bwd_dx_kernel<<<ew_blocks(total * (C / 4)), 256, 0, st>>>(to_v(x), to_v(dy), to_v(dx), mean, gamma, beta, act, coef);
+  bn_bwd_dx_kernel<false><<<ew_blocks(total * (C / 4)), 256, 0, st>>>(to_v(x), to_v(dy), to_v(dx), mean, gamma, beta, act, coef, nullptr);
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
+}
+
+extern "C" int myolo_bn_bwd_h(const myolo_view* x, const myolo_view* dy, const myolo_view* dx_half, const float* mean,
+                              const float* var, const float* gamma, const float* beta, float eps, int act, int train,
+                              float* dgamma, float* dbeta, double* ws, const float* out_scale, myolo_stream stream) {
+  MYOLO_CHECK_ARG(view_ok(x) && view_ok(dy) && view_ok(dx_half) && same_shape(x, dy) && same_shape(x, dx_half));
+  MYOLO_CHECK_ARG(mean && var && gamma && beta && dgamma && dbeta && ws && (x->c % 32) == 0 && x->c <= kWsMaxC);
+  MYOLO_CHECK_ARG(((uintptr_t)dx_half->p & 7) == 0 && !(act & MYOLO_ROUND_TF32));
+  cudaStream_t st = as_stream(stream);
+  const int C = x->c;
+  const long long total = (long long)x->n * x->h * x->w;
+  dim3 grid;
+  long long chunk;
+  reduce_grid(total, C, &grid, &chunk);
+  float* coef = reinterpret_cast<float*>(ws + kWsCoef);
+  Fin fin{dbeta, dgamma, coef, ws_ticket(ws, C), 1.0 / (double)total, train, C};
+  colreduce_kernel<2><<<grid, 256, 0, st>>>(to_v(x), to_v(dy), mean, var, gamma, beta, eps, act, ws + kWsSums, ws + kWsSums + C, chunk, fin);
+  bn_bwd_dx_kernel<true><<<ew_blocks(total * (C / 4)), 256, 0, st>>>(to_v(x), to_v(dy), to_v(dx_half), mean, gamma, beta, act, coef, out_scale);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }

@@ -474,16 +474,23 @@ using namespace myolo;
 using namespace myolo::tc;
 
 
-extern "C" int myolo_gemm_taps_win_supported(long long lda, long long ldc, long long M, int N, int K, int ntaps,
-                                             const int* shifts_host, int accumulate) {
+// min_m: smallest M for which a plain (single-tap) GEMM is routed here
+static int win_shape_ok(long long lda, long long ldc, long long M, int N, int K, int ntaps, const int* shifts_host,
+                        int accumulate, long long min_m) {
   if (!(M >= 1 && M < (1LL << 31) - 4096 && N >= 128 && (N % 128) == 0 && N <= 1024 && K >= BK && (K % BK) == 0 && (lda % 4) == 0 && (ldc % 4) == 0 &&
         ntaps >= 1 && ntaps <= 32 && !accumulate))
     return 0;
-  if (!shifts_host) return ntaps == 1 && M >= 4096;   // plain GEMM: worth it only for large M (persistent 256-row tiles)
+  if (!shifts_host) return ntaps == 1 && M >= min_m;
   for (int t = 0; t < ntaps; ++t)
     if (shifts_host[t] < -WHALO || shifts_host[t] > WHALO) return 0;
-  if (ntaps == 1 && M < 4096) return 0;
+  if (ntaps == 1 && M < min_m) return 0;
   return 1;
+}
+
+extern "C" int myolo_gemm_taps_win_supported(long long lda, long long ldc, long long M, int N, int K, int ntaps,
+                                             const int* shifts_host, int accumulate) {
+  // plain GEMM: worth it only for large M (persistent 256-row tiles)
+  return win_shape_ok(lda, ldc, M, N, K, ntaps, shifts_host, accumulate, 4096);
 }
 
 struct BnBwd {   // host-side bundle of the fused BN-backward epilogue arguments (all null = off)
@@ -511,7 +518,7 @@ static int launch_win(const float* A, long long lda, const float* Bt, float* C, 
                       const BnBwd& bnb = BnBwd{}, const HalfIO& hio = HalfIO{}) {
   MYOLO_CHECK_ARG(A && Bt && ((((uintptr_t)A | (uintptr_t)Bt | (uintptr_t)C) & 15) == 0));
   MYOLO_CHECK_ARG(C || (hio.on && hio.no_f32));
-  MYOLO_CHECK_ARG(myolo_gemm_taps_win_supported(lda, ldc, M, N, K, ntaps, shifts_host, accumulate));
+  MYOLO_CHECK_ARG(win_shape_ok(lda, ldc, M, N, K, ntaps, shifts_host, accumulate, hio.on ? 1 : 4096));
   if (hio.on) {
     MYOLO_CHECK_ARG((K % 64) == 0 && (lda % 8) == 0 && (N % 256) == 0 && !(act & MYOLO_ROUND_TF32));
     MYOLO_CHECK_ARG(!hio.Ch || ((hio.ldch % 8) == 0 && ((uintptr_t)hio.Ch & 15) == 0));
@@ -682,7 +689,8 @@ extern "C" int myolo_gemm_taps_bnbwd(const float* A, long long lda, const float*
 // half-operand (kind::f16) entry points: same kernel, IEEE-half A / Bt, fp32 accumulation in TMEM
 // ------------------------------------------------------------------------------------------
 extern "C" int myolo_gemm_taps_h_supported(long long lda, long long M, int N, int K, int ntaps, const int* shifts_host) {
-  return (N % 256) == 0 && (K % 64) == 0 && (lda % 8) == 0 && myolo_gemm_taps_win_supported(lda, N, M, N, K, ntaps, shifts_host, 0);
+  // the only half-operand GEMM kernel: it takes every M (no tf32-style hand-over of small plain GEMMs)
+  return (N % 256) == 0 && (K % 64) == 0 && (lda % 8) == 0 && win_shape_ok(lda, N, M, N, K, ntaps, shifts_host, 0, 1);
 }
 
 extern "C" int myolo_gemm_taps_h(const void* A, long long lda, const void* Bt, float* C, long long ldc, void* Ch,

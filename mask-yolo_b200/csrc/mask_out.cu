@@ -77,10 +77,21 @@ mask_out_fwd_kernel(const float* __restrict__ y4, const float* __restrict__ bd, 
 
 // backward of the same tail.  dlogit is zero except on the class channel of positive ROIs, so the
 // per-pixel work is a ballot over the NC gradients and a loop over the (usually one) non-zero class.
+__device__ __forceinline__ uint32_t pack_half2_sat(float lo, float hi) {
+  uint16_t a, b;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(a) : "f"(lo));
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(b) : "f"(hi));
+  return (uint32_t)a | ((uint32_t)b << 16);
+}
+
+// HALF: dy4 is stored as IEEE half, multiplied by the loss scale *gscale (the parameter gradients dw1 / db1 / dbd
+// are reduced from the unscaled values).
+template <bool HALF>
 __global__ void __launch_bounds__(256)
 mask_out_bwd_kernel(const float* __restrict__ y4, const float* __restrict__ bd, const float* __restrict__ w1,
                     const float* __restrict__ dlogit, float* __restrict__ dy4, float* __restrict__ dw1,
-                    float* __restrict__ db1, float* __restrict__ dbd, int n_roi, int H, int W, int Cmid, int NC) {
+                    float* __restrict__ db1, float* __restrict__ dbd, int n_roi, int H, int W, int Cmid, int NC,
+                    const float* __restrict__ gscale) {
   extern __shared__ float sm[];  // w1 [Cmid][NC] | acc_w1 [Cmid][NC] | acc_b1 [NC]
   float* s_w1 = sm;
   float* a_w1 = sm + Cmid * NC;
@@ -104,6 +115,7 @@ mask_out_bwd_kernel(const float* __restrict__ y4, const float* __restrict__ bd, 
 #pragma unroll
   for (int e = 0; e < 8; ++e) dbd_acc[e] = 0.f;
   bool any_local = false;
+  const float gs = (HALF && gscale) ? __ldg(gscale) : 1.f;
   for (long long it = warp; it < items; it += nwarps) {
     const int ab = (int)(it & 3);
     long long t = it >> 2;
@@ -163,8 +175,13 @@ mask_out_bwd_kernel(const float* __restrict__ y4, const float* __restrict__ bd, 
     }
 #pragma unroll
     for (int j = 0; j < 2; ++j)
-      if (j < nq)
-        reinterpret_cast<float4*>(dy4 + off)[j * 32 + lane] = make_float4(d[4 * j], d[4 * j + 1], d[4 * j + 2], d[4 * j + 3]);
+      if (j < nq) {
+        if (HALF)
+          reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(dy4) + off)[j * 32 + lane] =
+              make_uint2(pack_half2_sat(d[4 * j] * gs, d[4 * j + 1] * gs), pack_half2_sat(d[4 * j + 2] * gs, d[4 * j + 3] * gs));
+        else
+          reinterpret_cast<float4*>(dy4 + off)[j * 32 + lane] = make_float4(d[4 * j], d[4 * j + 1], d[4 * j + 2], d[4 * j + 3]);
+      }
   }
   if (any_local) {
 #pragma unroll
@@ -244,11 +261,70 @@ extern "C" int myolo_mask_out_bwd(const float* y4, const float* bd, const float*
   MYOLO_CHECK_ARG(Cmid > 0 && (Cmid % 128) == 0 && Cmid <= kMaxCmid);
   const size_t smem = (size_t)(2 * Cmid * NC + NC) * sizeof(float);
   MYOLO_CHECK_ARG(smem <= 200 * 1024);
-  if (smem > 48 * 1024) MYOLO_CUDA(cudaFuncSetAttribute(mask_out_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 48 * 1024) MYOLO_CUDA(cudaFuncSetAttribute(mask_out_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long items = (long long)n_roi * H * W * 4;
   const int per_sm = smem > 64 * 1024 ? 1 : 4;
   const int blocks = (int)max(1LL, min(ceil_div(items, 8), (long long)kNumSMs * per_sm));
-  mask_out_bwd_kernel<<<blocks, 256, smem, as_stream(stream)>>>(y4, bd, w1, dlogit, dy4, dw1, db1, dbd, n_roi, H, W, Cmid, NC);
+  mask_out_bwd_kernel<false><<<blocks, 256, smem, as_stream(stream)>>>(y4, bd, w1, dlogit, dy4, dw1, db1, dbd, n_roi, H, W, Cmid, NC, nullptr);
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
+}
+
+extern "C" int myolo_mask_out_bwd_h(const float* y4, const float* bd, const float* w1, const float* dlogit, void* dy4_half,
+                                    float* dw1, float* db1, float* dbd, int n_roi, int H, int W, int Cmid, int NC,
+                                    const float* gscale, myolo_stream stream) {
+  MYOLO_CHECK_ARG(y4 && bd && w1 && dlogit && dy4_half && dw1 && db1 && dbd && n_roi > 0 && H > 0 && W > 0 && NC > 0);
+  MYOLO_CHECK_ARG(Cmid > 0 && (Cmid % 128) == 0 && Cmid <= kMaxCmid && ((uintptr_t)dy4_half & 7) == 0);
+  const size_t smem = (size_t)(2 * Cmid * NC + NC) * sizeof(float);
+  MYOLO_CHECK_ARG(smem <= 200 * 1024);
+  if (smem > 48 * 1024) MYOLO_CUDA(cudaFuncSetAttribute(mask_out_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long items = (long long)n_roi * H * W * 4;
+  const int per_sm = smem > 64 * 1024 ? 1 : 4;
+  const int blocks = (int)max(1LL, min(ceil_div(items, 8), (long long)kNumSMs * per_sm));
+  mask_out_bwd_kernel<true><<<blocks, 256, smem, as_stream(stream)>>>(y4, bd, w1, dlogit, reinterpret_cast<float*>(dy4_half), dw1,
+                                                                      db1, dbd, n_roi, H, W, Cmid, NC, gscale);
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
+}
+
+// ---- loss scale of the half-precision backward pass -------------------------------------------------------------
+// gs[0] = S = 2^(4 - e) with max|g| in [2^(e-1), 2^e)  (the scaled gradient peaks in [8, 16): 12 binades of headroom
+// below the half maximum for growth through the five backward GEMMs, 18 binades of full precision below the peak),
+// gs[1] = 1/S, gs[2] = scratch (max bits, zero between calls).  S = 1 when the gradient is identically zero.
+namespace myolo {
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ g, long long n, unsigned* __restrict__ out) {
+  float m = 0.f;
+  const long long n4 = n >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(g)[i];
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) m = fmaxf(m, fabsf(g[(n4 << 2) + threadIdx.x]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));   // non-negative floats order like their bits
+}
+__global__ void grad_scale_finalize_kernel(float* __restrict__ gs) {
+  const float m = __uint_as_float(reinterpret_cast<unsigned*>(gs)[2]);
+  float S = 1.f;
+  if (m > 0.f && m < 3.0e38f) {
+    int e;
+    frexpf(m, &e);                    // m = f * 2^e, f in [0.5, 1)
+    e = 4 - e;
+    e = e < -60 ? -60 : (e > 60 ? 60 : e);
+    S = ldexpf(1.f, e);
+  }
+  gs[0] = S;
+  gs[1] = 1.f / S;
+  reinterpret_cast<unsigned*>(gs)[2] = 0u;
+}
+}  // namespace myolo
+
+extern "C" int myolo_grad_scale(const float* g, long long n, float* gs, myolo_stream stream) {
+  MYOLO_CHECK_ARG(g && gs && n > 0 && ((uintptr_t)g & 15) == 0);
+  const int blocks = (int)max(1LL, min(ceil_div(n / 4 + 1, 256), (long long)kNumSMs * 8));
+  absmax_kernel<<<blocks, 256, 0, as_stream(stream)>>>(g, n, reinterpret_cast<unsigned*>(gs) + 2);
+  grad_scale_finalize_kernel<<<1, 1, 0, as_stream(stream)>>>(gs);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }

@@ -194,11 +194,15 @@ class Engine:
                 self.wt[name] = torch.zeros(n * (3 if self._is_x3(name) else 1), dtype=torch.float32, device=self.dev)
         # "h16": IEEE-half staging of the mask-head weights.  fwd = per-tap transposed [t][Cout][Cin] (deconv: the
         # Keras layout is already [4*Cout][Cin]).
-        self.wth = {}
+        # dgrad = the HWIO kernel as it is ([t][Cin][Cout] = Bt of the data-gradient GEMM; deconv: transposed [Cin][4*Cout]).
+        self.wth, self.wth_d = {}, {}
         if self.h16:
             for name, (o, n, shape) in self.offs.items():
                 if name.startswith("myolo_mask_conv") and name.endswith("/kernel") or name == "myolo_mask_deconv/kernel":
                     self.wth[name] = torch.zeros(n, dtype=torch.float16, device=self.dev)
+                    if self.mode == "training":
+                        self.wth_d[name] = torch.zeros(n, dtype=torch.float16, device=self.dev)
+            self.gs = torch.tensor([1.0, 1.0, 0.0, 0.0], dtype=torch.float32, device=self.dev)   # loss scale {S, 1/S, scratch}
         self.ws = torch.zeros(8192, dtype=torch.float64, device=self.dev)       # BN family: zero between calls
         self.ws_loss = torch.zeros(16, dtype=torch.float64, device=self.dev)
         self.anchors = torch.tensor(self.cfg["ANCHORS"], dtype=torch.float32, device=self.dev)
@@ -265,6 +269,12 @@ class Engine:
                 C.call("myolo_prep_weights_h", self.p[name], buf, 1, 4 * shape[2], shape[3], 0, st)
             else:
                 C.call("myolo_prep_weights_h", self.p[name], buf, shape[0] * shape[1], shape[2], shape[3], 1, st)
+        for name, buf in self.wth_d.items():
+            shape = self.offs[name][2]
+            if name == "myolo_mask_deconv/kernel":
+                C.call("myolo_prep_weights_h", self.p[name], buf, 1, 4 * shape[2], shape[3], 1, st)
+            else:
+                C.call("myolo_prep_weights_h", self.p[name], buf, shape[0] * shape[1], shape[2], shape[3], 0, st)
 
     # ------------------------------------------------------------------ activations
     def _alloc_acts(self):
@@ -306,16 +316,18 @@ class Engine:
             n = B * R
             self.n_roi = n
             self.feat = PF(B, F_, F_, MASK_C, device=dev)
-            self.x0 = PF(n, P_, P_, MASK_C, device=dev, split=self.x3m)
             # pre-BN conv outputs: only conv1 (batch-statistics BN) needs one; conv2..4 fold their
             # fixed-statistics BN + ReLU into the GEMM epilogue (unless the 3xTF32 mask mode splits them)
             self.my = [None] + [PF(n, P_, P_, MASK_C, device=dev) if (i == 1 or self.x3m) else None for i in range(1, 5)]
             self.bn_scale = torch.zeros(4, MASK_C, device=dev)
             self.bn_shift = torch.zeros(4, MASK_C, device=dev)
-            self.ma = [self.x0] + [PF(n, P_, P_, MASK_C, device=dev, split=self.x3m and i < 4) for i in range(1, 5)]
-            self.y4d = PF(n, P_, P_, 4 * MASK_C, device=dev)
-            if self.h16:     # half copies of the conv operands x0, a1..a4
+            if self.h16:     # the conv operands x0, a1..a4 exist as IEEE half only
                 self.mah = [PF(n, P_, P_, MASK_C, device=dev, dtype=torch.float16) for _ in range(5)]
+                self.x0, self.ma = None, [None] * 5
+            else:
+                self.x0 = PF(n, P_, P_, MASK_C, device=dev, split=self.x3m)
+                self.ma = [self.x0] + [PF(n, P_, P_, MASK_C, device=dev, split=self.x3m and i < 4) for i in range(1, 5)]
+            self.y4d = PF(n, P_, P_, 4 * MASK_C, device=dev)
             mh, mw = self.cfg["MASK_SHAPE"]
             assert (mh, mw) == (2 * P_, 2 * P_)
             A["masks"] = f(n, mh, mw, NC)
@@ -327,7 +339,11 @@ class Engine:
                 self.roi_src = torch.zeros(B, R, dtype=torch.int32, device=dev)
                 self.roi_gt = torch.zeros(B, R, dtype=torch.int32, device=dev)
                 A["dlogit"] = f(n, mh, mw, NC)
-                self.dy4d = PF(n, P_, P_, 4 * MASK_C, device=dev)
+                if self.h16:     # loss-scaled half gradients; fp32 only for d(a1) (batch-statistics BN) and d(x0) (ROIAlign)
+                    self.dy4h = PF(n, P_, P_, 4 * MASK_C, device=dev, dtype=torch.float16)
+                    self.mgh = [PF(n, P_, P_, MASK_C, device=dev, dtype=torch.float16) for _ in range(2)]
+                else:
+                    self.dy4d = PF(n, P_, P_, 4 * MASK_C, device=dev)
                 self.mg = [PF(n, P_, P_, MASK_C, device=dev) for _ in range(2)]
                 self.dfeat = PF(B, F_, F_, MASK_C, device=dev)
                 self.dc4 = PF(B, F_, F_, 512, device=dev)
@@ -487,18 +503,18 @@ class Engine:
 
     def _mask_head_h16(self, rois: torch.Tensor, training: bool):
         """mask_head on tcgen05 kind::f16: every conv reads IEEE-half activations / weights, accumulates in fp32 and
-        stores its result as half for the next conv and as fp32 (the same rounded values) for the backward pass."""
+        stores its result as half (what the next conv and the whole backward pass read)."""
         A, st, n = self.A, self._st(), self.n_roi
         P_ = self.cfg["POOL"]
         npix = n * P_ * P_
         pfw, pfb = P_ + 1, (P_ + 1) * (P_ + 1)
-        C.call("myolo_roialign_fwd_h", self.feat.view(), rois, n, self.R, P_, self.x0.view(), self.mah[0].view(), st)
+        C.call("myolo_roialign_fwd_h", self.feat.view(), rois, n, self.R, P_, None, self.mah[0].view(), st)
         key = ("h16", P_)
         sh3 = self._shift_cache.get(key)
         if sh3 is None:
             sh3 = self._shift_cache[key] = C.int_array(conv3x3_shifts(P_))
         self._mask_fused = [False] * 5
-        M = self.x0.M
+        M = self.mah[0].M
         for i in (1, 2, 3, 4):
             name = f"myolo_mask_conv{i}/kernel"
             a_in = self.mah[i - 1]
@@ -514,7 +530,7 @@ class Engine:
                 b = self.bn[f"myolo_mask_bn{i}"]
                 C.call("myolo_bn_fold", b.gamma, b.beta, b.mmean, b.mvar, BN_EPS, self.bn_scale[i - 1], self.bn_shift[i - 1],
                        MASK_C, st)
-                C.call("myolo_gemm_taps_h", a_in.rows, MASK_C, self.wth[name], self.ma[i].rows, MASK_C, self.mah[i].rows, MASK_C,
+                C.call("myolo_gemm_taps_h", a_in.rows, MASK_C, self.wth[name], None, 0, self.mah[i].rows, MASK_C,
                        M, MASK_C, MASK_C, 9, sh3, self.p[f"myolo_mask_conv{i}/bias"], self.bn_scale[i - 1],
                        self.bn_shift[i - 1], C.ACT_RELU, pfw, pfb, None, st)
                 self._mask_fused[i] = True
@@ -525,7 +541,7 @@ class Engine:
                 b = self.bn["myolo_mask_bn1"]
                 C.call("myolo_bn_stats", self.my[1].view(), b.mean, b.var, self.ws, st)
                 self._bn_touched.append((b, npix))
-                C.call("myolo_bn_apply_h", self.my[1].view(), self.ma[1].view(), self.mah[1].view(), b.mean, b.var, b.gamma,
+                C.call("myolo_bn_apply_h", self.my[1].view(), None, self.mah[1].view(), b.mean, b.var, b.gamma,
                        b.beta, BN_EPS, C.ACT_RELU, st)
         if C.lib().myolo_deconv_mask_fwd_supported(MASK_C, self.NC):
             ids = self.target_ids if self.mode == "training" else None
@@ -642,10 +658,62 @@ class Engine:
         self._bn_bwd("conv1_bn", self._v(A["y0"]), C.view(gx, B, H0, H0, 32), relu6, True)
         C.call("myolo_conv1_wgrad", self._image, gx, self.g["conv1/kernel"], B, S, 32, st)
 
+    def _backward_mask_h16(self):
+        """Backward of the mask head on tcgen05 kind::f16.  The gradient tensors are half, multiplied by the
+        power-of-two loss scale gs[0] (device scalar, from max|dlogit|); every parameter gradient and the two fp32
+        hand-overs -- d(a1) into the batch-statistics BN backward, d(x0) into the ROIAlign backward -- are un-scaled
+        by gs[1] where they are produced."""
+        A, st, n = self.A, self._st(), self.n_roi
+        P_ = self.cfg["POOL"]
+        pfw, pfb = P_ + 1, (P_ + 1) * (P_ + 1)
+        M = self.mah[0].M
+        if self._mask_fused[1]:
+            raise C.MyoloError("backward needs the forward pass of the same step in the learning phase (batch-statistics bn1)")
+        gs, ugs = self.gs, self.gs[1:]
+        sh3 = self._shift_cache[("h16", P_)]
+        shn = self._neg_shifts
+        C.call("myolo_grad_scale", A["dlogit"], A["dlogit"].numel(), gs, st)
+        C.call("myolo_mask_out_bwd_h", self.y4d.rows, self.p["myolo_mask_deconv/bias"], self.p["myolo_mask/kernel"],
+               A["dlogit"], self.dy4h.rows, self.g["myolo_mask/kernel"], self.g["myolo_mask/bias"],
+               self.g["myolo_mask_deconv/bias"], n, P_, P_, MASK_C, self.NC, gs, st)
+        C.call("myolo_gemm_taps_wgrad_h", self.mah[4].rows, MASK_C, self.dy4h.rows, 4 * MASK_C, self.g["myolo_mask_deconv/kernel"],
+               M, 4 * MASK_C, MASK_C, 1, None, 1, ugs, st)
+        g0, g1 = self.mgh
+
+        def dgrad_bn(src_rows, lda, name, dst_rows, K, ntaps, shifts, layer):
+            b = self.bn[f"myolo_mask_bn{layer}"]
+            C.call("myolo_gemm_taps_bnbwd_h", src_rows, lda, self.wth_d[name], None, dst_rows, MASK_C, M, MASK_C, K, ntaps, shifts,
+                   pfw, pfb, self.mah[layer].rows, b.gamma, b.beta, b.mvar, BN_EPS, C.ACT_RELU, b.dgamma, b.dbeta,
+                   self.g[f"myolo_mask_conv{layer}/bias"], self.ws, ugs, st)
+
+        dgrad_bn(self.dy4h.rows, 4 * MASK_C, "myolo_mask_deconv/kernel", g0.rows, 4 * MASK_C, 1, None, 4)
+        for i in (4, 3, 2):
+            name = f"myolo_mask_conv{i}/kernel"
+            C.call("myolo_gemm_taps_wgrad_h", self.mah[i - 1].rows, MASK_C, g0.rows, MASK_C, self.g[name], M, MASK_C, MASK_C, 9,
+                   sh3, 0, ugs, st)
+            if i > 2:
+                dgrad_bn(g0.rows, MASK_C, name, g1.rows, MASK_C, 9, shn, i - 1)
+                g0, g1 = g1, g0
+        # d(a1), un-scaled fp32 -> batch-statistics BN backward -> d(pre-BN conv1) as scaled half
+        C.call("myolo_gemm_taps_h", g0.rows, MASK_C, self.wth_d["myolo_mask_conv2/kernel"], self.mg[0].rows, MASK_C, None, 0, M,
+               MASK_C, MASK_C, 9, shn, None, None, None, C.ACT_NONE, pfw, pfb, ugs, st)
+        b = self.bn["myolo_mask_bn1"]
+        C.call("myolo_bn_bwd_h", self.my[1].view(), self.mg[0].view(), g1.view(), b.mean, b.var, b.gamma, b.beta, BN_EPS,
+               C.ACT_RELU, 1, b.dgamma, b.dbeta, self.ws, gs, st)
+        name = "myolo_mask_conv1/kernel"
+        C.call("myolo_gemm_taps_wgrad_h", self.mah[0].rows, MASK_C, g1.rows, MASK_C, self.g[name], M, MASK_C, MASK_C, 9, sh3, 0,
+               ugs, st)
+        C.call("myolo_gemm_taps_h", g1.rows, MASK_C, self.wth_d[name], self.mg[1].rows, MASK_C, None, 0, M, MASK_C, MASK_C, 9,
+               shn, None, None, None, C.ACT_NONE, pfw, pfb, ugs, st)
+        return self.mg[1]
+
     def _backward_mask(self):
         A, st, n = self.A, self._st(), self.n_roi
         P_, B, F_ = self.cfg["POOL"], self.B, self.F
         pfw, pfb = P_ + 1, (P_ + 1) * (P_ + 1)
+        if self.h16:
+            g0 = self._backward_mask_h16()
+            return self._backward_feature_map(g0)
         a4 = self.ma[4]
         C.call("myolo_mask_out_bwd", self.y4d.rows, self.p["myolo_mask_deconv/bias"], self.p["myolo_mask/kernel"],
                A["dlogit"], self.dy4d.rows, self.g["myolo_mask/kernel"], self.g["myolo_mask/bias"],
@@ -689,6 +757,12 @@ class Engine:
             bn_done = i >= 2 and fusable(i - 1)
             dgrad(g0.rows, MASK_C, self.p[f"myolo_mask_conv{i}/kernel"], g1.rows, MASK_C, 9, shn, (i - 1) if bn_done else 0)
             g0, g1 = g1, g0
+        self._backward_feature_map(g0)
+
+    def _backward_feature_map(self, g0):
+        """d(x0) -> CropAndResizeGradImage -> feature_map conv backward (model.py:848, 385-387)."""
+        A, st, n = self.A, self._st(), self.n_roi
+        P_, B, F_ = self.cfg["POOL"], self.B, self.F
         # CropAndResizeGradImage into the feature-map gradient
         self.dfeat.storage.zero_()
         C.call("myolo_roialign_bwd", g0.view(), A["rois"], n, self.R, P_, self.dfeat.view(), st)

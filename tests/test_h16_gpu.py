@@ -213,3 +213,84 @@ def test_roialign_and_bn_half_outputs(C):
     C.call("myolo_bn_apply_h", x.view(), y32.view(), yh.view(), mean, var, gamma, beta, 1e-3, C.ACT_RELU, stream())
     assert torch.equal(yh.rows, y_ref.rows.half())
     assert torch.equal(y32.rows, y_ref.rows.half().float())
+
+
+@pytest.mark.parametrize("n,H,W,K,N,taps", [(40, 14, 14, 256, 256, 9), (300, 14, 14, 256, 256, 9), (23, 7, 9, 64, 128, 9),
+                                            (37, 14, 14, 256, 1024, 1), (11, 14, 14, 128, 64, 9)])
+def test_wgrad_half_operands(C, n, H, W, K, N, taps):
+    """filter gradient with both operands MN-major half (kind::f16) vs the exact CUDA-core kernel on the same
+    half-representable tensors; the gradient operand carries a loss scale that out_scale removes."""
+    from myolo.pf import PF, conv3x3_shifts
+    torch.manual_seed(40)
+    S = 32.0
+    a = PF(n, H, W, K)
+    a.valid().copy_(hq(torch.randn(n, H, W, K, device="cuda")))
+    d = PF(n, H, W, N)
+    d.valid().copy_(hq(torch.randn(n, H, W, N, device="cuda") * 0.1))
+    sh = C.int_array(conv3x3_shifts(W)) if taps == 9 else None
+    M = a.M
+    for tr in ((0, 1) if taps == 1 else (0,)):
+        ref = torch.zeros(taps * K * N, device="cuda")
+        C.call("myolo_gemm_taps_wgrad_ffma", a.rows, K, d.rows, N, ref, M, N, K, taps, sh, tr, stream())
+        ah = half_pf(a)
+        dh = PF(n, H, W, N, dtype=torch.float16)
+        dh.rows.copy_(d.rows * S)
+        out = torch.zeros(taps * K * N, device="cuda")
+        assert C.lib().myolo_gemm_taps_wgrad_h_supported(K, N, M, N, K, taps) == 1
+        unscale = torch.tensor([1.0 / S], device="cuda")
+        C.call("myolo_gemm_taps_wgrad_h", ah.rows, K, dh.rows, N, out, M, N, K, taps, sh, tr, unscale, stream())
+        torch.cuda.synchronize()
+        close(out, ref, 3e-5, f"half-operand wgrad (transpose_out={tr})")
+
+
+def test_mask_out_bwd_half_and_grad_scale(C):
+    from myolo.pf import PF
+    torch.manual_seed(41)
+    n, H, W, Cm, NC = 21, 14, 14, 256, 4
+    y4 = PF(n, H, W, 4 * Cm)
+    y4.valid().normal_()
+    bd, w1 = torch.randn(Cm, device="cuda") * 0.1, torch.randn(Cm, NC, device="cuda") / Cm ** 0.5
+    dlogit = torch.zeros(n, 2 * H, 2 * W, NC, device="cuda")
+    for r, k in ((0, 1), (7, 3), (20, 2)):
+        dlogit[r, :, :, k] = torch.randn(2 * H, 2 * W, device="cuda") * 3e-5
+    gs = torch.tensor([1.0, 1.0, 0.0, 0.0], device="cuda")
+    C.call("myolo_grad_scale", dlogit, dlogit.numel(), gs, stream())
+    m = dlogit.abs().max().item()
+    S = gs[0].item()
+    assert 8.0 <= m * S < 16.0 and gs[1].item() == 1.0 / S and gs[2].item() == 0.0, (m, S)
+    import math
+    assert math.log2(S) == int(math.log2(S)), "the loss scale is a power of two"
+    ref = PF(n, H, W, 4 * Cm)
+    gr = [torch.zeros(Cm, NC, device="cuda"), torch.zeros(NC, device="cuda"), torch.zeros(Cm, device="cuda")]
+    C.call("myolo_mask_out_bwd", y4.rows, bd, w1, dlogit, ref.rows, gr[0], gr[1], gr[2], n, H, W, Cm, NC, stream())
+    outh = PF(n, H, W, 4 * Cm, dtype=torch.float16)
+    gh = [torch.zeros(Cm, NC, device="cuda"), torch.zeros(NC, device="cuda"), torch.zeros(Cm, device="cuda")]
+    C.call("myolo_mask_out_bwd_h", y4.rows, bd, w1, dlogit, outh.rows, gh[0], gh[1], gh[2], n, H, W, Cm, NC, gs, stream())
+    assert torch.equal(outh.rows, (ref.rows * S).half()), "dy4 = half(S * exact)"
+    for a, b in zip(gh, gr):
+        close(a, b, 1e-5, "unscaled parameter gradients of the mask tail")
+    # all-zero gradient -> S = 1
+    z = torch.zeros(1024, device="cuda")
+    C.call("myolo_grad_scale", z, 1024, gs, stream())
+    assert gs[0].item() == 1.0 and gs[1].item() == 1.0
+
+
+def test_bn_backward_half_output(C):
+    from myolo.pf import PF
+    torch.manual_seed(42)
+    n, P, Cc = 9, 14, 64
+    x, dy = PF(n, P, P, Cc), PF(n, P, P, Cc)
+    x.valid().normal_()
+    dy.valid().normal_()
+    gamma, beta = torch.rand(Cc, device="cuda") + 0.5, torch.randn(Cc, device="cuda") * 0.1
+    mean, var = torch.empty(Cc, device="cuda"), torch.empty(Cc, device="cuda")
+    ws = torch.zeros(4112, dtype=torch.float64, device="cuda")
+    C.call("myolo_bn_stats", x.view(), mean, var, ws, stream())
+    ref = PF(n, P, P, Cc)
+    dg_r, db_r, dg, db = (torch.empty(Cc, device="cuda") for _ in range(4))
+    C.call("myolo_bn_bwd", x.view(), dy.view(), ref.view(), mean, var, gamma, beta, 1e-3, C.ACT_RELU, 1, dg_r, db_r, ws, stream())
+    outh = PF(n, P, P, Cc, dtype=torch.float16)
+    sc = torch.tensor([128.0], device="cuda")
+    C.call("myolo_bn_bwd_h", x.view(), dy.view(), outh.view(), mean, var, gamma, beta, 1e-3, C.ACT_RELU, 1, dg, db, ws, sc, stream())
+    assert torch.equal(outh.rows, (ref.rows * 128.0).half())
+    assert torch.equal(dg, dg_r) and torch.equal(db, db_r)
