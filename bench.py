@@ -34,7 +34,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="per-GPU batch")
     ap.add_argument("--size", type=int, default=224)
-    ap.add_argument("--precision", default=os.environ.get("MYOLO_PRECISION", "tf32x3"))
+    ap.add_argument("--precision", default=os.environ.get("MYOLO_PRECISION", "h16"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()

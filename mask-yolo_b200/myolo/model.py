@@ -271,7 +271,7 @@ class MaskYOLO:
         self.model_dir = model_dir
         self.yolo_pretrain_dir = yolo_pretrain_dir
         self.yolo_trainable = yolo_trainable
-        self.precision = precision or os.environ.get("MYOLO_PRECISION", "tf32x3")
+        self.precision = precision or os.environ.get("MYOLO_PRECISION", "h16")
         self.device, self.seed = device, seed
         self.learning_rate = getattr(config, "LEARNING_RATE", 1e-3)
         self.allreduce = None                    # set by myolo.ddp.attach() for data-parallel training
