@@ -238,10 +238,12 @@ int myolo_bn_apply_h(const myolo_view* x, const myolo_view* y, const myolo_view*
  * parameter gradient is un-scaled where it is reduced (out_scale / grad_unscale = gs + 1), so the flat gradient
  * buffer, Adam and the all-reduce never see S. */
 int myolo_grad_scale(const float* g, long long n, float* gs, myolo_stream stream);
-/* myolo_mask_out_bwd with dy4 stored as half * (*gscale); dw1 / db1 / dbd are unscaled. */
+/* myolo_mask_out_bwd with dy4 stored as half * (*gscale); dw1 / db1 / dbd are unscaled.  target_ids (nullable):
+ * the ids myolo_mask_loss was called with -- rois with id <= 0 have an identically zero dlogit, so their rows are
+ * zero-filled without reading it. */
 int myolo_mask_out_bwd_h(const float* y4, const float* bd, const float* w1, const float* dlogit, void* dy4_half,
                          float* dw1, float* db1, float* dbd, int n_roi, int H, int W, int Cmid, int NC,
-                         const float* gscale, myolo_stream stream);
+                         const float* gscale, const int* target_ids, myolo_stream stream);
 /* myolo_gemm_taps_wgrad with half A [rows][K] and half D [rows][N] (both MN-major operands of tcgen05 kind::f16):
  * dW[t][k][n] += (*out_scale) * sum_m A[m + shift[t], k] * D[m, n]  (fp32 atomics; out_scale nullable = 1).
  * K % 64 == 0, N % 64 == 0, lda % 8 == 0, ldd % 8 == 0. */

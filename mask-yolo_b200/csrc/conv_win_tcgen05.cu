@@ -54,6 +54,22 @@ __host__ __device__ constexpr uint32_t win_smem(int nacc) {
 // finish the network in registers: h = relu(acc + bd), logits = h . w1 + b1, sigmoid, pixel-shuffled
 // store of NC floats.  The [rows, 4*256] deconv activation is written only for rows of POSITIVE rois
 // (the only rows the backward pass ever reads; nothing is skipped arithmetically).
+// x[c] = this lane's (row's) value of column c.  Returns, in lane l, the sum over the 32 rows of column l
+// (butterfly transpose-reduce: 31 shuffles, no shared memory).
+__device__ __forceinline__ float warp_colsum32(float (&x)[32], int lane) {
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) {
+    const bool up = (lane & w) != 0;
+#pragma unroll
+    for (int i = 0; i < w; ++i) {
+      const float send = up ? x[i] : x[i + w];
+      const float keep = up ? x[i + w] : x[i];
+      x[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+    }
+  }
+  return x[0];
+}
+
 struct MaskTail {
   const float* bd;    // [256] deconv bias
   const float* w1;    // [256][NC] 1x1 kernel
@@ -332,16 +348,89 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int mrow0 = tile * WBM + acc * 128 + q * 32;
         const long long m = (long long)mrow0 + lane;
         const bool valid = (m < M) && pf_valid(m, ep.pf_w1, ep.pf_blk);
+        // half flavour of the fused BN backward: the activation chunk of the NEXT 32 columns is fetched while the
+        // current one is processed (the global-load latency was the longest stall of this epilogue)
+        const uint4* arow_h0 = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(ep.bn_a_h) + (size_t)m * N + half * WBN);
+        uint4 ahc[4];
+        if (EL == 2 && ep.bn_a) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) ahc[j] = valid ? __ldg(arow_h0 + j) : make_uint4(0u, 0u, 0u, 0u);
+        }
 #pragma unroll 1
         for (int c0 = 0; c0 < WBN; c0 += 32, ++nst) {
           float v[32];
           tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ts * TSTRIDE + (uint32_t)(acc * WBN + c0), v);
           const uint32_t sbuf = sbuf0;
+          const int n0 = half * WBN + c0;
+          if (EL == 2 && ep.bn_a) {
+            // ---- fused BN(+ReLU) backward on half tensors, register-only: v = d(a) of this thread's row (loss-scaled)
+            uint4 ahn[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              ahn[j] = (valid && c0 + 32 < WBN) ? __ldg(arow_h0 + (c0 + 32) / 8 + j) : make_uint4(0u, 0u, 0u, 0u);
+            float tt[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 be, ig;
+              asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(be.x), "=f"(be.y), "=f"(be.z), "=f"(be.w) : "r"(evs + 4u * (N + n0 + 4 * j)));
+              asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(ig.x), "=f"(ig.y), "=f"(ig.z), "=f"(ig.w) : "r"(evs + 4u * (2 * N + n0 + 4 * j)));
+              const uint32_t w0 = (j & 1) ? ahc[j >> 1].z : ahc[j >> 1].x, w1 = (j & 1) ? ahc[j >> 1].w : ahc[j >> 1].y;
+              const float aa[4] = {h2f((uint16_t)(w0 & 0xffffu)), h2f((uint16_t)(w0 >> 16)), h2f((uint16_t)(w1 & 0xffffu)),
+                                   h2f((uint16_t)(w1 >> 16))};
+              const float bb[4] = {be.x, be.y, be.z, be.w}, gg[4] = {ig.x, ig.y, ig.z, ig.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                bool pass = valid;
+                if (actk == MYOLO_ACT_RELU) pass = pass && aa[e] > 0.f;
+                else if (actk == MYOLO_ACT_RELU6) pass = pass && aa[e] > 0.f && aa[e] < 6.f;
+                const float g = pass ? v[4 * j + e] : 0.f;
+                v[4 * j + e] = g;
+                tt[4 * j + e] = g * (aa[e] - bb[e]) * gg[e];
+              }
+            }
+            // stores first (they only need g), then the two column reductions, which destroy their inputs
+            uint32_t tt_pack[2][2];
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 sc;
+              asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(sc.x), "=f"(sc.y), "=f"(sc.z), "=f"(sc.w) : "r"(evs + 4u * (n0 + 4 * j)));
+              float o[4] = {v[4 * j] * sc.x, v[4 * j + 1] * sc.y, v[4 * j + 2] * sc.z, v[4 * j + 3] * sc.w};
+              if (st_h) {
+                const uint32_t p0 = pack_h2(o[0], o[1]), p1 = pack_h2(o[2], o[3]);
+                o[0] = h2f((uint16_t)(p0 & 0xffffu)); o[1] = h2f((uint16_t)(p0 >> 16));
+                o[2] = h2f((uint16_t)(p1 & 0xffffu)); o[3] = h2f((uint16_t)(p1 >> 16));
+                tt_pack[j & 1][0] = p0;
+                tt_pack[j & 1][1] = p1;
+                if (j & 1) {
+                  const uint32_t haddr = sbufh + (uint32_t)lane * 64u + (uint32_t)((((uint32_t)j >> 1) ^ (((uint32_t)lane >> 1) & 3u)) << 4);
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(haddr), "r"(tt_pack[0][0]), "r"(tt_pack[0][1]), "r"(p0), "r"(p1));
+                }
+              }
+              if (st_f32) {
+                const uint32_t addr = sbuf + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]));
+              }
+            }
+            const float s0 = warp_colsum32(v, lane);
+            const float s1 = warp_colsum32(tt, lane);
+            atomicAdd(colacc + n0 + lane, s0);
+            atomicAdd(colacc + 256 + n0 + lane, s1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ahc[j] = ahn[j];
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0 && mrow0 < M && !(dbg & 4)) {
+              if (st_f32) tma_store_2d(&tmC, sbuf, n0, mrow0);
+              if (st_h) tma_store_2d(&tmCh, sbufh, n0, mrow0);
+            }
+            continue;
+          }
           // the previous store must have finished reading the staging buffer (the shared memory a second
           // buffer would take is worth more as a fifth weight stage)
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           __syncwarp();
-          const int n0 = half * WBN + c0;
           if (ep.bn_a) {
             // ---- fused BN(+ReLU) backward.  v = d(a) for this thread's row; a is read in place.
             const uint32_t sbuf2 = sbuf + 4u * 4096u;

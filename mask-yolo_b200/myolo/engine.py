@@ -675,7 +675,7 @@ class Engine:
         C.call("myolo_grad_scale", A["dlogit"], A["dlogit"].numel(), gs, st)
         C.call("myolo_mask_out_bwd_h", self.y4d.rows, self.p["myolo_mask_deconv/bias"], self.p["myolo_mask/kernel"],
                A["dlogit"], self.dy4h.rows, self.g["myolo_mask/kernel"], self.g["myolo_mask/bias"],
-               self.g["myolo_mask_deconv/bias"], n, P_, P_, MASK_C, self.NC, gs, st)
+               self.g["myolo_mask_deconv/bias"], n, P_, P_, MASK_C, self.NC, gs, self.target_ids, st)
         C.call("myolo_gemm_taps_wgrad_h", self.mah[4].rows, MASK_C, self.dy4h.rows, 4 * MASK_C, self.g["myolo_mask_deconv/kernel"],
                M, 4 * MASK_C, MASK_C, 1, None, 1, ugs, st)
         g0, g1 = self.mgh

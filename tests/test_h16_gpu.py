@@ -265,10 +265,20 @@ def test_mask_out_bwd_half_and_grad_scale(C):
     C.call("myolo_mask_out_bwd", y4.rows, bd, w1, dlogit, ref.rows, gr[0], gr[1], gr[2], n, H, W, Cm, NC, stream())
     outh = PF(n, H, W, 4 * Cm, dtype=torch.float16)
     gh = [torch.zeros(Cm, NC, device="cuda"), torch.zeros(NC, device="cuda"), torch.zeros(Cm, device="cuda")]
-    C.call("myolo_mask_out_bwd_h", y4.rows, bd, w1, dlogit, outh.rows, gh[0], gh[1], gh[2], n, H, W, Cm, NC, gs, stream())
+    C.call("myolo_mask_out_bwd_h", y4.rows, bd, w1, dlogit, outh.rows, gh[0], gh[1], gh[2], n, H, W, Cm, NC, gs, None, stream())
     assert torch.equal(outh.rows, (ref.rows * S).half()), "dy4 = half(S * exact)"
     for a, b in zip(gh, gr):
         close(a, b, 1e-5, "unscaled parameter gradients of the mask tail")
+    # with the target ids: non-positive rois are zero-filled without reading dlogit
+    ids = torch.zeros(n, dtype=torch.int32, device="cuda")
+    ids[[0, 7, 20]] = torch.tensor([1, 3, 2], dtype=torch.int32, device="cuda")
+    outh2 = PF(n, H, W, 4 * Cm, dtype=torch.float16)
+    outh2.valid().fill_(7.0)
+    gh2 = [torch.zeros(Cm, NC, device="cuda"), torch.zeros(NC, device="cuda"), torch.zeros(Cm, device="cuda")]
+    C.call("myolo_mask_out_bwd_h", y4.rows, bd, w1, dlogit, outh2.rows, gh2[0], gh2[1], gh2[2], n, H, W, Cm, NC, gs, ids, stream())
+    assert torch.equal(outh2.rows, outh.rows)
+    for a, b in zip(gh2, gh):
+        close(a, b, 1e-6, "same parameter gradients with the id fast path")
     # all-zero gradient -> S = 1
     z = torch.zeros(1024, device="cuda")
     C.call("myolo_grad_scale", z, 1024, gs, stream())
