@@ -80,6 +80,69 @@ struct MaskTail {
   int H, W, NC;
 };
 
+// One 32-column chunk of the mask tail for this thread's row: v = raw deconv accumulators -> (positive rois) y4 store,
+// h = relu(v + bd), lg[k][.] += h . w1[:, k].  NCT is a compile-time class count so the 2*NCT accumulation chains of a
+// 4-channel group are independent and interleave (with one warp per scheduler the FMA latency is otherwise exposed:
+// the two-chain form of this loop ran at 0.18 IPC).
+//
+// (Tried and rejected, measured on B200: the constants in __constant__ memory with compile-time offsets -- ptxas turns
+// them into LDCU.128 + uniform-register FFMA operands, 1.08 -> 1.46 ms; and the eight chunks of a row fully unrolled --
+// 38 KB of straight-line code per class count, 1.08 -> 2.1 ms.  The chunk loop stays rolled.)
+template <int NCT>
+__device__ __forceinline__ void mask_tail_chunk(float (&v)[32], uint32_t evs, int C0, float* ypos, float (&lg)[8][2]) {
+  if (ypos) {
+    float4* yp = reinterpret_cast<float4*>(ypos + C0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) yp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  }
+  {
+    float4 b4[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b4[j].x), "=f"(b4[j].y), "=f"(b4[j].z), "=f"(b4[j].w) : "r"(evs + 4u * (C0 + 4 * j)));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[4 * j] = fmaxf(v[4 * j] + b4[j].x, 0.f);
+      v[4 * j + 1] = fmaxf(v[4 * j + 1] + b4[j].y, 0.f);
+      v[4 * j + 2] = fmaxf(v[4 * j + 2] + b4[j].z, 0.f);
+      v[4 * j + 3] = fmaxf(v[4 * j + 3] + b4[j].w, 0.f);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float4 w[NCT];
+#pragma unroll
+    for (int k = 0; k < NCT; ++k)
+      asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(w[k].x), "=f"(w[k].y), "=f"(w[k].z), "=f"(w[k].w) : "r"(evs + 4u * (256 + k * 256 + C0 + 4 * j)));
+#pragma unroll
+    for (int k = 0; k < NCT; ++k) {
+      float a = lg[k][j & 1];
+      a = fmaf(v[4 * j], w[k].x, a);
+      a = fmaf(v[4 * j + 1], w[k].y, a);
+      a = fmaf(v[4 * j + 2], w[k].z, a);
+      a = fmaf(v[4 * j + 3], w[k].w, a);
+      lg[k][j & 1] = a;
+    }
+  }
+}
+
+// all 256 columns of one accumulator row; the TMEM load of the next chunk is in flight while a chunk is processed
+template <int NCT>
+__device__ __forceinline__ void mask_tail_row(uint32_t taddr, uint32_t evs, float* ypos, float (&lg)[8][2]) {
+  float va[32], vb[32];
+  tmem_ld32_issue(taddr, va);
+  tmem_ld_wait(va);
+#pragma unroll 1
+  for (int c0 = 0; c0 < 256; c0 += 64) {
+    tmem_ld32_issue(taddr + (uint32_t)(c0 + 32), vb);
+    mask_tail_chunk<NCT>(va, evs, c0, ypos, lg);
+    tmem_ld_wait(vb);
+    if (c0 + 64 < 256) tmem_ld32_issue(taddr + (uint32_t)(c0 + 64), va);
+    mask_tail_chunk<NCT>(vb, evs, c0 + 32, ypos, lg);
+    if (c0 + 64 < 256) tmem_ld_wait(va);
+  }
+}
+
 // CG = 2: the work item is shared by a CTA pair (cluster of two, cta_group::2): M = 256 rows per MMA, each
 // CTA holds 128 of them (its own activation window and TMEM accumulator) and HALF of every weight stage,
 // which halves the L2->SM fill per FLOP -- the limiter of the single-CTA variant (measured: 1.27 ms with
@@ -283,55 +346,20 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             ww = r % ep.pf_w1 - 1;
             pos = mt.ids && __ldg(mt.ids + roi) > 0;
           }
-          float lg[8];
+          float lg[8][2];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) lg[k] = 0.f;
-#pragma unroll 1
-          for (int c0 = 0; c0 < 256; c0 += 32) {
-            float v[32];
-            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ts * TSTRIDE + (uint32_t)(acc * 256 + c0), v);
-            if (pos) {
-              float4* yp = reinterpret_cast<float4*>(mt.y4 + (size_t)m * N + half * 256 + c0);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) yp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            }
-            // h = relu(acc + bd): the 8 bias vectors are fetched as one batch of independent LDS.128 ...
-            {
-              float4 b4[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b4[j].x), "=f"(b4[j].y), "=f"(b4[j].z), "=f"(b4[j].w) : "r"(evs + 4u * (c0 + 4 * j)));
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                v[4 * j] = fmaxf(v[4 * j] + b4[j].x, 0.f);
-                v[4 * j + 1] = fmaxf(v[4 * j + 1] + b4[j].y, 0.f);
-                v[4 * j + 2] = fmaxf(v[4 * j + 2] + b4[j].z, 0.f);
-                v[4 * j + 3] = fmaxf(v[4 * j + 3] + b4[j].w, 0.f);
-              }
-            }
-            // ... and so are the 32 weights of each class (the one-load-then-four-FMAs form of this loop was
-            // bound by shared-memory latency: 62 % of the kernel's stall samples)
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              if (k < mt.NC) {
-                float4 w4[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(w4[j].x), "=f"(w4[j].y), "=f"(w4[j].z), "=f"(w4[j].w) : "r"(evs + 4u * (256 + k * 256 + c0 + 4 * j)));
-                float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-                for (int j = 0; j < 8; j += 2) {
-                  s0 = fmaf(v[4 * j], w4[j].x, s0);
-                  s0 = fmaf(v[4 * j + 1], w4[j].y, s0);
-                  s0 = fmaf(v[4 * j + 2], w4[j].z, s0);
-                  s0 = fmaf(v[4 * j + 3], w4[j].w, s0);
-                  s1 = fmaf(v[4 * j + 4], w4[j + 1].x, s1);
-                  s1 = fmaf(v[4 * j + 5], w4[j + 1].y, s1);
-                  s1 = fmaf(v[4 * j + 6], w4[j + 1].z, s1);
-                  s1 = fmaf(v[4 * j + 7], w4[j + 1].w, s1);
-                }
-                lg[k] += s0 + s1;
-              }
+          for (int k = 0; k < 8; ++k) lg[k][0] = lg[k][1] = 0.f;
+          {
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + ts * TSTRIDE + (uint32_t)(acc * 256);
+            float* ypos = pos ? mt.y4 + (size_t)m * N + half * 256 : nullptr;
+            switch (mt.NC) {
+              case 1: mask_tail_row<1>(taddr, evs, ypos, lg); break;
+              case 2: mask_tail_row<2>(taddr, evs, ypos, lg); break;
+              case 3: mask_tail_row<3>(taddr, evs, ypos, lg); break;
+              case 4: mask_tail_row<4>(taddr, evs, ypos, lg); break;
+              case 5: mask_tail_row<5>(taddr, evs, ypos, lg); break;
+              case 6: mask_tail_row<6>(taddr, evs, ypos, lg); break;
+              default: mask_tail_row<7>(taddr, evs, ypos, lg); break;
             }
           }
           if (valid) {
@@ -339,7 +367,7 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             float* out = mt.masks + ((((size_t)roi * 2 * mt.H + 2 * hh + a) * 2 * mt.W) + 2 * ww + b) * mt.NC;
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-              if (k < mt.NC) out[k] = 1.f / (1.f + expf(-(lg[k] + __ldg(mt.b1 + k))));
+              if (k < mt.NC) out[k] = 1.f / (1.f + expf(-(lg[k][0] + lg[k][1] + __ldg(mt.b1 + k))));
           }
         }
       } else
@@ -368,16 +396,15 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               ahn[j] = (valid && c0 + 32 < WBN) ? __ldg(arow_h0 + (c0 + 32) / 8 + j) : make_uint4(0u, 0u, 0u, 0u);
+            // per element only g = d(a)*act'(a) and g*a: the per-column constants of dgamma = sum g*(a-beta)/gamma are
+            // applied AFTER the column reduction, where lane = column (every broadcast constant load costs a full
+            // shared-memory wavefront per lane-row, and this epilogue was bound by them)
             float tt[32];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              float4 be, ig;
-              asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(be.x), "=f"(be.y), "=f"(be.z), "=f"(be.w) : "r"(evs + 4u * (N + n0 + 4 * j)));
-              asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(ig.x), "=f"(ig.y), "=f"(ig.z), "=f"(ig.w) : "r"(evs + 4u * (2 * N + n0 + 4 * j)));
               const uint32_t w0 = (j & 1) ? ahc[j >> 1].z : ahc[j >> 1].x, w1 = (j & 1) ? ahc[j >> 1].w : ahc[j >> 1].y;
               const float aa[4] = {h2f((uint16_t)(w0 & 0xffffu)), h2f((uint16_t)(w0 >> 16)), h2f((uint16_t)(w1 & 0xffffu)),
                                    h2f((uint16_t)(w1 >> 16))};
-              const float bb[4] = {be.x, be.y, be.z, be.w}, gg[4] = {ig.x, ig.y, ig.z, ig.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 bool pass = valid;
@@ -385,7 +412,7 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 else if (actk == MYOLO_ACT_RELU6) pass = pass && aa[e] > 0.f && aa[e] < 6.f;
                 const float g = pass ? v[4 * j + e] : 0.f;
                 v[4 * j + e] = g;
-                tt[4 * j + e] = g * (aa[e] - bb[e]) * gg[e];
+                tt[4 * j + e] = g * aa[e];
               }
             }
             // stores first (they only need g), then the two column reductions, which destroy their inputs
@@ -414,7 +441,7 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               }
             }
             const float s0 = warp_colsum32(v, lane);
-            const float s1 = warp_colsum32(tt, lane);
+            const float s1 = (warp_colsum32(tt, lane) - evec[N + n0 + lane] * s0) * evec[2 * N + n0 + lane];
             atomicAdd(colacc + n0 + lane, s0);
             atomicAdd(colacc + 256 + n0 + lane, s1);
 #pragma unroll

@@ -38,11 +38,11 @@ mask_out_fwd_kernel(const float* __restrict__ y4, const float* __restrict__ bd, 
     bq[j] = (j < nq) ? __ldg(reinterpret_cast<const float4*>(bd) + j * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
   for (long long it = warp; it < items; it += nwarps) {
     const int ab = (int)(it & 3);
-    long long t = it >> 2;
-    const int w = (int)(t % W);
-    t /= W;
-    const int h = (int)(t % H);
-    const int n = (int)(t / H);
+    const unsigned t = (unsigned)(it >> 2);      // pixel index < 2^31 (checked by the host side): 32-bit div/mod
+    const unsigned t2 = t / (unsigned)W;
+    const int w = (int)(t - t2 * (unsigned)W);
+    const int n = (int)(t2 / (unsigned)H);
+    const int h = (int)(t2 - (unsigned)n * (unsigned)H);
     const size_t row = (size_t)pf_row(n, h, w, H, W);
     const float4* src = reinterpret_cast<const float4*>(y4 + row * (size_t)(4 * Cmid) + (size_t)ab * Cmid);
     float v[8];
@@ -118,11 +118,11 @@ mask_out_bwd_kernel(const float* __restrict__ y4, const float* __restrict__ bd, 
   const float gs = (HALF && gscale) ? __ldg(gscale) : 1.f;
   for (long long it = warp; it < items; it += nwarps) {
     const int ab = (int)(it & 3);
-    long long t = it >> 2;
-    const int w = (int)(t % W);
-    t /= W;
-    const int h = (int)(t % H);
-    const int n = (int)(t / H);
+    const unsigned t = (unsigned)(it >> 2);      // pixel index < 2^31 (checked by the host side): 32-bit div/mod
+    const unsigned t2 = t / (unsigned)W;
+    const int w = (int)(t - t2 * (unsigned)W);
+    const int n = (int)(t2 / (unsigned)H);
+    const int h = (int)(t2 - (unsigned)n * (unsigned)H);
     const size_t row = (size_t)pf_row(n, h, w, H, W);
     const size_t off = row * (size_t)(4 * Cmid) + (size_t)ab * Cmid;
     if (HALF && ids && __ldg(ids + n) <= 0) {
@@ -251,7 +251,7 @@ using namespace myolo;
 extern "C" int myolo_mask_out_fwd(const float* y4, const float* bd, const float* w1, const float* b1, float* masks,
                                   int n_roi, int H, int W, int Cmid, int NC, myolo_stream stream) {
   MYOLO_CHECK_ARG(y4 && bd && w1 && b1 && masks && n_roi > 0 && H > 0 && W > 0 && NC > 0);
-  MYOLO_CHECK_ARG(Cmid > 0 && (Cmid % 128) == 0 && Cmid <= kMaxCmid);
+  MYOLO_CHECK_ARG(Cmid > 0 && (Cmid % 128) == 0 && Cmid <= kMaxCmid && (long long)n_roi * H * W < (1LL << 31));
   const size_t smem = (size_t)(Cmid * NC + NC) * sizeof(float);
   MYOLO_CHECK_ARG(smem <= 200 * 1024);
   if (smem > 48 * 1024) MYOLO_CUDA(cudaFuncSetAttribute(mask_out_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -266,7 +266,7 @@ extern "C" int myolo_mask_out_bwd(const float* y4, const float* bd, const float*
                                   float* dw1, float* db1, float* dbd, int n_roi, int H, int W, int Cmid, int NC,
                                   myolo_stream stream) {
   MYOLO_CHECK_ARG(y4 && bd && w1 && dlogit && dy4 && dw1 && db1 && dbd && n_roi > 0 && H > 0 && W > 0 && NC > 0);
-  MYOLO_CHECK_ARG(Cmid > 0 && (Cmid % 128) == 0 && Cmid <= kMaxCmid);
+  MYOLO_CHECK_ARG(Cmid > 0 && (Cmid % 128) == 0 && Cmid <= kMaxCmid && (long long)n_roi * H * W < (1LL << 31));
   const size_t smem = (size_t)(2 * Cmid * NC + NC) * sizeof(float);
   MYOLO_CHECK_ARG(smem <= 200 * 1024);
   if (smem > 48 * 1024) MYOLO_CUDA(cudaFuncSetAttribute(mask_out_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -282,7 +282,8 @@ extern "C" int myolo_mask_out_bwd_h(const float* y4, const float* bd, const floa
                                     float* dw1, float* db1, float* dbd, int n_roi, int H, int W, int Cmid, int NC,
                                     const float* gscale, const int* target_ids, myolo_stream stream) {
   MYOLO_CHECK_ARG(y4 && bd && w1 && dlogit && dy4_half && dw1 && db1 && dbd && n_roi > 0 && H > 0 && W > 0 && NC > 0);
-  MYOLO_CHECK_ARG(Cmid > 0 && (Cmid % 128) == 0 && Cmid <= kMaxCmid && ((uintptr_t)dy4_half & 7) == 0);
+  MYOLO_CHECK_ARG(Cmid > 0 && (Cmid % 128) == 0 && Cmid <= kMaxCmid && ((uintptr_t)dy4_half & 7) == 0 &&
+                  (long long)n_roi * H * W < (1LL << 31));
   const size_t smem = (size_t)(2 * Cmid * NC + NC) * sizeof(float);
   MYOLO_CHECK_ARG(smem <= 200 * 1024);
   if (smem > 48 * 1024) MYOLO_CUDA(cudaFuncSetAttribute(mask_out_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

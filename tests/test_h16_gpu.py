@@ -278,7 +278,7 @@ def test_mask_out_bwd_half_and_grad_scale(C):
     C.call("myolo_mask_out_bwd_h", y4.rows, bd, w1, dlogit, outh2.rows, gh2[0], gh2[1], gh2[2], n, H, W, Cm, NC, gs, ids, stream())
     assert torch.equal(outh2.rows, outh.rows)
     for a, b in zip(gh2, gh):
-        close(a, b, 1e-6, "same parameter gradients with the id fast path")
+        close(a, b, 1e-5, "same parameter gradients with the id fast path")
     # all-zero gradient -> S = 1
     z = torch.zeros(1024, device="cuda")
     C.call("myolo_grad_scale", z, 1024, gs, stream())
