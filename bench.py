@@ -244,7 +244,8 @@ def main():
         ach = flops / (avg_ms * 1e-3) / 1e12
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("mask_conv_fwd_dram_bytes_per_launch")
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(
+                "mask_conv_fwd_h16_dram_bytes_per_launch" if args.precision == "h16" else "mask_conv_fwd_dram_bytes_per_launch")
         except Exception:
             pass
         h16 = args.precision == "h16"

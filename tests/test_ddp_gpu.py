@@ -35,7 +35,7 @@ def _worker(rank, world, port, q):
     P = init_params(c["NB"], c["NC"], 5 + rank, "trained_like")         # different weights per rank: broadcast must fix it
     img = torch.rand(2, 96, 96, 3, generator=torch.Generator().manual_seed(40 + rank))
     inputs = Hh.to_device(Hh.batch_from_boxes(c, 2, img, Hh.random_boxes(2, 2, 50 + rank), 60 + rank), f"cuda:{rank}")
-    eng = Engine(c, 2, "training", "tf32x3", device=rank, params=P)
+    eng = Engine(c, 2, "training", "h16", device=rank, params=P)
 
     class M:        # the attribute surface ddp.attach needs
         engine = eng
