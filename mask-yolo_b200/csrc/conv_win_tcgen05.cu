@@ -320,8 +320,20 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   } else {
     const int q = warp & 3;
     const uint32_t sbuf0 = stg0 + (uint32_t)q * 4096u;
-    const uint32_t sbufh = stgh0 + (uint32_t)q * 2048u;
+    const uint32_t sbufh0 = stgh0 + (uint32_t)q * 2048u;
     const bool st_f32 = !(EL == 2 && ep.no_f32), st_h = EL == 2 && ep.has_h;
+    // half-operand kernels with ONE output keep a ring of staging tiles in the space the other output's tiles would
+    // take (four 2 KB half tiles, or two 4 KB fp32 tiles), so a chunk no longer waits for the previous chunk's TMA
+    // store to finish reading shared memory (8 serialised store latencies per item were as long as the main loop)
+    const bool ring_h = EL == 2 && st_h && !st_f32, ring_f = EL == 2 && st_f32 && !st_h;
+    auto wait_store = [&]() {
+      if (lane == 0) {
+        if (ring_h) asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+        else if (ring_f) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
+      __syncwarp();
+    };
     const uint32_t evs = smem_u32(evec);
     const int actk = ep.act & 0xff;
     const bool rnd = (ep.act & MYOLO_ROUND_TF32) != 0;
@@ -388,7 +400,8 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int c0 = 0; c0 < WBN; c0 += 32, ++nst) {
           float v[32];
           tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ts * TSTRIDE + (uint32_t)(acc * WBN + c0), v);
-          const uint32_t sbuf = sbuf0;
+          const uint32_t sbuf = ring_f ? sbuf0 + (nst & 1u) * (4u * 4096u) : sbuf0;
+          const uint32_t sbufh = ring_h ? sbuf0 + ((nst >> 1) & 1u) * (4u * 4096u) + (nst & 1u) * 2048u : sbufh0;
           const int n0 = half * WBN + c0;
           if (EL == 2 && ep.bn_a) {
             // ---- fused BN(+ReLU) backward on half tensors, register-only: v = d(a) of this thread's row (loss-scaled)
@@ -417,8 +430,7 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
             // stores first (they only need g), then the two column reductions, which destroy their inputs
             uint32_t tt_pack[2][2];
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            __syncwarp();
+            wait_store();
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               float4 sc;
@@ -448,16 +460,19 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             for (int j = 0; j < 4; ++j) ahc[j] = ahn[j];
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane == 0 && mrow0 < M && !(dbg & 4)) {
-              if (st_f32) tma_store_2d(&tmC, sbuf, n0, mrow0);
-              if (st_h) tma_store_2d(&tmCh, sbufh, n0, mrow0);
+            if (lane == 0) {
+              if (mrow0 < M && !(dbg & 4)) {
+                if (st_f32) tma_store_2d(&tmC, sbuf, n0, mrow0);
+                if (st_h) tma_store_2d(&tmCh, sbufh, n0, mrow0);
+              } else if (ring_h || ring_f) {
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              }
             }
             continue;
           }
           // the previous store must have finished reading the staging buffer (the shared memory a second
           // buffer would take is worth more as a fifth weight stage)
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          __syncwarp();
+          wait_store();
           if (ep.bn_a) {
             // ---- fused BN(+ReLU) backward.  v = d(a) for this thread's row; a is read in place.
             const uint32_t sbuf2 = sbuf + 4u * 4096u;
@@ -553,9 +568,13 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
-          if (lane == 0 && mrow0 < M && !(dbg & 4)) {
-            if (st_f32) tma_store_2d(&tmC, sbuf, n0, mrow0);
-            if (st_h) tma_store_2d(&tmCh, sbufh, n0, mrow0);
+          if (lane == 0) {
+            if (mrow0 < M && !(dbg & 4)) {
+              if (st_f32) tma_store_2d(&tmC, sbuf, n0, mrow0);
+              if (st_h) tma_store_2d(&tmCh, sbufh, n0, mrow0);
+            } else if (ring_h || ring_f) {
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");   // keep one group per chunk: the rings count groups
+            }
           }
         }
       }

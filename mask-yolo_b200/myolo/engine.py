@@ -14,6 +14,7 @@ one NCCL all-reduce), keyed by the Keras variable names of the reference graph (
 from __future__ import annotations
 
 import math
+import os
 from collections import OrderedDict
 from typing import Dict, List, Optional
 
@@ -124,6 +125,10 @@ class Engine:
         self._shift_cache = {}
         self.inputs_ready = None       # optional CUDA event: inputs[1:] of forward_training are complete
         self.kernel_events = None      # bench.py: list collecting (start, end) CUDA events of the dominant kernel
+        # backbone backward: the two filter-gradient kernels of a block (pointwise wgrad, depthwise bwd_filter) run on a
+        # side stream next to the data-gradient chain (they are 20-70 us kernels that fill a fraction of the SMs)
+        self._side = torch.cuda.Stream(device=self.dev) if os.environ.get("MYOLO_BWD_STREAMS", "1") != "0" else None
+        self._evs = {}
         self.t = 0                     # Adam iteration
         self.seen = 0                  # yolo_custom_loss `seen` counter (model.py:95, 197)
         self._alloc_params(params if params is not None else init_params(self.NB, self.NC, seed))
@@ -626,12 +631,37 @@ class Engine:
             on_tail_ready()
         G, NB, NC = self.cfg["G"], self.NB, self.NC
         ny = NB * (5 + NC)
+        main, side = torch.cuda.current_stream(), self._side
+        sst = side.cuda_stream if side is not None else st
+
+        def ev(name):       # events are created once and re-recorded every step
+            e = self._evs.get(name)
+            if e is None:
+                e = self._evs[name] = torch.cuda.Event()
+            return e
+
+        def fork(name):     # the side stream may start once everything issued on main so far is done
+            if side is not None:
+                e = ev(name)
+                e.record(main)
+                side.wait_event(e)
+
+        def mark(name):     # remember the side stream's position
+            if side is not None:
+                ev(name).record(side)
+
+        def join(name):     # main waits for that position
+            if side is not None and name in self._evs:
+                main.wait_event(self._evs[name])
+
         # conv_23
         dy = A["dyolo"]
         C.call("myolo_colsum", self._v(dy), self.g["conv_23/bias"], self.ws, st)
-        C.call("myolo_pwconv_wgrad", A["ap14"], dy, self.g["conv_23/kernel"], B * G * G, 1024, ny, st)
+        fork("f23")           # also orders the side stream after grads.zero_()
+        C.call("myolo_pwconv_wgrad", A["ap14"], dy, self.g["conv_23/kernel"], B * G * G, 1024, ny, sst)
         gx, gy = self.gx, self.gy
         C.call("myolo_pwconv_dgrad", dy, self.p["conv_23/kernel"], gx, B * G * G, 1024, ny, st)
+        first = True
         for k, ci, co, s in reversed(BACKBONE_BLOCKS + YOLO_BLOCKS):
             Hi, Ho, _, _, _ = self.geo[k]
             npix = B * Ho * Ho
@@ -641,7 +671,12 @@ class Engine:
             d_ap = C.view(gx, B, Ho, Ho, co)
             self._bn_bwd(f"conv_pw_{k}_bn", self._v(A[f"yp{k}"]), d_ap, relu6, True)
             ad_hi = A[f"ad{k}"][0] if self.x3 else A[f"ad{k}"]
-            C.call("myolo_pwconv_wgrad", ad_hi, gx, self.g[f"conv_pw_{k}/kernel"], npix, ci, co, st)
+            fork("fw")
+            C.call("myolo_pwconv_wgrad", ad_hi, gx, self.g[f"conv_pw_{k}/kernel"], npix, ci, co, sst)      # reads gx
+            mark("w_done")
+            if not first:
+                join("f_done")          # the previous block's bwd_filter has finished reading gy
+            first = False
             C.call("myolo_pwconv_dgrad", gx, self.p[f"conv_pw_{k}/kernel"], gy, npix, ci, co, st)
             d_ad = C.view(gy, B, Ho, Ho, ci)
             self._bn_bwd(f"conv_dw_{k}_bn", self._v(A[f"yd{k}"]), d_ad, relu6, True)
@@ -651,12 +686,16 @@ class Engine:
                 xin = self.c4.view()
             else:
                 xin = self._v(A[f"ap{k - 1}"])
-            C.call("myolo_dwconv3x3_bwd_filter", xin, gy, self.g[f"conv_dw_{k}/depthwise_kernel"], s, st)
+            fork("ff")
+            C.call("myolo_dwconv3x3_bwd_filter", xin, gy, self.g[f"conv_dw_{k}/depthwise_kernel"], s, sst)  # reads gy
+            mark("f_done")
+            join("w_done")              # the pointwise wgrad has finished reading gx
             C.call("myolo_dwconv3x3_bwd_data", gy, self.p[f"conv_dw_{k}/depthwise_kernel"], gx, B, Hi, Hi, ci, s, st)
         S = self.cfg["S"]
         H0 = S // 2
         self._bn_bwd("conv1_bn", self._v(A["y0"]), C.view(gx, B, H0, H0, 32), relu6, True)
         C.call("myolo_conv1_wgrad", self._image, gx, self.g["conv1/kernel"], B, S, 32, st)
+        join("f_done")                  # every gradient is in the flat buffer once main passes this point
 
     def _backward_mask_h16(self):
         """Backward of the mask head on tcgen05 kind::f16.  The gradient tensors are half, multiplied by the
