@@ -240,10 +240,12 @@ int myolo_bn_apply_h(const myolo_view* x, const myolo_view* y, const myolo_view*
 int myolo_grad_scale(const float* g, long long n, float* gs, myolo_stream stream);
 /* myolo_mask_out_bwd with dy4 stored as half * (*gscale); dw1 / db1 / dbd are unscaled.  target_ids (nullable):
  * the ids myolo_mask_loss was called with -- rois with id <= 0 have an identically zero dlogit, so their rows are
- * zero-filled without reading it. */
+ * zero-filled without reading it.  prev_ids (nullable, int[n_roi], zero before the first call, owned by the dy4
+ * buffer): the ids of the call that last wrote dy4_half; rows that were not positive then are still zero and are not
+ * written again (the 2 GB zero fill per step was the whole cost of this kernel).  Updated to target_ids on return. */
 int myolo_mask_out_bwd_h(const float* y4, const float* bd, const float* w1, const float* dlogit, void* dy4_half,
                          float* dw1, float* db1, float* dbd, int n_roi, int H, int W, int Cmid, int NC,
-                         const float* gscale, const int* target_ids, myolo_stream stream);
+                         const float* gscale, const int* target_ids, int* prev_ids, myolo_stream stream);
 /* myolo_gemm_taps_wgrad with half A [rows][K] and half D [rows][N] (both MN-major operands of tcgen05 kind::f16):
  * dW[t][k][n] += (*out_scale) * sum_m A[m + shift[t], k] * D[m, n]  (fp32 atomics; out_scale nullable = 1).
  * K % 64 == 0, N % 64 == 0, lda % 8 == 0, ldd % 8 == 0. */

@@ -227,7 +227,7 @@ __device__ __forceinline__ float half_bits_to_float(uint32_t h) {
 // null, as fp32 holding the SAME half-rounded values (what the backward pass reads).
 __global__ void __launch_bounds__(256)
 bn_apply_h_kernel(V x, V y, V yh, const float* __restrict__ mean, const float* __restrict__ var,
-                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int act) {
+                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int act, int same_geo) {
   const int C4 = x.c >> 2;
   const FastDiv x_fc4 = x.fc4;
   const long long total = (long long)x.n * x.h * x.w * C4;
@@ -235,7 +235,8 @@ bn_apply_h_kernel(V x, V y, V yh, const float* __restrict__ mean, const float* _
     const uint32_t pp = fd_div((uint32_t)i, x_fc4);
     const int q = (int)((uint32_t)i - pp * (uint32_t)C4) * 4;
     const long long p = pp;
-    const float4 v = *reinterpret_cast<const float4*>(x.p + pix_off(x, p) + q);
+    const size_t xo = pix_off(x, p);
+    const float4 v = *reinterpret_cast<const float4*>(x.p + xo + q);
     const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + q));
     const float4 vv = __ldg(reinterpret_cast<const float4*>(var + q));
     const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + q));
@@ -246,9 +247,9 @@ bn_apply_h_kernel(V x, V y, V yh, const float* __restrict__ mean, const float* _
     o.z = apply_act(fmaf((v.z - mu.z) * (1.f / sqrtf(vv.z + eps)), ga.z, be.z), act & 0xff);
     o.w = apply_act(fmaf((v.w - mu.w) * (1.f / sqrtf(vv.w + eps)), ga.w, be.w), act & 0xff);
     const uint32_t p0 = pack_half2_sat(o.x, o.y), p1 = pack_half2_sat(o.z, o.w);
-    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(yh.p) + pix_off(yh, p) + q) = make_uint2(p0, p1);
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(yh.p) + (same_geo ? xo : pix_off(yh, p)) + q) = make_uint2(p0, p1);
     if (y.p)
-      *reinterpret_cast<float4*>(y.p + pix_off(y, p) + q) =
+      *reinterpret_cast<float4*>(y.p + (same_geo ? xo : pix_off(y, p)) + q) =
           make_float4(half_bits_to_float(p0 & 0xffffu), half_bits_to_float(p0 >> 16), half_bits_to_float(p1 & 0xffffu),
                       half_bits_to_float(p1 >> 16));
   }
@@ -274,7 +275,8 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(V src, V hi, V lo) {
 template <bool HALF>
 __global__ void __launch_bounds__(256)
 bn_bwd_dx_kernel(V x, V dy, V dx, const float* __restrict__ mean, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, int act, const float* __restrict__ coef, const float* __restrict__ oscale) {
+                 const float* __restrict__ beta, int act, const float* __restrict__ coef, const float* __restrict__ oscale,
+                 int same_geo) {
   const float os = (HALF && oscale) ? __ldg(oscale) : 1.f;
   const int C = x.c, C4 = C >> 2;
   const FastDiv x_fc4 = x.fc4;
@@ -283,8 +285,10 @@ bn_bwd_dx_kernel(V x, V dy, V dx, const float* __restrict__ mean, const float* _
     const uint32_t pp = fd_div((uint32_t)i, x_fc4);
     const int q = (int)((uint32_t)i - pp * (uint32_t)C4) * 4;
     const long long p = pp;
-    const float4 v = *reinterpret_cast<const float4*>(x.p + pix_off(x, p) + q);
-    const float4 g = *reinterpret_cast<const float4*>(dy.p + pix_off(dy, p) + q);
+    const size_t xo = pix_off(x, p);
+    const size_t go = same_geo ? xo : pix_off(dy, p);
+    const float4 v = *reinterpret_cast<const float4*>(x.p + xo + q);
+    const float4 g = *reinterpret_cast<const float4*>(dy.p + go + q);
     const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + q));
     const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + q));
     const float4 be = __ldg(reinterpret_cast<const float4*>(beta + q));
@@ -305,10 +309,10 @@ bn_bwd_dx_kernel(V x, V dy, V dx, const float* __restrict__ mean, const float* _
       if (act & MYOLO_ROUND_TF32) o[j] = round_tf32(o[j]);
     }
     if (HALF)
-      *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(dx.p) + pix_off(dx, p) + q) =
+      *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(dx.p) + (same_geo ? xo : pix_off(dx, p)) + q) =
           make_uint2(pack_half2_sat(o[0] * os, o[1] * os), pack_half2_sat(o[2] * os, o[3] * os));
     else
-      *reinterpret_cast<float4*>(dx.p + pix_off(dx, p) + q) = make_float4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<float4*>(dx.p + (same_geo ? xo : pix_off(dx, p)) + q) = make_float4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -518,7 +522,8 @@ extern "C" int myolo_bn_apply_h(const myolo_view* x, const myolo_view* y, const 
   const long long total = (long long)x->n * x->h * x->w * (x->c / 4);
   V vy = y ? to_v(y) : to_v(x);
   if (!y) vy.p = nullptr;
-  bn_apply_h_kernel<<<ew_blocks(total), 256, 0, as_stream(stream)>>>(to_v(x), vy, to_v(y_half), mean, var, gamma, beta, eps, act);
+  const int same_geo = x->sn == y_half->sn && x->sh == y_half->sh && (!y || (y->sn == x->sn && y->sh == x->sh));
+  bn_apply_h_kernel<<<ew_blocks(total), 256, 0, as_stream(stream)>>>(to_v(x), vy, to_v(y_half), mean, var, gamma, beta, eps, act, same_geo);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }
@@ -545,7 +550,8 @@ extern "C" int myolo_bn_bwd(const myolo_view* x, const myolo_view* dy, const myo
   float* coef = reinterpret_cast<float*>(ws + kWsCoef);   // 4*C floats
   Fin fin{dbeta, dgamma, coef, ws_ticket(ws, C), 1.0 / (double)total, train, C};
   colreduce_kernel<2><<<grid, 256, 0, st>>>(to_v(x), to_v(dy), mean, var, gamma, beta, eps, act, ws + kWsSums, ws + kWsSums + C, chunk, fin);
-  bn_bwd_dx_kernel<false><<<ew_blocks(total * (C / 4)), 256, 0, st>>>(to_v(x), to_v(dy), to_v(dx), mean, gamma, beta, act, coef, nullptr);
+  const int same_geo = x->sn == dy->sn && x->sh == dy->sh && x->sn == dx->sn && x->sh == dx->sh;
+  bn_bwd_dx_kernel<false><<<ew_blocks(total * (C / 4)), 256, 0, st>>>(to_v(x), to_v(dy), to_v(dx), mean, gamma, beta, act, coef, nullptr, same_geo);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }
@@ -565,7 +571,8 @@ extern "C" int myolo_bn_bwd_h(const myolo_view* x, const myolo_view* dy, const m
   float* coef = reinterpret_cast<float*>(ws + kWsCoef);
   Fin fin{dbeta, dgamma, coef, ws_ticket(ws, C), 1.0 / (double)total, train, C};
   colreduce_kernel<2><<<grid, 256, 0, st>>>(to_v(x), to_v(dy), mean, var, gamma, beta, eps, act, ws + kWsSums, ws + kWsSums + C, chunk, fin);
-  bn_bwd_dx_kernel<true><<<ew_blocks(total * (C / 4)), 256, 0, st>>>(to_v(x), to_v(dy), to_v(dx_half), mean, gamma, beta, act, coef, out_scale);
+  const int same_geo = x->sn == dy->sn && x->sh == dy->sh && x->sn == dx_half->sn && x->sh == dx_half->sh;
+  bn_bwd_dx_kernel<true><<<ew_blocks(total * (C / 4)), 256, 0, st>>>(to_v(x), to_v(dy), to_v(dx_half), mean, gamma, beta, act, coef, out_scale, same_geo);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(256)
 mask_out_bwd_kernel(const float* __restrict__ y4, const float* __restrict__ bd, const float* __restrict__ w1,
                     const float* __restrict__ dlogit, float* __restrict__ dy4, float* __restrict__ dw1,
                     float* __restrict__ db1, float* __restrict__ dbd, int n_roi, int H, int W, int Cmid, int NC,
-                    const float* __restrict__ gscale, const int* __restrict__ ids) {
+                    const float* __restrict__ gscale, const int* __restrict__ ids, const int* __restrict__ prev_ids) {
   extern __shared__ float sm[];  // w1 [Cmid][NC] | acc_w1 [Cmid][NC] | acc_b1 [NC]
   float* s_w1 = sm;
   float* a_w1 = sm + Cmid * NC;
@@ -127,7 +127,9 @@ mask_out_bwd_kernel(const float* __restrict__ y4, const float* __restrict__ bd, 
     const size_t off = row * (size_t)(4 * Cmid) + (size_t)ab * Cmid;
     if (HALF && ids && __ldg(ids + n) <= 0) {
       // not a positive roi: its dlogit is identically zero (myolo_mask_loss writes it so) -> a pure zero fill,
-      // without the dependent load of the gradient that made this kernel latency-bound
+      // without the dependent load of the gradient that made this kernel latency-bound.  With prev_ids (the ids of
+      // the call that last wrote this dy4 buffer) rows that were not positive then are zero already: nothing to do.
+      if (prev_ids && __ldg(prev_ids + n) <= 0) continue;
 #pragma unroll
       for (int j = 0; j < 2; ++j)
         if (j < nq) reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(dy4) + off)[j * 32 + lane] = make_uint2(0u, 0u);
@@ -273,14 +275,14 @@ extern "C" int myolo_mask_out_bwd(const float* y4, const float* bd, const float*
   const long long items = (long long)n_roi * H * W * 4;
   const int per_sm = smem > 64 * 1024 ? 1 : 4;
   const int blocks = (int)max(1LL, min(ceil_div(items, 8), (long long)kNumSMs * per_sm));
-  mask_out_bwd_kernel<false><<<blocks, 256, smem, as_stream(stream)>>>(y4, bd, w1, dlogit, dy4, dw1, db1, dbd, n_roi, H, W, Cmid, NC, nullptr, nullptr);
+  mask_out_bwd_kernel<false><<<blocks, 256, smem, as_stream(stream)>>>(y4, bd, w1, dlogit, dy4, dw1, db1, dbd, n_roi, H, W, Cmid, NC, nullptr, nullptr, nullptr);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }
 
 extern "C" int myolo_mask_out_bwd_h(const float* y4, const float* bd, const float* w1, const float* dlogit, void* dy4_half,
                                     float* dw1, float* db1, float* dbd, int n_roi, int H, int W, int Cmid, int NC,
-                                    const float* gscale, const int* target_ids, myolo_stream stream) {
+                                    const float* gscale, const int* target_ids, int* prev_ids, myolo_stream stream) {
   MYOLO_CHECK_ARG(y4 && bd && w1 && dlogit && dy4_half && dw1 && db1 && dbd && n_roi > 0 && H > 0 && W > 0 && NC > 0);
   MYOLO_CHECK_ARG(Cmid > 0 && (Cmid % 128) == 0 && Cmid <= kMaxCmid && ((uintptr_t)dy4_half & 7) == 0 &&
                   (long long)n_roi * H * W < (1LL << 31));
@@ -291,8 +293,11 @@ extern "C" int myolo_mask_out_bwd_h(const float* y4, const float* bd, const floa
   const int per_sm = smem > 64 * 1024 ? 1 : 4;
   const int blocks = (int)max(1LL, min(ceil_div(items, 8), (long long)kNumSMs * per_sm));
   mask_out_bwd_kernel<true><<<blocks, 256, smem, as_stream(stream)>>>(y4, bd, w1, dlogit, reinterpret_cast<float*>(dy4_half), dw1,
-                                                                      db1, dbd, n_roi, H, W, Cmid, NC, gscale, target_ids);
+                                                                      db1, dbd, n_roi, H, W, Cmid, NC, gscale, target_ids,
+                                                                      target_ids ? prev_ids : nullptr);
   MYOLO_CHECK_LAUNCH();
+  if (target_ids && prev_ids)   // remember which rows of this buffer are non-zero now
+    MYOLO_CUDA(cudaMemcpyAsync(prev_ids, target_ids, (size_t)n_roi * sizeof(int), cudaMemcpyDeviceToDevice, as_stream(stream)));
   return MYOLO_OK;
 }
 

@@ -115,6 +115,84 @@ roialign_bwd_kernel(V dout, const float* __restrict__ boxes, int n_roi, int rois
   }
 }
 
+// Run-length form of the backward scatter: a warp walks the P samples of one (roi, output row) left to right and
+// keeps the contributions to the current pair of feature columns (lo, lo+1) x (top, bottom row) in registers; they
+// go to memory as vector reductions only when the sample position moves on to another column.  A 14-sample row over
+// a 3..10 pixel wide box issues 1.4..4.7x fewer L2 atomics than one reduction per sample and corner (the atomics,
+// not the 0.94 GB gradient read, bound the per-sample kernel: 0.58 ms).  NQ = C / 128 float4 per lane.
+template <int NQ>
+__global__ void __launch_bounds__(256)
+roialign_bwd_rl_kernel(V dout, const float* __restrict__ boxes, int n_roi, int rois_per_img, int pool, V dfeat) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const long long items = (long long)n_roi * pool;
+  for (long long it = warp; it < items; it += nwarps) {
+    const int r = (int)(it / pool), y = (int)(it % pool);
+    const float4 bx = __ldg(reinterpret_cast<const float4*>(boxes) + r);
+    const int b = r / rois_per_img;
+    const Sample sy = crop_coord(bx.x, bx.z, y, pool, dfeat.h);
+    if (!sy.valid) continue;
+    float* fb = dfeat.p + (size_t)b * dfeat.sn;
+    float* rowt = fb + (size_t)sy.lo * dfeat.sh;
+    float* rowb = fb + (size_t)sy.hi * dfeat.sh;
+    const float* grow = dout.p + (size_t)r * dout.sn + (size_t)y * dout.sh;
+    const float wt = 1.f - sy.lerp, wb = sy.lerp;
+    const bool two_rows = sy.hi != sy.lo;      // hi == lo: the bottom weight is exactly zero
+    float4 at[2][NQ], ab[2][NQ];               // [column lo / lo+1][channel chunk], top and bottom row
+    int col = -1;                               // feature column of at[0] / ab[0]; -1 = nothing pending
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) at[c][q] = ab[c][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto flush = [&](int c, int column) {
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const size_t off = (size_t)column * dfeat.c + (size_t)(q * 32 + lane) * 4;
+        red_add4(rowt + off, at[c][q]);
+        if (two_rows) red_add4(rowb + off, ab[c][q]);
+        at[c][q] = ab[c][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    for (int x = 0; x < pool; ++x) {
+      const Sample sx = crop_coord(bx.y, bx.w, x, pool, dfeat.w);
+      if (!sx.valid) continue;
+      if (col >= 0 && sx.lo != col) {
+        if (sx.lo == col + 1) {                // moved on by one column: the old "lo+1" becomes "lo"
+          flush(0, col);
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) {
+            at[0][q] = at[1][q]; ab[0][q] = ab[1][q];
+            at[1][q] = ab[1][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        } else {
+          flush(0, col);
+          if (col + 1 < dfeat.w) flush(1, col + 1);
+        }
+      }
+      col = sx.lo;
+      const float wl = 1.f - sx.lerp, wr = sx.lerp;
+      const float4* gp = reinterpret_cast<const float4*>(grow + (size_t)x * dout.c);
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const float4 g = gp[q * 32 + lane];
+        const float4 dt = make_float4(wt * g.x, wt * g.y, wt * g.z, wt * g.w);
+        const float4 db = make_float4(wb * g.x, wb * g.y, wb * g.z, wb * g.w);
+        at[0][q].x += wl * dt.x; at[0][q].y += wl * dt.y; at[0][q].z += wl * dt.z; at[0][q].w += wl * dt.w;
+        ab[0][q].x += wl * db.x; ab[0][q].y += wl * db.y; ab[0][q].z += wl * db.z; ab[0][q].w += wl * db.w;
+        if (sx.hi != sx.lo) {                  // hi == lo: the right weight is exactly zero
+          at[1][q].x += wr * dt.x; at[1][q].y += wr * dt.y; at[1][q].z += wr * dt.z; at[1][q].w += wr * dt.w;
+          ab[1][q].x += wr * db.x; ab[1][q].y += wr * db.y; ab[1][q].z += wr * db.z; ab[1][q].w += wr * db.w;
+        }
+      }
+    }
+    if (col >= 0) {
+      flush(0, col);
+      if (col + 1 < dfeat.w) flush(1, col + 1);
+    }
+  }
+}
+
 static bool view_ok(const myolo_view* v) {
   return v && v->p && v->n > 0 && v->h > 0 && v->w > 0 && v->c > 0 && (v->c % 4) == 0 && (v->sn % 4) == 0 && (v->sh % 4) == 0;
 }
@@ -156,7 +234,12 @@ extern "C" int myolo_roialign_bwd(const myolo_view* dout, const float* boxes, in
   MYOLO_CHECK_ARG((n_roi + rois_per_img - 1) / rois_per_img <= dfeat->n);
   const long long items = (long long)n_roi * pool;
   const int blocks = (int)max(1LL, min(ceil_div(items, 8), (long long)kNumSMs * 8));
-  roialign_bwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(to_v(dout), boxes, n_roi, rois_per_img, pool, to_v(dfeat));
+  if (dfeat->c == 128)
+    roialign_bwd_rl_kernel<1><<<blocks, 256, 0, as_stream(stream)>>>(to_v(dout), boxes, n_roi, rois_per_img, pool, to_v(dfeat));
+  else if (dfeat->c == 256)
+    roialign_bwd_rl_kernel<2><<<blocks, 256, 0, as_stream(stream)>>>(to_v(dout), boxes, n_roi, rois_per_img, pool, to_v(dfeat));
+  else
+    roialign_bwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(to_v(dout), boxes, n_roi, rois_per_img, pool, to_v(dfeat));
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }

@@ -346,6 +346,7 @@ class Engine:
                 A["dlogit"] = f(n, mh, mw, NC)
                 if self.h16:     # loss-scaled half gradients; fp32 only for d(a1) (batch-statistics BN) and d(x0) (ROIAlign)
                     self.dy4h = PF(n, P_, P_, 4 * MASK_C, device=dev, dtype=torch.float16)
+                    self.dy4h_ids = torch.zeros(n, dtype=torch.int32, device=dev)   # which rois' rows of dy4h are non-zero
                     self.mgh = [PF(n, P_, P_, MASK_C, device=dev, dtype=torch.float16) for _ in range(2)]
                 else:
                     self.dy4d = PF(n, P_, P_, 4 * MASK_C, device=dev)
@@ -377,7 +378,7 @@ class Engine:
             C.call("myolo_bn_apply_split", xv, yv, yv_lo, mean, var, b.gamma, b.beta, BN_EPS, act & 0xff, st)
 
     def _gemm_fwd(self, a_rows, lo_off, name, out_rows, M, N, K, shifts, bias, pf_w1, pf_blk, scale=None, shift=None,
-                  act=0):
+                  act=0, stream=None):
         """Forward conv GEMM through the tap-GEMM entry point; 3xTF32 = the tap list tripled over the
         (A_hi,B_hi) (A_lo,B_hi) (A_hi,B_lo) operand pairs (lo_off = row distance hi -> lo)."""
         base = list(shifts) if shifts is not None else [0]
@@ -394,7 +395,7 @@ class Engine:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         C.call("myolo_gemm_taps", a_rows, K, self.wt[name], out_rows, N, M, N, K, len(sh), arr, bias, scale, shift,
-               act, pf_w1, pf_blk, 0, self._st())
+               act, pf_w1, pf_blk, 0, self._st() if stream is None else stream)
         if timed:
             e1.record()
             self.kernel_events.append((e0, e1))
@@ -446,9 +447,20 @@ class Engine:
             xin_view = out_view
             if k == 6 and self.with_mask:
                 # myolo_feature_maps = Conv2D(256, 3x3, SAME)(C4) + bias   (model.py:848)
+                # (on the side stream: 225 one-tile CTAs = 1.5 waves, next to the small kernels of the yolo branch;
+                # mask_head() joins before ROIAlign reads the feature map)
                 F_ = self.F
+                fm_stream = None
+                if self._side is not None and os.environ.get("MYOLO_FM_OVERLAP", "1") != "0":
+                    e = self._evs.setdefault("fm_fork", torch.cuda.Event())
+                    e.record(torch.cuda.current_stream())
+                    self._side.wait_event(e)
+                    fm_stream = self._side.cuda_stream
                 self._gemm_fwd(self.c4.rows, self.c4.lo_off, "feature_map/kernel", self.feat.rows, self.c4.M, MASK_C, 512,
-                               conv3x3_shifts(F_), self.p["feature_map/bias"], F_ + 1, (F_ + 1) * (F_ + 1))
+                               conv3x3_shifts(F_), self.p["feature_map/bias"], F_ + 1, (F_ + 1) * (F_ + 1), stream=fm_stream)
+                if fm_stream is not None:
+                    self._evs.setdefault("fm_done", torch.cuda.Event()).record(self._side)
+                    self._fm_pending = True
         G, NB, NC = self.cfg["G"], self.NB, self.NC
         # conv_23 (model.py:271) + reshape [B,G,G,NB,5+NC] (273): a pure view of the NHWC result
         C.call("myolo_gemm_taps_ffma", A["ap14"], 1024, self.wt["conv_23/kernel"], A["yolo"], NB * (5 + NC), B * G * G,
@@ -463,6 +475,9 @@ class Engine:
         A, st, n = self.A, self._st(), self.n_roi
         P_ = self.cfg["POOL"]
         npix = n * P_ * P_
+        if getattr(self, "_fm_pending", False):      # the feature_map conv ran on the side stream
+            torch.cuda.current_stream().wait_event(self._evs["fm_done"])
+            self._fm_pending = False
         if self.h16:
             return self._mask_head_h16(rois, training)
         C.call("myolo_roialign_fwd", self.feat.view(), rois, n, self.R, P_, self.x0.view(),
@@ -714,7 +729,7 @@ class Engine:
         C.call("myolo_grad_scale", A["dlogit"], A["dlogit"].numel(), gs, st)
         C.call("myolo_mask_out_bwd_h", self.y4d.rows, self.p["myolo_mask_deconv/bias"], self.p["myolo_mask/kernel"],
                A["dlogit"], self.dy4h.rows, self.g["myolo_mask/kernel"], self.g["myolo_mask/bias"],
-               self.g["myolo_mask_deconv/bias"], n, P_, P_, MASK_C, self.NC, gs, self.target_ids, st)
+               self.g["myolo_mask_deconv/bias"], n, P_, P_, MASK_C, self.NC, gs, self.target_ids, self.dy4h_ids, st)
         C.call("myolo_gemm_taps_wgrad_h", self.mah[4].rows, MASK_C, self.dy4h.rows, 4 * MASK_C, self.g["myolo_mask_deconv/kernel"],
                M, 4 * MASK_C, MASK_C, 1, None, 1, ugs, st)
         g0, g1 = self.mgh

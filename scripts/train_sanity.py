@@ -8,7 +8,7 @@ from myolo.shapes import ShapesConfig, make_batches
 
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 224
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 300
-prec = sys.argv[3] if len(sys.argv) > 3 else "tf32x3"
+prec = sys.argv[3] if len(sys.argv) > 3 else "h16"
 
 class Cfg(ShapesConfig):
     BATCH_SIZE = 16
@@ -25,5 +25,6 @@ for i in range(steps):
     v = model.keras_model.train_on_batch(batches[i % len(batches)])
     if i % 20 == 0 or i == steps - 1:
         npos = int(model.engine.n_pos.sum().item())
-        print(f"step {i:4d}  loss {v[0]:9.4f}  yolo {v[1]:9.4f}  mask {v[2]:7.4f}  positives {npos}", flush=True)
+        gs = f"  loss scale 2^{int(np.log2(model.engine.gs[0].item()))}" if prec == "h16" else ""
+        print(f"step {i:4d}  loss {v[0]:9.4f}  yolo {v[1]:9.4f}  mask {v[2]:7.4f}  positives {npos}{gs}", flush=True)
 print(f"{steps} steps in {time.time() - t0:.1f}s")

@@ -265,7 +265,7 @@ def test_mask_out_bwd_half_and_grad_scale(C):
     C.call("myolo_mask_out_bwd", y4.rows, bd, w1, dlogit, ref.rows, gr[0], gr[1], gr[2], n, H, W, Cm, NC, stream())
     outh = PF(n, H, W, 4 * Cm, dtype=torch.float16)
     gh = [torch.zeros(Cm, NC, device="cuda"), torch.zeros(NC, device="cuda"), torch.zeros(Cm, device="cuda")]
-    C.call("myolo_mask_out_bwd_h", y4.rows, bd, w1, dlogit, outh.rows, gh[0], gh[1], gh[2], n, H, W, Cm, NC, gs, None, stream())
+    C.call("myolo_mask_out_bwd_h", y4.rows, bd, w1, dlogit, outh.rows, gh[0], gh[1], gh[2], n, H, W, Cm, NC, gs, None, None, stream())
     assert torch.equal(outh.rows, (ref.rows * S).half()), "dy4 = half(S * exact)"
     for a, b in zip(gh, gr):
         close(a, b, 1e-5, "unscaled parameter gradients of the mask tail")
@@ -275,10 +275,26 @@ def test_mask_out_bwd_half_and_grad_scale(C):
     outh2 = PF(n, H, W, 4 * Cm, dtype=torch.float16)
     outh2.valid().fill_(7.0)
     gh2 = [torch.zeros(Cm, NC, device="cuda"), torch.zeros(NC, device="cuda"), torch.zeros(Cm, device="cuda")]
-    C.call("myolo_mask_out_bwd_h", y4.rows, bd, w1, dlogit, outh2.rows, gh2[0], gh2[1], gh2[2], n, H, W, Cm, NC, gs, ids, stream())
+    C.call("myolo_mask_out_bwd_h", y4.rows, bd, w1, dlogit, outh2.rows, gh2[0], gh2[1], gh2[2], n, H, W, Cm, NC, gs, ids, None, stream())
     assert torch.equal(outh2.rows, outh.rows)
     for a, b in zip(gh2, gh):
         close(a, b, 1e-5, "same parameter gradients with the id fast path")
+    # persistent buffer + prev_ids: only rows whose roi is or was positive are touched; a second step with another
+    # positive set must leave exactly the new set non-zero
+    buf = PF(n, H, W, 4 * Cm, dtype=torch.float16)
+    prev = torch.zeros(n, dtype=torch.int32, device="cuda")
+    g3 = [torch.zeros(Cm, NC, device="cuda"), torch.zeros(NC, device="cuda"), torch.zeros(Cm, device="cuda")]
+    C.call("myolo_mask_out_bwd_h", y4.rows, bd, w1, dlogit, buf.rows, g3[0], g3[1], g3[2], n, H, W, Cm, NC, gs, ids, prev, stream())
+    assert torch.equal(buf.rows, outh.rows) and torch.equal(prev, ids)
+    dlogit2 = torch.zeros_like(dlogit)
+    dlogit2[3, :, :, 1] = torch.randn(2 * H, 2 * W, device="cuda") * 3e-5
+    dlogit2[7, :, :, 2] = torch.randn(2 * H, 2 * W, device="cuda") * 3e-5
+    ids2 = torch.zeros(n, dtype=torch.int32, device="cuda")
+    ids2[[3, 7]] = torch.tensor([1, 2], dtype=torch.int32, device="cuda")
+    ref2 = PF(n, H, W, 4 * Cm, dtype=torch.float16)
+    C.call("myolo_mask_out_bwd_h", y4.rows, bd, w1, dlogit2, ref2.rows, g3[0], g3[1], g3[2], n, H, W, Cm, NC, gs, None, None, stream())
+    C.call("myolo_mask_out_bwd_h", y4.rows, bd, w1, dlogit2, buf.rows, g3[0], g3[1], g3[2], n, H, W, Cm, NC, gs, ids2, prev, stream())
+    assert torch.equal(buf.rows, ref2.rows) and torch.equal(prev, ids2)
     # all-zero gradient -> S = 1
     z = torch.zeros(1024, device="cuda")
     C.call("myolo_grad_scale", z, 1024, gs, stream())

@@ -156,12 +156,16 @@ def _boxes(n, seed):
     b[1] = torch.tensor([0.0, 0.0, 1.0, 1.0])
     b[2] = torch.tensor([0.2, 0.3, 0.2, 0.9])          # degenerate
     b[3] = torch.tensor([-0.5, 0.1, 1.5, 0.8])
+    b[4] = torch.tensor([0.7, 0.8, 0.3, 0.2])          # reversed box: sample positions run right to left
+    b[5] = torch.tensor([0.1, 0.45, 0.9, 0.55])        # samples several feature columns apart
+    b[6] = torch.tensor([0.0, 0.0, 12.0 / 11.0 * 0.5, 0.5])
     return b
 
 
-def test_roialign(C):
+@pytest.mark.parametrize("Cc", [64, 128, 256])      # 128 / 256: the run-length backward kernel; 64: one reduction per sample
+def test_roialign(C, Cc):
     torch.manual_seed(4)
-    B, Fh, Cc, R, P = 2, 12, 64, 9, 14
+    B, Fh, R, P = 2, 12, 9, 14
     feat = torch.randn(B, Fh, Fh, Cc).requires_grad_(True)
     boxes = _boxes(B * R, 5)
     idx = torch.arange(B).repeat_interleave(R)
