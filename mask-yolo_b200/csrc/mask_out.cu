@@ -116,20 +116,29 @@ mask_out_bwd_kernel(const float* __restrict__ y4, const float* __restrict__ bd, 
   for (int e = 0; e < 8; ++e) dbd_acc[e] = 0.f;
   bool any_local = false;
   const float gs = (HALF && gscale) ? __ldg(gscale) : 1.f;
-  for (long long it = warp; it < items; it += nwarps) {
-    const int ab = (int)(it & 3);
-    const unsigned t = (unsigned)(it >> 2);      // pixel index < 2^31 (checked by the host side): 32-bit div/mod
-    const unsigned t2 = t / (unsigned)W;
-    const int w = (int)(t - t2 * (unsigned)W);
-    const int n = (int)(t2 / (unsigned)H);
-    const int h = (int)(t2 - (unsigned)n * (unsigned)H);
+  // a warp takes 32 consecutive items (pixel, sub-position) of ONE roi at a time, so the roi-level decisions below
+  // cost one lookup per 32 items (as a per-item test their dependent loads were the whole run time of the kernel
+  // once the zero fill was gone)
+  const int per_roi = H * W * 4;
+  const int chunks = (per_roi + 31) / 32;
+  const long long tasks = (long long)n_roi * chunks;
+  (void)items;
+  for (long long task = warp; task < tasks; task += nwarps) {
+   const int n = (int)(task / chunks);
+   const int i0 = (int)(task - (long long)n * chunks) * 32;
+   // not a positive roi: its dlogit is identically zero (myolo_mask_loss writes it so) -> a pure zero fill, without
+   // the dependent load of the gradient.  With prev_ids (the ids of the call that last wrote this dy4 buffer) rows
+   // that were not positive then are zero already: nothing to do.
+   const bool zero_only = HALF && ids && __ldg(ids + n) <= 0;
+   if (zero_only && prev_ids && __ldg(prev_ids + n) <= 0) continue;
+   const int i1 = min(per_roi, i0 + 32);
+   for (int it = i0; it < i1; ++it) {
+    const int ab = it & 3;
+    const int pix = it >> 2;
+    const int h = pix / W, w = pix - h * W;
     const size_t row = (size_t)pf_row(n, h, w, H, W);
     const size_t off = row * (size_t)(4 * Cmid) + (size_t)ab * Cmid;
-    if (HALF && ids && __ldg(ids + n) <= 0) {
-      // not a positive roi: its dlogit is identically zero (myolo_mask_loss writes it so) -> a pure zero fill,
-      // without the dependent load of the gradient that made this kernel latency-bound.  With prev_ids (the ids of
-      // the call that last wrote this dy4 buffer) rows that were not positive then are zero already: nothing to do.
-      if (prev_ids && __ldg(prev_ids + n) <= 0) continue;
+    if (zero_only) {
 #pragma unroll
       for (int j = 0; j < 2; ++j)
         if (j < nq) reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(dy4) + off)[j * 32 + lane] = make_uint2(0u, 0u);
@@ -192,6 +201,7 @@ mask_out_bwd_kernel(const float* __restrict__ y4, const float* __restrict__ bd, 
         else
           reinterpret_cast<float4*>(dy4 + off)[j * 32 + lane] = make_float4(d[4 * j], d[4 * j + 1], d[4 * j + 2], d[4 * j + 3]);
       }
+   }
   }
   if (any_local) {
 #pragma unroll
