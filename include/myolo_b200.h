@@ -202,8 +202,8 @@ int myolo_roialign_bwd(const myolo_view* dout, const float* boxes, int n_roi, in
  * and sn / sh counted in ELEMENTS.  Conversions are round-to-nearest-even, saturating at +-65504. */
 /* out[t][c][r] = half(in[t][r][c]) when transpose != 0, else out = half(in) (weight staging, see myolo_prep_weights) */
 int myolo_prep_weights_h(const float* in, void* out_half, int ntaps, int rows, int cols, int transpose, myolo_stream stream);
-/* myolo_gemm_taps on the persistent CTA-pair kernel with half A / Bt.  Outputs: C (fp32, nullable) and Ch (half,
- * nullable), at least one.  When both are stored, C holds the half-rounded values.  acc_scale (nullable): DEVICE scalar
+/* myolo_gemm_taps on the persistent CTA-pair kernel with half A / Bt.  Output: EITHER C (fp32) OR Ch (half), the other
+ * NULL (eight epilogue warps own one staging tile each).  acc_scale (nullable): DEVICE scalar
  * multiplied into the accumulator before the epilogue (un-scaling of loss-scaled gradients).  N % 256 == 0, K % 64 == 0,
  * ntaps >= 2 with |shift| <= 16, or a plain GEMM with M >= 4096. */
 int myolo_gemm_taps_h(const void* A, long long lda, const void* Bt, float* C, long long ldc, void* Ch, long long ldch,
@@ -215,8 +215,8 @@ int myolo_gemm_taps_h_supported(long long lda, long long M, int N, int K, int nt
 int myolo_deconv_mask_fwd_h(const void* a4, const void* kd, const float* bd, const float* w1, const float* b1,
                             float* masks, const int* target_ids, float* y4, int n_roi, int H, int W, int Cmid, int NC,
                             myolo_stream stream);
-/* myolo_gemm_taps_bnbwd with half A / Bt / a_out; the result goes to C (fp32, nullable) and / or Ch (half, nullable),
- * both [M][N] with pitch ldc.  grad_unscale (nullable): DEVICE scalar applied to dgamma / dbeta / dbias (the incoming
+/* myolo_gemm_taps_bnbwd with half A / Bt / a_out; the result goes to EITHER C (fp32) OR Ch (half), [M][N] with pitch
+ * ldc, the other NULL.  grad_unscale (nullable): DEVICE scalar applied to dgamma / dbeta / dbias (the incoming
  * gradient carries a loss scale; the stored d(pre-BN) keeps it). */
 int myolo_gemm_taps_bnbwd_h(const void* A, long long lda, const void* Bt, float* C, void* Ch, long long ldc,
                             long long M, int N, int K, int ntaps, const int* shifts_host, int pf_w1, int pf_blk,

@@ -34,13 +34,16 @@ constexpr int WHALO = 16;
 constexpr uint32_t kWStageOut = 2 * 4 * 4096;   // per-epilogue-warp 32x32 fp32 staging buffers: TMA-store tile + BN-backward side tile
 constexpr uint32_t kWColAcc = 2 * 256 * 4;       // per-CTA column-sum accumulators of the fused BN backward
 constexpr uint32_t kWEpiVec = 2 * 1024 * 4;     // folded epilogue scale / shift, up to 1024 output channels
-constexpr uint32_t kWStageHalf = 4 * 2048;      // per-epilogue-warp 32x32 half staging tile (64B-swizzled TMA-store box)
+// threads per CTA: TMA warp + MMA warp + epilogue warps.  The half-operand flavour (EL = 2) runs EIGHT epilogue warps,
+// two per TMEM lane quarter, each taking half of the item's columns: its main loop is twice as fast as the tf32 one,
+// and with four warps the fused BN-backward epilogue (8.7 k instructions per item) was longer than the main loop.
+__host__ __device__ constexpr int win_threads(int el) { return el == 2 ? 320 : 192; }
 // NACC = 128-row accumulators per work item.  Window = 128*NACC + 32 rows; weight ring 128 KB (NACC 1) / 96 KB (NACC 2)
 __host__ __device__ constexpr int win_rows(int nacc) { return 128 * nacc + 2 * WHALO; }
 __host__ __device__ constexpr int win_box(int nacc) { return nacc == 1 ? win_rows(1) : win_rows(2) / 2; }
 __host__ __device__ constexpr uint32_t win_ring(int nacc) { return nacc == 1 ? 131072u : 98304u; }
 __host__ __device__ constexpr uint32_t win_smem(int nacc) {
-  return 2u * win_rows(nacc) * 128u + win_ring(nacc) + kWStageOut + kWColAcc + kWEpiVec + kWStageHalf + 1024u;
+  return 2u * win_rows(nacc) * 128u + win_ring(nacc) + kWStageOut + kWColAcc + kWEpiVec + 1024u;
 }
 
 // Work item = (256-row tile, WBN-column slice).  Two 128-row accumulators share every weight stage.
@@ -152,7 +155,7 @@ __device__ __forceinline__ void mask_tail_row(uint32_t taddr, uint32_t evs, floa
 // descriptor geometry is identical).  With EL = 2 the epilogue can store the result as half (tmCh, 64B-swizzled
 // 32x32 tiles) next to or instead of the fp32 tile, and the fused BN backward reads its activation as half.
 template <int WBN, int NACC, int CG, int EL = 4>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(win_threads(EL))
 tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmCh, long long M, int N,
                    int K, int ntaps, TapShifts sh, Epi ep, MaskTail mt, int nitems, int dbg) {
@@ -172,7 +175,7 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const uint32_t awin0 = base, bst0 = base + 2 * kWinBytes, stg0 = bst0 + kWBStages * kWBBytes;
   float* colacc = reinterpret_cast<float*>(smem_raw + (stg0 + kWStageOut - smem_u32(smem_raw)));          // [2][256]
   float* evec = reinterpret_cast<float*>(smem_raw + (stg0 + kWStageOut + kWColAcc - smem_u32(smem_raw)));  // [scale N | shift N]
-  const uint32_t stgh0 = stg0 + kWStageOut + kWColAcc + kWEpiVec;   // half staging tiles (1024-byte aligned)
+  constexpr int kEpiWarps = win_threads(EL) / 32 - 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int KEL = 128 / EL;                             // channels per 128-byte k-block
   const int kblocks = K / KEL;
@@ -194,7 +197,7 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       mbar_init(a_full(i), 1);
       mbar_init(a_empty(i), 1);
       mbar_init(t_full(i), 1);
-      mbar_init(t_empty(i), 4 * CG);  // one arrival per epilogue warp (of both CTAs of a pair)
+      mbar_init(t_empty(i), kEpiWarps * CG);  // one arrival per epilogue warp (of both CTAs of a pair)
     }
     for (int i = 0; i < kWBStages; ++i) {
       mbar_init(b_full(i), 1);
@@ -318,18 +321,21 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
     }
   } else {
-    const int q = warp & 3;
-    const uint32_t sbuf0 = stg0 + (uint32_t)q * 4096u;
-    const uint32_t sbufh0 = stgh0 + (uint32_t)q * 2048u;
+    const int q = warp & 3;                        // TMEM lane quarter this warp may read
+    const int ew = warp - 2;                       // epilogue warp index
+    const int eh = EL == 2 ? (ew >> 2) : 0;        // EL = 2: which half of the item's columns
+    constexpr int kColsPerWarp = EL == 2 ? WBN / 2 : WBN;
+    const int cbeg = eh * kColsPerWarp;
+    // staging: 4 KB per epilogue warp.  tf32 flavour: warps q = 0..3 own [q*4 KB] plus the side tile 16 KB further up.
+    // half flavour (exactly one output): 8 warps x 4 KB = one fp32 tile, or a ring of two 2 KB half tiles so that a
+    // chunk does not wait for the previous chunk's TMA store to finish reading shared memory.
+    const uint32_t sbuf0 = stg0 + (uint32_t)(EL == 2 ? ew : q) * 4096u;
     const bool st_f32 = !(EL == 2 && ep.no_f32), st_h = EL == 2 && ep.has_h;
-    // half-operand kernels with ONE output keep a ring of staging tiles in the space the other output's tiles would
-    // take (four 2 KB half tiles, or two 4 KB fp32 tiles), so a chunk no longer waits for the previous chunk's TMA
-    // store to finish reading shared memory (8 serialised store latencies per item were as long as the main loop)
-    const bool ring_h = EL == 2 && st_h && !st_f32, ring_f = EL == 2 && st_f32 && !st_h;
+    const bool ring_h = EL == 2 && st_h;
+    constexpr bool ring_f = false;
     auto wait_store = [&]() {
       if (lane == 0) {
-        if (ring_h) asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
-        else if (ring_f) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        if (ring_h) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       }
       __syncwarp();
@@ -346,7 +352,7 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       tc_fence_after();
       if (WBN == 256 && mt.masks) {
 #pragma unroll 1
-        for (int acc = 0; acc < NACC; ++acc) {
+        for (int acc = 0; acc < (eh == 0 ? NACC : 0); ++acc) {   // LSU-bound tail: one warp per lane quarter does all 256 columns
           const long long m = (long long)tile * WBM + acc * 128 + q * 32 + lane;
           const bool valid = (m < M) && pf_valid(m, ep.pf_w1, ep.pf_blk);
           int roi = 0, hh = 0, ww = 0;
@@ -394,21 +400,21 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         uint4 ahc[4];
         if (EL == 2 && ep.bn_a) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) ahc[j] = valid ? __ldg(arow_h0 + j) : make_uint4(0u, 0u, 0u, 0u);
+          for (int j = 0; j < 4; ++j) ahc[j] = valid ? __ldg(arow_h0 + cbeg / 8 + j) : make_uint4(0u, 0u, 0u, 0u);
         }
 #pragma unroll 1
-        for (int c0 = 0; c0 < WBN; c0 += 32, ++nst) {
+        for (int c0 = cbeg; c0 < cbeg + kColsPerWarp; c0 += 32, ++nst) {
           float v[32];
           tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ts * TSTRIDE + (uint32_t)(acc * WBN + c0), v);
-          const uint32_t sbuf = ring_f ? sbuf0 + (nst & 1u) * (4u * 4096u) : sbuf0;
-          const uint32_t sbufh = ring_h ? sbuf0 + ((nst >> 1) & 1u) * (4u * 4096u) + (nst & 1u) * 2048u : sbufh0;
+          const uint32_t sbuf = sbuf0;
+          const uint32_t sbufh = sbuf0 + (nst & 1u) * 2048u;
           const int n0 = half * WBN + c0;
           if (EL == 2 && ep.bn_a) {
             // ---- fused BN(+ReLU) backward on half tensors, register-only: v = d(a) of this thread's row (loss-scaled)
             uint4 ahn[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              ahn[j] = (valid && c0 + 32 < WBN) ? __ldg(arow_h0 + (c0 + 32) / 8 + j) : make_uint4(0u, 0u, 0u, 0u);
+              ahn[j] = (valid && c0 + 32 < cbeg + kColsPerWarp) ? __ldg(arow_h0 + (c0 + 32) / 8 + j) : make_uint4(0u, 0u, 0u, 0u);
             // per element only g = d(a)*act'(a) and g*a: the per-column constants of dgamma = sum g*(a-beta)/gamma are
             // applied AFTER the column reduction, where lane = column (every broadcast constant load costs a full
             // shared-memory wavefront per lane-row, and this epilogue was bound by them)
@@ -658,6 +664,7 @@ static int launch_win(const float* A, long long lda, const float* Bt, float* C, 
     MYOLO_CHECK_ARG((K % 64) == 0 && (lda % 8) == 0 && (N % 256) == 0 && !(act & MYOLO_ROUND_TF32));
     MYOLO_CHECK_ARG(!hio.Ch || ((hio.ldch % 8) == 0 && ((uintptr_t)hio.Ch & 15) == 0));
     MYOLO_CHECK_ARG(hio.Ch || !hio.no_f32 || mt.masks);
+    MYOLO_CHECK_ARG(!(hio.Ch && !hio.no_f32));   // one output per launch: the eight epilogue warps own one staging tile each
   }
   MYOLO_CHECK_ARG((scale == nullptr) == (shift_c == nullptr));
   MYOLO_CHECK_ARG(!(accumulate && (scale || (act & 0xff) != MYOLO_ACT_NONE)));
@@ -710,7 +717,7 @@ static int launch_win(const float* A, long long lda, const float* Bt, float* C, 
     tch = tc_;
   }
   static bool attr_set = false;
-  static int max_clusters = 0;
+  static int max_clusters = 0, max_clusters_h = 0;
   if (!attr_set) {
     MYOLO_CUDA(cudaFuncSetAttribute(tc_conv_win_kernel<128, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem(1)));
     MYOLO_CUDA(cudaFuncSetAttribute(tc_conv_win_kernel<256, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem(1)));
@@ -730,18 +737,22 @@ static int launch_win(const float* A, long long lda, const float* Bt, float* C, 
       q.numAttrs = 1;
       if (cudaOccupancyMaxActiveClusters(&max_clusters, tc_conv_win_kernel<256, 1, 2>, &q) != cudaSuccess) max_clusters = 0;
       (void)cudaGetLastError();
+      q.blockDim = dim3(win_threads(2));
+      if (cudaOccupancyMaxActiveClusters(&max_clusters_h, tc_conv_win_kernel<256, 1, 2, 2>, &q) != cudaSuccess) max_clusters_h = 0;
+      (void)cudaGetLastError();
     }
     attr_set = true;
   }
   Epi ep{bias, scale, shift_c, act, pf_w1, pf_blk, accumulate, bnb.a, bnb.gamma, bnb.beta, bnb.var, bnb.ws, bnb.eps,
          hio.on ? (const void*)bnb.a : nullptr, hio.on ? hio.no_f32 : 0, (hio.on && hio.Ch) ? 1 : 0, hio.acc_scale};
   cudaStream_t st = as_stream(stream);
-  if (cg == 2 && max_clusters > 0) {
+  const int maxcl = hio.on ? max_clusters_h : max_clusters;
+  if (cg == 2 && maxcl > 0) {
     const int nitems = (int)ceil_div(M, 256) * (N / wbn);
-    const int ncl = nitems < max_clusters ? nitems : max_clusters;
+    const int ncl = nitems < maxcl ? nitems : maxcl;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * ncl);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(win_threads(hio.on ? 2 : 4));
     cfg.dynamicSmemBytes = win_smem(1);
     cfg.stream = st;
     cudaLaunchAttribute at[1];
