@@ -113,6 +113,12 @@ int myolo_gemm_taps_wgrad_tc_supported(long long lda, long long ldd, long long M
  * the 3xTF32 tap triple (A_hi,B_hi), (A_lo,B_hi), (A_hi,B_lo).  in != out. */
 int myolo_prep_weights(const float* in, float* out, int ntaps, int rows, int cols, int transpose,
                        int round_tf32, myolo_stream stream);
+/* every staging job of a step in one launch.  jobs_dev: device array of n_jobs records
+ * { const float* in; void* out; int ntaps, rows, cols, transpose, mode, tile_begin; } (40 bytes each) with mode
+ * 0 copy / 1 tf32 rounding / 2 3xTF32 split / 3 IEEE half (= myolo_prep_weights with round_tf32 0/1/2 and
+ * myolo_prep_weights_h) and tile_begin = running sum of ntaps*ceil(rows/32)*ceil(cols/32) over the jobs before it;
+ * total_tiles = that sum over all jobs. */
+int myolo_prep_weights_batch(const void* jobs_dev, int n_jobs, int total_tiles, myolo_stream stream);
 /* pointwise / 3x3 named wrappers (SURVEY 8b names).  w = HWIO kernel [t][Cin][Cout]; wt = its
  * per-tap transpose [t][Cout][Cin] (myolo_prep_weights). */
 int myolo_pwconv_fwd(const float* x, const float* wt, float* y, long long M, int Cin, int Cout,

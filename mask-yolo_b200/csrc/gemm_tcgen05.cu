@@ -560,6 +560,70 @@ extern "C" int myolo_gemm_taps_wgrad_tc(const float* A, long long lda, const flo
   }
 }
 
+// ---- every weight staging job of a step in ONE launch ------------------------------------------------------------
+// mode: 0 copy, 1 tf32 rounding, 2 3xTF32 split ([hi | hi | lo] stacked copies), 3 IEEE half.  A block handles one
+// 32x32 tile of one tap of one job; tile_begin is the running sum of tiles over the jobs (binary search by block).
+namespace myolo {
+namespace tc {
+struct PrepJob {
+  const float* in;
+  void* out;
+  int ntaps, rows, cols, transpose, mode, tile_begin;
+};
+__global__ void prep_weights_batch_kernel(const PrepJob* __restrict__ jobs, int n_jobs) {
+  __shared__ float t[32][33];
+  int lo = 0, hi = n_jobs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].tile_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const PrepJob jb = jobs[lo];
+  const int tx = (jb.cols + 31) / 32, ty = (jb.rows + 31) / 32;
+  int tile = (int)blockIdx.x - jb.tile_begin;
+  const int tap = tile / (tx * ty);
+  tile -= tap * tx * ty;
+  const int by = tile / tx, bx = tile - by * tx;
+  const size_t per_tap = (size_t)jb.rows * jb.cols, total = per_tap * jb.ntaps;
+  const float* ip = jb.in + tap * per_tap;
+  float* of = reinterpret_cast<float*>(jb.out) + tap * per_tap;
+  uint16_t* oh = reinterpret_cast<uint16_t*>(jb.out) + tap * per_tap;
+  auto emit = [&](size_t idx, float v) {
+    if (jb.mode == 3) oh[idx] = f2h_sat(v);
+    else if (jb.mode == 2) {
+      const float h = round_tf32(v);
+      of[idx] = h;
+      of[total + idx] = h;
+      of[2 * total + idx] = round_tf32(v - h);
+    } else of[idx] = jb.mode == 1 ? round_tf32(v) : v;
+  };
+  const int c = bx * 32 + threadIdx.x;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int r = by * 32 + j;
+    const float v = (r < jb.rows && c < jb.cols) ? ip[(size_t)r * jb.cols + c] : 0.f;
+    if (!jb.transpose) {
+      if (r < jb.rows && c < jb.cols) emit((size_t)r * jb.cols + c, v);
+    } else {
+      t[j][threadIdx.x] = v;
+    }
+  }
+  if (!jb.transpose) return;
+  __syncthreads();
+  const int r2 = by * 32 + threadIdx.x;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int c2 = bx * 32 + j;
+    if (r2 < jb.rows && c2 < jb.cols) emit((size_t)c2 * jb.rows + r2, t[threadIdx.x][j]);
+  }
+}
+}  // namespace tc
+}  // namespace myolo
+
+extern "C" int myolo_prep_weights_batch(const void* jobs_dev, int n_jobs, int total_tiles, myolo_stream stream) {
+  MYOLO_CHECK_ARG(jobs_dev && n_jobs > 0 && total_tiles > 0);
+  prep_weights_batch_kernel<<<total_tiles, dim3(32, 8), 0, as_stream(stream)>>>(reinterpret_cast<const PrepJob*>(jobs_dev), n_jobs);
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
+}
+
 namespace myolo {
 namespace tc {
 // half staging of a weight block: out[t][c][r] = half(in[t][r][c]) (transpose) or out = half(in)

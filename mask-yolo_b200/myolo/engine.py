@@ -253,33 +253,50 @@ class Engine:
             else:
                 self._frozen = True
 
-    def refresh_weights(self):
-        """Re-stage the transposed (and, in tf32 mode, rounded) GEMM weight operands after an update."""
-        st = self._st()
+    def _prep_jobs(self):
+        """(src tensor, dst tensor, ntaps, rows, cols, transpose, mode) for every GEMM-side weight copy; mode as in
+        myolo_prep_weights_batch."""
+        jobs = []
         for name, buf in self.wt.items():
-            rnd = 2 if self._is_x3(name) else (1 if self.tc else 0)
+            mode = 2 if self._is_x3(name) else (1 if self.tc else 0)
             if name == "conv_23/kernel":
-                rnd = 0         # N = N_BOX*(5+NC) is not a tensor-core shape: always the exact CUDA-core kernel
+                mode = 0        # N = N_BOX*(5+NC) is not a tensor-core shape: always the exact CUDA-core kernel
             shape = self.offs[name][2]
             if name == "myolo_mask_deconv/kernel":
                 # Keras [2,2,Cout,Cin] is already the forward Bt ([N=4*Cout][K=Cin]); stage its
                 # transpose [Cin][4*Cout] for the dgrad GEMM.
-                C.call("myolo_prep_weights", self.p[name], buf, 1, 4 * shape[2], shape[3], 1, rnd, st)
+                jobs.append((self.p[name], buf, 1, 4 * shape[2], shape[3], 1, mode))
             else:
-                taps = shape[0] * shape[1]
-                C.call("myolo_prep_weights", self.p[name], buf, taps, shape[2], shape[3], 1, rnd, st)
+                jobs.append((self.p[name], buf, shape[0] * shape[1], shape[2], shape[3], 1, mode))
         for name, buf in self.wth.items():
             shape = self.offs[name][2]
             if name == "myolo_mask_deconv/kernel":
-                C.call("myolo_prep_weights_h", self.p[name], buf, 1, 4 * shape[2], shape[3], 0, st)
+                jobs.append((self.p[name], buf, 1, 4 * shape[2], shape[3], 0, 3))
             else:
-                C.call("myolo_prep_weights_h", self.p[name], buf, shape[0] * shape[1], shape[2], shape[3], 1, st)
+                jobs.append((self.p[name], buf, shape[0] * shape[1], shape[2], shape[3], 1, 3))
         for name, buf in self.wth_d.items():
             shape = self.offs[name][2]
             if name == "myolo_mask_deconv/kernel":
-                C.call("myolo_prep_weights_h", self.p[name], buf, 1, 4 * shape[2], shape[3], 1, st)
+                jobs.append((self.p[name], buf, 1, 4 * shape[2], shape[3], 1, 3))
             else:
-                C.call("myolo_prep_weights_h", self.p[name], buf, shape[0] * shape[1], shape[2], shape[3], 0, st)
+                jobs.append((self.p[name], buf, shape[0] * shape[1], shape[2], shape[3], 0, 3))
+        if self.h16:    # the tf32 staging of the mask-head weights is never read in h16 mode
+            jobs = [j for j in jobs if not (j[6] != 3 and any(j[1] is self.wt[n] for n in self.wth))]
+        return jobs
+
+    def refresh_weights(self):
+        """Re-stage the transposed / rounded / split / half GEMM weight operands after an update: one launch over a
+        device-side job table (built once; the buffers never move)."""
+        if getattr(self, "_prep_table", None) is None:
+            import struct
+            rec, tiles = b"", 0
+            jobs = self._prep_jobs()
+            for src, dst, ntaps, rows, cols, tr, mode in jobs:
+                rec += struct.pack("<QQiiiiii", src.data_ptr(), dst.data_ptr(), ntaps, rows, cols, tr, mode, tiles)
+                tiles += ntaps * ((rows + 31) // 32) * ((cols + 31) // 32)
+            self._prep_table = torch.frombuffer(bytearray(rec), dtype=torch.uint8).to(self.dev)
+            self._prep_n, self._prep_tiles = len(jobs), tiles
+        C.call("myolo_prep_weights_batch", self._prep_table, self._prep_n, self._prep_tiles, self._st())
 
     # ------------------------------------------------------------------ activations
     def _alloc_acts(self):
