@@ -264,6 +264,12 @@ int myolo_bn_bwd_h(const myolo_view* x, const myolo_view* dy, const myolo_view* 
                    const float* var, const float* gamma, const float* beta, float eps, int act, int train,
                    float* dgamma, float* dbeta, double* ws, const float* out_scale, myolo_stream stream);
 
+/* myolo_bn_bwd with fp32 x and HALF, loss-scaled dy and dx (dx may alias dy): dx keeps dy's scale, dgamma / dbeta are
+ * multiplied by *grad_unscale. */
+int myolo_bn_bwd_hh(const myolo_view* x, const myolo_view* dy_half, const myolo_view* dx_half, const float* mean,
+                    const float* var, const float* gamma, const float* beta, float eps, int act, int train,
+                    float* dgamma, float* dbeta, double* ws, const float* grad_unscale, myolo_stream stream);
+
 /* ---- K12: DecodeYOLOLayer / DetectionsLayer, myolo/model.py:1442-1473, 1493-1538 ---- */
 int myolo_yolo_decode(const float* y_pred, const float* anchors, float* boxes, float* detections /*nullable*/,
                       int B, int GH, int GW, int NB, int NC, myolo_stream stream);

@@ -68,9 +68,22 @@ struct Fin {
   double inv_count;   // 1 / pixels
   int train;          // MODE 2: batch-statistics BN (mean terms) or fixed statistics
   int C;
+  const float* unscale;   // MODE 2 with a loss-scaled half dy: device scalar applied to dbeta / dgamma only (the
+                          // mean terms of the coefficient table stay in scaled units, like the dx they produce)
 };
 
-template <int MODE>
+__device__ __forceinline__ float4 load_half4(const float* base, size_t off) {   // 4 IEEE halves at element offset `off`
+  const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(base) + off);
+  float4 r;
+  asm("cvt.f32.f16 %0, %1;" : "=f"(r.x) : "h"((uint16_t)(u.x & 0xffffu)));
+  asm("cvt.f32.f16 %0, %1;" : "=f"(r.y) : "h"((uint16_t)(u.x >> 16)));
+  asm("cvt.f32.f16 %0, %1;" : "=f"(r.z) : "h"((uint16_t)(u.y & 0xffffu)));
+  asm("cvt.f32.f16 %0, %1;" : "=f"(r.w) : "h"((uint16_t)(u.y >> 16)));
+  return r;
+}
+
+// DYH: dy is an IEEE-half view (MODE 2 only)
+template <int MODE, bool DYH = false>
 __global__ void __launch_bounds__(256)
 colreduce_kernel(V x, V dy, const float* __restrict__ mean, const float* __restrict__ var,
                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int act,
@@ -102,7 +115,7 @@ colreduce_kernel(V x, V dy, const float* __restrict__ mean, const float* __restr
       s0.x += v.x; s0.y += v.y; s0.z += v.z; s0.w += v.w;
       s1.x = fmaf(v.x, v.x, s1.x); s1.y = fmaf(v.y, v.y, s1.y); s1.z = fmaf(v.z, v.z, s1.z); s1.w = fmaf(v.w, v.w, s1.w);
     } else {
-      const float4 g = *reinterpret_cast<const float4*>(dy.p + pix_off(dy, p) + c0);
+      const float4 g = DYH ? load_half4(dy.p, pix_off(dy, p) + c0) : *reinterpret_cast<const float4*>(dy.p + pix_off(dy, p) + c0);
       const float xh0 = (v.x - mu.x) * rs.x, xh1 = (v.y - mu.y) * rs.y, xh2 = (v.z - mu.z) * rs.z, xh3 = (v.w - mu.w) * rs.w;
       const float g0 = g.x * act_grad_mask(fmaf(xh0, ga.x, be.x), act);
       const float g1 = g.y * act_grad_mask(fmaf(xh1, ga.y, be.y), act);
@@ -144,8 +157,9 @@ colreduce_kernel(V x, V dy, const float* __restrict__ mean, const float* __restr
       fin.o0[c] = (float)m;
       fin.o1[c] = (float)(vv > 0.0 ? vv : 0.0);
     } else if (MODE == 2) {
-      fin.o0[c] = (float)S0;
-      fin.o1[c] = (float)S1;
+      const double us = fin.unscale ? (double)__ldg(fin.unscale) : 1.0;
+      fin.o0[c] = (float)(S0 * us);
+      fin.o1[c] = (float)(S1 * us);
       if (fin.coef) {
         const float r = 1.f / sqrtf(var[c] + eps);
         fin.coef[c] = r;
@@ -290,7 +304,8 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(V src, V hi, V lo) {
 }
 
 // HALF: dx is an IEEE-half view and receives dx * (*oscale) (loss-scaled operand of the kind::f16 GEMMs)
-template <bool HALF>
+// DYH: dy is an IEEE-half view (already loss-scaled: dx inherits the scale, oscale must be null)
+template <bool HALF, bool DYH = false>
 __global__ void __launch_bounds__(256)
 bn_bwd_dx_kernel(V x, V dy, V dx, const float* __restrict__ mean, const float* __restrict__ gamma,
                  const float* __restrict__ beta, int act, const float* __restrict__ coef, const float* __restrict__ oscale,
@@ -319,7 +334,7 @@ bn_bwd_dx_kernel(V x, V dy, V dx, const float* __restrict__ mean, const float* _
     const size_t xo = pix_off(x, p);
     const size_t go = same_geo ? xo : pix_off(dy, p);
     const float4 v = *reinterpret_cast<const float4*>(x.p + xo + q);
-    const float4 g = *reinterpret_cast<const float4*>(dy.p + go + q);
+    const float4 g = DYH ? load_half4(dy.p, go + q) : *reinterpret_cast<const float4*>(dy.p + go + q);
     if (!fixed_q) load_q(q);
     const float vin[4] = {v.x, v.y, v.z, v.w}, gin[4] = {g.x, g.y, g.z, g.w};
     const float mua[4] = {mu.x, mu.y, mu.z, mu.w}, gaa[4] = {ga.x, ga.y, ga.z, ga.w}, bea[4] = {be.x, be.y, be.z, be.w};
@@ -598,6 +613,28 @@ extern "C" int myolo_bn_bwd_h(const myolo_view* x, const myolo_view* dy, const m
   colreduce_kernel<2><<<grid, 256, 0, st>>>(to_v(x), to_v(dy), mean, var, gamma, beta, eps, act, ws + kWsSums, ws + kWsSums + C, chunk, fin);
   const int same_geo = x->sn == dy->sn && x->sh == dy->sh && x->sn == dx_half->sn && x->sh == dx_half->sh;
   bn_bwd_dx_kernel<true><<<ew_blocks(total * (C / 4)), 256, 0, st>>>(to_v(x), to_v(dy), to_v(dx_half), mean, gamma, beta, act, coef, out_scale, same_geo);
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
+}
+
+extern "C" int myolo_bn_bwd_hh(const myolo_view* x, const myolo_view* dy_half, const myolo_view* dx_half, const float* mean,
+                               const float* var, const float* gamma, const float* beta, float eps, int act, int train,
+                               float* dgamma, float* dbeta, double* ws, const float* grad_unscale, myolo_stream stream) {
+  MYOLO_CHECK_ARG(view_ok(x) && view_ok(dy_half) && view_ok(dx_half) && same_shape(x, dy_half) && same_shape(x, dx_half));
+  MYOLO_CHECK_ARG(mean && var && gamma && beta && dgamma && dbeta && ws && (x->c % 32) == 0 && x->c <= kWsMaxC);
+  MYOLO_CHECK_ARG(((uintptr_t)dx_half->p & 7) == 0 && ((uintptr_t)dy_half->p & 7) == 0 && !(act & MYOLO_ROUND_TF32));
+  cudaStream_t st = as_stream(stream);
+  const int C = x->c;
+  const long long total = (long long)x->n * x->h * x->w;
+  dim3 grid;
+  long long chunk;
+  reduce_grid(total, C, &grid, &chunk);
+  float* coef = reinterpret_cast<float*>(ws + kWsCoef);
+  Fin fin{dbeta, dgamma, coef, ws_ticket(ws, C), 1.0 / (double)total, train, C, grad_unscale};
+  colreduce_kernel<2, true><<<grid, 256, 0, st>>>(to_v(x), to_v(dy_half), mean, var, gamma, beta, eps, act, ws + kWsSums, ws + kWsSums + C, chunk, fin);
+  const int same_geo = x->sn == dy_half->sn && x->sh == dy_half->sh && x->sn == dx_half->sn && x->sh == dx_half->sh;
+  bn_bwd_dx_kernel<true, true><<<ew_blocks(total * (C / 4)), 256, 0, st>>>(to_v(x), to_v(dy_half), to_v(dx_half), mean, gamma, beta, act, coef,
+                                                                         nullptr, same_geo);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }

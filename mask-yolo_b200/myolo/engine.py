@@ -765,12 +765,12 @@ class Engine:
             if i > 2:
                 dgrad_bn(g0.rows, MASK_C, name, g1.rows, MASK_C, 9, shn, i - 1)
                 g0, g1 = g1, g0
-        # d(a1), un-scaled fp32 -> batch-statistics BN backward -> d(pre-BN conv1) as scaled half
-        C.call("myolo_gemm_taps_h", g0.rows, MASK_C, self.wth_d["myolo_mask_conv2/kernel"], self.mg[0].rows, MASK_C, None, 0, M,
-               MASK_C, MASK_C, 9, shn, None, None, None, C.ACT_NONE, pfw, pfb, ugs, st)
+        # d(a1) as scaled half -> batch-statistics BN backward in place -> d(pre-BN conv1), still scaled half
+        C.call("myolo_gemm_taps_h", g0.rows, MASK_C, self.wth_d["myolo_mask_conv2/kernel"], None, 0, g1.rows, MASK_C, M,
+               MASK_C, MASK_C, 9, shn, None, None, None, C.ACT_NONE, pfw, pfb, None, st)
         b = self.bn["myolo_mask_bn1"]
-        C.call("myolo_bn_bwd_h", self.my[1].view(), self.mg[0].view(), g1.view(), b.mean, b.var, b.gamma, b.beta, BN_EPS,
-               C.ACT_RELU, 1, b.dgamma, b.dbeta, self.ws, gs, st)
+        C.call("myolo_bn_bwd_hh", self.my[1].view(), g1.view(), g1.view(), b.mean, b.var, b.gamma, b.beta, BN_EPS,
+               C.ACT_RELU, 1, b.dgamma, b.dbeta, self.ws, ugs, st)
         name = "myolo_mask_conv1/kernel"
         C.call("myolo_gemm_taps_wgrad_h", self.mah[0].rows, MASK_C, g1.rows, MASK_C, self.g[name], M, MASK_C, MASK_C, 9, sh3, 0,
                ugs, st)

@@ -316,3 +316,28 @@ def test_bn_backward_half_output(C):
     C.call("myolo_bn_bwd_h", x.view(), dy.view(), outh.view(), mean, var, gamma, beta, 1e-3, C.ACT_RELU, 1, dg, db, ws, sc, stream())
     assert torch.equal(outh.rows, (ref.rows * 128.0).half())
     assert torch.equal(dg, dg_r) and torch.equal(db, db_r)
+
+
+def test_bn_backward_half_in_half_out(C):
+    """batch-statistics BN backward on a loss-scaled half gradient, in place: dx keeps the scale, dgamma / dbeta do not"""
+    from myolo.pf import PF
+    torch.manual_seed(43)
+    n, P, Cc, S = 9, 14, 64, 256.0
+    x, dy = PF(n, P, P, Cc), PF(n, P, P, Cc)
+    x.valid().normal_()
+    dy.valid().copy_(hq(torch.randn(n, P, P, Cc, device="cuda") * 0.01))
+    gamma, beta = torch.rand(Cc, device="cuda") + 0.5, torch.randn(Cc, device="cuda") * 0.1
+    mean, var = torch.empty(Cc, device="cuda"), torch.empty(Cc, device="cuda")
+    ws = torch.zeros(4112, dtype=torch.float64, device="cuda")
+    C.call("myolo_bn_stats", x.view(), mean, var, ws, stream())
+    ref = PF(n, P, P, Cc)
+    dg_r, db_r, dg, db = (torch.empty(Cc, device="cuda") for _ in range(4))
+    C.call("myolo_bn_bwd", x.view(), dy.view(), ref.view(), mean, var, gamma, beta, 1e-3, C.ACT_RELU, 1, dg_r, db_r, ws, stream())
+    gh = PF(n, P, P, Cc, dtype=torch.float16)
+    gh.rows.copy_(dy.rows * S)
+    us = torch.tensor([1.0 / S], device="cuda")
+    C.call("myolo_bn_bwd_hh", x.view(), gh.view(), gh.view(), mean, var, gamma, beta, 1e-3, C.ACT_RELU, 1, dg, db, ws, us, stream())
+    close(gh.rows.float() / S, ref.rows, 6e-4, "dx (half, scaled)")
+    close(dg, dg_r, 1e-5, "dgamma")
+    close(db, db_r, 1e-5, "dbeta")
+    assert ws[:2064].abs().max().item() == 0, "tickets and sums are left zero (the coefficient table behind them is scratch)"
