@@ -129,6 +129,8 @@ class Engine:
         # side stream next to the data-gradient chain (they are 20-70 us kernels that fill a fraction of the SMs)
         self._side = torch.cuda.Stream(device=self.dev) if os.environ.get("MYOLO_BWD_STREAMS", "1") != "0" else None
         self._evs = {}
+        self._replay_on = os.environ.get("MYOLO_REPLAY", "1") != "0"
+        self._plan = None
         self.t = 0                     # Adam iteration
         self.seen = 0                  # yolo_custom_loss `seen` counter (model.py:95, 197)
         self._alloc_params(params if params is not None else init_params(self.NB, self.NC, seed))
@@ -407,15 +409,25 @@ class Engine:
         arr = self._shift_cache.get(key)
         if arr is None:
             arr = self._shift_cache[key] = C.int_array(sh)
-        timed = self.kernel_events is not None and name.startswith("myolo_mask_conv")
+        timed = name.startswith("myolo_mask_conv")
         if timed:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
+            C.record_py(self._ke_begin)
         C.call("myolo_gemm_taps", a_rows, K, self.wt[name], out_rows, N, M, N, K, len(sh), arr, bias, scale, shift,
                act, pf_w1, pf_blk, 0, self._st() if stream is None else stream)
         if timed:
+            C.record_py(self._ke_end)
+
+    def _ke_begin(self):
+        """bench.py hook: CUDA events around the dominant kernel (only while kernel_events is a list)"""
+        if self.kernel_events is not None:
+            self._ke0 = torch.cuda.Event(enable_timing=True)
+            self._ke0.record()
+
+    def _ke_end(self):
+        if self.kernel_events is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
-            self.kernel_events.append((e0, e1))
+            self.kernel_events.append((self._ke0, e1))
 
     def _bn_bwd(self, name, xv, dyv, act, training):
         b = self.bn[name]
@@ -470,13 +482,14 @@ class Engine:
                 fm_stream = None
                 if self._side is not None and os.environ.get("MYOLO_FM_OVERLAP", "1") != "0":
                     e = self._evs.setdefault("fm_fork", torch.cuda.Event())
-                    e.record(torch.cuda.current_stream())
-                    self._side.wait_event(e)
+                    cur, side_ = torch.cuda.current_stream(), self._side
+                    C.record_py(lambda: (e.record(cur), side_.wait_event(e)))
                     fm_stream = self._side.cuda_stream
                 self._gemm_fwd(self.c4.rows, self.c4.lo_off, "feature_map/kernel", self.feat.rows, self.c4.M, MASK_C, 512,
                                conv3x3_shifts(F_), self.p["feature_map/bias"], F_ + 1, (F_ + 1) * (F_ + 1), stream=fm_stream)
                 if fm_stream is not None:
-                    self._evs.setdefault("fm_done", torch.cuda.Event()).record(self._side)
+                    e2, side_ = self._evs.setdefault("fm_done", torch.cuda.Event()), self._side
+                    C.record_py(lambda: e2.record(side_))
                     self._fm_pending = True
         G, NB, NC = self.cfg["G"], self.NB, self.NC
         # conv_23 (model.py:271) + reshape [B,G,G,NB,5+NC] (273): a pure view of the NHWC result
@@ -493,7 +506,8 @@ class Engine:
         P_ = self.cfg["POOL"]
         npix = n * P_ * P_
         if getattr(self, "_fm_pending", False):      # the feature_map conv ran on the side stream
-            torch.cuda.current_stream().wait_event(self._evs["fm_done"])
+            cur, e2 = torch.cuda.current_stream(), self._evs["fm_done"]
+            C.record_py(lambda: cur.wait_event(e2))
             self._fm_pending = False
         if self.h16:
             return self._mask_head_h16(rois, training)
@@ -555,10 +569,7 @@ class Engine:
         for i in (1, 2, 3, 4):
             name = f"myolo_mask_conv{i}/kernel"
             a_in = self.mah[i - 1]
-            timed = self.kernel_events is not None
-            if timed:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
+            C.record_py(self._ke_begin)
             if training and i == 1:
                 # batch-statistics BN: the pre-BN tensor is kept in fp32 (statistics, backward)
                 C.call("myolo_gemm_taps_h", a_in.rows, MASK_C, self.wth[name], self.my[1].rows, MASK_C, None, 0, M, MASK_C, MASK_C,
@@ -571,9 +582,7 @@ class Engine:
                        M, MASK_C, MASK_C, 9, sh3, self.p[f"myolo_mask_conv{i}/bias"], self.bn_scale[i - 1],
                        self.bn_shift[i - 1], C.ACT_RELU, pfw, pfb, None, st)
                 self._mask_fused[i] = True
-            if timed:
-                e1.record()
-                self.kernel_events.append((e0, e1))
+            C.record_py(self._ke_end)
             if training and i == 1:
                 b = self.bn["myolo_mask_bn1"]
                 C.call("myolo_bn_stats", self.my[1].view(), b.mean, b.var, self.ws, st)
@@ -615,6 +624,11 @@ class Engine:
                mh, mw, top_k, float(cs_threshold), float(nms_threshold), idx, boxes, cls, score, cnt, pm, self._st())
         return idx, boxes, cls, score, cnt, pm
 
+    def _wait_inputs(self):
+        if self.inputs_ready is not None:
+            torch.cuda.current_stream().wait_event(self.inputs_ready)
+            self.inputs_ready = None
+
     def forward_training(self, inputs, learning_phase: bool = True):
         """mode='training' graph (model.py:844-901); learning_phase=False evaluates the same graph the way Keras
         validates (every BN on its moving statistics).  inputs as BatchGenerator yields them:
@@ -624,9 +638,7 @@ class Engine:
         A, B, st, cfg = self.A, self.B, self._st(), self.cfg
         G, NB, NC, TB, R = cfg["G"], self.NB, self.NC, self.TB, self.R
         yolo = self.forward(image, training=learning_phase)
-        if self.inputs_ready is not None:      # ground-truth tensors still in flight on the caller's copy stream
-            torch.cuda.current_stream().wait_event(self.inputs_ready)
-            self.inputs_ready = None
+        C.record_py(self._wait_inputs)         # ground-truth tensors still in flight on the caller's copy stream
         self.seen += 1
         warm = 1 if self.seen < cfg.get("WARM_UP_BATCHES", 0) else 0
         lw = cfg.get("LOSS_WEIGHTS", {})
@@ -655,12 +667,12 @@ class Engine:
         variable, into the flat gradient buffer.  `on_tail_ready()` is invoked once the
         feature_map + mask-head slice [tail_off:] is final (hook for the overlapped all-reduce)."""
         A, B, st = self.A, self.B, self._st()
-        self.grads.zero_()
+        C.record_py(self.grads.zero_)
         relu6 = C.ACT_RELU6
         if self.with_mask:
             self._backward_mask()
         if on_tail_ready is not None:
-            on_tail_ready()
+            C.record_py(on_tail_ready)
         G, NB, NC = self.cfg["G"], self.NB, self.NC
         ny = NB * (5 + NC)
         main, side = torch.cuda.current_stream(), self._side
@@ -675,16 +687,17 @@ class Engine:
         def fork(name):     # the side stream may start once everything issued on main so far is done
             if side is not None:
                 e = ev(name)
-                e.record(main)
-                side.wait_event(e)
+                C.record_py(lambda: (e.record(main), side.wait_event(e)))
 
         def mark(name):     # remember the side stream's position
             if side is not None:
-                ev(name).record(side)
+                e = ev(name)
+                C.record_py(lambda: e.record(side))
 
         def join(name):     # main waits for that position
             if side is not None and name in self._evs:
-                main.wait_event(self._evs[name])
+                e = self._evs[name]
+                C.record_py(lambda: main.wait_event(e))
 
         # conv_23
         dy = A["dyolo"]
@@ -835,7 +848,7 @@ class Engine:
         A, st, n = self.A, self._st(), self.n_roi
         P_, B, F_ = self.cfg["POOL"], self.B, self.F
         # CropAndResizeGradImage into the feature-map gradient
-        self.dfeat.storage.zero_()
+        C.record_py(self.dfeat.storage.zero_)
         C.call("myolo_roialign_bwd", g0.view(), A["rois"], n, self.R, P_, self.dfeat.view(), st)
         C.call("myolo_colsum", self.dfeat.view(), self.g["feature_map/bias"], self.ws, st)
         C.call("myolo_conv3x3_wgrad", self.c4.rows, self.dfeat.rows, self.g["feature_map/kernel"], B, F_, F_, 512, MASK_C, st)
@@ -878,13 +891,53 @@ class Engine:
 
     def train_step(self, inputs, lr: float = 1e-3, allreduce=None):
         """One fit step.  `allreduce(flat_grads, lo, hi)` (optional) sums gradient slices across
-        replicas; it is called for the tail bucket as soon as it is ready and for the head at the end."""
-        out = self.forward_training(inputs)
-        if allreduce is None:
-            self.backward()
-            scale = 1.0
+        replicas; it is called for the tail bucket as soon as it is ready and for the head at the end.
+
+        The forward + backward part is a fixed sequence of ~290 C-ABI launches with fixed arguments (only the input
+        pointers change), so it is recorded on the first step and replayed afterwards as raw ctypes calls
+        (MYOLO_REPLAY=0 disables this); the optimizer part carries per-step scalars and stays dynamic."""
+        if self._replay_on:
+            warm = 1 if (self.seen + 1) < self.cfg.get("WARM_UP_BATCHES", 0) else 0
+            key = (tuple((tuple(t.shape), t.dtype) for t in inputs), warm, id(allreduce),
+                   torch.cuda.current_stream().cuda_stream)
+            if self._plan is not None and self._plan["key"] == key:
+                out = self._replay_step(inputs)
+            else:
+                out = self._record_step(inputs, allreduce, key)
         else:
-            self.backward(on_tail_ready=lambda: allreduce(self.grads, self.tail_off, self.n_flat))
-            scale = allreduce(self.grads, 0, self.tail_off)
+            out = self.forward_training(inputs)
+            if allreduce is None:
+                self.backward()
+            else:
+                self.backward(on_tail_ready=lambda: allreduce(self.grads, self.tail_off, self.n_flat))
+        scale = allreduce(self.grads, 0, self.tail_off) if allreduce is not None else 1.0
         self.apply_updates(lr, scale if scale is not None else 1.0)
         return out
+
+    def _record_step(self, inputs, allreduce, key):
+        self._plan = None
+        C.start_recording()
+        try:
+            out = self.forward_training(inputs)
+            if allreduce is None:
+                self.backward()
+            else:
+                self.backward(on_tail_ready=lambda: allreduce(self.grads, self.tail_off, self.n_flat))
+        finally:
+            entries = C.stop_recording()
+        ptrs = {t.data_ptr(): k for k, t in enumerate(inputs)}
+        assert len(ptrs) == len(inputs), "input tensors must not alias each other"
+        patches = [(e[1], ai, ptrs[v]) for e in entries if e[0] is not None
+                   for ai, v in enumerate(e[1]) if type(v) is int and v in ptrs]
+        self._plan = dict(key=key, entries=entries, patches=patches, out=out, bn_touched=list(self._bn_touched))
+        return out
+
+    def _replay_step(self, inputs):
+        plan = self._plan
+        for conv, ai, k in plan["patches"]:
+            conv[ai] = inputs[k].data_ptr()
+        self._image = inputs[0]
+        self._bn_touched = list(plan["bn_touched"])
+        self.seen += 1
+        C.replay(plan["entries"])
+        return plan["out"]
