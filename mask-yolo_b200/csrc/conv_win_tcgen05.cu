@@ -129,20 +129,21 @@ __device__ __forceinline__ void mask_tail_chunk(float (&v)[32], uint32_t evs, in
   }
 }
 
-// all 256 columns of one accumulator row; the TMEM load of the next chunk is in flight while a chunk is processed
+// columns [cb, ce) of one accumulator row (a multiple of 64 wide); the TMEM load of the next chunk is in flight while
+// a chunk is processed
 template <int NCT>
-__device__ __forceinline__ void mask_tail_row(uint32_t taddr, uint32_t evs, float* ypos, float (&lg)[8][2]) {
+__device__ __forceinline__ void mask_tail_row(uint32_t taddr, uint32_t evs, float* ypos, float (&lg)[8][2], int cb, int ce) {
   float va[32], vb[32];
-  tmem_ld32_issue(taddr, va);
+  tmem_ld32_issue(taddr + (uint32_t)cb, va);
   tmem_ld_wait(va);
 #pragma unroll 1
-  for (int c0 = 0; c0 < 256; c0 += 64) {
+  for (int c0 = cb; c0 < ce; c0 += 64) {
     tmem_ld32_issue(taddr + (uint32_t)(c0 + 32), vb);
     mask_tail_chunk<NCT>(va, evs, c0, ypos, lg);
     tmem_ld_wait(vb);
-    if (c0 + 64 < 256) tmem_ld32_issue(taddr + (uint32_t)(c0 + 64), va);
+    if (c0 + 64 < ce) tmem_ld32_issue(taddr + (uint32_t)(c0 + 64), va);
     mask_tail_chunk<NCT>(vb, evs, c0 + 32, ypos, lg);
-    if (c0 + 64 < 256) tmem_ld_wait(va);
+    if (c0 + 64 < ce) tmem_ld_wait(va);
   }
 }
 
@@ -169,10 +170,18 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int cid = blockIdx.x / CG, ncl = gridDim.x / CG;   // work is distributed over clusters
   constexpr uint32_t TS = (WBN * NACC <= 256) ? 2 : 1;     // TMEM stages (epilogue overlapped when 2)
   constexpr uint32_t TSTRIDE = WBN * NACC;                  // TMEM columns per stage
-  __shared__ __align__(8) uint64_t bars[2 + 2 + kWBStages * 2 + 4];
+  // Ring depths.  A multi-tap conv spends ntaps weight stages per activation window, so two windows and a deep weight
+  // ring keep the tensor core fed.  A single-tap GEMM (deconv forward / dgrad, pointwise dgrads) consumes a window
+  // per weight stage: with two windows the producer ran only ~0.6 us ahead of the MMAs -- less than one TMA round
+  // trip -- and the kernel was latency-bound at 25 % tensor pipe (ncu: epilogue warps parked on t_full).  There the
+  // same shared memory is split four windows / five weight stages.
+  constexpr int kMaxAWin = NACC == 1 ? 4 : 2;
+  const int nawin = (ntaps == 1 && NACC == 1) ? 4 : 2;
+  const int nwb = (ntaps == 1 && NACC == 1) ? (int)((2 * kWinBytes + kWBStages * kWBBytes - 4 * kWinBytes) / kWBBytes) : kWBStages;
+  __shared__ __align__(8) uint64_t bars[2 * kMaxAWin + kWBStages * 2 + 4];
   __shared__ uint32_t tmem_slot;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t awin0 = base, bst0 = base + 2 * kWinBytes, stg0 = bst0 + kWBStages * kWBBytes;
+  const uint32_t awin0 = base, bst0 = base + (uint32_t)nawin * kWinBytes, stg0 = base + 2 * kWinBytes + kWBStages * kWBBytes;
   float* colacc = reinterpret_cast<float*>(smem_raw + (stg0 + kWStageOut - smem_u32(smem_raw)));          // [2][256]
   float* evec = reinterpret_cast<float*>(smem_raw + (stg0 + kWStageOut + kWColAcc - smem_u32(smem_raw)));  // [scale N | shift N]
   constexpr int kEpiWarps = win_threads(EL) / 32 - 2;
@@ -182,20 +191,22 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int nh = N / WBN;
   const uint32_t bar0 = smem_u32(bars);
   auto a_full = [&](int i) { return bar0 + 8u * i; };
-  auto a_empty = [&](int i) { return bar0 + 8u * (2 + i); };
-  auto b_full = [&](int i) { return bar0 + 8u * (4 + i); };
-  auto b_empty = [&](int i) { return bar0 + 8u * (4 + kWBStages + i); };
-  auto t_full = [&](int i) { return bar0 + 8u * (4 + 2 * kWBStages + i); };
-  auto t_empty = [&](int i) { return bar0 + 8u * (6 + 2 * kWBStages + i); };
+  auto a_empty = [&](int i) { return bar0 + 8u * (kMaxAWin + i); };
+  auto b_full = [&](int i) { return bar0 + 8u * (2 * kMaxAWin + i); };
+  auto b_empty = [&](int i) { return bar0 + 8u * (2 * kMaxAWin + kWBStages + i); };
+  auto t_full = [&](int i) { return bar0 + 8u * (2 * kMaxAWin + 2 * kWBStages + i); };
+  auto t_empty = [&](int i) { return bar0 + 8u * (2 * kMaxAWin + 2 * kWBStages + 2 + i); };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmC);
     if (EL == 2) tma_prefetch_desc(&tmCh);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kMaxAWin; ++i) {
       mbar_init(a_full(i), 1);
       mbar_init(a_empty(i), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(t_full(i), 1);
       mbar_init(t_empty(i), kEpiWarps * CG);  // one arrival per epilogue warp (of both CTAs of a pair)
     }
@@ -238,13 +249,14 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
   if (warp == 0) {
     if (lane == 0) {
-      uint32_t a_it = 0, b_it = 0;
+      // ring positions and phases are advanced incrementally: the depths are run-time values, and a division per tap
+      // on the single issuing thread costs more than the four MMAs it sits between
+      uint32_t ab = 0, aph = 0, s = 0, bph = 0;
       for (int item = cid; item < nitems; item += ncl) {
         const int tile = item / nh, half = item - tile * nh;
         const int row0 = tile * (WBM * CG) + (int)rank * WBM - WHALO;
         for (int kb = 0; kb < kblocks; ++kb) {
-          const uint32_t ab = a_it & 1u;
-          mbar_wait(a_empty(ab), ((a_it >> 1) & 1u) ^ 1u);
+          mbar_wait(a_empty(ab), aph ^ 1u);
           const uint32_t wa = awin0 + ab * kWinBytes;
           if (CG == 2) {
             // both CTAs' loads complete on the LEADER's barrier, which expects the bytes of the pair
@@ -257,10 +269,9 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             tma_load_2d(wa, &tmA, a_full(ab), kb * KEL, row0);
             if (NACC == 2) tma_load_2d(wa + WBOX * 128, &tmA, a_full(ab), kb * KEL, row0 + WBOX);
           }
-          ++a_it;
-          for (int t = 0; t < ntaps; ++t, ++b_it) {
-            const uint32_t s = b_it % kWBStages;
-            mbar_wait(b_empty(s), ((b_it / kWBStages) & 1u) ^ 1u);
+          if (++ab == (uint32_t)nawin) { ab = 0; aph ^= 1u; }
+          for (int t = 0; t < ntaps; ++t) {
+            mbar_wait(b_empty(s), bph ^ 1u);
             if (CG == 2) {
               if (leader) mbar_expect_tx(b_full(s), 2 * kWBBytes);
               tma_load_2d_2sm(bst0 + s * kWBBytes, &tmB, mapa_rank(b_full(s), 0), kb * KEL,
@@ -271,6 +282,7 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               mbar_expect_tx(b_full(s), kWBBytes);
               tma_load_2d(bst0 + s * kWBBytes, &tmB, b_full(s), kb * KEL, t * N + half * WBN);
             }
+            if (++s == (uint32_t)nwb) { s = 0; bph ^= 1u; }
           }
         }
       }
@@ -278,20 +290,18 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   } else if (warp == 1) {
     if (lane == 0 && leader) {
       constexpr uint32_t idesc = EL == 2 ? make_idesc_f16(128 * CG, WBN, 0, 0) : make_idesc(128 * CG, WBN, 0, 0);
-      uint32_t a_it = 0, b_it = 0, it = 0;
+      uint32_t ab = 0, aph = 0, s = 0, bph = 0, it = 0;
       for (int item = cid; item < nitems; item += ncl, ++it) {
         const uint32_t ts = it % TS;
         mbar_wait(t_empty(ts), ((it / TS) & 1u) ^ 1u);  // the epilogue that last used this TMEM stage has drained it
         tc_fence_after();
         const uint32_t tacc = tmem + ts * TSTRIDE;
-        for (int kb = 0; kb < kblocks; ++kb, ++a_it) {
-          const uint32_t ab = a_it & 1u;
-          mbar_wait(a_full(ab), (a_it >> 1) & 1u);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(a_full(ab), aph);
           tc_fence_after();
           const uint32_t wa = awin0 + ab * kWinBytes;
-          for (int t = 0; t < ntaps; ++t, ++b_it) {
-            const uint32_t s = b_it % kWBStages;
-            mbar_wait(b_full(s), (b_it / kWBStages) & 1u);
+          for (int t = 0; t < ntaps; ++t) {
+            mbar_wait(b_full(s), bph);
             tc_fence_after();
             const uint32_t row = (uint32_t)(WHALO + sh.s[t]);
             const uint64_t db = make_desc(bst0 + s * kWBBytes, 16, 1024);
@@ -314,8 +324,10 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               }
             }
             if (CG == 2) umma_commit_2sm(b_empty(s)); else umma_commit(b_empty(s));
+            if (++s == (uint32_t)nwb) { s = 0; bph ^= 1u; }
           }
           if (CG == 2) umma_commit_2sm(a_empty(ab)); else umma_commit(a_empty(ab));
+          if (++ab == (uint32_t)nawin) { ab = 0; aph ^= 1u; }
         }
         if (CG == 2) umma_commit_2sm(t_full(ts)); else umma_commit(t_full(ts));
       }
@@ -352,7 +364,10 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       tc_fence_after();
       if (WBN == 256 && mt.masks) {
 #pragma unroll 1
-        for (int acc = 0; acc < (eh == 0 ? NACC : 0); ++acc) {   // LSU-bound tail: one warp per lane quarter does all 256 columns
+        // the tail is bound by the latency of ONE warp per scheduler (ncu: 0.35 IPC, shared-memory pipe 36 %), so with
+        // eight epilogue warps (EL = 2) the two warps of a lane quarter take 128 channels each and the second hands
+        // its partial logits over through shared memory (one named barrier per item, double-buffered by item parity)
+        for (int acc = 0; acc < NACC; ++acc) {
           const long long m = (long long)tile * WBM + acc * 128 + q * 32 + lane;
           const bool valid = (m < M) && pf_valid(m, ep.pf_w1, ep.pf_blk);
           int roi = 0, hh = 0, ww = 0;
@@ -370,22 +385,41 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           {
             const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + ts * TSTRIDE + (uint32_t)(acc * 256);
             float* ypos = pos ? mt.y4 + (size_t)m * N + half * 256 : nullptr;
+            const int tcb = EL == 2 ? eh * 128 : 0, tce = EL == 2 ? tcb + 128 : 256;
             switch (mt.NC) {
-              case 1: mask_tail_row<1>(taddr, evs, ypos, lg); break;
-              case 2: mask_tail_row<2>(taddr, evs, ypos, lg); break;
-              case 3: mask_tail_row<3>(taddr, evs, ypos, lg); break;
-              case 4: mask_tail_row<4>(taddr, evs, ypos, lg); break;
-              case 5: mask_tail_row<5>(taddr, evs, ypos, lg); break;
-              case 6: mask_tail_row<6>(taddr, evs, ypos, lg); break;
-              default: mask_tail_row<7>(taddr, evs, ypos, lg); break;
+              case 1: mask_tail_row<1>(taddr, evs, ypos, lg, tcb, tce); break;
+              case 2: mask_tail_row<2>(taddr, evs, ypos, lg, tcb, tce); break;
+              case 3: mask_tail_row<3>(taddr, evs, ypos, lg, tcb, tce); break;
+              case 4: mask_tail_row<4>(taddr, evs, ypos, lg, tcb, tce); break;
+              case 5: mask_tail_row<5>(taddr, evs, ypos, lg, tcb, tce); break;
+              case 6: mask_tail_row<6>(taddr, evs, ypos, lg, tcb, tce); break;
+              default: mask_tail_row<7>(taddr, evs, ypos, lg, tcb, tce); break;
             }
+          }
+          float lgs[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) lgs[k] = lg[k][0] + lg[k][1];
+          if (EL == 2) {
+            const uint32_t xbuf = stg0 + (uint32_t)(q + 4) * 4096u + (((it * NACC + acc) & 1u) ? 1024u : 0u) + (uint32_t)lane * 32u;
+            if (eh == 1) {
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(xbuf), "f"(lgs[0]), "f"(lgs[1]), "f"(lgs[2]), "f"(lgs[3]) : "memory");
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(xbuf + 16u), "f"(lgs[4]), "f"(lgs[5]), "f"(lgs[6]), "f"(lgs[7]) : "memory");
+              asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+              continue;          // the first warp of the quarter finishes the pixel
+            }
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+            float4 p0, p1;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(p0.x), "=f"(p0.y), "=f"(p0.z), "=f"(p0.w) : "r"(xbuf) : "memory");
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(p1.x), "=f"(p1.y), "=f"(p1.z), "=f"(p1.w) : "r"(xbuf + 16u) : "memory");
+            lgs[0] += p0.x; lgs[1] += p0.y; lgs[2] += p0.z; lgs[3] += p0.w;
+            lgs[4] += p1.x; lgs[5] += p1.y; lgs[6] += p1.z; lgs[7] += p1.w;
           }
           if (valid) {
             const int a = half >> 1, b = half & 1;
             float* out = mt.masks + ((((size_t)roi * 2 * mt.H + 2 * hh + a) * 2 * mt.W) + 2 * ww + b) * mt.NC;
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-              if (k < mt.NC) out[k] = 1.f / (1.f + expf(-(lg[k][0] + lg[k][1] + __ldg(mt.b1 + k))));
+              if (k < mt.NC) out[k] = 1.f / (1.f + expf(-(lgs[k] + __ldg(mt.b1 + k))));
           }
         }
       } else

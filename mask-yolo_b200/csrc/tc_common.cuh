@@ -194,8 +194,11 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t local_addr, uint32_t rank
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
   return r;
 }
+// (default .release.cta semantics: the explicit .release.cluster form compiles to MEMBAR.ALL.GPU + ERRBAR, which made
+// every epilogue warp wait for its own global stores before handing the TMEM stage back -- 11 % of the deconv kernel's
+// stall samples.  The hand-back orders tcgen05.ld, which tcgen05.fence::before_thread_sync already covers.)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 // TMA load whose completion is signalled on a barrier of the pair's LEADER CTA (cluster address)
 __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0, int c1) {

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 PKG_ROOT = os.path.dirname(_HERE)                      # mask-yolo_b200/
 REPO_ROOT = os.path.dirname(PKG_ROOT)
 HEADER = os.path.join(REPO_ROOT, "include", "myolo_b200.h")
-LIB_PATH = os.path.join(PKG_ROOT, "lib", "libmyolo_sm100.so")
+LIB_PATH = os.environ.get("MYOLO_LIB") or os.path.join(PKG_ROOT, "lib", "libmyolo_sm100.so")   # MYOLO_LIB: A/B runs of two builds
 
 ACT_NONE, ACT_RELU, ACT_RELU6 = 0, 1, 2
 ROUND_TF32 = 0x100
