@@ -690,3 +690,29 @@ def test_staging_helpers_split_fold_copy_and_batched_moving_update(C):
         C.call("myolo_bn_moving_update", val[1], bi[3], mo[3], Cc, 0.99, step, 1, npix, 1e-3, stream())
         close(mo[0], mo[2], 1e-6, "batched moving mean")
         close(mo[1], mo[3], 1e-6, "batched moving var")
+
+
+def test_prep_weights_batch_equals_single_jobs(C):
+    """one-launch staging (device job table) against the per-job entry points, all four modes"""
+    import struct
+    torch.manual_seed(50)
+    specs = [(9, 64, 96, 1, 1), (1, 100, 40, 0, 0), (3, 32, 256, 1, 2), (9, 256, 256, 0, 3), (1, 1024, 256, 1, 3), (2, 33, 65, 1, 3)]
+    rec, tiles, outs, refs = b"", 0, [], []
+    keep = []
+    for ntaps, rows, cols, tr, mode in specs:
+        w = torch.randn(ntaps, rows, cols, device="cuda")
+        n = ntaps * rows * cols
+        if mode == 3:
+            out, ref = torch.zeros(n, dtype=torch.float16, device="cuda"), torch.zeros(n, dtype=torch.float16, device="cuda")
+            C.call("myolo_prep_weights_h", w, ref, ntaps, rows, cols, tr, stream())
+        else:
+            out, ref = torch.zeros(n * (3 if mode == 2 else 1), device="cuda"), torch.zeros(n * (3 if mode == 2 else 1), device="cuda")
+            C.call("myolo_prep_weights", w, ref, ntaps, rows, cols, tr, mode, stream())
+        rec += struct.pack("<QQiiiiii", w.data_ptr(), out.data_ptr(), ntaps, rows, cols, tr, mode, tiles)
+        tiles += ntaps * ((rows + 31) // 32) * ((cols + 31) // 32)
+        outs.append(out); refs.append(ref); keep.append(w)
+    table = torch.frombuffer(bytearray(rec), dtype=torch.uint8).cuda()
+    C.call("myolo_prep_weights_batch", table, len(specs), tiles, stream())
+    torch.cuda.synchronize()
+    for o, r, sp in zip(outs, refs, specs):
+        assert torch.equal(o, r), sp

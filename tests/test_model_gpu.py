@@ -269,3 +269,42 @@ def test_edge_cases_no_ground_truth_and_nan_free():
         assert g2["myolo_mask_conv3/kernel"].abs().max().item() == 0 and g2["feature_map/kernel"].abs().max().item() == 0
         assert g2["conv_pw_3/kernel"].abs().max().item() > 0          # the yolo loss still trains the backbone
         assert all(torch.isfinite(v).all() for v in g2.values())
+
+
+def test_replayed_steps_equal_recorded_steps():
+    """Engine.train_step records the launch sequence of its first step and replays it afterwards with patched input
+    pointers.  Steps on three different batches (different device tensors each step) must produce the same losses and
+    gradients as the same steps issued through the ordinary Python path.  The learning rate is 0 so that the weights
+    stay put (the first Adam step is lr*sign(g): atomics-order noise on near-zero gradients would otherwise make any
+    two runs drift apart and hide what this test is about); BN moving averages still advance."""
+    from myolo.engine import Engine, init_params
+    S, B = 96, 3
+    c = Hh.engine_cfg(S=S)
+    P = init_params(c["NB"], c["NC"], 21, "trained_like")
+    batches = []
+    for k in range(3):
+        img = torch.rand(B, S, S, 3, generator=torch.Generator().manual_seed(70 + k))
+        batches.append(Hh.to_device(Hh.batch_from_boxes(c, B, img, Hh.random_boxes(B, 2, 80 + k), 90 + k)))
+    res = {}
+    for mode in ("replay", "python"):
+        eng = Engine(c, B, "training", "h16", params=P)
+        eng._replay_on = mode == "replay"
+        losses, grads = [], []
+        for k in (0, 1, 2, 1, 0):
+            out = eng.train_step(batches[k], lr=0.0)
+            losses.append((out["yolo_sum_loss"].item(), out["mask_loss"].item(), int(eng.n_pos.sum().item())))
+            grads.append(eng.grad_dict())
+        torch.cuda.synchronize()
+        assert (eng._plan is not None) == (mode == "replay")
+        res[mode] = (losses, grads, eng.state_dict())
+    (la, ga, pa), (lb, gb, pb) = res["replay"], res["python"]
+    assert len({l[:2] for l in la[:3]}) == 3, "the three batches must differ"
+    for (y1, m1, n1), (y2, m2, n2) in zip(la, lb):
+        assert n1 == n2
+        assert abs(y1 - y2) <= 1e-5 * max(1.0, abs(y2)) and abs(m1 - m2) <= 1e-5 * max(1.0, abs(m2)), (la, lb)
+    for step, (g1, g2) in enumerate(zip(ga, gb)):
+        for k in g1:
+            if g2[k].abs().max() > 0:
+                assert _l2(g1[k], g2[k]) <= 1e-3, (step, k)
+    for k in pa:
+        assert _l2(pa[k], pb[k]) <= 1e-5, k
