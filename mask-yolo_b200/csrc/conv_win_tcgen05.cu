@@ -11,7 +11,8 @@
 // address, so a row-shifted start needs no base_offset).  Default configuration (template <256, 1, 2>):
 //   * CTA pair (cluster of 2, cta_group::2): one 256-row MMA spans both SMs; each CTA holds its own 128 rows
 //     (window + TMEM accumulator) and HALF of every weight stage -> L2->SM fill per FLOP halves;
-//   * 8-stage weight ring (16 KB per CTA per stage), double-buffered activation window;
+//   * 8-stage weight ring (16 KB per CTA per stage), double-buffered activation window; single-tap GEMMs split the
+//     same shared memory four windows / five weight stages (they consume a window per weight stage);
 //   * two TMEM stages: the epilogue of item i overlaps the main loop of item i+1;
 //   * epilogue through swizzled shared-memory staging + TMA tensor stores (a thread owns one output ROW;
 //     storing rows straight to global memory cost as much as the whole main loop).
@@ -19,8 +20,13 @@
 // layer's BN + ReLU with its dgamma / dbeta column sums (dgrad, myolo_gemm_taps_bnbwd); the whole mask tail
 // (deconv bias + ReLU + 1x1 conv + sigmoid, myolo_deconv_mask_fwd).
 //
-// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (leader CTA only),
-// warps 2..5 = epilogue.  Persistent: cluster i processes items i, i+n_clusters, ...
+// Two operand flavours (template parameter EL): 4 = fp32 words read by kind::tf32; 2 = IEEE half on kind::f16 (the
+// "h16" precision mode of the mask head: twice the tensor rate, half the operand bytes, fp32 accumulation; the epilogue
+// stores half or fp32, and the fused BN backward works in registers with butterfly column sums).
+//
+// Roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (leader CTA only), then the epilogue warps:
+// 4 (EL = 4, 192 threads) or 8 (EL = 2, 320 threads: two per TMEM lane quarter, half of the columns each).
+// Persistent: cluster i processes items i, i+n_clusters, ...
 // Replaces the Conv2D / Conv2DBackpropInput / Conv2DTranspose call sites of the mask head
 // (myolo/model.py:688-713) and the large pointwise GEMMs of the backbone.
 // MYOLO_WIN_BO (experiment switches, default 0): 2 no TMA loads, 4 no global stores, 8 128-column slices,
@@ -344,7 +350,6 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const uint32_t sbuf0 = stg0 + (uint32_t)(EL == 2 ? ew : q) * 4096u;
     const bool st_f32 = !(EL == 2 && ep.no_f32), st_h = EL == 2 && ep.has_h;
     const bool ring_h = EL == 2 && st_h;
-    constexpr bool ring_f = false;
     auto wait_store = [&]() {
       if (lane == 0) {
         if (ring_h) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -504,7 +509,7 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               if (mrow0 < M && !(dbg & 4)) {
                 if (st_f32) tma_store_2d(&tmC, sbuf, n0, mrow0);
                 if (st_h) tma_store_2d(&tmCh, sbufh, n0, mrow0);
-              } else if (ring_h || ring_f) {
+              } else if (ring_h) {
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
               }
             }
@@ -612,8 +617,8 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             if (mrow0 < M && !(dbg & 4)) {
               if (st_f32) tma_store_2d(&tmC, sbuf, n0, mrow0);
               if (st_h) tma_store_2d(&tmCh, sbufh, n0, mrow0);
-            } else if (ring_h || ring_f) {
-              asm volatile("cp.async.bulk.commit_group;" ::: "memory");   // keep one group per chunk: the rings count groups
+            } else if (ring_h) {
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");   // keep one group per chunk: the ring counts groups
             }
           }
         }
