@@ -318,8 +318,9 @@ int myolo_yolo_loss(const float* y_true, const float* y_pred, const float* true_
                     float* loss_out, float* dy_pred, double* ws, myolo_stream stream);
 
 /* ---- inference post-processing, myolo/model.py:1290-1304 + 1330-1391 (myolo_utils.py:88-113 NMB, 883-912 unmold_mask) ----
- * per image: the top_k detections by confidence that reach cs_threshold, greedy suppression (a box survives
- * if IoU < nms_threshold against every kept box), then each survivor's class mask resized (bilinear, pixel
+ * per image: the top_k detections by confidence that reach cs_threshold, NMB suppression exactly as the reference
+ * does it (a candidate is dropped when any EARLIER candidate of the SAME class -- dropped or not -- has IoU >=
+ * nms_threshold with it), then each survivor's class mask resized (bilinear, pixel
  * centres aligned) to its pixel box, thresholded at 0.5 and pasted into an S x S byte image.
  * detections [B,R,6] = DetectionsLayer output; masks [B,R,MH,MW,NC] (nullable together with out_masks).
  * out_index [B,top_k] (detection index or -1), out_boxes [B,top_k,4] int32 pixels (x1,y1,x2,y2) clipped to

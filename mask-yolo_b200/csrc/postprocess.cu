@@ -1,6 +1,6 @@
 // postprocess.cu -- inference post-processing on the device: what MaskYOLO.detect does
 // in numpy after keras_model.predict (myolo/model.py:1290-1304, 1330-1391; myolo_utils.py:88-113 NMB,
-// 883-912 unmold_mask): top-k detections by confidence, confidence threshold, greedy box suppression,
+// 883-912 unmold_mask): top-k detections by confidence, confidence threshold, NMB box suppression (the reference's rule),
 // and pasting each survivor's class-specific 28x28 soft mask into its pixel box (bilinear resize,
 // threshold 0.5).  One block per image for the selection, one block per (detection, image) for the paste.
 #include <math_constants.h>
@@ -62,13 +62,19 @@ detect_select_kernel(const float* __restrict__ det, int R, int S, int top_k, flo
     }
     __syncthreads();
   }
-  if (tid == 0) {                                   // NMB: greedy, a box survives if IoU < thr with every kept one
+  if (tid == 0) {
+    // NMB exactly as myolo_utils.py:88-113 (pinned by the reference's own outputs, tests/golden): candidate c is
+    // dropped when ANY earlier candidate j of the same class overlaps it by >= thr -- also a j that was dropped
+    // itself (this is not greedy NMS).
     int kept = 0;
     int keep[kMaxTopK];
     for (int c = 0; c < ncand; ++c) {
       const float* p = D + (size_t)cand[c] * 6;
       bool ok = true;
-      for (int j = 0; j < kept && ok; ++j) ok = box_iou(D + (size_t)keep[j] * 6, p) < nms_thr;
+      for (int j = 0; j < c && ok; ++j) {
+        const float* q = D + (size_t)cand[j] * 6;
+        ok = !(q[5] == p[5] && box_iou(q, p) >= nms_thr);
+      }
       if (ok) keep[kept++] = cand[c];
     }
     for (int j = 0; j < top_k; ++j) {

@@ -450,8 +450,8 @@ class MaskYOLO:
             self.load_weights(weights_dir)
         x = (image / 255.)[None].astype(np.float32)
         netout = self._predict_b1(x)[0][0]
-        return mutils.decode_one_yolo_output(netout, self.cfg["ANCHORS"], nms_threshold=0.3, obj_threshold=0.3,
-                                             nb_class=self.cfg["NC"])
+        return mutils.decode_one_yolo_output(netout, anchors=self.cfg["ANCHORS"], nms_threshold=0.3, obj_threshold=0.35,
+                                             nb_class=self.cfg["NC"])       # thresholds of model.py:1227-1231
 
     def _engine_b1(self):
         """Batch-1 engine sharing this model's weights (detect / infer_yolo run one image at a time)."""
@@ -484,7 +484,7 @@ class MaskYOLO:
         eng = self._engine_b1()
         x = torch.from_numpy((image / 255.)[None].astype(np.float32)).to(eng.dev)
         eng.forward_inference(x)
-        idx, boxes, cls, score, cnt, pm = eng.postprocess(top_k=top_k, cs_threshold=cs_threshold, nms_threshold=0.5)
+        idx, boxes, cls, score, cnt, pm = eng.postprocess(top_k=top_k, cs_threshold=cs_threshold, nms_threshold=0.7)   # model.py:1304
         n = int(cnt[0].item())
         masks = pm[0, :n].permute(1, 2, 0).bool().cpu().numpy() if n else np.zeros(tuple(image.shape[:2]) + (0,), bool)
         return {"rois": boxes[0, :n].cpu().numpy(), "class_ids": cls[0, :n].cpu().numpy(),

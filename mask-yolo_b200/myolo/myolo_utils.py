@@ -343,11 +343,12 @@ def batch_slice(inputs, graph_fn, batch_size, names=None):
 
 
 # --------------------------------------------------------------------------- inference post-processing
-def decode_one_yolo_output(netout, anchors, nms_threshold=0.3, obj_threshold=0.3, nb_class=None):
-    """numpy YOLO decode + greedy per-class NMS of ONE image's [GH,GW,NB,5+NC] output
-    (myolo_utils.py:36-85).  Returns BoundBox list with normalised corner coordinates."""
+def decode_one_yolo_output(netout, anchors, nb_class=None, obj_threshold=0.3, nms_threshold=0.3):
+    """numpy YOLO decode + per-class NMS of ONE image's [GH,GW,NB,5+NC] output, argument order and arithmetic of
+    myolo_utils.py:36-85 (pinned by tests/test_reference_golden.py).  Returns BoundBox list with normalised corner
+    coordinates.  Unlike the reference the caller's array is not modified."""
     gh, gw, nb = netout.shape[:3]
-    netout = np.array(netout, dtype=np.float64, copy=True)
+    netout = np.array(netout, copy=True)
     nb_class = netout.shape[-1] - 5 if nb_class is None else nb_class
     netout[..., 4] = _sigmoid(netout[..., 4])
     netout[..., 5:] = netout[..., 4][..., np.newaxis] * _softmax(netout[..., 5:])
@@ -375,24 +376,32 @@ def decode_one_yolo_output(netout, anchors, nms_threshold=0.3, obj_threshold=0.3
     return [bx for bx in boxes if bx.get_score() > obj_threshold]
 
 
-def bbox_iou_2(box1, box2):
-    """IoU of two (x1, y1, x2, y2) sequences (myolo_utils.py:201-228)."""
-    iw = _interval_overlap([box1[0], box1[2]], [box2[0], box2[2]])
-    ih = _interval_overlap([box1[1], box1[3]], [box2[1], box2[3]])
+def bbox_iou_2(box1, box2, image_shape=None):
+    """IoU of two normalised (x1, y1, x2, y2) sequences, evaluated in pixels of `image_shape` exactly like
+    myolo_utils.py:201-228 (image_shape None: coordinates taken as they are)."""
+    w, h = (image_shape[0], image_shape[1]) if image_shape is not None else (1, 1)
+    b1 = (box1[0] * w, box1[1] * h, box1[2] * w, box1[3] * h)
+    b2 = (box2[0] * w, box2[1] * h, box2[2] * w, box2[3] * h)
+    iw = _interval_overlap([b1[0], b1[2]], [b2[0], b2[2]])
+    ih = _interval_overlap([b1[1], b1[3]], [b2[1], b2[3]])
     inter = iw * ih
-    union = (box1[2] - box1[0]) * (box1[3] - box1[1]) + (box2[2] - box2[0]) * (box2[3] - box2[1]) - inter
+    w1, h1 = b1[2] - b1[0], b1[3] - b1[1]
+    w2, h2 = b2[2] - b2[0], b2[3] - b2[1]
+    union = w1 * h1 + w2 * h2 - inter
     return float(inter) / union
 
 
-def NMB(boxes, scores, threshold=0.5):
-    """Greedy suppression over score-sorted boxes; returns the kept indices (myolo_utils.py:88-113)."""
-    order = list(np.argsort(scores)[::-1])
-    keep = []
-    while order:
-        i = order.pop(0)
-        keep.append(int(i))
-        order = [j for j in order if bbox_iou_2(boxes[i], boxes[j]) < threshold]
-    return keep
+def NMB(boxes, class_ids, indices, image_shape, nms_threshold=0.3):
+    """"Suppress non-maximal boxes" exactly as myolo_utils.py:88-113: `boxes` / `class_ids` are the candidates in
+    descending score order, `indices` their detection indices; candidate j is dropped when ANY earlier candidate i
+    of the same class has IoU >= nms_threshold with it -- including an i that was dropped itself (this is not
+    greedy NMS; pinned by tests/test_reference_golden.py).  Returns the surviving entries of `indices`."""
+    remove = []
+    for i in range(len(indices)):
+        for j in range(i + 1, len(indices)):
+            if bbox_iou_2(boxes[i], boxes[j], image_shape) >= nms_threshold and class_ids[i] == class_ids[j]:
+                remove.append(j)
+    return np.delete(indices, remove)
 
 
 def unmold_mask(mask, bbox, image_shape):

@@ -36,7 +36,9 @@ def test_extract_bboxes_and_iou_helpers():
     assert abs(mutils.bbox_iou(a, c) - 1 / 7) < 1e-12
     assert mutils.bbox_iou(a, mutils.BoundBox(5, 5, 6, 6)) == 0
     assert mutils._interval_overlap([0, 2], [1, 5]) == 1 and mutils._interval_overlap([3, 4], [0, 1]) == 0
-    assert mutils.NMB(np.array([[0, 0, 10, 10], [1, 1, 10, 10], [20, 20, 30, 30]]), np.array([0.9, 0.8, 0.7])) == [0, 2]
+    bx = np.array([[0, 0, 10, 10], [1, 1, 10, 10], [20, 20, 30, 30]]) / 32.0
+    assert mutils.NMB(bx, np.array([1, 1, 1]), np.array([7, 3, 5]), [32, 32, 3], nms_threshold=0.5).tolist() == [7, 5]
+    assert mutils.NMB(bx, np.array([1, 2, 1]), np.array([7, 3, 5]), [32, 32, 3], nms_threshold=0.5).tolist() == [7, 3, 5]
 
 
 def test_batch_generator_encoding():

@@ -553,7 +553,8 @@ def test_deconv_mask_fused(C):
 
 def test_detect_postprocess_matches_numpy_pipeline(C):
     """Device top-k / threshold / NMB / mask paste against the host functions that restate
-    myolo_utils.NMB (88-113) and unmold_mask (883-912)."""
+    myolo_utils.NMB (88-113; itself pinned to the reference's outputs by tests/test_reference_golden.py) and
+    unmold_mask (883-912)."""
     from myolo import myolo_utils as mu
     rng = np.random.RandomState(30)
     B, R, NC, S, K = 3, 147, 4, 224, 10
@@ -576,7 +577,7 @@ def test_detect_postprocess_matches_numpy_pipeline(C):
     for b in range(B):
         order = np.argsort(det[b, :, 4])[::-1][:K]
         order = [i for i in order if det[b, i, 4] >= thr]
-        keep = [order[j] for j in mu.NMB(det[b, order, :4], det[b, order, 4])] if order else []
+        keep = list(mu.NMB(det[b, order, :4], det[b, order, 5], np.asarray(order), (S, S, 3), nms_threshold=0.5)) if order else []
         n = int(cnt[b].item())
         assert idx[b, :n].cpu().tolist() == [int(k) for k in keep], (b, idx[b].cpu().tolist(), keep)
         assert (idx[b, n:] == -1).all()
@@ -716,3 +717,46 @@ def test_prep_weights_batch_equals_single_jobs(C):
     torch.cuda.synchronize()
     for o, r, sp in zip(outs, refs, specs):
         assert torch.equal(o, r), sp
+
+
+def test_detect_postprocess_nmb_matches_reference_golden(C):
+    """The device NMB against the outputs of the REFERENCE's own NMB (tests/golden/reference_utils_fixture.npz):
+    same-class candidates only, and a candidate that was dropped still suppresses later ones."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_utils_fixture.npz"))
+    S, K = 224, 10
+    for case in range(4):
+        bx, cls, ind = gold[f"nmb{case}_boxes"], gold[f"nmb{case}_class_ids"], gold[f"nmb{case}_indices"]
+        n = len(ind)
+        det = np.zeros((1, n, 6), np.float32)
+        det[0, :, :4] = bx
+        det[0, :, 4] = 1.0 - 0.05 * np.arange(n)            # candidate order = descending score
+        det[0, :, 5] = cls
+        dd = cuda(torch.tensor(det))
+        i32 = lambda *sh: torch.empty(sh, dtype=torch.int32, device="cuda")
+        idx, boxes, cl, cnt = i32(1, K), i32(1, K, 4), i32(1, K), i32(1)
+        score = torch.empty(1, K, device="cuda")
+        C.call("myolo_detect_postprocess", dd, None, 1, n, 4, S, 28, 28, K, 0.0, float(0.3 + 0.2 * case), idx, boxes, cl, score,
+               cnt, None, stream())
+        kept_pos = [list(ind).index(v) for v in gold[f"nmb{case}_kept"]]
+        assert idx[0, :int(cnt[0].item())].cpu().tolist() == kept_pos, case
+
+
+def test_target_encoding_on_device_matches_reference_golden(C):
+    """myolo_extract_bboxes / myolo_encode_yolo_targets against what the REFERENCE's BatchGenerator.__getitem__ and
+    extract_bboxes produced for the same ground truth (tests/golden/reference_utils_fixture.npz): bit-exact."""
+    import os
+    from myolo import myolo_utils as mu
+    from tests.test_reference_golden import _Cfg
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_utils_fixture.npz"))
+    cfg = _Cfg()
+    for b in range(int(gold["bg_n_batches"])):
+        ids, boxes, masks = gold[f"bg_batch{b}_gt_class_ids"], gold[f"bg_batch{b}_gt_boxes"], gold[f"bg_batch{b}_gt_masks"]
+        tb_d, yt_d, _ = mu.encode_targets_device(cfg, torch.tensor(ids).cuda(), torch.tensor(boxes).cuda())
+        assert np.array_equal(yt_d.cpu().numpy(), gold[f"bg_batch{b}_yolo_target"].astype(np.float32)), "yolo_target"
+        assert np.array_equal(tb_d.cpu().numpy(), gold[f"bg_batch{b}_true_boxes"].astype(np.float32)), "true_boxes"
+        gm = torch.tensor(masks).to(torch.uint8).cuda().contiguous()
+        B, S, M = gm.shape[0], gm.shape[1], gm.shape[3]
+        bx = torch.empty(B, M, 4, dtype=torch.int32, device="cuda")
+        C.call("myolo_extract_bboxes", gm, B, S, M, bx, stream())
+        assert np.array_equal(bx.cpu().numpy(), boxes[:, :M]), "extract_bboxes"

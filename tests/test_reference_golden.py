@@ -1,0 +1,107 @@
+"""Host-side functions of the package against golden vectors produced by the REFERENCE's own code
+(tests/golden/reference_utils_fixture.npz, written by tests/golden/make_reference_fixtures.py from
+/root/reference/myolo/myolo_utils.py with its third-party imports stubbed out).  These pin SURVEY 8a row a14 and the
+numpy side of 8f rows 1-2 to the reference itself; the device kernels for the same rows are compared with the same
+vectors in tests/test_kernels_gpu.py.  Integer / index / boolean outputs must be identical, float64 outputs equal to
+the last bit (same operations in the same order)."""
+import os
+
+import numpy as np
+import pytest
+
+from myolo import myolo_utils as mutils
+from myolo.shapes import ShapesConfig
+
+FIX = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_utils_fixture.npz")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(FIX)
+
+
+class _Cfg(ShapesConfig):
+    BATCH_SIZE = 4
+    IMAGE_SHAPE = [224, 224, 3]
+    GRID_H = GRID_W = 7
+    N_BOX = 3
+    NUM_CLASSES = 4
+    ANCHORS = [0.57273, 0.677385, 1.87446, 2.06253, 3.33843, 5.47434]
+    TRUE_BOX_BUFFER = 15
+    MAX_GT_INSTANCES = 10
+
+
+def test_extract_bboxes(gold):
+    got = mutils.extract_bboxes(gold["eb_mask"])
+    assert got.dtype == gold["eb_boxes"].dtype and np.array_equal(got, gold["eb_boxes"])
+
+
+def _all_info(gold):
+    n = int(gold["bg_n_images"])
+    return [[gold[f"bg_image_{i}"], gold[f"bg_ids_{i}"], gold[f"bg_boxes_{i}"], gold[f"bg_masks_{i}"]] for i in range(n)]
+
+
+def test_batch_generator_target_encoding(gold):
+    """BatchGenerator.__getitem__ (myolo_utils.py:727-860): images / true boxes / YOLO target / padded GT arrays"""
+    info = _all_info(gold)
+    for rec in info:      # the boxes the reference's extract_bboxes produced for these masks
+        assert np.array_equal(mutils.extract_bboxes(rec[3]), rec[2])
+    gen = mutils.BatchGenerator(info, _Cfg(), mode="training", shuffle=False, norm=True)
+    assert len(gen) == int(gold["bg_n_batches"])
+    for b in range(len(gen)):
+        (images, tb, yt, ids, boxes, masks), outputs = gen[b]
+        assert outputs == []
+        meta = gold[f"bg_batch{b}_images_meta"]
+        assert tuple(images.shape) == tuple(meta[:4]) and images.dtype.itemsize == meta[4]
+        assert np.array_equal(images.astype(np.float64).sum(axis=(1, 2, 3)), gold[f"bg_batch{b}_images_sum"])
+        assert np.array_equal(images[:, 17], gold[f"bg_batch{b}_images_row"])
+        for name, got in (("true_boxes", tb), ("yolo_target", yt), ("gt_class_ids", ids), ("gt_boxes", boxes), ("gt_masks", masks)):
+            ref = gold[f"bg_batch{b}_{name}"]
+            assert got.shape == ref.shape and got.dtype == ref.dtype, (name, got.dtype, ref.dtype)
+            assert np.array_equal(got, ref), (b, name)
+    # the fixture exercises the interesting branches
+    yt_all = np.concatenate([gold[f"bg_batch{b}_yolo_target"] for b in range(len(gen))])
+    assert yt_all[..., 4].sum() >= 8
+
+
+def test_iou_helpers(gold):
+    boxes = gold["iou_boxes"]
+    for (i, j), v, v2 in zip(gold["iou_pairs"], gold["iou_values"], gold["iou2_values"]):
+        assert mutils.bbox_iou(mutils.BoundBox(*boxes[i]), mutils.BoundBox(*boxes[j])) == v
+        assert mutils.bbox_iou_2(boxes[i], boxes[j], [224, 224, 3]) == v2
+
+
+def test_nmb(gold):
+    """NMB (myolo_utils.py:88-113): a candidate is dropped when ANY earlier candidate of the same class overlaps it by
+    at least the threshold -- also an earlier candidate that was dropped itself (this is not greedy NMS)."""
+    differs_from_greedy = False
+    for case in range(4):
+        bx, cls, idx = gold[f"nmb{case}_boxes"], gold[f"nmb{case}_class_ids"], gold[f"nmb{case}_indices"]
+        thr = 0.3 + 0.2 * case
+        kept = mutils.NMB(bx, cls, idx.copy(), [224, 224, 3], nms_threshold=thr)
+        assert np.array_equal(np.asarray(kept), gold[f"nmb{case}_kept"]), case
+        greedy = []
+        for a in range(len(idx)):
+            if all(not (cls[a] == cls[k] and mutils.bbox_iou_2(bx[k], bx[a], [224, 224, 3]) >= thr) for k in greedy):
+                greedy.append(a)
+        differs_from_greedy |= list(idx[greedy]) != list(gold[f"nmb{case}_kept"])
+    assert differs_from_greedy, "the fixture must contain a chain A>B>C that separates the reference rule from greedy NMS"
+
+
+def test_decode_one_yolo_output(gold):
+    anchors = _Cfg.ANCHORS
+    for case in range(3):
+        got = mutils.decode_one_yolo_output(gold[f"dec{case}_netout"].copy(), anchors, 4, obj_threshold=0.3, nms_threshold=0.3)
+        ref = gold[f"dec{case}_boxes"]
+        assert len(got) == len(ref) and len(ref) > 0
+        arr = np.array([[b.xmin, b.ymin, b.xmax, b.ymax, b.c] for b in got])
+        assert np.array_equal(arr, ref)
+        assert np.array_equal(np.array([b.classes for b in got]), gold[f"dec{case}_classes"])
+        assert np.array_equal(np.array([[b.get_label(), b.get_score()] for b in got]), gold[f"dec{case}_label_score"])
+
+
+def test_sigmoid_softmax(gold):
+    x = gold["sm_x"]
+    assert np.array_equal(mutils._sigmoid(x), gold["sm_sigmoid"])
+    assert np.array_equal(mutils._softmax(x.copy()), gold["sm_softmax"])
+    assert np.array_equal(mutils._softmax(x.copy() / 30.0), gold["sm_softmax_small"])
