@@ -1,6 +1,8 @@
 """Synthetic Shapes data (squares, circles, triangles on a random background), the workload of
-example/shapes/dataset_shapes.py:53-204 restated with numpy rasterisation so that the benchmark
-and the tests can generate it anywhere (no cv2 / mrcnn dependency, seeded `random.Random`).
+example/shapes/dataset_shapes.py:53-204 with a seeded `random.Random` instead of the global generator.
+Shapes are rasterised with the same cv2 calls as the reference (120-135) -- specs, images and masks are then
+identical to the reference's for the same seed (tests/test_reference_golden.py, golden vectors from the real file) --
+and with a close numpy restatement when cv2 is not installed.
 
 ShapesConfig mirrors dataset_shapes.py:14-50.  ShapesDataset follows the mrcnn Dataset protocol
 (load_image / load_mask / image_ids), so load_image_gt and BatchGenerator consume it unchanged."""
@@ -11,6 +13,11 @@ import numpy as np
 
 from mrcnn import utils
 from .config import Config
+
+try:
+    import cv2
+except Exception:       # pragma: no cover - the numpy restatement below takes over
+    cv2 = None
 
 
 class ShapesConfig(Config):
@@ -61,11 +68,29 @@ class ShapesDataset(utils.Dataset):
         t = (yy - (y - s)) / (2.0 * s)
         return (t >= 0) & (t <= 1) & (np.abs(xx - x) <= half * t)
 
+    @classmethod
+    def draw_shape(cls, image, shape, dims, color):
+        """dataset_shapes.py:120-135 (cv2.rectangle / circle / fillPoly, filled); `image` is [h, w, c] uint8."""
+        x, y, s = dims
+        if cv2 is None:
+            image[cls._raster(shape, dims, image.shape[0], image.shape[1])] = color
+            return image
+        image = np.ascontiguousarray(image)
+        if shape == "square":
+            cv2.rectangle(image, (x - s, y - s), (x + s, y + s), color, -1)
+        elif shape == "circle":
+            cv2.circle(image, (x, y), s, color, -1)
+        elif shape == "triangle":
+            points = np.array([[(x, y - s), (x - s / math.sin(math.radians(60)), y + s),
+                                (x + s / math.sin(math.radians(60)), y + s)]], dtype=np.int32)
+            cv2.fillPoly(image, points, color)
+        return image
+
     def load_image(self, image_id):
         info = self.image_info[image_id]
         img = np.ones([info["height"], info["width"], 3], dtype=np.uint8) * np.array(info["bg_color"], dtype=np.uint8).reshape(1, 1, 3)
         for shape, color, dims in info["shapes"]:
-            img[self._raster(shape, dims, info["height"], info["width"])] = color
+            img = self.draw_shape(img, shape, dims, color)
         return img
 
     def load_mask(self, image_id):
@@ -74,7 +99,7 @@ class ShapesDataset(utils.Dataset):
         h, w = info["height"], info["width"]
         mask = np.zeros([h, w, len(shapes)], dtype=np.uint8)
         for i, (shape, _, dims) in enumerate(shapes):
-            mask[:, :, i] = self._raster(shape, dims, h, w)
+            mask[:, :, i:i + 1] = self.draw_shape(mask[:, :, i:i + 1].copy(), shape, dims, 1)
         occlusion = np.logical_not(mask[:, :, -1]).astype(np.uint8) if shapes else None
         for i in range(len(shapes) - 2, -1, -1):      # later shapes occlude earlier ones
             mask[:, :, i] = mask[:, :, i] * occlusion

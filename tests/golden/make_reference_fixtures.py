@@ -52,6 +52,32 @@ def load_reference_utils():
     return mod
 
 
+def load_reference_shapes():
+    """The REAL example/shapes/dataset_shapes.py (random specs 137-180, cv2 rasterisation 120-135, occlusion handling
+    98-118).  Its `mrcnn` base class comes from this repository's shim (bookkeeping + matterport's greedy NMS restated);
+    `myolo.model` (TensorFlow) is stubbed, `myolo.config` and `myolo.myolo_utils` are the reference's own files."""
+    repo = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    spec = importlib.util.spec_from_file_location("mrcnn.utils", os.path.join(repo, "mask-yolo_b200", "mrcnn", "utils.py"))
+    shim = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(shim)
+    _stub("mrcnn", utils=shim, visualize=_stub("mrcnn.visualize"))
+    sys.modules["mrcnn.utils"] = shim
+    for k in [k for k in sys.modules if k == "myolo" or k.startswith("myolo.")]:
+        del sys.modules[k]
+    sys.path.insert(0, "/root/reference")
+    try:
+        import myolo                                             # the reference's package
+        assert all(p.startswith("/root/reference") for p in myolo.__path__), list(myolo.__path__)   # a namespace package
+        sys.modules["myolo.model"] = types.ModuleType("myolo.model")
+        myolo.model = sys.modules["myolo.model"]
+        spec = importlib.util.spec_from_file_location("ref_dataset_shapes", "/root/reference/example/shapes/dataset_shapes.py")
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        sys.path.remove("/root/reference")
+    return mod
+
+
 class RefConfig(object):
     """The attributes BatchGenerator reads, with the Shapes values of example/shapes (3 anchors as in the shipped
     graph, 4 classes incl. background)."""
@@ -174,6 +200,29 @@ def main():
     out["sm_sigmoid"] = ref._sigmoid(x)
     out["sm_softmax"] = ref._softmax(x.copy())
     out["sm_softmax_small"] = ref._softmax(x.copy() / 30.0)
+
+    # ---- ShapesDataset (example/shapes/dataset_shapes.py:53-180): specs, images, masks for seeded `random`
+    import random
+    shp = load_reference_shapes()
+    for tag, seed, count, size in (("a", 1234, 10, 224), ("b", 7, 4, 128)):
+        random.seed(seed)
+        ds = shp.ShapesDataset()
+        ds.load_shapes(count, size, size)
+        ds.prepare()
+        out[f"shp{tag}_meta"] = np.array([seed, count, size], dtype=np.int64)
+        for i in ds.image_ids:
+            info = ds.image_info[i]
+            img = ds.load_image(i)
+            mask, ids = ds.load_mask(i)
+            out[f"shp{tag}_{i}_bg"] = np.asarray(info["bg_color"], dtype=np.int64)
+            out[f"shp{tag}_{i}_specs"] = np.array([[["square", "circle", "triangle"].index(s[0])] + list(s[1]) + list(s[2])
+                                                    for s in info["shapes"]], dtype=np.int64)
+            out[f"shp{tag}_{i}_ids"] = ids
+            out[f"shp{tag}_{i}_mask_bits"] = np.packbits(mask.astype(np.uint8))
+            out[f"shp{tag}_{i}_mask_shape"] = np.array(mask.shape, dtype=np.int64)
+            out[f"shp{tag}_{i}_image_rowsum"] = img.astype(np.int64).sum(axis=(1, 2))
+            out[f"shp{tag}_{i}_image_colsum"] = img.astype(np.int64).sum(axis=(0, 2))
+            out[f"shp{tag}_{i}_boxes"] = ref.extract_bboxes(mask)
 
     np.savez_compressed(OUT, **out)
     print(f"wrote {OUT}: {len(out)} arrays, {os.path.getsize(OUT) / 1024:.0f} KB")

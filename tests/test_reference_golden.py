@@ -105,3 +105,30 @@ def test_sigmoid_softmax(gold):
     assert np.array_equal(mutils._sigmoid(x), gold["sm_sigmoid"])
     assert np.array_equal(mutils._softmax(x.copy()), gold["sm_softmax"])
     assert np.array_equal(mutils._softmax(x.copy() / 30.0), gold["sm_softmax_small"])
+
+
+def test_shapes_dataset_matches_reference(gold):
+    """ShapesDataset (example/shapes/dataset_shapes.py:53-180): for the same seed the random specs, the rasterised
+    images and the occlusion-resolved masks are those of the reference's own file (cv2 rasterisation)."""
+    pytest.importorskip("cv2")
+    from myolo.shapes import ShapesDataset
+    for tag in ("a", "b"):
+        seed, count, size = (int(v) for v in gold[f"shp{tag}_meta"])
+        ds = ShapesDataset(seed=seed)
+        ds.load_shapes(count, size, size)
+        ds.prepare()
+        assert len(ds.image_ids) == count
+        for i in ds.image_ids:
+            info = ds.image_info[i]
+            assert list(info["bg_color"]) == gold[f"shp{tag}_{i}_bg"].tolist()
+            specs = [[["square", "circle", "triangle"].index(s[0])] + list(s[1]) + list(s[2]) for s in info["shapes"]]
+            assert specs == gold[f"shp{tag}_{i}_specs"].tolist(), (tag, i)
+            mask, ids = ds.load_mask(i)
+            assert np.array_equal(ids, gold[f"shp{tag}_{i}_ids"]) and ids.dtype == gold[f"shp{tag}_{i}_ids"].dtype
+            assert list(mask.shape) == gold[f"shp{tag}_{i}_mask_shape"].tolist() and mask.dtype == bool
+            assert np.array_equal(np.packbits(mask.astype(np.uint8)), gold[f"shp{tag}_{i}_mask_bits"]), (tag, i)
+            img = ds.load_image(i)
+            assert img.dtype == np.uint8
+            assert np.array_equal(img.astype(np.int64).sum(axis=(1, 2)), gold[f"shp{tag}_{i}_image_rowsum"])
+            assert np.array_equal(img.astype(np.int64).sum(axis=(0, 2)), gold[f"shp{tag}_{i}_image_colsum"])
+            assert np.array_equal(mutils.extract_bboxes(mask), gold[f"shp{tag}_{i}_boxes"])
