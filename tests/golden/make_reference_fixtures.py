@@ -224,6 +224,22 @@ def main():
             out[f"shp{tag}_{i}_image_colsum"] = img.astype(np.int64).sum(axis=(0, 2))
             out[f"shp{tag}_{i}_boxes"] = ref.extract_bboxes(mask)
 
+    # ---- Config (myolo/config.py) and ShapesConfig (dataset_shapes.py:14-50): every public class attribute and the
+    # attributes __init__ derives
+    import json
+
+    def dump(cls):
+        def norm(v):
+            return v.tolist() if isinstance(v, np.ndarray) else (list(v) if isinstance(v, tuple) else v)
+        d = {k: norm(getattr(cls, k)) for k in dir(cls) if not k.startswith("_") and not callable(getattr(cls, k))}
+        d["__instance__"] = {k: norm(v) for k, v in vars(cls()).items()}
+        return json.dumps(d, sort_keys=True)
+
+    import myolo.config as refcfg                # still the reference's module (loaded by load_reference_shapes)
+    assert refcfg.__file__.startswith("/root/reference")
+    out["config_json"] = np.array(dump(refcfg.Config))
+    out["shapes_config_json"] = np.array(dump(shp.ShapesConfig))
+
     np.savez_compressed(OUT, **out)
     print(f"wrote {OUT}: {len(out)} arrays, {os.path.getsize(OUT) / 1024:.0f} KB")
 
