@@ -135,7 +135,7 @@ def test_shapes_dataset_matches_reference(gold):
 
 
 def test_config_attributes_match_reference(gold):
-    """Config (myolo/config.py) attribute for attribute; ShapesConfig (dataset_shapes.py:14-50) except the three fields
+    """Config (myolo/config.py) attribute for attribute; ShapesConfig (dataset_shapes.py:14-50) except the fields
     the reference leaves inconsistent with its own shipped graph (N_BOX inherited as 5 with 3 anchors)."""
     import json
     from myolo.config import Config
@@ -151,13 +151,15 @@ def test_config_attributes_match_reference(gold):
     assert dump(Config) == ref
     ref_s, mine_s = json.loads(str(gold["shapes_config_json"])), dump(ShapesConfig)
     # inherited from the base class although ShapesConfig changes what they depend on: N_BOX 5 with 3 anchors,
-    # CLASS_WEIGHTS of length 2 with 4 classes (tf.gather out of range), MAX_GT_INSTANCES 10 vs a 15-wide box buffer
-    repaired = {"N_BOX", "MAX_GT_INSTANCES", "TRAIN_ROIS_PER_IMAGE", "CLASS_WEIGHTS"}
+    # CLASS_WEIGHTS of length 2 with 4 classes (tf.gather out of range); TRUE_BOX_BUFFER / MAX_GT_INSTANCES are 10 at
+    # HEAD but the graph the reference ships was built 15 wide (graph_fixture.json: input_true_boxes [-1,1,1,1,15,4])
+    repaired = {"N_BOX", "TRUE_BOX_BUFFER", "MAX_GT_INSTANCES", "TRAIN_ROIS_PER_IMAGE", "CLASS_WEIGHTS"}
     for k in set(ref_s) | set(mine_s):
         if k in repaired or k == "__instance__":
             continue
         assert mine_s.get(k) == ref_s.get(k), k
     assert ref_s["N_BOX"] == 5 and len(ref_s["ANCHORS"]) == 6 and mine_s["N_BOX"] == 3
+    assert ref_s["TRUE_BOX_BUFFER"] == 10 and mine_s["TRUE_BOX_BUFFER"] == mine_s["MAX_GT_INSTANCES"] == 15
     assert len(ref_s["CLASS_WEIGHTS"]) == 2 and ref_s["NUM_CLASSES"] == 4 and len(mine_s["CLASS_WEIGHTS"]) == 4
     for k in set(ref_s["__instance__"]) | set(mine_s["__instance__"]):
         if k not in repaired:
