@@ -339,6 +339,21 @@ int myolo_extract_bboxes(const unsigned char* gt_masks, int B, int S, int M, int
 int myolo_encode_yolo_targets(const int* gt_class_ids, const int* gt_boxes, int B, int M, int S, int G, int NB, int NC,
                               int TB, const float* anchors, float* yolo_target, float* true_boxes, myolo_stream stream);
 
+/* ---- the Shapes workload on the device: example/shapes/dataset_shapes.py:80-135 (load_image, load_mask,
+ * draw_shape = cv2.rectangle / cv2.circle / cv2.fillPoly, later shapes occlude earlier ones) + myolo_utils.py:274-366
+ * load_image_gt (instances with an empty visible mask are dropped, order kept) + 247-271 extract_bboxes + the padding and
+ * `image / 255.` of BatchGenerator.__getitem__ (821-851), for a whole batch.
+ * specs [B, 4 + 8*MS] int32 as the host generator draws them: bg r, g, b, n_shapes, then per shape
+ *   type (1 square, 2 circle, 3 triangle = class id), r, g, b, x, y, s, 0.
+ * ws: B*MS*(2*S+1) ints (row extents per shape + compaction slots), 8-byte aligned.
+ * Outputs: image_f32 [B,S,S,3] = float32(uint8 / 255.) (nullable), image_u8 [B,S,S,3] (nullable), gt_masks [B,S,S,M] bytes,
+ * gt_class_ids [B,TB], gt_boxes [B,TB,4] int32 (x1,y1,x2,y2; x2/y2 exclusive), gt_boxes_f the same as float (nullable);
+ * all zero padded.  S % 16 == 0, MS <= 8, MS <= M <= 128, MS <= TB.  Pixel-exact with OpenCV 4.13 for the generator's
+ * domain (centres inside [20, S-21], s in [20, S/4]; tests/test_shapes_raster.py). */
+int myolo_shapes_raster(const int* specs, int B, int S, int MS, int M, int TB, int* ws, float* image_f32,
+                        unsigned char* image_u8, unsigned char* gt_masks, int* gt_class_ids, int* gt_boxes,
+                        float* gt_boxes_f, myolo_stream stream);
+
 /* ---- K17: Keras Adam, myolo/model.py:1071-1075 ----  lr_t = lr*sqrt(1-b2^t)/(1-b1^t) computed by caller */
 int myolo_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr_t,
                     float b1, float b2, float eps, float grad_scale, myolo_stream stream);

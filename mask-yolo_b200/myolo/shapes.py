@@ -143,3 +143,69 @@ def make_batches(config, n_batches, seed=1234, mode="training"):
     out = [gen[i][0] for i in range(len(gen))]
     np.random.set_state(state)
     return out
+
+
+# --------------------------------------------------------------------------- device-side generation
+_TYPE_ID = {"square": 1, "circle": 2, "triangle": 3}          # = class ids (load_shapes above)
+
+
+def spec_table(dataset, image_ids=None, max_shapes=4):
+    """The integers the device rasteriser needs, one row per image: [bg r, g, b, n] + max_shapes x
+    [type, r, g, b, x, y, s, 0] (int32).  This is all that crosses the host -> device link per image."""
+    ids = dataset.image_ids if image_ids is None else image_ids
+    tab = np.zeros((len(ids), 4 + 8 * max_shapes), dtype=np.int32)
+    for row, i in zip(tab, ids):
+        info = dataset.image_info[i]
+        shapes = info["shapes"]
+        if len(shapes) > max_shapes:
+            raise ValueError("image %d has %d shapes, max_shapes is %d" % (i, len(shapes), max_shapes))
+        row[0:3] = info["bg_color"]
+        row[3] = len(shapes)
+        for k, (shape, color, (x, y, s)) in enumerate(shapes):
+            row[4 + 8 * k: 4 + 8 * k + 7] = (_TYPE_ID[shape],) + tuple(color) + (x, y, s)
+    return tab
+
+
+class DeviceShapes(object):
+    """Builds a training batch of the Shapes workload ON the GPU from its spec table: images, instance masks with
+    occlusion, class ids, boxes (myolo_shapes_raster) and the YOLO target / true-box tensors (myolo_encode_yolo_targets) --
+    the six inputs BatchGenerator(mode='training', norm=True) yields, bit for bit (tests/test_shapes_raster.py), without the
+    host rasterisation and the 43 MB per-step upload.  Buffers are allocated once; batch() overwrites them, so the returned
+    tensors are valid until the next call (the engine's recorded step keeps reading the same addresses)."""
+
+    def __init__(self, config, device=0, max_shapes=4):
+        import torch
+        from .config import resolve
+        self.torch = torch
+        self.c = c = resolve(config)
+        self.B, self.MS = int(config.BATCH_SIZE), int(max_shapes)
+        self.M = int(config.MAX_GT_INSTANCES)
+        B, S, G, TB = self.B, c["S"], c["G"], c["TB"]
+        dev = self.dev = torch.device("cuda", device)
+        self.spec_host = torch.empty(B, 4 + 8 * self.MS, dtype=torch.int32).pin_memory()
+        self.spec_dev = torch.empty_like(self.spec_host, device=dev)
+        self.ws = torch.empty(B * self.MS * (2 * S + 1), dtype=torch.int32, device=dev)
+        self.images = torch.empty(B, S, S, 3, dtype=torch.float32, device=dev)
+        self.masks = torch.empty(B, S, S, self.M, dtype=torch.uint8, device=dev)
+        self.ids = torch.empty(B, TB, dtype=torch.int32, device=dev)
+        self.boxes = torch.empty(B, TB, 4, dtype=torch.int32, device=dev)
+        self.boxes_f = torch.empty(B, TB, 4, dtype=torch.float32, device=dev)
+        self.yolo_target = torch.empty(B, G, G, c["NB"], 5 + c["NC"], dtype=torch.float32, device=dev)
+        self.true_boxes = torch.empty(B, 1, 1, 1, TB, 4, dtype=torch.float32, device=dev)
+        self.anchors = torch.tensor(c["ANCHORS"], dtype=torch.float32, device=dev)
+
+    def batch(self, specs, image_u8=None):
+        """specs: int32 [B, 4+8*max_shapes] (spec_table).  Returns [images, true_boxes, yolo_target, gt_class_ids,
+        gt_boxes (float), gt_masks (bytes)] as device tensors; `image_u8` (optional [B,S,S,3] byte tensor) also receives
+        the un-normalised image."""
+        from . import _cabi as C
+        torch, c = self.torch, self.c
+        assert tuple(specs.shape) == tuple(self.spec_host.shape), (specs.shape, self.spec_host.shape)
+        self.spec_host.copy_(torch.from_numpy(np.ascontiguousarray(specs, dtype=np.int32)))
+        self.spec_dev.copy_(self.spec_host, non_blocking=True)
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        C.call("myolo_shapes_raster", self.spec_dev, self.B, c["S"], self.MS, self.M, c["TB"], self.ws, self.images,
+               image_u8, self.masks, self.ids, self.boxes, self.boxes_f, st)
+        C.call("myolo_encode_yolo_targets", self.ids, self.boxes, self.B, c["TB"], c["S"], c["G"], c["NB"], c["NC"],
+               c["TB"], self.anchors, self.yolo_target, self.true_boxes, st)
+        return [self.images, self.true_boxes, self.yolo_target, self.ids, self.boxes_f, self.masks]
