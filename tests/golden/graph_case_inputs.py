@@ -1,0 +1,64 @@
+"""Seeded inputs of the reference-graph golden cases, shared by the generator (make_reference_graph_fixtures.py, runs
+where /root/reference exists) and the tests (which regenerate the same inputs instead of storing them).  Only
+np.random.RandomState is used: its streams are frozen across numpy versions."""
+import numpy as np
+
+CASES = {
+    # the Shapes configuration of the shipped graph: 3 anchors, 4 classes, 15-wide box buffer
+    "shapes": dict(B=2, G=7, NB=3, NC=4, TB=15, M=15, S=96, C=4, seed=101,
+                   ANCHORS=[1.27273, 1.277385, 2.47446, 2.56253, 4.03843, 4.07434], CLASS_WEIGHTS=[1.0, 1.0, 1.0, 1.0]),
+    # base Config values at HEAD: 5 anchors, 2 classes, 10-wide buffer; non-trivial class weights and scales
+    "base": dict(B=1, G=4, NB=5, NC=2, TB=10, M=10, S=64, C=8, seed=202,
+                 ANCHORS=[1.27, 1.31, 1.95, 1.85, 2.40, 2.72, 3.20, 3.32, 5.06, 5.05], CLASS_WEIGHTS=[0.5, 2.0],
+                 OBJECT_SCALE=5.0, NO_OBJECT_SCALE=0.7, COORD_SCALE=1.5, CLASS_SCALE=1.2),
+}
+
+
+def build(name):
+    """-> dict of numpy inputs for one case.  Ground truth: `n` axis-aligned ellipses per image; y_pred: N(0,1) logits,
+    except that the predictor responsible for each instance decodes to (roughly) the instance's box, so that positive
+    ROIs, class assignments and mask targets are exercised."""
+    c = dict(CASES[name])
+    rng = np.random.RandomState(c["seed"])
+    B, G, NB, NC, TB, M, S = c["B"], c["G"], c["NB"], c["NC"], c["TB"], c["M"], c["S"]
+    anchors = np.asarray(c["ANCHORS"], np.float64).reshape(NB, 2)
+    y_pred = rng.standard_normal((B, G, G, NB, 5 + NC)).astype(np.float32)
+    y_true = np.zeros((B, G, G, NB, 5 + NC), np.float32)
+    true_boxes = np.zeros((B, 1, 1, 1, TB, 4), np.float32)
+    ids = np.zeros((B, TB), np.int32)
+    boxes_px = np.zeros((B, TB, 4), np.float32)
+    masks = np.zeros((B, S, S, M), bool)
+    yy, xx = np.mgrid[0:S, 0:S]
+    for b in range(B):
+        n = int(rng.randint(2, 5))
+        for k in range(n):
+            w, h = rng.uniform(0.18, 0.45, size=2) * S
+            cx, cy = rng.uniform(0.25, 0.75, size=2) * S
+            x1, y1, x2, y2 = int(cx - w / 2), int(cy - h / 2), int(cx + w / 2), int(cy + h / 2)
+            masks[b, :, :, k] = ((xx - (x1 + x2 - 1) / 2.0) / ((x2 - x1) / 2.0)) ** 2 + \
+                                ((yy - (y1 + y2 - 1) / 2.0) / ((y2 - y1) / 2.0)) ** 2 <= 1.0
+            ids[b, k] = int(rng.randint(1, NC))
+            boxes_px[b, k] = (x1, y1, x2, y2)
+            # BatchGenerator-style encoding in grid units
+            gcx, gcy = 0.5 * (x1 + x2) / (S / G), 0.5 * (y1 + y2) / (S / G)
+            gw, gh = (x2 - x1) / (S / G), (y2 - y1) / (S / G)
+            gx, gy = int(gcx), int(gcy)
+            a = int(np.argmin(np.abs(anchors[:, 0] - gw) + np.abs(anchors[:, 1] - gh)))
+            y_true[b, gy, gx, a, 0:4] = (gcx, gcy, gw, gh)
+            y_true[b, gy, gx, a, 4] = 1.0
+            y_true[b, gy, gx, a, 5:] = 0.0
+            y_true[b, gy, gx, a, 5 + ids[b, k]] = 1.0
+            true_boxes[b, 0, 0, 0, k] = (gcx, gcy, gw, gh)
+            # responsible predictor decodes close to the instance (with a little noise)
+            fx, fy = np.clip(gcx - gx, 0.05, 0.95), np.clip(gcy - gy, 0.05, 0.95)
+            y_pred[b, gy, gx, a, 0] = np.log(fx / (1 - fx)) + 0.1 * rng.standard_normal()
+            y_pred[b, gy, gx, a, 1] = np.log(fy / (1 - fy)) + 0.1 * rng.standard_normal()
+            y_pred[b, gy, gx, a, 2] = np.log(gw / anchors[a, 0]) + 0.05 * rng.standard_normal()
+            y_pred[b, gy, gx, a, 3] = np.log(gh / anchors[a, 1]) + 0.05 * rng.standard_normal()
+    feat = rng.standard_normal((B, S // 8, S // 8, c["C"])).astype(np.float32)
+    R = G * G * NB
+    pred_masks = rng.uniform(0.0, 1.0, size=(B, R, 28, 28, NC)).astype(np.float32)
+    pred_masks[0, 0, 0, :4, :] = (0.0, 1.0, 1e-9, 1.0 - 1e-9)[:NC] if NC <= 4 else 0.5   # exercise the 1e-7 clip
+    c.update(y_pred=y_pred, y_true=y_true, true_boxes=true_boxes, gt_class_ids=ids, gt_boxes_px=boxes_px, gt_masks=masks,
+             feat=feat, pred_masks=pred_masks, R=R)
+    return c

@@ -1,0 +1,149 @@
+"""Golden vectors from the reference's OWN graph-building source (myolo/model.py), executed eagerly.
+
+Run HERE (the container that has /root/reference); the .npz it writes is committed, tests never read /root/reference:
+
+    python tests/golden/make_reference_graph_fixtures.py
+
+TensorFlow 1.x / Keras 2.x are not installable, so `tensorflow`, `keras.backend` and the other third-party imports of
+myolo/model.py are replaced by tests/golden/tf1_numpy_shim.py (primitive ops over numpy float32, restated from their
+documented behaviour) and empty stubs.  The functions below then run UNMODIFIED from /root/reference/myolo/model.py:
+
+    yolo_custom_loss 86-242 (both the normal and the warm-up branch)      DecodeYOLOLayer.call 1442-1473
+    DetectionsLayer.call 1493-1538        norm_boxes_graph 1394-1408      trim_zeros_graph 1411-1420
+    overlaps_graph 420-454                detect_mask_target_graph 457-602 through DetectMaskTargetLayer.call 635-649
+    PyramidROIAlign.call 327-410          myolo_mask_loss_graph 718-754
+
+Two things are patched, both documented reference defects: (1) model.py reads its configuration from the module
+global `config` = the base Config CLASS (model.py:25), so the case's values are set as class attributes; (2)
+DetectMaskTargetLayer.call uses the undefined name `utils` (644) -- it is bound to the reference's own
+myolo.myolo_utils, where batch_slice (929-963) lives."""
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import graph_case_inputs as GI          # noqa: E402
+import tf1_numpy_shim as tfs            # noqa: E402
+
+OUT = os.path.join(HERE, "reference_graph_fixture.npz")
+
+
+def _stub(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+class _LooseVersion(object):
+    def __init__(self, s):
+        self.v = tuple(int(p) for p in str(s).split(".")[:3] if p.isdigit())
+
+    def __ge__(self, o):
+        return self.v >= o.v
+
+
+class _Layer(object):
+    def __init__(self, **kwargs):
+        self.name = kwargs.get("name")
+
+
+class _Any(object):
+    def __init__(self, *a, **k):
+        pass
+
+
+def load_reference_model():
+    sys.modules["tensorflow"] = tfs
+    kb = _stub("keras.backend", reshape=tfs.k_reshape, switch=tfs.k_switch, mean=tfs.k_mean,
+               binary_crossentropy=tfs.k_binary_crossentropy)
+    _stub("keras", __version__="2.2.4", backend=kb, engine=_stub("keras.engine", Layer=_Layer),
+          layers=_stub("keras.layers"), models=_stub("keras.models"), utils=_stub("keras.utils", Sequence=object))
+    _stub("keras_applications", get_keras_submodule=lambda name: None,
+          mobilenet=_stub("keras_applications.mobilenet", _depthwise_conv_block=None),
+          mobilenet_v2=_stub("keras_applications.mobilenet_v2", MobileNetV2=None))
+    _stub("pytz", timezone=lambda name: None)
+    _stub("distutils", version=_stub("distutils.version", LooseVersion=_LooseVersion))
+    _stub("matplotlib", pyplot=_stub("matplotlib.pyplot"), patches=_stub("matplotlib.patches", Rectangle=_Any))
+    _stub("mrcnn", utils=_stub("mrcnn.utils", Dataset=_Any))
+    sk = _stub("skimage", __version__="0.0")
+    for sub in ("color", "io", "transform"):
+        setattr(sk, sub, _stub("skimage." + sub))
+    _stub("imgaug", augmenters=_stub("imgaug.augmenters"))
+    if not hasattr(np, "bool"):
+        np.bool = bool
+    for k in [k for k in sys.modules if k == "myolo" or k.startswith("myolo.")]:
+        del sys.modules[k]
+    sys.path.insert(0, "/root/reference")
+    try:
+        import myolo                                              # the reference's (namespace) package
+        assert all(p.startswith("/root/reference") for p in myolo.__path__), list(myolo.__path__)
+        sys.modules["myolo.visualize"] = types.ModuleType("myolo.visualize")    # matplotlib / IPython plotting only
+        myolo.visualize = sys.modules["myolo.visualize"]
+        import myolo.model as ref_model
+        import myolo.myolo_utils as ref_utils
+    finally:
+        sys.path.remove("/root/reference")
+    assert ref_model.__file__.startswith("/root/reference/")
+    ref_model.utils = ref_utils                                   # model.py:644 uses the undefined name `utils`
+    return ref_model
+
+
+def set_config(ref_model, c, warmup=0):
+    cfg = ref_model.config                                        # the Config CLASS (model.py:25)
+    cfg.BATCH_SIZE, cfg.GRID_H, cfg.GRID_W, cfg.N_BOX = c["B"], c["G"], c["G"], c["NB"]
+    cfg.NUM_CLASSES, cfg.ANCHORS, cfg.TRUE_BOX_BUFFER = c["NC"], list(c["ANCHORS"]), c["TB"]
+    cfg.CLASS_WEIGHTS = np.asarray(c["CLASS_WEIGHTS"], dtype="float32")
+    for k, d in (("OBJECT_SCALE", 5.0), ("NO_OBJECT_SCALE", 1.0), ("COORD_SCALE", 1.0), ("CLASS_SCALE", 1.0)):
+        setattr(cfg, k, c.get(k, d))
+    cfg.WARM_UP_BATCHES = warmup
+    cfg.TRAIN_ROIS_PER_IMAGE = c["R"]
+    cfg.MASK_SHAPE, cfg.USE_MINI_MASK, cfg.MAX_GT_INSTANCES = [28, 28], False, c["M"]
+    return cfg()
+
+
+def main():
+    M = load_reference_model()
+    T = tfs.T
+    out = {}
+    for name in GI.CASES:
+        c = GI.build(name)
+        cfg = set_config(M, c)
+        y_pred, y_true, tb = T(c["y_pred"]), T(c["y_true"]), T(c["true_boxes"])
+        out[name + "/yolo_loss"] = M.yolo_custom_loss(y_true, y_pred, tb).a
+        set_config(M, c, warmup=3)                                # seen = 1 after assign_add < 3: warm-up branch (196-207)
+        out[name + "/yolo_loss_warmup"] = M.yolo_custom_loss(y_true, y_pred, tb).a
+        cfg = set_config(M, c)
+        props = M.DecodeYOLOLayer(config=cfg).call([y_pred])
+        out[name + "/proposals"] = props.a
+        out[name + "/detections"] = M.DetectionsLayer(config=cfg).call([y_pred]).a
+        S = c["S"]
+        gt_norm = M.norm_boxes_graph(T(c["gt_boxes_px"]), T(np.asarray([S, S], np.int32)))
+        out[name + "/gt_boxes_norm"] = gt_norm.a
+        trimmed, nz = M.trim_zeros_graph(gt_norm[0])
+        out[name + "/trim_nonzero_0"] = nz.a
+        out[name + "/overlaps_0"] = M.overlaps_graph(props[0], trimmed).a
+        rois, tids, _, tmasks = M.DetectMaskTargetLayer(cfg).call([props, T(c["gt_class_ids"]), gt_norm, T(c["gt_masks"])])
+        out[name + "/rois"] = rois.a
+        out[name + "/target_class_ids"] = tids.a
+        assert set(np.unique(tmasks.a)) <= {0.0, 1.0}
+        out[name + "/target_masks_bits"] = np.packbits(tmasks.a.astype(np.uint8))
+        out[name + "/target_masks_shape"] = np.asarray(tmasks.a.shape)
+        assert (tids.a > 0).sum() >= 2, "case has too few positive ROIs to be useful"
+        pooled = M.PyramidROIAlign([14, 14]).call([rois, T(c["feat"])])
+        assert pooled.a.shape == (c["B"], c["R"], 14, 14, c["C"])
+        out[name + "/pooled_every5"] = pooled.a[:, ::5]
+        out[name + "/mask_loss"] = M.myolo_mask_loss_graph(tmasks, tids, T(c["pred_masks"])).a
+        out[name + "/mask_loss_no_positives"] = M.myolo_mask_loss_graph(tmasks, T(np.zeros_like(tids.a)), T(c["pred_masks"])).a
+        print(name, "yolo_loss", out[name + "/yolo_loss"], "warm-up", out[name + "/yolo_loss_warmup"], "positives",
+              (tids.a > 0).sum(1), "mask_loss", out[name + "/mask_loss"])
+    np.savez_compressed(OUT, **out)
+    print("wrote", OUT, os.path.getsize(OUT), "bytes,", len(out), "arrays")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,152 @@
+"""The oracle (and, on the GPU, the device kernels) against golden vectors produced by the REFERENCE's own
+myolo/model.py source, executed eagerly over a numpy stand-in for its TensorFlow/Keras primitives
+(tests/golden/make_reference_graph_fixtures.py + tf1_numpy_shim.py; the vectors are committed, inputs are regenerated
+from seeds by tests/golden/graph_case_inputs.py).  This pins the reference's formulas -- YOLO loss incl. the warm-up
+branch, box decoding, detections, box normalisation, IoU, positive/negative ROI selection and ordering, class / mask
+targets, the x/y-swapped ROIAlign call, the mask loss -- to its code rather than to a restatement.
+
+Tolerances: float32 arithmetic in a different association order -> 2e-6 absolute on O(1) coordinates, 1e-5 relative on
+the reduced losses; everything integer / boolean is exact."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import graph_case_inputs as GI          # noqa: E402
+
+from oracle import myolo_oracle as O    # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(HERE, "golden", "reference_graph_fixture.npz"))
+
+
+def _ocfg(c, warmup=0):
+    return dict(GRID_H=c["G"], GRID_W=c["G"], N_BOX=c["NB"], NUM_CLASSES=c["NC"], ANCHORS=c["ANCHORS"],
+                TRAIN_ROIS_PER_IMAGE=c["R"], MASK_SHAPE=[28, 28], MASK_POOL_SIZE=14, COORD_SCALE=c.get("COORD_SCALE", 1.0),
+                NO_OBJECT_SCALE=c.get("NO_OBJECT_SCALE", 1.0), OBJECT_SCALE=c.get("OBJECT_SCALE", 5.0),
+                CLASS_SCALE=c.get("CLASS_SCALE", 1.0), CLASS_WEIGHTS=np.asarray(c["CLASS_WEIGHTS"], np.float32),
+                WARM_UP_BATCHES=warmup, TRUE_BOX_BUFFER=c["TB"], LOSS_WEIGHTS={"yolo_sum_loss": 1.0, "myolo_mask_loss": 1.0})
+
+
+def _t(x):
+    return torch.from_numpy(np.ascontiguousarray(x))
+
+
+@pytest.mark.parametrize("name", list(GI.CASES))
+def test_oracle_equals_reference_source(gold, name):
+    c = GI.build(name)
+    g = lambda k: gold[name + "/" + k]                                             # noqa: E731
+    cfg = _ocfg(c)
+    y_pred, y_true, tb = _t(c["y_pred"]), _t(c["y_true"]), _t(c["true_boxes"])
+    # a11 yolo_custom_loss, normal and warm-up branch
+    assert np.isclose(O.yolo_custom_loss(y_true, y_pred, tb, cfg).item(), g("yolo_loss"), rtol=1e-5)
+    assert np.isclose(O.yolo_custom_loss(y_true, y_pred, tb, _ocfg(c, warmup=3), seen=1.0).item(), g("yolo_loss_warmup"), rtol=1e-5)
+    # a5 / a12 decode + detections
+    props = O.decode_yolo(y_pred, cfg)
+    assert np.allclose(props.numpy(), g("proposals"), rtol=0, atol=2e-6 * max(1.0, np.abs(g("proposals")).max()))
+    det = O.detections_layer(y_pred, cfg).numpy()
+    assert np.allclose(det[..., :5], g("detections")[..., :5], rtol=0, atol=2e-6 * max(1.0, np.abs(g("proposals")).max()))
+    assert np.array_equal(det[..., 5], g("detections")[..., 5])
+    # a6 norm_boxes_graph, trim_zeros_graph, overlaps_graph
+    S = c["S"]
+    gt_norm = O.norm_boxes_graph(_t(c["gt_boxes_px"]), S, S)
+    assert np.allclose(gt_norm.numpy(), g("gt_boxes_norm"), rtol=0, atol=1e-7)
+    nz = g("trim_nonzero_0")
+    assert np.array_equal((gt_norm[0].abs().sum(1) != 0).numpy(), nz)
+    ov = O.overlaps_graph(_t(g("proposals")[0]), _t(g("gt_boxes_norm")[0][nz]))
+    assert np.allclose(ov.numpy(), g("overlaps_0"), rtol=0, atol=2e-6, equal_nan=True)
+    # a7 DetectMaskTargetLayer on the reference's own proposals / normalised boxes (identical inputs -> exact selection)
+    rois, tids, tmasks = O.detect_mask_targets(_t(g("proposals")), _t(c["gt_class_ids"]), _t(g("gt_boxes_norm")),
+                                               _t(c["gt_masks"]), cfg)
+    assert np.array_equal(tids.numpy(), g("target_class_ids")) and (tids.numpy() > 0).sum() >= 2
+    assert np.array_equal(rois.numpy(), g("rois"))                                # same rows in the same order, bit for bit
+    ref_masks = np.unpackbits(g("target_masks_bits"))[:int(np.prod(g("target_masks_shape")))].reshape(g("target_masks_shape"))
+    assert np.array_equal(tmasks.numpy().astype(np.uint8), ref_masks)
+    # a8 PyramidROIAlign (boxes handed over as x1,y1,x2,y2: the reference's swapped sampling)
+    pooled = O.pyramid_roi_align(_t(g("rois")), _t(c["feat"]), 14).numpy()[:, ::5]
+    assert pooled.shape == g("pooled_every5").shape
+    assert np.allclose(pooled, g("pooled_every5"), rtol=0, atol=5e-6)
+    # a10 myolo_mask_loss_graph
+    tm = _t(ref_masks.astype(np.float32))
+    ml = O.myolo_mask_loss_graph(tm, _t(g("target_class_ids")), _t(c["pred_masks"]))
+    assert np.isclose(ml.item(), g("mask_loss"), rtol=1e-5)
+    assert O.myolo_mask_loss_graph(tm, torch.zeros_like(_t(g("target_class_ids"))), _t(c["pred_masks"])).item() == g("mask_loss_no_positives") == 0.0
+
+
+def test_shim_crop_and_resize_micro_cases():
+    """The one non-trivial primitive the stand-in supplies, against hand-computed values (tf.image.crop_and_resize:
+    corners map to [0, size-1], samples outside take the extrapolation value 0, crop size 1 samples the box centre)."""
+    import tf1_numpy_shim as tfs
+    img = np.arange(12, dtype=np.float32).reshape(1, 3, 4, 1)                      # value = 4*y + x
+    full = tfs.image.crop_and_resize(img, np.array([[0, 0, 1, 1]], np.float32), np.array([0]), [3, 4]).a
+    assert np.array_equal(full, img)
+    mid = tfs.image.crop_and_resize(img, np.array([[0, 0, 1, 1]], np.float32), np.array([0]), [2, 2]).a[0, :, :, 0]
+    assert np.array_equal(mid, [[0, 3], [8, 11]])
+    one = tfs.image.crop_and_resize(img, np.array([[0.25, 0.5, 0.75, 1.0]], np.float32), np.array([0]), [1, 1]).a
+    assert np.isclose(one.item(), 4 * 1.0 + 2.25)                                  # centre: y = 0.5*2 = 1, x = 0.75*3
+    out = tfs.image.crop_and_resize(img, np.array([[-0.5, 0, 0.5, 1.5]], np.float32), np.array([0]), [3, 4]).a[0, :, :, 0]
+    assert np.array_equal(out[0], [0, 0, 0, 0]) and out[1, 0] == 0.0 and np.array_equal(out[1:, 3], [0, 0])   # y=-1 row, x=4.5 col
+    assert np.isclose(out[2, 1], 4 * 1.0 + 1.5)
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(GI.CASES))
+def test_device_kernels_equal_reference_source(gold, name):
+    """The C-ABI entry points of rows a5/a7/a8/a10/a11/a12 directly against the reference-source vectors."""
+    from myolo import _cabi as C
+    c = GI.build(name)
+    g = lambda k: gold[name + "/" + k]                                             # noqa: E731
+    dev = torch.device("cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    B, G, NB, NC, TB, M, S, R = c["B"], c["G"], c["NB"], c["NC"], c["TB"], c["M"], c["S"], c["R"]
+    y_pred = _t(c["y_pred"]).to(dev)
+    anchors = torch.tensor(c["ANCHORS"], dtype=torch.float32, device=dev)
+    box_tol = 5e-6 * max(1.0, np.abs(g("proposals")).max())
+    # a5 / a12
+    props = torch.empty(B, R, 4, device=dev)
+    det = torch.empty(B, R, 6, device=dev)
+    C.call("myolo_yolo_decode", y_pred, anchors, props, det, B, G, G, NB, NC, st)
+    assert np.allclose(props.cpu().numpy(), g("proposals"), rtol=0, atol=box_tol)
+    assert np.allclose(det.cpu().numpy()[..., :5], g("detections")[..., :5], rtol=0, atol=box_tol)
+    assert np.array_equal(det.cpu().numpy()[..., 5], g("detections")[..., 5])
+    # a11, normal and warm-up branch
+    cw = torch.tensor(c["CLASS_WEIGHTS"], dtype=torch.float32, device=dev)
+    sc = C.float_array([c.get("OBJECT_SCALE", 5.0), c.get("NO_OBJECT_SCALE", 1.0), c.get("COORD_SCALE", 1.0), c.get("CLASS_SCALE", 1.0)])
+    lo = torch.empty(5, device=dev)
+    ws = torch.zeros(8, dtype=torch.float64, device=dev)
+    for warm, key in ((0, "yolo_loss"), (1, "yolo_loss_warmup")):
+        C.call("myolo_yolo_loss", _t(c["y_true"]).to(dev), y_pred, _t(c["true_boxes"]).reshape(B, TB, 4).to(dev), anchors, cw,
+               B, G, G, NB, NC, TB, sc, warm, 1.0, lo, None, ws, st)
+        assert np.isclose(lo[0].item(), g(key), rtol=3e-5), (key, lo[0].item(), g(key))
+    # a6 + a7 from the reference's proposals: selection, order, class ids and 28x28 targets exact
+    rois = torch.empty(B, R, 4, device=dev)
+    tids = torch.empty(B, R, dtype=torch.int32, device=dev)
+    tmask = torch.empty(B, R, 28, 28, device=dev)
+    npos = torch.empty(B, dtype=torch.int32, device=dev)
+    src = torch.empty(B, R, dtype=torch.int32, device=dev)
+    rgt = torch.empty(B, R, dtype=torch.int32, device=dev)
+    C.call("myolo_detect_mask_targets", _t(g("proposals")).to(dev), _t(c["gt_class_ids"]).to(dev), _t(c["gt_boxes_px"]).to(dev),
+           _t(c["gt_masks"].astype(np.uint8)).to(dev), B, R, TB, M, S, 28, 28, rois, tids, tmask, npos, src, rgt, st)
+    assert np.array_equal(tids.cpu().numpy(), g("target_class_ids"))
+    assert np.array_equal(rois.cpu().numpy(), g("rois"))
+    assert np.array_equal(npos.cpu().numpy(), (g("target_class_ids") > 0).sum(1))
+    ref_masks = np.unpackbits(g("target_masks_bits"))[:int(np.prod(g("target_masks_shape")))].reshape(g("target_masks_shape"))
+    assert np.array_equal(tmask.cpu().numpy().astype(np.uint8), ref_masks)
+    # a8: crop_and_resize over the reference's rois (x/y swapped, as the reference calls it)
+    feat = _t(c["feat"]).to(dev)
+    F = feat.shape[1]
+    pooled = torch.empty(B * R, 14, 14, c["C"], device=dev)
+    C.call("myolo_roialign_fwd", C.view(feat, B, F, F, c["C"]), rois, B * R, R, 14, C.view(pooled, B * R, 14, 14, c["C"]), 0, st)
+    assert np.allclose(pooled.reshape(B, R, 14, 14, c["C"])[:, ::5].cpu().numpy(), g("pooled_every5"), rtol=0, atol=5e-6)
+    # a10
+    lm = torch.empty(1, device=dev)
+    C.call("myolo_mask_loss", _t(c["pred_masks"]).reshape(B * R, 28, 28, NC).to(dev), tmask, tids, B * R, 28, 28, NC, 1.0, lm,
+           None, torch.zeros(2, dtype=torch.float64, device=dev), st)
+    assert np.isclose(lm.item(), g("mask_loss"), rtol=2e-5), (lm.item(), g("mask_loss"))
