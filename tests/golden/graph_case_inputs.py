@@ -62,3 +62,43 @@ def build(name):
     c.update(y_pred=y_pred, y_true=y_true, true_boxes=true_boxes, gt_class_ids=ids, gt_boxes_px=boxes_px, gt_masks=masks,
              feat=feat, pred_masks=pred_masks, R=R)
     return c
+
+
+# ---- network cases: the reference's graph BUILDERS (conv_block / mobilenet_graph / yolo_branch_graph / build_mask_graph)
+NET = dict(B=2, S=64, NB=3, NC=4, R=10, seed=303)
+
+
+def weights(nb, nc, seed):
+    """Every variable of the model (names and shapes from the product's param_specs, which a CPU test pins to the
+    reference's GraphDef) filled from a frozen RandomState stream: He-scaled kernels, non-trivial BN statistics."""
+    from myolo.engine import param_specs
+    rs = np.random.RandomState(seed)
+    P = {}
+    for name, shape, _ in param_specs(nb, nc):
+        leaf = name.rsplit("/", 1)[1]
+        if leaf in ("kernel", "depthwise_kernel"):
+            fan_in = shape[0] * shape[1] * (shape[2] if leaf == "kernel" else 1)
+            if name.startswith("myolo_mask_deconv"):
+                fan_in = shape[3]
+            P[name] = (rs.standard_normal(shape) * np.sqrt(2.0 / fan_in)).astype(np.float32)
+        elif leaf in ("gamma", "moving_variance"):
+            P[name] = rs.uniform(0.6, 1.4, size=shape).astype(np.float32)
+        elif leaf in ("beta", "moving_mean"):
+            P[name] = (0.1 * rs.standard_normal(shape)).astype(np.float32)
+        else:
+            P[name] = (0.05 * rs.standard_normal(shape)).astype(np.float32)
+    return P
+
+
+def net_inputs():
+    c = dict(NET)
+    rs = np.random.RandomState(c["seed"] + 1)
+    c["image"] = rs.uniform(0.0, 1.0, size=(c["B"], c["S"], c["S"], 3)).astype(np.float32)
+    F = c["S"] // 8
+    c["feat"] = rs.standard_normal((c["B"], F, F, 256)).astype(np.float32)
+    x1y1 = rs.uniform(-0.1, 0.6, size=(c["B"], c["R"], 2))
+    wh = rs.uniform(0.1, 0.6, size=(c["B"], c["R"], 2))
+    rois = np.concatenate([x1y1, x1y1 + wh], -1).astype(np.float32)
+    rois[:, -1] = 0.0                                              # a zero-padded ROI row
+    c["rois"] = rois
+    return c

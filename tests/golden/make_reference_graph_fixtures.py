@@ -27,7 +27,10 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 import graph_case_inputs as GI          # noqa: E402
+import keras2_layers_shim as kls        # noqa: E402
 import tf1_numpy_shim as tfs            # noqa: E402
+
+PRODUCT = os.path.join(os.path.dirname(os.path.dirname(HERE)), "mask-yolo_b200")
 
 OUT = os.path.join(HERE, "reference_graph_fixture.npz")
 
@@ -47,11 +50,6 @@ class _LooseVersion(object):
         return self.v >= o.v
 
 
-class _Layer(object):
-    def __init__(self, **kwargs):
-        self.name = kwargs.get("name")
-
-
 class _Any(object):
     def __init__(self, *a, **k):
         pass
@@ -61,10 +59,12 @@ def load_reference_model():
     sys.modules["tensorflow"] = tfs
     kb = _stub("keras.backend", reshape=tfs.k_reshape, switch=tfs.k_switch, mean=tfs.k_mean,
                binary_crossentropy=tfs.k_binary_crossentropy)
-    _stub("keras", __version__="2.2.4", backend=kb, engine=_stub("keras.engine", Layer=_Layer),
-          layers=_stub("keras.layers"), models=_stub("keras.models"), utils=_stub("keras.utils", Sequence=object))
-    _stub("keras_applications", get_keras_submodule=lambda name: None,
-          mobilenet=_stub("keras_applications.mobilenet", _depthwise_conv_block=None),
+    layers = _stub("keras.layers", **{k: getattr(kls, k) for k in ("ZeroPadding2D", "Conv2D", "DepthwiseConv2D", "Conv2DTranspose",
+                                                                   "BatchNormalization", "Activation", "Reshape", "TimeDistributed")})
+    _stub("keras", __version__="2.2.4", backend=kb, engine=_stub("keras.engine", Layer=kls.Layer),
+          layers=layers, models=_stub("keras.models"), utils=_stub("keras.utils", Sequence=object))
+    _stub("keras_applications", get_keras_submodule=lambda name: {"backend": kls.backend}[name],
+          mobilenet=_stub("keras_applications.mobilenet", _depthwise_conv_block=kls.depthwise_conv_block),
           mobilenet_v2=_stub("keras_applications.mobilenet_v2", MobileNetV2=None))
     _stub("pytz", timezone=lambda name: None)
     _stub("distutils", version=_stub("distutils.version", LooseVersion=_LooseVersion))
@@ -106,7 +106,52 @@ def set_config(ref_model, c, warmup=0):
     return cfg()
 
 
+def product_weights():
+    """Variable names / shapes come from the product's param_specs; it lives in a package that is also called `myolo`, so
+    the weights are drawn BEFORE the reference's package is imported and the product's modules are dropped again."""
+    sys.path.insert(0, PRODUCT)
+    try:
+        c = GI.NET
+        return GI.weights(c["NB"], c["NC"], c["seed"])
+    finally:
+        sys.path.remove(PRODUCT)
+        for k in [k for k in sys.modules if k == "myolo" or k.startswith("myolo.") or k == "mrcnn" or k.startswith("mrcnn.")]:
+            del sys.modules[k]
+
+
+def net_cases(M, out, W):
+    """conv_block + mobilenet_graph (42-79), yolo_branch_graph (249-278), build_mask_graph (668-715) from the reference's
+    source, in both learning phases.  Stored: strided samples of the activations (the tests regenerate inputs and weights
+    from seeds) and, per phase, which statistics every BatchNormalization used."""
+    c = GI.net_inputs()
+    kls.WEIGHTS.clear()
+    kls.WEIGHTS.update(W)
+
+    class Cfg(object):
+        N_BOX, NUM_CLASSES, GRID_H, GRID_W = c["NB"], c["NC"], c["S"] // 32, c["S"] // 32
+
+    for phase in (1, 0):
+        kls.STATE["learning_phase"] = phase
+        del kls.USED[:]
+        c3 = M.mobilenet_graph(tfs.T(c["image"]), "mobilenet")
+        yolo = M.yolo_branch_graph(c3, Cfg())
+        n_backbone_bn = len(kls.USED)
+        masks = M.build_mask_graph(tfs.T(c["rois"]), [tfs.T(c["feat"])], 14, c["NC"], train_bn=False)
+        tag = "net/phase%d/" % phase
+        assert c3.a.shape == (c["B"], c["S"] // 8, c["S"] // 8, 512) and yolo.a.shape == (c["B"], 2, 2, c["NB"], 5 + c["NC"])
+        assert masks.a.shape == (c["B"], c["R"], 28, 28, c["NC"])
+        out[tag + "c3_every8"] = c3.a[..., ::8]
+        out[tag + "yolo"] = yolo.a
+        out[tag + "masks_every3"] = masks.a[:, ::3]
+        out[tag + "bn_names"] = np.asarray([n for n, _ in kls.USED])
+        out[tag + "bn_batch_stats"] = np.asarray([k == "batch" for _, k in kls.USED])
+        print(tag, "c3 |max|", np.abs(c3.a).max(), "yolo |max|", np.abs(yolo.a).max(), "masks mean", masks.a.mean(),
+              "BN layers", n_backbone_bn, "+", len(kls.USED) - n_backbone_bn,
+              "mask BNs on batch statistics:", [n for n, k in kls.USED[n_backbone_bn:] if k == "batch"])
+
+
 def main():
+    W = product_weights()
     M = load_reference_model()
     T = tfs.T
     out = {}
@@ -141,6 +186,7 @@ def main():
         out[name + "/mask_loss_no_positives"] = M.myolo_mask_loss_graph(tmasks, T(np.zeros_like(tids.a)), T(c["pred_masks"])).a
         print(name, "yolo_loss", out[name + "/yolo_loss"], "warm-up", out[name + "/yolo_loss_warmup"], "positives",
               (tids.a > 0).sum(1), "mask_loss", out[name + "/mask_loss"])
+    net_cases(M, out, W)
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, os.path.getsize(OUT), "bytes,", len(out), "arrays")
 

@@ -79,6 +79,40 @@ def test_oracle_equals_reference_source(gold, name):
     assert O.myolo_mask_loss_graph(tm, torch.zeros_like(_t(g("target_class_ids"))), _t(c["pred_masks"])).item() == g("mask_loss_no_positives") == 0.0
 
 
+@pytest.mark.parametrize("phase", [1, 0])
+def test_oracle_networks_equal_reference_builders(gold, phase):
+    """a1-a4 and a9: conv_block + mobilenet_graph, yolo_branch_graph and build_mask_graph as the reference's own source
+    wires them (Keras layers restated by tests/golden/keras2_layers_shim.py), learning phase 1 and 0.  Also pins which
+    BatchNormalization layers follow the learning phase: all 29 of the backbone / YOLO branch and, in the mask head,
+    ONLY myolo_mask_bn1 (bn2-4 are called with training=False, model.py:695-708)."""
+    c = GI.net_inputs()
+    P = {k: _t(v).double() for k, v in GI.weights(c["NB"], c["NC"], c["seed"]).items()}     # fp64 oracle vs fp64 layers
+    tag = "net/phase%d/" % phase
+    training = bool(phase)
+    cfg = dict(GRID_H=c["S"] // 32, GRID_W=c["S"] // 32, N_BOX=c["NB"], NUM_CLASSES=c["NC"], MASK_POOL_SIZE=14)
+    rec = O._BNRec()
+    c3 = O.mobilenet_graph(_t(c["image"]).double(), P, training, rec)
+    yolo = O.yolo_branch_graph(c3, P, cfg, training, rec)
+    masks = O.build_mask_graph(_t(c["rois"]).double(), _t(c["feat"]).double(), P, cfg, training, rec)
+
+    def close(a, ref, tol, what):
+        scale = max(1.0, float(np.abs(ref).max()))
+        err = float(np.abs(a - ref).max())
+        assert err <= tol * scale, (what, err, scale)
+
+    close(c3.numpy()[..., ::8], gold[tag + "c3_every8"], 1e-9, "backbone feature map")
+    close(yolo.numpy(), gold[tag + "yolo"], 1e-9, "yolo branch output")
+    # the ROIAlign in front of the mask head runs in float32 in the reference's graph (tf.image.crop_and_resize)
+    close(masks.numpy()[:, ::3], gold[tag + "masks_every3"], 5e-6, "mask head output")
+    names, batch = [str(n) for n in gold[tag + "bn_names"]], gold[tag + "bn_batch_stats"]
+    assert len(names) == 33 and names[:2] == ["conv1_bn", "conv_dw_1_bn"] and names[-4:] == ["myolo_mask_bn%d" % i for i in (1, 2, 3, 4)]
+    assert [n for n, b in zip(names, batch) if b] == [n for n, _, _ in rec.items]        # same layers, same order
+    if training:
+        assert batch[:29].all() and batch[29:].tolist() == [True, False, False, False]
+    else:
+        assert not batch.any()
+
+
 def test_shim_crop_and_resize_micro_cases():
     """The one non-trivial primitive the stand-in supplies, against hand-computed values (tf.image.crop_and_resize:
     corners map to [0, size-1], samples outside take the extrapolation value 0, crop size 1 samples the box centre)."""
