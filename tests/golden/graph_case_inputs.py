@@ -102,3 +102,37 @@ def net_inputs():
     rois[:, -1] = 0.0                                              # a zero-padded ROI row
     c["rois"] = rois
     return c
+
+
+# ---- whole-model case: MaskYOLO.build (787-941), modes 'training' and 'inference'
+BUILD = dict(B=2, S=64, G=2, NB=3, NC=4, TB=15, M=15, R=12, seed=404, ANCHORS=[0.5, 0.6, 0.8, 0.7, 1.1, 1.2])
+
+
+def build_image():
+    c = dict(BUILD)
+    rs = np.random.RandomState(c["seed"] + 1)
+    c["image"] = rs.uniform(0.0, 1.0, size=(c["B"], c["S"], c["S"], 3)).astype(np.float32)
+    return c
+
+
+def gt_from_boxes(c, gt_class_ids, gt_boxes_px):
+    """Masks (ellipse inscribed in each pixel box), YOLO target and true-box buffer for given padded gt arrays."""
+    B, S, G, NB, NC, TB, M = c["B"], c["S"], c["G"], c["NB"], c["NC"], c["TB"], c["M"]
+    masks = np.zeros((B, S, S, M), bool)
+    y_true = np.zeros((B, G, G, NB, 5 + NC), np.float32)
+    true_boxes = np.zeros((B, 1, 1, 1, TB, 4), np.float32)
+    yy, xx = np.mgrid[0:S, 0:S]
+    for b in range(B):
+        for k in range(TB):
+            if gt_class_ids[b, k] == 0:
+                continue
+            x1, y1, x2, y2 = [float(v) for v in gt_boxes_px[b, k]]
+            masks[b, :, :, k] = ((xx - (x1 + x2 - 1) / 2.0) / ((x2 - x1) / 2.0)) ** 2 + \
+                                ((yy - (y1 + y2 - 1) / 2.0) / ((y2 - y1) / 2.0)) ** 2 <= 1.0
+            gcx, gcy, gw, gh = 0.5 * (x1 + x2) / (S / G), 0.5 * (y1 + y2) / (S / G), (x2 - x1) / (S / G), (y2 - y1) / (S / G)
+            gx, gy = min(int(gcx), G - 1), min(int(gcy), G - 1)
+            y_true[b, gy, gx, k % NB, 0:5] = (gcx, gcy, gw, gh, 1.0)
+            y_true[b, gy, gx, k % NB, 5:] = 0.0
+            y_true[b, gy, gx, k % NB, 5 + gt_class_ids[b, k]] = 1.0
+            true_boxes[b, 0, 0, 0, k] = (gcx, gcy, gw, gh)
+    return masks, y_true, true_boxes

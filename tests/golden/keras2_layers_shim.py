@@ -72,7 +72,7 @@ class Conv2D(Layer):
         Layer.__init__(self, name)
         self.filters, self.k = filters, kernel_size if isinstance(kernel_size, (tuple, list)) else (kernel_size, kernel_size)
         self.s = strides if isinstance(strides, (tuple, list)) else (strides, strides)
-        self.padding, self.use_bias, self.activation = padding, use_bias, activation
+        self.padding, self.use_bias, self.activation = padding.lower(), use_bias, activation      # Keras normalises the case
 
     def call(self, x):
         x = torch.from_numpy(np.ascontiguousarray(_np(x), dtype=STATE["dtype"])).permute(0, 3, 1, 2)
@@ -199,3 +199,38 @@ def depthwise_conv_block(inputs, pointwise_conv_filters, alpha, depth_multiplier
                name="conv_pw_%d" % block_id)(x)
     x = BatchNormalization(axis=-1, name="conv_pw_%d_bn" % block_id)(x)
     return Activation(relu6, name="conv_pw_%d_relu" % block_id)(x)
+
+
+# ---- the functional-API names MaskYOLO.build (787-941) uses, evaluated eagerly
+FEEDS = {}         # Input name -> numpy array
+
+
+def Input(shape=None, name=None, dtype=None, **kwargs):
+    """A placeholder is bound to its value at once (the graph is evaluated while it is being built)."""
+    return tfs.T(FEEDS[name])
+
+
+class Lambda(Layer):
+    def __init__(self, function, name=None, **kwargs):
+        Layer.__init__(self, name)
+        self.function = function
+
+    def call(self, x):
+        return self.function(x)
+
+
+class Model(object):
+    """KM.Model(inputs, outputs): keeps the evaluated outputs.  Calling the model on tensors (the nested yolo_model,
+    model.py:851-852) returns them, after checking that the tensors are the ones its placeholders were bound to."""
+
+    def __init__(self, inputs, outputs, name=None):
+        self.inputs, self.outputs, self.name, self.layers = list(inputs), outputs, name, []
+
+    def __call__(self, inputs):
+        assert len(inputs) == len(self.inputs)
+        for a, b in zip(inputs, self.inputs):
+            assert np.array_equal(_np(a), _np(b)), "nested model called on a tensor other than its bound placeholder"
+        return self.outputs
+
+    def summary(self):
+        return "%s: %d outputs" % (self.name, len(self.outputs) if isinstance(self.outputs, (list, tuple)) else 1)

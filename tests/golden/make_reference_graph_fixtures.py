@@ -57,12 +57,13 @@ class _Any(object):
 
 def load_reference_model():
     sys.modules["tensorflow"] = tfs
-    kb = _stub("keras.backend", reshape=tfs.k_reshape, switch=tfs.k_switch, mean=tfs.k_mean,
+    kb = _stub("keras.backend", shape=tfs.shape, reshape=tfs.k_reshape, switch=tfs.k_switch, mean=tfs.k_mean,
                binary_crossentropy=tfs.k_binary_crossentropy)
     layers = _stub("keras.layers", **{k: getattr(kls, k) for k in ("ZeroPadding2D", "Conv2D", "DepthwiseConv2D", "Conv2DTranspose",
-                                                                   "BatchNormalization", "Activation", "Reshape", "TimeDistributed")})
+                                                                   "BatchNormalization", "Activation", "Reshape", "TimeDistributed",
+                                                                   "Input", "Lambda")})
     _stub("keras", __version__="2.2.4", backend=kb, engine=_stub("keras.engine", Layer=kls.Layer),
-          layers=layers, models=_stub("keras.models"), utils=_stub("keras.utils", Sequence=object))
+          layers=layers, models=_stub("keras.models", Model=kls.Model), utils=_stub("keras.utils", Sequence=object))
     _stub("keras_applications", get_keras_submodule=lambda name: {"backend": kls.backend}[name],
           mobilenet=_stub("keras_applications.mobilenet", _depthwise_conv_block=kls.depthwise_conv_block),
           mobilenet_v2=_stub("keras_applications.mobilenet_v2", MobileNetV2=None))
@@ -142,12 +143,62 @@ def net_cases(M, out, W):
         assert masks.a.shape == (c["B"], c["R"], 28, 28, c["NC"])
         out[tag + "c3_every8"] = c3.a[..., ::8]
         out[tag + "yolo"] = yolo.a
-        out[tag + "masks_every3"] = masks.a[:, ::3]
+        out[tag + "masks_sub"] = masks.a[:, ::3, ::2, ::2]
         out[tag + "bn_names"] = np.asarray([n for n, _ in kls.USED])
         out[tag + "bn_batch_stats"] = np.asarray([k == "batch" for _, k in kls.USED])
         print(tag, "c3 |max|", np.abs(c3.a).max(), "yolo |max|", np.abs(yolo.a).max(), "masks mean", masks.a.mean(),
               "BN layers", n_backbone_bn, "+", len(kls.USED) - n_backbone_bn,
               "mask BNs on batch statistics:", [n for n, k in kls.USED[n_backbone_bn:] if k == "batch"])
+
+
+def build_cases(M, out, W):
+    """MaskYOLO(mode, config) -> MaskYOLO.build (761-941) from the reference's source: the training graph (six outputs) in
+    learning phase 1 and the inference graph (three outputs) in phase 0.  Ground-truth boxes are taken from the model's
+    own proposals so that positive ROIs exist and the mask loss is exercised; they are stored (the test regenerates the
+    image, the weights and everything derived from the boxes)."""
+    c = GI.build_image()
+    kls.WEIGHTS.clear()
+    kls.WEIGHTS.update(W)
+    base = dict(c, CLASS_WEIGHTS=[1.0] * c["NC"])
+    cfg = set_config(M, base)
+    cfg.IMAGE_SHAPE, cfg.BACKBONE, cfg.TOP_FEATURE_MAP_DEPTH, cfg.SECOND_PHASE_YOLO_DEPTH = [c["S"], c["S"], 3], "mobilenet", 256, 512
+    cfg.MASK_POOL_SIZE = 14
+    B, S, TB = c["B"], c["S"], c["TB"]
+    # proposals of the untrained network -> ground truth that overlaps some of them
+    kls.STATE["learning_phase"] = 1
+    c4 = M.mobilenet_graph(tfs.T(c["image"]), "mobilenet")
+    props = M.DecodeYOLOLayer(config=cfg).call([M.yolo_branch_graph(c4, cfg)]).a
+    ids = np.zeros((B, TB), np.int32)
+    boxes = np.zeros((B, TB, 4), np.float32)
+    rs = np.random.RandomState(c["seed"] + 2)
+    for b in range(B):
+        k = 0
+        for r in rs.permutation(props.shape[1]):
+            px = np.round(props[b, r] * (S - 1) + np.array([0, 0, 1, 1])).clip(0, S)
+            if px[2] - px[0] >= 8 and px[3] - px[1] >= 8 and k < 3:
+                ids[b, k], boxes[b, k] = int(rs.randint(1, c["NC"])), px
+                k += 1
+        assert k >= 2, "untrained proposals too degenerate for this seed"
+    masks, y_true, true_boxes = GI.gt_from_boxes(c, ids, boxes)
+    out["build/gt_class_ids"], out["build/gt_boxes_px"] = ids, boxes
+    kls.FEEDS.clear()
+    kls.FEEDS.update(input_image=c["image"], input_true_boxes=true_boxes, input_yolo_target=y_true, input_gt_class_ids=ids,
+                     input_gt_boxes=boxes, input_gt_masks=masks, input_yolo_feature_map=c4.a)
+    model = M.MaskYOLO(mode="training", config=cfg).keras_model
+    names = ["yolo_output", "yolo_proposals", "output_rois", "myolo_mask", "yolo_sum_loss", "mask_loss"]
+    assert model.name == "mask+yolo" and len(model.outputs) == 6
+    for n, t in zip(names, model.outputs):
+        out["build/training/" + n] = np.asarray(t.a)[:, ::2, ::3, ::3] if n == "myolo_mask" else np.asarray(t.a)
+    assert (np.abs(out["build/training/output_rois"]).sum(-1) > 0).any() and out["build/training/mask_loss"] > 0
+    print("build/training: yolo_sum_loss", out["build/training/yolo_sum_loss"], "mask_loss", out["build/training/mask_loss"])
+    kls.STATE["learning_phase"] = 0
+    c4 = M.mobilenet_graph(tfs.T(c["image"]), "mobilenet")
+    kls.FEEDS["input_yolo_feature_map"] = c4.a
+    model = M.MaskYOLO(mode="inference", config=cfg).keras_model
+    assert model.name == "mask_yolo_inference" and len(model.outputs) == 3
+    for n, t in zip(["yolo_output", "detections", "myolo_mask"], model.outputs):
+        out["build/inference/" + n] = np.asarray(t.a)[:, ::2, ::3, ::3] if n == "myolo_mask" else np.asarray(t.a)
+    print("build/inference: detections", out["build/inference/detections"].shape, "masks", out["build/inference/myolo_mask"].shape)
 
 
 def main():
@@ -187,6 +238,7 @@ def main():
         print(name, "yolo_loss", out[name + "/yolo_loss"], "warm-up", out[name + "/yolo_loss_warmup"], "positives",
               (tids.a > 0).sum(1), "mask_loss", out[name + "/mask_loss"])
     net_cases(M, out, W)
+    build_cases(M, out, W)
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, os.path.getsize(OUT), "bytes,", len(out), "arrays")
 

@@ -103,7 +103,7 @@ def test_oracle_networks_equal_reference_builders(gold, phase):
     close(c3.numpy()[..., ::8], gold[tag + "c3_every8"], 1e-9, "backbone feature map")
     close(yolo.numpy(), gold[tag + "yolo"], 1e-9, "yolo branch output")
     # the ROIAlign in front of the mask head runs in float32 in the reference's graph (tf.image.crop_and_resize)
-    close(masks.numpy()[:, ::3], gold[tag + "masks_every3"], 5e-6, "mask head output")
+    close(masks.numpy()[:, ::3, ::2, ::2], gold[tag + "masks_sub"], 5e-6, "mask head output")
     names, batch = [str(n) for n in gold[tag + "bn_names"]], gold[tag + "bn_batch_stats"]
     assert len(names) == 33 and names[:2] == ["conv1_bn", "conv_dw_1_bn"] and names[-4:] == ["myolo_mask_bn%d" % i for i in (1, 2, 3, 4)]
     assert [n for n, b in zip(names, batch) if b] == [n for n, _, _ in rec.items]        # same layers, same order
@@ -111,6 +111,40 @@ def test_oracle_networks_equal_reference_builders(gold, phase):
         assert batch[:29].all() and batch[29:].tolist() == [True, False, False, False]
     else:
         assert not batch.any()
+
+
+def test_oracle_whole_model_equals_reference_build(gold):
+    """MaskYOLO(mode, config).build (761-941) from the reference's source, training graph (six outputs, learning phase 1)
+    and inference graph (three outputs, phase 0), against oracle.forward_training / forward_inference in fp64: same
+    weights, same image, ground truth taken from the fixture."""
+    c = GI.build_image()
+    P = {k: _t(v).double() for k, v in GI.weights(GI.NET["NB"], GI.NET["NC"], GI.NET["seed"]).items()}
+    ids, boxes = gold["build/gt_class_ids"], gold["build/gt_boxes_px"]
+    masks, y_true, true_boxes = GI.gt_from_boxes(c, ids, boxes)
+    cfg = _ocfg(dict(c, CLASS_WEIGHTS=[1.0] * c["NC"]))
+    image = _t(c["image"]).double()
+    out = O.forward_training(P, [image, _t(true_boxes).double(), _t(y_true).double(), _t(ids), _t(boxes).double(), _t(masks)], cfg)
+
+    def close(a, ref, tol, what):
+        scale = max(1.0, float(np.abs(ref).max()))
+        err = float(np.abs(np.asarray(a) - ref).max())
+        assert err <= tol * scale, (what, err, scale)
+
+    g = lambda k: gold["build/training/" + k]                                     # noqa: E731
+    close(out["yolo_output"].numpy(), g("yolo_output"), 1e-9, "yolo_output")
+    close(out["yolo_proposals"].numpy(), g("yolo_proposals"), 1e-6, "yolo_proposals")       # float32 cell grid / anchors in the graph
+    close(out["output_rois"].numpy(), g("output_rois"), 1e-6, "output_rois")
+    assert np.array_equal(np.abs(out["output_rois"].numpy()).sum(-1) > 0, np.abs(g("output_rois")).sum(-1) > 0)
+    assert (out["target_class_ids"].numpy() > 0).sum() >= 2
+    close(out["myolo_mask"].numpy()[:, ::2, ::3, ::3], g("myolo_mask"), 5e-6, "myolo_mask")
+    assert np.isclose(out["yolo_sum_loss"].item(), g("yolo_sum_loss"), rtol=1e-6)
+    assert np.isclose(out["mask_loss"].item(), g("mask_loss"), rtol=1e-5)
+    inf = O.forward_inference(P, image, cfg)
+    g = lambda k: gold["build/inference/" + k]                                    # noqa: E731
+    close(inf["yolo_output"].numpy(), g("yolo_output"), 1e-9, "inference yolo_output")
+    close(inf["detections"].numpy()[..., :5], g("detections")[..., :5], 1e-6, "detections")
+    assert np.array_equal(inf["detections"].numpy()[..., 5], g("detections")[..., 5])
+    close(inf["myolo_mask"].numpy()[:, ::2, ::3, ::3], g("myolo_mask"), 5e-6, "inference myolo_mask")
 
 
 def test_shim_crop_and_resize_micro_cases():
