@@ -4,17 +4,30 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline``
 ``--impl reference`` legs may import this module.  The product package
 (``mask-yolo_b200/``) never imports it and has no CPU fallback.
 
-PARITY UNPINNED.  The reference (jianing-sun/Mask-YOLO @ 402dbd9) ships no golden vectors,
-no known-answer tests and cannot be executed here (TensorFlow 1.x / Keras 2.x /
-keras_applications / mrcnn are absent, Python 3.12).  This file is therefore a *restatement*
-of the reference's algorithm in torch-CPU tensor ops (fp32 by default, fp64 when the inputs are
-fp64), function by function, with the third-party semantics (TF ``crop_and_resize``,
-``FusedBatchNorm``, Keras ``BatchNormalization`` / ``Adam`` / ``binary_crossentropy``,
-``keras_applications.mobilenet._depthwise_conv_block``) restated from their published
-behaviour.  What IS pinned: the structure (variable names/shapes, paddings, strides, eps,
-crop sizes, thresholds, Adam constants) against the GraphDef the reference ships
-(tests/golden/graph_fixture.json, generated by tests/golden/make_graph_fixture.py), the
-hand-computed micro-cases in tests/test_oracle.py, and fp64-vs-fp32 self-consistency.
+PARITY STATUS.  The reference (jianing-sun/Mask-YOLO @ 402dbd9) ships no golden vectors and no
+known-answer tests, and its third-party stack (TensorFlow 1.x / Keras 2.x / keras_applications /
+mrcnn) cannot be installed here (Python 3.12).  This file is a *restatement* of the reference's
+algorithm in torch-CPU tensor ops (fp32 by default, fp64 when the inputs are fp64), function by
+function.  It is pinned as follows:
+  * PINNED to the reference's own Python source, executed here: every function of myolo/model.py on
+    the path -- yolo_custom_loss (both branches), DecodeYOLOLayer, DetectionsLayer, norm_boxes_graph,
+    trim_zeros_graph, overlaps_graph, DetectMaskTargetLayer / detect_mask_target_graph,
+    PyramidROIAlign, myolo_mask_loss_graph, conv_block, mobilenet_graph, yolo_branch_graph,
+    build_mask_graph and the whole MaskYOLO(mode, config).build for 'training' and 'inference' -- runs
+    UNMODIFIED from /root/reference over eager numpy/torch stand-ins for its TensorFlow / Keras
+    primitives (tests/golden/tf1_numpy_shim.py, keras2_layers_shim.py); the outputs are committed as
+    tests/golden/reference_graph_fixture.npz (tests/golden/make_reference_graph_fixtures.py) and
+    tests/test_reference_graph_golden.py holds this oracle to them: selections, orderings, class ids
+    and mask targets exact, fp64 network outputs to 1e-9, losses to 1e-5.  The host-side numpy
+    functions of myolo/myolo_utils.py and example/shapes/dataset_shapes.py run as they are
+    (tests/golden/make_reference_fixtures.py, tests/test_reference_golden.py).
+  * PARITY UNPINNED for the third-party PRIMITIVES only: the TF kernels (``crop_and_resize``,
+    ``FusedBatchNorm``, conv / SAME padding, reductions), Keras ``BatchNormalization`` moving update /
+    ``Adam`` / ``binary_crossentropy`` and ``keras_applications.mobilenet._depthwise_conv_block`` are
+    restated from their published behaviour (here and, independently, in the stand-ins); their
+    structure (variable names/shapes, paddings, strides, eps, crop sizes, thresholds, Adam constants,
+    BN train flags) is pinned against the GraphDef the reference ships (tests/golden/graph_fixture.json),
+    plus hand-computed micro-cases (tests/test_oracle.py) and fp64-vs-fp32 self-consistency.
 
 All ``file:line`` citations are relative to /root/reference/.
 Layout everywhere: activations NHWC, conv kernels HWIO, depthwise [3,3,C,1],
