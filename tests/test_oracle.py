@@ -1,8 +1,8 @@
 """CPU tests of the oracle (oracle/myolo_oracle.py): structure pinned against the GraphDef the
 reference ships (tests/golden/graph_fixture.json), hand-computed micro-cases for the third-party
 semantics it restates (tf.image.crop_and_resize, Keras BCE, YOLO loss, Keras Adam / BN update) and
-fp64-vs-fp32 self-consistency.  The reference has no golden vectors: parity is unpinned
-beyond these."""
+fp64-vs-fp32 self-consistency.  The reference has no golden vectors of its own; the vectors
+made by executing its source are checked in test_reference_graph_golden.py / test_reference_golden.py."""
 import json
 import math
 import os
