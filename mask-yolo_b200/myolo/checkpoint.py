@@ -1,0 +1,71 @@
+"""Checkpoint files of the B200 path: a flat {Keras variable name: array} mapping.
+
+The reference saves Keras HDF5 weight files (model.py:1157-1196: `load_weights(filepath, by_name, exclude)`, nested
+`yolo_model` group).  h5py is not a dependency of this package; what is read and written here are containers of the SAME
+key space -- the variable names of the reference's graph (`conv1/kernel`, `conv_dw_7_bn/moving_mean`,
+`myolo_mask_conv1/bias`, ...; SURVEY 10.3, pinned by tests/golden/graph_fixture.json):
+
+    .pt / .pth / anything else   torch.save of the dict (what MaskYOLO.train writes after every epoch)
+    .npz                         numpy archive, one array per variable
+    .safetensors                 safetensors file, one tensor per variable
+    .h5 / .hdf5                  refused with a pointer to scripts/h5_to_npz.py (run it where h5py is installed)
+
+Keras appends ':0' to variable names inside HDF5 files and prefixes nested-model variables with the model name;
+`normalise_key` strips both so that converted files load unchanged."""
+import os
+
+import numpy as np
+import torch
+
+_H5 = (".h5", ".hdf5", ".keras")
+
+
+def normalise_key(key: str) -> str:
+    """'yolo_model/conv_dw_7/depthwise_kernel:0' -> 'conv_dw_7/depthwise_kernel'"""
+    key = key.split(":")[0]
+    parts = key.split("/")
+    return "/".join(parts[-2:]) if len(parts) > 2 else key
+
+
+def read_checkpoint(path) -> dict:
+    """-> {variable name: float32 CPU tensor}"""
+    p = str(path)
+    ext = os.path.splitext(p)[1].lower()
+    if ext in _H5:
+        raise ImportError("Keras HDF5 checkpoints need h5py, which this package does not depend on: convert the file once "
+                          "with scripts/h5_to_npz.py (same variable names) and load the .npz")
+    if ext == ".npz":
+        with np.load(p) as z:
+            raw = {k: torch.from_numpy(np.asarray(z[k])) for k in z.files}
+    elif ext == ".safetensors":
+        from safetensors.torch import load_file
+        raw = load_file(p, device="cpu")
+    else:
+        raw = torch.load(p, map_location="cpu")
+        if not isinstance(raw, dict):
+            raise TypeError("%s does not hold a {variable name: tensor} mapping" % p)
+    return {normalise_key(k): torch.as_tensor(v).to(torch.float32) for k, v in raw.items()}
+
+
+def write_checkpoint(path, state: dict) -> None:
+    p = str(path)
+    ext = os.path.splitext(p)[1].lower()
+    if ext in _H5:
+        raise ImportError("writing Keras HDF5 needs h5py; write .npz / .safetensors / .pt (same variable names)")
+    cpu = {k: torch.as_tensor(v).detach().to("cpu", torch.float32).contiguous() for k, v in state.items()}
+    if ext == ".npz":
+        with open(p, "wb") as f:                       # np.savez would append '.npz' to other names; keep the given path
+            np.savez(f, **{k: v.numpy() for k, v in cpu.items()})
+    elif ext == ".safetensors":
+        from safetensors.torch import save_file
+        save_file(cpu, p)
+    else:
+        torch.save(cpu, p)
+
+
+def select(state: dict, exclude=None) -> dict:
+    """`exclude`: layer names whose variables are dropped (model.py:1170-1180 filters layers by name)."""
+    if not exclude:
+        return dict(state)
+    ex = set(exclude)
+    return {k: v for k, v in state.items() if k.split("/")[0] not in ex}

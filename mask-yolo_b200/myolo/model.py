@@ -21,6 +21,7 @@ import numpy as np
 import torch
 
 from . import _cabi as C
+from . import checkpoint
 from . import myolo_utils as mutils
 from .config import Config, resolve
 from .engine import Engine, init_params, param_specs, MASK_C
@@ -251,7 +252,7 @@ class _ModelHandle(object):
         return self._o.engine.state_dict()
 
     def save_weights(self, path):
-        torch.save(self._o.engine.state_dict(), path)
+        checkpoint.write_checkpoint(path, self._o.engine.state_dict())
 
     def load_weights(self, path, by_name=False):
         self._o.load_weights(path, by_name=by_name)
@@ -390,17 +391,10 @@ class MaskYOLO:
         self.engine.set_trainable(lambda name: bool(rx.fullmatch(name.split("/")[0])))
 
     def load_weights(self, filepath, by_name=False, exclude=None):
-        """Load a checkpoint written by this package (torch.save of {keras variable name: tensor}, or an
-        .npz with the same keys).  by_name tolerates missing variables; `exclude` drops layers by name
-        (model.py:1157-1196 semantics; HDF5 needs h5py, which this build does not depend on)."""
-        if str(filepath).endswith(".npz"):
-            sd = {k: torch.from_numpy(v) for k, v in np.load(filepath).items()}
-        elif str(filepath).endswith((".h5", ".hdf5")):
-            raise ImportError("Keras HDF5 checkpoints need h5py; convert to .npz keyed by variable name")
-        else:
-            sd = torch.load(filepath, map_location="cpu")
-        if exclude:
-            sd = {k: v for k, v in sd.items() if k.split("/")[0] not in set(exclude)}
+        """Load a checkpoint keyed by the Keras variable names: torch.save dict (what train() writes), .npz or
+        .safetensors (myolo.checkpoint; a Keras .h5 is converted once with scripts/h5_to_npz.py).  by_name tolerates
+        missing variables; `exclude` drops layers by name (model.py:1157-1196 semantics)."""
+        sd = checkpoint.select(checkpoint.read_checkpoint(filepath), exclude)
         self.engine.load_params(sd, strict=not (by_name or exclude))
 
     def train(self, train_dataset, val_dataset, learning_rate, epochs, layers, augmentation=None, custom_callbacks=None,

@@ -182,8 +182,11 @@ class DeviceShapes(object):
         self.M = int(config.MAX_GT_INSTANCES)
         B, S, G, TB = self.B, c["S"], c["G"], c["TB"]
         dev = self.dev = torch.device("cuda", device)
-        self.spec_host = torch.empty(B, 4 + 8 * self.MS, dtype=torch.int32).pin_memory()
-        self.spec_dev = torch.empty_like(self.spec_host, device=dev)
+        # ring of pinned upload buffers: the async copy of call k may still be queued when call k+1 fills the next one
+        self.spec_ring = [torch.empty(B, 4 + 8 * self.MS, dtype=torch.int32).pin_memory() for _ in range(4)]
+        self.spec_done = [None] * len(self.spec_ring)
+        self.calls = 0
+        self.spec_dev = torch.empty_like(self.spec_ring[0], device=dev)
         self.ws = torch.empty(B * self.MS * (2 * S + 1), dtype=torch.int32, device=dev)
         self.images = torch.empty(B, S, S, 3, dtype=torch.float32, device=dev)
         self.masks = torch.empty(B, S, S, self.M, dtype=torch.uint8, device=dev)
@@ -200,9 +203,17 @@ class DeviceShapes(object):
         the un-normalised image."""
         from . import _cabi as C
         torch, c = self.torch, self.c
-        assert tuple(specs.shape) == tuple(self.spec_host.shape), (specs.shape, self.spec_host.shape)
-        self.spec_host.copy_(torch.from_numpy(np.ascontiguousarray(specs, dtype=np.int32)))
-        self.spec_dev.copy_(self.spec_host, non_blocking=True)
+        slot = self.calls % len(self.spec_ring)
+        self.calls += 1
+        host = self.spec_ring[slot]
+        assert tuple(specs.shape) == tuple(host.shape), (specs.shape, host.shape)
+        if self.spec_done[slot] is not None:
+            self.spec_done[slot].synchronize()            # the upload that last used this pinned buffer has left it
+        host.copy_(torch.from_numpy(np.ascontiguousarray(specs, dtype=np.int32)))
+        self.spec_dev.copy_(host, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.dev))
+        self.spec_done[slot] = ev
         st = torch.cuda.current_stream(self.dev).cuda_stream
         C.call("myolo_shapes_raster", self.spec_dev, self.B, c["S"], self.MS, self.M, c["TB"], self.ws, self.images,
                image_u8, self.masks, self.ids, self.boxes, self.boxes_f, st)

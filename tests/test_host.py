@@ -117,3 +117,36 @@ def test_mrcnn_shim_and_reference_example_imports():
     finally:
         sys.path.remove(ex)
         sys.modules.pop("dataset_shapes", None)
+
+
+def test_checkpoint_containers_round_trip_by_variable_name(tmp_path):
+    """.pt / .npz / .safetensors hold the same {Keras variable name: array} mapping; HDF5-style names
+    (':0' suffix, nested-model prefix) are normalised; `exclude` drops whole layers; .h5 is refused with instructions."""
+    import torch
+    from myolo import checkpoint as ck
+    from myolo.engine import param_specs
+    specs = param_specs(3, 4)
+    rs = np.random.RandomState(0)
+    sd = {name: torch.from_numpy(rs.standard_normal(shape).astype(np.float32)) for name, shape, _ in specs[:12]}
+    for ext in (".pt", ".npz", ".safetensors"):
+        path = str(tmp_path / ("w" + ext))
+        ck.write_checkpoint(path, sd)
+        assert os.path.exists(path) and not os.path.exists(path + ".npz")
+        back = ck.read_checkpoint(path)
+        assert list(back) == list(sd) or set(back) == set(sd)
+        assert all(torch.equal(back[k], sd[k]) and back[k].dtype == torch.float32 for k in sd)
+    keras_style = {("yolo_model/" if i % 2 else "") + k + ":0": v.double() for i, (k, v) in enumerate(sd.items())}
+    path = str(tmp_path / "keras_names.npz")
+    with open(path, "wb") as f:
+        np.savez(f, **{k: v.numpy() for k, v in keras_style.items()})
+    back = ck.read_checkpoint(path)
+    assert set(back) == set(sd) and all(torch.equal(back[k], sd[k]) for k in sd)
+    assert ck.normalise_key("yolo_model/conv_dw_7/depthwise_kernel:0") == "conv_dw_7/depthwise_kernel"
+    assert ck.normalise_key("conv1/kernel") == "conv1/kernel"
+    kept = ck.select(sd, exclude=["conv1_bn"])
+    assert not any(k.startswith("conv1_bn/") for k in kept) and len(kept) == len(sd) - 4 and "conv1/kernel" in kept
+    for bad in ("weights.h5", "weights.hdf5"):
+        with pytest.raises(ImportError, match="h5_to_npz"):
+            ck.read_checkpoint(str(tmp_path / bad))
+    with pytest.raises(ImportError):
+        ck.write_checkpoint(str(tmp_path / "out.h5"), sd)
