@@ -37,6 +37,7 @@ def parse():
     ap.add_argument("--precision", default=os.environ.get("MYOLO_PRECISION", "h16"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     return ap.parse_args()
 
 
@@ -268,6 +269,15 @@ def main():
         dt = time.perf_counter() - t0
         cpu = {"value": 2 * n / dt, "unit": "images/sec", "cores": cores, "kind": "port",
                "sample": f"{n} oracle.train_step calls (fwd+bwd+Adam, torch CPU fp32) on 2 images of the same {args.size}x{args.size} Shapes batch"}
+    parity = None
+    if rank == 0 and not args.no_parity:
+        # BASELINE.json's metric carries "box+mask IoU vs ref": one small step of the same engine / precision against the
+        # CPU restatement of the reference path, outside the timed region (the oracle is the checker, never the thing timed)
+        try:
+            import __graft_entry__ as entry
+            parity = entry.parity_metrics(args.precision)
+        except Exception as e:                      # never lose the throughput line to the side check
+            parity = {"error": repr(e)[:200]}
     if rank == 0:
         fl = cpu_flops_per_image(c)
         line = {"metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": K, "warmup": W,
@@ -280,6 +290,7 @@ def main():
                            "l2": "activations per step (>10 GB) exceed the 126 MB L2; no explicit flush",
                            "weights": "random trained-like init (no checkpoints offline)"},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+                "parity": parity,
                 "model_tflops_per_s": value * fl / 1e12, "frac_of_conv_roofline": value * fl / 1e12 / pk["bf16_tflops_sustained"],
                 "loss": [float(out["yolo_sum_loss"]), float(out["mask_loss"])]}
         print(json.dumps(line))

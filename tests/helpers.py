@@ -80,3 +80,23 @@ def to_oracle_inputs(inputs):
 
 def to_device(inputs, dev="cuda"):
     return [t.contiguous().to(dev) for t in inputs]
+
+
+def box_iou_pairs(a, b):
+    """Element-wise IoU of two box tensors [..., 4] (x1, y1, x2, y2); two empty boxes count as identical (1)."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    iw = (torch.minimum(a[..., 2], b[..., 2]) - torch.maximum(a[..., 0], b[..., 0])).clamp(min=0)
+    ih = (torch.minimum(a[..., 3], b[..., 3]) - torch.maximum(a[..., 1], b[..., 1])).clamp(min=0)
+    inter = iw * ih
+    area = lambda t: (t[..., 2] - t[..., 0]).clamp(min=0) * (t[..., 3] - t[..., 1]).clamp(min=0)   # noqa: E731
+    union = area(a) + area(b) - inter
+    return torch.where(union > 0, inter / union.clamp(min=1e-300), torch.ones_like(union))
+
+
+def mask_iou(a, b, thr=0.5):
+    """IoU of the masks binarised at `thr`, per (roi, class): inputs [..., H, W, NC] -> [..., NC]; two empty masks
+    count as identical (1)."""
+    a, b = a.detach().cpu() >= thr, b.detach().cpu() >= thr
+    inter = (a & b).sum(dim=(-3, -2)).double()
+    union = (a | b).sum(dim=(-3, -2)).double()
+    return torch.where(union > 0, inter / union.clamp(min=1), torch.ones_like(union))

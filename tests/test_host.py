@@ -150,3 +150,18 @@ def test_checkpoint_containers_round_trip_by_variable_name(tmp_path):
             ck.read_checkpoint(str(tmp_path / bad))
     with pytest.raises(ImportError):
         ck.write_checkpoint(str(tmp_path / "out.h5"), sd)
+
+
+def test_iou_parity_helpers():
+    import torch
+    from tests import helpers as Hh
+    a = torch.tensor([[0.0, 0.0, 2.0, 2.0], [0.0, 0.0, 0.0, 0.0], [1.0, 1.0, 3.0, 3.0]])
+    b = torch.tensor([[1.0, 0.0, 3.0, 2.0], [0.0, 0.0, 0.0, 0.0], [1.0, 1.0, 3.0, 3.0]])
+    assert torch.allclose(Hh.box_iou_pairs(a, b), torch.tensor([1.0 / 3.0, 1.0, 1.0], dtype=torch.float64))
+    m = torch.zeros(2, 4, 4, 3)
+    m[0, :2, :, 0] = 0.9                                   # 8 pixels on
+    n = m.clone()
+    n[0, 2, :, 0] = 0.6                                    # 12 pixels on -> IoU 8/12
+    n[1, 0, 0, 2] = 0.49                                   # below the threshold: still empty
+    iou = Hh.mask_iou(m, n)
+    assert iou.shape == (2, 3) and abs(iou[0, 0].item() - 8.0 / 12.0) < 1e-12 and iou[1, 2].item() == 1.0 and iou[0, 1].item() == 1.0

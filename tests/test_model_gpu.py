@@ -102,6 +102,13 @@ def test_train_step_matches_oracle(precision):
     tol_out = {"fp32": 2e-4, "tf32x3": 1e-3, "tf32x3_all": 1e-3, "h16": 1e-3, "tf32": 0.5}[precision]
     errs = {k: _abs(out_e[k], out64[k].float()) for k in ("yolo_proposals", "yolo_output", "output_rois", "myolo_mask")}
     print(f"[{precision}] max abs output errors vs fp64 oracle: {errs}")
+    # BASELINE.json's parity figure: box and mask IoU against the reference path (here the fp64 oracle)
+    biou = Hh.box_iou_pairs(out_e["yolo_proposals"], out64["yolo_proposals"])
+    miou = Hh.mask_iou(out_e["myolo_mask"], out64["myolo_mask"])
+    print(f"[{precision}] box IoU vs oracle mean {biou.mean().item():.6f} min {biou.min().item():.6f}; "
+          f"mask IoU mean {miou.mean().item():.6f} min {miou.min().item():.6f}")
+    if precision != "tf32":
+        assert biou.mean().item() >= 0.999 and miou.mean().item() >= 0.999, (biou.mean().item(), miou.mean().item())
     same_sel = torch.equal(out_e["target_class_ids"].cpu(), out64["target_class_ids"])
     assert same_sel, "ROI selection / class ids must match the oracle (bit-exact index work)"
     # mask targets are rounded bilinear samples: bit-exact given identical proposals (kernel test);
