@@ -224,6 +224,37 @@ def main():
             out[f"shp{tag}_{i}_image_colsum"] = img.astype(np.int64).sum(axis=(0, 2))
             out[f"shp{tag}_{i}_boxes"] = ref.extract_bboxes(mask)
 
+    # ---- load_image_gt (274-366) and data_generator (457-686) of the reference's myolo_utils on its own ShapesDataset
+    refu = sys.modules["myolo.myolo_utils"]
+    assert refu.__file__.startswith("/root/reference")
+
+    class GenConfig(shp.ShapesConfig):
+        IMAGE_SHAPE = [128, 128, 3]
+        GRID_H = GRID_W = 4
+        N_BOX = 3
+        TRUE_BOX_BUFFER = 10
+        MAX_GT_INSTANCES = 10
+
+    gcfg = GenConfig()
+    random.seed(99)
+    ds = shp.ShapesDataset()
+    ds.load_shapes(5, 128, 128)
+    ds.prepare()
+    for i in ds.image_ids:
+        image, class_ids, bbox, mask = refu.load_image_gt(ds, gcfg, i, use_mini_mask=False)
+        out[f"lig_{i}_image_rowsum"] = image.astype(np.int64).sum(axis=(1, 2))
+        out[f"lig_{i}_class_ids"], out[f"lig_{i}_bbox"] = class_ids, bbox
+        out[f"lig_{i}_mask_bits"], out[f"lig_{i}_mask_shape"] = np.packbits(mask.astype(np.uint8)), np.array(mask.shape, dtype=np.int64)
+    gen = refu.data_generator(ds, gcfg, shuffle=False, batch_size=2, norm=True)
+    for b in range(3):                                   # 3 batches of 2 over 5 images: the third wraps around
+        (images, true_boxes, yolo_target), outputs = next(gen)
+        assert outputs == []
+        out[f"dg_batch{b}_images_sum"] = images.astype(np.float64).sum(axis=(1, 2, 3))
+        out[f"dg_batch{b}_images_row"] = images[:, 31]
+        out[f"dg_batch{b}_images_meta"] = np.array(images.shape + (images.dtype.itemsize,), dtype=np.int64)
+        out[f"dg_batch{b}_true_boxes"], out[f"dg_batch{b}_yolo_target"] = true_boxes, yolo_target
+    gen.close()
+
     # ---- Config (myolo/config.py) and ShapesConfig (dataset_shapes.py:14-50): every public class attribute and the
     # attributes __init__ derives
     import json

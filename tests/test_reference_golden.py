@@ -164,3 +164,39 @@ def test_config_attributes_match_reference(gold):
     for k in set(ref_s["__instance__"]) | set(mine_s["__instance__"]):
         if k not in repaired:
             assert mine_s["__instance__"].get(k) == ref_s["__instance__"].get(k), k
+
+
+def test_load_image_gt_and_data_generator_match_reference(gold):
+    """load_image_gt (myolo_utils.py:274-366) and the older python generator data_generator (457-686) on the Shapes
+    dataset, against the reference's own functions run on its own ShapesDataset with the same seed."""
+    from myolo.shapes import ShapesDataset
+
+    class GenConfig(ShapesConfig):
+        IMAGE_SHAPE = [128, 128, 3]
+        GRID_H = GRID_W = 4
+        N_BOX = 3
+        TRUE_BOX_BUFFER = 10
+        MAX_GT_INSTANCES = 10
+
+    cfg = GenConfig()
+    ds = ShapesDataset(seed=99)
+    ds.load_shapes(5, 128, 128)
+    ds.prepare()
+    for i in ds.image_ids:
+        image, class_ids, bbox, mask = mutils.load_image_gt(ds, cfg, i, use_mini_mask=False)
+        assert image.dtype == np.uint8 and np.array_equal(image.astype(np.int64).sum(axis=(1, 2)), gold[f"lig_{i}_image_rowsum"])
+        assert np.array_equal(class_ids, gold[f"lig_{i}_class_ids"]) and class_ids.dtype == gold[f"lig_{i}_class_ids"].dtype
+        assert np.array_equal(bbox, gold[f"lig_{i}_bbox"]) and bbox.dtype == gold[f"lig_{i}_bbox"].dtype
+        assert list(mask.shape) == gold[f"lig_{i}_mask_shape"].tolist()
+        assert np.array_equal(np.packbits(mask.astype(np.uint8)), gold[f"lig_{i}_mask_bits"])
+    gen = mutils.data_generator(ds, cfg, shuffle=False, batch_size=2, norm=True)
+    for b in range(3):
+        (images, true_boxes, yolo_target), outputs = next(gen)
+        assert outputs == []
+        assert list(images.shape) + [images.dtype.itemsize] == gold[f"dg_batch{b}_images_meta"].tolist()
+        assert np.array_equal(images.astype(np.float64).sum(axis=(1, 2, 3)), gold[f"dg_batch{b}_images_sum"])
+        assert np.array_equal(images[:, 31], gold[f"dg_batch{b}_images_row"])
+        for name, arr in (("true_boxes", true_boxes), ("yolo_target", yolo_target)):
+            ref = gold[f"dg_batch{b}_{name}"]
+            assert arr.shape == ref.shape and arr.dtype == ref.dtype and np.array_equal(arr, ref), (b, name)
+    gen.close()
