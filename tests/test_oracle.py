@@ -172,3 +172,24 @@ def test_fp64_fp32_self_consistency():
         b = O.forward_inference({k: v.double() for k, v in P.items()}, img.double(), oc)
     assert (a["detections"][..., :5] - b["detections"][..., :5].float()).abs().max() < 2e-4
     assert (a["yolo_output"] - b["yolo_output"].float()).abs().max() < 5e-4
+
+
+def test_crop_and_resize_equals_align_corners_bilinear_sampling_inside_the_image():
+    """Independent cross-check of the restated TF primitive: for samples that fall inside the image,
+    tf.image.crop_and_resize is plain bilinear sampling on the corner-aligned grid, which PyTorch implements separately as
+    grid_sample(align_corners=True).  (Outside the image the two differ by design: TF writes the extrapolation value for
+    the whole sample, grid_sample blends with zero padding -- those samples are covered by the hand-computed cases.)"""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(5)
+    B, H, W, C, N, ch, cw = 2, 9, 13, 3, 12, 7, 5
+    img = torch.randn(B, H, W, C, generator=g, dtype=torch.float64)
+    y1x1 = torch.rand(N, 2, generator=g, dtype=torch.float64) * 0.5
+    hw = torch.rand(N, 2, generator=g, dtype=torch.float64) * 0.5          # boxes stay inside [0, 1]
+    boxes = torch.cat([y1x1, y1x1 + hw], 1)                                # (y1, x1, y2, x2)
+    idx = torch.arange(N) % B
+    got = O.crop_and_resize(img, boxes, idx, ch, cw)
+    ys = boxes[:, 0:1] + (boxes[:, 2:3] - boxes[:, 0:1]) * torch.linspace(0, 1, ch, dtype=torch.float64)[None]     # [N, ch] in [0,1]
+    xs = boxes[:, 1:2] + (boxes[:, 3:4] - boxes[:, 1:2]) * torch.linspace(0, 1, cw, dtype=torch.float64)[None]
+    grid = torch.stack([(2 * xs - 1)[:, None, :].expand(N, ch, cw), (2 * ys - 1)[:, :, None].expand(N, ch, cw)], -1)
+    ref = F.grid_sample(img[idx].permute(0, 3, 1, 2), grid, mode="bilinear", padding_mode="zeros", align_corners=True)
+    assert torch.allclose(got, ref.permute(0, 2, 3, 1), atol=1e-12)
