@@ -354,6 +354,18 @@ int myolo_shapes_raster(const int* specs, int B, int S, int MS, int M, int TB, i
                         unsigned char* image_u8, unsigned char* gt_masks, int* gt_class_ids, int* gt_boxes,
                         float* gt_boxes_f, myolo_stream stream);
 
+/* ---- the data-parallel exchange step: ONE sum all-reduce of the flat fp32 gradient buffer per step, issued
+ * as two slices (mask-head tail first, overlapping the backbone backward).  The reference has no distributed code; this
+ * is the NCCL communicator behind the C ABI (bound at run time to the libnccl.so.2 PyTorch ships and has loaded).
+ * unique_id: rank 0 fills 128 bytes and hands them to every rank (any side channel, e.g. a torch.distributed broadcast);
+ * init: collective over all ranks, uses the calling thread's current CUDA device, returns the handle in *comm_out;
+ * run: in-place sum over ranks of buf[0..n) on `stream` (asynchronous, like every other entry point);
+ * destroy: releases the communicator. */
+int myolo_allreduce_unique_id(char* id128);
+int myolo_allreduce_init(const char* id128, int rank, int world, void** comm_out);
+int myolo_allreduce_run(void* comm, float* buf, long long n, myolo_stream stream);
+int myolo_allreduce_destroy(void* comm);
+
 /* ---- K17: Keras Adam, myolo/model.py:1071-1075 ----  lr_t = lr*sqrt(1-b2^t)/(1-b1^t) computed by caller */
 int myolo_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr_t,
                     float b1, float b2, float eps, float grad_scale, myolo_stream stream);

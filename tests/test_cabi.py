@@ -54,3 +54,20 @@ def test_product_code_never_imports_the_oracle():
                 n += 1
                 assert not pat.search(open(os.path.join(dp, f), errors="ignore").read()), os.path.join(dp, f)
     assert n >= 8
+
+
+def test_allreduce_entry_points_bind_nccl_at_run_time():
+    """myolo_allreduce_* resolve NCCL with dlsym from the library PyTorch ships; ncclGetUniqueId needs no GPU, so the
+    binding itself is checked here (communicator creation and the all-reduce are -m gpu)."""
+    import ctypes
+    from myolo import _cabi as C
+    from myolo import ddp
+    path = ddp.load_nccl_global()
+    assert "nccl" in path
+    a, b = ctypes.create_string_buffer(128), ctypes.create_string_buffer(128)
+    assert C.call("myolo_allreduce_unique_id", a) == 0 and C.call("myolo_allreduce_unique_id", b) == 0
+    assert any(a.raw) and a.raw != b.raw                    # 128 opaque bytes, different per call
+    with pytest.raises(C.MyoloError):
+        C.call("myolo_allreduce_run", None, None, 0, 0)     # argument checks come before any NCCL call
+    with pytest.raises(C.MyoloError):
+        C.call("myolo_allreduce_init", a, 3, 2, ctypes.addressof(ctypes.c_void_p()))
