@@ -146,7 +146,12 @@ def run_reference(args):
     print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "images/sec", "n_gpus": args.gpus,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
                       "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                      "config": {"workload": f"Shapes {args.size}x{args.size}, fwd+bwd+Adam, host CPU", "per_step_images": nimg},
+                      "config": {"workload": f"Shapes {args.size}x{args.size} batch {args.batch}/GPU, MobileNet+YOLO+ROIAlign+mask fwd+bwd+Adam",
+                                 "global_batch": args.batch * args.gpus, "N_BOX": c["NB"], "NUM_CLASSES": c["NC"],
+                                 "rois_per_image": c["R"], "precision": "fp32 (torch CPU)", "parallelism": "host CPU threads",
+                                 "sample_images_per_step": nimg,
+                                 "note": "the same workload as the GPU arm; each step is a bounded sample of it (per-image work "
+                                         "is independent except for BatchNorm statistics)"},
                       "cpu_baseline": {"value": v, "unit": "images/sec", "cores": cores, "kind": "port", "sample": sample},
                       "e2e": {"value": v, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
