@@ -12,6 +12,7 @@ There is no CPU path: constructing a model without an sm_100 GPU raises.
 from __future__ import annotations
 
 import datetime
+import math
 import os
 import re
 import time
@@ -51,7 +52,7 @@ def norm_boxes_graph(boxes, shape):
     return (boxes - shift) / scale
 
 
-def trim_zeros_graph(boxes, name=None):
+def trim_zeros_graph(boxes, name='trim_zeros'):
     """Drop all-zero rows; returns (boxes, keep mask)  (model.py:1411-1420)."""
     keep = boxes.abs().sum(1) != 0
     return boxes[keep], keep
@@ -75,8 +76,8 @@ class _Layer(object):
 class DecodeYOLOLayer(_Layer):
     """yolo_output [B,G,G,NB,5+NC] -> proposals [B, G*G*NB, (x1,y1,x2,y2)] normalised  (model.py:1429-1476)."""
 
-    def __init__(self, name=None, config=None, **kwargs):
-        self.name, self.cfg = name, resolve(config)
+    def __init__(self, config, **kwargs):
+        self.name, self.config, self.cfg = kwargs.get("name"), config, resolve(config)
 
     def call(self, inputs):
         y = _f32(inputs[0] if isinstance(inputs, (list, tuple)) else inputs)
@@ -93,8 +94,8 @@ class DecodeYOLOLayer(_Layer):
 class DetectionsLayer(_Layer):
     """yolo_output -> [B, R, (x1,y1,x2,y2, sigmoid(conf), argmax class)]  (model.py:1479-1541)."""
 
-    def __init__(self, name=None, config=None, **kwargs):
-        self.name, self.cfg = name, resolve(config)
+    def __init__(self, config, **kwargs):
+        self.name, self.config, self.cfg = kwargs.get("name"), config, resolve(config)
 
     def call(self, inputs):
         y = _f32(inputs[0] if isinstance(inputs, (list, tuple)) else inputs)
@@ -114,6 +115,7 @@ class PyramidROIAlign(_Layer):
     as (y1,x1,y2,x2) -- the reference's behaviour.  Returns [B,R,P,P,C]."""
 
     def __init__(self, pool_shape, **kwargs):
+        self.name = kwargs.get("name")
         self.pool_shape = tuple(pool_shape)
         assert self.pool_shape[0] == self.pool_shape[1]
 
@@ -137,7 +139,14 @@ class DetectMaskTargetLayer(_Layer):
     them: norm_boxes_graph (model.py:819-820) is fused into the kernel."""
 
     def __init__(self, config, **kwargs):
-        self.config, self.cfg = config, resolve(config)
+        self.name, self.config, self.cfg = kwargs.get("name"), config, resolve(config)
+
+    def compute_output_shape(self, input_shape):
+        return [(None, input_shape[0][1], 4), (None, input_shape[0][1]), (None, None),
+                (None, input_shape[0][1], self.cfg["MASK_SHAPE"][0], self.cfg["MASK_SHAPE"][1])]
+
+    def compute_mask(self, inputs, mask=None):
+        return [None, None, None, None]
 
     def call(self, inputs):
         props, ids, boxes, masks = inputs
@@ -156,9 +165,14 @@ class DetectMaskTargetLayer(_Layer):
         return [rois, tids, None, tmask]
 
 
-def detect_mask_target_graph(proposals, gt_class_ids, gt_boxes, gt_masks, config):
+def log2_graph(x):
+    """model.py:299-301"""
+    return torch.log(x) / math.log(2.0)
+
+
+def detect_mask_target_graph(yolo_proposals, gt_class_ids, gt_boxes, gt_masks, config):
     """One image (model.py:457-602): thin wrapper over the batched kernel."""
-    r = DetectMaskTargetLayer(config).call([proposals[None], gt_class_ids[None], gt_boxes[None], gt_masks[None]])
+    r = DetectMaskTargetLayer(config).call([yolo_proposals[None], gt_class_ids[None], gt_boxes[None], gt_masks[None]])
     return r[0][0], r[1][0], None, r[3][0]
 
 
@@ -188,21 +202,47 @@ def myolo_mask_loss_graph(target_masks, target_class_ids, pred_masks):
     return out[0]
 
 
-def conv_block(engine, inputs):
-    """model.py:42-52 on the engine's parameters: first conv + BN + ReLU6 (inference-mode BN)."""
-    engine.forward(inputs, training=False)
-    return engine.A["a0"]
+# The reference's graph builders add layers to Keras' implicit default graph.  Here the weights live in an Engine, and the
+# "implicit graph" is the engine of the most recently built MaskYOLO (or the one passed as `engine=`): the builders keep the
+# reference's positional signatures and run the corresponding part of that engine on device tensors.
+_CURRENT = {"engine": None}
 
 
-def mobilenet_graph(engine, input_image, training=False):
+def _engine(engine=None):
+    e = engine if engine is not None else _CURRENT["engine"]
+    if e is None:
+        raise RuntimeError("no engine: build a MaskYOLO first (its weights are what these graph functions run on) or pass engine=")
+    return e
+
+
+def conv_block(inputs, filters, alpha=1.0, kernel=(3, 3), strides=(1, 1), *, engine=None):
+    """model.py:42-52: ZeroPad + 3x3 conv + BN + ReLU6 (inference-mode BN).  The engine holds exactly the stem the
+    reference builds with it (32 filters, stride 2, model.py:66); other arguments are refused."""
+    if int(filters * alpha) != 32 or tuple(kernel) != (3, 3) or tuple(strides) != (2, 2):
+        raise NotImplementedError("the engine's stem is conv_block(x, 32, strides=(2, 2)) as in mobilenet_graph (model.py:66)")
+    e = _engine(engine)
+    e.forward(inputs, training=False)
+    return e.A["a0"]
+
+
+def mobilenet_graph(input_image, architecture, stage5=False, alpha=1.0, depth_multiplier=1, *, engine=None, training=False):
     """Truncated MobileNet-v1 backbone -> C4 [B,S/8,S/8,512]  (model.py:55-79)."""
-    engine.forward(input_image, training=training)
-    return engine.c4.dense() if engine.with_mask and not engine.x3 else engine.A["ap6"]
+    assert architecture == 'mobilenet'
+    e = _engine(engine)
+    e.forward(input_image, training=training)
+    return e.c4.dense() if e.with_mask and not e.x3 else e.A["ap6"]
 
 
-def yolo_branch_graph(engine, input_image, training=False):
-    """Backbone + YOLO branch -> [B,G,G,NB,5+NC]  (model.py:249-278)."""
-    return engine.forward(input_image, training=training)
+def yolo_branch_graph(x, config=None, alpha=1.0, depth_multiplier=1, *, engine=None, training=False):
+    """YOLO branch -> [B,G,G,NB,5+NC]  (model.py:249-278).  `x` is either the image (the whole backbone + branch pass is
+    run) or the C4 tensor mobilenet_graph just returned for this engine (the branch output of that same pass is returned:
+    the engine evaluates backbone and branch together)."""
+    e = _engine(engine)
+    if x.shape[-1] == 3:
+        return e.forward(x, training=training)
+    if x.shape[-1] != 512 or "yolo" not in e.A:
+        raise ValueError("x must be the image or the C4 feature map of the engine's last mobilenet_graph pass")
+    return e.A["yolo"].view(e.B, e.cfg["G"], e.cfg["G"], e.NB, 5 + e.NC)
 
 
 def build_yolo_model(config, depth=None, batch=None):
@@ -210,10 +250,16 @@ def build_yolo_model(config, depth=None, batch=None):
     return Engine(resolve(config), batch or config.BATCH_SIZE, "yolo")
 
 
-def build_mask_graph(engine, rois, training=False):
-    """Mask head on [B,R,4] rois -> [B,R,28,28,NC] sigmoid masks  (model.py:668-715).  Uses the
-    feature map left in the engine by the preceding backbone pass."""
-    return engine.mask_head(_f32(rois), training)
+def build_mask_graph(rois, feature_maps=None, pool_size=None, num_classes=None, train_bn=False, *, engine=None, training=False):
+    """Mask head on [B,R,4] rois -> [B,R,28,28,NC] sigmoid masks  (model.py:668-715).  The feature map is the one the
+    engine's preceding backbone pass left behind (`feature_maps` is accepted for signature parity); bn2-4 always use
+    their moving statistics, as in the reference, whatever `train_bn` says at HEAD (it is passed as training=False)."""
+    e = _engine(engine)
+    if pool_size is not None and int(pool_size) != int(e.cfg["POOL"]):
+        raise ValueError("pool_size %r differs from the engine's MASK_POOL_SIZE %r" % (pool_size, e.cfg["POOL"]))
+    if num_classes is not None and int(num_classes) != int(e.NC):
+        raise ValueError("num_classes %r differs from the engine's %r" % (num_classes, e.NC))
+    return e.mask_head(_f32(rois), training)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -289,6 +335,7 @@ class MaskYOLO:
         self.cfg = resolve(config)
         batch = int(config.BATCH_SIZE) if mode != "inference" else int(getattr(config, "BATCH_SIZE", 1))
         self.engine = Engine(self.cfg, batch, mode, self.precision, self.device, seed=self.seed)
+        _CURRENT["engine"] = self.engine                  # what the module-level graph functions run on by default
         self._stage_bufs = None
         if self.yolo_pretrain_dir is not None:
             self.load_weights(self.yolo_pretrain_dir, by_name=True)

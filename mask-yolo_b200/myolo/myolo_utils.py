@@ -8,6 +8,7 @@ into the engine's pinned staging buffers (myolo/model.py).
 from __future__ import annotations
 
 import logging
+import math
 import random
 
 import numpy as np
@@ -261,10 +262,13 @@ class BatchGenerator(object):
             np.random.shuffle(self.all_info)
 
 
-def data_generator(dataset, config, shuffle=True, augment=False, augmentation=None, batch_size=1, norm=True):
+def data_generator(dataset, config, shuffle=True, augment=False, augmentation=None, batch_size=1,
+                   no_augmentation_sources=None, norm=False):
     """The older python-generator variant (myolo_utils.py:457-686): loads images on the fly and yields
     ([images, true_boxes, yolo_target], []) -- the three YOLO inputs only.  A failing image is logged
-    and skipped; the fifth failure is re-raised."""
+    and skipped; the fifth failure is re-raised.  `no_augmentation_sources` (dataset sources that are never
+    augmented) is accepted for signature parity; imgaug augmentation is not available in this build.  As in
+    the reference, norm=False hands the uint8 image values over unscaled."""
     anchors = [BoundBox(0, 0, config.ANCHORS[2 * i], config.ANCHORS[2 * i + 1]) for i in range(_n_box(config))]
     image_ids = np.copy(dataset.image_ids)
     H, W = int(config.IMAGE_SHAPE[0]), int(config.IMAGE_SHAPE[1])
@@ -415,3 +419,59 @@ def unmold_mask(mask, bbox, image_shape):
     m = resize(mask, (y2 - y1, x2 - x1)) >= 0.5
     full[y1c:y2c, x1c:x2c] = m[y1c - y1:y2c - y1, x1c - x1:x2c - x1]
     return full
+
+
+# --------------------------------------------------------------------------- small helpers the reference also exports
+def box_refinement_graph(box, gt_box):
+    """Refinement (dy, dx, log dh, log dw) that maps `box` onto `gt_box` (myolo_utils.py:116-139); the reference's
+    coordinate naming is kept: columns 0/2 span the "width", 1/3 the "height".  Works on torch tensors [N, 4]."""
+    import torch
+    box, gt_box = box.to(torch.float32), gt_box.to(torch.float32)
+    width, height = box[:, 2] - box[:, 0], box[:, 3] - box[:, 1]
+    center_x, center_y = box[:, 0] + 0.5 * width, box[:, 1] + 0.5 * height
+    gt_width, gt_height = gt_box[:, 2] - gt_box[:, 0], gt_box[:, 3] - gt_box[:, 1]
+    gt_center_x, gt_center_y = gt_box[:, 0] + 0.5 * gt_width, gt_box[:, 1] + 0.5 * gt_height
+    return torch.stack([(gt_center_y - center_y) / height, (gt_center_x - center_x) / width,
+                        torch.log(gt_height / height), torch.log(gt_width / width)], dim=1)
+
+
+def compute_backbone_shapes(config, image_shape):
+    """[height, width] of the backbone's feature map (myolo_utils.py:142-150).  The reference divides by the LIST
+    config.BACKBONE_STRIDES (a TypeError at HEAD); the single stride it holds is used here."""
+    assert config.BACKBONE in ["mobilenet"]
+    stride = config.BACKBONE_STRIDES[0] if isinstance(config.BACKBONE_STRIDES, (list, tuple)) else config.BACKBONE_STRIDES
+    return np.array([int(math.ceil(image_shape[0] / stride)), int(math.ceil(image_shape[1] / stride))])
+
+
+def mold_image(images, config):
+    """RGB image(s) -> float32 minus config.MEAN_PIXEL (myolo_utils.py:153-158; the base Config defines no MEAN_PIXEL,
+    so -- exactly as in the reference -- the caller's config has to)."""
+    return images.astype(np.float32) - config.MEAN_PIXEL
+
+
+def draw_boxes(image, boxes, labels):
+    """Draw BoundBox rectangles and 'label score' captions into `image` in place (myolo_utils.py:863-880)."""
+    if cv2 is None:
+        raise ImportError("draw_boxes needs cv2")
+    image_h, image_w, _ = image.shape
+    for box in boxes:
+        xmin, ymin = int(box.xmin * image_w), int(box.ymin * image_h)
+        xmax, ymax = int(box.xmax * image_w), int(box.ymax * image_h)
+        cv2.rectangle(image, (xmin, ymin), (xmax, ymax), (0, 255, 0), 1)
+        cv2.putText(image, labels[box.get_label()] + ' ' + str(box.get_score()), (xmin, ymax - 13),
+                    cv2.FONT_HERSHEY_SIMPLEX, 1.5e-3 * image_h, (0, 255, 0), 1)
+    return image
+
+
+def resize_one_image(image, gt_box, gt_mask, new_shape):
+    """myolo_utils.py:915-925, kept as it is at HEAD: rescales and clips `gt_box` IN PLACE (index 2 is computed from
+    gt_box[1], as in the reference) and returns None; the resized image is discarded."""
+    if cv2 is None:
+        raise ImportError("resize_one_image needs cv2")
+    original_w, original_h = image.shape[0], image.shape[1]
+    new_w, new_h = new_shape[0], new_shape[1]
+    cv2.resize(image, (new_w, new_h))
+    gt_box[0], gt_box[2] = int(gt_box[0] * float(new_w) / original_w), int(gt_box[1] * float(new_w) / original_w)
+    gt_box[1], gt_box[3] = int(gt_box[1] * float(new_h) / original_h), int(gt_box[3] * float(new_h) / original_h)
+    gt_box[0], gt_box[2] = max(min(gt_box[0], new_w), 0), max(min(gt_box[2], new_w), 0)
+    gt_box[1], gt_box[3] = max(min(gt_box[1], new_h), 0), max(min(gt_box[3], new_h), 0)

@@ -78,7 +78,7 @@ def test_shapes_dataset_and_data_generator():
     class C128(ShapesConfig):
         IMAGE_SHAPE = [128, 128, 3]
         GRID_H = GRID_W = 4
-    g = mutils.data_generator(ds, C128(), shuffle=False, batch_size=2)
+    g = mutils.data_generator(ds, C128(), shuffle=False, batch_size=2, norm=True)
     (images, tb, yt), _ = next(g)
     assert images.shape == (2, 128, 128, 3) and yt.shape == (2, 4, 4, 3, 9) and yt[..., 4].sum() >= 2
     b = make_batches(C128(), 1, seed=5)

@@ -147,6 +147,22 @@ def test_oracle_whole_model_equals_reference_build(gold):
     close(inf["myolo_mask"].numpy()[:, ::2, ::3, ::3], g("myolo_mask"), 5e-6, "inference myolo_mask")
 
 
+@pytest.mark.parametrize("name", list(GI.CASES))
+def test_package_tensor_helpers_equal_reference_source(gold, name):
+    """The package's own norm_boxes_graph / trim_zeros_graph / overlaps_graph (plain tensor functions of myolo.model,
+    usable on any device) against the reference-source vectors."""
+    from myolo import model as M
+    c = GI.build(name)
+    g = lambda k: gold[name + "/" + k]                                             # noqa: E731
+    S = c["S"]
+    gt_norm = M.norm_boxes_graph(_t(c["gt_boxes_px"]), (S, S))
+    assert np.allclose(gt_norm.numpy(), g("gt_boxes_norm"), rtol=0, atol=1e-7)
+    boxes, keep = M.trim_zeros_graph(gt_norm[0])
+    assert np.array_equal(keep.numpy(), g("trim_nonzero_0")) and boxes.shape[0] == int(g("trim_nonzero_0").sum())
+    ov = M.overlaps_graph(_t(g("proposals")[0]), _t(g("gt_boxes_norm")[0][g("trim_nonzero_0")]))
+    assert np.allclose(ov.numpy(), g("overlaps_0"), rtol=0, atol=2e-6, equal_nan=True)
+
+
 def test_shim_crop_and_resize_micro_cases():
     """The one non-trivial primitive the stand-in supplies, against hand-computed values (tf.image.crop_and_resize:
     corners map to [0, size-1], samples outside take the extrapolation value 0, crop size 1 samples the box centre)."""
@@ -218,3 +234,49 @@ def test_device_kernels_equal_reference_source(gold, name):
     C.call("myolo_mask_loss", _t(c["pred_masks"]).reshape(B * R, 28, 28, NC).to(dev), tmask, tids, B * R, 28, 28, NC, 1.0, lm,
            None, torch.zeros(2, dtype=torch.float64, device=dev), st)
     assert np.isclose(lm.item(), g("mask_loss"), rtol=2e-5), (lm.item(), g("mask_loss"))
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(reason="module-level layer operators of myolo.model: written against the verified C-ABI signatures but not yet "
+                          "run on a GPU (round-1 GPU budget was spent); expected to pass", strict=False)
+@pytest.mark.parametrize("name", list(GI.CASES))
+def test_module_level_layer_operators_equal_reference_source(gold, name):
+    """DecodeYOLOLayer / DetectionsLayer / DetectMaskTargetLayer / PyramidROIAlign / yolo_custom_loss /
+    myolo_mask_loss_graph of the package, called the way the reference's build() calls them, on device tensors."""
+    from myolo import model as M
+    from myolo.config import Config
+    c = GI.build(name)
+    g = lambda k: gold[name + "/" + k]                                             # noqa: E731
+
+    class Cfg(Config):
+        BATCH_SIZE, GRID_H, GRID_W, N_BOX, NUM_CLASSES = c["B"], c["G"], c["G"], c["NB"], c["NC"]
+        ANCHORS, TRUE_BOX_BUFFER, MAX_GT_INSTANCES = list(c["ANCHORS"]), c["TB"], c["M"]
+        IMAGE_SHAPE = [c["S"], c["S"], 3]
+        CLASS_WEIGHTS = np.asarray(c["CLASS_WEIGHTS"], dtype="float32")
+        OBJECT_SCALE, NO_OBJECT_SCALE = c.get("OBJECT_SCALE", 5.0), c.get("NO_OBJECT_SCALE", 1.0)
+        COORD_SCALE, CLASS_SCALE = c.get("COORD_SCALE", 1.0), c.get("CLASS_SCALE", 1.0)
+        TRAIN_ROIS_PER_IMAGE = c["R"]
+
+    cfg = Cfg()
+    # the decode kernels take the grid from the tensor; resolve() derives G from IMAGE_SHAPE (S // 32), which these
+    # synthetic cases do not follow, so the layers get a config whose IMAGE_SHAPE matches the grid
+    class GridCfg(Cfg):
+        IMAGE_SHAPE = [32 * c["G"], 32 * c["G"], 3]
+    gcfg = GridCfg()
+    dev = torch.device("cuda")
+    y_pred = _t(c["y_pred"]).to(dev)
+    tol = 5e-6 * max(1.0, np.abs(g("proposals")).max())
+    props = M.DecodeYOLOLayer(name='decode_yolo_layer', config=gcfg)([y_pred])
+    assert np.allclose(props.cpu().numpy(), g("proposals"), rtol=0, atol=tol)
+    det = M.DetectionsLayer(name="decode_yolo_layer", config=gcfg)([y_pred])
+    assert np.allclose(det.cpu().numpy()[..., :5], g("detections")[..., :5], rtol=0, atol=tol)
+    assert np.array_equal(det.cpu().numpy()[..., 5], g("detections")[..., 5])
+    loss = M.yolo_custom_loss(_t(c["y_true"]).to(dev), y_pred, _t(c["true_boxes"]).to(dev), gcfg)
+    assert np.isclose(loss.item(), g("yolo_loss"), rtol=3e-5)
+    rois, tids, _, tmask = M.DetectMaskTargetLayer(cfg, name='detect_mask_targets')(
+        [_t(g("proposals")).to(dev), _t(c["gt_class_ids"]).to(dev), _t(c["gt_boxes_px"]).to(dev), _t(c["gt_masks"]).to(dev)])
+    assert np.array_equal(tids.cpu().numpy(), g("target_class_ids")) and np.array_equal(rois.cpu().numpy(), g("rois"))
+    pooled = M.PyramidROIAlign([14, 14], name="roi_align_mask")([rois, _t(c["feat"]).to(dev)])
+    assert np.allclose(pooled[:, ::5].cpu().numpy(), g("pooled_every5"), rtol=0, atol=5e-6)
+    ml = M.myolo_mask_loss_graph(tmask, tids, _t(c["pred_masks"]).to(dev))
+    assert np.isclose(ml.item(), g("mask_loss"), rtol=2e-5)
