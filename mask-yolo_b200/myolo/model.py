@@ -262,6 +262,39 @@ def build_mask_graph(rois, feature_maps=None, pool_size=None, num_classes=None, 
     return e.mask_head(_f32(rois), training)
 
 
+class Prefetcher(object):
+    """Builds `sequence[i]` for i in `indices` on background threads and yields the results IN ORDER, never more than
+    `depth` of them ahead of the consumer -- what Keras' OrderedEnqueuer does for fit_generator(max_queue_size=depth).
+    numpy releases the GIL in the large copies that dominate BatchGenerator.__getitem__, so the batch for step k+1 is
+    assembled while the GPU runs step k.  An exception in a worker is re-raised at the position of its item."""
+
+    def __init__(self, sequence, indices, depth=3, workers=1):
+        self.sequence, self.indices = sequence, list(indices)
+        self.depth, self.workers = max(1, int(depth)), max(1, int(workers))
+
+    def __iter__(self):
+        import collections
+        from concurrent.futures import ThreadPoolExecutor
+        pool = ThreadPoolExecutor(max_workers=min(self.workers, self.depth), thread_name_prefix="myolo-prefetch")
+        pending = collections.deque()
+        todo = iter(self.indices)
+        try:
+            for i in todo:
+                pending.append(pool.submit(self.sequence.__getitem__, i))
+                if len(pending) >= self.depth:
+                    break
+            while pending:
+                item = pending.popleft().result()
+                for i in todo:                        # keep the window full: one new item per consumed item
+                    pending.append(pool.submit(self.sequence.__getitem__, i))
+                    break
+                yield item
+        finally:
+            for f in pending:
+                f.cancel()
+            pool.shutdown(wait=True)
+
+
 # ------------------------------------------------------------------------------------------------
 # keras_model-like handle
 # ------------------------------------------------------------------------------------------------
@@ -445,10 +478,12 @@ class MaskYOLO:
         self.engine.load_params(sd, strict=not (by_name or exclude))
 
     def train(self, train_dataset, val_dataset, learning_rate, epochs, layers, augmentation=None, custom_callbacks=None,
-              no_augmentation_sources=None, max_cached=(50, 6), verbose=1):
+              no_augmentation_sources=None, max_cached=(50, 6), verbose=1, max_queue_size=3, workers=2):
         """fit loop of model.py:943-1060: caches the first 50 / 6 images of the datasets, builds the
         BatchGenerators, trains `layers` with Adam and writes './saved_model_<Mon DD-HH-MM>.pt' after
-        every epoch.  Returns the per-epoch history dict."""
+        every epoch.  Batches are built ahead of the GPU by background threads, in order, at most `max_queue_size` of
+        them (the reference's fit_generator(max_queue_size=3) enqueuer, model.py:1047-1058).  Returns the per-epoch
+        history dict."""
         layer_regex = {"all": ".*"}
         layers = layer_regex.get(layers, layers)
         cfg = self.config
@@ -467,8 +502,7 @@ class MaskYOLO:
         B = self.engine.B
         for ep in range(self.epoch, epochs):
             t0, acc, nb = time.time(), np.zeros(3), 0
-            for i in range(len(train_gen)):
-                inputs, _ = train_gen[i]
+            for inputs, _ in Prefetcher(train_gen, range(len(train_gen)), max_queue_size, workers):
                 if inputs[0].shape[0] != B:
                     continue
                 vals = self._train_on_batch(inputs)
@@ -477,7 +511,8 @@ class MaskYOLO:
             acc /= max(nb, 1)
             vloss = float("nan")
             if val_gen is not None:
-                vs = [self._train_on_batch(val_gen[i][0], update=False)[0] for i in range(len(val_gen)) if val_gen[i][0][0].shape[0] == B]
+                vs = [self._train_on_batch(inputs, update=False)[0]
+                      for inputs, _ in Prefetcher(val_gen, range(len(val_gen)), max_queue_size, workers) if inputs[0].shape[0] == B]
                 vloss = float(np.mean(vs)) if vs else float("nan")
             for k, v in zip(("loss", "yolo_sum_loss", "myolo_mask_loss"), acc):
                 history[k].append(float(v))

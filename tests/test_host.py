@@ -165,3 +165,86 @@ def test_iou_parity_helpers():
     n[1, 0, 0, 2] = 0.49                                   # below the threshold: still empty
     iou = Hh.mask_iou(m, n)
     assert iou.shape == (2, 3) and abs(iou[0, 0].item() - 8.0 / 12.0) < 1e-12 and iou[1, 2].item() == 1.0 and iou[0, 1].item() == 1.0
+
+
+def test_prefetcher_is_ordered_bounded_and_propagates_errors():
+    import threading
+    import time
+    from myolo.model import Prefetcher
+
+    class Seq(object):
+        def __init__(self, fail_at=None):
+            self.lock, self.inflight, self.peak, self.built, self.fail_at = threading.Lock(), 0, 0, [], fail_at
+
+        def __getitem__(self, i):
+            with self.lock:
+                self.inflight += 1
+                self.peak = max(self.peak, self.inflight)
+                self.built.append(i)
+            time.sleep(0.004 * (4 - i % 4))                 # later items of a window finish first
+            with self.lock:
+                self.inflight -= 1
+            if i == self.fail_at:
+                raise ValueError("item %d" % i)
+            return i * i
+
+    s = Seq()
+    consumed = []
+    for v in Prefetcher(s, range(11), depth=3, workers=2):
+        consumed.append(v)
+        assert len(s.built) <= len(consumed) + 3            # never more than `depth` items ahead of the consumer
+    assert consumed == [i * i for i in range(11)] and s.peak <= 2
+    s = Seq(fail_at=5)
+    got = []
+    with pytest.raises(ValueError, match="item 5"):
+        for v in Prefetcher(s, range(11), depth=3, workers=2):
+            got.append(v)
+    assert got == [0, 1, 4, 9, 16] and max(s.built) <= 8    # raised at its position; the producer stopped
+    assert list(Prefetcher(Seq(), [], 3, 2)) == [] and list(Prefetcher(Seq(), [3], 1, 1)) == [9]
+
+
+def test_train_loop_on_stub_engine(tmp_path):
+    """MaskYOLO.train (model.py:943-1060) with the device step stubbed out: caching, BatchGenerator construction, the
+    prefetched epoch loop, validation with update=False, history and the per-epoch checkpoint."""
+    import torch
+    from myolo.model import MaskYOLO
+
+    class C128(ShapesConfig):
+        BATCH_SIZE = 4
+        IMAGE_SHAPE = [128, 128, 3]
+        IMAGE_MIN_DIM = IMAGE_MAX_DIM = 128
+        GRID_H = GRID_W = 4
+
+    class StubEngine(object):
+        B = 4
+        trainable = None
+
+        def state_dict(self):
+            return {"conv1/kernel": torch.zeros(3, 3, 3, 32)}
+
+        def set_trainable(self, pred):
+            self.trainable = [n for n in ("conv1/kernel", "myolo_mask_conv1/kernel") if pred(n)]
+
+    cfg = C128()
+    tr, va = ShapesDataset(seed=1), ShapesDataset(seed=2)
+    tr.load_shapes(10, 128, 128); tr.prepare()
+    va.load_shapes(4, 128, 128); va.prepare()
+    m = MaskYOLO.__new__(MaskYOLO)
+    m.mode, m.config, m.model_dir, m.epoch, m.engine, m.learning_rate = "training", cfg, str(tmp_path), 0, StubEngine(), None
+    calls = []
+
+    def fake_step(inputs, update=True, lr=None):
+        assert len(inputs) == 6 and inputs[0].shape == (4, 128, 128, 3) and inputs[0].dtype == np.float32
+        assert inputs[5].shape == (4, 128, 128, cfg.MAX_GT_INSTANCES) and inputs[3].shape == (4, cfg.TRUE_BOX_BUFFER)
+        calls.append(update)
+        return [3.0, 1.0, 2.0]
+
+    m._train_on_batch = fake_step
+    np.random.seed(0)
+    hist = m.train(tr, va, learning_rate=0.01, epochs=2, layers=r"(myolo_mask.*)", verbose=0)
+    # 10 images / batch 4 -> 3 batches (the last one refilled from the preceding images), 4 val images -> 1 batch
+    assert calls == [True, True, True, False] * 2
+    assert hist == {"loss": [3.0, 3.0], "yolo_sum_loss": [1.0, 1.0], "myolo_mask_loss": [2.0, 2.0], "val_loss": [3.0, 3.0]}
+    assert m.engine.trainable == ["myolo_mask_conv1/kernel"] and m.learning_rate == 0.01 and m.epoch == 2
+    saved = [f for f in os.listdir(str(tmp_path)) if f.startswith("saved_model_") and f.endswith(".pt")]
+    assert len(saved) == 1 and "conv1/kernel" in torch.load(os.path.join(str(tmp_path), saved[0]))
