@@ -348,8 +348,8 @@ int myolo_encode_yolo_targets(const int* gt_class_ids, const int* gt_boxes, int 
  * ws: B*MS*(2*S+1) ints (row extents per shape + compaction slots), 8-byte aligned.
  * Outputs: image_f32 [B,S,S,3] = float32(uint8 / 255.) (nullable), image_u8 [B,S,S,3] (nullable), gt_masks [B,S,S,M] bytes,
  * gt_class_ids [B,TB], gt_boxes [B,TB,4] int32 (x1,y1,x2,y2; x2/y2 exclusive), gt_boxes_f the same as float (nullable);
- * all zero padded.  S % 16 == 0, MS <= 8, MS <= M <= 128, MS <= TB.  Pixel-exact with OpenCV 4.13 for the generator's
- * domain (centres inside [20, S-21], s in [20, S/4]; tests/test_shapes_raster.py). */
+ * all zero padded.  S % 16 == 0, MS <= 8, MS <= M <= 128, MS <= TB.  Pixel-exact with OpenCV 4.13 (the row-extent
+ * functions are compared with cv2 on the CPU for arbitrary centres / sizes / image shapes, tests/test_shapes_raster.py). */
 int myolo_shapes_raster(const int* specs, int B, int S, int MS, int M, int TB, int* ws, float* image_f32,
                         unsigned char* image_u8, unsigned char* gt_masks, int* gt_class_ids, int* gt_boxes,
                         float* gt_boxes_f, myolo_stream stream);

@@ -120,8 +120,9 @@ MYOLO_HD static inline void rect_rows(int* lo, int* hi, int stride, int W, int H
 }
 
 // cv2.fillPoly of the triangle apex (ax, ay), base corners (bl, by) and (br, by), by > ay: CollectPolyEdges draws the three
-// boundary lines and builds one PolyEdge per slanted side (16.16 fixed point, start at +1/2 pixel, from the CLIPPED end
-// points when a side leaves the image); FillEdgeCollection then fills rows ay .. by-1 from x_left >> 16 to
+// boundary lines and builds one PolyEdge per slanted side (16.16 fixed point, start at +1/2 pixel; when a side leaves the
+// image its x comes from the CLIPPED end points -- even when clipping leaves a single pixel or rejects the side -- and its
+// y from them only if they still span rows); FillEdgeCollection then fills rows ay .. by-1 from x_left >> 16 to
 // (x_right - 1) >> 16.
 MYOLO_HD static inline void triangle_rows(int* lo, int* hi, int stride, int W, int H, int ax, int ay, int bl, int br, int by) {
   const int XY_SHIFT = 16;
@@ -139,10 +140,9 @@ MYOLO_HD static inline void triangle_rows(int* lo, int* hi, int stride, int W, i
           (unsigned long long)p0y >= (unsigned long long)H || (unsigned long long)p1y >= (unsigned long long)H) {
         long long t0x = p0x, t0y = p0y, t1x = p1x, t1y = p1y;
         clip_line(W, H, t0x, t0y, t1x, t1y);
-        if (t0y != t1y) {
-          c0x = (t0x << XY_SHIFT) + HALF; c0y = t0y;
-          c1x = (t1x << XY_SHIFT) + HALF; c1y = t1y;
-        }
+        c0x = (t0x << XY_SHIFT) + HALF;                           // x always from the clipped points ...
+        c1x = (t1x << XY_SHIFT) + HALF;
+        if (t0y != t1y) { c0y = t0y; c1y = t1y; }                 // ... y only when the clipped side still spans rows
       }
       const long long d = (c1x - c0x) / (c1y - c0y);            // truncating division, as in C++
       const long long y0 = p0y < p1y ? p0y : p1y;

@@ -71,14 +71,22 @@ def test_row_extents_equal_cv2_on_the_generator_domain(ext):
     assert n > 8000
 
 
-def test_squares_and_circles_equal_cv2_anywhere(ext):
-    """Rectangles and circles are exact for any centre / size / image shape (clipped, degenerate, fully outside)."""
+def test_all_three_shapes_equal_cv2_anywhere(ext):
+    """Rectangles, circles and triangles are exact for any centre / size / image shape: clipped on every side, degenerate
+    (s = 0), apex outside the image, a side that touches the image in a single pixel, fully outside."""
     rng = random.Random(12)
-    for _ in range(4000):
-        W, H, t = rng.randint(8, 80), rng.randint(8, 80), rng.randint(1, 2)
+    per_kind = {1: 0, 2: 0, 3: 0}
+    for _ in range(9000):
+        W, H, t = rng.randint(8, 80), rng.randint(8, 80), rng.randint(1, 3)
         x, y, s = rng.randint(-40, 120), rng.randint(-40, 120), rng.randint(0, 70)
         lo, hi = ext(t, x, y, s, W, H)
         assert np.array_equal(_mask_from_rows(lo, hi, W), _cv(t, x, y, s, W, H)), (W, H, t, x, y, s)
+        per_kind[t] += 1
+    assert min(per_kind.values()) > 2500
+    # the cases that pinned the clipped-edge rule of fillPoly (a side reduced to one border pixel by clipLine)
+    for W, H, x, y, s in ((37, 49, 39, 91, 47), (41, 27, 69, 10, 33), (67, 13, 93, -10, 24), (63, 64, -31, -5, 27)):
+        lo, hi = ext(3, x, y, s, W, H)
+        assert np.array_equal(_mask_from_rows(lo, hi, W), _cv(3, x, y, s, W, H)), (W, H, x, y, s)
 
 
 def _compose(rows_fn, info, S, M, TB):
