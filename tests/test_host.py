@@ -248,3 +248,46 @@ def test_train_loop_on_stub_engine(tmp_path):
     assert m.engine.trainable == ["myolo_mask_conv1/kernel"] and m.learning_rate == 0.01 and m.epoch == 2
     saved = [f for f in os.listdir(str(tmp_path)) if f.startswith("saved_model_") and f.endswith(".pt")]
     assert len(saved) == 1 and "conv1/kernel" in torch.load(os.path.join(str(tmp_path), saved[0]))
+
+
+def test_padded_flat_layout_turns_a_3x3_same_conv_into_nine_shifted_gemms():
+    """DESIGN section 3, on the CPU: in the padded-flat layout a 3x3 SAME convolution is sum_t A[row + shift_t] @ W_t with
+    shift(dy,dx) = (dy-1)(W+1) + (dx-1), tiles cannot bleed into each other, and the transposed (negated) shifts give the
+    data gradient; guard rows and pad rows stay zero."""
+    import torch
+    import torch.nn.functional as F
+    from myolo import pf
+    n, H, W, C, Co = 3, 5, 4, 6, 7
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(n, H, W, C, generator=g, dtype=torch.float64)
+    w = torch.randn(3, 3, C, Co, generator=g, dtype=torch.float64)          # HWIO
+    A = pf.PF(n, H, W, C, device="cpu", dtype=torch.float64).load_dense(x)
+    assert A.M == n * (H + 1) * (W + 1) and A.rows.shape == (A.M, C)
+    assert torch.equal(A.dense(), x)
+    full = A.storage.view(-1, C)
+    gr = pf.guard_rows(W)
+    assert gr >= W + 2 and not full[:gr].any() and not full[gr + A.M:].any()     # zero guards around the matrix
+    grid = A.rows.view(n, H + 1, W + 1, C)
+    assert not grid[:, 0].any() and not grid[:, :, 0].any()                      # one zero row-block / one zero pixel per line
+    shifts = pf.conv3x3_shifts(W)
+    assert shifts == [(dy - 1) * (W + 1) + (dx - 1) for dy in range(3) for dx in range(3)] and max(map(abs, shifts)) == W + 2
+
+    def tap_gemm(storage_rows, M, weights, sh):
+        out = torch.zeros(M, weights.shape[-1], dtype=torch.float64)
+        for t, s in enumerate(sh):
+            out += storage_rows[gr + s: gr + s + M] @ weights[t]
+        return out
+
+    y = tap_gemm(full, A.M, w.reshape(9, C, Co), shifts).view(n, H + 1, W + 1, Co)[:, 1:, 1:]
+    ref = F.conv2d(x.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), padding=1).permute(0, 2, 3, 1)
+    assert torch.allclose(y, ref, atol=1e-12)
+    # data gradient: dy in PF layout (pads zero), taps with negated shifts and transposed weights
+    dy = torch.randn(n, H, W, Co, generator=g, dtype=torch.float64)
+    D = pf.PF(n, H, W, Co, device="cpu", dtype=torch.float64).load_dense(dy)
+    dx = tap_gemm(D.storage.view(-1, Co), D.M, w.reshape(9, C, Co).transpose(1, 2), pf.conv3x3_shifts(W, negate=True))
+    xr = x.clone().requires_grad_(True)
+    F.conv2d(xr.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), padding=1).permute(0, 2, 3, 1).backward(dy)
+    assert torch.allclose(dx.view(n, H + 1, W + 1, C)[:, 1:, 1:], xr.grad, atol=1e-12)
+    v = A.view()
+    assert (v.n, v.h, v.w, v.c, v.sh, v.sn) == (n, H, W, C, (W + 1) * C, (H + 1) * (W + 1) * C)
+    assert v.p == A.rows.data_ptr() + 8 * ((W + 1) + 1) * C                     # first valid pixel, float64 here
