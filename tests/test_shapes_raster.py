@@ -226,3 +226,73 @@ def test_shapes_raster_rejects_bad_arguments():
         C.call("myolo_shapes_raster", z, 1, 40, 4, 10, 10, z, None, None, m, z, z, None, 0)
     with pytest.raises(C.MyoloError):          # more shapes than mask channels
         C.call("myolo_shapes_raster", z, 1, 64, 4, 2, 10, z, None, None, m, z, z, None, 0)
+
+
+def test_owner_composition_drops_fully_occluded_instances_like_load_image_gt(ext):
+    """A hand-made image the generator's NMS would never produce: shape 0 is completely covered by shape 2, shape 1 partly.
+    load_image_gt drops the invisible instance and keeps the order of the others; so does the owner rule."""
+    S = 96
+
+    class Cfg(ShapesConfig):
+        IMAGE_SHAPE = [S, S, 3]
+        IMAGE_MIN_DIM = IMAGE_MAX_DIM = S
+
+    cfg = Cfg()
+    ds = ShapesDataset(0)
+    ds.add_class("shapes", 1, "square")
+    ds.add_class("shapes", 2, "circle")
+    ds.add_class("shapes", 3, "triangle")
+    shapes = [("circle", (10, 20, 30), (40, 40, 8)), ("triangle", (50, 60, 70), (60, 50, 20)), ("square", (90, 100, 110), (42, 42, 14))]
+    ds.add_image("shapes", image_id=0, path=None, width=S, height=S, bg_color=[1, 2, 3], shapes=shapes)
+    ds.add_image("shapes", image_id=1, path=None, width=S, height=S, bg_color=[7, 8, 9], shapes=[])
+    ds.prepare()
+    image, class_ids, bbox, mask = mutils.load_image_gt(ds, cfg, 0, use_mini_mask=False)
+    assert class_ids.tolist() == [3, 1] and mask.shape == (S, S, 2)               # the circle is gone
+    im2, m2, ids2, bx2 = _compose(ext, ds.image_info[0], S, cfg.MAX_GT_INSTANCES, cfg.TRUE_BOX_BUFFER)
+    assert np.array_equal(image, im2) and np.array_equal(mask, m2[:, :, :2]) and not m2[:, :, 2:].any()
+    assert ids2[:3].tolist() == [3, 1, 0] and np.array_equal(bbox, bx2[:2]) and not bx2[2:].any()
+    tab = spec_table(ds)
+    assert tab[0, 3] == 3 and tab[1, 3] == 0 and tab[1, :3].tolist() == [7, 8, 9] and not tab[1, 4:].any()
+    im3, m3, ids3, bx3 = _compose(ext, ds.image_info[1], S, cfg.MAX_GT_INSTANCES, cfg.TRUE_BOX_BUFFER)
+    assert (im3 == np.array([7, 8, 9], np.uint8)).all() and not m3.any() and not ids3.any() and not bx3.any()
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(reason="written after the round-1 GPU budget was spent; the same rule is verified in numpy above", strict=False)
+def test_device_raster_drops_fully_occluded_instances_and_handles_empty_images():
+    import torch
+    from myolo import _cabi as C
+    S, MS, M, TB = 96, 4, 10, 10
+    specs = np.zeros((2, 4 + 8 * MS), np.int32)
+    specs[0, :4] = (1, 2, 3, 3)
+    specs[0, 4:11] = (2, 10, 20, 30, 40, 40, 8)            # circle, later covered completely by the square
+    specs[0, 12:19] = (3, 50, 60, 70, 60, 50, 20)          # triangle, partly covered
+    specs[0, 20:27] = (1, 90, 100, 110, 42, 42, 14)        # square
+    specs[1, :4] = (7, 8, 9, 0)                            # no shapes at all
+    dev = torch.device("cuda")
+    sp = torch.from_numpy(specs).to(dev)
+    ws = torch.empty(2 * MS * (2 * S + 1), dtype=torch.int32, device=dev)
+    img = torch.empty(2, S, S, 3, dtype=torch.uint8, device=dev)
+    masks = torch.empty(2, S, S, M, dtype=torch.uint8, device=dev)
+    ids = torch.empty(2, TB, dtype=torch.int32, device=dev)
+    boxes = torch.empty(2, TB, 4, dtype=torch.int32, device=dev)
+    C.call("myolo_shapes_raster", sp, 2, S, MS, M, TB, ws, None, img, masks, ids, boxes, None, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+
+    class Cfg(ShapesConfig):
+        IMAGE_SHAPE = [S, S, 3]
+        IMAGE_MIN_DIM = IMAGE_MAX_DIM = S
+        MAX_GT_INSTANCES = M
+        TRUE_BOX_BUFFER = TB
+
+    ds = ShapesDataset(0)
+    for k, name in enumerate(("square", "circle", "triangle")):
+        ds.add_class("shapes", k + 1, name)
+    ds.add_image("shapes", image_id=0, path=None, width=S, height=S, bg_color=[1, 2, 3],
+                 shapes=[("circle", (10, 20, 30), (40, 40, 8)), ("triangle", (50, 60, 70), (60, 50, 20)), ("square", (90, 100, 110), (42, 42, 14))])
+    ds.prepare()
+    image, class_ids, bbox, mask = mutils.load_image_gt(ds, Cfg(), 0, use_mini_mask=False)
+    assert np.array_equal(img[0].cpu().numpy(), image)
+    assert ids[0].cpu().tolist() == [3, 1] + [0] * (TB - 2) and np.array_equal(boxes[0, :2].cpu().numpy(), bbox)
+    assert np.array_equal(masks[0, :, :, :2].cpu().numpy().astype(bool), mask) and not masks[0, :, :, 2:].any()
+    assert (img[1].cpu().numpy() == np.array([7, 8, 9], np.uint8)).all() and not masks[1].any() and not ids[1].any() and not boxes.cpu()[1].any()
