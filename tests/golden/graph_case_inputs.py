@@ -11,6 +11,10 @@ CASES = {
     "base": dict(B=1, G=4, NB=5, NC=2, TB=10, M=10, S=64, C=8, seed=202,
                  ANCHORS=[1.27, 1.31, 1.95, 1.85, 2.40, 2.72, 3.20, 3.32, 5.06, 5.05], CLASS_WEIGHTS=[0.5, 2.0],
                  OBJECT_SCALE=5.0, NO_OBJECT_SCALE=0.7, COORD_SCALE=1.5, CLASS_SCALE=1.2),
+    # the second image has NO ground truth at all (every padded row is zero): trim_zeros leaves nothing, the IoU matrix
+    # is [R, 0], every ROI is negative (model.py:487-545 on empty tensors)
+    "nogt": dict(B=2, G=4, NB=3, NC=4, TB=6, M=6, S=64, C=4, seed=505, empty_images=[1],
+                 ANCHORS=[0.6, 0.6, 1.2, 1.3, 2.0, 2.1], CLASS_WEIGHTS=[1.0, 1.0, 1.0, 1.0]),
 }
 
 
@@ -31,6 +35,8 @@ def build(name):
     yy, xx = np.mgrid[0:S, 0:S]
     for b in range(B):
         n = int(rng.randint(2, 5))
+        if b in c.get("empty_images", ()):
+            n = 0
         for k in range(n):
             w, h = rng.uniform(0.18, 0.45, size=2) * S
             cx, cy = rng.uniform(0.25, 0.75, size=2) * S

@@ -142,7 +142,12 @@ def less(x, y): return T(np.less(*_like(x, y)))
 def greater(x, y): return T(np.greater(*_like(x, y)))
 def equal(x, y): return T(np.equal(*_like(x, y)))
 def reduce_sum(x, axis=None): return T(np.sum(_a(x), axis=axis, dtype=_a(x).dtype if _a(x).dtype != np.bool_ else None))
-def reduce_max(x, axis=None): return T(np.max(_a(x), axis=axis))
+def reduce_max(x, axis=None):
+    a = _a(x)
+    if a.size == 0 and axis is not None:      # TF reduces an empty axis to the lowest finite value of the dtype
+        shp = [s for k, s in enumerate(a.shape) if k != (axis % a.ndim)]
+        return T(np.full(shp, np.finfo(a.dtype).min if a.dtype.kind == "f" else np.iinfo(a.dtype).min, dtype=a.dtype))
+    return T(np.max(a, axis=axis))
 def argmax(x, axis=None): return T(np.argmax(_a(x), axis=axis).astype(np.int64))
 
 
