@@ -575,11 +575,26 @@ class MaskYOLO:
                 "scores": score[0, :n].cpu().numpy(), "masks": masks}
 
     def decode_masks(self, detections, myolo_mask, image_shape):
-        """Class-specific 28x28 masks -> full-size boolean masks pasted at their boxes (model.py:1330-1391)."""
-        S = self.cfg["S"]
-        out = []
-        for d, m in zip(detections, myolo_mask):
-            cls = int(d[5])
-            box = np.round(d[:4] * S).astype(np.int32)
-            out.append(mutils.unmold_mask(m[:, :, cls], box, image_shape))
-        return np.stack(out, -1) if out else np.zeros(tuple(image_shape[:2]) + (0,), bool)
+        """Network outputs of ONE image -> (boxes [N,4] normalised (x1,y1,x2,y2), class_ids [N], scores [N], full-size
+        boolean masks [H,W,N])  (model.py:1330-1391): class-specific 28x28 masks, zero-area boxes dropped, each mask
+        resized into its box by unmold_mask."""
+        assert len(detections) == 1            # only detect for one image per time
+        assert len(myolo_mask) == 1
+        assert list(image_shape) == list(self.config.IMAGE_SHAPE)
+        detection = np.asarray(detections[0])
+        masks_all = np.asarray(myolo_mask[0])
+        N = len(detection)
+        boxes = detection[:N, :4]
+        scores = detection[:N, 4]
+        class_ids = detection[:N, 5].astype(np.int32)
+        masks = masks_all[np.arange(N), :, :, class_ids]
+        exclude_ix = np.where((boxes[:, 2] - boxes[:, 0]) * (boxes[:, 3] - boxes[:, 1]) <= 0)[0]
+        if exclude_ix.shape[0] > 0:
+            boxes = np.delete(boxes, exclude_ix, axis=0)
+            class_ids = np.delete(class_ids, exclude_ix, axis=0)
+            scores = np.delete(scores, exclude_ix, axis=0)
+            masks = np.delete(masks, exclude_ix, axis=0)
+            N = class_ids.shape[0]
+        full_masks = [mutils.unmold_mask(masks[i], boxes[i], image_shape) for i in range(N)]
+        full_masks = np.stack(full_masks, axis=-1) if full_masks else np.empty(tuple(image_shape[:2]) + (0,))
+        return boxes, class_ids, scores, full_masks

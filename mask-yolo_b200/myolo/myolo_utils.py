@@ -409,8 +409,30 @@ def NMB(boxes, class_ids, indices, image_shape, nms_threshold=0.3):
 
 
 def unmold_mask(mask, bbox, image_shape):
-    """Paste a [h, w] soft mask into its (x1, y1, x2, y2) pixel box of a full-size boolean image
-    (myolo_utils.py:883-912): bilinear resize to the box, threshold 0.5."""
+    """A small soft mask -> full-size boolean mask (myolo_utils.py:883-912).  `bbox` = (x1, y1, x2, y2) NORMALISED, as
+    DetectionsLayer emits it; the reference's integer rules are kept: corners truncated with int(), x1/y1 clamped to
+    [0, size], x2/y2 to [1, size], the mask resized (bilinear) to the CLIPPED box and thresholded at 0.5.  (The reference
+    resizes with scikit-image, which is not available here: cv2's bilinear resize stands in for it.  A box that is empty
+    after truncation gives an empty mask; the reference fails with a broadcasting error there.)"""
+    threshold = 0.5
+    w, h = image_shape[0], image_shape[1]
+    x1, y1, x2, y2 = bbox
+    x1 = min(max(0, int(x1 * w)), w)
+    x2 = min(max(1, int(x2 * w)), w)
+    y1 = min(max(0, int(y1 * h)), h)
+    y2 = min(max(1, int(y2 * h)), h)
+    full_mask = np.zeros(image_shape[:2], dtype=bool)
+    if x2 <= x1 or y2 <= y1:
+        return full_mask
+    m = resize(mask, (max(1, y2 - y1), max(1, x2 - x1)))
+    full_mask[y1:y2, x1:x2] = np.where(m >= threshold, 1, 0).astype(bool)
+    return full_mask
+
+
+def paste_mask_px(mask, bbox, image_shape):
+    """Paste a [h, w] soft mask into its (x1, y1, x2, y2) PIXEL box of a full-size boolean image: bilinear resize to the
+    (unclipped) box, threshold 0.5, crop to the image.  This is what the device kernel behind MaskYOLO.detect computes
+    (myolo_detect_postprocess, boxes = round(normalised * S)); unmold_mask above keeps the reference's own integer rules."""
     x1, y1, x2, y2 = [int(v) for v in bbox]
     full = np.zeros(image_shape[:2], dtype=bool)
     x1c, y1c, x2c, y2c = max(x1, 0), max(y1, 0), min(x2, image_shape[1]), min(y2, image_shape[0])

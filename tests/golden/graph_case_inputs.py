@@ -142,3 +142,26 @@ def gt_from_boxes(c, gt_class_ids, gt_boxes_px):
             y_true[b, gy, gx, k % NB, 5 + gt_class_ids[b, k]] = 1.0
             true_boxes[b, 0, 0, 0, k] = (gcx, gcy, gw, gh)
     return masks, y_true, true_boxes
+
+
+# ---- decode_masks / unmold_mask case (model.py:1330-1391, myolo_utils.py:883-912)
+def decode_masks_inputs(S=96, N=14, NC=4, seed=606):
+    """detections [1,N,6] (normalised boxes incl. boxes leaving the image, a zero-area and an inverted one; score; class)
+    and myolo_mask [1,N,28,28,NC]."""
+    rs = np.random.RandomState(seed)
+    c = rs.uniform(0.1, 0.9, size=(N, 2))
+    wh = rs.uniform(0.08, 0.6, size=(N, 2))
+    det = np.zeros((1, N, 6), np.float32)
+    det[0, :, 0:2], det[0, :, 2:4] = c - wh / 2, c + wh / 2            # some corners fall below 0 or above 1
+    det[0, 3, 2] = det[0, 3, 0]                                          # zero area -> filtered out
+    det[0, 5, [0, 2]] = det[0, 5, [2, 0]]                                # inverted -> negative area -> filtered out
+    det[0, 7, :4] = (0.97, 0.2, 1.4, 0.9)                                # hugs the right border
+    det[0, :, 4] = rs.uniform(0, 1, size=N)
+    det[0, :, 5] = rs.randint(0, NC, size=N)
+    masks = rs.uniform(0, 1, size=(1, N, 28, 28, NC)).astype(np.float32)
+    yy, xx = np.mgrid[0:28, 0:28]
+    masks[0, :, :, :, :] *= 0.2
+    for i in range(N):                                                   # a blob per detection so that masks have structure
+        cy, cx, r = rs.uniform(8, 20), rs.uniform(8, 20), rs.uniform(4, 12)
+        masks[0, i, :, :, int(det[0, i, 5])] += 0.75 * (((yy - cy) ** 2 + (xx - cx) ** 2) <= r * r)
+    return dict(S=S, N=N, NC=NC, detections=det, myolo_mask=masks)

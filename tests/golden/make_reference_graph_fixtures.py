@@ -201,6 +201,27 @@ def build_cases(M, out, W):
     print("build/inference: detections", out["build/inference/detections"].shape, "masks", out["build/inference/myolo_mask"].shape)
 
 
+def decode_masks_case(M, out):
+    """MaskYOLO.decode_masks (1330-1391) and myolo_utils.unmold_mask (883-912) from the reference's source.  The one
+    primitive underneath, the reference's `resize` wrapper around scikit-image (absent), is replaced by the cv2 bilinear
+    resize the package uses -- what is pinned is everything around it: class-specific mask selection, the zero-area
+    filter, int() truncation and clamping of the normalised corners, resizing into the CLIPPED box, threshold, paste."""
+    import cv2
+    c = GI.decode_masks_inputs()
+    refu = M.mutils
+    assert refu.__file__.startswith("/root/reference/")
+    refu.resize = lambda image, output_shape, **kw: cv2.resize(np.asarray(image, dtype=np.float32),
+                                                               (int(output_shape[1]), int(output_shape[0])),
+                                                               interpolation=cv2.INTER_LINEAR)
+    M.config.IMAGE_SHAPE = [c["S"], c["S"], 3]
+    obj = M.MaskYOLO.__new__(M.MaskYOLO)
+    boxes, class_ids, scores, full = M.MaskYOLO.decode_masks(obj, c["detections"], c["myolo_mask"], (c["S"], c["S"], 3))
+    assert boxes.shape[0] == c["N"] - 2 and full.shape == (c["S"], c["S"], c["N"] - 2) and full.any()
+    out["decode_masks/boxes"], out["decode_masks/class_ids"], out["decode_masks/scores"] = boxes, class_ids, scores
+    out["decode_masks/full_bits"], out["decode_masks/full_shape"] = np.packbits(full.astype(np.uint8)), np.asarray(full.shape)
+    print("decode_masks:", boxes.shape[0], "kept of", c["N"], "mask pixels", int(full.sum()))
+
+
 def main():
     W = product_weights()
     M = load_reference_model()
@@ -239,6 +260,7 @@ def main():
               (tids.a > 0).sum(1), "mask_loss", out[name + "/mask_loss"])
     net_cases(M, out, W)
     build_cases(M, out, W)
+    decode_masks_case(M, out)
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, os.path.getsize(OUT), "bytes,", len(out), "arrays")
 

@@ -93,8 +93,16 @@ def test_decode_one_yolo_output_and_unmold():
     boxes = mutils.decode_one_yolo_output(netout, [1.0, 1.0], obj_threshold=0.3, nb_class=2)
     assert len(boxes) == 1 and boxes[0].get_label() == 0
     assert abs(boxes[0].xmin - (0.25 - 0.25)) < 1e-9 and abs(boxes[0].ymax - (0.75 + 0.25)) < 1e-9
-    full = mutils.unmold_mask(np.ones((28, 28), np.float32), [10, 20, 30, 50], (64, 64, 3))
+    full = mutils.paste_mask_px(np.ones((28, 28), np.float32), [10, 20, 30, 50], (64, 64, 3))
     assert full.sum() == 20 * 30 and full[20:50, 10:30].all()
+    # unmold_mask keeps the reference's rules: normalised box, int() truncation, clamp, resize to the clipped box
+    full = mutils.unmold_mask(np.ones((28, 28), np.float32), [10.9 / 64, 20.2 / 64, 30.99 / 64, 1.5], (64, 64, 3))
+    assert full.sum() == 20 * 44 and full[20:64, 10:30].all()
+    half = np.zeros((28, 28), np.float32)
+    half[:, 14:] = 1.0
+    full = mutils.unmold_mask(half, [0.0, 0.0, 2.0, 1.0], (64, 64, 3))      # x2 clamped to 64: the mask is squeezed into the clipped box
+    assert full[:, 32:].all() and not full[:, :31].any()
+    assert not mutils.unmold_mask(half, [1.0, 0.0, 1.0, 1.0], (64, 64, 3)).any()
 
 
 def test_mrcnn_shim_and_reference_example_imports():

@@ -553,8 +553,8 @@ def test_deconv_mask_fused(C):
 
 def test_detect_postprocess_matches_numpy_pipeline(C):
     """Device top-k / threshold / NMB / mask paste against the host functions that restate
-    myolo_utils.NMB (88-113; itself pinned to the reference's outputs by tests/test_reference_golden.py) and
-    unmold_mask (883-912)."""
+    myolo_utils.NMB (88-113; itself pinned to the reference's outputs by tests/test_reference_golden.py) and the
+    pixel-box mask paste (paste_mask_px: round, resize to the unclipped box, crop)."""
     from myolo import myolo_utils as mu
     rng = np.random.RandomState(30)
     B, R, NC, S, K = 3, 147, 4, 224, 10
@@ -586,7 +586,7 @@ def test_detect_postprocess_matches_numpy_pipeline(C):
         assert cls[b, :n].cpu().tolist() == [int(det[b, k, 5]) for k in keep]
         for j, k in enumerate(keep):
             box = np.round(det[b, k, :4] * S).astype(np.int32)
-            ref = mu.unmold_mask(masks[b, k, :, :, int(det[b, k, 5])], box, (S, S, 3))
+            ref = mu.paste_mask_px(masks[b, k, :, :, int(det[b, k, 5])], box, (S, S, 3))
             got = pm[b, j].bool().cpu().numpy()
             total_px += ref.sum()
             mism += (ref != got).sum()

@@ -163,6 +163,28 @@ def test_package_tensor_helpers_equal_reference_source(gold, name):
     assert np.allclose(ov.numpy(), g("overlaps_0"), rtol=0, atol=2e-6, equal_nan=True)
 
 
+def test_decode_masks_and_unmold_mask_equal_reference_source(gold):
+    """MaskYOLO.decode_masks (model.py:1330-1391) / unmold_mask (myolo_utils.py:883-912) of the package against the
+    reference's own code: kept detections, order, class ids, scores and every pixel of the pasted full-size masks (boxes
+    that leave the image, a zero-area and an inverted box included).  Both sides resize with the same cv2 call."""
+    from myolo.model import MaskYOLO
+    from myolo.shapes import ShapesConfig
+    c = GI.decode_masks_inputs()
+
+    class Cfg(ShapesConfig):
+        IMAGE_SHAPE = [c["S"], c["S"], 3]
+
+    m = MaskYOLO.__new__(MaskYOLO)
+    m.config = Cfg()
+    boxes, class_ids, scores, full = m.decode_masks(c["detections"], c["myolo_mask"], (c["S"], c["S"], 3))
+    assert np.array_equal(boxes, gold["decode_masks/boxes"]) and np.array_equal(scores, gold["decode_masks/scores"])
+    assert np.array_equal(class_ids, gold["decode_masks/class_ids"]) and class_ids.dtype == gold["decode_masks/class_ids"].dtype
+    assert list(full.shape) == gold["decode_masks/full_shape"].tolist() and full.dtype == bool
+    assert np.array_equal(np.packbits(full.astype(np.uint8)), gold["decode_masks/full_bits"])
+    with pytest.raises(AssertionError):
+        m.decode_masks(np.concatenate([c["detections"]] * 2), c["myolo_mask"], (c["S"], c["S"], 3))
+
+
 def test_shim_crop_and_resize_micro_cases():
     """The one non-trivial primitive the stand-in supplies, against hand-computed values (tf.image.crop_and_resize:
     corners map to [0, size-1], samples outside take the extrapolation value 0, crop size 1 samples the box centre)."""
