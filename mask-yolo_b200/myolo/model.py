@@ -295,6 +295,24 @@ class Prefetcher(object):
             pool.shutdown(wait=True)
 
 
+class DetectResults(list):
+    """What MaskYOLO.detect returns.  The reference's code returns `[{"bboxes", "class_ids", "confidence_scores",
+    "full_masks"}]` (model.py:1316-1328) while its docstring documents the keys "rois", "class_ids", "scores", "masks":
+    `results[0]["bboxes"]` and `results["rois"]` both work here."""
+    _ALIASES = {"rois": "bboxes", "scores": "confidence_scores", "masks": "full_masks"}
+
+    def __init__(self, boxes, class_ids, scores, masks):
+        list.__init__(self, [{"bboxes": boxes, "class_ids": class_ids, "confidence_scores": scores, "full_masks": masks}])
+
+    def __getitem__(self, key):
+        if isinstance(key, str):
+            return list.__getitem__(self, 0)[self._ALIASES.get(key, key)]
+        return list.__getitem__(self, key)
+
+    def keys(self):
+        return list(list.__getitem__(self, 0)) + list(self._ALIASES)
+
+
 # ------------------------------------------------------------------------------------------------
 # keras_model-like handle
 # ------------------------------------------------------------------------------------------------
@@ -558,9 +576,11 @@ class MaskYOLO:
 
     def detect(self, image, weights_dir=None, save_path=None, cs_threshold=0.35, display=False, top_k=10):
         """Full inference on one uint8 image (model.py:1238-1328), end to end on the GPU: network, top-10 by
-        confidence, confidence threshold, NMB and mask paste (myolo_detect_postprocess).  Returns a dict with
-        'rois' (x1,y1,x2,y2 pixels), 'class_ids', 'scores' and boolean 'masks' [H,W,N].  The reference's
-        debugging overrides (hard-coded indices 1306, fixed 224 scale 1307) are not reproduced."""
+        confidence, confidence threshold, NMB and mask paste (myolo_detect_postprocess).  Returns DetectResults: a
+        one-element list holding the dict the reference's code builds ('bboxes', 'class_ids', 'confidence_scores',
+        'full_masks', model.py:1316-1321) that also answers to the keys its docstring promises ('rois' (x1,y1,x2,y2
+        pixels), 'class_ids', 'scores', boolean 'masks' [H,W,N]).  The reference's debugging overrides (hard-coded
+        indices 1306, fixed 224 scale 1307) are not reproduced."""
         assert self.mode == "inference", "Create model in inference mode."
         assert image.dtype == np.uint8 and list(image.shape) == list(self.config.IMAGE_SHAPE)
         if weights_dir is not None:
@@ -571,8 +591,7 @@ class MaskYOLO:
         idx, boxes, cls, score, cnt, pm = eng.postprocess(top_k=top_k, cs_threshold=cs_threshold, nms_threshold=0.7)   # model.py:1304
         n = int(cnt[0].item())
         masks = pm[0, :n].permute(1, 2, 0).bool().cpu().numpy() if n else np.zeros(tuple(image.shape[:2]) + (0,), bool)
-        return {"rois": boxes[0, :n].cpu().numpy(), "class_ids": cls[0, :n].cpu().numpy(),
-                "scores": score[0, :n].cpu().numpy(), "masks": masks}
+        return DetectResults(boxes[0, :n].cpu().numpy(), cls[0, :n].cpu().numpy(), score[0, :n].cpu().numpy(), masks)
 
     def decode_masks(self, detections, myolo_mask, image_shape):
         """Network outputs of ONE image -> (boxes [N,4] normalised (x1,y1,x2,y2), class_ids [N], scores [N], full-size

@@ -114,3 +114,13 @@ def test_small_exported_helpers():
     assert U.resize_one_image(np.zeros((100, 100, 3), np.uint8), gt_box, None, (50, 50)) is None
     assert gt_box == [5, 10, 10, 20]                         # index 2 from gt_box[1], as at HEAD
     assert torch.allclose(M.log2_graph(torch.tensor([8.0])), torch.tensor([3.0]))
+
+
+def test_detect_results_answer_to_both_key_sets():
+    """detect() results: the list-of-one-dict the reference's code returns and the keys its docstring documents."""
+    import numpy as np
+    from myolo.model import DetectResults
+    r = DetectResults(np.zeros((2, 4), np.int32), np.array([1, 2]), np.array([0.9, 0.8]), np.zeros((8, 8, 2), bool))
+    assert len(r) == 1 and set(r[0]) == {"bboxes", "class_ids", "confidence_scores", "full_masks"}
+    assert r["rois"] is r[0]["bboxes"] and r["scores"] is r[0]["confidence_scores"] and r["masks"] is r[0]["full_masks"]
+    assert r["class_ids"].tolist() == [1, 2] and [d["full_masks"].shape for d in r] == [(8, 8, 2)]
