@@ -4,6 +4,8 @@
 // and pasting each survivor's class-specific 28x28 soft mask into its pixel box (bilinear resize,
 // threshold 0.5).  One block per image for the selection, one block per (detection, image) for the paste.
 #include <math_constants.h>
+#include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 
 namespace myolo {
@@ -99,15 +101,22 @@ detect_select_kernel(const float* __restrict__ det, int R, int S, int top_k, flo
 // grid (top_k, B).  Full-size boolean mask of detection j of image b (all zero when j >= count).
 __global__ void __launch_bounds__(256)
 mask_paste_kernel(const float* __restrict__ det, const float* __restrict__ masks, const int* __restrict__ idx,
-                  int R, int NC, int S, int MH, int MW, int top_k, unsigned char* __restrict__ out) {
+                  int R, int NC, int S, int MH, int MW, int top_k, int rule, unsigned char* __restrict__ out) {
   const int j = blockIdx.x, b = blockIdx.y;
   unsigned char* O = out + ((size_t)b * top_k + j) * S * S;
   const int r = idx[b * top_k + j];
   int x1 = 0, y1 = 0, x2 = 0, y2 = 0, cls = 0;
   if (r >= 0) {
     const float* p = det + ((size_t)b * R + r) * 6;
-    x1 = (int)rintf(p[0] * (float)S); y1 = (int)rintf(p[1] * (float)S);     // decode_masks: np.round(d[:4]*S), unclipped
-    x2 = (int)rintf(p[2] * (float)S); y2 = (int)rintf(p[3] * (float)S);
+    if (rule == 1) {
+      // the reference's unmold_mask (myolo_utils.py:895-901): int() truncation, x1/y1 clamped to [0,S], x2/y2 to [1,S];
+      // the mask is then resized into this CLIPPED box
+      x1 = min(max(0, (int)(p[0] * (float)S)), S); y1 = min(max(0, (int)(p[1] * (float)S)), S);
+      x2 = min(max(1, (int)(p[2] * (float)S)), S); y2 = min(max(1, (int)(p[3] * (float)S)), S);
+    } else {
+      x1 = (int)rintf(p[0] * (float)S); y1 = (int)rintf(p[1] * (float)S);   // round(d[:4]*S), unclipped box, cropped below
+      x2 = (int)rintf(p[2] * (float)S); y2 = (int)rintf(p[3] * (float)S);
+    }
     cls = (int)p[5];
   }
   const int bw = x2 - x1, bh = y2 - y1;
@@ -155,7 +164,10 @@ extern "C" int myolo_detect_postprocess(const float* detections, const float* ma
                                               out_class, out_score, out_count);
   if (masks) {
     dim3 grid(top_k, B);
-    mask_paste_kernel<<<grid, 256, 0, st>>>(detections, masks, out_index, R, NC, S, MH, MW, top_k, out_masks);
+    // MYOLO_PASTE_RULE=reference selects the reference's integer rules for the mask box (default: round / unclipped / crop)
+    const char* e = getenv("MYOLO_PASTE_RULE");
+    const int rule = (e && strcmp(e, "reference") == 0) ? 1 : 0;
+    mask_paste_kernel<<<grid, 256, 0, st>>>(detections, masks, out_index, R, NC, S, MH, MW, top_k, rule, out_masks);
   }
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;

@@ -594,6 +594,40 @@ def test_detect_postprocess_matches_numpy_pipeline(C):
     assert total_px > 1000 and mism <= 2e-3 * total_px, (mism, total_px)     # cv2 vs device rounding at exactly 0.5
 
 
+@pytest.mark.xfail(reason="MYOLO_PASTE_RULE=reference was added after the round-1 GPU budget was spent", strict=False)
+def test_detect_postprocess_reference_paste_rule(C, monkeypatch):
+    """Opt-in mask box rule of the reference's unmold_mask (int() truncation, clamp, resize into the clipped box) against
+    myolo_utils.unmold_mask, which is pinned to the reference's source (tests/test_reference_graph_golden.py)."""
+    from myolo import myolo_utils as mu
+    monkeypatch.setenv("MYOLO_PASTE_RULE", "reference")
+    rng = np.random.RandomState(31)
+    B, R, NC, S, K = 2, 60, 4, 96, 10
+    det = np.zeros((B, R, 6), np.float32)
+    c = rng.rand(B, R, 2)
+    wh = rng.rand(B, R, 2) * 0.5 + 0.1
+    det[..., 0:2], det[..., 2:4] = c - wh / 2, c + wh / 2                    # many boxes leave the image
+    det[..., 4] = rng.permutation(B * R).reshape(B, R) / float(B * R)
+    det[..., 5] = rng.randint(0, NC, (B, R))
+    masks = rng.rand(B, R, 28, 28, NC).astype(np.float32)
+    dd, md = cuda(torch.tensor(det)), cuda(torch.tensor(masks))
+    i32 = lambda *sh: torch.empty(sh, dtype=torch.int32, device="cuda")      # noqa: E731
+    idx, boxes, cls, cnt = i32(B, K), i32(B, K, 4), i32(B, K), i32(B)
+    score = torch.empty(B, K, device="cuda")
+    pm = torch.empty(B, K, S, S, dtype=torch.uint8, device="cuda")
+    C.call("myolo_detect_postprocess", dd, md, B, R, NC, S, 28, 28, K, 0.0, 2.0, idx, boxes, cls, score, cnt, pm, stream())
+    total_px = mism = 0
+    for b in range(B):
+        n = int(cnt[b].item())
+        assert n == K                                                        # threshold 0, no suppression (IoU < 2)
+        for j in range(n):
+            k = int(idx[b, j].item())
+            ref = mu.unmold_mask(masks[b, k, :, :, int(det[b, k, 5])], det[b, k, :4], (S, S, 3))
+            got = pm[b, j].bool().cpu().numpy()
+            total_px += ref.sum()
+            mism += (ref != got).sum()
+    assert total_px > 1000 and mism <= 2e-3 * total_px, (mism, total_px)
+
+
 def test_dgrad_with_fused_bn_backward(C):
     """myolo_gemm_taps_bnbwd (dgrad GEMM + BN/ReLU backward in the epilogue) against the exact two-step path:
     CUDA-core dgrad followed by myolo_bn_act_bwd_from_output."""
