@@ -191,6 +191,9 @@ def build_cases(M, out, W):
         out["build/training/" + n] = np.asarray(t.a)[:, ::2, ::3, ::3] if n == "myolo_mask" else np.asarray(t.a)
     assert (np.abs(out["build/training/output_rois"]).sum(-1) > 0).any() and out["build/training/mask_loss"] > 0
     print("build/training: yolo_sum_loss", out["build/training/yolo_sum_loss"], "mask_loss", out["build/training/mask_loss"])
+    model = M.MaskYOLO(mode="yolo", config=cfg).keras_model          # same feeds, learning phase still 1
+    assert model.name == "only_yolo" and len(model.outputs) == 2
+    out["build/yolo/yolo_output"], out["build/yolo/yolo_sum_loss"] = np.asarray(model.outputs[0].a), np.asarray(model.outputs[1].a)
     kls.STATE["learning_phase"] = 0
     c4 = M.mobilenet_graph(tfs.T(c["image"]), "mobilenet")
     kls.FEEDS["input_yolo_feature_map"] = c4.a

@@ -139,6 +139,9 @@ def test_oracle_whole_model_equals_reference_build(gold):
     close(out["myolo_mask"].numpy()[:, ::2, ::3, ::3], g("myolo_mask"), 5e-6, "myolo_mask")
     assert np.isclose(out["yolo_sum_loss"].item(), g("yolo_sum_loss"), rtol=1e-6)
     assert np.isclose(out["mask_loss"].item(), g("mask_loss"), rtol=1e-5)
+    # mode 'yolo' (906-920): backbone + YOLO branch + YOLO loss only, same learning phase
+    close(out["yolo_output"].numpy(), gold["build/yolo/yolo_output"], 1e-9, "yolo-mode yolo_output")
+    assert np.isclose(out["yolo_sum_loss"].item(), gold["build/yolo/yolo_sum_loss"], rtol=1e-6)
     inf = O.forward_inference(P, image, cfg)
     g = lambda k: gold["build/inference/" + k]                                    # noqa: E731
     close(inf["yolo_output"].numpy(), g("yolo_output"), 1e-9, "inference yolo_output")
