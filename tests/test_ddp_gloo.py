@@ -41,9 +41,15 @@ def test_bucketed_allreduce_world2():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = sorted(q.get(timeout=120) for _ in procs)
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    try:
+        res = sorted(q.get(timeout=120) for _ in procs)
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+    finally:                                   # never leave a rank behind
+        for p in procs:
+            if p.is_alive():
+                p.kill()
+                p.join(timeout=10)
     assert res[0][1] and res[1][1]
     assert res[0][2] == [0, 1, 2, 3, 4] and res[1][2] == [5, 6, 7, 8, 9]

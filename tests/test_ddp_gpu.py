@@ -76,10 +76,16 @@ def test_two_gpu_step_is_mean_of_replica_gradients(transport):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q, transport)) for r in range(2)]
     for p in procs:
         p.start()
-    res = sorted(q.get(timeout=300) for _ in procs)
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    try:
+        res = sorted(q.get(timeout=180) for _ in procs)
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+    finally:                                   # never leave a rank behind (a deadlocked collective would hang pytest's exit)
+        for p in procs:
+            if p.is_alive():
+                p.kill()
+                p.join(timeout=10)
     for rank, err, same in res:
         assert same, "replicas must hold identical weights after the step"
         assert err <= 2e-5, (rank, err)
@@ -121,7 +127,12 @@ def test_cabi_allreduce_single_rank_communicator():
     q = ctx.Queue()
     p = ctx.Process(target=_cabi_world1_worker, args=(_free_port(), q))
     p.start()
-    status, detail = q.get(timeout=120)
-    p.join(timeout=60)
+    try:
+        status, detail = q.get(timeout=120)
+        p.join(timeout=60)
+    finally:
+        if p.is_alive():
+            p.kill()
+            p.join(timeout=10)
     assert status == "ok", detail
     assert p.exitcode == 0
