@@ -13,6 +13,7 @@ python bench.py > gpurun_out/first_bench.json 2> gpurun_out/first_bench.err; tai
 bash scripts/profile_step.sh h16 | tail -25
 python scripts/shapes_raster_time.py | tail -1
 python scripts/device_feed_e2e.py | tail -1
+python scripts/bench_hbm_kernels.py | tail -12
 if [ "$(nvidia-smi -L | wc -l)" -ge 2 ]; then
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
       bench.py --gpus 2 --no-cpu-baseline > gpurun_out/first_bench_2gpu.json 2> gpurun_out/first_bench_2gpu.err
