@@ -275,5 +275,17 @@ def main():
     print(f"wrote {OUT}: {len(out)} arrays, {os.path.getsize(OUT) / 1024:.0f} KB")
 
 
+def fuzz(path, n):
+    """Reference side of tests/test_reference_live_fuzz.py: the reference's own myolo_utils through tests/golden/fuzz_cases."""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import fuzz_cases
+    ref = load_reference_utils()
+    assert ref.__file__ if hasattr(ref, "__file__") else True
+    np.savez_compressed(path, **fuzz_cases.run(ref, n))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) == 4 and sys.argv[1] == "--fuzz":
+        fuzz(sys.argv[2], int(sys.argv[3]))
+    else:
+        main()
