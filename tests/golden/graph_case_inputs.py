@@ -18,11 +18,23 @@ CASES = {
 }
 
 
+def fuzz_case(i):
+    """Random configuration number i for the live differential test (tests/test_reference_live_fuzz.py)."""
+    rs = np.random.RandomState(9000 + i)
+    NB, NC = int(rs.randint(1, 6)), int(rs.randint(2, 7))
+    TB = int(rs.randint(5, 13))
+    return dict(B=int(rs.randint(1, 4)), G=int(rs.randint(2, 8)), NB=NB, NC=NC, TB=TB, M=TB, S=int(rs.choice([48, 64, 96])), C=4,
+                seed=7000 + i, ANCHORS=[float(v) for v in rs.uniform(0.4, 4.5, size=2 * NB)],
+                CLASS_WEIGHTS=[float(v) for v in rs.uniform(0.5, 2.0, size=NC)], OBJECT_SCALE=float(rs.uniform(1, 6)),
+                NO_OBJECT_SCALE=float(rs.uniform(0.3, 1.5)), COORD_SCALE=float(rs.uniform(0.5, 2.0)), CLASS_SCALE=float(rs.uniform(0.5, 2.0)),
+                empty_images=[0] if i % 7 == 3 else [])
+
+
 def build(name):
-    """-> dict of numpy inputs for one case.  Ground truth: `n` axis-aligned ellipses per image; y_pred: N(0,1) logits,
+    """-> dict of numpy inputs for one case (a name in CASES, or a dict such as fuzz_case(i) returns).  Ground truth: `n` axis-aligned ellipses per image; y_pred: N(0,1) logits,
     except that the predictor responsible for each instance decodes to (roughly) the instance's box, so that positive
     ROIs, class assignments and mask targets are exercised."""
-    c = dict(CASES[name])
+    c = dict(CASES[name]) if isinstance(name, str) else dict(name)
     rng = np.random.RandomState(c["seed"])
     B, G, NB, NC, TB, M, S = c["B"], c["G"], c["NB"], c["NC"], c["TB"], c["M"], c["S"]
     anchors = np.asarray(c["ANCHORS"], np.float64).reshape(NB, 2)

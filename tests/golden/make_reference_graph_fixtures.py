@@ -268,5 +268,33 @@ def main():
     print("wrote", OUT, os.path.getsize(OUT), "bytes,", len(out), "arrays")
 
 
+def fuzz(path, n):
+    """Reference side of the live differential test of the graph functions: n random configurations (grid, anchors,
+    classes, buffer width, loss scales, class weights, warm-up on/off, some images without ground truth)."""
+    M = load_reference_model()
+    T = tfs.T
+    out = {}
+    for i in range(n):
+        c = GI.build(GI.fuzz_case(i))
+        warm = 3 if i % 3 == 1 else 0
+        cfg = set_config(M, c, warmup=warm)
+        y_pred, y_true, tb = T(c["y_pred"]), T(c["y_true"]), T(c["true_boxes"])
+        out["%d/yolo_loss" % i] = M.yolo_custom_loss(y_true, y_pred, tb).a
+        props = M.DecodeYOLOLayer(config=cfg).call([y_pred])
+        out["%d/proposals" % i] = props.a
+        out["%d/detections" % i] = M.DetectionsLayer(config=cfg).call([y_pred]).a
+        gt_norm = M.norm_boxes_graph(T(c["gt_boxes_px"]), T(np.asarray([c["S"], c["S"]], np.int32)))
+        out["%d/gt_boxes_norm" % i] = gt_norm.a
+        rois, tids, _, tmasks = M.DetectMaskTargetLayer(cfg).call([props, T(c["gt_class_ids"]), gt_norm, T(c["gt_masks"])])
+        out["%d/rois" % i], out["%d/target_class_ids" % i] = rois.a, tids.a
+        out["%d/target_masks_bits" % i] = np.packbits(tmasks.a.astype(np.uint8))
+        out["%d/pooled_every7" % i] = M.PyramidROIAlign([14, 14]).call([rois, T(c["feat"])]).a[:, ::7]
+        out["%d/mask_loss" % i] = M.myolo_mask_loss_graph(tmasks, tids, T(c["pred_masks"])).a
+    np.savez_compressed(path, **out)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) == 4 and sys.argv[1] == "--fuzz":
+        fuzz(sys.argv[2], int(sys.argv[3]))
+    else:
+        main()

@@ -37,3 +37,49 @@ def test_host_functions_agree_with_the_reference_on_random_cases(tmp_path):
     assert sum(mine["dec%d" % k].shape[0] for k in range(n)) > n
     assert sum(len(mine["nmb%d" % k]) for k in range(n)) < sum(len(mine["iou_%d" % k]) for k in range(n))     # something was suppressed
     assert any((mine["eb%d" % k][3] == 0).all() for k in range(n))                                               # the empty channel
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="the reference checkout is only present in the build container")
+def test_oracle_agrees_with_the_reference_graph_functions_on_random_configurations(tmp_path):
+    """The ORACLE against the reference's own graph functions (yolo_custom_loss incl. warm-up, DecodeYOLOLayer,
+    DetectionsLayer, norm_boxes_graph, DetectMaskTargetLayer, PyramidROIAlign, myolo_mask_loss_graph) run live over the
+    numpy stand-in for TensorFlow, on 24 random configurations: grid 2..7, 1..5 anchors, 2..6 classes, buffer 5..12, random
+    loss scales / class weights / anchors, warm-up on and off, images without ground truth."""
+    import torch
+    n = 24
+    out = str(tmp_path / "ref_graph_fuzz.npz")
+    env = dict(os.environ, PYTHONPATH="")
+    subprocess.check_call([sys.executable, os.path.join(HERE, "golden", "make_reference_graph_fixtures.py"), "--fuzz", out, str(n)],
+                          env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    ref = np.load(out)
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import graph_case_inputs as GI
+    from oracle import myolo_oracle as O
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(x))                     # noqa: E731
+    positives = 0
+    for i in range(n):
+        c = GI.build(GI.fuzz_case(i))
+        g = lambda k: ref["%d/%s" % (i, k)]                                     # noqa: E731
+        warm = 3 if i % 3 == 1 else 0
+        cfg = dict(GRID_H=c["G"], GRID_W=c["G"], N_BOX=c["NB"], NUM_CLASSES=c["NC"], ANCHORS=c["ANCHORS"],
+                   TRAIN_ROIS_PER_IMAGE=c["R"], MASK_SHAPE=[28, 28], MASK_POOL_SIZE=14, COORD_SCALE=c["COORD_SCALE"],
+                   NO_OBJECT_SCALE=c["NO_OBJECT_SCALE"], OBJECT_SCALE=c["OBJECT_SCALE"], CLASS_SCALE=c["CLASS_SCALE"],
+                   CLASS_WEIGHTS=np.asarray(c["CLASS_WEIGHTS"], np.float32), WARM_UP_BATCHES=warm, TRUE_BOX_BUFFER=c["TB"])
+        y_pred = t(c["y_pred"])
+        loss = O.yolo_custom_loss(t(c["y_true"]), y_pred, t(c["true_boxes"]), cfg, seen=1.0).item()
+        assert np.isclose(loss, g("yolo_loss"), rtol=2e-5), (i, loss, g("yolo_loss"))
+        scale = max(1.0, float(np.abs(g("proposals")).max()))
+        assert np.allclose(O.decode_yolo(y_pred, cfg).numpy(), g("proposals"), rtol=0, atol=2e-6 * scale), i
+        det = O.detections_layer(y_pred, cfg).numpy()
+        assert np.allclose(det[..., :5], g("detections")[..., :5], rtol=0, atol=2e-6 * scale) and np.array_equal(det[..., 5], g("detections")[..., 5]), i
+        gt_norm = O.norm_boxes_graph(t(c["gt_boxes_px"]), c["S"], c["S"])
+        assert np.allclose(gt_norm.numpy(), g("gt_boxes_norm"), rtol=0, atol=1e-7), i
+        rois, tids, tmasks = O.detect_mask_targets(t(g("proposals")), t(c["gt_class_ids"]), t(g("gt_boxes_norm")), t(c["gt_masks"]), cfg)
+        assert np.array_equal(tids.numpy(), g("target_class_ids")) and np.array_equal(rois.numpy(), g("rois")), i
+        assert np.array_equal(np.packbits(tmasks.numpy().astype(np.uint8)), g("target_masks_bits")), i
+        positives += int((tids.numpy() > 0).sum())
+        pooled = O.pyramid_roi_align(t(g("rois")), t(c["feat"]), 14).numpy()[:, ::7]
+        assert np.allclose(pooled, g("pooled_every7"), rtol=0, atol=5e-6), i
+        ml = O.myolo_mask_loss_graph(tmasks, tids, t(c["pred_masks"])).item()
+        assert np.isclose(ml, g("mask_loss"), rtol=2e-5, atol=1e-7), (i, ml, g("mask_loss"))
+    assert positives > n                                                        # the cases exercise the positive-ROI path
