@@ -108,8 +108,14 @@ def weights(nb, nc, seed):
     return P
 
 
-def net_inputs():
-    c = dict(NET)
+def net_fuzz_case(i):
+    rs = np.random.RandomState(9500 + i)
+    return dict(B=int(rs.randint(1, 3)), S=int(rs.choice([64, 96, 128])), NB=int(rs.choice([1, 2, 3, 5])), NC=int(rs.choice([2, 4, 5])),
+                R=int(rs.randint(3, 9)), seed=9600 + i)
+
+
+def net_inputs(case=None):
+    c = dict(NET if case is None else case)
     rs = np.random.RandomState(c["seed"] + 1)
     c["image"] = rs.uniform(0.0, 1.0, size=(c["B"], c["S"], c["S"], 3)).astype(np.float32)
     F = c["S"] // 8

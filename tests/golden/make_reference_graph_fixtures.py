@@ -293,8 +293,40 @@ def fuzz(path, n):
     np.savez_compressed(path, **out)
 
 
+def fuzz_net(path, n):
+    """Reference side of the live differential test of the graph BUILDERS: n random (batch, image size, anchors, classes)
+    configurations with their own weights, both learning phases."""
+    cases = [GI.net_fuzz_case(i) for i in range(n)]
+    sys.path.insert(0, PRODUCT)
+    try:
+        weights = [GI.weights(c["NB"], c["NC"], c["seed"]) for c in cases]      # before the reference's `myolo` is imported
+    finally:
+        sys.path.remove(PRODUCT)
+        for k in [k for k in sys.modules if k == "myolo" or k.startswith("myolo.") or k == "mrcnn" or k.startswith("mrcnn.")]:
+            del sys.modules[k]
+    M = load_reference_model()
+    out = {}
+    for i, (case, W) in enumerate(zip(cases, weights)):
+        c = GI.net_inputs(case)
+        kls.WEIGHTS.clear()
+        kls.WEIGHTS.update(W)
+
+        class Cfg(object):
+            N_BOX, NUM_CLASSES, GRID_H, GRID_W = c["NB"], c["NC"], c["S"] // 32, c["S"] // 32
+
+        for phase in (1, 0):
+            kls.STATE["learning_phase"] = phase
+            c3 = M.mobilenet_graph(tfs.T(c["image"]), "mobilenet")
+            out["%d/%d/c3" % (i, phase)] = c3.a[..., ::16]
+            out["%d/%d/yolo" % (i, phase)] = M.yolo_branch_graph(c3, Cfg()).a
+            out["%d/%d/masks" % (i, phase)] = M.build_mask_graph(tfs.T(c["rois"]), [tfs.T(c["feat"])], 14, c["NC"], train_bn=False).a[:, ::2, ::3, ::3]
+    np.savez_compressed(path, **out)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) == 4 and sys.argv[1] == "--fuzz":
+    if len(sys.argv) == 4 and sys.argv[1] == "--fuzz-net":
+        fuzz_net(sys.argv[2], int(sys.argv[3]))
+    elif len(sys.argv) == 4 and sys.argv[1] == "--fuzz":
         fuzz(sys.argv[2], int(sys.argv[3]))
     else:
         main()

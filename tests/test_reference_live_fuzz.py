@@ -83,3 +83,36 @@ def test_oracle_agrees_with_the_reference_graph_functions_on_random_configuratio
         ml = O.myolo_mask_loss_graph(tmasks, tids, t(c["pred_masks"])).item()
         assert np.isclose(ml, g("mask_loss"), rtol=2e-5, atol=1e-7), (i, ml, g("mask_loss"))
     assert positives > n                                                        # the cases exercise the positive-ROI path
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="the reference checkout is only present in the build container")
+def test_oracle_agrees_with_the_reference_graph_builders_on_random_configurations(tmp_path):
+    """conv_block + mobilenet_graph, yolo_branch_graph and build_mask_graph of the reference run live (Keras-layer
+    stand-ins, fp64) against the fp64 oracle for 5 random (batch, image size, anchors, classes) configurations, each with
+    its own weights, in both learning phases."""
+    import torch
+    n = 5
+    out = str(tmp_path / "ref_net_fuzz.npz")
+    env = dict(os.environ, PYTHONPATH="")
+    subprocess.check_call([sys.executable, os.path.join(HERE, "golden", "make_reference_graph_fixtures.py"), "--fuzz-net", out, str(n)],
+                          env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    ref = np.load(out)
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import graph_case_inputs as GI
+    from oracle import myolo_oracle as O
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).double()            # noqa: E731
+
+    def close(a, b, tol, what):
+        err, scale = float(np.abs(a - b).max()), max(1.0, float(np.abs(b).max()))
+        assert err <= tol * scale, (what, err, scale)
+
+    for i in range(n):
+        c = GI.net_inputs(GI.net_fuzz_case(i))
+        P = {k: t(v) for k, v in GI.weights(c["NB"], c["NC"], c["seed"]).items()}
+        cfg = dict(GRID_H=c["S"] // 32, GRID_W=c["S"] // 32, N_BOX=c["NB"], NUM_CLASSES=c["NC"], MASK_POOL_SIZE=14)
+        for phase in (1, 0):
+            c3 = O.mobilenet_graph(t(c["image"]), P, bool(phase))
+            close(c3.numpy()[..., ::16], ref["%d/%d/c3" % (i, phase)], 1e-9, (i, phase, "c3"))
+            close(O.yolo_branch_graph(c3, P, cfg, bool(phase)).numpy(), ref["%d/%d/yolo" % (i, phase)], 1e-9, (i, phase, "yolo"))
+            masks = O.build_mask_graph(t(c["rois"]), t(c["feat"]), P, cfg, bool(phase))
+            close(masks.numpy()[:, ::2, ::3, ::3], ref["%d/%d/masks" % (i, phase)], 5e-6, (i, phase, "masks"))
