@@ -284,8 +284,41 @@ def fuzz(path, n):
     np.savez_compressed(path, **fuzz_cases.run(ref, n))
 
 
+SHAPES_FUZZ = ((11, 128, 40), (12, 224, 40), (13, 320, 20), (14, 96, 40))        # (seed, image size, images)
+
+
+def fuzz_shapes(path):
+    """Reference side of the live Shapes test: its own ShapesDataset (seeded `random`) and load_image_gt."""
+    import random
+    load_reference_utils()
+    shp = load_reference_shapes()
+    refu = sys.modules["myolo.myolo_utils"]
+    assert refu.__file__.startswith("/root/reference")
+    out = {}
+    for seed, size, count in SHAPES_FUZZ:
+        class Cfg(shp.ShapesConfig):
+            IMAGE_SHAPE = [size, size, 3]
+        random.seed(seed)
+        ds = shp.ShapesDataset()
+        ds.load_shapes(count, size, size)
+        ds.prepare()
+        for i in ds.image_ids:
+            info = ds.image_info[i]
+            image, class_ids, bbox, mask = refu.load_image_gt(ds, Cfg(), i, use_mini_mask=False)
+            tag = "%d_%d" % (seed, i)
+            out[tag + "_specs"] = np.array([[["square", "circle", "triangle"].index(s[0])] + list(s[1]) + list(s[2]) for s in info["shapes"]],
+                                           dtype=np.int64).reshape(-1, 7)
+            out[tag + "_bg"] = np.asarray(info["bg_color"], dtype=np.int64)
+            out[tag + "_image"] = np.array([image.astype(np.int64).sum(), (image.astype(np.int64) * np.arange(1, size + 1)[:, None, None]).sum()])
+            out[tag + "_ids"], out[tag + "_bbox"] = class_ids, bbox
+            out[tag + "_mask"] = np.packbits(mask.astype(np.uint8))
+    np.savez_compressed(path, **out)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) == 4 and sys.argv[1] == "--fuzz":
+    if len(sys.argv) == 3 and sys.argv[1] == "--fuzz-shapes":
+        fuzz_shapes(sys.argv[2])
+    elif len(sys.argv) == 4 and sys.argv[1] == "--fuzz":
         fuzz(sys.argv[2], int(sys.argv[3]))
     else:
         main()

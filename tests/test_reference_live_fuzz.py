@@ -116,3 +116,65 @@ def test_oracle_agrees_with_the_reference_graph_builders_on_random_configuration
             close(O.yolo_branch_graph(c3, P, cfg, bool(phase)).numpy(), ref["%d/%d/yolo" % (i, phase)], 1e-9, (i, phase, "yolo"))
             masks = O.build_mask_graph(t(c["rois"]), t(c["feat"]), P, cfg, bool(phase))
             close(masks.numpy()[:, ::2, ::3, ::3], ref["%d/%d/masks" % (i, phase)], 5e-6, (i, phase, "masks"))
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="the reference checkout is only present in the build container")
+def test_shapes_dataset_and_device_raster_rule_agree_with_the_reference_dataset(tmp_path):
+    """140 images of the reference's own ShapesDataset (seeded `random`, four image sizes) through its own load_image_gt,
+    against (1) the package's ShapesDataset + load_image_gt and (2) the owner-per-pixel rule of the DEVICE rasteriser
+    evaluated in numpy over the g++ build of csrc/shapes_extents.h -- specs, images, class ids, boxes and every mask bit."""
+    out = str(tmp_path / "ref_shapes_fuzz.npz")
+    env = dict(os.environ, PYTHONPATH="")
+    subprocess.check_call([sys.executable, os.path.join(HERE, "golden", "make_reference_fixtures.py"), "--fuzz-shapes", out],
+                          env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    ref = np.load(out)
+    import ctypes
+    from myolo import myolo_utils as U
+    from myolo.shapes import ShapesConfig, ShapesDataset
+    so = str(tmp_path / "shapes_extents_host.so")
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-I", os.path.join(os.path.dirname(HERE), "mask-yolo_b200", "csrc"),
+                           os.path.join(HERE, "shapes_extents_harness.cpp"), "-o", so])
+    lib = ctypes.CDLL(so)
+    lib.shape_rows_host.argtypes = [ctypes.c_int] * 6 + [ctypes.c_void_p] * 2
+    lib.shape_rows_host.restype = None
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    from make_reference_fixtures import SHAPES_FUZZ
+    n_img = n_tri = 0
+    for seed, size, count in SHAPES_FUZZ:
+        class Cfg(ShapesConfig):
+            IMAGE_SHAPE = [size, size, 3]
+            IMAGE_MIN_DIM = IMAGE_MAX_DIM = size
+        ds = ShapesDataset(seed)
+        ds.load_shapes(count, size, size)
+        ds.prepare()
+        weights = np.arange(1, size + 1)[:, None, None]
+        for i in ds.image_ids:
+            tag, info = "%d_%d" % (seed, i), ds.image_info[i]
+            specs = np.array([[["square", "circle", "triangle"].index(s[0])] + list(s[1]) + list(s[2]) for s in info["shapes"]],
+                             dtype=np.int64).reshape(-1, 7)
+            assert np.array_equal(specs, ref[tag + "_specs"]) and list(info["bg_color"]) == ref[tag + "_bg"].tolist(), tag
+            image, class_ids, bbox, mask = U.load_image_gt(ds, Cfg(), i, use_mini_mask=False)
+            chk = lambda im: [im.astype(np.int64).sum(), (im.astype(np.int64) * weights).sum()]        # noqa: E731
+            assert chk(image) == ref[tag + "_image"].tolist() and np.array_equal(class_ids, ref[tag + "_ids"]), tag
+            assert np.array_equal(bbox, ref[tag + "_bbox"]) and np.array_equal(np.packbits(mask.astype(np.uint8)), ref[tag + "_mask"]), tag
+            # the device rule: owner = last shape covering the pixel
+            owner = np.full((size, size), -1, np.int32)
+            cols = np.arange(size)[None, :]
+            for k, (t, _, _, _, x, y, s) in enumerate(specs.tolist()):
+                lo, hi = np.empty(size, np.int32), np.empty(size, np.int32)
+                lib.shape_rows_host(t + 1, x, y, s, size, size, lo.ctypes.data, hi.ctypes.data)
+                owner[(cols >= lo[:, None]) & (cols <= hi[:, None])] = k
+                n_tri += t == 2
+            img2 = np.empty((size, size, 3), np.uint8)
+            img2[:] = np.asarray(info["bg_color"], np.uint8)
+            keep = []
+            for k, row in enumerate(specs.tolist()):
+                img2[owner == k] = row[1:4]
+                if (owner == k).any():
+                    keep.append(k)
+            assert chk(img2) == ref[tag + "_image"].tolist(), tag
+            m2 = np.stack([owner == k for k in keep], -1) if keep else np.zeros((size, size, 0), bool)
+            assert np.array_equal(np.packbits(m2.astype(np.uint8)), ref[tag + "_mask"]), tag
+            assert [specs[k][0] + 1 for k in keep] == ref[tag + "_ids"].tolist(), tag
+            n_img += 1
+    assert n_img == 140 and n_tri > 40
