@@ -1,11 +1,19 @@
 #!/usr/bin/env python
 """Mask-YOLO benchmark: images/sec of one full training step (forward, both losses, backward, Adam,
-BN moving update) on synthetic Shapes 224x224, per-GPU batch 32 (BASELINE.json configs[1]; weak
-scaling across GPUs, configs[3]).  Prints ONE JSON line (contract in the task statement).
+BN moving update).  Prints ONE JSON line (contract in the task statement).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]           our arm (sm_100a engine)
-  python bench.py --impl reference ...                           the reference's algorithm on the host CPU
+  python bench.py [--gpus N] [--steps K] [--warmup W]           our arm (sm_100a engine), BASELINE.json configs[1]:
+                                                                 Shapes 224x224, per-GPU batch 32 (weak scaling, configs[3])
+  python bench.py --config c3|c5 ...                             configs[2]: rice-like 416x416 batch 16, NC=2, R=845 dense ROIs
+                                                                 configs[4]: COCO-shape 640x640 batch 8/GPU, NC=81, R=2000
+  python bench.py --impl reference ...                           the reference's algorithm on the host CPU, full batch per step
                                                                  (oracle port: the Keras/TF code cannot run here)
+
+Our arm times the headline precision (`h16`) and, in the same invocation, the fp32-class mode (`tf32x3`) -> `fp32_class`.
+`value` = device-timed steps on batches resident in HBM; `e2e` = the public fit loop (MaskYOLO.fit_batches, the body of
+MaskYOLO.train) fed numpy batches as BatchGenerator yields them: conversion into pinned memory, host->device copy and the
+device->host read of the losses of EVERY step inside the timed region; `e2e_train_on_batch` = the same through the strictly
+synchronous keras_model.train_on_batch(numpy batch) call.
 """
 import argparse
 import json
@@ -24,6 +32,12 @@ import numpy as np
 import torch
 
 METRIC = "images/sec fwd+bwd @224x224 Shapes"
+WORKLOADS = {
+    # name: (image side, per-GPU batch, description)
+    "c2": (224, 32, "Shapes 224x224 batch 32/GPU, MobileNet+YOLO+ROIAlign+mask fwd+bwd+Adam"),
+    "c3": (416, 16, "synthetic rice-like 416x416 batch 16/GPU (2 classes, 5 anchors, 845 dense ROIs/image), fwd+bwd+Adam"),
+    "c5": (640, 8, "synthetic COCO-shape 640x640 batch 8/GPU (81 classes, 5 anchors, 2000 ROIs/image), fwd+bwd+Adam"),
+}
 
 
 def parse():
@@ -32,25 +46,102 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="per-GPU batch")
-    ap.add_argument("--size", type=int, default=224)
+    ap.add_argument("--config", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: the config's)")
+    ap.add_argument("--size", type=int, default=None)
     ap.add_argument("--precision", default=os.environ.get("MYOLO_PRECISION", "h16"))
+    ap.add_argument("--no-fp32-class", action="store_true", help="skip the second (tf32x3) timing")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
-    return ap.parse_args()
+    a = ap.parse_args()
+    S, B, _ = WORKLOADS[a.config]
+    a.size = a.size or S
+    a.batch = a.batch or B
+    return a
 
 
-def bench_config(batch, size):
+# ------------------------------------------------------------------------------------------------ workloads
+def bench_config(batch, size, name="c2"):
+    """Config instance of a workload (the reference's Config schema)."""
+    from myolo.config import Config
     from myolo.shapes import ShapesConfig
+    if name == "c2":
+        class BenchConfig(ShapesConfig):
+            BATCH_SIZE = batch
+            IMAGE_SHAPE = [size, size, 3]
+            IMAGE_MIN_DIM = IMAGE_MAX_DIM = size
+            GRID_H = GRID_W = size // 32
+        return BenchConfig()
+    nc = 2 if name == "c3" else 81              # example/rice/rice_dataset.py:60-82 (background + rice); COCO 80 + background
 
-    class BenchConfig(ShapesConfig):
+    class BigConfig(Config):                     # base Config: 5 anchors, TRUE_BOX_BUFFER 10, MAX_GT_INSTANCES 10
+        NAME = "rice_like" if name == "c3" else "coco_shape"
         BATCH_SIZE = batch
+        NUM_CLASSES = nc
         IMAGE_SHAPE = [size, size, 3]
         IMAGE_MIN_DIM = IMAGE_MAX_DIM = size
         GRID_H = GRID_W = size // 32
+        N_BOX = 5
+        TRAIN_ROIS_PER_IMAGE = (size // 32) ** 2 * 5
+        CLASS_WEIGHTS = np.ones(nc, dtype="float32")
+    return BigConfig()
 
-    return BenchConfig()
+
+def init_weights(c, name):
+    """Random 'trained-like' weights (no checkpoints offline).  For the dense-ROI workloads the detection head is damped
+    so that the decoded proposals sit near the anchor priors, which is what the ground truth below is laid on."""
+    from myolo.engine import init_params
+    P = init_params(c["NB"], c["NC"], 0, "trained_like")
+    if name != "c2":
+        P["conv_23/kernel"] = P["conv_23/kernel"] * 0.05
+        P["conv_23/bias"] = torch.zeros_like(P["conv_23/bias"])
+    return P
+
+
+def make_host_batches(cfg, name, n_batches, seed):
+    """`n_batches` training batches as lists of numpy arrays in BatchGenerator's format and dtypes."""
+    from myolo.config import resolve
+    if name == "c2":
+        from myolo.shapes import make_batches
+        return make_batches(cfg, n_batches, seed=seed)
+    from tests import helpers as Hh
+    c = dict(resolve(cfg))
+    B, S, G, NB = int(cfg.BATCH_SIZE), c["S"], c["G"], c["NB"]
+    anc = np.asarray(c["ANCHORS"], np.float64).reshape(NB, 2)
+    out = []
+    for k in range(n_batches):
+        rng = np.random.RandomState(seed + 17 * k)
+        image = torch.from_numpy(rng.rand(B, S, S, 3).astype(np.float32))
+        boxes = []
+        for b in range(B):
+            bl = []
+            for m in range(c["MAXGT"] - (b % 3 if name == "c3" else 0)):          # c3: 8-10 instances per image
+                if name == "c3":
+                    # elongated grains on the anchor priors of a random cell (the two largest anchors): every prior of the
+                    # neighbourhood overlaps them -> dense positives
+                    a = anc[NB - 1 - (m % 2)] * (1.0 + 0.1 * (rng.rand(2) - 0.5)) * np.array([1.0, 0.8 + 0.4 * rng.rand()])
+                    cx, cy = (rng.randint(2, G - 2, 2) + 0.5) / G
+                    w, h = a / G
+                else:
+                    cx, cy = rng.rand(2) * 0.7 + 0.15
+                    w, h = rng.rand(2) * 0.35 + 0.05
+                bl.append([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2])
+            boxes.append(bl)
+        t = Hh.batch_from_boxes(c, B, image, boxes, seed + 17 * k + 1)
+        t[1], t[2] = t[1].double(), t[2].double()                                   # BatchGenerator yields float64 here
+        out.append([x.numpy() if x.dtype != torch.uint8 else x.numpy().astype(bool) for x in t])
+    return out
+
+
+def workload_config(args, c, world):
+    """The `config` object of the JSON line: identical for both arms (same workload, metric and unit)."""
+    return {"workload": WORKLOADS[args.config][2] if (args.size, args.batch) == WORKLOADS[args.config][:2]
+            else f"{args.config} at {args.size}x{args.size} batch {args.batch}/GPU",
+            "name": args.config, "image_size": args.size, "per_gpu_batch": args.batch, "global_batch": args.batch * world,
+            "N_BOX": c["NB"], "NUM_CLASSES": c["NC"], "rois_per_image": c["R"], "parallelism": f"dp{world}",
+            "l2": "activations per step (>10 GB) exceed the 126 MB L2; no explicit flush",
+            "weights": "random trained-like init (no checkpoints offline)"}
 
 
 def peaks():
@@ -96,23 +187,31 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
-def oracle_step_fn(cfg, batch_np, nimg):
-    """Closure running oracle.train_step (fwd+bwd+Adam+BN update) on the first `nimg` images."""
+# ------------------------------------------------------------------------------------------------ CPU legs (oracle)
+def oracle_inputs(batch_np, nimg):
+    return [torch.from_numpy(np.ascontiguousarray(batch_np[0][:nimg])).float(), torch.from_numpy(np.asarray(batch_np[1][:nimg])).float(),
+            torch.from_numpy(np.asarray(batch_np[2][:nimg])).float(), torch.from_numpy(np.asarray(batch_np[3][:nimg])),
+            torch.from_numpy(np.asarray(batch_np[4][:nimg])).float(), torch.from_numpy(np.asarray(batch_np[5][:nimg])).bool()]
+
+
+def oracle_step_fn(cfg, batch_np, nimg, name="c2"):
+    """Closure running oracle.train_step (fwd+bwd+Adam+BN update) on the first `nimg` images; every call starts from the
+    same initial weights.  Returns (closure, initial weights)."""
     from myolo.config import resolve
-    from myolo.engine import init_params
     from oracle import myolo_oracle as O
     from tests import helpers as Hh
     c = resolve(cfg)
     oc = Hh.oracle_cfg(c)
-    P = init_params(c["NB"], c["NC"], 0, "trained_like")
-    x = [torch.from_numpy(np.ascontiguousarray(batch_np[0][:nimg])), torch.from_numpy(batch_np[1][:nimg]).float(),
-         torch.from_numpy(batch_np[2][:nimg]).float(), torch.from_numpy(batch_np[3][:nimg]),
-         torch.from_numpy(batch_np[4][:nimg]).float(), torch.from_numpy(batch_np[5][:nimg]).bool()]
-    opt = {}
-    return lambda: O.train_step(P, opt, x, oc, lr=1e-3)
+    P0 = init_weights(c, name)
+    x = oracle_inputs(batch_np, nimg)
+
+    def step():
+        P = {k: v.clone() for k, v in P0.items()}
+        return O.train_step(P, {}, x, oc, lr=1e-3)
+    return step, P0
 
 
-def cpu_flops_per_image(c):
+def flops_per_image(c):
     n_roi = c["R"]
     mask = 4 * 2 * 196 * 2304 * 256 * n_roi + 2 * 196 * 256 * 1024 * n_roi + 2 * 784 * 256 * c["NC"] * n_roi
     back = (1.263e9 + 1.85e9) * (c["S"] / 224.0) ** 2
@@ -120,19 +219,19 @@ def cpu_flops_per_image(c):
 
 
 def run_reference(args):
-    """Reference arm: the reference's algorithm (oracle port; Keras/TF 1.x is not installable here) on
-    the host cores, bounded sample per step."""
+    """Reference arm: the reference's algorithm (oracle port; Keras/TF 1.x is not installable here) on the host cores
+    with every thread torch can use, on the FULL per-GPU batch of the workload each step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from myolo.shapes import make_batches
-    cfg = bench_config(4, args.size)
-    batch = make_batches(cfg, 1, seed=1234)[0]
+    from myolo.config import resolve
+    cfg = bench_config(args.batch, args.size, args.config)
+    c = resolve(cfg)
+    batch = make_host_batches(cfg, args.config, 1, seed=1234)[0]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    t0 = time.perf_counter(); oracle_step_fn(cfg, batch, 1)(); t1 = time.perf_counter() - t0
-    nimg = int(max(1, min(4, 150.0 / (max(t1, 1e-3) * (args.steps + args.warmup)))))
-    step = oracle_step_fn(cfg, batch, nimg)
+    nimg = args.batch
+    step, _ = oracle_step_fn(cfg, batch, nimg, args.config)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -140,48 +239,32 @@ def run_reference(args):
         step()
     dt = time.perf_counter() - t0
     v = nimg * args.steps / dt
-    from myolo.config import resolve
-    c = resolve(cfg)
-    sample = f"{args.steps} oracle.train_step calls on {nimg} image(s) of the {args.size}x{args.size} Shapes workload (NB={c['NB']}, NC={c['NC']}, R={c['R']})"
+    sample = f"{args.steps} oracle.train_step calls (fwd+bwd+Adam, torch CPU fp32, {cores} threads) on the full batch of {nimg} " \
+             f"images of the workload (NB={c['NB']}, NC={c['NC']}, R={c['R']})"
     print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "images/sec", "n_gpus": args.gpus,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
                       "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                      "config": {"workload": f"Shapes {args.size}x{args.size} batch {args.batch}/GPU, MobileNet+YOLO+ROIAlign+mask fwd+bwd+Adam",
-                                 "global_batch": args.batch * args.gpus, "N_BOX": c["NB"], "NUM_CLASSES": c["NC"],
-                                 "rois_per_image": c["R"], "precision": "fp32 (torch CPU)", "parallelism": "host CPU threads",
-                                 "sample_images_per_step": nimg,
-                                 "note": "the same workload as the GPU arm; each step is a bounded sample of it (per-image work "
-                                         "is independent except for BatchNorm statistics)"},
+                      "config": workload_config(args, c, args.gpus),
+                      "sample_images_per_step": nimg,
+                      "note": "rank 0 only: one host runs the reference's CPU path on one per-GPU batch per step",
                       "cpu_baseline": {"value": v, "unit": "images/sec", "cores": cores, "kind": "port", "sample": sample},
                       "e2e": {"value": v, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
-def main():
-    args = parse()
-    if args.impl == "reference":
-        return run_reference(args)
+# ------------------------------------------------------------------------------------------------ our arm
+def time_precision(args, precision, cfg, host_batches, world, rank, local, with_kernel_events):
+    """Build the model in `precision`, time K device-resident steps (CUDA events) and the end-to-end loops."""
     import torch.distributed as dist
     from myolo import _cabi as C
     from myolo import ddp
     from myolo.model import MaskYOLO
-    from myolo.shapes import make_batches
-    from myolo.engine import init_params
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    cfg = bench_config(args.batch, args.size)
-    model = MaskYOLO("training", cfg, precision=args.precision, device=local)
+    model = MaskYOLO("training", cfg, precision=precision, device=local)
     eng = model.engine
     c = eng.cfg
-    eng.load_params(init_params(c["NB"], c["NC"], 0, "trained_like"))
+    eng.load_params(init_weights(c, args.config))
     if world > 1:
         ddp.attach(model)
-    pool = 3
-    host_batches = make_batches(cfg, pool, seed=1234 + rank)
+    pool = len(host_batches)
     dev_batches = []
     for hb in host_batches:
         staged = model._stage(hb)
@@ -197,15 +280,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- dominant-kernel timing hooks: the 9-tap tcgen05 GEMM of the mask-head 3x3 convolutions
     eng.kernel_events = []
     for i in range(W):
         eng.train_step(dev_batches[i % pool], 1e-3, model.allreduce)
-    eng.kernel_events = []
+    eng.kernel_events = [] if with_kernel_events else None
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
-    time.sleep(0.25)
     launches0 = C.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -215,89 +294,182 @@ def main():
     barrier()
     launches = C.launch_count - launches0
     ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
-    kev = list(eng.kernel_events)
+    kev = list(eng.kernel_events or [])
     eng.kernel_events = None
     npos = int(eng.n_pos.sum().item())
-    # ---- end to end through the public API: host numpy batch -> pinned -> H2D -> step -> D2H losses
-    e2e = None
+    res = {"precision": precision, "launches": launches, "kev": kev, "npos": npos,
+           "loss": [float(out["yolo_sum_loss"]), float(out["mask_loss"])]}
+    # ---- end to end: numpy batches (BatchGenerator's dtypes) -> pinned staging -> H2D -> step -> D2H losses, every step
     if not args.no_e2e:
         torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))
-        host_batches = [model.pin_inputs(hb) for hb in host_batches]     # the inputs live in pinned host memory
-        for i in range(2):
-            model.keras_model.train_on_batch(host_batches[i % pool])
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(K):
-            vals = model.keras_model.train_on_batch(host_batches[i % pool])
-        torch.cuda.synchronize()
-        dt = torch.tensor([time.perf_counter() - t0], device="cuda")
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": B * world * K / dt.item(), "unit": "images/sec", "h2d_bytes_per_step": int(model.last_h2d_bytes),
-               "d2h_bytes_per_step": int(model.last_d2h_bytes), "ms_per_step": 1e3 * dt.item() / K}
-    clocks = sampler.stop()
+
+        def timed(run):
+            run(2)
+            barrier()
+            t0 = time.perf_counter()
+            run(K)
+            torch.cuda.synchronize()
+            dt = torch.tensor([time.perf_counter() - t0], device="cuda")
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            return dt.item()
+
+        def run_fit(n):
+            for _ in model.fit_batches(host_batches[i % pool] for i in range(n)):
+                pass
+
+        def run_sync(n):
+            for i in range(n):
+                model.keras_model.train_on_batch(host_batches[i % pool])
+
+        dt = timed(run_fit)
+        res["e2e"] = {"value": B * world * K / dt, "unit": "images/sec", "h2d_bytes_per_step": int(model.last_h2d_bytes),
+                      "d2h_bytes_per_step": int(model.last_d2h_bytes), "ms_per_step": 1e3 * dt / K,
+                      "path": "MaskYOLO.fit_batches (the fit loop of MaskYOLO.train) over numpy batches: host conversion into pinned "
+                              "staging + H2D + step + D2H of the losses, every step; losses of step k read after step k+1 is enqueued"}
+        dt = timed(run_sync)
+        res["e2e_train_on_batch"] = {"value": B * world * K / dt, "unit": "images/sec", "ms_per_step": 1e3 * dt / K,
+                                     "path": "keras_model.train_on_batch(numpy batch), synchronous per step"}
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_step = ms.item() / K
-    value = B * world * K / (ms.item() / 1e3)
+    res["ms_total"] = ms.item()
+    res["ms_per_step"] = ms.item() / K
+    res["value"] = B * world * K / (ms.item() / 1e3)
+    res["n_roi"] = eng.n_roi
+    res["cfg"] = c
+    del model, eng, dev_batches
+    torch.cuda.empty_cache()
+    return res
+
+
+def parity_leg(args, cfg, batch_np, nimg, precisions, want_cpu):
+    """One oracle.train_step on the first `nimg` images of the workload's first batch -- timed (cpu_baseline) and used
+    as the checker for one step of the engine from the same weights (parity): outside every GPU-timed region."""
+    from myolo.config import resolve
+    from myolo.model import MaskYOLO
+    from tests import helpers as Hh
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step, P0 = oracle_step_fn(cfg, batch_np, nimg, args.config)
+    t0 = time.perf_counter()
+    oout, _ = step()
+    dt, n = time.perf_counter() - t0, 1
+    if dt < 8.0:                                         # small sample: repeat for a steadier rate
+        t0 = time.perf_counter()
+        while n < 4 and time.perf_counter() - t0 < 16:
+            step(); n += 1
+        dt = (time.perf_counter() - t0) / max(n - 1, 1) if n > 1 else dt
+    c = resolve(cfg)
+    cpu = {"value": nimg / dt, "unit": "images/sec", "cores": cores, "kind": "port",
+           "sample": f"oracle.train_step (fwd+bwd+Adam, torch CPU fp32) on {nimg} image(s) of the workload's first batch "
+                     f"({args.size}x{args.size}, NB={c['NB']}, NC={c['NC']}, R={c['R']}), {n} call(s)"} if want_cpu else None
+    parity = {}
+    if args.no_parity:
+        return cpu, None
+    sub_cfg = bench_config(nimg, args.size, args.config)
+    sub = [np.ascontiguousarray(x[:nimg]) for x in batch_np]
+    for prec in precisions:
+        try:
+            model = MaskYOLO("training", sub_cfg, precision=prec)
+            model.engine.load_params(P0)
+            vals = model.keras_model.train_on_batch(sub)
+            torch.cuda.synchronize()
+            dev = model.last_outputs
+            dm = (dev["myolo_mask"].cpu() - oout["myolo_mask"]).abs()
+            biou = Hh.box_iou_pairs(dev["yolo_proposals"], oout["yolo_proposals"])
+            miou = Hh.mask_iou(dev["myolo_mask"], oout["myolo_mask"])
+            parity[prec] = {
+                "box_iou_mean": biou.mean().item(), "box_iou_min": biou.min().item(),
+                "mask_iou_mean": miou.mean().item(), "mask_iou_min": miou.min().item(),
+                "max_abs_box_err": (dev["yolo_proposals"].cpu() - oout["yolo_proposals"]).abs().max().item(),
+                "max_abs_class_score_err": (dev["yolo_output"].cpu() - oout["yolo_output"]).abs().max().item(),
+                "max_abs_mask_err": dm.max().item(), "mask_elements_off_by_1e-3": (dm > 1e-3).float().mean().item(),
+                "roi_selection_identical": bool(torch.equal(dev["target_class_ids"].cpu(), oout["target_class_ids"])),
+                "positive_rois": int((oout["target_class_ids"] > 0).sum().item()),
+                "loss": vals[0], "oracle_loss": oout["loss"].item()}
+            del model
+            torch.cuda.empty_cache()
+        except Exception as e:                      # never lose the throughput line to the side check
+            parity[prec] = {"error": repr(e)[:200]}
+    parity["against"] = f"oracle.train_step (CPU restatement of the reference path) on {nimg} image(s) of the benchmark workload, one step"
+    return cpu, parity
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cfg = bench_config(args.batch, args.size, args.config)
+    host_batches = make_host_batches(cfg, args.config, 3, seed=1234 + rank)
+    K, W = args.steps, args.warmup
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.25)
+    main_res = time_precision(args, args.precision, cfg, host_batches, world, rank, local, True)
+    clocks = sampler.stop()
+    fp32 = None
+    if not args.no_fp32_class and args.precision != "tf32x3":
+        r2 = time_precision(args, "tf32x3", cfg, host_batches, world, rank, local, False)
+        fp32 = {"precision": "tf32x3", "dtype": "3xTF32 forward GEMMs (fp32-grade), tf32 backward GEMMs, f32 accumulate/epilogues",
+                "value": r2["value"], "unit": "images/sec", "ms_per_step": r2["ms_per_step"],
+                "e2e": r2.get("e2e"), "e2e_train_on_batch": r2.get("e2e_train_on_batch"), "gpu_launches": r2["launches"],
+                "loss": r2["loss"]}
+    c = main_res["cfg"]
     # ---- roofline of the dominant kernel
     pk, pk_src = peaks()
     roof = None
+    kev = main_res["kev"]
     if kev:
         durs = [a.elapsed_time(b) for a, b in kev]
         avg_ms = float(np.mean(durs))
-        flops = 2.0 * eng.n_roi * 196 * 2304 * 256
+        flops = 2.0 * main_res["n_roi"] * 196 * 2304 * 256
         ach = flops / (avg_ms * 1e-3) / 1e12
-        traffic = None
+        traffic, traffic_src = None, None
+        h16 = args.precision == "h16"
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(
-                "mask_conv_fwd_h16_dram_bytes_per_launch" if args.precision == "h16" else "mask_conv_fwd_dram_bytes_per_launch")
+            tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+            key = "mask_conv_fwd_h16" if h16 else "mask_conv_fwd"
+            per_roi = tj.get(key + "_dram_bytes_per_roi")
+            if per_roi is not None:
+                traffic, traffic_src = per_roi * main_res["n_roi"], tj.get("source")
+            elif args.config == "c2":
+                traffic, traffic_src = tj.get(key + "_dram_bytes_per_launch"), tj.get("source_h16" if h16 else "source")
         except Exception:
             pass
-        h16 = args.precision == "h16"
         roof = {"kernel": "tc_conv_win_kernel<256> (mask-head 3x3 conv forward, persistent 9-tap tcgen05 kind::%s, CTA pairs)" % ("f16" if h16 else "tf32"),
                 "bound": "tensor", "achieved": ach,
                 "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"],
-                "traffic": traffic, "avg_launch_ms": avg_ms, "launches_timed": len(durs), "algorithmic_flops_per_launch": flops,
+                "traffic": traffic, "traffic_source": traffic_src, "avg_launch_ms": avg_ms, "launches_timed": len(durs),
+                "algorithmic_flops_per_launch": flops,
                 "peak_source": pk_src + (" bf16 sustained (kind::f16 runs at the bf16 rate)" if h16 else
                                          " bf16 sustained (tf32 runs at half the bf16 tensor rate: nominal 1.1 vs 2.25 PFLOP/s)"),
-                "step_share": sum(durs) / ms.item()}
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
-        step = oracle_step_fn(cfg, [t.numpy() if torch.is_tensor(t) else t for t in host_batches[0]], 2)
-        step()
-        t0 = time.perf_counter(); n = 0
-        while n < 3 and time.perf_counter() - t0 < 20:
-            step(); n += 1
-        dt = time.perf_counter() - t0
-        cpu = {"value": 2 * n / dt, "unit": "images/sec", "cores": cores, "kind": "port",
-               "sample": f"{n} oracle.train_step calls (fwd+bwd+Adam, torch CPU fp32) on 2 images of the same {args.size}x{args.size} Shapes batch"}
-    parity = None
-    if rank == 0 and not args.no_parity:
-        # BASELINE.json's metric carries "box+mask IoU vs ref": one small step of the same engine / precision against the
-        # CPU restatement of the reference path, outside the timed region (the oracle is the checker, never the thing timed)
-        try:
-            import __graft_entry__ as entry
-            parity = entry.parity_metrics(args.precision)
-        except Exception as e:                      # never lose the throughput line to the side check
-            parity = {"error": repr(e)[:200]}
+                "step_share": sum(durs) / main_res["ms_total"]}
+    cpu = parity = None
+    if rank == 0 and (not args.no_cpu_baseline or not args.no_parity):
+        nimg = args.batch if args.config == "c2" else 2
+        precs = [args.precision] + (["tf32x3"] if fp32 is not None else [])
+        cpu, parity = parity_leg(args, cfg, host_batches[0], nimg, precs, world == 1 and not args.no_cpu_baseline)
     if rank == 0:
-        fl = cpu_flops_per_image(c)
+        fl = flops_per_image(c)
+        value = main_res["value"]
         line = {"metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": main_res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": {"fp32": "f32", "h16": "f16 operands (mask head) / 3xtf32 (backbone), f32 accumulate"}.get(args.precision, "tf32"),
-                "data": "synthetic",
-                "config": {"workload": f"Shapes {args.size}x{args.size} batch {B}/GPU, MobileNet+YOLO+ROIAlign+mask fwd+bwd+Adam",
-                           "global_batch": B * world, "N_BOX": c["NB"], "NUM_CLASSES": c["NC"], "rois_per_image": c["R"],
-                           "precision": args.precision, "positive_rois_last_step": npos, "parallelism": f"dp{world}",
-                           "l2": "activations per step (>10 GB) exceed the 126 MB L2; no explicit flush",
-                           "weights": "random trained-like init (no checkpoints offline)"},
-                "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-                "parity": parity,
+                "data": "synthetic", "config": workload_config(args, c, world), "precision": args.precision,
+                "positive_rois_last_step": main_res["npos"],
+                "e2e": main_res.get("e2e"), "e2e_train_on_batch": main_res.get("e2e_train_on_batch"),
+                "gpu_launches": main_res["launches"], "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+                "fp32_class": fp32, "parity": parity,
                 "model_tflops_per_s": value * fl / 1e12, "frac_of_conv_roofline": value * fl / 1e12 / pk["bf16_tflops_sustained"],
-                "loss": [float(out["yolo_sum_loss"]), float(out["mask_loss"])]}
+                "loss": main_res["loss"]}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

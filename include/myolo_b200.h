@@ -369,6 +369,11 @@ int myolo_allreduce_destroy(void* comm);
 /* ---- K17: Keras Adam, myolo/model.py:1071-1075 ----  lr_t = lr*sqrt(1-b2^t)/(1-b1^t) computed by caller */
 int myolo_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr_t,
                     float b1, float b2, float eps, float grad_scale, myolo_stream stream);
+/* the same update restricted to the variables Keras would hand the optimizer: `trainable[i]` is 1 for elements of
+ * trainable variables and 0 for frozen ones (MaskYOLO.set_trainable, model.py:1120-1155; yolo_trainable=False,
+ * model.py:854-868); a frozen element keeps p, m and v bit-for-bit. */
+int myolo_adam_step_masked(float* p, const float* g, float* m, float* v, const float* trainable, long long n,
+                           float lr_t, float b1, float b2, float eps, float grad_scale, myolo_stream stream);
 
 #ifdef __cplusplus
 }

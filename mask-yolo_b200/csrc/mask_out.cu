@@ -221,9 +221,12 @@ mask_out_bwd_kernel(const float* __restrict__ y4, const float* __restrict__ bd, 
 
 // Keras Adam (optimizers.py, Keras 2.x): m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ;
 // p -= lr_t * m / (sqrt(v) + eps), lr_t = lr sqrt(1-b2^t)/(1-b1^t) folded by the caller.
+// MASKED: `mask` (1 = trainable, 0 = frozen) is read per element; a frozen element keeps p, m and v untouched (Keras
+// leaves non-trainable weights out of the optimizer's update list altogether, model.py:1120-1155).
+template <bool MASKED>
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-            long long n, float lr_t, float b1, float b2, float eps, float gs) {
+            const float* __restrict__ mask, long long n, float lr_t, float b1, float b2, float eps, float gs) {
   const long long n4 = n >> 2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 pp = reinterpret_cast<float4*>(p)[i];
@@ -234,8 +237,15 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     const float* G = &gg.x;
     float* M = &mm.x;
     float* V = &vv.x;
+    float4 kk = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (MASKED) {
+      kk = reinterpret_cast<const float4*>(mask)[i];
+      if (kk.x == 0.f && kk.y == 0.f && kk.z == 0.f && kk.w == 0.f) continue;
+    }
+    const float* Kp = &kk.x;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
+      if (MASKED && Kp[e] == 0.f) continue;
       const float ge = G[e] * gs;
       M[e] = b1 * M[e] + (1.f - b1) * ge;
       V[e] = b2 * V[e] + (1.f - b2) * ge * ge;
@@ -247,6 +257,7 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   }
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
     const long long i = (n4 << 2) + threadIdx.x;
+    if (MASKED && mask[i] == 0.f) return;
     const float ge = g[i] * gs;
     const float me = b1 * m[i] + (1.f - b1) * ge;
     const float ve = b2 * v[i] + (1.f - b2) * ge * ge;
@@ -358,7 +369,17 @@ extern "C" int myolo_adam_step(float* p, const float* g, float* m, float* v, lon
   MYOLO_CHECK_ARG(p && g && m && v && n > 0);
   MYOLO_CHECK_ARG((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0);
   const int blocks = (int)max(1LL, min(ceil_div(n / 4 + 1, 256), (long long)kNumSMs * 8));
-  adam_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p, g, m, v, n, lr_t, b1, b2, eps, grad_scale);
+  adam_kernel<false><<<blocks, 256, 0, as_stream(stream)>>>(p, g, m, v, nullptr, n, lr_t, b1, b2, eps, grad_scale);
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
+}
+
+extern "C" int myolo_adam_step_masked(float* p, const float* g, float* m, float* v, const float* trainable, long long n,
+                                      float lr_t, float b1, float b2, float eps, float grad_scale, myolo_stream stream) {
+  MYOLO_CHECK_ARG(p && g && m && v && trainable && n > 0);
+  MYOLO_CHECK_ARG((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)trainable) & 15) == 0);
+  const int blocks = (int)max(1LL, min(ceil_div(n / 4 + 1, 256), (long long)kNumSMs * 8));
+  adam_kernel<true><<<blocks, 256, 0, as_stream(stream)>>>(p, g, m, v, trainable, n, lr_t, b1, b2, eps, grad_scale);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }

@@ -36,21 +36,25 @@ detect_select_kernel(const float* __restrict__ det, int R, int S, int top_k, flo
   __shared__ int ncand;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
   const float* D = det + (size_t)b * R * 6;
-  for (int r = tid; r < R; r += blockDim.x) sc[r] = D[(size_t)r * 6 + 4];
+  // decode_masks drops boxes without area before anything is ranked (model.py:1367-1375)
+  for (int r = tid; r < R; r += blockDim.x) {
+    const float* p = D + (size_t)r * 6;
+    sc[r] = ((p[2] - p[0]) * (p[3] - p[1]) <= 0.f) ? -CUDART_INF_F : p[4];
+  }
   if (tid == 0) ncand = 0;
   __syncthreads();
-  for (int k = 0; k < top_k; ++k) {                 // k-th largest score, lowest index on ties
+  for (int k = 0; k < top_k; ++k) {                 // k-th largest score; HIGHEST index on ties (np.argsort(scores)[::-1])
     float bv = -CUDART_INF_F;
     int bi = -1;
     for (int r = tid; r < R; r += blockDim.x) {
       const float v = sc[r];
-      if (v > bv) { bv = v; bi = r; }
+      if (v >= bv) { bv = v; bi = r; }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
       const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ov > bv || (ov == bv && oi >= 0 && (bi < 0 || oi < bi))) { bv = ov; bi = oi; }
+      if (ov > bv || (ov == bv && oi > bi)) { bv = ov; bi = oi; }
     }
     if (lane == 0) { rv[wp] = bv; ri[wp] = bi; }
     __syncthreads();
@@ -58,7 +62,8 @@ detect_select_kernel(const float* __restrict__ det, int R, int S, int top_k, flo
       float v = rv[0];
       int i = ri[0];
       for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
-        if (rv[w] > v || (rv[w] == v && ri[w] >= 0 && (i < 0 || ri[w] < i))) { v = rv[w]; i = ri[w]; }
+        if (rv[w] > v || (rv[w] == v && ri[w] > i)) { v = rv[w]; i = ri[w]; }
+      if (i >= 0 && v == -CUDART_INF_F) i = -1;      // nothing left to rank (taken already, or no area)
       if (i >= 0 && v >= cs_thr) cand[ncand++] = i;  // detections below the confidence threshold are dropped
       if (i >= 0) sc[i] = -CUDART_INF_F;
     }
@@ -84,7 +89,8 @@ detect_select_kernel(const float* __restrict__ det, int R, int S, int top_k, flo
       if (j < kept) {
         const float* p = D + (size_t)keep[j] * 6;
         out_idx[o] = keep[j];
-        for (int e = 0; e < 4; ++e) out_boxes[o * 4 + e] = min(max((int)rintf(p[e] * (float)S), 0), S);
+        // the pixel box unmold_mask pastes into (myolo_utils.py:895-901): int() truncation, x1/y1 in [0,S], x2/y2 in [1,S]
+        for (int e = 0; e < 4; ++e) out_boxes[o * 4 + e] = min(max(e < 2 ? 0 : 1, (int)(p[e] * (float)S)), S);
         out_class[o] = (int)p[5];
         out_score[o] = p[4];
       } else {
@@ -101,22 +107,17 @@ detect_select_kernel(const float* __restrict__ det, int R, int S, int top_k, flo
 // grid (top_k, B).  Full-size boolean mask of detection j of image b (all zero when j >= count).
 __global__ void __launch_bounds__(256)
 mask_paste_kernel(const float* __restrict__ det, const float* __restrict__ masks, const int* __restrict__ idx,
-                  int R, int NC, int S, int MH, int MW, int top_k, int rule, unsigned char* __restrict__ out) {
+                  int R, int NC, int S, int MH, int MW, int top_k, unsigned char* __restrict__ out) {
   const int j = blockIdx.x, b = blockIdx.y;
   unsigned char* O = out + ((size_t)b * top_k + j) * S * S;
   const int r = idx[b * top_k + j];
   int x1 = 0, y1 = 0, x2 = 0, y2 = 0, cls = 0;
   if (r >= 0) {
     const float* p = det + ((size_t)b * R + r) * 6;
-    if (rule == 1) {
-      // the reference's unmold_mask (myolo_utils.py:895-901): int() truncation, x1/y1 clamped to [0,S], x2/y2 to [1,S];
-      // the mask is then resized into this CLIPPED box
-      x1 = min(max(0, (int)(p[0] * (float)S)), S); y1 = min(max(0, (int)(p[1] * (float)S)), S);
-      x2 = min(max(1, (int)(p[2] * (float)S)), S); y2 = min(max(1, (int)(p[3] * (float)S)), S);
-    } else {
-      x1 = (int)rintf(p[0] * (float)S); y1 = (int)rintf(p[1] * (float)S);   // round(d[:4]*S), unclipped box, cropped below
-      x2 = (int)rintf(p[2] * (float)S); y2 = (int)rintf(p[3] * (float)S);
-    }
+    // the reference's unmold_mask (myolo_utils.py:895-901): int() truncation, x1/y1 clamped to [0,S], x2/y2 to [1,S];
+    // the mask is then resized into this CLIPPED box
+    x1 = min(max(0, (int)(p[0] * (float)S)), S); y1 = min(max(0, (int)(p[1] * (float)S)), S);
+    x2 = min(max(1, (int)(p[2] * (float)S)), S); y2 = min(max(1, (int)(p[3] * (float)S)), S);
     cls = (int)p[5];
   }
   const int bw = x2 - x1, bh = y2 - y1;
@@ -164,10 +165,7 @@ extern "C" int myolo_detect_postprocess(const float* detections, const float* ma
                                               out_class, out_score, out_count);
   if (masks) {
     dim3 grid(top_k, B);
-    // MYOLO_PASTE_RULE=reference selects the reference's integer rules for the mask box (default: round / unclipped / crop)
-    const char* e = getenv("MYOLO_PASTE_RULE");
-    const int rule = (e && strcmp(e, "reference") == 0) ? 1 : 0;
-    mask_paste_kernel<<<grid, 256, 0, st>>>(detections, masks, out_index, R, NC, S, MH, MW, top_k, rule, out_masks);
+    mask_paste_kernel<<<grid, 256, 0, st>>>(detections, masks, out_index, R, NC, S, MH, MW, top_k, out_masks);
   }
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;

@@ -41,7 +41,7 @@ def read_checkpoint(path) -> dict:
         from safetensors.torch import load_file
         raw = load_file(p, device="cpu")
     else:
-        raw = torch.load(p, map_location="cpu")
+        raw = torch.load(p, map_location="cpu", weights_only=True)      # tensors only: no pickled code runs
         if not isinstance(raw, dict):
             raise TypeError("%s does not hold a {variable name: tensor} mapping" % p)
     return {normalise_key(k): torch.as_tensor(v).to(torch.float32) for k, v in raw.items()}

@@ -120,6 +120,7 @@ class Engine:
         self.NB, self.NC, self.TB, self.R = cfg["NB"], cfg["NC"], cfg["TB"], cfg["G"] * cfg["G"] * cfg["NB"]
         self.with_mask = mode != "yolo"
         self._frozen = False
+        self._frozen_names = set()
         self._moving_key = None
         self._neg_shifts = C.int_array(conv3x3_shifts(cfg["POOL"], negate=True))
         self._shift_cache = {}
@@ -132,6 +133,7 @@ class Engine:
         self._replay_on = os.environ.get("MYOLO_REPLAY", "1") != "0"
         self._plan = None
         self.t = 0                     # Adam iteration
+        self.version = 0               # bumped whenever the weights change (load_params, apply_updates)
         self.seen = 0                  # yolo_custom_loss `seen` counter (model.py:95, 197)
         self._alloc_params(params if params is not None else init_params(self.NB, self.NC, seed))
         self._alloc_acts()
@@ -233,6 +235,7 @@ class Engine:
                 continue
             src = torch.as_tensor(P[name], dtype=torch.float32).reshape(shape)
             (self.p[name] if tr else self.stats[name]).copy_(src)
+        self.version = getattr(self, "version", 0) + 1
         if hasattr(self, "wt"):
             self.refresh_weights()
 
@@ -245,15 +248,35 @@ class Engine:
     def grad_dict(self) -> Dict[str, torch.Tensor]:
         return OrderedDict((n, self.g[n].detach().cpu().clone()) for n in self.offs)
 
-    def set_trainable(self, predicate):
-        """predicate(keras variable name) -> bool.  Frozen variables keep zero Adam updates."""
-        self.trainable_mask.zero_()
+    def set_trainable(self, predicate, base: bool = False):
+        """predicate(keras variable name) -> bool.  A frozen variable is left out of the optimizer altogether (its value
+        and its Adam moments stay bit-for-bit; a frozen BatchNormalization layer also keeps its moving statistics), which
+        is what Keras does with `layer.trainable = False` (model.py:1120-1155).
+        base=True installs a PERSISTENT freeze that later calls can only narrow, never lift: the reference's
+        set_trainable recurses into the nested 'yolo_model' but never touches the Model object itself, so
+        `yolo_model.trainable = False` (yolo_trainable=False, model.py:854-868) survives train(layers='all')."""
+        if base:
+            self._base_trainable = {name for name in self.offs if predicate(name)}
+            predicate = lambda name: True                                           # noqa: E731
+        allowed = getattr(self, "_base_trainable", None)
+        mask = torch.zeros(self.n_flat, dtype=torch.float32)
         self._frozen = False
+        self._frozen_names = set()
         for name, (o, n, _) in self.offs.items():
-            if predicate(name):
-                self.trainable_mask[o:o + n] = 1.0
+            if predicate(name) and (allowed is None or name in allowed):
+                mask[o:o + n] = 1.0
             else:
                 self._frozen = True
+                self._frozen_names.add(name)
+        self.trainable_mask.copy_(mask)
+        self._moving_key = None            # the set of BN layers whose moving statistics advance may have changed
+
+    def reset_optimizer(self):
+        """Fresh Adam state: the reference builds a new keras.optimizers.Adam in every compile() (model.py:1071-1075),
+        i.e. iteration count and both moment estimates start from zero."""
+        self.t = 0
+        self.adam_m.zero_()
+        self.adam_v.zero_()
 
     def _prep_jobs(self):
         """(src tensor, dst tensor, ntaps, rows, cols, transpose, mode) for every GEMM-side weight copy; mode as in
@@ -862,31 +885,43 @@ class Engine:
         self.t += 1
         b1, b2 = 0.9, 0.999
         lr_t = lr * math.sqrt(1.0 - b2 ** self.t) / (1.0 - b1 ** self.t)
-        if self._frozen:
-            self.grads.mul_(self.trainable_mask)        # set_trainable(): frozen variables get no update
-        C.call("myolo_adam_step", self.params, self.grads, self.adam_m, self.adam_v, self.n_flat, lr_t, b1, b2, 1e-8,
-               grad_scale, st)
+        if self._frozen:                                # set_trainable(): frozen variables are not in the optimizer
+            C.call("myolo_adam_step_masked", self.params, self.grads, self.adam_m, self.adam_v, self.trainable_mask,
+                   self.n_flat, lr_t, b1, b2, 1e-8, grad_scale, st)
+            # Keras drops the moving-average updates of a BatchNormalization layer whose `trainable` is False
+            fz = self._frozen_names
+            self._bn_touched = [(b, n) for b, n in self._bn_touched if (b.name + "/gamma") not in fz]
+        else:
+            C.call("myolo_adam_step", self.params, self.grads, self.adam_m, self.adam_v, self.n_flat, lr_t, b1, b2, 1e-8,
+                   grad_scale, st)
         if self._bn_touched:
-            # one launch for every (layer, statistic): the record table is rebuilt only when the set of
-            # batch-statistics layers changes (it never does within a run)
-            key = tuple(id(b) for b, _ in self._bn_touched)
+            # one launch for every (layer, statistic) that shares a step count (the zero-debias factor 1 - momentum^step is
+            # a kernel argument); layers that were frozen for a while lag behind and form their own group.  The record
+            # tables are rebuilt only when the set of batch-statistics layers changes (it never does within a run).
+            base = min(b.step for b, _ in self._bn_touched)
+            key = tuple((id(b), b.step - base) for b, _ in self._bn_touched)     # membership and grouping
             if self._moving_key != key:
                 import struct
-                steps = {b.step for b, _ in self._bn_touched}
-                assert len(steps) == 1, "batched moving-average update needs a common step count"
-                rec = b""
+                groups = {}
                 for b, npix in self._bn_touched:
-                    n = float(npix)
-                    corr = (n / max(n - 1.0, 1.0)) * (n / (n - (1.0 + BN_EPS)))
-                    rec += struct.pack("<QQQif", b.mean.data_ptr(), b.bmean.data_ptr(), b.mmean.data_ptr(), b.c, 1.0)
-                    rec += struct.pack("<QQQif", b.var.data_ptr(), b.bvar.data_ptr(), b.mvar.data_ptr(), b.c, corr)
-                self._moving_table = torch.frombuffer(bytearray(rec), dtype=torch.uint8).to(self.dev)
-                self._moving_key, self._moving_n = key, 2 * len(self._bn_touched)
+                    groups.setdefault(b.step, []).append((b, npix))
+                self._moving_tables = []
+                for _, members in sorted(groups.items()):
+                    rec = b""
+                    for b, npix in members:
+                        n = float(npix)
+                        corr = (n / max(n - 1.0, 1.0)) * (n / (n - (1.0 + BN_EPS)))
+                        rec += struct.pack("<QQQif", b.mean.data_ptr(), b.bmean.data_ptr(), b.mmean.data_ptr(), b.c, 1.0)
+                        rec += struct.pack("<QQQif", b.var.data_ptr(), b.bvar.data_ptr(), b.mvar.data_ptr(), b.c, corr)
+                    self._moving_tables.append((torch.frombuffer(bytearray(rec), dtype=torch.uint8).to(self.dev),
+                                                2 * len(members), members[0][0]))
+                self._moving_key = key
             for b, _ in self._bn_touched:
                 b.step += 1
-            C.call("myolo_bn_moving_update_batch", self._moving_table, self._moving_n, BN_MOMENTUM,
-                   self._bn_touched[0][0].step, st)
+            for table, n, b0 in self._moving_tables:
+                C.call("myolo_bn_moving_update_batch", table, n, BN_MOMENTUM, b0.step, st)
         self._bn_touched = []
+        self.version += 1
         self.refresh_weights()
 
     def train_step(self, inputs, lr: float = 1e-3, allreduce=None):
@@ -896,6 +931,7 @@ class Engine:
         The forward + backward part is a fixed sequence of ~290 C-ABI launches with fixed arguments (only the input
         pointers change), so it is recorded on the first step and replayed afterwards as raw ctypes calls
         (MYOLO_REPLAY=0 disables this); the optimizer part carries per-step scalars and stays dynamic."""
+        C.set_precision(C.PREC_TF32 if self.tc else C.PREC_FP32)    # process-global dispatch switch: another engine may have moved it
         if self._replay_on:
             warm = 1 if (self.seen + 1) < self.cfg.get("WARM_UP_BATCHES", 0) else 0
             key = (tuple((tuple(t.shape), t.dtype) for t in inputs), warm, id(allreduce),
@@ -925,10 +961,12 @@ class Engine:
                 self.backward(on_tail_ready=lambda: allreduce(self.grads, self.tail_off, self.n_flat))
         finally:
             entries = C.stop_recording()
-        ptrs = {t.data_ptr(): k for k, t in enumerate(inputs)}
-        assert len(ptrs) == len(inputs), "input tensors must not alias each other"
-        patches = [(e[1], ai, ptrs[v]) for e in entries if e[0] is not None
-                   for ai, v in enumerate(e[1]) if type(v) is int and v in ptrs]
+        # replay patches: (converted-argument list, argument position, input index) for every argument that WAS one of the
+        # input tensors when the call was issued (identity of the Python object at that position, not its integer value)
+        ids = {id(t): k for k, t in enumerate(inputs)}
+        assert len(ids) == len(inputs), "input tensors must not alias each other"
+        patches = [(e[1], ai, ids[id(a)]) for e in entries if e[0] is not None
+                   for ai, a in enumerate(e[2]) if id(a) in ids]
         self._plan = dict(key=key, entries=entries, patches=patches, out=out, bn_touched=list(self._bn_touched))
         return out
 

@@ -387,16 +387,32 @@ class MaskYOLO:
         batch = int(config.BATCH_SIZE) if mode != "inference" else int(getattr(config, "BATCH_SIZE", 1))
         self.engine = Engine(self.cfg, batch, mode, self.precision, self.device, seed=self.seed)
         _CURRENT["engine"] = self.engine                  # what the module-level graph functions run on by default
-        self._stage_bufs = None
+        self._stage_bufs, self._stage_shapes = None, None
+        self._slot_free = [None] * self._STAGE_SLOTS
+        self._last_slot = None
         if self.yolo_pretrain_dir is not None:
             self.load_weights(self.yolo_pretrain_dir, by_name=True)
-            if not self.yolo_trainable:           # model.py:854-868: freeze the pretrained yolo branch
+            if not self.yolo_trainable:
+                # model.py:854-868 sets trainable=False on every layer of the 'whole_yolo_branch' model: the backbone
+                # layers one by one, and the nested 'yolo_model' (conv_dw_7..14, conv_pw_7..14, conv_23) as a CONTAINER.
+                # set_trainable() later re-opens layers by regex but never touches the container's own flag, so the
+                # nested model stays frozen for good (base=True), the backbone only until the next set_trainable().
+                nested = re.compile(r"(conv_(dw|pw)_(7|8|9|1[0-4])(_bn)?|conv_23)/.*")
+                self.engine.set_trainable(lambda n: not nested.fullmatch(n), base=True)
                 self.engine.set_trainable(lambda n: n.startswith(("feature_map", "myolo_mask")))
         return _ModelHandle(self)
 
     # ---- host <-> device staging (pinned buffers, one async copy per input)
+    _WANT = [torch.float32, torch.float32, torch.float32, torch.int32, torch.float32, torch.uint8]
+    _STAGE_SLOTS = 2
+
     def _stage(self, inputs: List[np.ndarray]):
-        want = [torch.float32, torch.float32, torch.float32, torch.int32, torch.float32, torch.uint8]
+        """numpy batch (what BatchGenerator yields) -> device tensors.  Each input is converted into a page-locked staging
+        buffer (numpy copy: float64 -> float32 for the two YOLO tensors, bool -> bytes for the masks) and uploaded with one
+        asynchronous copy on a side stream.  Two slots of staging + device buffers alternate, so the upload of step k+1 can
+        run while step k still reads its inputs (fit_batches); the recorded launch plan of the engine is re-pointed at the
+        slot's addresses on replay."""
+        want = self._WANT
         if all(isinstance(x, torch.Tensor) and x.is_cuda for x in inputs):
             # batch already resident in HBM (myolo.shapes.DeviceShapes): nothing to stage
             for x, dt in zip(inputs, want):
@@ -405,28 +421,39 @@ class MaskYOLO:
             self.engine.inputs_ready = None
             self.last_h2d_bytes = 0
             return list(inputs)
-        if self._stage_bufs is None or any(tuple(b[0].shape) != tuple(np.shape(x)) for b, x in zip(self._stage_bufs, inputs)) \
-                or len(self._stage_bufs) != len(inputs):
-            self._stage_bufs = []
-            for x, dt in zip(inputs, want):
-                host = torch.empty(tuple(np.shape(x)), dtype=dt).pin_memory()
-                self._stage_bufs.append((host, torch.empty_like(host, device=self.engine.dev)))
+        shapes = [tuple(np.shape(x)) for x in inputs]
+        if self._stage_bufs is None or self._stage_shapes != shapes:
+            self._stage_bufs, self._stage_shapes, self._stage_k = [], shapes, 0
+            for _ in range(self._STAGE_SLOTS):
+                slot = []
+                for shp, dt in zip(shapes, want):
+                    host = torch.empty(shp, dtype=dt).pin_memory()
+                    slot.append((host, host.numpy(), torch.empty_like(host, device=self.engine.dev)))
+                self._stage_bufs.append([slot, None])           # [buffers, event: last upload from this slot has completed]
         # copies run on a side stream in consumption order: the step starts as soon as the IMAGE has
         # landed; the ground-truth tensors (two thirds of the bytes) arrive under the backbone forward and
         # are awaited right before the first kernel that reads them (Engine.inputs_ready)
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(device=self.engine.dev)
+        entry = self._stage_bufs[self._stage_k % self._STAGE_SLOTS]
+        self._stage_k += 1
+        slot = entry[0]
+        if entry[1] is not None:
+            entry[1].synchronize()                        # the upload that last read this pinned slot has left it
         main = torch.cuda.current_stream(self.engine.dev)
-        self._copy_stream.wait_stream(main)               # the previous step no longer reads the device buffers
+        if self._slot_free[(self._stage_k - 1) % self._STAGE_SLOTS] is not None:
+            # the step that last consumed this slot's device tensors has finished reading them
+            self._copy_stream.wait_event(self._slot_free[(self._stage_k - 1) % self._STAGE_SLOTS])
         out, nbytes = [], 0
         with torch.cuda.stream(self._copy_stream):
-            for k, ((host, devt), x) in enumerate(zip(self._stage_bufs, inputs)):
+            for k, ((host, host_np, devt), x) in enumerate(zip(slot, inputs)):
                 if isinstance(x, torch.Tensor) and x.is_pinned() and x.dtype == host.dtype and x.is_contiguous():
                     host = x                              # already pinned and typed (pin_inputs): no host-side copy
                 elif isinstance(x, torch.Tensor):
                     host.copy_(x)
                 else:
-                    host.copy_(torch.from_numpy(np.ascontiguousarray(x)))
+                    x = np.asarray(x)
+                    np.copyto(host_np, x.view(np.uint8) if x.dtype == np.bool_ else x, casting="unsafe")
                 devt.copy_(host, non_blocking=True)
                 if k == 0:
                     ev_img = torch.cuda.Event()
@@ -435,10 +462,21 @@ class MaskYOLO:
                 out.append(devt)
             ev_all = torch.cuda.Event()
             ev_all.record(self._copy_stream)
+        entry[1] = ev_all
         main.wait_event(ev_img)
         self.engine.inputs_ready = ev_all
         self.last_h2d_bytes = nbytes
+        self._last_slot = (self._stage_k - 1) % self._STAGE_SLOTS
         return out
+
+    def _mark_slot_consumed(self):
+        """Record, on the compute stream, that the step just enqueued is the last reader of its staging slot."""
+        k = getattr(self, "_last_slot", None)
+        if k is not None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.engine.dev))
+            self._slot_free[k] = ev
+            self._last_slot = None
 
     @staticmethod
     def pin_inputs(inputs):
@@ -452,20 +490,53 @@ class MaskYOLO:
             out.append(t)
         return out
 
-    def _train_on_batch(self, inputs, update=True, lr=None):
+    def _enqueue_step(self, inputs, update=True, lr=None):
+        """Stage one batch and enqueue its step; returns the device-side outputs (nothing is read back yet)."""
         dev_inputs = self._stage(inputs)
         eng = self.engine
         if update:
             out = eng.train_step(dev_inputs, lr if lr is not None else self.learning_rate, self.allreduce)
         else:
             out = eng.forward_training(dev_inputs, learning_phase=False)     # Keras validates with learning phase 0
+        self._mark_slot_consumed()
         res = [out["yolo_sum_loss"]] + ([out["mask_loss"]] if "mask_loss" in out else [])
-        vals = torch.stack(res).cpu().tolist()           # device -> host read of the step's losses
-        self.last_d2h_bytes = 4 * len(vals)
+        if getattr(self, "_loss_ring", None) is None or self._loss_ring[0].numel() != len(res):
+            self._loss_ring = [torch.empty(len(res), dtype=torch.float32).pin_memory() for _ in range(4)]
+            self._loss_k = 0
+        host = self._loss_ring[self._loss_k % len(self._loss_ring)]
+        self._loss_k += 1
+        host.copy_(torch.stack(res), non_blocking=True)      # device -> host read of the step's losses (pinned, async)
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream(eng.dev))
+        self.last_d2h_bytes = 4 * len(res)
+        self.last_outputs = out
+        return host, done
+
+    def _read_step(self, pending):
+        host, done = pending
+        done.synchronize()
+        vals = host.tolist()
         lw = self.cfg["LOSS_WEIGHTS"]
         total = vals[0] * lw.get("yolo_sum_loss", 1.0) + (vals[1] * lw.get("myolo_mask_loss", 1.0) if len(vals) > 1 else 0.0)
-        self.last_outputs = out
         return [total] + vals
+
+    def _train_on_batch(self, inputs, update=True, lr=None):
+        return self._read_step(self._enqueue_step(inputs, update, lr))
+
+    def fit_batches(self, batches, update=True, lr=None):
+        """The fit loop's inner pipeline (what Keras' fit_generator does around train_on_batch, model.py:1047-1059):
+        consumes an iterable of BatchGenerator outputs and yields [loss, yolo_sum_loss, myolo_mask_loss] per batch, in
+        order.  The losses of step k are read after step k+1 has been staged and enqueued, so the host-side conversion
+        and upload of the next batch overlap the device's work on the current one; every batch is still copied from
+        host memory and every step's losses are still read back."""
+        pending = None
+        for inputs in batches:
+            nxt = self._enqueue_step(inputs, update, lr)
+            if pending is not None:
+                yield self._read_step(pending)
+            pending = nxt
+        if pending is not None:
+            yield self._read_step(pending)
 
     def _predict(self, inputs):
         image = inputs[0] if isinstance(inputs, (list, tuple)) else inputs
@@ -482,6 +553,7 @@ class MaskYOLO:
         """Adam(lr, beta_1 0.9, beta_2 0.999, epsilon 1e-8) over LOSS_WEIGHTS-weighted losses
         (model.py:1062-1118).  `momentum` is accepted and unused, as in the reference."""
         self.learning_rate = float(learning_rate)
+        self.engine.reset_optimizer()             # a new keras.optimizers.Adam per compile() (model.py:1071-1075)
 
     def set_trainable(self, layer_regex, keras_model=None, indent=0, verbose=1):
         """Train only the layers whose Keras name fully matches layer_regex (model.py:1120-1155)."""
@@ -520,17 +592,17 @@ class MaskYOLO:
         B = self.engine.B
         for ep in range(self.epoch, epochs):
             t0, acc, nb = time.time(), np.zeros(3), 0
-            for inputs, _ in Prefetcher(train_gen, range(len(train_gen)), max_queue_size, workers):
-                if inputs[0].shape[0] != B:
-                    continue
-                vals = self._train_on_batch(inputs)
+            full = (inputs for inputs, _ in Prefetcher(train_gen, range(len(train_gen)), max_queue_size, workers)
+                    if inputs[0].shape[0] == B)
+            for vals in self.fit_batches(full):
                 acc[:len(vals)] += vals
                 nb += 1
             acc /= max(nb, 1)
             vloss = float("nan")
             if val_gen is not None:
-                vs = [self._train_on_batch(inputs, update=False)[0]
-                      for inputs, _ in Prefetcher(val_gen, range(len(val_gen)), max_queue_size, workers) if inputs[0].shape[0] == B]
+                vfull = (inputs for inputs, _ in Prefetcher(val_gen, range(len(val_gen)), max_queue_size, workers)
+                         if inputs[0].shape[0] == B)
+                vs = [v[0] for v in self.fit_batches(vfull, update=False)]
                 vloss = float(np.mean(vs)) if vs else float("nan")
             for k, v in zip(("loss", "yolo_sum_loss", "myolo_mask_loss"), acc):
                 history[k].append(float(v))
@@ -559,11 +631,17 @@ class MaskYOLO:
         """Batch-1 engine sharing this model's weights (detect / infer_yolo run one image at a time)."""
         if self.engine.B == 1:
             return self.engine
+        src = self.engine
         if getattr(self, "_eng1", None) is None:
             mode = "inference" if self.mode != "yolo" else "yolo"
-            self._eng1 = Engine(self.cfg, 1, mode, self.precision, self.device, params=self.engine.state_dict())
-        else:
-            self._eng1.load_params(self.engine.state_dict())
+            self._eng1 = Engine(self.cfg, 1, mode, self.precision, self.device, params=src.state_dict())
+            self._eng1_version = src.version
+        elif self._eng1_version != src.version:           # weights changed since the last call: device-to-device copy
+            self._eng1.params.copy_(src.params)
+            for k, v in src.stats.items():
+                self._eng1.stats[k].copy_(v)
+            self._eng1.refresh_weights()
+            self._eng1_version = src.version
         return self._eng1
 
     def _predict_b1(self, x):

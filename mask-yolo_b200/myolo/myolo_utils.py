@@ -429,21 +429,6 @@ def unmold_mask(mask, bbox, image_shape):
     return full_mask
 
 
-def paste_mask_px(mask, bbox, image_shape):
-    """Paste a [h, w] soft mask into its (x1, y1, x2, y2) PIXEL box of a full-size boolean image: bilinear resize to the
-    (unclipped) box, threshold 0.5, crop to the image.  This is what the device kernel behind MaskYOLO.detect computes
-    (myolo_detect_postprocess, boxes = round(normalised * S)); unmold_mask above keeps the reference's own integer rules."""
-    x1, y1, x2, y2 = [int(v) for v in bbox]
-    full = np.zeros(image_shape[:2], dtype=bool)
-    x1c, y1c, x2c, y2c = max(x1, 0), max(y1, 0), min(x2, image_shape[1]), min(y2, image_shape[0])
-    if x2 <= x1 or y2 <= y1 or x2c <= x1c or y2c <= y1c:
-        return full
-    m = resize(mask, (y2 - y1, x2 - x1)) >= 0.5
-    full[y1c:y2c, x1c:x2c] = m[y1c - y1:y2c - y1, x1c - x1:x2c - x1]
-    return full
-
-
-# --------------------------------------------------------------------------- small helpers the reference also exports
 def box_refinement_graph(box, gt_box):
     """Refinement (dy, dx, log dh, log dw) that maps `box` onto `gt_box` (myolo_utils.py:116-139); the reference's
     coordinate naming is kept: columns 0/2 span the "width", 1/3 the "height".  Works on torch tensors [N, 4]."""

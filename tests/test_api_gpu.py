@@ -70,7 +70,9 @@ def test_set_trainable_freezes_layers_and_bad_image_size_raises():
     assert torch.equal(before["myolo_mask_conv2/kernel"], after["myolo_mask_conv2/kernel"])
     assert not torch.equal(before["conv_23/kernel"], after["conv_23/kernel"])           # trainable
     assert not torch.equal(before["conv_pw_12/kernel"], after["conv_pw_12/kernel"])
-    assert not torch.equal(before["conv_pw_3_bn/moving_mean"], after["conv_pw_3_bn/moving_mean"])   # BN still in training phase
+    # Keras drops the moving-average updates of a BatchNormalization layer whose `trainable` is False (Layer.updates)
+    assert torch.equal(before["conv_pw_3_bn/moving_mean"], after["conv_pw_3_bn/moving_mean"])
+    assert not torch.equal(before["conv_pw_12_bn/moving_mean"], after["conv_pw_12_bn/moving_mean"])
     v2 = model.keras_model.test_on_batch(batch)
     assert all(np.isfinite(v2))
 
@@ -78,3 +80,58 @@ def test_set_trainable_freezes_layers_and_bad_image_size_raises():
         IMAGE_SHAPE = [100, 100, 3]
     with pytest.raises(Exception, match="dividable by 32"):
         MaskYOLO(mode="training", config=Bad())
+
+
+def test_frozen_variables_stay_out_of_the_optimizer(tmp_path):
+    """(1) yolo_trainable=False freezes backbone + nested yolo_model at build; train(layers='all') re-opens the backbone
+    layers but the nested yolo_model (conv_dw/pw_7..14, conv_23) stays frozen: the reference's set_trainable never touches
+    the container's own `trainable` flag (model.py:854-868, 1120-1155).  (2) A variable that is frozen AFTER it has collected Adam
+    moments does not keep moving.  (3) compile() starts a fresh Adam (model.py:1071-1075)."""
+    from myolo.model import MaskYOLO
+    from myolo.shapes import ShapesDataset, make_batches
+    from myolo import checkpoint
+    cfg = _cfg()
+    seed_model = MaskYOLO(mode="training", config=cfg, seed=5)
+    ck = os.path.join(str(tmp_path), "yolo_pretrain.npz")
+    checkpoint.write_checkpoint(ck, seed_model.engine.state_dict())
+    del seed_model
+    model = MaskYOLO(mode="training", config=cfg, model_dir=str(tmp_path), yolo_pretrain_dir=ck, yolo_trainable=False)
+    before = model.engine.state_dict()
+    b0 = make_batches(cfg, 1, seed=3)[0]
+    model.keras_model.train_on_batch(b0)                           # as built: only feature_map + mask head move
+    built = model.engine.state_dict()
+    assert all(torch.equal(before[k], built[k]) for k in before if not k.startswith(("feature_map", "myolo_mask")))
+    assert not torch.equal(before["myolo_mask_conv2/kernel"], built["myolo_mask_conv2/kernel"])
+    before = built
+    tr = ShapesDataset(seed=1)
+    tr.load_shapes(8, 128, 128); tr.prepare()
+    np.random.seed(0)
+    model.train(tr, None, learning_rate=1e-3, epochs=1, layers="all", verbose=0)
+    after = model.engine.state_dict()
+    import re
+    nested = re.compile(r"(conv_(dw|pw)_(7|8|9|1[0-4])(_bn)?|conv_23)/.*")
+    for k in before:
+        if nested.fullmatch(k):
+            assert torch.equal(before[k], after[k]), k             # weights AND moving statistics of the nested yolo model
+    assert not torch.equal(before["conv_pw_3/kernel"], after["conv_pw_3/kernel"])          # backbone re-opened by 'all'
+    assert not torch.equal(before["conv_pw_3_bn/moving_mean"], after["conv_pw_3_bn/moving_mean"])
+    assert not torch.equal(before["myolo_mask_conv2/kernel"], after["myolo_mask_conv2/kernel"])
+    assert not torch.equal(before["feature_map/kernel"], after["feature_map/kernel"])
+
+    # (2) + (3)
+    model = MaskYOLO(mode="training", config=cfg)
+    batch = make_batches(cfg, 1, seed=3)[0]
+    for _ in range(3):
+        model.keras_model.train_on_batch(batch)
+    assert model.engine.t == 3 and model.engine.adam_m.abs().max().item() > 0
+    model.set_trainable(r"(myolo_mask.*)|(feature_map)")
+    mid = model.engine.state_dict()
+    o, n, _ = model.engine.offs["conv_pw_3/kernel"]
+    m_mid = model.engine.adam_m[o:o + n].clone()
+    model.keras_model.train_on_batch(batch)
+    end = model.engine.state_dict()
+    assert torch.equal(mid["conv_pw_3/kernel"], end["conv_pw_3/kernel"]) and torch.equal(mid["conv1_bn/gamma"], end["conv1_bn/gamma"])
+    assert torch.equal(m_mid, model.engine.adam_m[o:o + n])
+    assert not torch.equal(mid["myolo_mask_conv1/kernel"], end["myolo_mask_conv1/kernel"])
+    model.compile(1e-3)
+    assert model.engine.t == 0 and model.engine.adam_m.abs().max().item() == 0 and model.engine.adam_v.abs().max().item() == 0

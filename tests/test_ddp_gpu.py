@@ -65,8 +65,7 @@ def _worker(rank, world, port, q, transport="torch"):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-@pytest.mark.parametrize("transport", ["torch", pytest.param("cabi", marks=pytest.mark.xfail(
-    reason="C-ABI NCCL transport: verified with a one-rank communicator on B200 in round 1; two ranks not yet run", strict=False))])
+@pytest.mark.parametrize("transport", ["torch", "cabi"])
 def test_two_gpu_step_is_mean_of_replica_gradients(transport):
     """transport 'torch': torch.distributed all_reduce; 'cabi': the C ABI's own NCCL communicator (myolo_allreduce_*)."""
     import torch.multiprocessing as mp

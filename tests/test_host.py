@@ -93,8 +93,6 @@ def test_decode_one_yolo_output_and_unmold():
     boxes = mutils.decode_one_yolo_output(netout, [1.0, 1.0], obj_threshold=0.3, nb_class=2)
     assert len(boxes) == 1 and boxes[0].get_label() == 0
     assert abs(boxes[0].xmin - (0.25 - 0.25)) < 1e-9 and abs(boxes[0].ymax - (0.75 + 0.25)) < 1e-9
-    full = mutils.paste_mask_px(np.ones((28, 28), np.float32), [10, 20, 30, 50], (64, 64, 3))
-    assert full.sum() == 20 * 30 and full[20:50, 10:30].all()
     # unmold_mask keeps the reference's rules: normalised box, int() truncation, clamp, resize to the clipped box
     full = mutils.unmold_mask(np.ones((28, 28), np.float32), [10.9 / 64, 20.2 / 64, 30.99 / 64, 1.5], (64, 64, 3))
     assert full.sum() == 20 * 44 and full[20:64, 10:30].all()
@@ -230,8 +228,11 @@ def test_train_loop_on_stub_engine(tmp_path):
         def state_dict(self):
             return {"conv1/kernel": torch.zeros(3, 3, 3, 32)}
 
-        def set_trainable(self, pred):
+        def set_trainable(self, pred, base=False):
             self.trainable = [n for n in ("conv1/kernel", "myolo_mask_conv1/kernel") if pred(n)]
+
+        def reset_optimizer(self):
+            self.resets = getattr(self, "resets", 0) + 1
 
     cfg = C128()
     tr, va = ShapesDataset(seed=1), ShapesDataset(seed=2)
@@ -247,13 +248,18 @@ def test_train_loop_on_stub_engine(tmp_path):
         calls.append(update)
         return [3.0, 1.0, 2.0]
 
-    m._train_on_batch = fake_step
+    # the fit loop stages + enqueues step k+1 before it reads the losses of step k (MaskYOLO.fit_batches)
+    order = []
+    m._enqueue_step = lambda inputs, update=True, lr=None: (order.append("enqueue"), fake_step(inputs, update, lr))[1]
+    m._read_step = lambda pending: (order.append("read"), pending)[1]
     np.random.seed(0)
     hist = m.train(tr, va, learning_rate=0.01, epochs=2, layers=r"(myolo_mask.*)", verbose=0)
     # 10 images / batch 4 -> 3 batches (the last one refilled from the preceding images), 4 val images -> 1 batch
     assert calls == [True, True, True, False] * 2
     assert hist == {"loss": [3.0, 3.0], "yolo_sum_loss": [1.0, 1.0], "myolo_mask_loss": [2.0, 2.0], "val_loss": [3.0, 3.0]}
     assert m.engine.trainable == ["myolo_mask_conv1/kernel"] and m.learning_rate == 0.01 and m.epoch == 2
+    assert m.engine.resets == 1                                   # compile() starts a fresh Adam (model.py:1071-1075)
+    assert order[:7] == ["enqueue", "enqueue", "read", "enqueue", "read", "read", "enqueue"]     # 3 train batches, then validation
     saved = [f for f in os.listdir(str(tmp_path)) if f.startswith("saved_model_") and f.endswith(".pt")]
     assert len(saved) == 1 and "conv1/kernel" in torch.load(os.path.join(str(tmp_path), saved[0]))
 

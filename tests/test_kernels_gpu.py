@@ -552,80 +552,52 @@ def test_deconv_mask_fused(C):
 
 
 def test_detect_postprocess_matches_numpy_pipeline(C):
-    """Device top-k / threshold / NMB / mask paste against the host functions that restate
-    myolo_utils.NMB (88-113; itself pinned to the reference's outputs by tests/test_reference_golden.py) and the
-    pixel-box mask paste (paste_mask_px: round, resize to the unclipped box, crop)."""
+    """Device zero-area drop / top-k / threshold / NMB / mask paste against the host functions: myolo_utils.NMB (88-113) and
+    myolo_utils.unmold_mask (883-912: int() truncation, clamp, resize into the CLIPPED box), both pinned to the reference's
+    own source (tests/test_reference_golden.py, tests/test_reference_graph_golden.py)."""
     from myolo import myolo_utils as mu
-    rng = np.random.RandomState(30)
-    B, R, NC, S, K = 3, 147, 4, 224, 10
-    det = np.zeros((B, R, 6), np.float32)
-    c = rng.rand(B, R, 2) * 0.8 + 0.1
-    wh = rng.rand(B, R, 2) * 0.4 + 0.05
-    det[..., 0:2], det[..., 2:4] = c - wh / 2, c + wh / 2
-    det[:, :20, :4] = det[:, 20:40, :4] + rng.randn(B, 20, 4).astype(np.float32) * 0.01     # near-duplicates -> suppression
-    det[..., 4] = rng.permutation(B * R).reshape(B, R) / float(B * R)                        # distinct scores
-    det[..., 5] = rng.randint(0, NC, (B, R))
-    masks = rng.rand(B, R, 28, 28, NC).astype(np.float32)
-    thr = 0.9
-    dd, md = cuda(torch.tensor(det)), cuda(torch.tensor(masks))
-    i32 = lambda *sh: torch.empty(sh, dtype=torch.int32, device="cuda")
-    idx, boxes, cls, cnt = i32(B, K), i32(B, K, 4), i32(B, K), i32(B)
-    score = torch.empty(B, K, device="cuda")
-    pm = torch.empty(B, K, S, S, dtype=torch.uint8, device="cuda")
-    C.call("myolo_detect_postprocess", dd, md, B, R, NC, S, 28, 28, K, thr, 0.5, idx, boxes, cls, score, cnt, pm, stream())
-    total_px = mism = 0
-    for b in range(B):
-        order = np.argsort(det[b, :, 4])[::-1][:K]
-        order = [i for i in order if det[b, i, 4] >= thr]
-        keep = list(mu.NMB(det[b, order, :4], det[b, order, 5], np.asarray(order), (S, S, 3), nms_threshold=0.5)) if order else []
-        n = int(cnt[b].item())
-        assert idx[b, :n].cpu().tolist() == [int(k) for k in keep], (b, idx[b].cpu().tolist(), keep)
-        assert (idx[b, n:] == -1).all()
-        exp_boxes = np.clip(np.round(det[b, keep, :4] * S), 0, S).astype(np.int32)
-        assert np.array_equal(boxes[b, :n].cpu().numpy(), exp_boxes)
-        assert cls[b, :n].cpu().tolist() == [int(det[b, k, 5]) for k in keep]
-        for j, k in enumerate(keep):
-            box = np.round(det[b, k, :4] * S).astype(np.int32)
-            ref = mu.paste_mask_px(masks[b, k, :, :, int(det[b, k, 5])], box, (S, S, 3))
-            got = pm[b, j].bool().cpu().numpy()
-            total_px += ref.sum()
-            mism += (ref != got).sum()
-        assert pm[b, n:].sum().item() == 0
-    assert total_px > 1000 and mism <= 2e-3 * total_px, (mism, total_px)     # cv2 vs device rounding at exactly 0.5
-
-
-@pytest.mark.xfail(reason="MYOLO_PASTE_RULE=reference was added after the round-1 GPU budget was spent", strict=False)
-def test_detect_postprocess_reference_paste_rule(C, monkeypatch):
-    """Opt-in mask box rule of the reference's unmold_mask (int() truncation, clamp, resize into the clipped box) against
-    myolo_utils.unmold_mask, which is pinned to the reference's source (tests/test_reference_graph_golden.py)."""
-    from myolo import myolo_utils as mu
-    monkeypatch.setenv("MYOLO_PASTE_RULE", "reference")
-    rng = np.random.RandomState(31)
-    B, R, NC, S, K = 2, 60, 4, 96, 10
-    det = np.zeros((B, R, 6), np.float32)
-    c = rng.rand(B, R, 2)
-    wh = rng.rand(B, R, 2) * 0.5 + 0.1
-    det[..., 0:2], det[..., 2:4] = c - wh / 2, c + wh / 2                    # many boxes leave the image
-    det[..., 4] = rng.permutation(B * R).reshape(B, R) / float(B * R)
-    det[..., 5] = rng.randint(0, NC, (B, R))
-    masks = rng.rand(B, R, 28, 28, NC).astype(np.float32)
-    dd, md = cuda(torch.tensor(det)), cuda(torch.tensor(masks))
-    i32 = lambda *sh: torch.empty(sh, dtype=torch.int32, device="cuda")      # noqa: E731
-    idx, boxes, cls, cnt = i32(B, K), i32(B, K, 4), i32(B, K), i32(B)
-    score = torch.empty(B, K, device="cuda")
-    pm = torch.empty(B, K, S, S, dtype=torch.uint8, device="cuda")
-    C.call("myolo_detect_postprocess", dd, md, B, R, NC, S, 28, 28, K, 0.0, 2.0, idx, boxes, cls, score, cnt, pm, stream())
-    total_px = mism = 0
-    for b in range(B):
-        n = int(cnt[b].item())
-        assert n == K                                                        # threshold 0, no suppression (IoU < 2)
-        for j in range(n):
-            k = int(idx[b, j].item())
-            ref = mu.unmold_mask(masks[b, k, :, :, int(det[b, k, 5])], det[b, k, :4], (S, S, 3))
-            got = pm[b, j].bool().cpu().numpy()
-            total_px += ref.sum()
-            mism += (ref != got).sum()
-    assert total_px > 1000 and mism <= 2e-3 * total_px, (mism, total_px)
+    for seed, (B, R, NC, S, K), thr, nms, spread in ((30, (3, 147, 4, 224, 10), 0.9, 0.5, 0.8), (31, (2, 60, 4, 96, 10), 0.0, 2.0, 1.0)):
+        rng = np.random.RandomState(seed)
+        det = np.zeros((B, R, 6), np.float32)
+        c = rng.rand(B, R, 2) * spread + (1 - spread) / 2          # spread 1.0: many boxes leave the image
+        wh = rng.rand(B, R, 2) * 0.4 + 0.05
+        det[..., 0:2], det[..., 2:4] = c - wh / 2, c + wh / 2
+        det[:, :20, :4] = det[:, 20:40, :4] + rng.randn(B, 20, 4).astype(np.float32) * 0.01     # near-duplicates -> suppression
+        det[..., 4] = rng.permutation(B * R).reshape(B, R) / float(B * R)                        # distinct scores
+        det[..., 5] = rng.randint(0, NC, (B, R))
+        top = np.argsort(det[0, :, 4])[::-1]
+        det[0, top[1], 2] = det[0, top[1], 0]                                                    # a high-scoring box without area
+        masks = rng.rand(B, R, 28, 28, NC).astype(np.float32)
+        dd, md = cuda(torch.tensor(det)), cuda(torch.tensor(masks))
+        i32 = lambda *sh: torch.empty(sh, dtype=torch.int32, device="cuda")      # noqa: E731
+        idx, boxes, cls, cnt = i32(B, K), i32(B, K, 4), i32(B, K), i32(B)
+        score = torch.empty(B, K, device="cuda")
+        pm = torch.empty(B, K, S, S, dtype=torch.uint8, device="cuda")
+        C.call("myolo_detect_postprocess", dd, md, B, R, NC, S, 28, 28, K, thr, nms, idx, boxes, cls, score, cnt, pm, stream())
+        total_px = mism = 0
+        for b in range(B):
+            area = (det[b, :, 2] - det[b, :, 0]) * (det[b, :, 3] - det[b, :, 1])
+            live = np.where(area > 0)[0]                              # decode_masks: np.delete of the zero-area rows
+            order = live[np.argsort(det[b, live, 4])[::-1][:K]]
+            order = [i for i in order if det[b, i, 4] >= thr]
+            keep = list(mu.NMB(det[b, order, :4], det[b, order, 5], np.asarray(order), (S, S, 3), nms_threshold=nms)) if order else []
+            n = int(cnt[b].item())
+            assert idx[b, :n].cpu().tolist() == [int(k) for k in keep], (b, idx[b].cpu().tolist(), keep)
+            assert (idx[b, n:] == -1).all()
+            if b == 0:
+                assert int(top[1]) not in idx[b].cpu().tolist()
+            px = (det[b, keep, :4] * np.float32(S)).astype(np.int32)  # int() truncation
+            exp_boxes = np.stack([np.clip(px[:, 0], 0, S), np.clip(px[:, 1], 0, S), np.clip(px[:, 2], 1, S), np.clip(px[:, 3], 1, S)], 1) \
+                if keep else np.zeros((0, 4), np.int32)
+            assert np.array_equal(boxes[b, :n].cpu().numpy(), exp_boxes)
+            assert cls[b, :n].cpu().tolist() == [int(det[b, k, 5]) for k in keep]
+            for j, k in enumerate(keep):
+                ref = mu.unmold_mask(masks[b, k, :, :, int(det[b, k, 5])], det[b, k, :4], (S, S, 3))
+                got = pm[b, j].bool().cpu().numpy()
+                total_px += ref.sum()
+                mism += (ref != got).sum()
+            assert pm[b, n:].sum().item() == 0
+        assert total_px > 1000 and mism <= 2e-3 * total_px, (mism, total_px)     # cv2 vs device rounding at exactly 0.5
 
 
 def test_dgrad_with_fused_bn_backward(C):

@@ -205,9 +205,7 @@ def test_shim_crop_and_resize_micro_cases():
 
 
 # ------------------------------------------------------------------------------------------------ GPU
-_GPU_CASES = [pytest.param(n, marks=pytest.mark.xfail(reason="case added after the round-1 GPU budget was spent (the oracle "
-                                                             "matches it on the CPU; the engine-level no-GT test is green)",
-                                                      strict=False)) if n == "nogt" else n for n in GI.CASES]
+_GPU_CASES = list(GI.CASES)
 
 
 @pytest.mark.gpu
@@ -267,8 +265,6 @@ def test_device_kernels_equal_reference_source(gold, name):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(reason="module-level layer operators of myolo.model: written against the verified C-ABI signatures but not yet "
-                          "run on a GPU (round-1 GPU budget was spent); expected to pass", strict=False)
 @pytest.mark.parametrize("name", list(GI.CASES))
 def test_module_level_layer_operators_equal_reference_source(gold, name):
     """DecodeYOLOLayer / DetectionsLayer / DetectMaskTargetLayer / PyramidROIAlign / yolo_custom_loss /

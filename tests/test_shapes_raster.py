@@ -258,7 +258,6 @@ def test_owner_composition_drops_fully_occluded_instances_like_load_image_gt(ext
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(reason="written after the round-1 GPU budget was spent; the same rule is verified in numpy above", strict=False)
 def test_device_raster_drops_fully_occluded_instances_and_handles_empty_images():
     import torch
     from myolo import _cabi as C
