@@ -32,6 +32,10 @@ import numpy as np
 import torch
 
 METRIC = "images/sec fwd+bwd @224x224 Shapes"
+
+
+def metric_name(args):
+    return METRIC if args.config == "c2" and args.size == 224 else f"images/sec fwd+bwd @{args.size}x{args.size} ({args.config})"
 WORKLOADS = {
     # name: (image side, per-GPU batch, description)
     "c2": (224, 32, "Shapes 224x224 batch 32/GPU, MobileNet+YOLO+ROIAlign+mask fwd+bwd+Adam"),
@@ -241,7 +245,7 @@ def run_reference(args):
     v = nimg * args.steps / dt
     sample = f"{args.steps} oracle.train_step calls (fwd+bwd+Adam, torch CPU fp32, {cores} threads) on the full batch of {nimg} " \
              f"images of the workload (NB={c['NB']}, NC={c['NC']}, R={c['R']})"
-    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "images/sec", "n_gpus": args.gpus,
+    print(json.dumps({"impl": "reference", "metric": metric_name(args), "value": v, "unit": "images/sec", "n_gpus": args.gpus,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
                       "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                       "config": workload_config(args, c, args.gpus),
@@ -375,18 +379,9 @@ def parity_leg(args, cfg, batch_np, nimg, precisions, want_cpu):
             vals = model.keras_model.train_on_batch(sub)
             torch.cuda.synchronize()
             dev = model.last_outputs
-            dm = (dev["myolo_mask"].cpu() - oout["myolo_mask"]).abs()
-            biou = Hh.box_iou_pairs(dev["yolo_proposals"], oout["yolo_proposals"])
-            miou = Hh.mask_iou(dev["myolo_mask"], oout["myolo_mask"])
-            parity[prec] = {
-                "box_iou_mean": biou.mean().item(), "box_iou_min": biou.min().item(),
-                "mask_iou_mean": miou.mean().item(), "mask_iou_min": miou.min().item(),
-                "max_abs_box_err": (dev["yolo_proposals"].cpu() - oout["yolo_proposals"]).abs().max().item(),
-                "max_abs_class_score_err": (dev["yolo_output"].cpu() - oout["yolo_output"]).abs().max().item(),
-                "max_abs_mask_err": dm.max().item(), "mask_elements_off_by_1e-3": (dm > 1e-3).float().mean().item(),
-                "roi_selection_identical": bool(torch.equal(dev["target_class_ids"].cpu(), oout["target_class_ids"])),
-                "positive_rois": int((oout["target_class_ids"] > 0).sum().item()),
-                "loss": vals[0], "oracle_loss": oout["loss"].item()}
+            m = Hh.step_parity(dev, oout, args.size // 8)
+            parity[prec] = {k: v for k, v in m.items() if not k.startswith("_")}
+            parity[prec].update(loss=vals[0], oracle_loss=oout["loss"].item())
             del model
             torch.cuda.empty_cache()
         except Exception as e:                      # never lose the throughput line to the side check
@@ -460,7 +455,7 @@ def main():
     if rank == 0:
         fl = flops_per_image(c)
         value = main_res["value"]
-        line = {"metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": K, "warmup": W,
+        line = {"metric": metric_name(args), "value": value, "unit": "images/sec", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": main_res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": {"fp32": "f32", "h16": "f16 operands (mask head) / 3xtf32 (backbone), f32 accumulate"}.get(args.precision, "tf32"),
                 "data": "synthetic", "config": workload_config(args, c, world), "precision": args.precision,

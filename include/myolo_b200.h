@@ -51,6 +51,17 @@ int myolo_conv1_wgrad(const float* x, const float* dy, float* dw, int B, int S, 
 /* ---- K2: depthwise 3x3, myolo/model.py:68-77,256-268 (ZeroPad(1,1) + DepthwiseConv VALID) ---- */
 /* x is a strided view (dense or padded-flat); y, dy, dx are dense NHWC. */
 int myolo_dwconv3x3_fwd(const myolo_view* x, const float* w, float* y, int stride, myolo_stream stream);
+/* fused variants.  in_*: BatchNormalization statistics / affine terms of the layer that PRODUCED x; when
+ * given, x is that layer's pre-BN output and act(BN(x)) (in_act: MYOLO_ACT_*) is applied while x is read, zero padding
+ * after it -- the post-BN activation never exists in HBM (replaces the FusedBatchNorm + Relu6 nodes between a pointwise
+ * conv and the next depthwise conv, keras_applications _depthwise_conv_block).  out_mean / out_var: when given, receive
+ * the batch mean / biased variance of y over (n, h, w), reduced in the epilogue (ws: BN workspace, zero before and after). */
+int myolo_dwconv3x3_fwd_bn(const myolo_view* x, const float* w, float* y, int stride, const float* in_mean,
+                           const float* in_var, const float* in_gamma, const float* in_beta, float eps, int in_act,
+                           float* out_mean, float* out_var, double* ws, myolo_stream stream);
+int myolo_dwconv3x3_bwd_filter_bn(const myolo_view* x, const float* dy, float* dw, int stride, const float* in_mean,
+                                  const float* in_var, const float* in_gamma, const float* in_beta, float eps, int in_act,
+                                  myolo_stream stream);
 int myolo_dwconv3x3_bwd_data(const float* dy, const float* w, float* dx, int B, int H, int W, int C, int stride, myolo_stream stream);
 int myolo_dwconv3x3_bwd_filter(const myolo_view* x, const float* dy, float* dw, int stride, myolo_stream stream);
 
@@ -91,6 +102,14 @@ int myolo_gemm_taps_tc(const float* A, long long lda, const float* Bt, float* C,
                        const float* bias, const float* scale, const float* shift_c, int act,
                        int pf_w1, int pf_blk, int accumulate, myolo_stream stream);
 int myolo_gemm_taps_tc_supported(long long lda, long long ldc, long long M, int N, int K, int ntaps, int accumulate);
+/* myolo_gemm_taps_tc without bias / scale / activation, plus the batch statistics of its result in the epilogue: mean[n] /
+ * var[n] (biased) of C[:, n] over the valid rows (n_valid of them; pad rows of a padded-flat result do not count).  This is
+ * the FusedBatchNorm statistics pass of the BatchNormalization that follows a pointwise convolution (keras_applications
+ * _depthwise_conv_block; call sites myolo/model.py:68-77, 256-268), folded into the convolution.  ws: the BN workspace
+ * (zero before, zero after).  Supported whenever myolo_gemm_taps_tc_supported and N <= 1024. */
+int myolo_gemm_taps_tc_stats(const float* A, long long lda, const float* Bt, float* C, long long ldc, long long M,
+                             int N, int K, int ntaps, const int* shifts_host, int pf_w1, int pf_blk,
+                             float* mean, float* var, double* ws, long long n_valid, myolo_stream stream);
 /* persistent multi-tap variant with shared-memory reuse of the A rows across taps (conv_win_tcgen05.cu):
  * N == 256, 2 <= ntaps, every |shift| <= 16 (3x3 conv on padded-flat tiles up to 14 wide); A must carry
  * >= 16 zero guard rows after row M.  myolo_gemm_taps picks it automatically in TF32 mode. */
@@ -114,11 +133,18 @@ int myolo_gemm_taps_wgrad_tc_supported(long long lda, long long ldd, long long M
 int myolo_prep_weights(const float* in, float* out, int ntaps, int rows, int cols, int transpose,
                        int round_tf32, myolo_stream stream);
 /* every staging job of a step in one launch.  jobs_dev: device array of n_jobs records
- * { const float* in; void* out; int ntaps, rows, cols, transpose, mode, tile_begin; } (40 bytes each) with mode
- * 0 copy / 1 tf32 rounding / 2 3xTF32 split / 3 IEEE half (= myolo_prep_weights with round_tf32 0/1/2 and
+ * { const float* in; void* out; int ntaps, rows, cols, transpose, mode, tile_begin, out_ld, out_total; } (48 bytes each)
+ * with mode 0 copy / 1 tf32 rounding / 2 3xTF32 split / 3 IEEE half (= myolo_prep_weights with round_tf32 0/1/2 and
  * myolo_prep_weights_h) and tile_begin = running sum of ntaps*ceil(rows/32)*ceil(cols/32) over the jobs before it;
- * total_tiles = that sum over all jobs. */
+ * total_tiles = that sum over all jobs.  out_ld (0 = dense) is the leading dimension of the staged matrix and out_total
+ * (0 = ntaps*rows*cols) the distance between the three copies of mode 2: larger values leave zero padding the job never
+ * writes, which is how conv_23's N_BOX*(5+NC) output channels (27, 35, 430) become a tensor-core shape. */
 int myolo_prep_weights_batch(const void* jobs_dev, int n_jobs, int total_tiles, myolo_stream stream);
+/* dst[r][0..cols) = src[r][0..cols) between matrices of different row pitch (elements): un-pads the tensor-core result of
+ * conv_23 (myolo/model.py:271) into the dense [B,G,G,N_BOX*(5+NC)] tensor the decode / loss kernels read, and pads its
+ * gradient for the data-gradient GEMM. */
+int myolo_copy_cols(const float* src, long long src_ld, float* dst, long long dst_ld, long long rows, int cols,
+                    myolo_stream stream);
 /* pointwise / 3x3 named wrappers (SURVEY 8b names).  w = HWIO kernel [t][Cin][Cout]; wt = its
  * per-tap transpose [t][Cout][Cin] (myolo_prep_weights). */
 int myolo_pwconv_fwd(const float* x, const float* wt, float* y, long long M, int Cin, int Cout,

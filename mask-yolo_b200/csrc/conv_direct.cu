@@ -12,12 +12,56 @@ namespace myolo {
 // depthwise 3x3 forward.  block = 256 threads = 32 pixel-slots x 8 channel-quads (32 channels).
 // tile = 8x8 outputs; input halo tile (7*S+3)^2 x 32ch staged in smem with float4 loads.
 // ------------------------------------------------------------------------------------------
-template <int S>
+// Fusions (BN statistics in the producer's epilogue, BN apply in the consumer's load):
+//   INBN : the input is the PRE-BN output of the producing layer; a = act(gamma*(x-mean)*rs + beta) is applied while the
+//          halo tile is staged (zero padding stays zero: ZeroPad comes after the activation), so the producer's post-BN
+//          activation is never written to HBM;
+//   STATS: per-channel sum / sum of squares of THIS layer's output, reduced per block and added to the fp64 workspace of
+//          the BN family (bn.cu); the block that draws the last ticket of its 32-channel group turns them into the batch
+//          mean / biased variance and zeroes the workspace again (same contract as colreduce_kernel<3>).
+struct DwBn {
+  const float* mean;     // INBN: statistics / affine terms of the producing layer's BN
+  const float* var;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  int act;
+};
+struct DwStats {
+  double* sums;          // [2][C]: zero before the launch, zero after it
+  int* ticket;           // one counter per 32-channel group
+  float* mean;           // out: batch mean / biased variance of y
+  float* var;
+  double inv_count;      // 1 / (B*Ho*Wo)
+  int C;
+};
+
+// a = act(x * sc + sh) with sc = gamma * rs, sh = beta - mean * sc (one FMA + the clamp per element: these kernels are
+// instruction-bound, and the filter-gradient kernel meets every input nine times)
+__device__ __forceinline__ float4 dw_in_bn(float4 v, const float4& sc, const float4& sh, int act) {
+  v.x = apply_act(fmaf(v.x, sc.x, sh.x), act);
+  v.y = apply_act(fmaf(v.y, sc.y, sh.y), act);
+  v.z = apply_act(fmaf(v.z, sc.z, sh.z), act);
+  v.w = apply_act(fmaf(v.w, sc.w, sh.w), act);
+  return v;
+}
+__device__ __forceinline__ void dw_bn_consts(const DwBn& bn, int c, float4& sc, float4& sh) {
+  const float4 mu = __ldg(reinterpret_cast<const float4*>(bn.mean + c));
+  const float4 vv = __ldg(reinterpret_cast<const float4*>(bn.var + c));
+  const float4 ga = __ldg(reinterpret_cast<const float4*>(bn.gamma + c));
+  const float4 be = __ldg(reinterpret_cast<const float4*>(bn.beta + c));
+  sc = make_float4(ga.x / sqrtf(vv.x + bn.eps), ga.y / sqrtf(vv.y + bn.eps), ga.z / sqrtf(vv.z + bn.eps), ga.w / sqrtf(vv.w + bn.eps));
+  sh = make_float4(fmaf(-mu.x, sc.x, be.x), fmaf(-mu.y, sc.y, be.y), fmaf(-mu.z, sc.z, be.z), fmaf(-mu.w, sc.w, be.w));
+}
+
+template <int S, bool INBN, bool STATS>
 __global__ void __launch_bounds__(256) dw_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                      float* __restrict__ y, int H, int W, int C, int Ho, int Wo,
-                                                     int ntx, long long xsn, long long xsh) {
+                                                     int ntx, long long xsn, long long xsh, DwBn bn, DwStats st) {
   constexpr int IT = 7 * S + 3;
-  __shared__ __align__(16) float tile[IT * IT * 32];
+  constexpr int kTile = IT * IT * 32, kRed = 2 * 32 * 33;
+  __shared__ __align__(16) float tile[kTile > kRed ? kTile : kRed];
+  __shared__ int s_last;
   const int tid = threadIdx.x;
   const int cq = tid & 7, pg = tid >> 3;
   const int c0 = blockIdx.y * 32;
@@ -25,18 +69,23 @@ __global__ void __launch_bounds__(256) dw_fwd_kernel(const float* __restrict__ x
   const int oy0 = (blockIdx.x / ntx) * 8, ox0 = (blockIdx.x % ntx) * 8;
   const int iy0 = oy0 * S - 1, ix0 = ox0 * S - 1;
   const float* xb = x + (size_t)b * xsn + c0;
+  float4 bsc = make_float4(0.f, 0.f, 0.f, 0.f), bsh = bsc;
+  if (INBN) dw_bn_consts(bn, c0 + cq * 4, bsc, bsh);     // the staging loop below keeps (i & 7) == cq: one channel quad per thread
   for (int i = tid; i < IT * IT * 8; i += 256) {
     const int pix = i >> 3, q = i & 7;
     const int gy = iy0 + pix / IT, gx = ix0 + pix % IT;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (gy >= 0 && gy < H && gx >= 0 && gx < W)
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
       v = __ldg(reinterpret_cast<const float4*>(xb + (size_t)gy * xsh + (size_t)gx * C + q * 4));
+      if (INBN) v = dw_in_bn(v, bsc, bsh, bn.act);
+    }
     *reinterpret_cast<float4*>(&tile[pix * 32 + q * 4]) = v;
   }
   float4 wr[9];
 #pragma unroll
   for (int k = 0; k < 9; ++k) wr[k] = __ldg(reinterpret_cast<const float4*>(w + (size_t)k * C + c0 + cq * 4));
   __syncthreads();
+  float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
     const int o = pg + 32 * j;
@@ -55,7 +104,41 @@ __global__ void __launch_bounds__(256) dw_fwd_kernel(const float* __restrict__ x
         acc.w = fmaf(v.w, ww.w, acc.w);
       }
     *reinterpret_cast<float4*>(y + (((size_t)b * Ho + oy0 + oy) * Wo + ox0 + ox) * C + c0 + cq * 4) = acc;
+    if (STATS) {
+      s0.x += acc.x; s0.y += acc.y; s0.z += acc.z; s0.w += acc.w;
+      s1.x = fmaf(acc.x, acc.x, s1.x); s1.y = fmaf(acc.y, acc.y, s1.y); s1.z = fmaf(acc.z, acc.z, s1.z); s1.w = fmaf(acc.w, acc.w, s1.w);
+    }
   }
+  if (!STATS) return;
+  __syncthreads();                      // every thread is done reading the halo tile: reuse it for the reduction
+  float (*red)[32][33] = reinterpret_cast<float (*)[32][33]>(tile);
+  red[0][cq * 4 + 0][pg] = s0.x; red[0][cq * 4 + 1][pg] = s0.y; red[0][cq * 4 + 2][pg] = s0.z; red[0][cq * 4 + 3][pg] = s0.w;
+  red[1][cq * 4 + 0][pg] = s1.x; red[1][cq * 4 + 1][pg] = s1.y; red[1][cq * 4 + 2][pg] = s1.z; red[1][cq * 4 + 3][pg] = s1.w;
+  __syncthreads();
+  if (tid < 64) {
+    const int which = tid >> 5, c = tid & 31;
+    double s = 0.0;
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) s += (double)red[which][c][j];
+    atomicAdd(st.sums + (size_t)which * st.C + c0 + c, s);
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(st.ticket + blockIdx.y, 1) == (int)(gridDim.x * gridDim.z) - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (tid < 32) {
+    const int c = c0 + tid;
+    const double S0 = *(volatile double*)(st.sums + c), S1 = *(volatile double*)(st.sums + st.C + c);
+    const double m = S0 * st.inv_count;
+    const double vv = S1 * st.inv_count - m * m;
+    st.mean[c] = (float)m;
+    st.var[c] = (float)(vv > 0.0 ? vv : 0.0);
+    st.sums[c] = 0.0;
+    st.sums[st.C + c] = 0.0;
+  }
+  if (tid == 0) st.ticket[blockIdx.y] = 0;
 }
 
 // depthwise backward w.r.t. input: gather form, one thread = one input pixel x 4 channels.
@@ -99,10 +182,11 @@ __global__ void __launch_bounds__(256) dw_bwd_data_kernel(const float* __restric
 
 // depthwise backward w.r.t. filter: per-block register accumulation over a pixel chunk, smem
 // reduction across the 32 pixel slots, one atomicAdd per (tap, channel) per block.
-template <int S>
+// INBN: x is the producing layer's PRE-BN output; its BN + activation is applied on load (see dw_fwd_kernel)
+template <int S, bool INBN>
 __global__ void __launch_bounds__(256) dw_bwd_filter_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                             float* __restrict__ dw, int B, int H, int W, int C, int Ho,
-                                                            int Wo, long long chunk, long long xsn, long long xsh) {
+                                                            int Wo, long long chunk, long long xsn, long long xsh, DwBn bn) {
   __shared__ float red[9 * 32 * 33];
   const int tid = threadIdx.x;
   const int cq = tid & 7, pg = tid >> 3;
@@ -113,6 +197,8 @@ __global__ void __launch_bounds__(256) dw_bwd_filter_kernel(const float* __restr
   float4 acc[9];
 #pragma unroll
   for (int k = 0; k < 9; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 bsc = make_float4(0.f, 0.f, 0.f, 0.f), bsh = bsc;
+  if (INBN) dw_bn_consts(bn, c0, bsc, bsh);
   for (long long p = p0 + pg; p < p1; p += 32) {
     const unsigned pu = (unsigned)p;
     const int ox = (int)(pu % (unsigned)Wo);
@@ -128,7 +214,8 @@ __global__ void __launch_bounds__(256) dw_bwd_filter_kernel(const float* __restr
       for (int kx = 0; kx < 3; ++kx) {
         const int ix = ox * S + kx - 1;
         if (ix < 0 || ix >= W) continue;
-        const float4 v = __ldg(reinterpret_cast<const float4*>(x + (size_t)b * xsn + (size_t)iy * xsh + (size_t)ix * C + c0));
+        float4 v = __ldg(reinterpret_cast<const float4*>(x + (size_t)b * xsn + (size_t)iy * xsh + (size_t)ix * C + c0));
+        if (INBN) v = dw_in_bn(v, bsc, bsh, bn.act);
         float4& a = acc[ky * 3 + kx];
         a.x = fmaf(v.x, g.x, a.x);
         a.y = fmaf(v.y, g.y, a.y);
@@ -285,19 +372,43 @@ static bool dw_view_ok(const myolo_view* v) {
   return v && v->p && v->n > 0 && v->h > 0 && v->w > 0 && v->c > 0 && (v->c % 32) == 0 && (v->sn % 4) == 0 && (v->sh % 4) == 0;
 }
 
-extern "C" int myolo_dwconv3x3_fwd(const myolo_view* xv, const float* w, float* y, int stride, myolo_stream stream) {
+// workspace layout of the BN family (bn.cu): [0,16) doubles of int tickets | sums from double 16 on
+static constexpr int kDwWsSums = 16, kDwWsMaxC = 1024;
+
+extern "C" int myolo_dwconv3x3_fwd_bn(const myolo_view* xv, const float* w, float* y, int stride, const float* in_mean,
+                                      const float* in_var, const float* in_gamma, const float* in_beta, float eps, int in_act,
+                                      float* out_mean, float* out_var, double* ws, myolo_stream stream) {
   MYOLO_CHECK_ARG(dw_view_ok(xv) && w && y && (stride == 1 || stride == 2));
+  const bool inbn = in_mean != nullptr, stats = out_mean != nullptr;
+  MYOLO_CHECK_ARG(!inbn || (in_var && in_gamma && in_beta));
+  MYOLO_CHECK_ARG(!stats || (out_var && ws && xv->c <= kDwWsMaxC));
   const float* x = xv->p;
   const int B = xv->n, H = xv->h, W = xv->w, C = xv->c;
   const int Ho = dw_out(H, stride), Wo = dw_out(W, stride);
   const int ntx = (Wo + 7) / 8, nty = (Ho + 7) / 8;
   dim3 grid(ntx * nty, C / 32, B);
-  if (stride == 1)
-    dw_fwd_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(x, w, y, H, W, C, Ho, Wo, ntx, xv->sn, xv->sh);
-  else
-    dw_fwd_kernel<2><<<grid, 256, 0, as_stream(stream)>>>(x, w, y, H, W, C, Ho, Wo, ntx, xv->sn, xv->sh);
+  DwBn bn{in_mean, in_var, in_gamma, in_beta, eps, in_act};
+  DwStats st{ws ? ws + kDwWsSums : nullptr, reinterpret_cast<int*>(ws), out_mean, out_var, 1.0 / ((double)B * Ho * Wo), C};
+  cudaStream_t cs = as_stream(stream);
+#define MYOLO_DW_FWD(S_, I_, T_) dw_fwd_kernel<S_, I_, T_><<<grid, 256, 0, cs>>>(x, w, y, H, W, C, Ho, Wo, ntx, xv->sn, xv->sh, bn, st)
+  if (stride == 1) {
+    if (inbn && stats) MYOLO_DW_FWD(1, true, true);
+    else if (inbn) MYOLO_DW_FWD(1, true, false);
+    else if (stats) MYOLO_DW_FWD(1, false, true);
+    else MYOLO_DW_FWD(1, false, false);
+  } else {
+    if (inbn && stats) MYOLO_DW_FWD(2, true, true);
+    else if (inbn) MYOLO_DW_FWD(2, true, false);
+    else if (stats) MYOLO_DW_FWD(2, false, true);
+    else MYOLO_DW_FWD(2, false, false);
+  }
+#undef MYOLO_DW_FWD
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
+}
+
+extern "C" int myolo_dwconv3x3_fwd(const myolo_view* xv, const float* w, float* y, int stride, myolo_stream stream) {
+  return myolo_dwconv3x3_fwd_bn(xv, w, y, stride, nullptr, nullptr, nullptr, nullptr, 0.f, 0, nullptr, nullptr, nullptr, stream);
 }
 
 extern "C" int myolo_dwconv3x3_bwd_data(const float* dy, const float* w, float* dx, int B, int H, int W, int C,
@@ -315,9 +426,13 @@ extern "C" int myolo_dwconv3x3_bwd_data(const float* dy, const float* w, float* 
   return MYOLO_OK;
 }
 
-extern "C" int myolo_dwconv3x3_bwd_filter(const myolo_view* xv, const float* dy, float* dw, int stride,
-                                          myolo_stream stream) {
+extern "C" int myolo_dwconv3x3_bwd_filter_bn(const myolo_view* xv, const float* dy, float* dw, int stride, const float* in_mean,
+                                             const float* in_var, const float* in_gamma, const float* in_beta, float eps,
+                                             int in_act, myolo_stream stream) {
   MYOLO_CHECK_ARG(dw_view_ok(xv) && dy && dw && (stride == 1 || stride == 2));
+  const bool inbn = in_mean != nullptr;
+  MYOLO_CHECK_ARG(!inbn || (in_var && in_gamma && in_beta));
+  DwBn bn{in_mean, in_var, in_gamma, in_beta, eps, in_act};
   const float* x = xv->p;
   const int B = xv->n, H = xv->h, W = xv->w, C = xv->c;
   const int Ho = dw_out(H, stride), Wo = dw_out(W, stride);
@@ -328,10 +443,19 @@ extern "C" int myolo_dwconv3x3_bwd_filter(const myolo_view* xv, const float* dy,
   nchunks = ceil_div(total, chunk);
   MYOLO_CUDA(cudaMemsetAsync(dw, 0, (size_t)9 * C * sizeof(float), as_stream(stream)));
   dim3 grid((unsigned)nchunks, cgroups);
-  if (stride == 1)
-    dw_bwd_filter_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(x, dy, dw, B, H, W, C, Ho, Wo, chunk, xv->sn, xv->sh);
-  else
-    dw_bwd_filter_kernel<2><<<grid, 256, 0, as_stream(stream)>>>(x, dy, dw, B, H, W, C, Ho, Wo, chunk, xv->sn, xv->sh);
+  cudaStream_t cs = as_stream(stream);
+  if (stride == 1) {
+    if (inbn) dw_bwd_filter_kernel<1, true><<<grid, 256, 0, cs>>>(x, dy, dw, B, H, W, C, Ho, Wo, chunk, xv->sn, xv->sh, bn);
+    else dw_bwd_filter_kernel<1, false><<<grid, 256, 0, cs>>>(x, dy, dw, B, H, W, C, Ho, Wo, chunk, xv->sn, xv->sh, bn);
+  } else {
+    if (inbn) dw_bwd_filter_kernel<2, true><<<grid, 256, 0, cs>>>(x, dy, dw, B, H, W, C, Ho, Wo, chunk, xv->sn, xv->sh, bn);
+    else dw_bwd_filter_kernel<2, false><<<grid, 256, 0, cs>>>(x, dy, dw, B, H, W, C, Ho, Wo, chunk, xv->sn, xv->sh, bn);
+  }
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
+}
+
+extern "C" int myolo_dwconv3x3_bwd_filter(const myolo_view* xv, const float* dy, float* dw, int stride,
+                                          myolo_stream stream) {
+  return myolo_dwconv3x3_bwd_filter_bn(xv, dy, dw, stride, nullptr, nullptr, nullptr, nullptr, 0.f, 0, stream);
 }

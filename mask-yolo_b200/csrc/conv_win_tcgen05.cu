@@ -63,22 +63,6 @@ __host__ __device__ constexpr uint32_t win_smem(int nacc) {
 // finish the network in registers: h = relu(acc + bd), logits = h . w1 + b1, sigmoid, pixel-shuffled
 // store of NC floats.  The [rows, 4*256] deconv activation is written only for rows of POSITIVE rois
 // (the only rows the backward pass ever reads; nothing is skipped arithmetically).
-// x[c] = this lane's (row's) value of column c.  Returns, in lane l, the sum over the 32 rows of column l
-// (butterfly transpose-reduce: 31 shuffles, no shared memory).
-__device__ __forceinline__ float warp_colsum32(float (&x)[32], int lane) {
-#pragma unroll
-  for (int w = 16; w >= 1; w >>= 1) {
-    const bool up = (lane & w) != 0;
-#pragma unroll
-    for (int i = 0; i < w; ++i) {
-      const float send = up ? x[i] : x[i + w];
-      const float keep = up ? x[i + w] : x[i];
-      x[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
-    }
-  }
-  return x[0];
-}
-
 struct MaskTail {
   const float* bd;    // [256] deconv bias
   const float* w1;    // [256][NC] 1x1 kernel
@@ -87,6 +71,10 @@ struct MaskTail {
   const int* ids;     // [n_roi] target class ids (>0 = positive) or nullptr
   float* y4;          // [rows][4*256] pre-bias deconv output (positive rois only)
   int H, W, NC;
+  // tensor-core tail: the 1x1 conv runs as a second tcgen05 GEMM inside the epilogue (any NC <= 128).  h = relu(acc + bd)
+  // goes to shared memory as the half A operand [128 rows][256], the 1x1 kernel sits in shared memory as the half B
+  // operand [ncp/CG classes][256], and the logits land in the TMEM columns the deconv accumulator has just left.
+  int tc, ncp, nawin, nwb;
 };
 
 // One 32-column chunk of the mask tail for this thread's row: v = raw deconv accumulators -> (positive rois) y4 store,
@@ -182,14 +170,19 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   // trip -- and the kernel was latency-bound at 25 % tensor pipe (ncu: epilogue warps parked on t_full).  There the
   // same shared memory is split four windows / five weight stages.
   constexpr int kMaxAWin = NACC == 1 ? 4 : 2;
-  const int nawin = (ntaps == 1 && NACC == 1) ? 4 : 2;
-  const int nwb = (ntaps == 1 && NACC == 1) ? (int)((2 * kWinBytes + kWBStages * kWBBytes - 4 * kWinBytes) / kWBBytes) : kWBStages;
-  __shared__ __align__(8) uint64_t bars[2 * kMaxAWin + kWBStages * 2 + 4];
+  const int nawin = mt.tc ? mt.nawin : ((ntaps == 1 && NACC == 1) ? 4 : 2);
+  const int nwb = mt.tc ? mt.nwb
+                        : ((ntaps == 1 && NACC == 1) ? (int)((2 * kWinBytes + kWBStages * kWBBytes - 4 * kWinBytes) / kWBBytes) : kWBStages);
+  __shared__ __align__(8) uint64_t bars[2 * kMaxAWin + kWBStages * 2 + 4 + 2];
   __shared__ uint32_t tmem_slot;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t awin0 = base, bst0 = base + (uint32_t)nawin * kWinBytes, stg0 = base + 2 * kWinBytes + kWBStages * kWBBytes;
+  // tensor-core mask tail: [windows][weight stages][A2: 128 rows x 256 half, 4 swizzled k-blocks][B2: ncp/CG classes x 256 half][evec]
+  const uint32_t a2_0 = bst0 + (uint32_t)nwb * kWBBytes;
+  const uint32_t b2_0 = a2_0 + 65536u;
+  const uint32_t b2_rows = mt.tc ? (uint32_t)(mt.ncp / CG) : 0u;
   float* colacc = reinterpret_cast<float*>(smem_raw + (stg0 + kWStageOut - smem_u32(smem_raw)));          // [2][256]
-  float* evec = reinterpret_cast<float*>(smem_raw + (stg0 + kWStageOut + kWColAcc - smem_u32(smem_raw)));  // [scale N | shift N]
+  float* evec = reinterpret_cast<float*>(smem_raw + ((mt.tc ? b2_0 + b2_rows * 512u : stg0 + kWStageOut + kWColAcc) - smem_u32(smem_raw)));  // [scale N | shift N]
   constexpr int kEpiWarps = win_threads(EL) / 32 - 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int KEL = 128 / EL;                             // channels per 128-byte k-block
@@ -202,6 +195,8 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   auto b_empty = [&](int i) { return bar0 + 8u * (2 * kMaxAWin + kWBStages + i); };
   auto t_full = [&](int i) { return bar0 + 8u * (2 * kMaxAWin + 2 * kWBStages + i); };
   auto t_empty = [&](int i) { return bar0 + 8u * (2 * kMaxAWin + 2 * kWBStages + 2 + i); };
+  const uint32_t a2_full = bar0 + 8u * (2 * kMaxAWin + 2 * kWBStages + 4);   // leader: every epilogue warp of the pair has written A2
+  const uint32_t d2_full = bar0 + 8u * (2 * kMaxAWin + 2 * kWBStages + 5);   // both CTAs: the logits of the item are in TMEM
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -220,11 +215,26 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       mbar_init(b_full(i), 1);
       mbar_init(b_empty(i), 1);
     }
+    mbar_init(a2_full, kEpiWarps * CG);
+    mbar_init(d2_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // epilogue constants, folded:  act((acc + bias) * scale + shift) = act(acc * S + T)
   const float accs = ep.acc_scale ? __ldg(ep.acc_scale) : 1.f;
-  if (mt.masks) {   // mask tail: evec = [bd 256 | w1 transposed NC x 256]
+  if (mt.masks && mt.tc) {   // tensor-core mask tail: evec = [bd 256 | b1 ncp]; B2 = this CTA's classes of w1 as half, K-major
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) evec[i] = __ldg(mt.bd + i);
+    for (int i = threadIdx.x; i < mt.ncp; i += blockDim.x) evec[256 + i] = i < mt.NC ? __ldg(mt.b1 + i) : 0.f;
+    const int rows = (int)b2_rows;
+    for (int i = threadIdx.x; i < rows * 256; i += blockDim.x) {
+      const int k = i / rows, nl = i - k * rows;           // consecutive threads: consecutive classes of one input channel
+      const int cls = (int)rank * rows + nl;
+      const float wv = cls < mt.NC ? __ldg(mt.w1 + (size_t)k * mt.NC + cls) : 0.f;
+      const uint32_t addr = b2_0 + (uint32_t)(k >> 6) * (uint32_t)rows * 128u + (uint32_t)nl * 128u +
+                            (uint32_t)((((k & 63) >> 3) ^ (nl & 7)) << 4) + (uint32_t)(k & 7) * 2u;
+      asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(f2h_sat(wv)) : "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  } else if (mt.masks) {   // mask tail: evec = [bd 256 | w1 transposed NC x 256]
     for (int i = threadIdx.x; i < 256; i += blockDim.x) evec[i] = __ldg(mt.bd + i);
     for (int i = threadIdx.x; i < 256 * mt.NC; i += blockDim.x) evec[256 + (i % mt.NC) * 256 + i / mt.NC] = __ldg(mt.w1 + i);
   } else if (ep.bn_a) {   // fused BN backward: evec = [gamma*rs | beta | 1/gamma], column accumulators zeroed
@@ -297,6 +307,29 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     if (lane == 0 && leader) {
       constexpr uint32_t idesc = EL == 2 ? make_idesc_f16(128 * CG, WBN, 0, 0) : make_idesc(128 * CG, WBN, 0, 0);
       uint32_t ab = 0, aph = 0, s = 0, bph = 0, it = 0;
+      // tensor-core mask tail of item j: logits[256 rows][ncp] = A2 (h as half, written by the epilogue warps of both
+      // CTAs) x B2^T, into the first ncp columns of the TMEM stage the epilogue has just drained.  Issued right AFTER the
+      // main loop of item j+1 (which never depends on the epilogue of item j), so the tensor pipe runs main(j+1), tail(j),
+      // main(j+2), ... back to back while the epilogue warps drain item j+1.  (Issued in the middle of main(j+1) it made
+      // t_full(j+1) wait for the drain of item j: 1.04 ms instead of 0.83 ms with the FMA tail.)
+      auto issue_tail = [&](uint32_t j) {
+        const uint32_t idesc2 = make_idesc_f16(128 * CG, mt.ncp, 0, 0);
+        mbar_wait_cluster(a2_full, j & 1u);
+        tc_fence_after();
+        const uint32_t tacc2 = tmem + (j % TS) * TSTRIDE;
+#pragma unroll 1
+        for (int kb2 = 0; kb2 < 4; ++kb2) {
+          const uint64_t da2 = make_desc(a2_0 + (uint32_t)kb2 * 16384u, 16, 1024);
+          const uint64_t db2 = make_desc(b2_0 + (uint32_t)kb2 * b2_rows * 128u, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t accf = (kb2 | k) != 0 ? 1u : 0u;
+            if (CG == 2) umma_f16_2sm(tacc2, da2 + (uint64_t)(k * 2), db2 + (uint64_t)(k * 2), idesc2, accf);
+            else umma_f16(tacc2, da2 + (uint64_t)(k * 2), db2 + (uint64_t)(k * 2), idesc2, accf);
+          }
+        }
+        if (CG == 2) umma_commit_2sm(d2_full); else umma_commit(d2_full);
+      };
       for (int item = cid; item < nitems; item += ncl, ++it) {
         const uint32_t ts = it % TS;
         mbar_wait(t_empty(ts), ((it / TS) & 1u) ^ 1u);  // the epilogue that last used this TMEM stage has drained it
@@ -336,7 +369,9 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           if (++ab == (uint32_t)nawin) { ab = 0; aph ^= 1u; }
         }
         if (CG == 2) umma_commit_2sm(t_full(ts)); else umma_commit(t_full(ts));
+        if (mt.tc && it > 0) issue_tail(it - 1);
       }
+      if (mt.tc && it > 0) issue_tail(it - 1);
     }
   } else {
     const int q = warp & 3;                        // TMEM lane quarter this warp may read
@@ -367,6 +402,106 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const uint32_t ts = it % TS;
       mbar_wait(t_full(ts), (it / TS) & 1u);
       tc_fence_after();
+      if (WBN == 256 && NACC == 1 && mt.masks && mt.tc) {
+        // ---- tensor-core mask tail.  This thread's row = input pixel (roi, hh, ww) of sub-pixel (a, b) = item's slice.
+        const long long m = (long long)tile * WBM + q * 32 + lane;
+        const bool valid = (m < M) && pf_valid(m, ep.pf_w1, ep.pf_blk);
+        int roi = 0, hh = 0, ww = 0;
+        bool pos = false;
+        if (valid) {
+          roi = (int)(m / ep.pf_blk);
+          const int r = (int)(m - (long long)roi * ep.pf_blk);
+          hh = r / ep.pf_w1 - 1;
+          ww = r % ep.pf_w1 - 1;
+          pos = mt.ids && __ldg(mt.ids + roi) > 0;
+        }
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + ts * TSTRIDE;
+        float* ypos = pos ? mt.y4 + (size_t)m * N + half * 256 : nullptr;
+        const int tcb = EL == 2 ? eh * 128 : 0, tce = EL == 2 ? tcb + 128 : 256;
+        const uint32_t rrow = (uint32_t)(q * 32 + lane);
+        // drain: h = relu(acc + bd) as half into A2 (K-major, 128B swizzle: 4 k-blocks of 64 channels x 128 rows x 128 B)
+        {
+          float va[32], vb[32];
+          auto put = [&](float (&v)[32], int c0) {
+            if (ypos) {
+              float4* yp = reinterpret_cast<float4*>(ypos + c0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) yp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            const uint32_t rowbase = a2_0 + (uint32_t)(c0 >> 6) * 16384u + rrow * 128u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {      // 8 channels = one 16-byte chunk
+              float4 b0, b1v;
+              asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b0.x), "=f"(b0.y), "=f"(b0.z), "=f"(b0.w) : "r"(evs + 4u * (c0 + 8 * j)));
+              asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b1v.x), "=f"(b1v.y), "=f"(b1v.z), "=f"(b1v.w) : "r"(evs + 4u * (c0 + 8 * j + 4)));
+              const uint32_t p0 = pack_h2(fmaxf(v[8 * j] + b0.x, 0.f), fmaxf(v[8 * j + 1] + b0.y, 0.f));
+              const uint32_t p1 = pack_h2(fmaxf(v[8 * j + 2] + b0.z, 0.f), fmaxf(v[8 * j + 3] + b0.w, 0.f));
+              const uint32_t p2 = pack_h2(fmaxf(v[8 * j + 4] + b1v.x, 0.f), fmaxf(v[8 * j + 5] + b1v.y, 0.f));
+              const uint32_t p3 = pack_h2(fmaxf(v[8 * j + 6] + b1v.z, 0.f), fmaxf(v[8 * j + 7] + b1v.w, 0.f));
+              const uint32_t chunk = (uint32_t)(((c0 & 63) >> 3) + j);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowbase + ((chunk ^ (rrow & 7u)) << 4)), "r"(p0), "r"(p1),
+                           "r"(p2), "r"(p3) : "memory");
+            }
+          };
+          tmem_ld32_issue(taddr + (uint32_t)tcb, va);
+          tmem_ld_wait(va);
+#pragma unroll 1
+          for (int c0 = tcb; c0 < tce; c0 += 64) {
+            tmem_ld32_issue(taddr + (uint32_t)(c0 + 32), vb);
+            put(va, c0);
+            tmem_ld_wait(vb);
+            if (c0 + 64 < tce) tmem_ld32_issue(taddr + (uint32_t)(c0 + 64), va);
+            put(vb, c0 + 32);
+            if (c0 + 64 < tce) tmem_ld_wait(va);
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes of A2 -> visible to the tensor core
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cluster_release(mapa_rank(a2_full, 0));
+          else mbar_arrive(a2_full);
+        }
+        // logits of this row: ncp columns at the start of the same TMEM stage
+        mbar_wait(d2_full, it & 1u);
+        tc_fence_after();
+        const int a = half >> 1, b = half & 1;
+        float* out = mt.masks + ((((size_t)roi * 2 * mt.H + 2 * hh + a) * 2 * mt.W) + 2 * ww + b) * mt.NC;
+        const int nch = mt.ncp >> 4, chstep = EL == 2 ? 2 : 1;
+        int lastch = eh;
+        while (lastch + chstep < nch) lastch += chstep;
+        bool released = false;
+#pragma unroll 1
+        for (int ch = eh; ch < nch; ch += chstep) {
+          float lgv[16];
+          tmem_ld16(taddr + (uint32_t)(ch * 16), lgv);
+          if (ch == lastch) {      // every TMEM read of this warp is done: hand the stage back before the sigmoids
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (CG == 2) mbar_arrive_cluster(mapa_rank(t_empty(ts), 0));
+              else mbar_arrive(t_empty(ts));
+            }
+            released = true;
+          }
+          if (valid) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              const int cls = ch * 16 + k;
+              if (cls < mt.NC) out[cls] = 1.f / (1.f + expf(-(lgv[k] + evec[256 + cls])));
+            }
+          }
+        }
+        if (!released) {           // a warp without a logits chunk of its own (ncp = 16 and the quarter's second warp)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (CG == 2) mbar_arrive_cluster(mapa_rank(t_empty(ts), 0));
+            else mbar_arrive(t_empty(ts));
+          }
+        }
+        continue;
+      }
       if (WBN == 256 && mt.masks) {
 #pragma unroll 1
         // the tail is bound by the latency of ONE warp per scheduler (ncu: 0.35 IPC, shared-memory pipe 36 %), so with
@@ -654,6 +789,13 @@ using namespace myolo;
 using namespace myolo::tc;
 
 
+// largest dynamic shared memory a CTA-pair launch may ask for (227 KB minus the static barriers)
+constexpr uint32_t kWinSmemMax = 230400u;
+// tensor-core mask tail: shared memory = alignment slack + windows + weight stages + A2 (64 KB) + B2 + epilogue vectors
+static uint32_t tail_smem(int nawin, int nwb, int ncp) {
+  return 1024u + (uint32_t)nawin * (uint32_t)win_rows(1) * 128u + (uint32_t)nwb * 16384u + 65536u + (uint32_t)(ncp / 2) * 512u + 2048u;
+}
+
 // min_m: smallest M for which a plain (single-tap) GEMM is routed here
 static int win_shape_ok(long long lda, long long ldc, long long M, int N, int K, int ntaps, const int* shifts_host,
                         int accumulate, long long min_m) {
@@ -762,8 +904,8 @@ static int launch_win(const float* A, long long lda, const float* Bt, float* C, 
     MYOLO_CUDA(cudaFuncSetAttribute(tc_conv_win_kernel<256, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem(1)));
     MYOLO_CUDA(cudaFuncSetAttribute(tc_conv_win_kernel<128, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem(2)));
     MYOLO_CUDA(cudaFuncSetAttribute(tc_conv_win_kernel<256, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem(2)));
-    MYOLO_CUDA(cudaFuncSetAttribute(tc_conv_win_kernel<256, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem(1)));
-    MYOLO_CUDA(cudaFuncSetAttribute(tc_conv_win_kernel<256, 1, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem(1)));
+    MYOLO_CUDA(cudaFuncSetAttribute(tc_conv_win_kernel<256, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinSmemMax));
+    MYOLO_CUDA(cudaFuncSetAttribute(tc_conv_win_kernel<256, 1, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinSmemMax));
     {   // how many CTA pairs fit at once (GPCs with an odd SM count leave SMs unpaired)
       cudaLaunchConfig_t q = {};
       q.gridDim = dim3(kNumSMs);
@@ -786,13 +928,23 @@ static int launch_win(const float* A, long long lda, const float* Bt, float* C, 
          hio.on ? (const void*)bnb.a : nullptr, hio.on ? hio.no_f32 : 0, (hio.on && hio.Ch) ? 1 : 0, hio.acc_scale};
   cudaStream_t st = as_stream(stream);
   const int maxcl = hio.on ? max_clusters_h : max_clusters;
+  MaskTail mtl = mt;
+  uint32_t smem_pair = win_smem(1);
+  if (mtl.masks && mtl.tc) {
+    // ring depths that fit next to A2 / B2: four windows while the class block is small, three for many classes
+    MYOLO_CHECK_ARG(cg == 2 && maxcl > 0 && ntaps == 1 && N == 1024 && K == 256 && mtl.ncp >= 16 && mtl.ncp <= 128 && (mtl.ncp % 16) == 0);
+    mtl.nwb = 4;
+    mtl.nawin = tail_smem(4, 4, mtl.ncp) <= kWinSmemMax ? 4 : 3;
+    smem_pair = tail_smem(mtl.nawin, mtl.nwb, mtl.ncp);
+    MYOLO_CHECK_ARG(smem_pair <= kWinSmemMax);
+  }
   if (cg == 2 && maxcl > 0) {
     const int nitems = (int)ceil_div(M, 256) * (N / wbn);
     const int ncl = nitems < maxcl ? nitems : maxcl;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * ncl);
     cfg.blockDim = dim3(win_threads(hio.on ? 2 : 4));
-    cfg.dynamicSmemBytes = win_smem(1);
+    cfg.dynamicSmemBytes = smem_pair;
     cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -800,9 +952,9 @@ static int launch_win(const float* A, long long lda, const float* Bt, float* C, 
     cfg.attrs = at;
     cfg.numAttrs = 1;
     if (hio.on)
-      MYOLO_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_win_kernel<256, 1, 2, 2>, ta, tb, tc_, tch, M, N, K, ntaps, sh, ep, mt, nitems, bo_mode));
+      MYOLO_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_win_kernel<256, 1, 2, 2>, ta, tb, tc_, tch, M, N, K, ntaps, sh, ep, mtl, nitems, bo_mode));
     else
-      MYOLO_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_win_kernel<256, 1, 2>, ta, tb, tc_, tch, M, N, K, ntaps, sh, ep, mt, nitems, bo_mode));
+      MYOLO_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_win_kernel<256, 1, 2>, ta, tb, tc_, tch, M, N, K, ntaps, sh, ep, mtl, nitems, bo_mode));
     return MYOLO_OK;
   }
   if (hio.on) {
@@ -835,14 +987,38 @@ extern "C" int myolo_gemm_taps_win(const float* A, long long lda, const float* B
                     mt, stream);
 }
 
-extern "C" int myolo_deconv_mask_fwd_supported(int Cmid, int NC) { return Cmid == 256 && NC >= 1 && NC <= 7; }
+extern "C" int myolo_deconv_mask_fwd_supported(int Cmid, int NC) { return Cmid == 256 && NC >= 1 && NC <= 128; }
+
+// which tail the fused kernel runs: exact-fp32 FMA chains in the epilogue registers (NC <= 7: measured 0.81 ms against
+// 1.07 ms for the tensor-core tail at 4 classes -- the logits take the place of the accumulator stage, so the stage is
+// handed back only after a GEMM that queues behind the next item's main loop) or the 1x1 conv as a second tcgen05 GEMM
+// (8 <= NC <= 128, where the FMA chains would cost more than the deconvolution itself).
+// MYOLO_MASK_TAIL = ffma | tc overrides the choice where both exist (A/B measurements).
+static int tail_on_tensor_core(int NC, int half_flavour) {
+  if (NC > 7) return 1;
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("MYOLO_MASK_TAIL");
+    mode = e && strcmp(e, "ffma") == 0 ? 1 : (e && strcmp(e, "tc") == 0 ? 2 : 0);
+  }
+  (void)half_flavour;
+  if (mode == 2) return 1;
+  return 0;
+}
+static MaskTail make_tail(const float* bd, const float* w1, const float* b1, float* masks, const int* ids, float* y4, int H,
+                          int W, int NC, int half_flavour) {
+  MaskTail mt{bd, w1, b1, masks, ids, y4, H, W, NC, 0, 0, 0, 0};
+  mt.tc = tail_on_tensor_core(NC, half_flavour);
+  mt.ncp = (NC + 15) / 16 * 16;
+  return mt;
+}
 
 extern "C" int myolo_deconv_mask_fwd(const float* a4, const float* kd, const float* bd, const float* w1, const float* b1,
                                      float* masks, const int* target_ids, float* y4, int n_roi, int H, int W, int Cmid,
                                      int NC, myolo_stream stream) {
   MYOLO_CHECK_ARG(a4 && kd && bd && w1 && b1 && masks && y4 && n_roi > 0 && H > 0 && W > 0);
   MYOLO_CHECK_ARG(myolo_deconv_mask_fwd_supported(Cmid, NC));
-  MaskTail mt{bd, w1, b1, masks, target_ids, y4, H, W, NC};
+  MaskTail mt = make_tail(bd, w1, b1, masks, target_ids, y4, H, W, NC, 0);
   const long long M = (long long)n_roi * (H + 1) * (W + 1);
   return launch_win(a4, Cmid, kd, y4, 4 * Cmid, M, 4 * Cmid, Cmid, 1, nullptr, nullptr, nullptr, nullptr, MYOLO_ACT_NONE,
                     W + 1, (H + 1) * (W + 1), 0, mt, stream);
@@ -895,7 +1071,7 @@ extern "C" int myolo_deconv_mask_fwd_h(const void* a4, const void* kd, const flo
                                        int NC, myolo_stream stream) {
   MYOLO_CHECK_ARG(a4 && kd && bd && w1 && b1 && masks && y4 && n_roi > 0 && H > 0 && W > 0);
   MYOLO_CHECK_ARG(myolo_deconv_mask_fwd_supported(Cmid, NC));
-  MaskTail mt{bd, w1, b1, masks, target_ids, y4, H, W, NC};
+  MaskTail mt = make_tail(bd, w1, b1, masks, target_ids, y4, H, W, NC, 1);
   const long long M = (long long)n_roi * (H + 1) * (W + 1);
   HalfIO hio{1, nullptr, 0, 1, nullptr};
   return launch_win(reinterpret_cast<const float*>(a4), Cmid, reinterpret_cast<const float*>(kd), y4, 4 * Cmid, M, 4 * Cmid,

@@ -37,8 +37,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * 8 + 1];
   __shared__ uint32_t tmem_slot;
+  __shared__ float colacc[4][2][BN];   // epilogue statistics: per-column sum / sum of squares, one slot per epilogue warp
+                                       // (summed in a fixed order afterwards: the statistics are reproducible run to run)
+  __shared__ int s_last;
   constexpr uint32_t kABytes = BM * BK * 4, kBBytes = BN * BK * 4, kStage = kABytes + kBBytes;
   constexpr uint32_t kCols = BN < 32 ? 32 : BN;
+
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long m0 = (long long)blockIdx.x * BM;
@@ -124,6 +128,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (ep.bias) t += __ldg(ep.bias + n);
             if (ep.scale) t = fmaf(t, __ldg(ep.scale + n), __ldg(ep.shift + n));
             o[e] = apply_act(t, ep.act);
+            v[j + e] = o[e];
           }
           float4* dst = reinterpret_cast<float4*>(crow + c0 + j);
           float4 r = make_float4(o[0], o[1], o[2], o[3]);
@@ -134,11 +139,45 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           *dst = r;
         }
       }
+      if (ep.st_sums) {     // warp-uniform: column sums of the stored values over this warp's 32 rows (invalid rows count 0)
+        float sq[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          v[j] = valid ? v[j] : 0.f;
+          sq[j] = v[j] * v[j];
+        }
+        const float s0 = warp_colsum32(v, lane), s1 = warp_colsum32(sq, lane);
+        colacc[q][0][c0 + lane] = s0;
+        colacc[q][1][c0 + lane] = s1;
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, kCols);
+  if (ep.st_sums == nullptr) return;
+  for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) {
+    const int which = i / BN, n = i - which * BN;
+    atomicAdd(ep.st_sums + (size_t)which * N + n0 + n,
+              ((double)colacc[0][which][n] + (double)colacc[1][which][n]) + ((double)colacc[2][which][n] + (double)colacc[3][which][n]));
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ep.st_ticket + blockIdx.y, 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int n = threadIdx.x; n < BN; n += blockDim.x) {
+    const int c = n0 + n;
+    const double S0 = *(volatile double*)(ep.st_sums + c), S1 = *(volatile double*)(ep.st_sums + N + c);
+    const double mean = S0 * ep.st_inv;
+    const double var = S1 * ep.st_inv - mean * mean;
+    ep.st_mean[c] = (float)mean;
+    ep.st_var[c] = (float)(var > 0.0 ? var : 0.0);
+    ep.st_sums[c] = 0.0;
+    ep.st_sums[N + c] = 0.0;
+  }
+  if (threadIdx.x == 0) ep.st_ticket[blockIdx.y] = 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -500,10 +539,10 @@ extern "C" int myolo_gemm_taps_tc_supported(long long lda, long long ldc, long l
          ntaps >= 1 && ntaps <= 32 && (long long)ntaps * N < (1LL << 31);
 }
 
-extern "C" int myolo_gemm_taps_tc(const float* A, long long lda, const float* Bt, float* C, long long ldc, long long M,
-                                  int N, int K, int ntaps, const int* shifts_host, const float* bias,
-                                  const float* scale, const float* shift_c, int act, int pf_w1, int pf_blk,
-                                  int accumulate, myolo_stream stream) {
+static int gemm_taps_tc_impl(const float* A, long long lda, const float* Bt, float* C, long long ldc, long long M, int N, int K,
+                             int ntaps, const int* shifts_host, const float* bias, const float* scale, const float* shift_c,
+                             int act, int pf_w1, int pf_blk, int accumulate, float* st_mean, float* st_var, double* ws,
+                             long long n_valid, myolo_stream stream) {
   MYOLO_CHECK_ARG(A && Bt && C && aligned16(A) && aligned16(Bt) && aligned16(C));
   MYOLO_CHECK_ARG(myolo_gemm_taps_tc_supported(lda, ldc, M, N, K, ntaps, accumulate));
   MYOLO_CHECK_ARG((scale == nullptr) == (shift_c == nullptr));
@@ -522,6 +561,14 @@ extern "C" int myolo_gemm_taps_tc(const float* A, long long lda, const float* Bt
   rc = get_map(Bt, (long long)ntaps * N, K, K, bn, &tb);
   if (rc) return rc;
   Epi ep{bias, scale, shift_c, act, pf_w1, pf_blk, accumulate};
+  if (st_mean) {      // statistics of the stored result in the epilogue: workspace layout of the BN family (bn.cu)
+    MYOLO_CHECK_ARG(st_var && ws && N <= 1024 && n_valid > 0 && !accumulate);
+    ep.st_sums = ws + 16;
+    ep.st_ticket = reinterpret_cast<int*>(ws);
+    ep.st_mean = st_mean;
+    ep.st_var = st_var;
+    ep.st_inv = 1.0 / (double)n_valid;
+  }
   cudaStream_t st = as_stream(stream);
   switch (bn) {
     case 256: return launch_gemm<256>(ta, tb, C, ldc, M, N, K, ntaps, sh, ep, st);
@@ -529,6 +576,24 @@ extern "C" int myolo_gemm_taps_tc(const float* A, long long lda, const float* Bt
     case 64: return launch_gemm<64>(ta, tb, C, ldc, M, N, K, ntaps, sh, ep, st);
     default: return launch_gemm<32>(ta, tb, C, ldc, M, N, K, ntaps, sh, ep, st);
   }
+}
+
+extern "C" int myolo_gemm_taps_tc(const float* A, long long lda, const float* Bt, float* C, long long ldc, long long M,
+                                  int N, int K, int ntaps, const int* shifts_host, const float* bias,
+                                  const float* scale, const float* shift_c, int act, int pf_w1, int pf_blk,
+                                  int accumulate, myolo_stream stream) {
+  return gemm_taps_tc_impl(A, lda, Bt, C, ldc, M, N, K, ntaps, shifts_host, bias, scale, shift_c, act, pf_w1, pf_blk, accumulate,
+                           nullptr, nullptr, nullptr, 0, stream);
+}
+
+// the same GEMM with the batch statistics of its result (per output channel, over the valid rows: n_valid of them) taken
+// in the epilogue -- the BatchNormalization that follows a pointwise convolution needs no statistics pass of its own
+extern "C" int myolo_gemm_taps_tc_stats(const float* A, long long lda, const float* Bt, float* C, long long ldc, long long M,
+                                        int N, int K, int ntaps, const int* shifts_host, int pf_w1, int pf_blk,
+                                        float* mean, float* var, double* ws, long long n_valid, myolo_stream stream) {
+  MYOLO_CHECK_ARG(mean && var && ws);
+  return gemm_taps_tc_impl(A, lda, Bt, C, ldc, M, N, K, ntaps, shifts_host, nullptr, nullptr, nullptr, MYOLO_ACT_NONE, pf_w1,
+                           pf_blk, 0, mean, var, ws, n_valid, stream);
 }
 
 extern "C" int myolo_gemm_taps_wgrad_tc_supported(long long lda, long long ldd, long long M, int N, int K, int ntaps) {
@@ -569,6 +634,9 @@ struct PrepJob {
   const float* in;
   void* out;
   int ntaps, rows, cols, transpose, mode, tile_begin;
+  int out_ld;      // leading dimension of the staged matrix (0 = dense: rows when transposing, cols otherwise); a larger
+                   // value leaves zero padding columns / rows that the job never writes (conv_23: 27 -> 32 channels)
+  int out_total;   // elements between the hi / hi / lo copies of mode 2 (0 = ntaps*rows*cols)
 };
 __global__ void prep_weights_batch_kernel(const PrepJob* __restrict__ jobs, int n_jobs) {
   __shared__ float t[32][33];
@@ -583,7 +651,8 @@ __global__ void prep_weights_batch_kernel(const PrepJob* __restrict__ jobs, int 
   const int tap = tile / (tx * ty);
   tile -= tap * tx * ty;
   const int by = tile / tx, bx = tile - by * tx;
-  const size_t per_tap = (size_t)jb.rows * jb.cols, total = per_tap * jb.ntaps;
+  const size_t per_tap = (size_t)jb.rows * jb.cols, total = jb.out_total > 0 ? (size_t)jb.out_total : per_tap * jb.ntaps;
+  const size_t ld_t = jb.out_ld > 0 ? (size_t)jb.out_ld : (size_t)jb.rows, ld_n = jb.out_ld > 0 ? (size_t)jb.out_ld : (size_t)jb.cols;
   const float* ip = jb.in + tap * per_tap;
   float* of = reinterpret_cast<float*>(jb.out) + tap * per_tap;
   uint16_t* oh = reinterpret_cast<uint16_t*>(jb.out) + tap * per_tap;
@@ -601,7 +670,7 @@ __global__ void prep_weights_batch_kernel(const PrepJob* __restrict__ jobs, int 
     const int r = by * 32 + j;
     const float v = (r < jb.rows && c < jb.cols) ? ip[(size_t)r * jb.cols + c] : 0.f;
     if (!jb.transpose) {
-      if (r < jb.rows && c < jb.cols) emit((size_t)r * jb.cols + c, v);
+      if (r < jb.rows && c < jb.cols) emit((size_t)r * ld_n + c, v);
     } else {
       t[j][threadIdx.x] = v;
     }
@@ -611,11 +680,31 @@ __global__ void prep_weights_batch_kernel(const PrepJob* __restrict__ jobs, int 
   const int r2 = by * 32 + threadIdx.x;
   for (int j = threadIdx.y; j < 32; j += 8) {
     const int c2 = bx * 32 + j;
-    if (r2 < jb.rows && c2 < jb.cols) emit((size_t)c2 * jb.rows + r2, t[threadIdx.x][j]);
+    if (r2 < jb.rows && c2 < jb.cols) emit((size_t)c2 * ld_t + r2, t[threadIdx.x][j]);
+  }
+}
+
+// dst[r][0..cols) = src[r][0..cols) for two row pitches (columns of dst beyond `cols` are left alone)
+__global__ void copy_cols_kernel(const float* __restrict__ src, long long src_ld, float* __restrict__ dst, long long dst_ld,
+                                 long long rows, int cols) {
+  const long long total = rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    const int c = (int)(i - r * cols);
+    dst[r * dst_ld + c] = src[r * src_ld + c];
   }
 }
 }  // namespace tc
 }  // namespace myolo
+
+extern "C" int myolo_copy_cols(const float* src, long long src_ld, float* dst, long long dst_ld, long long rows, int cols,
+                               myolo_stream stream) {
+  MYOLO_CHECK_ARG(src && dst && rows > 0 && cols > 0 && src_ld >= cols && dst_ld >= cols);
+  const int blocks = (int)max(1LL, min(ceil_div(rows * cols, 256), (long long)kNumSMs * 8));
+  copy_cols_kernel<<<blocks, 256, 0, as_stream(stream)>>>(src, src_ld, dst, dst_ld, rows, cols);
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
+}
 
 extern "C" int myolo_prep_weights_batch(const void* jobs_dev, int n_jobs, int total_tiles, myolo_stream stream) {
   MYOLO_CHECK_ARG(jobs_dev && n_jobs > 0 && total_tiles > 0);

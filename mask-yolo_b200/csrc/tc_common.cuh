@@ -88,6 +88,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 16 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // split form of tmem_ld32: issue now, use the registers only after tmem_ld_wait(v) (which names them as in/out
 // operands so the compiler cannot move a use above the wait)
 __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, float* v) {
@@ -155,6 +167,22 @@ __device__ __forceinline__ bool pf_valid(long long m, int pf_w1, int pf_blk) {
   return (r / pf_w1) >= 1 && (r % pf_w1) >= 1;
 }
 
+// x[c] = this lane's (row's) value of column c.  Returns, in lane l, the sum over the 32 rows of column l
+// (butterfly transpose-reduce: 31 shuffles, no shared memory).
+__device__ __forceinline__ float warp_colsum32(float (&x)[32], int lane) {
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) {
+    const bool up = (lane & w) != 0;
+#pragma unroll
+    for (int i = 0; i < w; ++i) {
+      const float send = up ? x[i] : x[i + w];
+      const float keep = up ? x[i + w] : x[i];
+      x[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+    }
+  }
+  return x[0];
+}
+
 struct Epi {
   const float* bias;
   const float* scale;
@@ -174,6 +202,14 @@ struct Epi {
   int has_h;              // store the result as half through the second output map (the fp32 copy, when also
                           // stored, is the half-rounded value so both consumers see the same numbers)
   const float* acc_scale; // device scalar multiplied into the accumulator before the epilogue (nullable)
+  // batch statistics of the stored result in the epilogue (tc_gemm_kernel only): per-column sum / sum of
+  // squares over the valid rows, fp64 workspace of the BN family (bn.cu: zero before, zero after), the CTA that draws the
+  // last ticket of its column tile writes mean / biased variance.  st_sums == nullptr: off.
+  double* st_sums;        // [2][N]
+  int* st_ticket;         // one counter per column tile
+  float* st_mean;
+  float* st_var;
+  double st_inv;          // 1 / number of valid rows
 };
 
 
@@ -199,6 +235,27 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t local_addr, uint32_t rank
 // stall samples.  The hand-back orders tcgen05.ld, which tcgen05.fence::before_thread_sync already covers.)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+// cluster-scope release / acquire pair for data one CTA of the pair writes to its own shared memory with ordinary stores
+// and the pair's tensor cores then read (the A operand of the tensor-core mask tail)
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  long long t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (spin == 256) t0 = clock64();
+    if (spin > 256 && (spin & 255) == 0 && clock64() - t0 > kWatchdogCycles) __trap();
+  }
 }
 // TMA load whose completion is signalled on a barrier of the pair's LEADER CTA (cluster address)
 __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0, int c1) {

@@ -131,6 +131,11 @@ class Engine:
         self._side = torch.cuda.Stream(device=self.dev) if os.environ.get("MYOLO_BWD_STREAMS", "1") != "0" else None
         self._evs = {}
         self._replay_on = os.environ.get("MYOLO_REPLAY", "1") != "0"
+        # BatchNormalization fusions of the backbone (bit mask; A/B switch): 1 = batch statistics of a depthwise output in
+        # the depthwise kernel's epilogue, 2 = BN + ReLU6 after conv1 / a pointwise conv applied by the next depthwise
+        # kernel (forward and filter gradient) while it loads, 4 = statistics of a pointwise output in the GEMM epilogue
+        self._fuse_bn = int(os.environ.get("MYOLO_FUSE_BN", "0"))
+        self._deferred = {}
         self._plan = None
         self.t = 0                     # Adam iteration
         self.version = 0               # bumped whenever the weights change (load_params, apply_updates)
@@ -201,6 +206,14 @@ class Engine:
         for name, (o, n, shape) in self.offs.items():
             if name.endswith("/kernel") and name != "conv1/kernel":
                 self.wt[name] = torch.zeros(n * (3 if self._is_x3(name) else 1), dtype=torch.float32, device=self.dev)
+        # conv_23 (model.py:271) on tcgen05: its N_BOX*(5+NC) output channels (27 / 35 / 430) are padded to a multiple of 32
+        # with zero weights -- forward Bt [Npad][1024] (3xTF32 triple in the x3 modes), data-gradient Bt [1024][Npad]
+        self.ny = self.NB * (5 + self.NC)
+        self.ny_pad = (self.ny + 31) // 32 * 32
+        if self.tc:
+            self.wt["conv_23/kernel"] = torch.zeros(self.ny_pad * 1024 * (3 if self.x3 else 1), dtype=torch.float32, device=self.dev)
+            self.w23_d = torch.zeros(1024 * self.ny_pad, dtype=torch.float32, device=self.dev)
+            self.b23_pad = torch.zeros(self.ny_pad, dtype=torch.float32, device=self.dev)
         # "h16": IEEE-half staging of the mask-head weights.  fwd = per-tap transposed [t][Cout][Cin] (deconv: the
         # Keras layout is already [4*Cout][Cin]).
         # dgrad = the HWIO kernel as it is ([t][Cin][Cout] = Bt of the data-gradient GEMM; deconv: transposed [Cin][4*Cout]).
@@ -223,8 +236,8 @@ class Engine:
         """Does the forward GEMM of this kernel run as 3xTF32?"""
         if name.startswith("myolo_mask_conv"):
             return self.x3m
-        if name.startswith("myolo_mask") or name == "conv_23/kernel":
-            return False            # deconv: single pass; conv_23 (N=45) and the 1x1 mask conv are CUDA-core fp32
+        if name.startswith("myolo_mask"):
+            return False            # deconv: single pass; the 1x1 mask conv runs inside the deconv kernel's epilogue
         return self.x3
 
     def load_params(self, P: Dict[str, torch.Tensor], strict: bool = True):
@@ -279,32 +292,37 @@ class Engine:
         self.adam_v.zero_()
 
     def _prep_jobs(self):
-        """(src tensor, dst tensor, ntaps, rows, cols, transpose, mode) for every GEMM-side weight copy; mode as in
-        myolo_prep_weights_batch."""
+        """(src tensor, dst tensor, ntaps, rows, cols, transpose, mode, out_ld, out_total) for every GEMM-side weight copy;
+        fields as in myolo_prep_weights_batch."""
         jobs = []
         for name, buf in self.wt.items():
             mode = 2 if self._is_x3(name) else (1 if self.tc else 0)
-            if name == "conv_23/kernel":
-                mode = 0        # N = N_BOX*(5+NC) is not a tensor-core shape: always the exact CUDA-core kernel
             shape = self.offs[name][2]
-            if name == "myolo_mask_deconv/kernel":
+            if name == "conv_23/kernel":
+                if self.tc:     # zero-padded staging: [Npad][1024] per copy
+                    jobs.append((self.p[name], buf, 1, 1024, self.ny, 1, mode, 0, self.ny_pad * 1024))
+                    jobs.append((self.p[name], self.w23_d, 1, 1024, self.ny, 0, 1, self.ny_pad, 0))
+                    jobs.append((self.p["conv_23/bias"], self.b23_pad, 1, 1, self.ny, 0, 0, 0, 0))
+                else:           # exact CUDA-core kernel: plain transposed copy
+                    jobs.append((self.p[name], buf, 1, 1024, self.ny, 1, 0, 0, 0))
+            elif name == "myolo_mask_deconv/kernel":
                 # Keras [2,2,Cout,Cin] is already the forward Bt ([N=4*Cout][K=Cin]); stage its
                 # transpose [Cin][4*Cout] for the dgrad GEMM.
-                jobs.append((self.p[name], buf, 1, 4 * shape[2], shape[3], 1, mode))
+                jobs.append((self.p[name], buf, 1, 4 * shape[2], shape[3], 1, mode, 0, 0))
             else:
-                jobs.append((self.p[name], buf, shape[0] * shape[1], shape[2], shape[3], 1, mode))
+                jobs.append((self.p[name], buf, shape[0] * shape[1], shape[2], shape[3], 1, mode, 0, 0))
         for name, buf in self.wth.items():
             shape = self.offs[name][2]
             if name == "myolo_mask_deconv/kernel":
-                jobs.append((self.p[name], buf, 1, 4 * shape[2], shape[3], 0, 3))
+                jobs.append((self.p[name], buf, 1, 4 * shape[2], shape[3], 0, 3, 0, 0))
             else:
-                jobs.append((self.p[name], buf, shape[0] * shape[1], shape[2], shape[3], 1, 3))
+                jobs.append((self.p[name], buf, shape[0] * shape[1], shape[2], shape[3], 1, 3, 0, 0))
         for name, buf in self.wth_d.items():
             shape = self.offs[name][2]
             if name == "myolo_mask_deconv/kernel":
-                jobs.append((self.p[name], buf, 1, 4 * shape[2], shape[3], 1, 3))
+                jobs.append((self.p[name], buf, 1, 4 * shape[2], shape[3], 1, 3, 0, 0))
             else:
-                jobs.append((self.p[name], buf, shape[0] * shape[1], shape[2], shape[3], 0, 3))
+                jobs.append((self.p[name], buf, shape[0] * shape[1], shape[2], shape[3], 0, 3, 0, 0))
         if self.h16:    # the tf32 staging of the mask-head weights is never read in h16 mode
             jobs = [j for j in jobs if not (j[6] != 3 and any(j[1] is self.wt[n] for n in self.wth))]
         return jobs
@@ -316,8 +334,8 @@ class Engine:
             import struct
             rec, tiles = b"", 0
             jobs = self._prep_jobs()
-            for src, dst, ntaps, rows, cols, tr, mode in jobs:
-                rec += struct.pack("<QQiiiiii", src.data_ptr(), dst.data_ptr(), ntaps, rows, cols, tr, mode, tiles)
+            for src, dst, ntaps, rows, cols, tr, mode, out_ld, out_total in jobs:
+                rec += struct.pack("<QQiiiiiiii", src.data_ptr(), dst.data_ptr(), ntaps, rows, cols, tr, mode, tiles, out_ld, out_total)
                 tiles += ntaps * ((rows + 31) // 32) * ((cols + 31) // 32)
             self._prep_table = torch.frombuffer(bytearray(rec), dtype=torch.uint8).to(self.dev)
             self._prep_n, self._prep_tiles = len(jobs), tiles
@@ -343,6 +361,8 @@ class Engine:
                 self.c4 = PF(B, Ho, Ho, co, device=dev, split=self.x3)   # C4 feeds the 3x3 feature_map conv
                 if self.x3:
                     A["ap6"] = f(B, Ho, Ho, co)                   # full-precision C4 for the depthwise consumer
+            elif k == 14 and self.x3:
+                A[f"ap{k}"] = f(2, B, Ho, Ho, co)                 # hi / lo operand pair of the 3xTF32 conv_23 GEMM
             else:
                 A[f"ap{k}"] = f(B, Ho, Ho, co)
             maxel = max(maxel, B * H * H * ci, B * Ho * Ho * co)
@@ -351,6 +371,10 @@ class Engine:
         G, NB, NC, R = self.cfg["G"], self.NB, self.NC, self.R
         assert H == G
         A["yolo"] = f(B, G, G, NB * (5 + NC))
+        if self.tc:     # tensor-core conv_23: result / gradient with the channel count padded to a multiple of 32
+            A["yolo_pad"] = torch.zeros(B * G * G, self.ny_pad, dtype=torch.float32, device=dev)
+            if self.mode != "inference":
+                A["dyolo_pad"] = torch.zeros(B * G * G, self.ny_pad, dtype=torch.float32, device=dev)
         A["proposals"] = f(B, R, 4)
         A["detections"] = f(B, R, 6)
         self.loss_yolo = torch.zeros(5, device=dev)
@@ -406,14 +430,19 @@ class Engine:
         n, h, w, c = t.shape
         return C.view(t, n, h, w, c)
 
-    def _bn_fwd(self, name, xv, yv, act, training, n_pix, yv_lo=None):
+    def _bn_fwd(self, name, xv, yv, act, training, n_pix, yv_lo=None, stats=True, apply=True):
+        """stats=False: the producing kernel has already left the batch statistics in b.mean / b.var (epilogue fusion);
+        apply=False: the consumer applies the normalisation + activation while it loads (no post-BN tensor)."""
         b, st = self.bn[name], self._st()
         if training:
-            C.call("myolo_bn_stats", xv, b.mean, b.var, self.ws, st)
+            if stats:
+                C.call("myolo_bn_stats", xv, b.mean, b.var, self.ws, st)
             self._bn_touched.append((b, n_pix))
             mean, var = b.mean, b.var
         else:
             mean, var = b.mmean, b.mvar
+        if not apply:
+            return
         if yv_lo is None:
             C.call("myolo_bn_apply", xv, yv, mean, var, b.gamma, b.beta, BN_EPS, act, st)
         else:
@@ -439,6 +468,17 @@ class Engine:
                act, pf_w1, pf_blk, 0, self._st() if stream is None else stream)
         if timed:
             C.record_py(self._ke_end)
+
+    def _gemm_fwd_stats(self, a_rows, lo_off, name, out_rows, M, N, K, b):
+        """Pointwise forward GEMM on the one-tile tcgen05 kernel with the batch statistics of its result (BN layer `b`)
+        reduced in the epilogue; 3xTF32 operand triple as in _gemm_fwd."""
+        sh = [0, lo_off, 0] if self._is_x3(name) else [0]
+        key = (name, tuple(sh))
+        arr = self._shift_cache.get(key)
+        if arr is None:
+            arr = self._shift_cache[key] = C.int_array(sh)
+        C.call("myolo_gemm_taps_tc_stats", a_rows, K, self.wt[name], out_rows, N, M, N, K, len(sh), arr, 0, 0, b.mean, b.var,
+               self.ws, M, self._st())
 
     def _ke_begin(self):
         """bench.py hook: CUDA events around the dominant kernel (only while kernel_events is a list)"""
@@ -469,33 +509,70 @@ class Engine:
         self._bn_touched: List = []
         self._image = image
         relu6 = C.ACT_RELU6
+        # Fusions of the backbone's BatchNormalization layers (training phase only):
+        #   * batch statistics of a depthwise / pointwise output are reduced in the epilogue of the kernel that produces it;
+        #   * BN + ReLU6 after conv1 and after a pointwise conv is applied by the NEXT depthwise kernel while it stages its
+        #     input (and again by that layer's filter-gradient kernel in the backward pass): the post-BN activation is
+        #     never written, except where a GEMM reads it through TMA (block 6 -> feature_map, block 14 -> conv_23).
+        fm = self._fuse_bn if training else 0
+        fuse, dw_stats = bool(fm & 2), bool(fm & 1)
+        self._deferred = {}          # block id (0 = conv1) -> BN layer whose apply was left to the consumer
         # conv_block (model.py:42-52)
         C.call("myolo_conv1_fwd", image, self.p["conv1/kernel"], A["y0"], B, S, 32, st)
-        self._bn_fwd("conv1_bn", self._v(A["y0"]), self._v(A["a0"]), relu6, training, B * (S // 2) ** 2)
-        xin_view = self._v(A["a0"])
+        self._bn_fwd("conv1_bn", self._v(A["y0"]), self._v(A["a0"]), relu6, training, B * (S // 2) ** 2, apply=not fuse)
+        xin_view = self._v(A["y0"] if fuse else A["a0"])
+        in_bn = self.bn["conv1_bn"] if fuse else None
+        if fuse:
+            self._deferred[0] = in_bn
         for k, ci, co, s in BACKBONE_BLOCKS + YOLO_BLOCKS:
             Hi, Ho, _, _, _ = self.geo[k]
             npix = B * Ho * Ho
             # _depthwise_conv_block: ZeroPad(1,1) + depthwise 3x3 VALID stride s -> BN -> ReLU6
-            C.call("myolo_dwconv3x3_fwd", xin_view, self.p[f"conv_dw_{k}/depthwise_kernel"], A[f"yd{k}"], s, st)
+            bd = self.bn[f"conv_dw_{k}_bn"]
+            if fuse or dw_stats:
+                ib = in_bn
+                C.call("myolo_dwconv3x3_fwd_bn", xin_view, self.p[f"conv_dw_{k}/depthwise_kernel"], A[f"yd{k}"], s,
+                       ib.mean if ib else None, ib.var if ib else None, ib.gamma if ib else None, ib.beta if ib else None,
+                       BN_EPS, relu6, bd.mean if dw_stats else None, bd.var if dw_stats else None,
+                       self.ws if dw_stats else None, st)
+            else:
+                C.call("myolo_dwconv3x3_fwd", xin_view, self.p[f"conv_dw_{k}/depthwise_kernel"], A[f"yd{k}"], s, st)
             ad = A[f"ad{k}"]
             if self.x3:
-                self._bn_fwd(f"conv_dw_{k}_bn", self._v(A[f"yd{k}"]), self._v(ad[0]), relu6, training, npix, self._v(ad[1]))
+                self._bn_fwd(f"conv_dw_{k}_bn", self._v(A[f"yd{k}"]), self._v(ad[0]), relu6, training, npix, self._v(ad[1]),
+                             stats=not dw_stats)
             else:
-                self._bn_fwd(f"conv_dw_{k}_bn", self._v(A[f"yd{k}"]), self._v(ad), relu6 | self.rnd, training, npix)
+                self._bn_fwd(f"conv_dw_{k}_bn", self._v(A[f"yd{k}"]), self._v(ad), relu6 | self.rnd, training, npix, stats=not dw_stats)
             # pointwise 1x1 -> BN -> ReLU6
-            self._gemm_fwd(ad, npix, f"conv_pw_{k}/kernel", A[f"yp{k}"], npix, co, ci, None, None, 0, 0)
+            pw_stats = bool(fm & 4) and self.tc
+            if pw_stats:
+                self._gemm_fwd_stats(ad, npix, f"conv_pw_{k}/kernel", A[f"yp{k}"], npix, co, ci, self.bn[f"conv_pw_{k}_bn"])
+            else:
+                self._gemm_fwd(ad, npix, f"conv_pw_{k}/kernel", A[f"yp{k}"], npix, co, ci, None, None, 0, 0)
+            defer = fuse and k not in (6, 14)
+            in_bn = None
             if k == 6 and self.with_mask:
                 if self.x3:
                     out_view = self._v(A["ap6"])
-                    self._bn_fwd(f"conv_pw_{k}_bn", self._v(A[f"yp{k}"]), out_view, relu6, training, npix)
+                    self._bn_fwd(f"conv_pw_{k}_bn", self._v(A[f"yp{k}"]), out_view, relu6, training, npix, stats=not pw_stats)
                     C.call("myolo_split_tf32", out_view, self.c4.view(), self.c4.view(lo=True), st)
                 else:
                     out_view = self.c4.view()
-                    self._bn_fwd(f"conv_pw_{k}_bn", self._v(A[f"yp{k}"]), out_view, relu6 | self.rnd, training, npix)
+                    self._bn_fwd(f"conv_pw_{k}_bn", self._v(A[f"yp{k}"]), out_view, relu6 | self.rnd, training, npix,
+                                 stats=not pw_stats)
+            elif defer:
+                self._bn_fwd(f"conv_pw_{k}_bn", self._v(A[f"yp{k}"]), None, relu6, training, npix, stats=not pw_stats, apply=False)
+                out_view = self._v(A[f"yp{k}"])
+                in_bn = self.bn[f"conv_pw_{k}_bn"]
+                self._deferred[k] = in_bn
+            elif k == 14 and self.x3:
+                out_view = self._v(A["ap14"][0])
+                self._bn_fwd(f"conv_pw_{k}_bn", self._v(A[f"yp{k}"]), out_view, relu6, training, npix, self._v(A["ap14"][1]),
+                             stats=not pw_stats)
             else:
                 out_view = self._v(A[f"ap{k}"])
-                self._bn_fwd(f"conv_pw_{k}_bn", self._v(A[f"yp{k}"]), out_view, relu6, training, npix)
+                self._bn_fwd(f"conv_pw_{k}_bn", self._v(A[f"yp{k}"]), out_view, relu6 | (self.rnd if k == 14 else 0), training,
+                             npix, stats=not pw_stats)
             xin_view = out_view
             if k == 6 and self.with_mask:
                 # myolo_feature_maps = Conv2D(256, 3x3, SAME)(C4) + bias   (model.py:848)
@@ -516,8 +593,20 @@ class Engine:
                     self._fm_pending = True
         G, NB, NC = self.cfg["G"], self.NB, self.NC
         # conv_23 (model.py:271) + reshape [B,G,G,NB,5+NC] (273): a pure view of the NHWC result
-        C.call("myolo_gemm_taps_ffma", A["ap14"], 1024, self.wt["conv_23/kernel"], A["yolo"], NB * (5 + NC), B * G * G,
-               NB * (5 + NC), 1024, 1, None, self.p["conv_23/bias"], None, None, C.ACT_NONE, 0, 0, 0, st)
+        ny, m23 = self.ny, B * G * G
+        if self.tc:
+            # tcgen05 tiles (3xTF32 operand triple in the x3 modes) on the zero-padded channel count, bias in the epilogue;
+            # the dense [.., ny] tensor the decode / loss kernels read is then cut out of the padded result
+            sh = [0, m23, 0] if self.x3 else [0]
+            arr = self._shift_cache.get(("c23", m23, self.x3))
+            if arr is None:
+                arr = self._shift_cache[("c23", m23, self.x3)] = C.int_array(sh)
+            C.call("myolo_gemm_taps_tc", A["ap14"], 1024, self.wt["conv_23/kernel"], A["yolo_pad"], self.ny_pad, m23, self.ny_pad,
+                   1024, len(sh), arr, self.b23_pad, None, None, C.ACT_NONE, 0, 0, 0, st)
+            C.call("myolo_copy_cols", A["yolo_pad"], self.ny_pad, A["yolo"], ny, m23, ny, st)
+        else:
+            C.call("myolo_gemm_taps_ffma", A["ap14"], 1024, self.wt["conv_23/kernel"], A["yolo"], ny, m23, ny, 1024, 1, None,
+                   self.p["conv_23/bias"], None, None, C.ACT_NONE, 0, 0, 0, st)
         # DecodeYOLOLayer / DetectionsLayer (model.py:1442-1473, 1493-1538)
         C.call("myolo_yolo_decode", A["yolo"], self.anchors, A["proposals"], A["detections"], B, G, G, NB, NC, st)
         return A["yolo"].view(B, G, G, NB, 5 + NC)
@@ -726,9 +815,15 @@ class Engine:
         dy = A["dyolo"]
         C.call("myolo_colsum", self._v(dy), self.g["conv_23/bias"], self.ws, st)
         fork("f23")           # also orders the side stream after grads.zero_()
-        C.call("myolo_pwconv_wgrad", A["ap14"], dy, self.g["conv_23/kernel"], B * G * G, 1024, ny, sst)
+        ap14 = A["ap14"][0] if self.x3 else A["ap14"]
+        C.call("myolo_pwconv_wgrad", ap14, dy, self.g["conv_23/kernel"], B * G * G, 1024, ny, sst)
         gx, gy = self.gx, self.gy
-        C.call("myolo_pwconv_dgrad", dy, self.p["conv_23/kernel"], gx, B * G * G, 1024, ny, st)
+        if self.tc:     # data gradient on tcgen05: dy padded to ny_pad channels against the zero-padded [1024][ny_pad] kernel
+            C.call("myolo_copy_cols", dy, ny, A["dyolo_pad"], self.ny_pad, B * G * G, ny, st)
+            C.call("myolo_gemm_taps", A["dyolo_pad"], self.ny_pad, self.w23_d, gx, 1024, B * G * G, 1024, self.ny_pad, 1, None,
+                   None, None, None, C.ACT_NONE, 0, 0, 0, st)
+        else:
+            C.call("myolo_pwconv_dgrad", dy, self.p["conv_23/kernel"], gx, B * G * G, 1024, ny, st)
         first = True
         for k, ci, co, s in reversed(BACKBONE_BLOCKS + YOLO_BLOCKS):
             Hi, Ho, _, _, _ = self.geo[k]
@@ -748,14 +843,21 @@ class Engine:
             C.call("myolo_pwconv_dgrad", gx, self.p[f"conv_pw_{k}/kernel"], gy, npix, ci, co, st)
             d_ad = C.view(gy, B, Ho, Ho, ci)
             self._bn_bwd(f"conv_dw_{k}_bn", self._v(A[f"yd{k}"]), d_ad, relu6, True)
-            if k == 1:
+            ib = self._deferred.get(k - 1)
+            if ib is not None:          # the block's input exists only as the producer's pre-BN output: BN + ReLU6 on load
+                xin = self._v(A["y0"] if k == 1 else A[f"yp{k - 1}"])
+            elif k == 1:
                 xin = self._v(A["a0"])
             elif k == 7 and self.with_mask and not self.x3:
                 xin = self.c4.view()
             else:
                 xin = self._v(A[f"ap{k - 1}"])
             fork("ff")
-            C.call("myolo_dwconv3x3_bwd_filter", xin, gy, self.g[f"conv_dw_{k}/depthwise_kernel"], s, sst)  # reads gy
+            if ib is not None:
+                C.call("myolo_dwconv3x3_bwd_filter_bn", xin, gy, self.g[f"conv_dw_{k}/depthwise_kernel"], s, ib.mean, ib.var,
+                       ib.gamma, ib.beta, BN_EPS, relu6, sst)                                           # reads gy
+            else:
+                C.call("myolo_dwconv3x3_bwd_filter", xin, gy, self.g[f"conv_dw_{k}/depthwise_kernel"], s, sst)  # reads gy
             mark("f_done")
             join("w_done")              # the pointwise wgrad has finished reading gx
             C.call("myolo_dwconv3x3_bwd_data", gy, self.p[f"conv_dw_{k}/depthwise_kernel"], gx, B, Hi, Hi, ci, s, st)

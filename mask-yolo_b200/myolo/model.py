@@ -561,10 +561,10 @@ class MaskYOLO:
         self.engine.set_trainable(lambda name: bool(rx.fullmatch(name.split("/")[0])))
 
     def load_weights(self, filepath, by_name=False, exclude=None):
-        """Load a checkpoint keyed by the Keras variable names: torch.save dict (what train() writes), .npz or
-        .safetensors (myolo.checkpoint; a Keras .h5 is converted once with scripts/h5_to_npz.py).  by_name tolerates
-        missing variables; `exclude` drops layers by name (model.py:1157-1196 semantics)."""
-        sd = checkpoint.select(checkpoint.read_checkpoint(filepath), exclude)
+        """Load a checkpoint keyed by the Keras variable names: a Keras 2.x .h5 weight file (myolo.h5lite), a torch.save dict
+        (what train() writes), .npz or .safetensors (myolo.checkpoint).  by_name tolerates missing variables; `exclude` drops
+        layers by name, the nested 'yolo_model' included (model.py:1157-1196 semantics)."""
+        sd = checkpoint.read_checkpoint(filepath, exclude)
         self.engine.load_params(sd, strict=not (by_name or exclude))
 
     def train(self, train_dataset, val_dataset, learning_rate, epochs, layers, augmentation=None, custom_callbacks=None,

@@ -100,3 +100,49 @@ def mask_iou(a, b, thr=0.5):
     inter = (a & b).sum(dim=(-3, -2)).double()
     union = (a | b).sum(dim=(-3, -2)).double()
     return torch.where(union > 0, inter / union.clamp(min=1), torch.ones_like(union))
+
+
+def sample_validity(rois, F_, pool=14):
+    """Sample-validity pattern of crop_and_resize for [..., 4] boxes on an F x F map, in the oracle's float32 arithmetic
+    (oracle.crop_and_resize): [n, 2, pool] booleans.  Two sets of ROI coordinates that differ in this pattern make
+    crop_and_resize zero different samples -- a discontinuity of the reference's own function, in any implementation."""
+    r = rois.detach().float().cpu().reshape(-1, 4)
+    ar = torch.arange(pool, dtype=torch.float32)[None, :]
+    pats = []
+    for lo, hi in ((0, 2), (1, 3)):
+        step = (r[:, hi] - r[:, lo]) * (F_ - 1) / (pool - 1)
+        pos = (r[:, lo] * (F_ - 1))[:, None] + ar * step[:, None]
+        pats.append((pos >= 0) & (pos <= F_ - 1))
+    return torch.stack(pats, 1)
+
+
+def step_parity(dev, ref, F_):
+    """Outputs of one fit step of the engine (`dev`) against oracle.train_step's (`ref`): the figures BASELINE.json's metric
+    asks for (box / mask IoU vs the reference path) and the 1e-3 checks of north_star.  Boxes and class scores: max abs error
+    and the same relative to the output scale (decoded boxes reach |coordinate| ~ 20 for large anchors).  Masks: over the
+    ROIs whose sample-validity pattern agrees under both sets of ROI coordinates, in images with identical ROI selection."""
+    B, R = ref["target_class_ids"].shape
+    NC = ref["myolo_mask"].shape[-1]
+    out = {}
+    for k, name in (("yolo_proposals", "box"), ("yolo_output", "class_score")):
+        r = ref[k].float()
+        e = (dev[k].detach().cpu().reshape(r.shape) - r).abs().max().item()
+        out[f"max_abs_{name}_err"] = e
+        out[f"{name}_scale"] = r.abs().max().item()
+        out[f"max_{name}_err_rel_to_scale"] = e / max(1.0, r.abs().max().item())
+    biou = box_iou_pairs(dev["yolo_proposals"], ref["yolo_proposals"])
+    same_img = (dev["target_class_ids"].cpu().int() == ref["target_class_ids"].int()).all(dim=1)
+    flips = (sample_validity(dev["output_rois"], F_) != sample_validity(ref["output_rois"], F_)).flatten(1).any(dim=1)
+    keep = same_img[:, None].expand(B, R).reshape(-1) & ~flips
+    dm = (dev["myolo_mask"].detach().cpu().reshape(B * R, -1, NC) - ref["myolo_mask"].float().reshape(B * R, -1, NC)).abs()
+    mh = int(round(dm.shape[1] ** 0.5))
+    miou = mask_iou(dev["myolo_mask"].detach().cpu().reshape(B * R, mh, mh, NC)[keep], ref["myolo_mask"].reshape(B * R, mh, mh, NC)[keep])
+    out.update(box_iou_mean=biou.mean().item(), box_iou_min=biou.min().item(),
+               mask_iou_mean=miou.mean().item(), mask_iou_min=miou.min().item(),
+               max_abs_mask_err=dm[keep].max().item() if bool(keep.any()) else None,
+               rois_compared=int(keep.sum()), rois_total=B * R, rois_with_flipped_border_sample=int(flips.sum()),
+               images_with_identical_roi_selection=int(same_img.sum()), images=B,
+               roi_selection_identical=bool(same_img.all()),
+               positive_rois=int((ref["target_class_ids"] > 0).sum().item()))
+    out["_same_img"], out["_keep"], out["_flips"] = same_img, keep, flips
+    return out

@@ -42,19 +42,6 @@ def _oracle(name):
     return _ORACLE[name]
 
 
-def _validity(rois, F_, pool=14):
-    """Sample-validity pattern of crop_and_resize for [n,4] boxes on an F x F map, in the oracle's float32 arithmetic
-    (oracle.crop_and_resize): [n, 2, pool] booleans."""
-    r = rois.detach().float().cpu().reshape(-1, 4)
-    ar = torch.arange(pool, dtype=torch.float32)[None, :]
-    pats = []
-    for lo, hi in ((0, 2), (1, 3)):
-        step = (r[:, hi] - r[:, lo]) * (F_ - 1) / (pool - 1)
-        pos = (r[:, lo] * (F_ - 1))[:, None] + ar * step[:, None]
-        pats.append((pos >= 0) & (pos <= F_ - 1))
-    return torch.stack(pats, 1)
-
-
 def _l2(a, b):
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return ((a - b).norm() / max(b.norm().item(), 1e-30)).item()
@@ -103,18 +90,14 @@ def test_train_step_matches_oracle_at_benchmark_config(name, precision):
     # lr = 0: outputs, losses and gradients are those of the oracle's step; the weights stay put for the second pass below
     out = eng.train_step(dev_in, lr=0.0)
     torch.cuda.synchronize()
+    m = Hh.step_parity(out, oout, F_)
+    same_img, keep = m["_same_img"], m["_keep"]
+    print(f"[{name}/{precision}] " + ", ".join(f"{k} {v:.3e}" if isinstance(v, float) else f"{k} {v}" for k, v in m.items() if not k.startswith("_")))
     # ---- boxes and class scores: 1e-3 absolute (relative to the output scale where that exceeds 1)
-    for k in ("yolo_proposals", "yolo_output"):
-        ref = oout[k].float()
-        err = (out[k].cpu().reshape(ref.shape) - ref).abs().max().item()
-        print(f"[{name}/{precision}] max abs error {k}: {err:.3e} (scale {ref.abs().max().item():.2f})")
-        assert err <= 1e-3 * max(1.0, ref.abs().max().item()), (k, err)
-    biou = Hh.box_iou_pairs(out["yolo_proposals"], oout["yolo_proposals"])
-    assert biou.mean().item() >= 0.999, biou.mean().item()
+    assert m["max_box_err_rel_to_scale"] <= 1e-3 and m["max_class_score_err_rel_to_scale"] <= 1e-3, m
+    assert m["box_iou_mean"] >= 0.999, m["box_iou_mean"]
     # ---- ROI selection: identical, or different only where the best IoU is within rounding of the 0.5 threshold
-    tid_e, tid_o = out["target_class_ids"].cpu(), oout["target_class_ids"].int()
-    same_img = (tid_e == tid_o).all(dim=1)
-    if not bool(same_img.all()):
+    if not m["roi_selection_identical"]:
         from oracle import myolo_oracle as O
         gtb = O.norm_boxes_graph(torch.from_numpy(batch[4]).float(), S, S)
         for b in torch.nonzero(~same_img).flatten().tolist():
@@ -122,21 +105,10 @@ def test_train_step_matches_oracle_at_benchmark_config(name, precision):
             marginal = (iou - 0.5).abs() < 2e-3
             assert bool(marginal.any()), f"image {b}: selection differs without a threshold-marginal proposal"
         assert (~same_img).sum().item() <= max(1, B // 8), "too many images with a marginal selection flip"
-    print(f"[{name}/{precision}] ROI selection identical in {int(same_img.sum())}/{B} images")
     # ---- masks, free running: all ROIs whose sample-validity pattern is the same under both sets of ROI coordinates
-    keep = same_img[:, None].expand(B, R).reshape(-1)
-    ve = _validity(out["output_rois"], F_)
-    vo = _validity(oout["output_rois"], F_)
-    flips = (ve != vo).flatten(1).any(dim=1)
-    keep = keep & ~flips
-    dm = (out["myolo_mask"].cpu().reshape(B * R, 28, 28, NC) - oout["myolo_mask"].float().reshape(B * R, 28, 28, NC)).abs()
-    worst = dm[keep].max().item()
-    print(f"[{name}/{precision}] masks: max abs error {worst:.3e} over {int(keep.sum())}/{B * R} ROIs "
-          f"({int(flips.sum())} with a flipped border sample excluded)")
-    assert flips.float().mean().item() <= 0.01 and keep.float().mean().item() >= 0.85
-    assert worst <= 1e-3, worst
-    miou = Hh.mask_iou(out["myolo_mask"].cpu().reshape(B * R, 28, 28, NC)[keep], oout["myolo_mask"].reshape(B * R, 28, 28, NC)[keep])
-    assert miou.mean().item() >= 0.999, miou.mean().item()
+    assert m["rois_with_flipped_border_sample"] <= 0.01 * B * R and m["rois_compared"] >= 0.85 * B * R, m
+    assert m["max_abs_mask_err"] <= 1e-3, m["max_abs_mask_err"]
+    assert m["mask_iou_mean"] >= 0.999, m["mask_iou_mean"]
     # ---- losses
     for k in ("yolo_sum_loss", "mask_loss"):
         lo, le = oout[k].item(), out[k].item()

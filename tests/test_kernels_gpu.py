@@ -62,6 +62,75 @@ def test_dwconv(C, B, H, W, Cc, s):
     close(dwd, wr.grad.reshape(3, 3, Cc), 2e-6, "dw bwd filter")
 
 
+@pytest.mark.parametrize("B,H,W,Cc,s", [(2, 16, 16, 32, 1), (3, 14, 14, 96, 2), (1, 13, 11, 64, 1), (4, 28, 28, 256, 2)])
+def test_dwconv_fused_bn(C, B, H, W, Cc, s):
+    """Depthwise forward with the producer's BN + ReLU6 applied on load and the batch statistics of its own output taken in
+    the epilogue; filter gradient with the same BN on load -- against the oracle's separate steps."""
+    torch.manual_seed(40)
+    xpre = torch.randn(B, H, W, Cc) * 2 + 0.5
+    w = torch.randn(3, 3, Cc, 1)
+    mean, var = torch.randn(Cc) * 0.3, torch.rand(Cc) + 0.5
+    gamma, beta = torch.rand(Cc) + 0.5, torch.randn(Cc) * 0.5
+    a = O.relu6((xpre - mean) / torch.sqrt(var + 1e-3) * gamma + beta)
+    wr = w.clone().requires_grad_(True)
+    y = O.depthwise3x3_nhwc(a, wr, s)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    ws = torch.zeros(8192, dtype=torch.float64, device="cuda")
+    xd, wd = cuda(xpre), cuda(w.reshape(3, 3, Cc))
+    md, vd, gd, bd = cuda(mean), cuda(var), cuda(gamma), cuda(beta)
+    yd = torch.empty(y.shape, device="cuda")
+    om, ov = torch.empty(Cc, device="cuda"), torch.empty(Cc, device="cuda")
+    for rep in range(2):                       # twice: the workspace must come back zeroed
+        C.call("myolo_dwconv3x3_fwd_bn", C.view(xd, B, H, W, Cc), wd, yd, s, md, vd, gd, bd, 1e-3, C.ACT_RELU6, om, ov, ws, stream())
+        close(yd, y, 5e-6, "fused dw fwd")
+        yf = y.detach().reshape(-1, Cc).double()
+        close(om, yf.mean(0).float(), 2e-5, "epilogue mean")
+        close(ov, yf.var(0, unbiased=False).float(), 2e-5, "epilogue variance")
+        assert ws.abs().max().item() == 0
+    # statistics only / BN on load only
+    a_d = cuda(a)
+    C.call("myolo_dwconv3x3_fwd_bn", C.view(a_d, B, H, W, Cc), wd, yd, s, None, None, None, None, 0.0, 0, om, ov, ws, stream())
+    close(yd, y, 2e-6, "dw fwd + stats"); close(om, yf.mean(0).float(), 2e-5, "mean")
+    C.call("myolo_dwconv3x3_fwd_bn", C.view(xd, B, H, W, Cc), wd, yd, s, md, vd, gd, bd, 1e-3, C.ACT_RELU6, None, None, None, stream())
+    close(yd, y, 5e-6, "dw fwd, BN on load")
+    dwd = torch.empty(3, 3, Cc, device="cuda")
+    C.call("myolo_dwconv3x3_bwd_filter_bn", C.view(xd, B, H, W, Cc), cuda(dy), dwd, s, md, vd, gd, bd, 1e-3, C.ACT_RELU6, stream())
+    close(dwd, wr.grad.reshape(3, 3, Cc), 6e-6, "dw bwd filter, BN on load")
+
+
+@pytest.mark.parametrize("M,K,N,x3", [(1000, 64, 64, 1), (777, 128, 256, 1), (4096 + 37, 32, 128, 0), (300, 512, 1024, 1), (130, 64, 32, 0)])
+def test_gemm_epilogue_statistics(C, M, K, N, x3):
+    """myolo_gemm_taps_tc_stats: the pointwise GEMM (3xTF32 operand triple or single pass) with per-channel batch mean /
+    biased variance of its result reduced in the epilogue, against the same GEMM + a separate statistics pass."""
+    torch.manual_seed(41)
+    A = torch.randn(M, K) * 1.5 + 0.2
+    W = torch.randn(K, N) / K ** 0.5
+    Wd = cuda(W)
+    if x3:
+        hi = A.cuda().clone()
+        lo = torch.empty_like(hi)
+        C.call("myolo_split_tf32", C.view(hi, 1, 1, M, K), C.view(hi, 1, 1, M, K), C.view(lo, 1, 1, M, K), stream())
+        Ad = torch.cat([hi, lo], 0).contiguous()
+        Wt = torch.empty(3, N, K, device="cuda")              # [B_hi | B_hi | B_lo], each transposed to [N][K]
+        C.call("myolo_prep_weights", Wd, Wt, 1, K, N, 1, 2, stream())
+        sh, nt = C.int_array([0, M, 0]), 3
+    else:
+        Ad, Wt, sh, nt = cuda(A), _prep(C, Wd, 1, K, N, 1, 1), None, 1
+    ref = torch.empty(M, N, device="cuda")
+    C.call("myolo_gemm_taps_tc", Ad, K, Wt, ref, N, M, N, K, nt, sh, None, None, None, 0, 0, 0, 0, stream())
+    out = torch.full((M, N), 7.0, device="cuda")
+    mean, var = torch.empty(N, device="cuda"), torch.empty(N, device="cuda")
+    ws = torch.zeros(8192, dtype=torch.float64, device="cuda")
+    for rep in range(2):
+        C.call("myolo_gemm_taps_tc_stats", Ad, K, Wt, out, N, M, N, K, nt, sh, 0, 0, mean, var, ws, M, stream())
+        assert torch.equal(out, ref)
+        close(mean, ref.double().mean(0).float(), 2e-5, "epilogue mean")
+        close(var, ref.double().var(0, unbiased=False).float(), 2e-5, "epilogue variance")
+        assert ws.abs().max().item() == 0
+    close(ref, (A.double() @ W.double()).float(), 2e-3 if not x3 else 3e-5, "gemm")
+
+
 # ----------------------------------------------------------------------------- K1 stem conv
 def test_conv1(C):
     torch.manual_seed(1)
@@ -522,17 +591,19 @@ def test_conv3x3_window_kernel(C, n, H, W, Ci):
         close(o2.rows, r2.rows, 2e-3, "windowed conv dgrad")
 
 
-def test_deconv_mask_fused(C):
-    """tcgen05 deconv GEMM with the mask tail in its epilogue vs the unfused exact path."""
+@pytest.mark.parametrize("n,NC", [(37, 4), (150, 7), (150, 81)])
+def test_deconv_mask_fused(C, n, NC):
+    """tcgen05 (tf32) deconv GEMM with the mask tail in its epilogue vs the unfused exact path: exact-fp32 FMA chains in
+    registers up to seven classes, a second (half-operand) tcgen05 GEMM beyond."""
     from myolo.pf import PF
     torch.manual_seed(21)
-    n, H, W, Cm, NC = 37, 14, 14, 256, 4
+    H, W, Cm = 14, 14, 256
     pa = PF(n, H, W, Cm)
     pa.valid().normal_()
     kd = torch.randn(4 * Cm, Cm, device="cuda") / Cm ** 0.5
     bd, w1, b1 = torch.randn(Cm, device="cuda") * 0.1, torch.randn(Cm, NC, device="cuda") / Cm ** 0.5, torch.randn(NC, device="cuda") * 0.1
     ids = torch.zeros(n, dtype=torch.int32, device="cuda")
-    ids[[0, 5, 36]] = torch.tensor([1, 3, 2], dtype=torch.int32, device="cuda")
+    ids[[0, 5, n - 1]] = torch.tensor([1, 3, 2], dtype=torch.int32, device="cuda")
     y_ref = PF(n, H, W, 4 * Cm)
     C.call("myolo_gemm_taps_ffma", pa.rows, Cm, kd, y_ref.rows, 4 * Cm, pa.M, 4 * Cm, Cm, 1, None, None, None, None, 0,
            W + 1, (H + 1) * (W + 1), 0, stream())
@@ -542,6 +613,8 @@ def test_deconv_mask_fused(C):
     m = torch.full((n, 2 * H, 2 * W, NC), -1.0, device="cuda")
     assert C.lib().myolo_deconv_mask_fwd_supported(Cm, NC) == 1
     C.call("myolo_deconv_mask_fwd", pa.rows, kd, bd, w1, b1, m, ids, y4.rows, n, H, W, Cm, NC, stream())
+    torch.cuda.synchronize()
+    assert m.min().item() >= 0.0, "every mask element was written"
     close(m, m_ref, 1e-3, "fused masks")
     yv, rv = y4.valid(), y_ref.valid()
     for r in range(n):
