@@ -246,6 +246,8 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
     for (int n = threadIdx.x; n < 512; n += blockDim.x) colacc[n] = 0.f;
   } else {
+    if (ep.st_sums)
+      for (int n = threadIdx.x; n < 512; n += blockDim.x) colacc[n] = 0.f;
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
       const float sc = ep.scale ? __ldg(ep.scale + n) : 1.f;
       const float b = ep.bias ? __ldg(ep.bias + n) : 0.f;
@@ -729,6 +731,9 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               if (rnd) o[e] = round_tf32(o[e]);
               if (!valid) o[e] = 0.f;   // padded-flat pad rows stay zero
             }
+            if (ep.st_sums && !st_h) {   // batch statistics of the stored result (pad rows contribute zeros)
+              v[4 * j] = o[0]; v[4 * j + 1] = o[1]; v[4 * j + 2] = o[2]; v[4 * j + 3] = o[3];
+            }
             if (st_h) {   // the half copy; v[] keeps the packed words until the 16-byte chunk is complete
               const uint32_t p0 = pack_h2(o[0], o[1]), p1 = pack_h2(o[2], o[3]);
               o[0] = h2f((uint16_t)(p0 & 0xffffu)); o[1] = h2f((uint16_t)(p0 >> 16));
@@ -756,6 +761,14 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");   // keep one group per chunk: the ring counts groups
             }
           }
+          if (ep.st_sums && !st_h && !ep.bn_a) {   // column sums of the chunk while its TMA store is in flight
+            float sq[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
+            const float s0 = warp_colsum32(v, lane), s1 = warp_colsum32(sq, lane);
+            atomicAdd(colacc + n0 + lane, s0);
+            atomicAdd(colacc + 256 + n0 + lane, s1);
+          }
         }
       }
       tc_fence_before();
@@ -769,10 +782,11 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
-  if (ep.bn_a) {   // one fp64 atomic per (CTA, column, statistic)
+  if (ep.bn_a || ep.st_sums) {   // one fp64 atomic per (CTA, column, statistic)
+    double* dst = ep.bn_a ? ep.bn_ws : ep.st_sums;
     for (int n = threadIdx.x; n < 2 * N; n += blockDim.x) {
       const float vsum = colacc[(n / N) * 256 + (n % N)];
-      if (vsum != 0.f) atomicAdd(ep.bn_ws + n, (double)vsum);
+      if (vsum != 0.f) atomicAdd(dst + n, (double)vsum);
     }
   }
   if (CG == 2) cluster_sync_all();   // no CTA of the pair may free TMEM / exit while the other still uses it
@@ -832,6 +846,7 @@ struct HalfIO {
   long long ldch;
   int no_f32;
   const float* acc_scale;
+  double* st_sums;   // fp32-output launches only: per-column sum / sum of squares of the stored result ([2][N] fp64, += )
 };
 
 static int launch_win(const float* A, long long lda, const float* Bt, float* C, long long ldc, long long M, int N, int K,
@@ -926,6 +941,10 @@ static int launch_win(const float* A, long long lda, const float* Bt, float* C, 
   }
   Epi ep{bias, scale, shift_c, act, pf_w1, pf_blk, accumulate, bnb.a, bnb.gamma, bnb.beta, bnb.var, bnb.ws, bnb.eps,
          hio.on ? (const void*)bnb.a : nullptr, hio.on ? hio.no_f32 : 0, (hio.on && hio.Ch) ? 1 : 0, hio.acc_scale};
+  if (hio.on && hio.st_sums) {
+    MYOLO_CHECK_ARG(N == 256 && !hio.no_f32 && !hio.Ch && !bnb.a && !mt.masks);
+    ep.st_sums = hio.st_sums;
+  }
   cudaStream_t st = as_stream(stream);
   const int maxcl = hio.on ? max_clusters_h : max_clusters;
   MaskTail mtl = mt;
@@ -1064,6 +1083,37 @@ extern "C" int myolo_gemm_taps_h(const void* A, long long lda, const void* Bt, f
   HalfIO hio{1, Ch, ldch, C ? 0 : 1, acc_scale};
   return launch_win(reinterpret_cast<const float*>(A), lda, reinterpret_cast<const float*>(Bt), C, C ? ldc : N, M, N, K, ntaps,
                     shifts_host, bias, scale, shift_c, act, pf_w1, pf_blk, 0, mt, stream, BnBwd{}, hio);
+}
+
+namespace myolo {
+__global__ void stats_finalize_kernel(double* __restrict__ sums, float* __restrict__ mean, float* __restrict__ var, int C,
+                                      double inv_count) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double m = sums[c] * inv_count;
+  const double vv = sums[C + c] * inv_count - m * m;
+  mean[c] = (float)m;
+  var[c] = (float)(vv > 0.0 ? vv : 0.0);
+  sums[c] = 0.0;
+  sums[C + c] = 0.0;
+}
+}  // namespace myolo
+
+// myolo_gemm_taps_h with an fp32 result and the batch statistics of that result (valid rows only: n_valid of them) taken in
+// the epilogue: mean / biased variance per output channel.  ws: the BN workspace (zero before, zero after).
+extern "C" int myolo_gemm_taps_h_stats(const void* A, long long lda, const void* Bt, float* C, long long ldc, long long M, int N,
+                                       int K, int ntaps, const int* shifts_host, const float* bias, int pf_w1, int pf_blk,
+                                       float* mean, float* var, double* ws, long long n_valid, myolo_stream stream) {
+  MYOLO_CHECK_ARG(C && mean && var && ws && n_valid > 0 && N == 256);
+  MYOLO_CHECK_ARG(myolo_gemm_taps_h_supported(lda, M, N, K, ntaps, shifts_host));
+  MaskTail mt{};
+  HalfIO hio{1, nullptr, 0, 0, nullptr, ws + 16};
+  int rc = launch_win(reinterpret_cast<const float*>(A), lda, reinterpret_cast<const float*>(Bt), C, ldc, M, N, K, ntaps,
+                      shifts_host, bias, nullptr, nullptr, MYOLO_ACT_NONE, pf_w1, pf_blk, 0, mt, stream, BnBwd{}, hio);
+  if (rc) return rc;
+  stats_finalize_kernel<<<(N + 127) / 128, 128, 0, as_stream(stream)>>>(ws + 16, mean, var, N, 1.0 / (double)n_valid);
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
 }
 
 extern "C" int myolo_deconv_mask_fwd_h(const void* a4, const void* kd, const float* bd, const float* w1, const float* b1,

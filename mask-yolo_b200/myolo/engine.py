@@ -133,8 +133,9 @@ class Engine:
         self._replay_on = os.environ.get("MYOLO_REPLAY", "1") != "0"
         # BatchNormalization fusions of the backbone (bit mask; A/B switch): 1 = batch statistics of a depthwise output in
         # the depthwise kernel's epilogue, 2 = BN + ReLU6 after conv1 / a pointwise conv applied by the next depthwise
-        # kernel (forward and filter gradient) while it loads, 4 = statistics of a pointwise output in the GEMM epilogue
-        self._fuse_bn = int(os.environ.get("MYOLO_FUSE_BN", "0"))
+        # kernel (forward and filter gradient) while it loads, 4 = statistics of a pointwise output in the GEMM epilogue,
+        # 8 = statistics of myolo_mask_conv1's output (myolo_mask_bn1) in the conv kernel's epilogue (h16 mode)
+        self._fuse_bn = int(os.environ.get("MYOLO_FUSE_BN", "13"))      # measured best: profiles/r02_fuse_bn_ab.txt
         self._deferred = {}
         self._plan = None
         self.t = 0                     # Adam iteration
@@ -683,9 +684,15 @@ class Engine:
             a_in = self.mah[i - 1]
             C.record_py(self._ke_begin)
             if training and i == 1:
-                # batch-statistics BN: the pre-BN tensor is kept in fp32 (statistics, backward)
-                C.call("myolo_gemm_taps_h", a_in.rows, MASK_C, self.wth[name], self.my[1].rows, MASK_C, None, 0, M, MASK_C, MASK_C,
-                       9, sh3, self.p[f"myolo_mask_conv{i}/bias"], None, None, C.ACT_NONE, pfw, pfb, None, st)
+                # batch-statistics BN: the pre-BN tensor is kept in fp32 (statistics, backward); its batch statistics are
+                # reduced in the conv's epilogue (bit 8 of MYOLO_FUSE_BN)
+                if self._fuse_bn & 8:
+                    b1 = self.bn["myolo_mask_bn1"]
+                    C.call("myolo_gemm_taps_h_stats", a_in.rows, MASK_C, self.wth[name], self.my[1].rows, MASK_C, M, MASK_C,
+                           MASK_C, 9, sh3, self.p[f"myolo_mask_conv{i}/bias"], pfw, pfb, b1.mean, b1.var, self.ws, npix, st)
+                else:
+                    C.call("myolo_gemm_taps_h", a_in.rows, MASK_C, self.wth[name], self.my[1].rows, MASK_C, None, 0, M, MASK_C,
+                           MASK_C, 9, sh3, self.p[f"myolo_mask_conv{i}/bias"], None, None, C.ACT_NONE, pfw, pfb, None, st)
             else:
                 b = self.bn[f"myolo_mask_bn{i}"]
                 C.call("myolo_bn_fold", b.gamma, b.beta, b.mmean, b.mvar, BN_EPS, self.bn_scale[i - 1], self.bn_shift[i - 1],
@@ -697,7 +704,8 @@ class Engine:
             C.record_py(self._ke_end)
             if training and i == 1:
                 b = self.bn["myolo_mask_bn1"]
-                C.call("myolo_bn_stats", self.my[1].view(), b.mean, b.var, self.ws, st)
+                if not (self._fuse_bn & 8):
+                    C.call("myolo_bn_stats", self.my[1].view(), b.mean, b.var, self.ws, st)
                 self._bn_touched.append((b, npix))
                 C.call("myolo_bn_apply_h", self.my[1].view(), None, self.mah[1].view(), b.mean, b.var, b.gamma,
                        b.beta, BN_EPS, C.ACT_RELU, st)

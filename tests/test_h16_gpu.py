@@ -95,6 +95,20 @@ def test_conv3x3_half_operands(C, n, H, W):
     with pytest.raises(C.MyoloError):
         C.call("myolo_gemm_taps_h", xh.rows, Ci, wth, out.rows, Co, outh.rows, Co, M, Co, Ci, 9, sh, bias, scale, shift, C.ACT_RELU,
                pfw, pfb, None, stream())
+    # fp32 output + the batch statistics of the result over the valid pixels in the epilogue (myolo_mask_conv1 -> bn1)
+    ws = torch.zeros(8192, dtype=torch.float64, device="cuda")
+    o2, ref2 = PF(n, H, W, Co), PF(n, H, W, Co)
+    C.call("myolo_gemm_taps_h", xh.rows, Ci, wth, ref2.rows, Co, None, 0, M, Co, Ci, 9, sh, bias, None, None, C.ACT_NONE, pfw, pfb,
+           None, stream())
+    mean, var = torch.empty(Co, device="cuda"), torch.empty(Co, device="cuda")
+    for rep in range(2):                      # twice: the workspace comes back zeroed
+        C.call("myolo_gemm_taps_h_stats", xh.rows, Ci, wth, o2.rows, Co, M, Co, Ci, 9, sh, bias, pfw, pfb, mean, var, ws,
+               n * H * W, stream())
+        assert torch.equal(o2.rows, ref2.rows)
+        flat = ref2.valid().reshape(-1, Co).double()
+        close(mean, flat.mean(0).float(), 2e-5, "epilogue mean")
+        close(var, flat.var(0, unbiased=False).float(), 2e-5, "epilogue variance")
+        assert ws.abs().max().item() == 0
     # dgrad form (negated shifts, un-transposed weights), fp32 output scaled by a device scalar
     shn = C.int_array(conv3x3_shifts(W, negate=True))
     wh = w.half()

@@ -788,14 +788,37 @@ def test_prep_weights_batch_equals_single_jobs(C):
         else:
             out, ref = torch.zeros(n * (3 if mode == 2 else 1), device="cuda"), torch.zeros(n * (3 if mode == 2 else 1), device="cuda")
             C.call("myolo_prep_weights", w, ref, ntaps, rows, cols, tr, mode, stream())
-        rec += struct.pack("<QQiiiiii", w.data_ptr(), out.data_ptr(), ntaps, rows, cols, tr, mode, tiles)
+        rec += struct.pack("<QQiiiiiiii", w.data_ptr(), out.data_ptr(), ntaps, rows, cols, tr, mode, tiles, 0, 0)
         tiles += ntaps * ((rows + 31) // 32) * ((cols + 31) // 32)
         outs.append(out); refs.append(ref); keep.append(w)
+    # zero-padded staging (conv_23: 27 output channels -> 32): transposed 3xTF32 triple [3][32][K] and plain [K][32]
+    K, N, NP = 96, 27, 32
+    w23 = torch.randn(K, N, device="cuda")
+    pad_t = torch.zeros(3, NP, K, device="cuda")
+    rec += struct.pack("<QQiiiiiiii", w23.data_ptr(), pad_t.data_ptr(), 1, K, N, 1, 2, tiles, 0, NP * K)
+    tiles += ((K + 31) // 32) * ((N + 31) // 32)
+    pad_n = torch.zeros(K, NP, device="cuda")
+    rec += struct.pack("<QQiiiiiiii", w23.data_ptr(), pad_n.data_ptr(), 1, K, N, 0, 1, tiles, NP, 0)
+    tiles += ((K + 31) // 32) * ((N + 31) // 32)
     table = torch.frombuffer(bytearray(rec), dtype=torch.uint8).cuda()
-    C.call("myolo_prep_weights_batch", table, len(specs), tiles, stream())
+    C.call("myolo_prep_weights_batch", table, len(specs) + 2, tiles, stream())
     torch.cuda.synchronize()
     for o, r, sp in zip(outs, refs, specs):
         assert torch.equal(o, r), sp
+    ref3 = torch.zeros(3, N, K, device="cuda")
+    C.call("myolo_prep_weights", w23, ref3, 1, K, N, 1, 2, stream())
+    assert torch.equal(pad_t[:, :N], ref3) and pad_t[:, N:].abs().max().item() == 0
+    ref1 = torch.zeros(K, N, device="cuda")
+    C.call("myolo_prep_weights", w23, ref1, 1, K, N, 0, 1, stream())
+    assert torch.equal(pad_n[:, :N], ref1) and pad_n[:, N:].abs().max().item() == 0
+    # myolo_copy_cols: cut the dense columns out of a padded matrix and back
+    src = torch.randn(50, NP, device="cuda")
+    dense = torch.empty(50, N, device="cuda")
+    C.call("myolo_copy_cols", src, NP, dense, N, 50, N, stream())
+    assert torch.equal(dense, src[:, :N])
+    back = torch.zeros(50, NP, device="cuda")
+    C.call("myolo_copy_cols", dense, N, back, NP, 50, N, stream())
+    assert torch.equal(back[:, :N], dense) and back[:, N:].abs().max().item() == 0
 
 
 def test_detect_postprocess_nmb_matches_reference_golden(C):
