@@ -247,10 +247,12 @@ int myolo_gemm_taps_h_supported(long long lda, long long M, int N, int K, int nt
 /* myolo_gemm_taps_h with an fp32 result (bias added, no activation) and the batch statistics of that result in the
  * epilogue: mean[n] / var[n] (biased) over the valid rows (n_valid of them; pad rows of the padded-flat result do not
  * count).  myolo_mask_conv1 + the statistics pass of myolo_mask_bn1, the one mask-head BatchNormalization that follows
- * the learning phase (myolo/model.py:688-690).  N == 256; ws: the BN workspace (zero before, zero after). */
+ * the learning phase (myolo/model.py:688-690).  pivot (nullable, [N]): subtracted from every value before the sums are
+ * taken, e.g. the layer's moving mean, so that the variance does not lose mean^2 / variance digits; the results do not
+ * depend on it beyond rounding.  N == 256; ws: the BN workspace (zero before, zero after). */
 int myolo_gemm_taps_h_stats(const void* A, long long lda, const void* Bt, float* C, long long ldc, long long M, int N,
                             int K, int ntaps, const int* shifts_host, const float* bias, int pf_w1, int pf_blk,
-                            float* mean, float* var, double* ws, long long n_valid, myolo_stream stream);
+                            const float* pivot, float* mean, float* var, double* ws, long long n_valid, myolo_stream stream);
 int myolo_deconv_mask_fwd_h(const void* a4, const void* kd, const float* bd, const float* w1, const float* b1,
                             float* masks, const int* target_ids, float* y4, int n_roi, int H, int W, int Cmid, int NC,
                             myolo_stream stream);

@@ -246,8 +246,12 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
     for (int n = threadIdx.x; n < 512; n += blockDim.x) colacc[n] = 0.f;
   } else {
+    // epilogue statistics: one private slot per epilogue warp ([2 statistics][128 columns]) in the 2 KB of colacc plus the
+    // 6 KB of evec the folded constants leave free; a column of a slot is only ever touched by one lane of one warp, in
+    // item order, so the per-CTA sums are reproducible run to run (shared-memory atomics made myolo_mask_bn1's statistics
+    // differ by 1e-5 between two runs, enough to move mask-head gradients by 3e-3)
     if (ep.st_sums)
-      for (int n = threadIdx.x; n < 512; n += blockDim.x) colacc[n] = 0.f;
+      for (int n = threadIdx.x; n < 2048; n += blockDim.x) colacc[n < 512 ? n : 512 + n] = 0.f;
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
       const float sc = ep.scale ? __ldg(ep.scale + n) : 1.f;
       const float b = ep.bias ? __ldg(ep.bias + n) : 0.f;
@@ -731,7 +735,7 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               if (rnd) o[e] = round_tf32(o[e]);
               if (!valid) o[e] = 0.f;   // padded-flat pad rows stay zero
             }
-            if (ep.st_sums && !st_h) {   // batch statistics of the stored result (pad rows contribute zeros)
+            if (EL == 2 && ep.st_sums && !st_h) {   // batch statistics of the stored result
               v[4 * j] = o[0]; v[4 * j + 1] = o[1]; v[4 * j + 2] = o[2]; v[4 * j + 3] = o[3];
             }
             if (st_h) {   // the half copy; v[] keeps the packed words until the 16-byte chunk is complete
@@ -761,13 +765,20 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");   // keep one group per chunk: the ring counts groups
             }
           }
-          if (ep.st_sums && !st_h && !ep.bn_a) {   // column sums of the chunk while its TMA store is in flight
+          if (EL == 2 && ep.st_sums && !st_h && !ep.bn_a) {   // column sums of the chunk while its TMA store is in flight
+            // shifted by a per-column pivot (the layer's moving mean): E[x^2] - E[x]^2 would lose mean^2 / variance digits
+            const float pv = ep.st_pivot ? __ldg(ep.st_pivot + n0 + lane) : 0.f;
             float sq[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
+            for (int j = 0; j < 32; ++j) {
+              const float pj = __shfl_sync(0xffffffffu, pv, j);
+              v[j] = valid ? v[j] - pj : 0.f;
+              sq[j] = v[j] * v[j];
+            }
             const float s0 = warp_colsum32(v, lane), s1 = warp_colsum32(sq, lane);
-            atomicAdd(colacc + n0 + lane, s0);
-            atomicAdd(colacc + 256 + n0 + lane, s1);
+            float* slot = colacc + (ew < 2 ? ew * 256 : 1024 + (ew - 2) * 256) + (c0 - cbeg) + lane;
+            slot[0] += s0;
+            slot[128] += s1;
           }
         }
       }
@@ -782,11 +793,21 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
-  if (ep.bn_a || ep.st_sums) {   // one fp64 atomic per (CTA, column, statistic)
-    double* dst = ep.bn_a ? ep.bn_ws : ep.st_sums;
+  if (ep.bn_a) {   // one fp64 atomic per (CTA, column, statistic)
     for (int n = threadIdx.x; n < 2 * N; n += blockDim.x) {
       const float vsum = colacc[(n / N) * 256 + (n % N)];
-      if (vsum != 0.f) atomicAdd(dst + n, (double)vsum);
+      if (vsum != 0.f) atomicAdd(ep.bn_ws + n, (double)vsum);
+    }
+  } else if (EL == 2 && ep.st_sums) {   // the four warps of a column half, in a fixed order
+    for (int n = threadIdx.x; n < 2 * N; n += blockDim.x) {
+      const int stat = n / N, col = n - stat * N, h = col >> 7, cc = col & 127;
+      double acc = 0.0;
+#pragma unroll
+      for (int w4 = 0; w4 < 4; ++w4) {
+        const int w = h * 4 + w4;
+        acc += (double)colacc[(w < 2 ? w * 256 : 1024 + (w - 2) * 256) + stat * 128 + cc];
+      }
+      if (acc != 0.0) atomicAdd(ep.st_sums + n, acc);
     }
   }
   if (CG == 2) cluster_sync_all();   // no CTA of the pair may free TMEM / exit while the other still uses it
@@ -847,6 +868,7 @@ struct HalfIO {
   int no_f32;
   const float* acc_scale;
   double* st_sums;   // fp32-output launches only: per-column sum / sum of squares of the stored result ([2][N] fp64, += )
+  const float* st_pivot;   // per-column value subtracted before the sums are taken (nullable)
 };
 
 static int launch_win(const float* A, long long lda, const float* Bt, float* C, long long ldc, long long M, int N, int K,
@@ -944,6 +966,7 @@ static int launch_win(const float* A, long long lda, const float* Bt, float* C, 
   if (hio.on && hio.st_sums) {
     MYOLO_CHECK_ARG(N == 256 && !hio.no_f32 && !hio.Ch && !bnb.a && !mt.masks);
     ep.st_sums = hio.st_sums;
+    ep.st_pivot = hio.st_pivot;
   }
   cudaStream_t st = as_stream(stream);
   const int maxcl = hio.on ? max_clusters_h : max_clusters;
@@ -1086,13 +1109,13 @@ extern "C" int myolo_gemm_taps_h(const void* A, long long lda, const void* Bt, f
 }
 
 namespace myolo {
-__global__ void stats_finalize_kernel(double* __restrict__ sums, float* __restrict__ mean, float* __restrict__ var, int C,
-                                      double inv_count) {
+__global__ void stats_finalize_kernel(double* __restrict__ sums, const float* __restrict__ pivot, float* __restrict__ mean,
+                                      float* __restrict__ var, int C, double inv_count) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const double m = sums[c] * inv_count;
+  const double m = sums[c] * inv_count;                      // mean of (x - pivot)
   const double vv = sums[C + c] * inv_count - m * m;
-  mean[c] = (float)m;
+  mean[c] = (float)(m + (pivot ? (double)pivot[c] : 0.0));
   var[c] = (float)(vv > 0.0 ? vv : 0.0);
   sums[c] = 0.0;
   sums[C + c] = 0.0;
@@ -1103,15 +1126,16 @@ __global__ void stats_finalize_kernel(double* __restrict__ sums, float* __restri
 // the epilogue: mean / biased variance per output channel.  ws: the BN workspace (zero before, zero after).
 extern "C" int myolo_gemm_taps_h_stats(const void* A, long long lda, const void* Bt, float* C, long long ldc, long long M, int N,
                                        int K, int ntaps, const int* shifts_host, const float* bias, int pf_w1, int pf_blk,
-                                       float* mean, float* var, double* ws, long long n_valid, myolo_stream stream) {
-  MYOLO_CHECK_ARG(C && mean && var && ws && n_valid > 0 && N == 256);
+                                       const float* pivot, float* mean, float* var, double* ws, long long n_valid,
+                                       myolo_stream stream) {
+  MYOLO_CHECK_ARG(C && mean && var && ws && n_valid > 0 && N == 256 && pivot != mean);
   MYOLO_CHECK_ARG(myolo_gemm_taps_h_supported(lda, M, N, K, ntaps, shifts_host));
   MaskTail mt{};
-  HalfIO hio{1, nullptr, 0, 0, nullptr, ws + 16};
+  HalfIO hio{1, nullptr, 0, 0, nullptr, ws + 16, pivot};
   int rc = launch_win(reinterpret_cast<const float*>(A), lda, reinterpret_cast<const float*>(Bt), C, ldc, M, N, K, ntaps,
                       shifts_host, bias, nullptr, nullptr, MYOLO_ACT_NONE, pf_w1, pf_blk, 0, mt, stream, BnBwd{}, hio);
   if (rc) return rc;
-  stats_finalize_kernel<<<(N + 127) / 128, 128, 0, as_stream(stream)>>>(ws + 16, mean, var, N, 1.0 / (double)n_valid);
+  stats_finalize_kernel<<<(N + 127) / 128, 128, 0, as_stream(stream)>>>(ws + 16, pivot, mean, var, N, 1.0 / (double)n_valid);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }

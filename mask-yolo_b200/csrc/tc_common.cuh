@@ -210,6 +210,7 @@ struct Epi {
   float* st_mean;
   float* st_var;
   double st_inv;          // 1 / number of valid rows
+  const float* st_pivot;  // conv_win kernel: per-column value subtracted before the sums are taken (nullable)
 };
 
 

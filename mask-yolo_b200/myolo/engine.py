@@ -129,6 +129,8 @@ class Engine:
         # backbone backward: the two filter-gradient kernels of a block (pointwise wgrad, depthwise bwd_filter) run on a
         # side stream next to the data-gradient chain (they are 20-70 us kernels that fill a fraction of the SMs)
         self._side = torch.cuda.Stream(device=self.dev) if os.environ.get("MYOLO_BWD_STREAMS", "1") != "0" else None
+        # third stream: the YOLO branch's backward next to the mask head's (Engine.backward)
+        self._ystream = torch.cuda.Stream(device=self.dev) if os.environ.get("MYOLO_Y_OVERLAP", "1") != "0" else None
         self._evs = {}
         self._replay_on = os.environ.get("MYOLO_REPLAY", "1") != "0"
         # BatchNormalization fusions of the backbone (bit mask; A/B switch): 1 = batch statistics of a depthwise output in
@@ -227,6 +229,7 @@ class Engine:
                         self.wth_d[name] = torch.zeros(n, dtype=torch.float16, device=self.dev)
             self.gs = torch.tensor([1.0, 1.0, 0.0, 0.0], dtype=torch.float32, device=self.dev)   # loss scale {S, 1/S, scratch}
         self.ws = torch.zeros(8192, dtype=torch.float64, device=self.dev)       # BN family: zero between calls
+        self.ws_y = torch.zeros(8192, dtype=torch.float64, device=self.dev)     # the same for the YOLO-branch backward stream
         self.ws_loss = torch.zeros(16, dtype=torch.float64, device=self.dev)
         self.anchors = torch.tensor(self.cfg["ANCHORS"], dtype=torch.float32, device=self.dev)
         self.class_w = torch.tensor(np.asarray(self.cfg["CLASS_WEIGHTS"], dtype=np.float32), device=self.dev)
@@ -493,11 +496,11 @@ class Engine:
             e1.record()
             self.kernel_events.append((self._ke0, e1))
 
-    def _bn_bwd(self, name, xv, dyv, act, training):
+    def _bn_bwd(self, name, xv, dyv, act, training, st=None, ws=None):
         b = self.bn[name]
         mean, var = (b.mean, b.var) if training else (b.mmean, b.mvar)
         C.call("myolo_bn_bwd", xv, dyv, dyv, mean, var, b.gamma, b.beta, BN_EPS, act, 1 if training else 0,
-               b.dgamma, b.dbeta, self.ws, self._st())
+               b.dgamma, b.dbeta, self.ws if ws is None else ws, self._st() if st is None else st)
 
     # ------------------------------------------------------------------ forward
     def forward(self, image: torch.Tensor, training: Optional[bool] = None):
@@ -689,7 +692,7 @@ class Engine:
                 if self._fuse_bn & 8:
                     b1 = self.bn["myolo_mask_bn1"]
                     C.call("myolo_gemm_taps_h_stats", a_in.rows, MASK_C, self.wth[name], self.my[1].rows, MASK_C, M, MASK_C,
-                           MASK_C, 9, sh3, self.p[f"myolo_mask_conv{i}/bias"], pfw, pfb, b1.mean, b1.var, self.ws, npix, st)
+                           MASK_C, 9, sh3, self.p[f"myolo_mask_conv{i}/bias"], pfw, pfb, b1.mmean, b1.mean, b1.var, self.ws, npix, st)
                 else:
                     C.call("myolo_gemm_taps_h", a_in.rows, MASK_C, self.wth[name], self.my[1].rows, MASK_C, None, 0, M, MASK_C,
                            MASK_C, 9, sh3, self.p[f"myolo_mask_conv{i}/bias"], None, None, C.ACT_NONE, pfw, pfb, None, st)
@@ -785,33 +788,90 @@ class Engine:
     def backward(self, on_tail_ready=None):
         """Gradients of LOSS_WEIGHTS-weighted (yolo_sum_loss + mask_loss) w.r.t. every trainable
         variable, into the flat gradient buffer.  `on_tail_ready()` is invoked once the
-        feature_map + mask-head slice [tail_off:] is final (hook for the overlapped all-reduce)."""
-        A, B, st = self.A, self.B, self._st()
-        C.record_py(self.grads.zero_)
-        relu6 = C.ACT_RELU6
-        if self.with_mask:
-            self._backward_mask()
-        if on_tail_ready is not None:
-            C.record_py(on_tail_ready)
-        G, NB, NC = self.cfg["G"], self.NB, self.NC
-        ny = NB * (5 + NC)
-        main, side = torch.cuda.current_stream(), self._side
-        sst = side.cuda_stream if side is not None else st
+        feature_map + mask-head slice [tail_off:] is final (hook for the overlapped all-reduce).
 
-        def ev(name):       # events are created once and re-recorded every step
-            e = self._evs.get(name)
-            if e is None:
-                e = self._evs[name] = torch.cuda.Event()
-            return e
+        Streams: the backward of the YOLO branch (conv_23, blocks 14..7) depends on the yolo loss only, so it runs on its
+        own stream NEXT TO the mask-head backward (eight milliseconds of persistent tensor-core kernels, one CTA per SM,
+        which leave the issue slots of every SM mostly idle): ~40 latency-bound launches leave the critical path.  The two
+        chains meet at block 6, where d(C4) of the feature_map branch is added.  The filter-gradient kernels of blocks
+        6..1 run on the side stream next to the data-gradient chain, as before."""
+        A, B = self.A, self.B
+        C.record_py(self.grads.zero_)
+        main, side, ys = torch.cuda.current_stream(), self._side, self._ystream
+        overlap = self.with_mask and ys is not None
+        blocks = list(reversed(BACKBONE_BLOCKS + YOLO_BLOCKS))
+        n_y = len(YOLO_BLOCKS)
+        if overlap:
+            e0, e1 = self._ev("y_fork"), self._ev("y_done")
+            C.record_py(lambda: (e0.record(main), ys.wait_event(e0)))          # after grads.zero_()
+            self._backward_conv23(ys, None, self.ws_y)
+            self._backward_blocks(blocks[:n_y], ys, None, self.ws_y)
+            C.record_py(lambda: e1.record(ys))
+            self._backward_mask()
+            if on_tail_ready is not None:
+                C.record_py(on_tail_ready)
+            C.record_py(lambda: main.wait_event(e1))
+            self._backward_blocks(blocks[n_y:], main, side, self.ws)
+        else:
+            if self.with_mask:
+                self._backward_mask()
+            if on_tail_ready is not None:
+                C.record_py(on_tail_ready)
+            self._backward_conv23(main, side, self.ws)
+            self._backward_blocks(blocks, main, side, self.ws)
+        S = self.cfg["S"]
+        H0 = S // 2
+        st = main.cuda_stream
+        self._bn_bwd("conv1_bn", self._v(A["y0"]), C.view(self.gx, B, H0, H0, 32), C.ACT_RELU6, True)
+        C.call("myolo_conv1_wgrad", self._image, self.gx, self.g["conv1/kernel"], B, S, 32, st)
+        if side is not None and "f_done" in self._evs:
+            e = self._evs["f_done"]
+            C.record_py(lambda: main.wait_event(e))     # every gradient is in the flat buffer once main passes this point
+
+    def _ev(self, name):        # events are created once and re-recorded every step
+        e = self._evs.get(name)
+        if e is None:
+            e = self._evs[name] = torch.cuda.Event()
+        return e
+
+    def _backward_conv23(self, main, side, ws):
+        """conv_23 (model.py:271): bias / kernel gradients and d(ap14) into gx, on stream `main` (kernel gradient on `side`)."""
+        A, B = self.A, self.B
+        G, ny = self.cfg["G"], self.ny
+        st = main.cuda_stream
+        sst = side.cuda_stream if side is not None else st
+        dy = A["dyolo"]
+        C.call("myolo_colsum", self._v(dy), self.g["conv_23/bias"], ws, st)
+        if side is not None:
+            e = self._ev("f23")
+            C.record_py(lambda: (e.record(main), side.wait_event(e)))
+        ap14 = A["ap14"][0] if self.x3 else A["ap14"]
+        C.call("myolo_pwconv_wgrad", ap14, dy, self.g["conv_23/kernel"], B * G * G, 1024, ny, sst)
+        if self.tc:     # data gradient on tcgen05: dy padded to ny_pad channels against the zero-padded [1024][ny_pad] kernel
+            C.call("myolo_copy_cols", dy, ny, A["dyolo_pad"], self.ny_pad, B * G * G, ny, st)
+            C.call("myolo_gemm_taps", A["dyolo_pad"], self.ny_pad, self.w23_d, self.gx, 1024, B * G * G, 1024, self.ny_pad, 1,
+                   None, None, None, None, C.ACT_NONE, 0, 0, 0, st)
+        else:
+            C.call("myolo_pwconv_dgrad", dy, self.p["conv_23/kernel"], self.gx, B * G * G, 1024, ny, st)
+
+    def _backward_blocks(self, blocks, main, side, ws):
+        """Backward of depthwise-separable blocks (given last to first); d(block output) arrives in gx and d(block input)
+        leaves in gx.  Data-gradient chain on `main`; with a `side` stream the two filter-gradient kernels of a block run
+        there (they are 20-70 us kernels that fill a fraction of the SMs)."""
+        A, B = self.A, self.B
+        relu6 = C.ACT_RELU6
+        gx, gy = self.gx, self.gy
+        st = main.cuda_stream
+        sst = side.cuda_stream if side is not None else st
 
         def fork(name):     # the side stream may start once everything issued on main so far is done
             if side is not None:
-                e = ev(name)
+                e = self._ev(name)
                 C.record_py(lambda: (e.record(main), side.wait_event(e)))
 
         def mark(name):     # remember the side stream's position
             if side is not None:
-                e = ev(name)
+                e = self._ev(name)
                 C.record_py(lambda: e.record(side))
 
         def join(name):     # main waits for that position
@@ -819,28 +879,15 @@ class Engine:
                 e = self._evs[name]
                 C.record_py(lambda: main.wait_event(e))
 
-        # conv_23
-        dy = A["dyolo"]
-        C.call("myolo_colsum", self._v(dy), self.g["conv_23/bias"], self.ws, st)
-        fork("f23")           # also orders the side stream after grads.zero_()
-        ap14 = A["ap14"][0] if self.x3 else A["ap14"]
-        C.call("myolo_pwconv_wgrad", ap14, dy, self.g["conv_23/kernel"], B * G * G, 1024, ny, sst)
-        gx, gy = self.gx, self.gy
-        if self.tc:     # data gradient on tcgen05: dy padded to ny_pad channels against the zero-padded [1024][ny_pad] kernel
-            C.call("myolo_copy_cols", dy, ny, A["dyolo_pad"], self.ny_pad, B * G * G, ny, st)
-            C.call("myolo_gemm_taps", A["dyolo_pad"], self.ny_pad, self.w23_d, gx, 1024, B * G * G, 1024, self.ny_pad, 1, None,
-                   None, None, None, C.ACT_NONE, 0, 0, 0, st)
-        else:
-            C.call("myolo_pwconv_dgrad", dy, self.p["conv_23/kernel"], gx, B * G * G, 1024, ny, st)
         first = True
-        for k, ci, co, s in reversed(BACKBONE_BLOCKS + YOLO_BLOCKS):
+        for k, ci, co, s in blocks:
             Hi, Ho, _, _, _ = self.geo[k]
             npix = B * Ho * Ho
             if k == 6 and self.with_mask:
                 # join the feature_map branch: d(C4) += dgrad of the 3x3 conv (padded-flat -> dense)
                 C.call("myolo_view_copy", self.dc4.view(), C.view(gx, B, Ho, Ho, co), 1, st)
             d_ap = C.view(gx, B, Ho, Ho, co)
-            self._bn_bwd(f"conv_pw_{k}_bn", self._v(A[f"yp{k}"]), d_ap, relu6, True)
+            self._bn_bwd(f"conv_pw_{k}_bn", self._v(A[f"yp{k}"]), d_ap, relu6, True, st, ws)
             ad_hi = A[f"ad{k}"][0] if self.x3 else A[f"ad{k}"]
             fork("fw")
             C.call("myolo_pwconv_wgrad", ad_hi, gx, self.g[f"conv_pw_{k}/kernel"], npix, ci, co, sst)      # reads gx
@@ -850,7 +897,7 @@ class Engine:
             first = False
             C.call("myolo_pwconv_dgrad", gx, self.p[f"conv_pw_{k}/kernel"], gy, npix, ci, co, st)
             d_ad = C.view(gy, B, Ho, Ho, ci)
-            self._bn_bwd(f"conv_dw_{k}_bn", self._v(A[f"yd{k}"]), d_ad, relu6, True)
+            self._bn_bwd(f"conv_dw_{k}_bn", self._v(A[f"yd{k}"]), d_ad, relu6, True, st, ws)
             ib = self._deferred.get(k - 1)
             if ib is not None:          # the block's input exists only as the producer's pre-BN output: BN + ReLU6 on load
                 xin = self._v(A["y0"] if k == 1 else A[f"yp{k - 1}"])
@@ -869,11 +916,6 @@ class Engine:
             mark("f_done")
             join("w_done")              # the pointwise wgrad has finished reading gx
             C.call("myolo_dwconv3x3_bwd_data", gy, self.p[f"conv_dw_{k}/depthwise_kernel"], gx, B, Hi, Hi, ci, s, st)
-        S = self.cfg["S"]
-        H0 = S // 2
-        self._bn_bwd("conv1_bn", self._v(A["y0"]), C.view(gx, B, H0, H0, 32), relu6, True)
-        C.call("myolo_conv1_wgrad", self._image, gx, self.g["conv1/kernel"], B, S, 32, st)
-        join("f_done")                  # every gradient is in the flat buffer once main passes this point
 
     def _backward_mask_h16(self):
         """Backward of the mask head on tcgen05 kind::f16.  The gradient tensors are half, multiplied by the
