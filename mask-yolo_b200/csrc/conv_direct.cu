@@ -4,6 +4,7 @@
 // input halo tile staged once in shared memory, grid sized in (tile x channel-group x image).
 // Reference call sites: myolo/model.py:42-52 (conv_block) and 68-77 / 256-268
 // (keras_applications _depthwise_conv_block: ZeroPad(1,1) + DepthwiseConv2D 3x3 VALID stride s).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace myolo {
@@ -139,6 +140,212 @@ __global__ void __launch_bounds__(256) dw_fwd_kernel(const float* __restrict__ x
     st.sums[st.C + c] = 0.0;
   }
   if (tid == 0) st.ticket[blockIdx.y] = 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Strip kernels (round 2).  The tile kernels above stage an 8x8 halo tile per 32 channels in shared memory: load,
+// barrier, compute, store, with ~25 KB in flight per SM -- measured 0.2-0.36 of the HBM peak even on the 100 MB layers,
+// bound by latency and instruction issue.  Here a thread owns one channel quad of one output COLUMN (b, ox) and walks
+// a strip of TY output rows with the three input columns it needs in registers: every input row costs three 128-bit
+// loads (two of them shared with the neighbouring threads through L1), no shared memory, no barrier, ~30 independent
+// loads in flight per thread.  A warp covers 4 adjacent columns x 32 channels = 512 contiguous bytes of an NHWC row.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fma4(float4& a, const float4& v, const float4& w) {
+  a.x = fmaf(v.x, w.x, a.x);
+  a.y = fmaf(v.y, w.y, a.y);
+  a.z = fmaf(v.z, w.z, a.z);
+  a.w = fmaf(v.w, w.w, a.w);
+}
+
+// forward (and, with FLIP, the stride-1 data gradient: the same correlation with the kernel rotated by 180 degrees)
+#ifndef MYOLO_DW_MINBLK
+#define MYOLO_DW_MINBLK 2
+#endif
+#ifndef MYOLO_DW_TY1
+#define MYOLO_DW_TY1 8
+#endif
+template <int S, int TY, bool INBN, bool STATS, bool FLIP>
+__global__ void __launch_bounds__(256, MYOLO_DW_MINBLK) dw_strip_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                       float* __restrict__ y, int B, int H, int W, int C, int Ho, int Wo,
+                                                       long long xsn, long long xsh, DwBn bn, DwStats st) {
+  __shared__ float red[STATS ? 2 * 32 * 33 : 1];
+  __shared__ int s_last;
+  const int tid = threadIdx.x;
+  const int cq = tid & 7, pg = tid >> 3;
+  const int c = blockIdx.y * 32 + cq * 4;
+  const int col = blockIdx.x * 32 + pg;
+  const bool active = col < B * Wo;
+  const int b = active ? col / Wo : 0, ox = active ? col - (col / Wo) * Wo : 0;
+  const int oy0 = blockIdx.z * TY;
+  float4 wr[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) wr[k] = __ldg(reinterpret_cast<const float4*>(w + (size_t)(FLIP ? 8 - k : k) * C + c));
+  float4 bsc = make_float4(0.f, 0.f, 0.f, 0.f), bsh = bsc;
+  if (INBN) dw_bn_consts(bn, c, bsc, bsh);
+  float4 acc[TY];
+#pragma unroll
+  for (int t = 0; t < TY; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* xb = x + (size_t)b * xsn + c;
+  const int ix0 = ox * S - 1;
+  constexpr int ROWS = S * (TY - 1) + 3;       // input rows a strip touches
+  // every load of the strip is issued before the first FMA (ROWS x 3 quads in registers): the kernel lives on
+  // memory-level parallelism, not on occupancy (measured on B200, dw1: 38.9 us with the loads interleaved row by row at
+  // 102 registers, 30.7 us once the compiler was given 128 registers and hoisted them)
+  float4 vin[ROWS][3];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    const int iy = oy0 * S - 1 + r;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int ix = ix0 + j;
+      vin[r][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (active && iy >= 0 && iy < H && ix >= 0 && ix < W)
+        vin[r][j] = __ldg(reinterpret_cast<const float4*>(xb + (size_t)iy * xsh + (size_t)ix * C));
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    const int iy = oy0 * S - 1 + r;
+    float4 v[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int ix = ix0 + j;
+      v[j] = vin[r][j];
+      if (INBN && active && iy >= 0 && iy < H && ix >= 0 && ix < W) v[j] = dw_in_bn(v[j], bsc, bsh, bn.act);
+    }
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      // input row r is tap row ky of output row t with S*t + ky == r
+      if ((r - ky) >= 0 && (r - ky) % S == 0 && (r - ky) / S < TY) {
+        const int t = (r - ky) / S;
+        fma4(acc[t], v[0], wr[ky * 3 + 0]);
+        fma4(acc[t], v[1], wr[ky * 3 + 1]);
+        fma4(acc[t], v[2], wr[ky * 3 + 2]);
+      }
+    }
+  }
+  float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+#pragma unroll
+  for (int t = 0; t < TY; ++t) {
+    const int oy = oy0 + t;
+    if (active && oy < Ho) {
+      *reinterpret_cast<float4*>(y + (((size_t)b * Ho + oy) * Wo + ox) * C + c) = acc[t];
+      if (STATS) {
+        s0.x += acc[t].x; s0.y += acc[t].y; s0.z += acc[t].z; s0.w += acc[t].w;
+        s1.x = fmaf(acc[t].x, acc[t].x, s1.x); s1.y = fmaf(acc[t].y, acc[t].y, s1.y);
+        s1.z = fmaf(acc[t].z, acc[t].z, s1.z); s1.w = fmaf(acc[t].w, acc[t].w, s1.w);
+      }
+    }
+  }
+  if (!STATS) return;
+  float (*rd)[32][33] = reinterpret_cast<float (*)[32][33]>(red);
+  rd[0][cq * 4 + 0][pg] = s0.x; rd[0][cq * 4 + 1][pg] = s0.y; rd[0][cq * 4 + 2][pg] = s0.z; rd[0][cq * 4 + 3][pg] = s0.w;
+  rd[1][cq * 4 + 0][pg] = s1.x; rd[1][cq * 4 + 1][pg] = s1.y; rd[1][cq * 4 + 2][pg] = s1.z; rd[1][cq * 4 + 3][pg] = s1.w;
+  __syncthreads();
+  if (tid < 64) {
+    const int which = tid >> 5, cc = tid & 31;
+    double sum = 0.0;
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) sum += (double)rd[which][cc][j];
+    atomicAdd(st.sums + (size_t)which * st.C + blockIdx.y * 32 + cc, sum);
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(st.ticket + blockIdx.y, 1) == (int)(gridDim.x * gridDim.z) - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (tid < 32) {
+    const int cc = blockIdx.y * 32 + tid;
+    const double S0 = *(volatile double*)(st.sums + cc), S1 = *(volatile double*)(st.sums + st.C + cc);
+    const double m = S0 * st.inv_count;
+    const double vv = S1 * st.inv_count - m * m;
+    st.mean[cc] = (float)m;
+    st.var[cc] = (float)(vv > 0.0 ? vv : 0.0);
+    st.sums[cc] = 0.0;
+    st.sums[st.C + cc] = 0.0;
+  }
+  if (tid == 0) st.ticket[blockIdx.y] = 0;
+}
+
+// filter gradient: thread = channel quad x output column (b, ox) x a strip of `rows` output rows.  Stride 1 keeps the
+// 3x3 input window in registers and loads one new input row (3 quads) + one dy quad per output row; stride 2 loads two.
+template <int S, bool INBN>
+__global__ void __launch_bounds__(256) dw_bwd_filter_strip_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                  float* __restrict__ dw, int B, int H, int W, int C, int Ho,
+                                                                  int Wo, int rows, long long xsn, long long xsh, DwBn bn) {
+  __shared__ float red[9 * 32 * 33];
+  const int tid = threadIdx.x;
+  const int cq = tid & 7, pg = tid >> 3;
+  const int c = blockIdx.y * 32 + cq * 4;
+  const int col = blockIdx.x * 32 + pg;
+  const bool active = col < B * Wo;
+  const int b = active ? col / Wo : 0, ox = active ? col - (col / Wo) * Wo : 0;
+  const int oy0 = blockIdx.z * rows, oy1 = min(Ho, oy0 + rows);
+  float4 bsc = make_float4(0.f, 0.f, 0.f, 0.f), bsh = bsc;
+  if (INBN) dw_bn_consts(bn, c, bsc, bsh);
+  float4 acc[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* xb = x + (size_t)b * xsn + c;
+  const int ix0 = ox * S - 1;
+  auto load_row = [&](int iy, float4 (&v)[3]) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int ix = ix0 + j;
+      v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (active && iy >= 0 && iy < H && ix >= 0 && ix < W) {
+        v[j] = __ldg(reinterpret_cast<const float4*>(xb + (size_t)iy * xsh + (size_t)ix * C));
+        if (INBN) v[j] = dw_in_bn(v[j], bsc, bsh, bn.act);
+      }
+    }
+  };
+  // RB output rows per trip: the S*RB new input rows and the RB dy quads of a trip are loaded before its first FMA
+  // (memory-level parallelism, see dw_strip_kernel); the 3-S input rows the next trip shares are carried in registers.
+  constexpr int RB = S == 1 ? 4 : 2;
+  constexpr int XR = S * RB + (3 - S);          // input rows a trip reads: S*RB new ones + the carried ones
+  float4 xr[XR][3];
+  if (oy0 < oy1) {
+#pragma unroll
+    for (int r = 0; r < 3 - S; ++r) load_row(oy0 * S - 1 + r, xr[r]);
+  }
+  for (int oy = oy0; oy < oy1; oy += RB) {
+#pragma unroll
+    for (int r = 3 - S; r < XR; ++r) load_row(oy * S - 1 + r, xr[r]);
+    float4 g[RB];
+#pragma unroll
+    for (int t = 0; t < RB; ++t) {
+      g[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (active && oy + t < oy1) g[t] = __ldg(reinterpret_cast<const float4*>(dy + (((size_t)b * Ho + oy + t) * Wo + ox) * C + c));
+    }
+#pragma unroll
+    for (int t = 0; t < RB; ++t)
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) fma4(acc[ky * 3 + j], xr[S * t + ky][j], g[t]);
+#pragma unroll
+    for (int r = 0; r < 3 - S; ++r)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) xr[r][j] = xr[S * RB + r][j];
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    float* r = &red[(k * 32 + cq * 4) * 33 + pg];
+    r[0] = acc[k].x;
+    r[33] = acc[k].y;
+    r[66] = acc[k].z;
+    r[99] = acc[k].w;
+  }
+  __syncthreads();
+  for (int i = tid; i < 9 * 32; i += 256) {
+    const float* r = &red[i * 33];
+    float sum = 0.f;
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) sum += r[j];
+    const int k = i / 32, cc = i % 32;
+    if (sum != 0.f) atomicAdd(dw + (size_t)k * C + blockIdx.y * 32 + cc, sum);
+  }
 }
 
 // depthwise backward w.r.t. input: gather form, one thread = one input pixel x 4 channels.
@@ -390,19 +597,43 @@ extern "C" int myolo_dwconv3x3_fwd_bn(const myolo_view* xv, const float* w, floa
   DwBn bn{in_mean, in_var, in_gamma, in_beta, eps, in_act};
   DwStats st{ws ? ws + kDwWsSums : nullptr, reinterpret_cast<int*>(ws), out_mean, out_var, 1.0 / ((double)B * Ho * Wo), C};
   cudaStream_t cs = as_stream(stream);
-#define MYOLO_DW_FWD(S_, I_, T_) dw_fwd_kernel<S_, I_, T_><<<grid, 256, 0, cs>>>(x, w, y, H, W, C, Ho, Wo, ntx, xv->sn, xv->sh, bn, st)
-  if (stride == 1) {
-    if (inbn && stats) MYOLO_DW_FWD(1, true, true);
-    else if (inbn) MYOLO_DW_FWD(1, true, false);
-    else if (stats) MYOLO_DW_FWD(1, false, true);
-    else MYOLO_DW_FWD(1, false, false);
-  } else {
-    if (inbn && stats) MYOLO_DW_FWD(2, true, true);
-    else if (inbn) MYOLO_DW_FWD(2, true, false);
-    else if (stats) MYOLO_DW_FWD(2, false, true);
-    else MYOLO_DW_FWD(2, false, false);
+  static int use_tile = -1;
+  if (use_tile < 0) {
+    const char* e = getenv("MYOLO_DW_TILE");      // 1: the shared-memory tile kernels of round 1 (A/B switch)
+    use_tile = (e && atoi(e)) ? 1 : 0;
   }
+  if (use_tile) {
+#define MYOLO_DW_FWD(S_, I_, T_) dw_fwd_kernel<S_, I_, T_><<<grid, 256, 0, cs>>>(x, w, y, H, W, C, Ho, Wo, ntx, xv->sn, xv->sh, bn, st)
+    if (stride == 1) {
+      if (inbn && stats) MYOLO_DW_FWD(1, true, true);
+      else if (inbn) MYOLO_DW_FWD(1, true, false);
+      else if (stats) MYOLO_DW_FWD(1, false, true);
+      else MYOLO_DW_FWD(1, false, false);
+    } else {
+      if (inbn && stats) MYOLO_DW_FWD(2, true, true);
+      else if (inbn) MYOLO_DW_FWD(2, true, false);
+      else if (stats) MYOLO_DW_FWD(2, false, true);
+      else MYOLO_DW_FWD(2, false, false);
+    }
 #undef MYOLO_DW_FWD
+  } else {
+    constexpr int TY1 = MYOLO_DW_TY1, TY2 = 4;
+    dim3 g1((unsigned)ceil_div((long long)B * Wo, 32), C / 32, (unsigned)ceil_div(Ho, stride == 1 ? TY1 : TY2));
+#define MYOLO_DW_STRIP(S_, T_, I_, ST_) \
+  dw_strip_kernel<S_, T_, I_, ST_, false><<<g1, 256, 0, cs>>>(x, w, y, B, H, W, C, Ho, Wo, xv->sn, xv->sh, bn, st)
+    if (stride == 1) {
+      if (inbn && stats) MYOLO_DW_STRIP(1, TY1, true, true);
+      else if (inbn) MYOLO_DW_STRIP(1, TY1, true, false);
+      else if (stats) MYOLO_DW_STRIP(1, TY1, false, true);
+      else MYOLO_DW_STRIP(1, TY1, false, false);
+    } else {
+      if (inbn && stats) MYOLO_DW_STRIP(2, TY2, true, true);
+      else if (inbn) MYOLO_DW_STRIP(2, TY2, true, false);
+      else if (stats) MYOLO_DW_STRIP(2, TY2, false, true);
+      else MYOLO_DW_STRIP(2, TY2, false, false);
+    }
+#undef MYOLO_DW_STRIP
+  }
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }
@@ -418,7 +649,20 @@ extern "C" int myolo_dwconv3x3_bwd_data(const float* dy, const float* w, float* 
   const int Ho = dw_out(H, stride), Wo = dw_out(W, stride);
   const long long total = (long long)B * H * W * (C / 4);
   const int blocks = (int)min(ceil_div(total, 256), (long long)kNumSMs * 32);
-  if (stride == 1)
+  static int use_old = -1;
+  if (use_old < 0) {
+    const char* e = getenv("MYOLO_DW_TILE");
+    use_old = (e && atoi(e)) ? 1 : 0;
+  }
+  if (stride == 1 && !use_old && (C % 32) == 0) {
+    // stride 1: dx = dy correlated with the kernel rotated by 180 degrees, same geometry -> the forward strip kernel
+    constexpr int TY = MYOLO_DW_TY1;
+    dim3 grid((unsigned)ceil_div((long long)B * W, 32), C / 32, (unsigned)ceil_div(H, TY));
+    DwBn bn{};
+    DwStats st{};
+    dw_strip_kernel<1, TY, false, false, true><<<grid, 256, 0, as_stream(stream)>>>(dy, w, dx, B, H, W, C, H, W,
+                                                                                     (long long)H * W * C, (long long)W * C, bn, st);
+  } else if (stride == 1)
     dw_bwd_data_kernel<1><<<blocks, 256, 0, as_stream(stream)>>>(dy, w, dx, B, H, W, C, Ho, Wo);
   else
     dw_bwd_data_kernel<2><<<blocks, 256, 0, as_stream(stream)>>>(dy, w, dx, B, H, W, C, Ho, Wo);
@@ -444,6 +688,28 @@ extern "C" int myolo_dwconv3x3_bwd_filter_bn(const myolo_view* xv, const float* 
   MYOLO_CUDA(cudaMemsetAsync(dw, 0, (size_t)9 * C * sizeof(float), as_stream(stream)));
   dim3 grid((unsigned)nchunks, cgroups);
   cudaStream_t cs = as_stream(stream);
+  static int use_old = -1;
+  if (use_old < 0) {
+    const char* e = getenv("MYOLO_DW_TILE");
+    use_old = (e && atoi(e)) ? 1 : 0;
+  }
+  if (!use_old) {
+    // strips of output rows per thread: about four blocks per SM in total
+    const long long coltiles = ceil_div((long long)B * Wo, 32);
+    long long nstrips = max(1LL, min((long long)Ho, ceil_div((long long)kNumSMs * 4, coltiles * cgroups)));
+    const int rows = (int)ceil_div(Ho, nstrips);
+    nstrips = ceil_div(Ho, rows);
+    dim3 g2((unsigned)coltiles, cgroups, (unsigned)nstrips);
+    if (stride == 1) {
+      if (inbn) dw_bwd_filter_strip_kernel<1, true><<<g2, 256, 0, cs>>>(x, dy, dw, B, H, W, C, Ho, Wo, rows, xv->sn, xv->sh, bn);
+      else dw_bwd_filter_strip_kernel<1, false><<<g2, 256, 0, cs>>>(x, dy, dw, B, H, W, C, Ho, Wo, rows, xv->sn, xv->sh, bn);
+    } else {
+      if (inbn) dw_bwd_filter_strip_kernel<2, true><<<g2, 256, 0, cs>>>(x, dy, dw, B, H, W, C, Ho, Wo, rows, xv->sn, xv->sh, bn);
+      else dw_bwd_filter_strip_kernel<2, false><<<g2, 256, 0, cs>>>(x, dy, dw, B, H, W, C, Ho, Wo, rows, xv->sn, xv->sh, bn);
+    }
+    MYOLO_CHECK_LAUNCH();
+    return MYOLO_OK;
+  }
   if (stride == 1) {
     if (inbn) dw_bwd_filter_kernel<1, true><<<grid, 256, 0, cs>>>(x, dy, dw, B, H, W, C, Ho, Wo, chunk, xv->sn, xv->sh, bn);
     else dw_bwd_filter_kernel<1, false><<<grid, 256, 0, cs>>>(x, dy, dw, B, H, W, C, Ho, Wo, chunk, xv->sn, xv->sh, bn);

@@ -131,6 +131,9 @@ class Engine:
         self._side = torch.cuda.Stream(device=self.dev) if os.environ.get("MYOLO_BWD_STREAMS", "1") != "0" else None
         # third stream: the YOLO branch's backward next to the mask head's (Engine.backward)
         self._ystream = torch.cuda.Stream(device=self.dev) if os.environ.get("MYOLO_Y_OVERLAP", "1") != "0" else None
+        # fourth stream: the mask head's filter gradients, off the data-gradient chain (Engine._backward_mask_h16)
+        self._wstream = torch.cuda.Stream(device=self.dev) if (os.environ.get("MYOLO_W_OVERLAP", "0") != "0" and precision == "h16") else None
+        self._w_used = False
         self._evs = {}
         self._replay_on = os.environ.get("MYOLO_REPLAY", "1") != "0"
         # BatchNormalization fusions of the backbone (bit mask; A/B switch): 1 = batch statistics of a depthwise output in
@@ -417,7 +420,7 @@ class Engine:
                 if self.h16:     # loss-scaled half gradients; fp32 only for d(a1) (batch-statistics BN) and d(x0) (ROIAlign)
                     self.dy4h = PF(n, P_, P_, 4 * MASK_C, device=dev, dtype=torch.float16)
                     self.dy4h_ids = torch.zeros(n, dtype=torch.int32, device=dev)   # which rois' rows of dy4h are non-zero
-                    self.mgh = [PF(n, P_, P_, MASK_C, device=dev, dtype=torch.float16) for _ in range(2)]
+                    self.mgh = [PF(n, P_, P_, MASK_C, device=dev, dtype=torch.float16) for _ in range(4 if self._wstream is not None else 2)]
                 else:
                     self.dy4d = PF(n, P_, P_, 4 * MASK_C, device=dev)
                 self.mg = [PF(n, P_, P_, MASK_C, device=dev) for _ in range(2)]
@@ -808,14 +811,14 @@ class Engine:
             self._backward_blocks(blocks[:n_y], ys, None, self.ws_y)
             C.record_py(lambda: e1.record(ys))
             self._backward_mask()
-            if on_tail_ready is not None:
+            if on_tail_ready is not None and not self._w_used:
                 C.record_py(on_tail_ready)
             C.record_py(lambda: main.wait_event(e1))
             self._backward_blocks(blocks[n_y:], main, side, self.ws)
         else:
             if self.with_mask:
                 self._backward_mask()
-            if on_tail_ready is not None:
+            if on_tail_ready is not None and not self._w_used:
                 C.record_py(on_tail_ready)
             self._backward_conv23(main, side, self.ws)
             self._backward_blocks(blocks, main, side, self.ws)
@@ -827,6 +830,11 @@ class Engine:
         if side is not None and "f_done" in self._evs:
             e = self._evs["f_done"]
             C.record_py(lambda: main.wait_event(e))     # every gradient is in the flat buffer once main passes this point
+        if self._w_used:                                # ... and the mask head's filter gradients
+            W, ew = self._wstream, self._ev("w_done")
+            C.record_py(lambda: (ew.record(W), main.wait_event(ew)))
+            if on_tail_ready is not None:
+                C.record_py(on_tail_ready)
 
     def _ev(self, name):        # events are created once and re-recorded every step
         e = self._evs.get(name)
@@ -931,13 +939,29 @@ class Engine:
         gs, ugs = self.gs, self.gs[1:]
         sh3 = self._shift_cache[("h16", P_)]
         shn = self._neg_shifts
+        # Filter gradients feed nothing but Adam: with a W stream they are issued there BEHIND the mask head's data-gradient
+        # chain (one event after its last GEMM), so that they run next to ROIAlign's backward, the feature_map backward and
+        # blocks 6..1 of the backbone instead of in front of them; Engine.backward joins the stream before the optimizer.
+        # Every layer then keeps its own gradient tensor (mgh[0..3]) instead of two ping-pong buffers.
+        main, W = torch.cuda.current_stream(), self._wstream
+        wst = W.cuda_stream if W is not None else st
+        self._w_used = W is not None
+
+        deferred = []
+
+        def wgrad(*args):       # args end with the stream handle
+            if W is not None:
+                deferred.append(args)
+            else:
+                C.call("myolo_gemm_taps_wgrad_h", *args)
+
         C.call("myolo_grad_scale", A["dlogit"], A["dlogit"].numel(), gs, st)
         C.call("myolo_mask_out_bwd_h", self.y4d.rows, self.p["myolo_mask_deconv/bias"], self.p["myolo_mask/kernel"],
                A["dlogit"], self.dy4h.rows, self.g["myolo_mask/kernel"], self.g["myolo_mask/bias"],
                self.g["myolo_mask_deconv/bias"], n, P_, P_, MASK_C, self.NC, gs, self.target_ids, self.dy4h_ids, st)
-        C.call("myolo_gemm_taps_wgrad_h", self.mah[4].rows, MASK_C, self.dy4h.rows, 4 * MASK_C, self.g["myolo_mask_deconv/kernel"],
-               M, 4 * MASK_C, MASK_C, 1, None, 1, ugs, st)
-        g0, g1 = self.mgh
+        wgrad(self.mah[4].rows, MASK_C, self.dy4h.rows, 4 * MASK_C, self.g["myolo_mask_deconv/kernel"],
+              M, 4 * MASK_C, MASK_C, 1, None, 1, ugs, wst)
+        G = self.mgh if W is not None else [self.mgh[0], self.mgh[1], self.mgh[0], self.mgh[1]]     # d(pre-BN) of conv4..conv1
 
         def dgrad_bn(src_rows, lda, name, dst_rows, K, ntaps, shifts, layer):
             b = self.bn[f"myolo_mask_bn{layer}"]
@@ -945,25 +969,29 @@ class Engine:
                    pfw, pfb, self.mah[layer].rows, b.gamma, b.beta, b.mvar, BN_EPS, C.ACT_RELU, b.dgamma, b.dbeta,
                    self.g[f"myolo_mask_conv{layer}/bias"], self.ws, ugs, st)
 
-        dgrad_bn(self.dy4h.rows, 4 * MASK_C, "myolo_mask_deconv/kernel", g0.rows, 4 * MASK_C, 1, None, 4)
+        dgrad_bn(self.dy4h.rows, 4 * MASK_C, "myolo_mask_deconv/kernel", G[0].rows, 4 * MASK_C, 1, None, 4)
         for i in (4, 3, 2):
             name = f"myolo_mask_conv{i}/kernel"
-            C.call("myolo_gemm_taps_wgrad_h", self.mah[i - 1].rows, MASK_C, g0.rows, MASK_C, self.g[name], M, MASK_C, MASK_C, 9,
-                   sh3, 0, ugs, st)
+            gi = G[4 - i]
+            wgrad(self.mah[i - 1].rows, MASK_C, gi.rows, MASK_C, self.g[name], M, MASK_C, MASK_C, 9, sh3, 0, ugs, wst)
             if i > 2:
-                dgrad_bn(g0.rows, MASK_C, name, g1.rows, MASK_C, 9, shn, i - 1)
-                g0, g1 = g1, g0
+                dgrad_bn(gi.rows, MASK_C, name, G[4 - i + 1].rows, MASK_C, 9, shn, i - 1)
         # d(a1) as scaled half -> batch-statistics BN backward in place -> d(pre-BN conv1), still scaled half
-        C.call("myolo_gemm_taps_h", g0.rows, MASK_C, self.wth_d["myolo_mask_conv2/kernel"], None, 0, g1.rows, MASK_C, M,
+        g2, g1 = G[2], G[3]
+        C.call("myolo_gemm_taps_h", g2.rows, MASK_C, self.wth_d["myolo_mask_conv2/kernel"], None, 0, g1.rows, MASK_C, M,
                MASK_C, MASK_C, 9, shn, None, None, None, C.ACT_NONE, pfw, pfb, None, st)
         b = self.bn["myolo_mask_bn1"]
         C.call("myolo_bn_bwd_hh", self.my[1].view(), g1.view(), g1.view(), b.mean, b.var, b.gamma, b.beta, BN_EPS,
                C.ACT_RELU, 1, b.dgamma, b.dbeta, self.ws, ugs, st)
         name = "myolo_mask_conv1/kernel"
-        C.call("myolo_gemm_taps_wgrad_h", self.mah[0].rows, MASK_C, g1.rows, MASK_C, self.g[name], M, MASK_C, MASK_C, 9, sh3, 0,
-               ugs, st)
+        wgrad(self.mah[0].rows, MASK_C, g1.rows, MASK_C, self.g[name], M, MASK_C, MASK_C, 9, sh3, 0, ugs, wst)
         C.call("myolo_gemm_taps_h", g1.rows, MASK_C, self.wth_d[name], self.mg[1].rows, MASK_C, None, 0, M, MASK_C, MASK_C, 9,
                shn, None, None, None, C.ACT_NONE, pfw, pfb, ugs, st)
+        if W is not None:       # the data-gradient chain of the mask head is issued: the filter gradients start behind it
+            e = self._ev("w_start")
+            C.record_py(lambda: (e.record(main), W.wait_event(e)))
+            for args in deferred:
+                C.call("myolo_gemm_taps_wgrad_h", *args)
         return self.mg[1]
 
     def _backward_mask(self):
@@ -1026,7 +1054,12 @@ class Engine:
         C.record_py(self.dfeat.storage.zero_)
         C.call("myolo_roialign_bwd", g0.view(), A["rois"], n, self.R, P_, self.dfeat.view(), st)
         C.call("myolo_colsum", self.dfeat.view(), self.g["feature_map/bias"], self.ws, st)
-        C.call("myolo_conv3x3_wgrad", self.c4.rows, self.dfeat.rows, self.g["feature_map/kernel"], B, F_, F_, 512, MASK_C, st)
+        W = self._wstream if getattr(self, "_w_used", False) else None
+        if W is not None:
+            main, e = torch.cuda.current_stream(), self._ev("w_fm")
+            C.record_py(lambda: (e.record(main), W.wait_event(e)))
+        C.call("myolo_conv3x3_wgrad", self.c4.rows, self.dfeat.rows, self.g["feature_map/kernel"], B, F_, F_, 512, MASK_C,
+               W.cuda_stream if W is not None else st)
         C.call("myolo_conv3x3_dgrad", self.dfeat.rows, self.p["feature_map/kernel"], self.dc4.rows, B, F_, F_, 512, MASK_C, st)
 
     # ------------------------------------------------------------------ optimizer
