@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--size", type=int, default=None)
     ap.add_argument("--precision", default=os.environ.get("MYOLO_PRECISION", "h16"))
     ap.add_argument("--no-fp32-class", action="store_true", help="skip the second (tf32x3) timing")
+    ap.add_argument("--no-sparse", action="store_true", help="skip the secondary exact-sparse-backward timing")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
@@ -256,13 +257,15 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
-def time_precision(args, precision, cfg, host_batches, world, rank, local, with_kernel_events):
+def time_precision(args, precision, cfg, host_batches, world, rank, local, with_kernel_events, sparse=False):
     """Build the model in `precision`, time K device-resident steps (CUDA events) and the end-to-end loops."""
     import torch.distributed as dist
     from myolo import _cabi as C
     from myolo import ddp
     from myolo.model import MaskYOLO
+    os.environ["MYOLO_SPARSE_BWD"] = "1" if sparse else "0"
     model = MaskYOLO("training", cfg, precision=precision, device=local)
+    os.environ["MYOLO_SPARSE_BWD"] = "0"
     eng = model.engine
     c = eng.cfg
     eng.load_params(init_weights(c, args.config))
@@ -341,6 +344,7 @@ def time_precision(args, precision, cfg, host_batches, world, rank, local, with_
     res["value"] = B * world * K / (ms.item() / 1e3)
     res["n_roi"] = eng.n_roi
     res["cfg"] = c
+    res["sparse_stats"] = dict(eng.sparse_stats)
     del model, eng, dev_batches
     torch.cuda.empty_cache()
     return res
@@ -417,6 +421,18 @@ def main():
                 "value": r2["value"], "unit": "images/sec", "ms_per_step": r2["ms_per_step"],
                 "e2e": r2.get("e2e"), "e2e_train_on_batch": r2.get("e2e_train_on_batch"), "gpu_launches": r2["launches"],
                 "loss": r2["loss"]}
+    sparse = None
+    if not args.no_sparse and args.precision == "h16":
+        r3 = time_precision(args, "h16", cfg, host_batches, world, rank, local, False, sparse=True)
+        sparse = {"what": "SECONDARY figure, never the headline: the same step with the exact sparse backward of the mask head "
+                          "(Engine(sparse_backward=True)): above myolo_mask_bn1 only the rois with a target class carry gradient, "
+                          "so conv2..conv4 / deconv backward run on their tiles alone; gradients equal the dense step's up to "
+                          "fp32 summation order (tests/test_model_gpu.py::test_sparse_mask_backward_equals_dense). `value` above "
+                          "is the DENSE step.",
+                  "value": r3["value"], "unit": "images/sec", "ms_per_step": r3["ms_per_step"], "e2e": r3.get("e2e"),
+                  "positive_rois_per_step": r3["sparse_stats"]["rois"] / max(r3["sparse_stats"]["steps"], 1),
+                  "steps_sparse_dense_nopos": [r3["sparse_stats"]["sparse"], r3["sparse_stats"]["dense_fallback"],
+                                               r3["sparse_stats"]["no_positives"]], "loss": r3["loss"]}
     c = main_res["cfg"]
     # ---- roofline of the dominant kernel
     pk, pk_src = peaks()
@@ -462,7 +478,7 @@ def main():
                 "positive_rois_last_step": main_res["npos"],
                 "e2e": main_res.get("e2e"), "e2e_train_on_batch": main_res.get("e2e_train_on_batch"),
                 "gpu_launches": main_res["launches"], "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-                "fp32_class": fp32, "parity": parity,
+                "fp32_class": fp32, "sparse_backward": sparse, "parity": parity,
                 "model_tflops_per_s": value * fl / 1e12, "frac_of_conv_roofline": value * fl / 1e12 / pk["bf16_tflops_sustained"],
                 "loss": main_res["loss"]}
         print(json.dumps(line))

@@ -145,6 +145,12 @@ int myolo_prep_weights_batch(const void* jobs_dev, int n_jobs, int total_tiles, 
  * gradient for the data-gradient GEMM. */
 int myolo_copy_cols(const float* src, long long src_ld, float* dst, long long dst_ld, long long rows, int cols,
                     myolo_stream stream);
+/* gather (scatter == 0): dst tile i = src tile list[i]; scatter: dst tile list[i] = src tile i, for i < n_list; a tile is
+ * tile_bytes contiguous bytes (multiple of 16).  Moves the padded-flat tiles of the POSITIVE rois into / out of compact
+ * tensors for the exact sparse backward of the mask head: only rois with a target class carry gradient above
+ * myolo_mask_bn1 (myolo_mask_loss_graph, myolo/model.py:718-754, gathers the positive rois before the loss). */
+int myolo_copy_tiles(const void* src, void* dst, const int* list, int n_list, long long tile_bytes, int scatter,
+                     myolo_stream stream);
 /* pointwise / 3x3 named wrappers (SURVEY 8b names).  w = HWIO kernel [t][Cin][Cout]; wt = its
  * per-tap transpose [t][Cout][Cin] (myolo_prep_weights). */
 int myolo_pwconv_fwd(const float* x, const float* wt, float* y, long long M, int Cin, int Cout,

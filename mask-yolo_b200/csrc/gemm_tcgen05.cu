@@ -697,6 +697,31 @@ __global__ void copy_cols_kernel(const float* __restrict__ src, long long src_ld
 }  // namespace tc
 }  // namespace myolo
 
+namespace myolo {
+namespace tc {
+// tile i of the compact buffer <-> tile list[i] of the full buffer, 16 bytes per thread and step
+__global__ void __launch_bounds__(256) copy_tiles_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst,
+                                                         const int* __restrict__ list, long long tile_vec, int scatter) {
+  const long long t = __ldg(list + blockIdx.y);
+  const uint4* s = src + (scatter ? (long long)blockIdx.y : t) * tile_vec;
+  uint4* d = dst + (scatter ? t : (long long)blockIdx.y) * tile_vec;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < tile_vec; i += (long long)gridDim.x * blockDim.x) d[i] = s[i];
+}
+}  // namespace tc
+}  // namespace myolo
+
+extern "C" int myolo_copy_tiles(const void* src, void* dst, const int* list, int n_list, long long tile_bytes, int scatter,
+                                myolo_stream stream) {
+  MYOLO_CHECK_ARG(src && dst && list && n_list > 0 && n_list <= 65535 && tile_bytes > 0 && (tile_bytes % 16) == 0);
+  MYOLO_CHECK_ARG(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0);
+  const long long tv = tile_bytes / 16;
+  dim3 grid((unsigned)max(1LL, min(ceil_div(tv, 256), 64LL)), (unsigned)n_list);
+  copy_tiles_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), list,
+                                                         tv, scatter);
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
+}
+
 extern "C" int myolo_copy_cols(const float* src, long long src_ld, float* dst, long long dst_ld, long long rows, int cols,
                                myolo_stream stream) {
   MYOLO_CHECK_ARG(src && dst && rows > 0 && cols > 0 && src_ld >= cols && dst_ld >= cols);

@@ -129,6 +129,20 @@ def stop_recording():
     return r
 
 
+class no_record(object):
+    """Suspend the launch recording: for a host action that is itself recorded with record_py and issues C-ABI calls whose
+    arguments change from step to step (it runs again at every replay)."""
+
+    def __enter__(self):
+        global _rec
+        self.saved, _rec = _rec, None
+
+    def __exit__(self, *a):
+        global _rec
+        _rec = self.saved
+        return False
+
+
 def record_py(fn):
     """Run a host-side action (event record / wait, torch fill, hook) and, while recording, note it in sequence."""
     fn()

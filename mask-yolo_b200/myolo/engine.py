@@ -104,7 +104,7 @@ class Engine:
     LOSS_WEIGHTS."""
 
     def __init__(self, cfg: dict, batch: int, mode: str = "training", precision: str = "tf32", device: int = 0,
-                 params: Optional[Dict[str, torch.Tensor]] = None, seed: int = 0):
+                 params: Optional[Dict[str, torch.Tensor]] = None, seed: int = 0, sparse_backward: Optional[bool] = None):
         assert mode in ("training", "inference", "yolo")
         if not torch.cuda.is_available():
             raise C.MyoloError("the Mask-YOLO hot path needs an sm_100 (B200) GPU; there is no CPU fallback")
@@ -134,6 +134,12 @@ class Engine:
         # fourth stream: the mask head's filter gradients, off the data-gradient chain (Engine._backward_mask_h16)
         self._wstream = torch.cuda.Stream(device=self.dev) if (os.environ.get("MYOLO_W_OVERLAP", "0") != "0" and precision == "h16") else None
         self._w_used = False
+        # exact sparse backward of the mask head (h16 mode; OFF by default, never the headline number): above
+        # myolo_mask_bn1 only the rois with a target class carry gradient, see _sparse_mask_middle
+        if sparse_backward is None:
+            sparse_backward = os.environ.get("MYOLO_SPARSE_BWD", "0") != "0"
+        self.sparse_backward = bool(sparse_backward) and precision == "h16" and mode == "training"
+        self.sparse_stats = {"steps": 0, "sparse": 0, "dense_fallback": 0, "no_positives": 0, "rois": 0}
         self._evs = {}
         self._replay_on = os.environ.get("MYOLO_REPLAY", "1") != "0"
         # BatchNormalization fusions of the backbone (bit mask; A/B switch): 1 = batch statistics of a depthwise output in
@@ -423,6 +429,15 @@ class Engine:
                     self.mgh = [PF(n, P_, P_, MASK_C, device=dev, dtype=torch.float16) for _ in range(4 if self._wstream is not None else 2)]
                 else:
                     self.dy4d = PF(n, P_, P_, 4 * MASK_C, device=dev)
+                if self.h16 and self.sparse_backward:
+                    # compact padded-flat tensors for up to pcap positive rois (more than that: the step runs dense)
+                    self.pcap = max(64, n // 8)
+                    hp = lambda c: PF(self.pcap, P_, P_, c, device=dev, dtype=torch.float16)      # noqa: E731
+                    self.sp_a = [None] + [hp(MASK_C) for _ in range(4)]        # a1..a4 of the positive rois
+                    self.sp_dy4 = hp(4 * MASK_C)
+                    self.sp_g = [hp(MASK_C) for _ in range(2)]
+                    self.sp_list = torch.zeros(self.pcap, dtype=torch.int32, device=dev)
+                    self.sp_list_host = torch.zeros(self.pcap, dtype=torch.int32).pin_memory()
                 self.mg = [PF(n, P_, P_, MASK_C, device=dev) for _ in range(2)]
                 self.dfeat = PF(B, F_, F_, MASK_C, device=dev)
                 self.dc4 = PF(B, F_, F_, 512, device=dev)
@@ -959,27 +974,17 @@ class Engine:
         C.call("myolo_mask_out_bwd_h", self.y4d.rows, self.p["myolo_mask_deconv/bias"], self.p["myolo_mask/kernel"],
                A["dlogit"], self.dy4h.rows, self.g["myolo_mask/kernel"], self.g["myolo_mask/bias"],
                self.g["myolo_mask_deconv/bias"], n, P_, P_, MASK_C, self.NC, gs, self.target_ids, self.dy4h_ids, st)
-        wgrad(self.mah[4].rows, MASK_C, self.dy4h.rows, 4 * MASK_C, self.g["myolo_mask_deconv/kernel"],
-              M, 4 * MASK_C, MASK_C, 1, None, 1, ugs, wst)
+        if not self.sparse_backward:
+            wgrad(self.mah[4].rows, MASK_C, self.dy4h.rows, 4 * MASK_C, self.g["myolo_mask_deconv/kernel"],
+                  M, 4 * MASK_C, MASK_C, 1, None, 1, ugs, wst)
         G = self.mgh if W is not None else [self.mgh[0], self.mgh[1], self.mgh[0], self.mgh[1]]     # d(pre-BN) of conv4..conv1
-
-        def dgrad_bn(src_rows, lda, name, dst_rows, K, ntaps, shifts, layer):
-            b = self.bn[f"myolo_mask_bn{layer}"]
-            C.call("myolo_gemm_taps_bnbwd_h", src_rows, lda, self.wth_d[name], None, dst_rows, MASK_C, M, MASK_C, K, ntaps, shifts,
-                   pfw, pfb, self.mah[layer].rows, b.gamma, b.beta, b.mvar, BN_EPS, C.ACT_RELU, b.dgamma, b.dbeta,
-                   self.g[f"myolo_mask_conv{layer}/bias"], self.ws, ugs, st)
-
-        dgrad_bn(self.dy4h.rows, 4 * MASK_C, "myolo_mask_deconv/kernel", G[0].rows, 4 * MASK_C, 1, None, 4)
-        for i in (4, 3, 2):
-            name = f"myolo_mask_conv{i}/kernel"
-            gi = G[4 - i]
-            wgrad(self.mah[i - 1].rows, MASK_C, gi.rows, MASK_C, self.g[name], M, MASK_C, MASK_C, 9, sh3, 0, ugs, wst)
-            if i > 2:
-                dgrad_bn(gi.rows, MASK_C, name, G[4 - i + 1].rows, MASK_C, 9, shn, i - 1)
-        # d(a1) as scaled half -> batch-statistics BN backward in place -> d(pre-BN conv1), still scaled half
-        g2, g1 = G[2], G[3]
-        C.call("myolo_gemm_taps_h", g2.rows, MASK_C, self.wth_d["myolo_mask_conv2/kernel"], None, 0, g1.rows, MASK_C, M,
-               MASK_C, MASK_C, 9, shn, None, None, None, C.ACT_NONE, pfw, pfb, None, st)
+        if self.sparse_backward:
+            # everything between the loss and d(a1) on the positive rois only; a host action (it reads the number of
+            # positives) that is recorded as such and issues its own launches at every replay
+            g1 = self.mgh[1]
+            C.record_py(self._sparse_mask_middle)
+        else:
+            g1 = self._dense_mask_middle(G, wgrad, M, pfw, pfb, sh3, shn, ugs, st)
         b = self.bn["myolo_mask_bn1"]
         C.call("myolo_bn_bwd_hh", self.my[1].view(), g1.view(), g1.view(), b.mean, b.var, b.gamma, b.beta, BN_EPS,
                C.ACT_RELU, 1, b.dgamma, b.dbeta, self.ws, ugs, st)
@@ -993,6 +998,96 @@ class Engine:
             for args in deferred:
                 C.call("myolo_gemm_taps_wgrad_h", *args)
         return self.mg[1]
+
+    def _dense_mask_middle(self, G, wgrad, M, pfw, pfb, sh3, shn, ugs, st):
+        """deconv data gradient + BN4 backward, conv4..conv2 filter / data gradients with the fused BN backward, conv2's data
+        gradient: from dy4h to d(a1) (scaled half, returned) over ALL rois."""
+        def dgrad_bn(src_rows, lda, name, dst_rows, K, ntaps, shifts, layer):
+            b = self.bn[f"myolo_mask_bn{layer}"]
+            C.call("myolo_gemm_taps_bnbwd_h", src_rows, lda, self.wth_d[name], None, dst_rows, MASK_C, M, MASK_C, K, ntaps, shifts,
+                   pfw, pfb, self.mah[layer].rows, b.gamma, b.beta, b.mvar, BN_EPS, C.ACT_RELU, b.dgamma, b.dbeta,
+                   self.g[f"myolo_mask_conv{layer}/bias"], self.ws, ugs, st)
+
+        dgrad_bn(self.dy4h.rows, 4 * MASK_C, "myolo_mask_deconv/kernel", G[0].rows, 4 * MASK_C, 1, None, 4)
+        for i in (4, 3, 2):
+            name = f"myolo_mask_conv{i}/kernel"
+            gi = G[4 - i]
+            wgrad(self.mah[i - 1].rows, MASK_C, gi.rows, MASK_C, self.g[name], M, MASK_C, MASK_C, 9, sh3, 0, ugs,
+                  self._wstream.cuda_stream if self._w_used else st)
+            if i > 2:
+                dgrad_bn(gi.rows, MASK_C, name, G[4 - i + 1].rows, MASK_C, 9, shn, i - 1)
+        # d(a1) as scaled half
+        g2, g1 = G[2], G[3]
+        C.call("myolo_gemm_taps_h", g2.rows, MASK_C, self.wth_d["myolo_mask_conv2/kernel"], None, 0, g1.rows, MASK_C, M,
+               MASK_C, MASK_C, 9, shn, None, None, None, C.ACT_NONE, pfw, pfb, None, st)
+        return g1
+
+    def _sparse_mask_middle(self):
+        """Exact sparse form of _dense_mask_middle.  The mask loss touches the rois with a target class only
+        (myolo_mask_loss_graph gathers them, model.py:718-754), bn2..bn4 use fixed statistics and every roi is its own
+        "image" for the convolutions, so d(a4)..d(a1) and every summand of the filter / BN gradients of conv2..conv4 and of
+        the deconvolution are identically zero for all other rois.  Their padded-flat tiles are gathered into compact
+        tensors, the SAME kernels run on P tiles instead of n_roi, and d(a1) is scattered back into a zeroed full tensor
+        for the batch-statistics backward of bn1, which couples all rois.  Runs as a host action inside the recorded step
+        (it needs the number of positives on the host: one 4*B-byte read).  More positives than the compact tensors hold:
+        the dense form runs for that step."""
+        with C.no_record():
+            st = self._st()
+            B, R, n = self.B, self.R, self.n_roi
+            P_ = self.cfg["POOL"]
+            pfw, pfb = P_ + 1, (P_ + 1) * (P_ + 1)
+            M = self.mah[0].M
+            ugs = self.gs[1:]
+            sh3, shn = self._shift_cache[("h16", P_)], self._neg_shifts
+            npos = self.n_pos.cpu().tolist()             # the positives are the first n_pos[b] rois of image b (a7)
+            idx = [b * R + j for b in range(B) for j in range(npos[b])]
+            P = len(idx)
+            self.sparse_stats["steps"] += 1
+            self.sparse_stats["rois"] += P
+            g1 = self.mgh[1]
+            if P > self.pcap:
+                self.sparse_stats["dense_fallback"] += 1
+                G = [self.mgh[0], self.mgh[1], self.mgh[0], self.mgh[1]]
+                call = lambda *a: C.call("myolo_gemm_taps_wgrad_h", *a)                       # noqa: E731
+                call(self.mah[4].rows, MASK_C, self.dy4h.rows, 4 * MASK_C, self.g["myolo_mask_deconv/kernel"], M, 4 * MASK_C,
+                     MASK_C, 1, None, 1, ugs, st)
+                w_used, self._w_used = self._w_used, False
+                self._dense_mask_middle(G, call, M, pfw, pfb, sh3, shn, ugs, st)
+                self._w_used = w_used
+                return
+            C.record_py(g1.storage.zero_)                 # (not recording here: simply runs) d(a1) of the other rois
+            if P == 0:
+                self.sparse_stats["no_positives"] += 1
+                return
+            self.sparse_stats["sparse"] += 1
+            self.sp_list_host[:P] = torch.tensor(idx, dtype=torch.int32)
+            self.sp_list[:P].copy_(self.sp_list_host[:P], non_blocking=True)
+            tile = pfb * MASK_C * 2                        # bytes of one roi's padded-flat tile, half
+            for i in (1, 2, 3, 4):
+                C.call("myolo_copy_tiles", self.mah[i].rows, self.sp_a[i].rows, self.sp_list, P, tile, 0, st)
+            C.call("myolo_copy_tiles", self.dy4h.rows, self.sp_dy4.rows, self.sp_list, P, 4 * tile, 0, st)
+            Mc = P * pfb
+            a, dy4, (ga, gb) = self.sp_a, self.sp_dy4, self.sp_g
+            C.call("myolo_gemm_taps_wgrad_h", a[4].rows, MASK_C, dy4.rows, 4 * MASK_C, self.g["myolo_mask_deconv/kernel"], Mc,
+                   4 * MASK_C, MASK_C, 1, None, 1, ugs, st)
+
+            def dgrad_bn(src_rows, lda, name, dst_rows, K, ntaps, shifts, layer):
+                b = self.bn[f"myolo_mask_bn{layer}"]
+                C.call("myolo_gemm_taps_bnbwd_h", src_rows, lda, self.wth_d[name], None, dst_rows, MASK_C, Mc, MASK_C, K, ntaps,
+                       shifts, pfw, pfb, a[layer].rows, b.gamma, b.beta, b.mvar, BN_EPS, C.ACT_RELU, b.dgamma, b.dbeta,
+                       self.g[f"myolo_mask_conv{layer}/bias"], self.ws, ugs, st)
+
+            dgrad_bn(dy4.rows, 4 * MASK_C, "myolo_mask_deconv/kernel", ga.rows, 4 * MASK_C, 1, None, 4)
+            for i in (4, 3, 2):
+                name = f"myolo_mask_conv{i}/kernel"
+                C.call("myolo_gemm_taps_wgrad_h", a[i - 1].rows, MASK_C, ga.rows, MASK_C, self.g[name], Mc, MASK_C, MASK_C, 9,
+                       sh3, 0, ugs, st)
+                if i > 2:
+                    dgrad_bn(ga.rows, MASK_C, name, gb.rows, MASK_C, 9, shn, i - 1)
+                    ga, gb = gb, ga
+            C.call("myolo_gemm_taps_h", ga.rows, MASK_C, self.wth_d["myolo_mask_conv2/kernel"], None, 0, gb.rows, MASK_C, Mc,
+                   MASK_C, MASK_C, 9, shn, None, None, None, C.ACT_NONE, pfw, pfb, None, st)
+            C.call("myolo_copy_tiles", gb.rows, g1.rows, self.sp_list, P, tile, 1, st)
 
     def _backward_mask(self):
         A, st, n = self.A, self._st(), self.n_roi

@@ -4,6 +4,6 @@
 PREC=${1:-h16}
 mkdir -p gpurun_out
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_step_${PREC}.csv \
-    python bench.py --precision ${PREC} --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-parity --no-fp32-class > gpurun_out/launches_step_${PREC}.log 2>&1
+    python bench.py --precision ${PREC} --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-parity --no-fp32-class --no-sparse > gpurun_out/launches_step_${PREC}.log 2>&1
 python scripts/summarize_launches.py gpurun_out/launches_step_${PREC}.csv > gpurun_out/step_breakdown_${PREC}.txt
 tail -60 gpurun_out/step_breakdown_${PREC}.txt

@@ -315,3 +315,53 @@ def test_replayed_steps_equal_recorded_steps():
                 assert _l2(g1[k], g2[k]) <= 1e-3, (step, k)
     for k in pa:
         assert _l2(pa[k], pb[k]) <= 1e-5, k
+
+
+def test_sparse_mask_backward_equals_dense():
+    """Exact sparse backward of the mask head (Engine(sparse_backward=True), h16): above myolo_mask_bn1 only the rois with a
+    target class carry gradient, so running conv2..conv4 / deconv backward on their tiles alone must reproduce the dense
+    step -- same outputs and losses, gradients equal up to the summation order of the fp32 atomics.  Also: a batch without
+    positives, the dense fallback when the compact tensors are too small, and replayed steps."""
+    from myolo.engine import Engine
+    S, B = 128, 6
+    c, oc, P, inputs, _, _ = _reference(S, B, 100)
+    dev_in = Hh.to_device(inputs)
+    dense = Engine(c, B, "training", "h16", params=P, sparse_backward=False)
+    ref = []
+    for step in range(3):
+        out_d = dense.train_step(dev_in, lr=0.0)
+        ref.append(({k: out_d[k].item() for k in ("mask_loss", "yolo_sum_loss")}, dense.grad_dict()))
+    npos = int(dense.n_pos.sum().item())
+    assert npos >= B
+    for pcap, expect in ((None, "sparse"), (2, "dense_fallback")):
+        eng = Engine(c, B, "training", "h16", params=P, sparse_backward=True)
+        assert eng.sparse_backward
+        if pcap is not None:
+            eng.pcap = pcap
+        for step in range(3):                          # step 0 records, 1 and 2 replay (the host action runs every time)
+            out_s = eng.train_step(dev_in, lr=0.0)
+            torch.cuda.synchronize()
+            losses, gd = ref[step]                       # the dense engine's step of the same number
+            for k in ("mask_loss", "yolo_sum_loss"):      # the forward is the same code: equal up to the order of its atomics
+                assert abs(out_s[k].item() - losses[k]) <= 1e-6 * max(1.0, abs(losses[k])), k
+            gs = eng.grad_dict()
+            # the mask head's own gradients: same products, fp32 summation order only; the backbone below inherits the
+            # run-to-run noise of ROIAlign's backward atomics, amplified by 29 BN layers (as in the replay test above)
+            head = [(_l2(gs[k], gd[k]), k) for k in gd if gd[k].abs().max() > 0 and k.startswith("myolo_mask")]
+            rest = [(_l2(gs[k], gd[k]), k) for k in gd if gd[k].abs().max() > 0 and not k.startswith("myolo_mask")]
+            assert max(head)[0] <= 2e-5, (expect, step, max(head))
+            assert max(rest)[0] <= 1e-3, (expect, step, max(rest))
+            for k in gd:
+                if gd[k].abs().max() == 0:
+                    assert gs[k].abs().max().item() == 0, k
+        assert eng.sparse_stats[expect] == 3 and eng.sparse_stats["rois"] == 3 * npos, eng.sparse_stats
+    # no positives at all: every mask-head gradient is exactly zero, the yolo branch still trains
+    img = torch.rand(B, S, S, 3, generator=torch.Generator().manual_seed(8))
+    inputs2 = Hh.to_device(Hh.batch_from_boxes(c, B, img, [[] for _ in range(B)], 11))
+    eng = Engine(c, B, "training", "h16", params=P, sparse_backward=True)
+    out2 = eng.train_step(inputs2, lr=0.0)
+    torch.cuda.synchronize()
+    g2 = eng.grad_dict()
+    assert out2["mask_loss"].item() == 0.0 and eng.sparse_stats["no_positives"] == 1
+    assert g2["myolo_mask_conv3/kernel"].abs().max().item() == 0 and g2["feature_map/kernel"].abs().max().item() == 0
+    assert g2["conv_pw_3/kernel"].abs().max().item() > 0 and all(torch.isfinite(v).all() for v in g2.values())
