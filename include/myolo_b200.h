@@ -117,6 +117,15 @@ int myolo_gemm_taps_win(const float* A, long long lda, const float* Bt, float* C
                         long long M, int N, int K, int ntaps, const int* shifts_host,
                         const float* bias, const float* scale, const float* shift_c, int act,
                         int pf_w1, int pf_blk, int accumulate, myolo_stream stream);
+/* plain GEMM over k-segments on the same persistent kernel: C[m][n] = sum_g sum_k A[m + seg_off[g]][k] * Bt[g][n][k]
+ * (seg_off >= 0, host array of nseg <= 8 row offsets into ONE matrix A), and -- when mean / var are given -- the batch
+ * statistics of C over its M rows in the epilogue (ws: BN workspace, zero before and after).  This is how the pointwise
+ * convolutions of the backbone (keras_applications _depthwise_conv_block, call sites myolo/model.py:68-77, 256-268) run in
+ * the 3xTF32 modes: A = [tf32 high part | tf32 low part] of the activation, lo_off rows apart, Bt = the [hi | hi | lo]
+ * weight triple of myolo_prep_weights (round 2), seg_off = {0, lo_off, 0}.  M >= 4096, N % 128 == 0, K % 32 == 0. */
+int myolo_gemm_segs_win(const float* A, long long lda, const float* Bt, float* C, long long ldc, long long M, int N,
+                        int K, int nseg, const int* seg_off_host, float* mean, float* var, double* ws, myolo_stream stream);
+int myolo_gemm_segs_win_supported(long long lda, long long ldc, long long M, int N, int K, int nseg);
 int myolo_gemm_taps_win_supported(long long lda, long long ldc, long long M, int N, int K, int ntaps,
                                   const int* shifts_host, int accumulate);
 int myolo_gemm_taps_wgrad_ffma(const float* A, long long lda, const float* D, long long ldd, float* dW,

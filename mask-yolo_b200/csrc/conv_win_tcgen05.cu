@@ -153,7 +153,7 @@ template <int WBN, int NACC, int CG, int EL = 4>
 __global__ void __launch_bounds__(win_threads(EL))
 tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmCh, long long M, int N,
-                   int K, int ntaps, TapShifts sh, Epi ep, MaskTail mt, int nitems, int dbg) {
+                   int K, int ntaps, TapShifts sh, Epi ep, MaskTail mt, int nitems, int dbg, int nseg, TapShifts seg) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int WBM = 128 * NACC, WROWS = win_rows(NACC), WBOX = win_box(NACC);
   constexpr uint32_t kWinBytes = WROWS * 128;
@@ -276,7 +276,11 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       uint32_t ab = 0, aph = 0, s = 0, bph = 0;
       for (int item = cid; item < nitems; item += ncl) {
         const int tile = item / nh, half = item - tile * nh;
-        const int row0 = tile * (WBM * CG) + (int)rank * WBM - WHALO;
+        const int row00 = tile * (WBM * CG) + (int)rank * WBM - WHALO;
+        // k-segments (nseg > 1, plain GEMMs): C = sum_g A[rows + seg[g]] * Bt[g]; the hi / lo operand pair of a 3xTF32
+        // GEMM is three segments over two row ranges of ONE tensor map (seg = {0, lo_off, 0})
+        for (int g = 0; g < nseg; ++g) {
+        const int row0 = row00 + seg.s[g];
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(a_empty(ab), aph ^ 1u);
           const uint32_t wa = awin0 + ab * kWinBytes;
@@ -297,15 +301,16 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             if (CG == 2) {
               if (leader) mbar_expect_tx(b_full(s), 2 * kWBBytes);
               tma_load_2d_2sm(bst0 + s * kWBBytes, &tmB, mapa_rank(b_full(s), 0), kb * KEL,
-                              t * N + half * WBN + (int)rank * (WBN / 2));
+                              (g * ntaps + t) * N + half * WBN + (int)rank * (WBN / 2));
             } else if (dbg & 2) {
               mbar_arrive(b_full(s));
             } else {
               mbar_expect_tx(b_full(s), kWBBytes);
-              tma_load_2d(bst0 + s * kWBBytes, &tmB, b_full(s), kb * KEL, t * N + half * WBN);
+              tma_load_2d(bst0 + s * kWBBytes, &tmB, b_full(s), kb * KEL, (g * ntaps + t) * N + half * WBN);
             }
             if (++s == (uint32_t)nwb) { s = 0; bph ^= 1u; }
           }
+        }
         }
       }
     }
@@ -341,7 +346,8 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         mbar_wait(t_empty(ts), ((it / TS) & 1u) ^ 1u);  // the epilogue that last used this TMEM stage has drained it
         tc_fence_after();
         const uint32_t tacc = tmem + ts * TSTRIDE;
-        for (int kb = 0; kb < kblocks; ++kb) {
+        for (int gk = 0; gk < nseg * kblocks; ++gk) {
+          const int kb = gk;                                    // only its being zero matters below
           mbar_wait(a_full(ab), aph);
           tc_fence_after();
           const uint32_t wa = awin0 + ab * kWinBytes;
@@ -735,7 +741,7 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               if (rnd) o[e] = round_tf32(o[e]);
               if (!valid) o[e] = 0.f;   // padded-flat pad rows stay zero
             }
-            if (EL == 2 && ep.st_sums && !st_h) {   // batch statistics of the stored result
+            if (ep.st_sums && !st_h) {   // batch statistics of the stored result (pad / out-of-range rows are zero)
               v[4 * j] = o[0]; v[4 * j + 1] = o[1]; v[4 * j + 2] = o[2]; v[4 * j + 3] = o[3];
             }
             if (st_h) {   // the half copy; v[] keeps the packed words until the 16-byte chunk is complete
@@ -764,6 +770,16 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             } else if (ring_h) {
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");   // keep one group per chunk: the ring counts groups
             }
+          }
+          if (EL == 4 && ep.st_sums && !ep.bn_a) {
+            // tf32 flavour (pointwise convolutions of the backbone): four epilogue warps, any N; the chunk's column sums
+            // go straight to the fp64 workspace (one atomic per column and 32-row chunk)
+            float sq[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
+            const float s0 = warp_colsum32(v, lane), s1 = warp_colsum32(sq, lane);
+            if (s0 != 0.f) atomicAdd(ep.st_sums + n0 + lane, (double)s0);
+            if (s1 != 0.f) atomicAdd(ep.st_sums + N + n0 + lane, (double)s1);
           }
           if (EL == 2 && ep.st_sums && !st_h && !ep.bn_a) {   // column sums of the chunk while its TMA store is in flight
             // shifted by a per-column pivot (the layer's moving mean): E[x^2] - E[x]^2 would lose mean^2 / variance digits
@@ -874,7 +890,8 @@ struct HalfIO {
 static int launch_win(const float* A, long long lda, const float* Bt, float* C, long long ldc, long long M, int N, int K,
                       int ntaps, const int* shifts_host, const float* bias, const float* scale, const float* shift_c,
                       int act, int pf_w1, int pf_blk, int accumulate, const MaskTail& mt, myolo_stream stream,
-                      const BnBwd& bnb = BnBwd{}, const HalfIO& hio = HalfIO{}) {
+                      const BnBwd& bnb = BnBwd{}, const HalfIO& hio = HalfIO{}, int nseg = 1, const int* seg_off = nullptr,
+                      double* stats_sums = nullptr) {
   MYOLO_CHECK_ARG(A && Bt && ((((uintptr_t)A | (uintptr_t)Bt | (uintptr_t)C) & 15) == 0));
   MYOLO_CHECK_ARG(C || (hio.on && hio.no_f32));
   MYOLO_CHECK_ARG(win_shape_ok(lda, ldc, M, N, K, ntaps, shifts_host, accumulate, hio.on ? 1 : 4096));
@@ -889,11 +906,19 @@ static int launch_win(const float* A, long long lda, const float* Bt, float* C, 
   MYOLO_CHECK_ARG(pf_w1 <= 0 || pf_blk > 0);
   TapShifts sh;
   for (int t = 0; t < 32; ++t) sh.s[t] = (shifts_host && t < ntaps) ? shifts_host[t] : 0;
+  MYOLO_CHECK_ARG(nseg >= 1 && nseg <= 8 && (nseg == 1 || (seg_off && ntaps == 1 && !hio.on && !mt.masks && !bnb.a)));
+  TapShifts seg;
+  for (int g = 0; g < 32; ++g) seg.s[g] = (seg_off && g < nseg) ? seg_off[g] : 0;
   CUtensorMap ta, tb;
   // rows in [M, M + max shift) are the zero guard rows of the padded-flat tensor; everything else out of
   // range (negative rows, the tail of the last tile) is TMA zero fill
   int maxs = 0;
   for (int t = 0; t < ntaps; ++t) maxs = sh.s[t] > maxs ? sh.s[t] : maxs;
+  long long maxseg = 0;
+  for (int g = 0; g < nseg; ++g) {
+    MYOLO_CHECK_ARG(seg.s[g] >= 0);
+    maxseg = seg.s[g] > maxseg ? seg.s[g] : maxseg;
+  }
   static int bo_mode = -1;
   if (bo_mode < 0) {
     const char* e = getenv("MYOLO_WIN_BO");
@@ -926,9 +951,9 @@ static int launch_win(const float* A, long long lda, const float* Bt, float* C, 
       tch = ta;
     }
   } else {
-    rc = get_map(A, M + maxs, K, lda, win_box(nacc), &ta);
+    rc = get_map(A, M + maxs + maxseg, K, lda, win_box(nacc), &ta);
     if (rc) return rc;
-    rc = get_map(Bt, (long long)ntaps * N, K, K, wbn / cg, &tb);
+    rc = get_map(Bt, (long long)nseg * ntaps * N, K, K, wbn / cg, &tb);
     if (rc) return rc;
     rc = get_map(C, M, N, ldc, 32, &tc_);
     if (rc) return rc;
@@ -968,6 +993,10 @@ static int launch_win(const float* A, long long lda, const float* Bt, float* C, 
     ep.st_sums = hio.st_sums;
     ep.st_pivot = hio.st_pivot;
   }
+  if (stats_sums) {
+    MYOLO_CHECK_ARG(!hio.on && !bnb.a && !mt.masks && !accumulate);
+    ep.st_sums = stats_sums;
+  }
   cudaStream_t st = as_stream(stream);
   const int maxcl = hio.on ? max_clusters_h : max_clusters;
   MaskTail mtl = mt;
@@ -994,9 +1023,9 @@ static int launch_win(const float* A, long long lda, const float* Bt, float* C, 
     cfg.attrs = at;
     cfg.numAttrs = 1;
     if (hio.on)
-      MYOLO_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_win_kernel<256, 1, 2, 2>, ta, tb, tc_, tch, M, N, K, ntaps, sh, ep, mtl, nitems, bo_mode));
+      MYOLO_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_win_kernel<256, 1, 2, 2>, ta, tb, tc_, tch, M, N, K, ntaps, sh, ep, mtl, nitems, bo_mode, nseg, seg));
     else
-      MYOLO_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_win_kernel<256, 1, 2>, ta, tb, tc_, tch, M, N, K, ntaps, sh, ep, mtl, nitems, bo_mode));
+      MYOLO_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_win_kernel<256, 1, 2>, ta, tb, tc_, tch, M, N, K, ntaps, sh, ep, mtl, nitems, bo_mode, nseg, seg));
     return MYOLO_OK;
   }
   if (hio.on) {
@@ -1004,13 +1033,13 @@ static int launch_win(const float* A, long long lda, const float* Bt, float* C, 
     return MYOLO_ERR_CUDA;
   }
   if (cg == 2) {   // no pair fits (should not happen on B200): rebuild the weight map for the single-CTA box
-    rc = get_map(Bt, (long long)ntaps * N, K, K, wbn, &tb);
+    rc = get_map(Bt, (long long)nseg * ntaps * N, K, K, wbn, &tb);
     if (rc) return rc;
   }
   const int nitems = (int)ceil_div(M, 128 * nacc) * (N / wbn);
   const int grid = nitems < kNumSMs ? nitems : kNumSMs;
 #define MYOLO_WIN_LAUNCH(BN_, NA_) \
-  tc_conv_win_kernel<BN_, NA_, 1><<<grid, kThreads, win_smem(NA_), st>>>(ta, tb, tc_, tch, M, N, K, ntaps, sh, ep, mt, nitems, bo_mode)
+  tc_conv_win_kernel<BN_, NA_, 1><<<grid, kThreads, win_smem(NA_), st>>>(ta, tb, tc_, tch, M, N, K, ntaps, sh, ep, mt, nitems, bo_mode, nseg, seg)
   if (wbn == 256 && nacc == 1) MYOLO_WIN_LAUNCH(256, 1);
   else if (wbn == 256) MYOLO_WIN_LAUNCH(256, 2);
   else if (nacc == 1) MYOLO_WIN_LAUNCH(128, 1);
@@ -1027,6 +1056,42 @@ extern "C" int myolo_gemm_taps_win(const float* A, long long lda, const float* B
   MaskTail mt{};
   return launch_win(A, lda, Bt, C, ldc, M, N, K, ntaps, shifts_host, bias, scale, shift_c, act, pf_w1, pf_blk, accumulate,
                     mt, stream);
+}
+
+namespace myolo {
+__global__ void stats_finalize_kernel(double* __restrict__ sums, const float* __restrict__ pivot, float* __restrict__ mean,
+                                      float* __restrict__ var, int C, double inv_count) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double m = sums[c] * inv_count;                      // mean of (x - pivot)
+  const double vv = sums[C + c] * inv_count - m * m;
+  mean[c] = (float)(m + (pivot ? (double)pivot[c] : 0.0));
+  var[c] = (float)(vv > 0.0 ? vv : 0.0);
+  sums[c] = 0.0;
+  sums[C + c] = 0.0;
+}
+}  // namespace myolo
+
+// Plain GEMM over k-segments on the persistent kernel: C[m][n] = sum_g sum_k A[m + seg_off[g]][k] * Bt[g][n][k], with the
+// batch statistics of C (mean / biased variance per column over the M rows) reduced in the epilogue when mean != null.
+// The pointwise convolutions of the backbone in the 3xTF32 modes: A holds the tf32 high and low parts of the activation
+// lo_off rows apart, Bt the [hi | hi | lo] weight triple, seg_off = {0, lo_off, 0}.
+extern "C" int myolo_gemm_segs_win_supported(long long lda, long long ldc, long long M, int N, int K, int nseg) {
+  return nseg >= 1 && nseg <= 8 && N <= 1024 && win_shape_ok(lda, ldc, M, N, K, 1, nullptr, 0, 4096);
+}
+
+extern "C" int myolo_gemm_segs_win(const float* A, long long lda, const float* Bt, float* C, long long ldc, long long M, int N,
+                                   int K, int nseg, const int* seg_off_host, float* mean, float* var, double* ws,
+                                   myolo_stream stream) {
+  MYOLO_CHECK_ARG(myolo_gemm_segs_win_supported(lda, ldc, M, N, K, nseg) && seg_off_host);
+  MYOLO_CHECK_ARG((mean == nullptr) == (var == nullptr) && (!mean || ws));
+  MaskTail mt{};
+  int rc = launch_win(A, lda, Bt, C, ldc, M, N, K, 1, nullptr, nullptr, nullptr, nullptr, MYOLO_ACT_NONE, 0, 0, 0, mt, stream,
+                      BnBwd{}, HalfIO{}, nseg, seg_off_host, mean ? ws + 16 : nullptr);
+  if (rc || !mean) return rc;
+  stats_finalize_kernel<<<(N + 127) / 128, 128, 0, as_stream(stream)>>>(ws + 16, nullptr, mean, var, N, 1.0 / (double)M);
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
 }
 
 extern "C" int myolo_deconv_mask_fwd_supported(int Cmid, int NC) { return Cmid == 256 && NC >= 1 && NC <= 128; }
@@ -1108,19 +1173,6 @@ extern "C" int myolo_gemm_taps_h(const void* A, long long lda, const void* Bt, f
                     shifts_host, bias, scale, shift_c, act, pf_w1, pf_blk, 0, mt, stream, BnBwd{}, hio);
 }
 
-namespace myolo {
-__global__ void stats_finalize_kernel(double* __restrict__ sums, const float* __restrict__ pivot, float* __restrict__ mean,
-                                      float* __restrict__ var, int C, double inv_count) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const double m = sums[c] * inv_count;                      // mean of (x - pivot)
-  const double vv = sums[C + c] * inv_count - m * m;
-  mean[c] = (float)(m + (pivot ? (double)pivot[c] : 0.0));
-  var[c] = (float)(vv > 0.0 ? vv : 0.0);
-  sums[c] = 0.0;
-  sums[C + c] = 0.0;
-}
-}  // namespace myolo
 
 // myolo_gemm_taps_h with an fp32 result and the batch statistics of that result (valid rows only: n_valid of them) taken in
 // the epilogue: mean / biased variance per output channel.  ws: the BN workspace (zero before, zero after).

@@ -146,7 +146,8 @@ class Engine:
         # the depthwise kernel's epilogue, 2 = BN + ReLU6 after conv1 / a pointwise conv applied by the next depthwise
         # kernel (forward and filter gradient) while it loads, 4 = statistics of a pointwise output in the GEMM epilogue,
         # 8 = statistics of myolo_mask_conv1's output (myolo_mask_bn1) in the conv kernel's epilogue (h16 mode)
-        self._fuse_bn = int(os.environ.get("MYOLO_FUSE_BN", "13"))      # measured best: profiles/r02_fuse_bn_ab.txt
+        self._fuse_bn = int(os.environ.get("MYOLO_FUSE_BN", "13"))
+        self._pw_win = os.environ.get("MYOLO_PW_WIN", "0") != "0"      # pointwise forward on the persistent window kernel (A/B)      # measured best: profiles/r02_fuse_bn_ab.txt
         self._deferred = {}
         self._plan = None
         self.t = 0                     # Adam iteration
@@ -492,13 +493,18 @@ class Engine:
             C.record_py(self._ke_end)
 
     def _gemm_fwd_stats(self, a_rows, lo_off, name, out_rows, M, N, K, b):
-        """Pointwise forward GEMM on the one-tile tcgen05 kernel with the batch statistics of its result (BN layer `b`)
-        reduced in the epilogue; 3xTF32 operand triple as in _gemm_fwd."""
-        sh = [0, lo_off, 0] if self._is_x3(name) else [0]
+        """Pointwise forward GEMM with the batch statistics of its result (BN layer `b`) reduced in the epilogue.  3xTF32
+        layers with M >= 4096 and N % 128 == 0 run on the persistent window kernel as three k-segments (TMA-store epilogue,
+        CTA pairs); the rest on the one-tile kernel with the operand triple as taps, as in _gemm_fwd."""
+        x3 = self._is_x3(name)
+        sh = [0, lo_off, 0] if x3 else [0]
         key = (name, tuple(sh))
         arr = self._shift_cache.get(key)
         if arr is None:
             arr = self._shift_cache[key] = C.int_array(sh)
+        if x3 and self._pw_win and C.lib().myolo_gemm_segs_win_supported(K, N, M, N, K, 3):
+            C.call("myolo_gemm_segs_win", a_rows, K, self.wt[name], out_rows, N, M, N, K, 3, arr, b.mean, b.var, self.ws, self._st())
+            return
         C.call("myolo_gemm_taps_tc_stats", a_rows, K, self.wt[name], out_rows, N, M, N, K, len(sh), arr, 0, 0, b.mean, b.var,
                self.ws, M, self._st())
 

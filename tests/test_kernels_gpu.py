@@ -131,6 +131,39 @@ def test_gemm_epilogue_statistics(C, M, K, N, x3):
     close(ref, (A.double() @ W.double()).float(), 2e-3 if not x3 else 3e-5, "gemm")
 
 
+@pytest.mark.parametrize("M,K,N,stats", [(4096 + 37, 64, 128, 1), (6272, 512, 512, 1), (25088, 128, 256, 1), (8200, 32, 1024, 0)])
+def test_gemm_k_segments_on_the_window_kernel(C, M, K, N, stats):
+    """myolo_gemm_segs_win: the 3xTF32 pointwise GEMM as three k-segments of the persistent window kernel (hi / lo operand
+    planes lo_off rows apart in one matrix), with the batch statistics of the result in the epilogue, against the
+    one-tile kernel on the same operands."""
+    torch.manual_seed(42)
+    A = torch.randn(M, K) * 1.5 + 0.2
+    W = torch.randn(K, N) / K ** 0.5
+    Wd = cuda(W)
+    hi = A.cuda().clone()
+    lo = torch.empty_like(hi)
+    C.call("myolo_split_tf32", C.view(hi, 1, 1, M, K), C.view(hi, 1, 1, M, K), C.view(lo, 1, 1, M, K), stream())
+    Ad = torch.cat([hi, lo], 0).contiguous()
+    Wt = torch.empty(3, N, K, device="cuda")
+    C.call("myolo_prep_weights", Wd, Wt, 1, K, N, 1, 2, stream())
+    sh = C.int_array([0, M, 0])
+    ref = torch.empty(M, N, device="cuda")
+    C.call("myolo_gemm_taps_tc", Ad, K, Wt, ref, N, M, N, K, 3, sh, None, None, None, 0, 0, 0, 0, stream())
+    assert C.lib().myolo_gemm_segs_win_supported(K, N, M, N, K, 3) == 1
+    out = torch.full((M, N), 7.0, device="cuda")
+    mean, var = torch.empty(N, device="cuda"), torch.empty(N, device="cuda")
+    ws = torch.zeros(8192, dtype=torch.float64, device="cuda")
+    for rep in range(2):
+        C.call("myolo_gemm_segs_win", Ad, K, Wt, out, N, M, N, K, 3, sh, mean if stats else None, var if stats else None,
+               ws if stats else None, stream())
+        close(out, ref, 2e-6, "k-segment GEMM vs tap GEMM (same products, different accumulation order)")
+        if stats:
+            close(mean, ref.double().mean(0).float(), 2e-5, "epilogue mean")
+            close(var, ref.double().var(0, unbiased=False).float(), 2e-5, "epilogue variance")
+            assert ws.abs().max().item() == 0
+    close(out, (A.double() @ W.double()).float(), 3e-5, "3xTF32 product")
+
+
 # ----------------------------------------------------------------------------- K1 stem conv
 def test_conv1(C):
     torch.manual_seed(1)
