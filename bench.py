@@ -345,8 +345,10 @@ def time_precision(args, precision, cfg, host_batches, world, rank, local, with_
     res["n_roi"] = eng.n_roi
     res["cfg"] = c
     res["sparse_stats"] = dict(eng.sparse_stats)
-    del model, eng, dev_batches
-    torch.cuda.empty_cache()
+    del model, eng, dev_batches, out
+    import gc
+    gc.collect()                      # MaskYOLO <-> keras_model handle is a reference cycle: without this the engine's
+    torch.cuda.empty_cache()          # buffers (80 GB in tf32x3 at config 5) outlive the function
     return res
 
 
@@ -386,7 +388,9 @@ def parity_leg(args, cfg, batch_np, nimg, precisions, want_cpu):
             m = Hh.step_parity(dev, oout, args.size // 8)
             parity[prec] = {k: v for k, v in m.items() if not k.startswith("_")}
             parity[prec].update(loss=vals[0], oracle_loss=oout["loss"].item())
-            del model
+            del model, dev
+            import gc
+            gc.collect()
             torch.cuda.empty_cache()
         except Exception as e:                      # never lose the throughput line to the side check
             parity[prec] = {"error": repr(e)[:200]}
