@@ -368,13 +368,15 @@ int myolo_yolo_loss(const float* y_true, const float* y_pred, const float* true_
                     float* loss_out, float* dy_pred, double* ws, myolo_stream stream);
 
 /* ---- inference post-processing, myolo/model.py:1290-1304 + 1330-1391 (myolo_utils.py:88-113 NMB, 883-912 unmold_mask) ----
- * per image: the top_k detections by confidence that reach cs_threshold, NMB suppression exactly as the reference
- * does it (a candidate is dropped when any EARLIER candidate of the SAME class -- dropped or not -- has IoU >=
- * nms_threshold with it), then each survivor's class mask resized (bilinear, pixel
- * centres aligned) to its pixel box, thresholded at 0.5 and pasted into an S x S byte image.
+ * per image: detections without area are dropped first (decode_masks, model.py:1367-1375), then the top_k detections by
+ * confidence that reach cs_threshold (ties: the higher index first, as np.argsort(scores)[::-1] orders them), NMB
+ * suppression exactly as the reference does it (a candidate is dropped when any EARLIER candidate of the SAME class --
+ * dropped or not -- has IoU >= nms_threshold with it), then each survivor's class mask pasted by unmold_mask's rule: the
+ * box corners truncated with int(), x1/y1 clamped to [0,S], x2/y2 to [1,S], the mask resized (bilinear, pixel centres
+ * aligned) into that CLIPPED box, thresholded at 0.5 and written into an S x S byte image.
  * detections [B,R,6] = DetectionsLayer output; masks [B,R,MH,MW,NC] (nullable together with out_masks).
- * out_index [B,top_k] (detection index or -1), out_boxes [B,top_k,4] int32 pixels (x1,y1,x2,y2) clipped to
- * [0,S], out_class / out_score [B,top_k], out_count [B], out_masks [B,top_k,S,S] bytes.  top_k <= 32. */
+ * out_index [B,top_k] (detection index or -1), out_boxes [B,top_k,4] int32 pixels (x1,y1,x2,y2) = the box the mask was
+ * pasted into, out_class / out_score [B,top_k], out_count [B], out_masks [B,top_k,S,S] bytes.  top_k <= 32. */
 int myolo_detect_postprocess(const float* detections, const float* masks, int B, int R, int NC, int S, int MH, int MW,
                              int top_k, float cs_threshold, float nms_threshold, int* out_index, int* out_boxes,
                              int* out_class, float* out_score, int* out_count, unsigned char* out_masks,
