@@ -268,6 +268,11 @@ int myolo_gemm_taps_h_supported(long long lda, long long M, int N, int K, int nt
 int myolo_gemm_taps_h_stats(const void* A, long long lda, const void* Bt, float* C, long long ldc, long long M, int N,
                             int K, int ntaps, const int* shifts_host, const float* bias, int pf_w1, int pf_blk,
                             const float* pivot, float* mean, float* var, double* ws, long long n_valid, myolo_stream stream);
+/* The same with the result stored as IEEE half (Ch, pitch ldch) and the statistics taken from the half-rounded values,
+ * i.e. of exactly the tensor the BatchNormalization that follows reads (default h16 path of myolo_mask_bn1). */
+int myolo_gemm_taps_hh_stats(const void* A, long long lda, const void* Bt, void* Ch, long long ldch, long long M, int N,
+                             int K, int ntaps, const int* shifts_host, const float* bias, int pf_w1, int pf_blk,
+                             const float* pivot, float* mean, float* var, double* ws, long long n_valid, myolo_stream stream);
 int myolo_deconv_mask_fwd_h(const void* a4, const void* kd, const float* bd, const float* w1, const float* b1,
                             float* masks, const int* target_ids, float* y4, int n_roi, int H, int W, int Cmid, int NC,
                             myolo_stream stream);
@@ -281,6 +286,25 @@ int myolo_gemm_taps_bnbwd_h(const void* A, long long lda, const void* Bt, float*
                             const float* grad_unscale, myolo_stream stream);
 int myolo_bn_epi_finalize_s(double* sums, const float* gamma, const float* var, float eps, float* dgamma,
                             float* dbeta, float* dbias, int C, const float* unscale, myolo_stream stream);
+/* Backward of a BATCH-statistics BatchNormalization + activation in two launches instead of three passes
+ * (myolo_mask_bn1 in the learning phase, myolo/model.py:688-690; keras BatchNormalization training=True):
+ * 1. myolo_gemm_taps_bnbwd_sums_h = myolo_gemm_taps_bnbwd_h on the data-gradient GEMM that PRODUCES d(a): its epilogue
+ *    stores g1 = gamma * rsqrt(var + eps) * d(a) * act'(a) as half (loss scale kept) and leaves sum(g), sum(g * xhat) in ws;
+ *    var is the BATCH variance of the forward pass.  Nothing is finalised: ws is NOT zero on return.
+ * 2. myolo_bn_bwd_batch_fix_hh: dgamma / dbeta from those sums (times *grad_unscale), ws zeroed again, and in place over
+ *    the view's pixels  g_half <- g_half - gamma*rs*(S0/n + xhat*S1/n),  xhat = (z_half - mean) * rs,  n = pixels of the
+ *    view (z_half = the half pre-BN tensor of the forward pass).  Between the two calls g_half may be rearranged (the
+ *    sparse backward scatters a compact result into a zeroed full tensor); rows that stayed zero get the mean terms only. */
+int myolo_gemm_taps_bnbwd_sums_h(const void* A, long long lda, const void* Bt, void* Ch, long long ldc, long long M,
+                                 int N, int K, int ntaps, const int* shifts_host, int pf_w1, int pf_blk,
+                                 const void* a_out, const float* gamma, const float* beta, const float* var, float eps,
+                                 int act, double* ws, myolo_stream stream);
+int myolo_bn_bwd_batch_fix_hh(const myolo_view* z_half, const myolo_view* g_half, const float* mean, const float* var,
+                              const float* gamma, float eps, float* dgamma, float* dbeta, double* ws,
+                              const float* grad_unscale, myolo_stream stream);
+/* myolo_bn_apply from a half pre-BN tensor to a half result. */
+int myolo_bn_apply_hh(const myolo_view* x_half, const myolo_view* y_half, const float* mean, const float* var,
+                      const float* gamma, const float* beta, float eps, int act, myolo_stream stream);
 /* myolo_roialign_fwd with the pooled values stored as half (out_half) and, when out != NULL, also as fp32. */
 int myolo_roialign_fwd_h(const myolo_view* feat, const float* boxes, int n_roi, int rois_per_img, int pool,
                          const myolo_view* out, const myolo_view* out_half, myolo_stream stream);

@@ -257,6 +257,7 @@ __device__ __forceinline__ float half_bits_to_float(uint32_t h) {
 
 // BN + activation with the result stored as IEEE half (yh, operand of a kind::f16 GEMM) and, when y.p is not
 // null, as fp32 holding the SAME half-rounded values (what the backward pass reads).
+template <bool XH>
 __global__ void __launch_bounds__(256)
 bn_apply_h_kernel(V x, V y, V yh, const float* __restrict__ mean, const float* __restrict__ var,
                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int act, int same_geo) {
@@ -271,7 +272,7 @@ bn_apply_h_kernel(V x, V y, V yh, const float* __restrict__ mean, const float* _
     const int q = (int)((uint32_t)i - pp * (uint32_t)C4) * 4;
     const long long p = pp;
     const size_t xo = pix_off(x, p);
-    const float4 v = *reinterpret_cast<const float4*>(x.p + xo + q);
+    const float4 v = XH ? load_half4(x.p, xo + q) : *reinterpret_cast<const float4*>(x.p + xo + q);
     if (!fixed_q) co = bn_quad(mean, var, gamma, beta, eps, q);
     float4 o;
     o.x = apply_act(fmaf((v.x - co.mu.x) * co.rs.x, co.ga.x, co.be.x), act & 0xff);
@@ -353,6 +354,54 @@ bn_bwd_dx_kernel(V x, V dy, V dx, const float* __restrict__ mean, const float* _
           make_uint2(pack_half2_sat(o[0] * os, o[1] * os), pack_half2_sat(o[2] * os, o[3] * os));
     else
       *reinterpret_cast<float4*>(dx.p + (same_geo ? xo : pix_off(dx, p)) + q) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// Second half of the backward of a BATCH-statistics BN whose first half ran in a GEMM epilogue (myolo_gemm_taps_bnbwd_sums_h):
+// the epilogue left g1 = gamma*rs * g (g = dy * act', half, loss-scaled) and the column sums S0 = sum g, S1 = sum g*xhat.
+// dx = gamma*rs * (g - S0/n - xhat * S1/n) = g1 - A - B * (z - mean),  A = gamma*rs*S0/n,  B = gamma*rs^2*S1/n.
+__global__ void bn_batch_coef_kernel(double* __restrict__ sums, const float* __restrict__ gamma, const float* __restrict__ var,
+                                     float eps, double inv_count, const float* __restrict__ unscale, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta, float* __restrict__ coef, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double S0 = sums[c], S1 = sums[C + c];
+  const double us = unscale ? (double)__ldg(unscale) : 1.0;
+  dbeta[c] = (float)(S0 * us);
+  dgamma[c] = (float)(S1 * us);
+  const double r = 1.0 / sqrt((double)var[c] + (double)eps), gr = (double)gamma[c] * r;
+  coef[c] = (float)(gr * S0 * inv_count);
+  coef[C + c] = (float)(gr * r * S1 * inv_count);
+  sums[c] = 0.0;
+  sums[C + c] = 0.0;
+}
+
+__global__ void __launch_bounds__(256)
+bn_batch_fix_hh_kernel(V z, V g, const float* __restrict__ mean, const float* __restrict__ coef, int same_geo) {
+  const int C = z.c, C4 = C >> 2;
+  const FastDiv x_fc4 = z.fc4;
+  const long long total = (long long)z.n * z.h * z.w * C4;
+  const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+  const bool fixed_q = (stride % C4) == 0;
+  float4 mu, ka, kb;
+  auto load_q = [&](int q) {
+    mu = __ldg(reinterpret_cast<const float4*>(mean + q));
+    ka = __ldg(reinterpret_cast<const float4*>(coef + q));
+    kb = __ldg(reinterpret_cast<const float4*>(coef + C + q));
+  };
+  load_q((int)(i0 % C4) * 4);
+  for (long long i = i0; i < total; i += stride) {
+    const uint32_t pp = fd_div((uint32_t)i, x_fc4);
+    const int q = (int)((uint32_t)i - pp * (uint32_t)C4) * 4;
+    const long long p = pp;
+    const size_t zo = pix_off(z, p);
+    const size_t go = same_geo ? zo : pix_off(g, p);
+    const float4 v = load_half4(z.p, zo + q);
+    const float4 gv = load_half4(g.p, go + q);
+    if (!fixed_q) load_q(q);
+    const float o0 = gv.x - ka.x - kb.x * (v.x - mu.x), o1 = gv.y - ka.y - kb.y * (v.y - mu.y);
+    const float o2 = gv.z - ka.z - kb.z * (v.z - mu.z), o3 = gv.w - ka.w - kb.w * (v.w - mu.w);
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(g.p) + go + q) = make_uint2(pack_half2_sat(o0, o1), pack_half2_sat(o2, o3));
   }
 }
 
@@ -563,7 +612,41 @@ extern "C" int myolo_bn_apply_h(const myolo_view* x, const myolo_view* y, const 
   V vy = y ? to_v(y) : to_v(x);
   if (!y) vy.p = nullptr;
   const int same_geo = x->sn == y_half->sn && x->sh == y_half->sh && (!y || (y->sn == x->sn && y->sh == x->sh));
-  bn_apply_h_kernel<<<ew_blocks(total), 256, 0, as_stream(stream)>>>(to_v(x), vy, to_v(y_half), mean, var, gamma, beta, eps, act, same_geo);
+  bn_apply_h_kernel<false><<<ew_blocks(total), 256, 0, as_stream(stream)>>>(to_v(x), vy, to_v(y_half), mean, var, gamma, beta, eps, act, same_geo);
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
+}
+
+// BN + activation from an IEEE-half pre-BN tensor to an IEEE-half result (myolo_mask_bn1 in h16 mode)
+extern "C" int myolo_bn_apply_hh(const myolo_view* x_half, const myolo_view* y_half, const float* mean, const float* var,
+                                 const float* gamma, const float* beta, float eps, int act, myolo_stream stream) {
+  MYOLO_CHECK_ARG(view_ok(x_half) && view_ok(y_half) && same_shape(x_half, y_half));
+  MYOLO_CHECK_ARG(mean && var && gamma && beta && ((uintptr_t)y_half->p & 7) == 0 && ((uintptr_t)x_half->p & 7) == 0);
+  const long long total = (long long)x_half->n * x_half->h * x_half->w * (x_half->c / 4);
+  V vy = to_v(x_half);
+  vy.p = nullptr;
+  const int same_geo = x_half->sn == y_half->sn && x_half->sh == y_half->sh;
+  bn_apply_h_kernel<true><<<ew_blocks(total), 256, 0, as_stream(stream)>>>(to_v(x_half), vy, to_v(y_half), mean, var, gamma, beta, eps, act, same_geo);
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
+}
+
+// Finishes the backward of a batch-statistics BN + activation whose masked, gamma*rs-scaled gradient and column sums were
+// produced by myolo_gemm_taps_bnbwd_sums_h on the SAME workspace: dgamma / dbeta (un-scaled by *grad_unscale), the sums
+// zeroed again, and g_half <- g_half - A - B * (z_half - mean) in place over the view's pixels.
+extern "C" int myolo_bn_bwd_batch_fix_hh(const myolo_view* z_half, const myolo_view* g_half, const float* mean, const float* var,
+                                         const float* gamma, float eps, float* dgamma, float* dbeta, double* ws,
+                                         const float* grad_unscale, myolo_stream stream) {
+  MYOLO_CHECK_ARG(view_ok(z_half) && view_ok(g_half) && same_shape(z_half, g_half));
+  MYOLO_CHECK_ARG(mean && var && gamma && dgamma && dbeta && ws && z_half->c <= kWsMaxC);
+  MYOLO_CHECK_ARG(((uintptr_t)z_half->p & 7) == 0 && ((uintptr_t)g_half->p & 7) == 0);
+  cudaStream_t st = as_stream(stream);
+  const int C = z_half->c;
+  const long long total = (long long)z_half->n * z_half->h * z_half->w;
+  float* coef = reinterpret_cast<float*>(ws + kWsCoef);
+  bn_batch_coef_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws + kWsSums, gamma, var, eps, 1.0 / (double)total, grad_unscale, dgamma, dbeta, coef, C);
+  const int same_geo = z_half->sn == g_half->sn && z_half->sh == g_half->sh;
+  bn_batch_fix_hh_kernel<<<ew_blocks(total * (C / 4)), 256, 0, st>>>(to_v(z_half), to_v(g_half), mean, coef, same_geo);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }

@@ -726,7 +726,8 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               atomicAdd(colacc + n0 + lane, s0);
               atomicAdd(colacc + 256 + n0 + lane, s1);
             }
-          } else
+          } else {
+          uint32_t hp0 = 0u, hp1 = 0u;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float4 sc, sf;
@@ -741,25 +742,26 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               if (rnd) o[e] = round_tf32(o[e]);
               if (!valid) o[e] = 0.f;   // padded-flat pad rows stay zero
             }
-            if (ep.st_sums && !st_h) {   // batch statistics of the stored result (pad / out-of-range rows are zero)
-              v[4 * j] = o[0]; v[4 * j + 1] = o[1]; v[4 * j + 2] = o[2]; v[4 * j + 3] = o[3];
-            }
-            if (st_h) {   // the half copy; v[] keeps the packed words until the 16-byte chunk is complete
+            if (st_h) {   // the half copy; hp0 / hp1 keep the packed words until the 16-byte chunk is complete
               const uint32_t p0 = pack_h2(o[0], o[1]), p1 = pack_h2(o[2], o[3]);
               o[0] = h2f((uint16_t)(p0 & 0xffffu)); o[1] = h2f((uint16_t)(p0 >> 16));
               o[2] = h2f((uint16_t)(p1 & 0xffffu)); o[3] = h2f((uint16_t)(p1 >> 16));
-              v[4 * j] = __uint_as_float(p0);
-              v[4 * j + 1] = __uint_as_float(p1);
               if (j & 1) {
                 const uint32_t haddr = sbufh + (uint32_t)lane * 64u + (uint32_t)((((uint32_t)j >> 1) ^ (((uint32_t)lane >> 1) & 3u)) << 4);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(haddr), "r"(__float_as_uint(v[4 * j - 4])),
-                             "r"(__float_as_uint(v[4 * j - 3])), "r"(p0), "r"(p1));
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(haddr), "r"(hp0), "r"(hp1), "r"(p0), "r"(p1));
+              } else {
+                hp0 = p0;
+                hp1 = p1;
               }
+            }
+            if (ep.st_sums) {   // batch statistics of the STORED result (half-rounded when the output is half; pad rows are zero)
+              v[4 * j] = o[0]; v[4 * j + 1] = o[1]; v[4 * j + 2] = o[2]; v[4 * j + 3] = o[3];
             }
             if (st_f32) {
               const uint32_t addr = sbuf + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
               asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]));
             }
+          }
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
@@ -781,7 +783,7 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             if (s0 != 0.f) atomicAdd(ep.st_sums + n0 + lane, (double)s0);
             if (s1 != 0.f) atomicAdd(ep.st_sums + N + n0 + lane, (double)s1);
           }
-          if (EL == 2 && ep.st_sums && !st_h && !ep.bn_a) {   // column sums of the chunk while its TMA store is in flight
+          if (EL == 2 && ep.st_sums && !ep.bn_a) {   // column sums of the chunk while its TMA store is in flight
             // shifted by a per-column pivot (the layer's moving mean): E[x^2] - E[x]^2 would lose mean^2 / variance digits
             const float pv = ep.st_pivot ? __ldg(ep.st_pivot + n0 + lane) : 0.f;
             float sq[32];
@@ -883,7 +885,7 @@ struct HalfIO {
   long long ldch;
   int no_f32;
   const float* acc_scale;
-  double* st_sums;   // fp32-output launches only: per-column sum / sum of squares of the stored result ([2][N] fp64, += )
+  double* st_sums;   // per-column sum / sum of squares of the stored result ([2][N] fp64, += )
   const float* st_pivot;   // per-column value subtracted before the sums are taken (nullable)
 };
 
@@ -989,7 +991,7 @@ static int launch_win(const float* A, long long lda, const float* Bt, float* C, 
   Epi ep{bias, scale, shift_c, act, pf_w1, pf_blk, accumulate, bnb.a, bnb.gamma, bnb.beta, bnb.var, bnb.ws, bnb.eps,
          hio.on ? (const void*)bnb.a : nullptr, hio.on ? hio.no_f32 : 0, (hio.on && hio.Ch) ? 1 : 0, hio.acc_scale};
   if (hio.on && hio.st_sums) {
-    MYOLO_CHECK_ARG(N == 256 && !hio.no_f32 && !hio.Ch && !bnb.a && !mt.masks);
+    MYOLO_CHECK_ARG(N == 256 && !bnb.a && !mt.masks);
     ep.st_sums = hio.st_sums;
     ep.st_pivot = hio.st_pivot;
   }
@@ -1192,6 +1194,24 @@ extern "C" int myolo_gemm_taps_h_stats(const void* A, long long lda, const void*
   return MYOLO_OK;
 }
 
+// the same with the result stored as IEEE half and the statistics taken from the half-rounded values (so that the BN that
+// follows normalises exactly the tensor it reads)
+extern "C" int myolo_gemm_taps_hh_stats(const void* A, long long lda, const void* Bt, void* Ch, long long ldch, long long M, int N,
+                                        int K, int ntaps, const int* shifts_host, const float* bias, int pf_w1, int pf_blk,
+                                        const float* pivot, float* mean, float* var, double* ws, long long n_valid,
+                                        myolo_stream stream) {
+  MYOLO_CHECK_ARG(Ch && mean && var && ws && n_valid > 0 && N == 256 && pivot != mean);
+  MYOLO_CHECK_ARG(myolo_gemm_taps_h_supported(lda, M, N, K, ntaps, shifts_host));
+  MaskTail mt{};
+  HalfIO hio{1, Ch, ldch, 1, nullptr, ws + 16, pivot};
+  int rc = launch_win(reinterpret_cast<const float*>(A), lda, reinterpret_cast<const float*>(Bt), nullptr, N, M, N, K, ntaps,
+                      shifts_host, bias, nullptr, nullptr, MYOLO_ACT_NONE, pf_w1, pf_blk, 0, mt, stream, BnBwd{}, hio);
+  if (rc) return rc;
+  stats_finalize_kernel<<<(N + 127) / 128, 128, 0, as_stream(stream)>>>(ws + 16, pivot, mean, var, N, 1.0 / (double)n_valid);
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
+}
+
 extern "C" int myolo_deconv_mask_fwd_h(const void* a4, const void* kd, const float* bd, const float* w1, const float* b1,
                                        float* masks, const int* target_ids, float* y4, int n_roi, int H, int W, int Cmid,
                                        int NC, myolo_stream stream) {
@@ -1222,4 +1242,20 @@ extern "C" int myolo_gemm_taps_bnbwd_h(const void* A, long long lda, const void*
                       shifts_host, nullptr, nullptr, nullptr, act, pf_w1, pf_blk, 0, mt, stream, bnb, hio);
   if (rc) return rc;
   return myolo_bn_epi_finalize_s(ws + 16, gamma, var, eps, dgamma, dbeta, dbias, N, grad_unscale, stream);
+}
+
+// myolo_gemm_taps_bnbwd_h without the finalisation: the column sums (sum g, sum g*xhat in the loss-scaled domain) stay in the
+// BN workspace for myolo_bn_bwd_batch_fix_hh -- the backward of a BATCH-statistics BN whose first pass rides in this GEMM's
+// epilogue.  var is the batch variance of the forward pass.
+extern "C" int myolo_gemm_taps_bnbwd_sums_h(const void* A, long long lda, const void* Bt, void* Ch, long long ldc, long long M,
+                                            int N, int K, int ntaps, const int* shifts_host, int pf_w1, int pf_blk,
+                                            const void* a_out, const float* gamma, const float* beta, const float* var, float eps,
+                                            int act, double* ws, myolo_stream stream) {
+  MYOLO_CHECK_ARG(a_out && gamma && beta && var && ws && Ch);
+  MYOLO_CHECK_ARG(N == 256 && ldc == N && myolo_gemm_taps_h_supported(lda, M, N, K, ntaps, shifts_host));
+  MaskTail mt{};
+  BnBwd bnb{reinterpret_cast<const float*>(a_out), gamma, beta, var, ws + 16, eps};
+  HalfIO hio{1, Ch, ldc, 1, nullptr};
+  return launch_win(reinterpret_cast<const float*>(A), lda, reinterpret_cast<const float*>(Bt), nullptr, ldc, M, N, K, ntaps,
+                    shifts_host, nullptr, nullptr, nullptr, act, pf_w1, pf_blk, 0, mt, stream, bnb, hio);
 }

@@ -145,8 +145,11 @@ class Engine:
         # BatchNormalization fusions of the backbone (bit mask; A/B switch): 1 = batch statistics of a depthwise output in
         # the depthwise kernel's epilogue, 2 = BN + ReLU6 after conv1 / a pointwise conv applied by the next depthwise
         # kernel (forward and filter gradient) while it loads, 4 = statistics of a pointwise output in the GEMM epilogue,
-        # 8 = statistics of myolo_mask_conv1's output (myolo_mask_bn1) in the conv kernel's epilogue (h16 mode)
-        self._fuse_bn = int(os.environ.get("MYOLO_FUSE_BN", "13"))
+        # 8 = statistics of myolo_mask_conv1's output (myolo_mask_bn1) in the conv kernel's epilogue (h16 mode),
+        # 16 = myolo_mask_bn1 on a HALF pre-BN tensor (statistics of the half-rounded values, taken in the epilogue) and its
+        # backward's reduction pass in the epilogue of myolo_mask_conv2's data-gradient GEMM (h16 mode; implies 8)
+        self._fuse_bn = int(os.environ.get("MYOLO_FUSE_BN", "29"))
+        self._bn1_half = bool(self._fuse_bn & 16) and precision == "h16"
         self._pw_win = os.environ.get("MYOLO_PW_WIN", "0") != "0"      # pointwise forward on the persistent window kernel (A/B)      # measured best: profiles/r02_fuse_bn_ab.txt
         self._deferred = {}
         self._plan = None
@@ -403,7 +406,9 @@ class Engine:
             self.feat = PF(B, F_, F_, MASK_C, device=dev)
             # pre-BN conv outputs: only conv1 (batch-statistics BN) needs one; conv2..4 fold their
             # fixed-statistics BN + ReLU into the GEMM epilogue (unless the 3xTF32 mask mode splits them)
-            self.my = [None] + [PF(n, P_, P_, MASK_C, device=dev) if (i == 1 or self.x3m) else None for i in range(1, 5)]
+            self.my = [None] + [PF(n, P_, P_, MASK_C, device=dev) if ((i == 1 and not self._bn1_half) or self.x3m) else None
+                                for i in range(1, 5)]
+            self.z1h = PF(n, P_, P_, MASK_C, device=dev, dtype=torch.float16) if self._bn1_half else None
             self.bn_scale = torch.zeros(4, MASK_C, device=dev)
             self.bn_shift = torch.zeros(4, MASK_C, device=dev)
             if self.h16:     # the conv operands x0, a1..a4 exist as IEEE half only
@@ -713,7 +718,11 @@ class Engine:
             if training and i == 1:
                 # batch-statistics BN: the pre-BN tensor is kept in fp32 (statistics, backward); its batch statistics are
                 # reduced in the conv's epilogue (bit 8 of MYOLO_FUSE_BN)
-                if self._fuse_bn & 8:
+                if self._bn1_half:
+                    b1 = self.bn["myolo_mask_bn1"]
+                    C.call("myolo_gemm_taps_hh_stats", a_in.rows, MASK_C, self.wth[name], self.z1h.rows, MASK_C, M, MASK_C,
+                           MASK_C, 9, sh3, self.p[f"myolo_mask_conv{i}/bias"], pfw, pfb, b1.mmean, b1.mean, b1.var, self.ws, npix, st)
+                elif self._fuse_bn & 8:
                     b1 = self.bn["myolo_mask_bn1"]
                     C.call("myolo_gemm_taps_h_stats", a_in.rows, MASK_C, self.wth[name], self.my[1].rows, MASK_C, M, MASK_C,
                            MASK_C, 9, sh3, self.p[f"myolo_mask_conv{i}/bias"], pfw, pfb, b1.mmean, b1.mean, b1.var, self.ws, npix, st)
@@ -731,11 +740,15 @@ class Engine:
             C.record_py(self._ke_end)
             if training and i == 1:
                 b = self.bn["myolo_mask_bn1"]
-                if not (self._fuse_bn & 8):
+                if not (self._fuse_bn & 8) and not self._bn1_half:
                     C.call("myolo_bn_stats", self.my[1].view(), b.mean, b.var, self.ws, st)
                 self._bn_touched.append((b, npix))
-                C.call("myolo_bn_apply_h", self.my[1].view(), None, self.mah[1].view(), b.mean, b.var, b.gamma,
-                       b.beta, BN_EPS, C.ACT_RELU, st)
+                if self._bn1_half:
+                    C.call("myolo_bn_apply_hh", self.z1h.view(), self.mah[1].view(), b.mean, b.var, b.gamma, b.beta, BN_EPS,
+                           C.ACT_RELU, st)
+                else:
+                    C.call("myolo_bn_apply_h", self.my[1].view(), None, self.mah[1].view(), b.mean, b.var, b.gamma,
+                           b.beta, BN_EPS, C.ACT_RELU, st)
         if C.lib().myolo_deconv_mask_fwd_supported(MASK_C, self.NC):
             ids = self.target_ids if self.mode == "training" else None
             C.call("myolo_deconv_mask_fwd_h", self.mah[4].rows, self.wth["myolo_mask_deconv/kernel"], self.p["myolo_mask_deconv/bias"],
@@ -992,8 +1005,12 @@ class Engine:
         else:
             g1 = self._dense_mask_middle(G, wgrad, M, pfw, pfb, sh3, shn, ugs, st)
         b = self.bn["myolo_mask_bn1"]
-        C.call("myolo_bn_bwd_hh", self.my[1].view(), g1.view(), g1.view(), b.mean, b.var, b.gamma, b.beta, BN_EPS,
-               C.ACT_RELU, 1, b.dgamma, b.dbeta, self.ws, ugs, st)
+        if self._bn1_half:      # the reduction pass ran in the epilogue of conv2's data-gradient GEMM (_conv2_dgrad)
+            C.call("myolo_bn_bwd_batch_fix_hh", self.z1h.view(), g1.view(), b.mean, b.var, b.gamma, BN_EPS, b.dgamma, b.dbeta,
+                   self.ws, ugs, st)
+        else:
+            C.call("myolo_bn_bwd_hh", self.my[1].view(), g1.view(), g1.view(), b.mean, b.var, b.gamma, b.beta, BN_EPS,
+                   C.ACT_RELU, 1, b.dgamma, b.dbeta, self.ws, ugs, st)
         name = "myolo_mask_conv1/kernel"
         wgrad(self.mah[0].rows, MASK_C, g1.rows, MASK_C, self.g[name], M, MASK_C, MASK_C, 9, sh3, 0, ugs, wst)
         C.call("myolo_gemm_taps_h", g1.rows, MASK_C, self.wth_d[name], self.mg[1].rows, MASK_C, None, 0, M, MASK_C, MASK_C, 9,
@@ -1024,9 +1041,19 @@ class Engine:
                 dgrad_bn(gi.rows, MASK_C, name, G[4 - i + 1].rows, MASK_C, 9, shn, i - 1)
         # d(a1) as scaled half
         g2, g1 = G[2], G[3]
-        C.call("myolo_gemm_taps_h", g2.rows, MASK_C, self.wth_d["myolo_mask_conv2/kernel"], None, 0, g1.rows, MASK_C, M,
-               MASK_C, MASK_C, 9, shn, None, None, None, C.ACT_NONE, pfw, pfb, None, st)
+        self._conv2_dgrad(g2.rows, g1.rows, self.mah[1].rows, M, pfw, pfb, shn, st)
         return g1
+
+    def _conv2_dgrad(self, g2_rows, g1_rows, a1_rows, M, pfw, pfb, shn, st):
+        """Data gradient of myolo_mask_conv2 = d(a1).  With the half bn1 path its epilogue already applies relu'(a1) and
+        gamma * rs and leaves bn1's two column sums in the BN workspace for myolo_bn_bwd_batch_fix_hh."""
+        if self._bn1_half:
+            b = self.bn["myolo_mask_bn1"]
+            C.call("myolo_gemm_taps_bnbwd_sums_h", g2_rows, MASK_C, self.wth_d["myolo_mask_conv2/kernel"], g1_rows, MASK_C, M,
+                   MASK_C, MASK_C, 9, shn, pfw, pfb, a1_rows, b.gamma, b.beta, b.var, BN_EPS, C.ACT_RELU, self.ws, st)
+        else:
+            C.call("myolo_gemm_taps_h", g2_rows, MASK_C, self.wth_d["myolo_mask_conv2/kernel"], None, 0, g1_rows, MASK_C, M,
+                   MASK_C, MASK_C, 9, shn, None, None, None, C.ACT_NONE, pfw, pfb, None, st)
 
     def _sparse_mask_middle(self):
         """Exact sparse form of _dense_mask_middle.  The mask loss touches the rois with a target class only
@@ -1091,8 +1118,7 @@ class Engine:
                 if i > 2:
                     dgrad_bn(ga.rows, MASK_C, name, gb.rows, MASK_C, 9, shn, i - 1)
                     ga, gb = gb, ga
-            C.call("myolo_gemm_taps_h", ga.rows, MASK_C, self.wth_d["myolo_mask_conv2/kernel"], None, 0, gb.rows, MASK_C, Mc,
-                   MASK_C, MASK_C, 9, shn, None, None, None, C.ACT_NONE, pfw, pfb, None, st)
+            self._conv2_dgrad(ga.rows, gb.rows, a[1].rows, Mc, pfw, pfb, shn, st)
             C.call("myolo_copy_tiles", gb.rows, g1.rows, self.sp_list, P, tile, 1, st)
 
     def _backward_mask(self):

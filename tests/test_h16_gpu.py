@@ -364,3 +364,100 @@ def test_bn_backward_half_in_half_out(C):
     close(dg, dg_r, 1e-5, "dgamma")
     close(db, db_r, 1e-5, "dbeta")
     assert ws[:2064].abs().max().item() == 0, "tickets and sums are left zero (the coefficient table behind them is scratch)"
+
+
+def test_bn1_half_path_forward(C):
+    """myolo_mask_conv1 -> myolo_mask_bn1 on a HALF pre-BN tensor: the conv stores half and takes the batch statistics of the
+    half-rounded values in its epilogue (myolo_gemm_taps_hh_stats), BN + ReLU reads half and writes half (myolo_bn_apply_hh)."""
+    from myolo.pf import PF, conv3x3_shifts
+    torch.manual_seed(51)
+    n, H, W, Ci, Co = 300, 14, 14, 256, 256
+    x = PF(n, H, W, Ci)
+    x.valid().copy_(hq(torch.randn(n, H, W, Ci, device="cuda")))
+    w = hq(torch.randn(9, Ci, Co, device="cuda") / (9 * Ci) ** 0.5)
+    wth = w.transpose(1, 2).contiguous().half()
+    bias = torch.randn(Co, device="cuda") * 0.5
+    sh = C.int_array(conv3x3_shifts(W))
+    pfw, pfb, M = W + 1, (H + 1) * (W + 1), x.M
+    xh = half_pf(x)
+    ref32 = PF(n, H, W, Co)
+    C.call("myolo_gemm_taps_h", xh.rows, Ci, wth, ref32.rows, Co, None, 0, M, Co, Ci, 9, sh, bias, None, None, C.ACT_NONE, pfw, pfb,
+           None, stream())
+    ws = torch.zeros(8192, dtype=torch.float64, device="cuda")
+    mean, var = torch.empty(Co, device="cuda"), torch.empty(Co, device="cuda")
+    zh = PF(n, H, W, Co, dtype=torch.float16)
+    for rep in range(2):
+        pivot = None if rep == 0 else bias + 0.1
+        C.call("myolo_gemm_taps_hh_stats", xh.rows, Ci, wth, zh.rows, Co, M, Co, Ci, 9, sh, bias, pfw, pfb, pivot, mean, var, ws,
+               n * H * W, stream())
+        assert torch.equal(zh.rows, ref32.rows.half()), "half result = round-to-nearest-even of the fp32 one"
+        flat = zh.valid().reshape(-1, Co).double()
+        close(mean, flat.mean(0).float(), 2e-5, "mean of the half-rounded result")
+        close(var, flat.var(0, unbiased=False).float(), 2e-5, "variance of the half-rounded result")
+        assert ws.abs().max().item() == 0
+    assert zh.storage[:Co].abs().max().item() == 0 and zh.rows.view(n, H + 1, W + 1, Co)[:, 0].abs().max().item() == 0
+    gamma, beta = torch.rand(Co, device="cuda") + 0.5, torch.randn(Co, device="cuda") * 0.1
+    z32 = PF(n, H, W, Co)
+    z32.rows.copy_(zh.rows)
+    y_ref, yh = PF(n, H, W, Co), PF(n, H, W, Co, dtype=torch.float16)
+    C.call("myolo_bn_apply", z32.view(), y_ref.view(), mean, var, gamma, beta, 1e-3, C.ACT_RELU, stream())
+    C.call("myolo_bn_apply_hh", zh.view(), yh.view(), mean, var, gamma, beta, 1e-3, C.ACT_RELU, stream())
+    assert torch.equal(yh.rows, y_ref.rows.half())
+
+
+@pytest.mark.parametrize("n", [40, 300])
+def test_bn1_half_path_backward(C, n):
+    """Backward of a batch-statistics BN + ReLU split over the epilogue of the GEMM that produces d(a)
+    (myolo_gemm_taps_bnbwd_sums_h: relu'(a), gamma * rs, the two column sums) and one in-place correction pass
+    (myolo_bn_bwd_batch_fix_hh), against the exact path: CUDA-core data-gradient GEMM, then myolo_bn_bwd on fp32."""
+    from myolo.pf import PF, conv3x3_shifts
+    torch.manual_seed(52)
+    H, W, Cc, S = 14, 14, 256, 64.0
+    z = PF(n, H, W, Cc)
+    z.valid().copy_(hq(torch.randn(n, H, W, Cc, device="cuda") * 1.3 + 0.2))
+    gamma, beta = torch.rand(Cc, device="cuda") + 0.5, torch.randn(Cc, device="cuda") * 0.1
+    mean, var = torch.empty(Cc, device="cuda"), torch.empty(Cc, device="cuda")
+    ws = torch.zeros(4112, dtype=torch.float64, device="cuda")
+    C.call("myolo_bn_stats", z.view(), mean, var, ws, stream())
+    zh = half_pf(z)
+    ah = PF(n, H, W, Cc, dtype=torch.float16)
+    C.call("myolo_bn_apply_hh", zh.view(), ah.view(), mean, var, gamma, beta, 1e-3, C.ACT_RELU, stream())
+    g_true = PF(n, H, W, Cc)
+    g_true.valid().copy_(hq(torch.randn(n, H, W, Cc, device="cuda")))
+    w = hq(torch.randn(9, Cc, Cc, device="cuda") / (9 * Cc) ** 0.5)
+    shn = C.int_array(conv3x3_shifts(W, negate=True))
+    pfw, pfb, M = W + 1, (H + 1) * (W + 1), z.M
+    # exact: d(a) on CUDA cores in fp32, then the three-pass BN backward on the fp32 pre-BN tensor
+    da = PF(n, H, W, Cc)
+    C.call("myolo_gemm_taps_ffma", g_true.rows, Cc, w, da.rows, Cc, M, Cc, Cc, 9, shn, None, None, None, 0, pfw, pfb, 0, stream())
+    ref = PF(n, H, W, Cc)
+    dg_r, db_r, dg, db = (torch.empty(Cc, device="cuda") for _ in range(4))
+    C.call("myolo_bn_bwd", z.view(), da.view(), ref.view(), mean, var, gamma, beta, 1e-3, C.ACT_RELU, 1, dg_r, db_r, ws, stream())
+    # fused: loss-scaled half gradient in, half d(pre-BN) out
+    g_scaled = PF(n, H, W, Cc, dtype=torch.float16)
+    g_scaled.rows.copy_(g_true.rows * S)
+    g1 = PF(n, H, W, Cc, dtype=torch.float16)
+    us = torch.tensor([1.0 / S], device="cuda")
+    for rep in range(2):
+        C.call("myolo_gemm_taps_bnbwd_sums_h", g_scaled.rows, Cc, w.half(), g1.rows, Cc, M, Cc, Cc, 9, shn, pfw, pfb, ah.rows,
+               gamma, beta, var, 1e-3, C.ACT_RELU, ws, stream())
+        assert ws[16:16 + 2 * Cc].abs().max().item() > 0, "the column sums wait in the workspace"
+        C.call("myolo_bn_bwd_batch_fix_hh", zh.view(), g1.view(), mean, var, gamma, 1e-3, dg, db, ws, us, stream())
+        torch.cuda.synchronize()
+        # two half roundings of values up to ~S * max|d(a)| * gamma * rs
+        close(g1.rows.float() / S, ref.rows, 1.5e-3, "d(pre-BN), half, scaled")
+        close(dg, dg_r, 2e-3, "dgamma (xhat recovered from the half activation)")
+        close(db, db_r, 1e-4, "dbeta")
+        assert ws[:2064].abs().max().item() == 0, "tickets and sums are left zero"
+        v = g1.rows.view(n, H + 1, W + 1, Cc)
+        assert v[:, 0].abs().max().item() == 0 and v[:, :, 0].abs().max().item() == 0, "pad pixels stay zero"
+    # rows that were zero before the correction pass (the sparse backward's other rois) receive the mean terms only
+    g1.rows.zero_()
+    ws[16:16 + Cc] = 3.0
+    ws[16 + Cc:16 + 2 * Cc] = -2.0
+    C.call("myolo_bn_bwd_batch_fix_hh", zh.view(), g1.view(), mean, var, gamma, 1e-3, dg, db, ws, None, stream())
+    rs = 1.0 / torch.sqrt(var + 1e-3)
+    npx = n * H * W
+    want = -(gamma * rs) * (3.0 / npx + (zh.valid().float() - mean) * rs * (-2.0 / npx))
+    close(g1.valid().float(), want, 2e-3, "mean terms on zero rows")
+    assert torch.equal(dg, torch.full_like(dg, -2.0)) and torch.equal(db, torch.full_like(db, 3.0))
