@@ -308,6 +308,10 @@ int myolo_bn_apply_hh(const myolo_view* x_half, const myolo_view* y_half, const 
 /* myolo_roialign_fwd with the pooled values stored as half (out_half) and, when out != NULL, also as fp32. */
 int myolo_roialign_fwd_h(const myolo_view* feat, const float* boxes, int n_roi, int rois_per_img, int pool,
                          const myolo_view* out, const myolo_view* out_half, myolo_stream stream);
+/* myolo_roialign_bwd (CropAndResizeGradImage) on a half, loss-scaled gradient: every value read is multiplied by
+ * *in_scale (device scalar, nullable = 1); dfeat stays fp32.  C = 128 or 256. */
+int myolo_roialign_bwd_h(const myolo_view* dout_half, const float* boxes, int n_roi, int rois_per_img, int pool,
+                         const myolo_view* dfeat, const float* in_scale, myolo_stream stream);
 /* myolo_bn_apply with the result stored as half (y_half) and, when y != NULL, as fp32 holding the same rounded values. */
 int myolo_bn_apply_h(const myolo_view* x, const myolo_view* y, const myolo_view* y_half, const float* mean,
                      const float* var, const float* gamma, const float* beta, float eps, int act, myolo_stream stream);

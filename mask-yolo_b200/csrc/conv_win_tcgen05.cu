@@ -171,14 +171,20 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   // same shared memory is split four windows / five weight stages.
   constexpr int kMaxAWin = NACC == 1 ? 4 : 2;
   const int nawin = mt.tc ? mt.nawin : ((ntaps == 1 && NACC == 1) ? 4 : 2);
-  const int nwb = mt.tc ? mt.nwb
-                        : ((ntaps == 1 && NACC == 1) ? (int)((2 * kWinBytes + kWBStages * kWBBytes - 4 * kWinBytes) / kWBBytes) : kWBStages);
-  __shared__ __align__(8) uint64_t bars[2 * kMaxAWin + kWBStages * 2 + 4 + 2];
+  // fused BN backward, half flavour: the activation tiles arrive by TMA into the shared memory of the LAST weight stage
+  // (8 epilogue warps x 2 KB).  Read with per-lane global loads (16 bytes per lane at a 512-byte pitch) they slowed the
+  // main loop from 0.91 to 1.05 ms per launch although the epilogue warps idle 40 % of the time.
+  const bool act_tma = EL == 2 && NACC == 1 && ep.bn_a != nullptr && ep.bn_tma != 0;
+  const int nwb = (mt.tc ? mt.nwb
+                         : ((ntaps == 1 && NACC == 1) ? (int)((2 * kWinBytes + kWBStages * kWBBytes - 4 * kWinBytes) / kWBBytes) : kWBStages)) -
+                  (act_tma ? 1 : 0);
+  __shared__ __align__(8) uint64_t bars[2 * kMaxAWin + kWBStages * 2 + 4 + 2 + 8];
   __shared__ uint32_t tmem_slot;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t awin0 = base, bst0 = base + (uint32_t)nawin * kWinBytes, stg0 = base + 2 * kWinBytes + kWBStages * kWBBytes;
   // tensor-core mask tail: [windows][weight stages][A2: 128 rows x 256 half, 4 swizzled k-blocks][B2: ncp/CG classes x 256 half][evec]
   const uint32_t a2_0 = bst0 + (uint32_t)nwb * kWBBytes;
+  const uint32_t astg0 = a2_0;                                // act_tma: [epilogue warp][32 rows][32 half], 64B swizzle
   const uint32_t b2_0 = a2_0 + 65536u;
   const uint32_t b2_rows = mt.tc ? (uint32_t)(mt.ncp / CG) : 0u;
   float* colacc = reinterpret_cast<float*>(smem_raw + (stg0 + kWStageOut - smem_u32(smem_raw)));          // [2][256]
@@ -197,6 +203,7 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   auto t_empty = [&](int i) { return bar0 + 8u * (2 * kMaxAWin + 2 * kWBStages + 2 + i); };
   const uint32_t a2_full = bar0 + 8u * (2 * kMaxAWin + 2 * kWBStages + 4);   // leader: every epilogue warp of the pair has written A2
   const uint32_t d2_full = bar0 + 8u * (2 * kMaxAWin + 2 * kWBStages + 5);   // both CTAs: the logits of the item are in TMEM
+  auto act_full = [&](int i) { return bar0 + 8u * (2 * kMaxAWin + 2 * kWBStages + 6 + i); };   // per epilogue warp: activation tile landed
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -217,6 +224,7 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
     mbar_init(a2_full, kEpiWarps * CG);
     mbar_init(d2_full, 1);
+    for (int i = 0; i < 8; ++i) mbar_init(act_full(i), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // epilogue constants, folded:  act((acc + bias) * scale + shift) = act(acc * S + T)
@@ -407,11 +415,37 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const uint32_t evs = smem_u32(evec);
     const int actk = ep.act & 0xff;
     const bool rnd = (ep.act & MYOLO_ROUND_TF32) != 0;
-    uint32_t it = 0, nst = 0;
+    uint32_t it = 0, nst = 0, actn = 0;
+    const uint32_t astg = astg0 + (uint32_t)ew * 2048u;
+    // lane 0: fetch the activation tile of (item_, 32 columns from c0_) for this warp's 32 rows
+    auto issue_act = [&](int item_, int c0_) {
+      const int tile_ = (item_ / nh) * CG + (int)rank;
+      long long r0 = (long long)tile_ * WBM + q * 32;
+      if (r0 >= M) r0 = 0;                                  // rows past the end are masked by `valid`; keep the box in range
+      mbar_expect_tx(act_full(ew), 2048u);
+      tma_load_2d(astg, &tmC, act_full(ew), (item_ % nh) * WBN + c0_, (int)r0);
+    };
+    if (act_tma && lane == 0 && cid < nitems) issue_act(cid, cbeg);
     for (int item = cid; item < nitems; item += ncl, ++it) {
       const int half = item % nh;
       const int tile = (item / nh) * CG + (int)rank;      // this CTA's 128*NACC-row tile
       const uint32_t ts = it % TS;
+      // fused BN backward, half flavour: this thread's first 32 activations of the item are fetched BEFORE the wait for the
+      // accumulator (the epilogue warps idle there; the load's DRAM latency used to start after it, once per item), and
+      // the rest of the row's 256-byte span is pulled into L2 for the chunk-ahead loads below
+      uint4 ahp[4];
+      if (EL == 2 && NACC == 1 && ep.bn_a && (dbg & 64)) {
+        const long long mp = (long long)tile * WBM + q * 32 + lane;
+        const bool vp = (mp < M) && pf_valid(mp, ep.pf_w1, ep.pf_blk);
+        const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(ep.bn_a_h) + (size_t)mp * N + half * WBN + cbeg);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ahp[j] = vp ? __ldg(ap + j) : make_uint4(0u, 0u, 0u, 0u);
+        if (vp) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(ap + 4));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(ap + 8));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(ap + 12));
+        }
+      }
       mbar_wait(t_full(ts), (it / TS) & 1u);
       tc_fence_after();
       if (WBN == 256 && NACC == 1 && mt.masks && mt.tc) {
@@ -584,9 +618,15 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // current one is processed (the global-load latency was the longest stall of this epilogue)
         const uint4* arow_h0 = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(ep.bn_a_h) + (size_t)m * N + half * WBN);
         uint4 ahc[4];
-        if (EL == 2 && ep.bn_a) {
+        if (EL == 2 && ep.bn_a && !act_tma) {
+          if (NACC == 1 && (dbg & 64)) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) ahc[j] = valid ? __ldg(arow_h0 + cbeg / 8 + j) : make_uint4(0u, 0u, 0u, 0u);
+            for (int j = 0; j < 4; ++j) ahc[j] = ahp[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              ahc[j] = (valid && !(dbg & 128)) ? __ldg(arow_h0 + cbeg / 8 + j) : make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);
+          }
         }
 #pragma unroll 1
         for (int c0 = cbeg; c0 < cbeg + kColsPerWarp; c0 += 32, ++nst) {
@@ -598,9 +638,26 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           if (EL == 2 && ep.bn_a) {
             // ---- fused BN(+ReLU) backward on half tensors, register-only: v = d(a) of this thread's row (loss-scaled)
             uint4 ahn[4];
+            if (act_tma) {
+              mbar_wait(act_full(ew), actn & 1u);
+              ++actn;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t aaddr = astg + (uint32_t)lane * 64u + (uint32_t)(((uint32_t)j ^ (((uint32_t)lane >> 1) & 3u)) << 4);
+                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(ahc[j].x), "=r"(ahc[j].y), "=r"(ahc[j].z), "=r"(ahc[j].w) : "r"(aaddr) : "memory");
+              }
+              __syncwarp();
+              if (lane == 0) {      // the tile is in registers: its buffer takes the next chunk (of this item or of the next one)
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                if (c0 + 32 < cbeg + kColsPerWarp) issue_act(item, c0 + 32);
+                else if (item + ncl < nitems) issue_act(item + ncl, cbeg);
+              }
+            } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              ahn[j] = (valid && c0 + 32 < cbeg + kColsPerWarp) ? __ldg(arow_h0 + (c0 + 32) / 8 + j) : make_uint4(0u, 0u, 0u, 0u);
+              ahn[j] = (valid && c0 + 32 < cbeg + kColsPerWarp && !(dbg & 128)) ? __ldg(arow_h0 + (c0 + 32) / 8 + j)
+                                                                                   : make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);
+            }
             // per element only g = d(a)*act'(a) and g*a: the per-column constants of dgamma = sum g*(a-beta)/gamma are
             // applied AFTER the column reduction, where lane = column (every broadcast constant load costs a full
             // shared-memory wavefront per lane-row, and this epilogue was bound by them)
@@ -644,12 +701,18 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]));
               }
             }
-            const float s0 = warp_colsum32(v, lane);
-            const float s1 = (warp_colsum32(tt, lane) - evec[N + n0 + lane] * s0) * evec[2 * N + n0 + lane];
-            atomicAdd(colacc + n0 + lane, s0);
-            atomicAdd(colacc + 256 + n0 + lane, s1);
+            if (!(dbg & 256)) {
+              const float s0 = warp_colsum32(v, lane);
+              const float s1 = (warp_colsum32(tt, lane) - evec[N + n0 + lane] * s0) * evec[2 * N + n0 + lane];
+              atomicAdd(colacc + n0 + lane, s0);
+              atomicAdd(colacc + 256 + n0 + lane, s1);
+            } else if (v[0] + tt[31] == 12345.f) {   // timing experiment: no column reductions
+              atomicAdd(colacc + n0 + lane, v[1] + tt[2]);
+            }
+            if (!act_tma) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) ahc[j] = ahn[j];
+              for (int j = 0; j < 4; ++j) ahc[j] = ahn[j];
+            }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) {
@@ -924,7 +987,7 @@ static int launch_win(const float* A, long long lda, const float* Bt, float* C, 
   static int bo_mode = -1;
   if (bo_mode < 0) {
     const char* e = getenv("MYOLO_WIN_BO");
-    bo_mode = e ? atoi(e) : 0;  // experiment switches: 2 = no TMA loads, 4 = skip the global stores, 8 = 128-column slices, 16 = two accumulators, 32 = no CTA pairs
+    bo_mode = e ? atoi(e) : 0;  // experiment switches: 2 = no TMA loads, 4 = skip the global stores, 8 = 128-column slices, 16 = two accumulators, 32 = no CTA pairs, 64 = early activation fetch in the fused BN backward (measured slower), 512 = activation of the fused BN backward by per-lane loads instead of TMA, 128 / 256 = timing experiments: no activation loads / no column reductions in that epilogue (wrong results)
   }
   const int wbn = (((bo_mode & 8) && !mt.masks) || (N % 256) != 0) ? 128 : 256;
   // one accumulator + two TMEM stages (epilogue overlapped with the next item's main loop) is the default;
@@ -990,6 +1053,12 @@ static int launch_win(const float* A, long long lda, const float* Bt, float* C, 
   }
   Epi ep{bias, scale, shift_c, act, pf_w1, pf_blk, accumulate, bnb.a, bnb.gamma, bnb.beta, bnb.var, bnb.ws, bnb.eps,
          hio.on ? (const void*)bnb.a : nullptr, hio.on ? hio.no_f32 : 0, (hio.on && hio.Ch) ? 1 : 0, hio.acc_scale};
+  if (hio.on && bnb.a && hio.no_f32 && hio.Ch && cg == 2 && !(bo_mode & 512)) {
+    // the activation of the fused BN backward by TMA: same geometry as the half output (32 x 32 tiles, 64B swizzle)
+    rc = get_map_h(bnb.a, M, N, N, 32, 32, &tc_);
+    if (rc) return rc;
+    ep.bn_tma = 1;
+  }
   if (hio.on && hio.st_sums) {
     MYOLO_CHECK_ARG(N == 256 && !bnb.a && !mt.masks);
     ep.st_sums = hio.st_sums;

@@ -7,6 +7,7 @@
 // (C*4 bytes each, served from L2 after first touch: the whole feature map is B*F*F*C*4 bytes)
 // and one C*4-byte streaming write.  Coordinates are computed with explicitly rounded fp32 ops in
 // the reference's order so the sample positions are bit-identical to the CPU oracle.
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "crop.cuh"
 
@@ -120,9 +121,12 @@ roialign_bwd_kernel(V dout, const float* __restrict__ boxes, int n_roi, int rois
 // go to memory as vector reductions only when the sample position moves on to another column.  A 14-sample row over
 // a 3..10 pixel wide box issues 1.4..4.7x fewer L2 atomics than one reduction per sample and corner (the atomics,
 // not the 0.94 GB gradient read, bound the per-sample kernel: 0.58 ms).  NQ = C / 128 float4 per lane.
-template <int NQ>
+// GH: dout is an IEEE-half view holding the gradient times a loss scale; *in_scale (device scalar, nullable = 1) removes it
+template <int NQ, bool GH = false>
 __global__ void __launch_bounds__(256)
-roialign_bwd_rl_kernel(V dout, const float* __restrict__ boxes, int n_roi, int rois_per_img, int pool, V dfeat) {
+roialign_bwd_rl_kernel(V dout, const float* __restrict__ boxes, int n_roi, int rois_per_img, int pool, V dfeat,
+                       const float* __restrict__ in_scale = nullptr) {
+  const float gsc = (GH && in_scale) ? __ldg(in_scale) : 1.f;
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -173,9 +177,20 @@ roialign_bwd_rl_kernel(V dout, const float* __restrict__ boxes, int n_roi, int r
       col = sx.lo;
       const float wl = 1.f - sx.lerp, wr = sx.lerp;
       const float4* gp = reinterpret_cast<const float4*>(grow + (size_t)x * dout.c);
+      const uint2* gph = reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(dout.p) + (size_t)r * dout.sn +
+                                                        (size_t)y * dout.sh + (size_t)x * dout.c);
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
-        const float4 g = gp[q * 32 + lane];
+        float4 g;
+        if (GH) {
+          const uint2 u = __ldg(gph + q * 32 + lane);
+          g = make_float4(gsc * __half2float(__ushort_as_half((unsigned short)(u.x & 0xffffu))),
+                          gsc * __half2float(__ushort_as_half((unsigned short)(u.x >> 16))),
+                          gsc * __half2float(__ushort_as_half((unsigned short)(u.y & 0xffffu))),
+                          gsc * __half2float(__ushort_as_half((unsigned short)(u.y >> 16))));
+        } else {
+          g = gp[q * 32 + lane];
+        }
         const float4 dt = make_float4(wt * g.x, wt * g.y, wt * g.z, wt * g.w);
         const float4 db = make_float4(wb * g.x, wb * g.y, wb * g.z, wb * g.w);
         at[0][q].x += wl * dt.x; at[0][q].y += wl * dt.y; at[0][q].z += wl * dt.z; at[0][q].w += wl * dt.w;
@@ -240,6 +255,24 @@ extern "C" int myolo_roialign_bwd(const myolo_view* dout, const float* boxes, in
     roialign_bwd_rl_kernel<2><<<blocks, 256, 0, as_stream(stream)>>>(to_v(dout), boxes, n_roi, rois_per_img, pool, to_v(dfeat));
   else
     roialign_bwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(to_v(dout), boxes, n_roi, rois_per_img, pool, to_v(dfeat));
+  MYOLO_CHECK_LAUNCH();
+  return MYOLO_OK;
+}
+
+// myolo_roialign_bwd on a HALF, loss-scaled gradient (the data gradient of myolo_mask_conv1 in h16 mode); *in_scale
+// (device scalar, nullable) is multiplied into every value read, dfeat stays fp32 and unscaled.  C = 128 or 256.
+extern "C" int myolo_roialign_bwd_h(const myolo_view* dout_half, const float* boxes, int n_roi, int rois_per_img, int pool,
+                                    const myolo_view* dfeat, const float* in_scale, myolo_stream stream) {
+  MYOLO_CHECK_ARG(view_ok(dfeat) && view_ok(dout_half) && boxes && n_roi > 0 && rois_per_img > 0 && pool > 0);
+  MYOLO_CHECK_ARG(dout_half->n == n_roi && dout_half->h == pool && dout_half->w == pool && dout_half->c == dfeat->c);
+  MYOLO_CHECK_ARG((n_roi + rois_per_img - 1) / rois_per_img <= dfeat->n && ((uintptr_t)dout_half->p & 7) == 0);
+  MYOLO_CHECK_ARG(dfeat->c == 128 || dfeat->c == 256);
+  const long long items = (long long)n_roi * pool;
+  const int blocks = (int)max(1LL, min(ceil_div(items, 8), (long long)kNumSMs * 8));
+  if (dfeat->c == 128)
+    roialign_bwd_rl_kernel<1, true><<<blocks, 256, 0, as_stream(stream)>>>(to_v(dout_half), boxes, n_roi, rois_per_img, pool, to_v(dfeat), in_scale);
+  else
+    roialign_bwd_rl_kernel<2, true><<<blocks, 256, 0, as_stream(stream)>>>(to_v(dout_half), boxes, n_roi, rois_per_img, pool, to_v(dfeat), in_scale);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }

@@ -211,6 +211,8 @@ struct Epi {
   float* st_var;
   double st_inv;          // 1 / number of valid rows
   const float* st_pivot;  // conv_win kernel: per-column value subtracted before the sums are taken (nullable)
+  int bn_tma;             // conv_win kernel, half flavour of the fused BN backward: the activation arrives by TMA through the
+                          // (otherwise unused) fp32 output map, one 32x32 half tile per epilogue warp and chunk
 };
 
 

@@ -150,6 +150,9 @@ class Engine:
         # backward's reduction pass in the epilogue of myolo_mask_conv2's data-gradient GEMM (h16 mode; implies 8)
         self._fuse_bn = int(os.environ.get("MYOLO_FUSE_BN", "29"))
         self._bn1_half = bool(self._fuse_bn & 16) and precision == "h16"
+        # h16: d(x0), the data gradient of myolo_mask_conv1, stays a loss-scaled half tensor like every other gradient of the
+        # mask head; ROIAlign's backward removes the scale while it reads (A/B switch)
+        self._dx0_half = os.environ.get("MYOLO_DX0_HALF", "1") != "0" and precision == "h16"
         self._pw_win = os.environ.get("MYOLO_PW_WIN", "0") != "0"      # pointwise forward on the persistent window kernel (A/B)      # measured best: profiles/r02_fuse_bn_ab.txt
         self._deferred = {}
         self._plan = None
@@ -444,7 +447,12 @@ class Engine:
                     self.sp_g = [hp(MASK_C) for _ in range(2)]
                     self.sp_list = torch.zeros(self.pcap, dtype=torch.int32, device=dev)
                     self.sp_list_host = torch.zeros(self.pcap, dtype=torch.int32).pin_memory()
-                self.mg = [PF(n, P_, P_, MASK_C, device=dev) for _ in range(2)]
+                if self.h16 and self._dx0_half:
+                    self.mg = [None, PF(n, P_, P_, MASK_C, device=dev, dtype=torch.float16)]
+                else:
+                    self.mg = [PF(n, P_, P_, MASK_C, device=dev) for _ in range(1 if self.h16 else 2)]
+                    if self.h16:
+                        self.mg = [None, self.mg[0]]
                 self.dfeat = PF(B, F_, F_, MASK_C, device=dev)
                 self.dc4 = PF(B, F_, F_, 512, device=dev)
         self.A = A
@@ -1013,8 +1021,12 @@ class Engine:
                    C.ACT_RELU, 1, b.dgamma, b.dbeta, self.ws, ugs, st)
         name = "myolo_mask_conv1/kernel"
         wgrad(self.mah[0].rows, MASK_C, g1.rows, MASK_C, self.g[name], M, MASK_C, MASK_C, 9, sh3, 0, ugs, wst)
-        C.call("myolo_gemm_taps_h", g1.rows, MASK_C, self.wth_d[name], self.mg[1].rows, MASK_C, None, 0, M, MASK_C, MASK_C, 9,
-               shn, None, None, None, C.ACT_NONE, pfw, pfb, ugs, st)
+        if self._dx0_half:
+            C.call("myolo_gemm_taps_h", g1.rows, MASK_C, self.wth_d[name], None, 0, self.mg[1].rows, MASK_C, M, MASK_C, MASK_C, 9,
+                   shn, None, None, None, C.ACT_NONE, pfw, pfb, None, st)
+        else:
+            C.call("myolo_gemm_taps_h", g1.rows, MASK_C, self.wth_d[name], self.mg[1].rows, MASK_C, None, 0, M, MASK_C, MASK_C, 9,
+                   shn, None, None, None, C.ACT_NONE, pfw, pfb, ugs, st)
         if W is not None:       # the data-gradient chain of the mask head is issued: the filter gradients start behind it
             e = self._ev("w_start")
             C.record_py(lambda: (e.record(main), W.wait_event(e)))
@@ -1179,7 +1191,10 @@ class Engine:
         P_, B, F_ = self.cfg["POOL"], self.B, self.F
         # CropAndResizeGradImage into the feature-map gradient
         C.record_py(self.dfeat.storage.zero_)
-        C.call("myolo_roialign_bwd", g0.view(), A["rois"], n, self.R, P_, self.dfeat.view(), st)
+        if g0.rows.dtype == torch.float16:
+            C.call("myolo_roialign_bwd_h", g0.view(), A["rois"], n, self.R, P_, self.dfeat.view(), self.gs[1:], st)
+        else:
+            C.call("myolo_roialign_bwd", g0.view(), A["rois"], n, self.R, P_, self.dfeat.view(), st)
         C.call("myolo_colsum", self.dfeat.view(), self.g["feature_map/bias"], self.ws, st)
         W = self._wstream if getattr(self, "_w_used", False) else None
         if W is not None:

@@ -282,6 +282,20 @@ def test_roialign(C, Cc):
     dod = cuda(dout)
     C.call("myolo_roialign_bwd", C.view(dod, B * R, P, P, Cc), bd, B * R, R, P, C.view(dfd, B, Fh, Fh, Cc), stream())
     close(dfd, feat.grad, 1e-5, "roialign bwd")
+    if Cc >= 128:     # the same from a half, loss-scaled gradient (h16 mode): the scale is removed while reading
+        from myolo.pf import PF
+        dh = PF(B * R, P, P, Cc, dtype=torch.float16)
+        dh.valid().copy_(dod * 64.0)
+        ref = torch.zeros_like(fd)
+        C.call("myolo_roialign_bwd", C.view(dh.valid().float().contiguous() / 64.0, B * R, P, P, Cc), bd, B * R, R, P,
+               C.view(ref, B, Fh, Fh, Cc), stream())
+        dfh = torch.zeros_like(fd)
+        us = torch.tensor([1.0 / 64.0], device="cuda")
+        C.call("myolo_roialign_bwd_h", dh.view(), bd, B * R, R, P, C.view(dfh, B, Fh, Fh, Cc), us, stream())
+        close(dfh, ref, 5e-6, "roialign bwd from the half gradient (fp32 atomics order)")
+        with pytest.raises(C.MyoloError):
+            C.call("myolo_roialign_bwd_h", dh.view(), bd, B * R, R, P, C.view(torch.zeros(B, Fh, Fh, 64, device="cuda"), B, Fh, Fh, 64),
+                   us, stream())
 
 
 # ----------------------------------------------------------------------------- tap-GEMM family
