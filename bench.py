@@ -485,6 +485,9 @@ def main():
                 "fp32_class": fp32, "sparse_backward": sparse, "parity": parity,
                 "model_tflops_per_s": value * fl / 1e12, "frac_of_conv_roofline": value * fl / 1e12 / pk["bf16_tflops_sustained"],
                 "loss": main_res["loss"]}
+        from myolo import _cabi
+        if _cabi.WHATIF_SKIP:       # profiling run with entry points switched off: timing experiment, not a benchmark
+            line["invalid"] = "MYOLO_WHATIF_SKIP=" + ",".join(sorted(_cabi.WHATIF_SKIP))
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -150,9 +150,17 @@ def record_py(fn):
         _rec.append([None, fn, None, 0, "py"])
 
 
+# profiling only (scripts/whatif_critical_path.sh): entry points named in MYOLO_WHATIF_SKIP are NOT launched, so that the
+# step time without them shows what each costs on the critical path.  The step's results are garbage; bench.py marks
+# such a line invalid.
+WHATIF_SKIP = frozenset(x for x in os.environ.get("MYOLO_WHATIF_SKIP", "").split(",") if x)
+
+
 def call(name: str, *args):
     """Invoke a C-ABI entry point; tensors -> device pointers; nonzero status -> MyoloError."""
     global launch_count
+    if WHATIF_SKIP and name in WHATIF_SKIP:
+        return 0
     l = lib()
     fn = getattr(l, name)
     n = KERNELS_PER_CALL.get(name, 1)
