@@ -332,7 +332,7 @@ int myolo_mask_out_bwd_h(const float* y4, const float* bd, const float* w1, cons
                          const float* gscale, const int* target_ids, int* prev_ids, myolo_stream stream);
 /* myolo_gemm_taps_wgrad with half A [rows][K] and half D [rows][N] (both MN-major operands of tcgen05 kind::f16):
  * dW[t][k][n] += (*out_scale) * sum_m A[m + shift[t], k] * D[m, n]  (fp32 atomics; out_scale nullable = 1).
- * K % 64 == 0, N % 64 == 0, lda % 8 == 0, ldd % 8 == 0. */
+ * K % 64 == 0, N % 64 == 0, lda % 8 == 0, ldd % 8 == 0; dW 16-byte aligned unless transpose_out (128-bit vector reductions). */
 int myolo_gemm_taps_wgrad_h(const void* A, long long lda, const void* D, long long ldd, float* dW, long long M,
                             int N, int K, int ntaps, const int* shifts_host, int transpose_out,
                             const float* out_scale, myolo_stream stream);
