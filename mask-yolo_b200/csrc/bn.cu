@@ -405,6 +405,99 @@ bn_batch_fix_hh_kernel(V z, V g, const float* __restrict__ mean, const float* __
   }
 }
 
+// ---- 8 channels (16 bytes of half) per thread and two pixels in flight: the one-tensor passes of myolo_mask_bn1 over the
+// 0.5 GB half tensors of the mask head.  (The 4-channel kernels above move 8 bytes per load with one load in flight per
+// thread: 3.0 TB/s on the apply pass against 4.8 TB/s for the correction pass, which has two.)
+__device__ __forceinline__ void unpack_half8(const uint4& u, float (&f)[8]) {
+  f[0] = half_bits_to_float(u.x & 0xffffu); f[1] = half_bits_to_float(u.x >> 16);
+  f[2] = half_bits_to_float(u.y & 0xffffu); f[3] = half_bits_to_float(u.y >> 16);
+  f[4] = half_bits_to_float(u.z & 0xffffu); f[5] = half_bits_to_float(u.z >> 16);
+  f[6] = half_bits_to_float(u.w & 0xffffu); f[7] = half_bits_to_float(u.w >> 16);
+}
+__device__ __forceinline__ uint4 pack_half8(const float (&f)[8]) {
+  return make_uint4(pack_half2_sat(f[0], f[1]), pack_half2_sat(f[2], f[3]), pack_half2_sat(f[4], f[5]), pack_half2_sat(f[6], f[7]));
+}
+
+__global__ void __launch_bounds__(256)
+bn_apply_hh8_kernel(V x, V yh, const float* __restrict__ mean, const float* __restrict__ var, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, float eps, int act, int same_geo, FastDiv fc8) {
+  const int C8 = x.c >> 3;
+  const long long total = (long long)x.n * x.h * x.w * C8;
+  const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+  const bool fixed_q = (stride % C8) == 0;
+  float mu[8], rs[8], ga[8], be[8];      // the same arithmetic as bn_apply_kernel: act(((x - mu) * rs) * ga + be)
+  auto load_q = [&](int q) {
+    const BnQuad a = bn_quad(mean, var, gamma, beta, eps, q), b = bn_quad(mean, var, gamma, beta, eps, q + 4);
+    mu[0] = a.mu.x; mu[1] = a.mu.y; mu[2] = a.mu.z; mu[3] = a.mu.w; mu[4] = b.mu.x; mu[5] = b.mu.y; mu[6] = b.mu.z; mu[7] = b.mu.w;
+    rs[0] = a.rs.x; rs[1] = a.rs.y; rs[2] = a.rs.z; rs[3] = a.rs.w; rs[4] = b.rs.x; rs[5] = b.rs.y; rs[6] = b.rs.z; rs[7] = b.rs.w;
+    ga[0] = a.ga.x; ga[1] = a.ga.y; ga[2] = a.ga.z; ga[3] = a.ga.w; ga[4] = b.ga.x; ga[5] = b.ga.y; ga[6] = b.ga.z; ga[7] = b.ga.w;
+    be[0] = a.be.x; be[1] = a.be.y; be[2] = a.be.z; be[3] = a.be.w; be[4] = b.be.x; be[5] = b.be.y; be[6] = b.be.z; be[7] = b.be.w;
+  };
+  load_q((int)(i0 % C8) * 8);
+  const uint16_t* xp = reinterpret_cast<const uint16_t*>(x.p);
+  uint16_t* yp = reinterpret_cast<uint16_t*>(yh.p);
+  for (long long i = i0; i < total; i += 2 * stride) {
+    const long long i2 = i + stride;
+    const bool two = i2 < total;
+    const uint32_t pa = fd_div((uint32_t)i, fc8), pb = fd_div((uint32_t)(two ? i2 : i), fc8);
+    const int qa = (int)((uint32_t)i - pa * (uint32_t)C8) * 8, qb = (int)((uint32_t)(two ? i2 : i) - pb * (uint32_t)C8) * 8;
+    const size_t xa = pix_off(x, pa), xb = pix_off(x, pb);
+    const uint4 ua = *reinterpret_cast<const uint4*>(xp + xa + qa);
+    const uint4 ub = *reinterpret_cast<const uint4*>(xp + xb + qb);
+    float f[8];
+    if (!fixed_q) load_q(qa);
+    unpack_half8(ua, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = apply_act(fmaf((f[j] - mu[j]) * rs[j], ga[j], be[j]), act & 0xff);
+    *reinterpret_cast<uint4*>(yp + (same_geo ? xa : pix_off(yh, pa)) + qa) = pack_half8(f);
+    if (two) {
+      if (!fixed_q) load_q(qb);
+      unpack_half8(ub, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = apply_act(fmaf((f[j] - mu[j]) * rs[j], ga[j], be[j]), act & 0xff);
+      *reinterpret_cast<uint4*>(yp + (same_geo ? xb : pix_off(yh, pb)) + qb) = pack_half8(f);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bn_batch_fix_hh8_kernel(V z, V g, const float* __restrict__ mean, const float* __restrict__ coef, int same_geo, FastDiv fc8) {
+  const int C = z.c, C8 = C >> 3;
+  const long long total = (long long)z.n * z.h * z.w * C8;
+  const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+  const bool fixed_q = (stride % C8) == 0;
+  float mu[8], ka[8], kb[8];
+  auto load_q = [&](int q) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float4 m = __ldg(reinterpret_cast<const float4*>(mean + q + 4 * h));
+      const float4 a = __ldg(reinterpret_cast<const float4*>(coef + q + 4 * h));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(coef + C + q + 4 * h));
+      mu[4 * h] = m.x; mu[4 * h + 1] = m.y; mu[4 * h + 2] = m.z; mu[4 * h + 3] = m.w;
+      ka[4 * h] = a.x; ka[4 * h + 1] = a.y; ka[4 * h + 2] = a.z; ka[4 * h + 3] = a.w;
+      kb[4 * h] = b.x; kb[4 * h + 1] = b.y; kb[4 * h + 2] = b.z; kb[4 * h + 3] = b.w;
+    }
+  };
+  load_q((int)(i0 % C8) * 8);
+  const uint16_t* zp = reinterpret_cast<const uint16_t*>(z.p);
+  uint16_t* gp = reinterpret_cast<uint16_t*>(g.p);
+  for (long long i = i0; i < total; i += stride) {
+    const uint32_t pp = fd_div((uint32_t)i, fc8);
+    const int q = (int)((uint32_t)i - pp * (uint32_t)C8) * 8;
+    const size_t zo = pix_off(z, pp);
+    const size_t go = same_geo ? zo : pix_off(g, pp);
+    const uint4 uz = *reinterpret_cast<const uint4*>(zp + zo + q);
+    const uint4 ug = *reinterpret_cast<const uint4*>(gp + go + q);
+    if (!fixed_q) load_q(q);
+    float fz[8], fg[8];
+    unpack_half8(uz, fz);
+    unpack_half8(ug, fg);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) fg[j] = fg[j] - ka[j] - kb[j] * (fz[j] - mu[j]);
+    *reinterpret_cast<uint4*>(gp + go + q) = pack_half8(fg);
+  }
+}
+
 __global__ void bn_moving_update_kernel(const float* __restrict__ value, float* __restrict__ biased,
                                         float* __restrict__ moving, int C, float momentum, float corr, float debias) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -547,6 +640,11 @@ bn_act_bwd_from_output_kernel(V a, V dy, V dx, const float* __restrict__ gamma, 
 static bool view_ok(const myolo_view* v) {
   return v && v->p && v->n > 0 && v->h > 0 && v->w > 0 && v->c > 0 && (v->c % 4) == 0 && (v->sn % 4) == 0 && (v->sh % 4) == 0;
 }
+// a half view whose pixels can be moved 8 channels (16 bytes) at a time
+static bool half8_ok(const myolo_view* v) {
+  return (v->c % 8) == 0 && (v->sn % 8) == 0 && (v->sh % 8) == 0 && ((uintptr_t)v->p & 15) == 0 &&
+         (long long)v->n * v->h * v->w * (v->c / 8) < (1LL << 31);
+}
 static bool same_shape(const myolo_view* a, const myolo_view* b) {
   return a->n == b->n && a->h == b->h && a->w == b->w && a->c == b->c;
 }
@@ -626,6 +724,13 @@ extern "C" int myolo_bn_apply_hh(const myolo_view* x_half, const myolo_view* y_h
   V vy = to_v(x_half);
   vy.p = nullptr;
   const int same_geo = x_half->sn == y_half->sn && x_half->sh == y_half->sh;
+  if (half8_ok(x_half) && half8_ok(y_half)) {
+    const long long t8 = total / 2;
+    bn_apply_hh8_kernel<<<ew_blocks(t8 / 2 + 1), 256, 0, as_stream(stream)>>>(to_v(x_half), to_v(y_half), mean, var, gamma, beta, eps, act,
+                                                                           same_geo, make_fd((uint32_t)(x_half->c / 8)));
+    MYOLO_CHECK_LAUNCH();
+    return MYOLO_OK;
+  }
   bn_apply_h_kernel<true><<<ew_blocks(total), 256, 0, as_stream(stream)>>>(to_v(x_half), vy, to_v(y_half), mean, var, gamma, beta, eps, act, same_geo);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
@@ -646,6 +751,12 @@ extern "C" int myolo_bn_bwd_batch_fix_hh(const myolo_view* z_half, const myolo_v
   float* coef = reinterpret_cast<float*>(ws + kWsCoef);
   bn_batch_coef_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws + kWsSums, gamma, var, eps, 1.0 / (double)total, grad_unscale, dgamma, dbeta, coef, C);
   const int same_geo = z_half->sn == g_half->sn && z_half->sh == g_half->sh;
+  if (half8_ok(z_half) && half8_ok(g_half)) {
+    bn_batch_fix_hh8_kernel<<<ew_blocks(total * (C / 8)), 256, 0, st>>>(to_v(z_half), to_v(g_half), mean, coef, same_geo,
+                                                                        make_fd((uint32_t)(C / 8)));
+    MYOLO_CHECK_LAUNCH();
+    return MYOLO_OK;
+  }
   bn_batch_fix_hh_kernel<<<ew_blocks(total * (C / 4)), 256, 0, st>>>(to_v(z_half), to_v(g_half), mean, coef, same_geo);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
