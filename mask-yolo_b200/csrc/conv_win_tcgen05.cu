@@ -848,15 +848,17 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           }
           if (EL == 2 && ep.st_sums && !ep.bn_a) {   // column sums of the chunk while its TMA store is in flight
             // shifted by a per-column pivot (the layer's moving mean): E[x^2] - E[x]^2 would lose mean^2 / variance digits
+            // The shift is applied to the 32-row column sums, where lane = column (sum (x-p) = S0 - n p, sum (x-p)^2 =
+            // S1 - 2 p S0 + n p^2; over 32 rows that costs ~1e-7 * (mean^2 + var) / var of relative accuracy) instead of to
+            // every element, which needed one shuffle per column to hand each row its pivots.
             const float pv = ep.st_pivot ? __ldg(ep.st_pivot + n0 + lane) : 0.f;
+            const float nv = (float)__popc(__ballot_sync(0xffffffffu, valid));
             float sq[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float pj = __shfl_sync(0xffffffffu, pv, j);
-              v[j] = valid ? v[j] - pj : 0.f;
-              sq[j] = v[j] * v[j];
-            }
-            const float s0 = warp_colsum32(v, lane), s1 = warp_colsum32(sq, lane);
+            for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];      // rows that are not valid hold zeros
+            const float r0 = warp_colsum32(v, lane), r1 = warp_colsum32(sq, lane);
+            const float s0 = fmaf(-nv, pv, r0);
+            const float s1 = fmaf(pv, fmaf(nv, pv, -2.f * r0), r1);
             float* slot = colacc + (ew < 2 ? ew * 256 : 1024 + (ew - 2) * 256) + (c0 - cbeg) + lane;
             slot[0] += s0;
             slot[128] += s1;
