@@ -150,11 +150,23 @@ __global__ void __launch_bounds__(256) dw_fwd_kernel(const float* __restrict__ x
 // loads (two of them shared with the neighbouring threads through L1), no shared memory, no barrier, ~30 independent
 // loads in flight per thread.  A warp covers 4 adjacent columns x 32 channels = 512 contiguous bytes of an NHWC row.
 // ------------------------------------------------------------------------------------------
+// a += v * w on a channel quad as two packed fp32 pairs (Blackwell FFMA2: each half rounded like a scalar fmaf)
 __device__ __forceinline__ void fma4(float4& a, const float4& v, const float4& w) {
+#ifdef MYOLO_DW_SCALAR_FMA
   a.x = fmaf(v.x, w.x, a.x);
   a.y = fmaf(v.y, w.y, a.y);
   a.z = fmaf(v.z, w.z, a.z);
   a.w = fmaf(v.w, w.w, a.w);
+#else
+  asm("{\n\t.reg .b64 a0, a1, v0, v1, w0, w1;\n\t"
+      "mov.b64 a0, {%0, %1};\n\tmov.b64 a1, {%2, %3};\n\t"
+      "mov.b64 v0, {%4, %5};\n\tmov.b64 v1, {%6, %7};\n\t"
+      "mov.b64 w0, {%8, %9};\n\tmov.b64 w1, {%10, %11};\n\t"
+      "fma.rn.f32x2 a0, v0, w0, a0;\n\tfma.rn.f32x2 a1, v1, w1, a1;\n\t"
+      "mov.b64 {%0, %1}, a0;\n\tmov.b64 {%2, %3}, a1;\n\t}"
+      : "+f"(a.x), "+f"(a.y), "+f"(a.z), "+f"(a.w)
+      : "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "f"(w.x), "f"(w.y), "f"(w.z), "f"(w.w));
+#endif
 }
 
 // forward (and, with FLIP, the stride-1 data gradient: the same correlation with the kernel rotated by 180 degrees)

@@ -85,13 +85,36 @@ struct MaskTail {
 // (Tried and rejected, measured on B200: the constants in __constant__ memory with compile-time offsets -- ptxas turns
 // them into LDCU.128 + uniform-register FFMA operands, 1.08 -> 1.46 ms; and the eight chunks of a row fully unrolled --
 // 38 KB of straight-line code per class count, 1.08 -> 2.1 ms.  The chunk loop stays rolled.)
+// Packed fp32 pairs (Blackwell FFMA2 / FADD2: two fp32 operations per instruction, each rounded like its scalar form).
+// The scalar FFMA issues every other cycle per scheduler, so the 128 dot-product FMAs of a 32-channel chunk were the
+// longest part of this epilogue (profiles/r02_mask_tail_parts.txt: 0.42 ms of the kernel); as 64 FFMA2 they take half.
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t p, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(p)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// lg[k][p]: a PAIR of partial logits of class k (even / odd channels of the 4-channel groups with parity p); the caller
+// adds the four partial sums.
 template <int NCT>
-__device__ __forceinline__ void mask_tail_chunk(float (&v)[32], uint32_t evs, int C0, float* ypos, float (&lg)[8][2]) {
+__device__ __forceinline__ void mask_tail_chunk(float (&v)[32], uint32_t evs, int C0, float* ypos, uint64_t (&lg)[8][2]) {
   if (ypos) {
     float4* yp = reinterpret_cast<float4*>(ypos + C0);
 #pragma unroll
     for (int j = 0; j < 8; ++j) yp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
   }
+  uint64_t h[16];      // relu(v + bd) as channel pairs
   {
     float4 b4[8];
 #pragma unroll
@@ -99,25 +122,24 @@ __device__ __forceinline__ void mask_tail_chunk(float (&v)[32], uint32_t evs, in
       asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b4[j].x), "=f"(b4[j].y), "=f"(b4[j].z), "=f"(b4[j].w) : "r"(evs + 4u * (C0 + 4 * j)));
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      v[4 * j] = fmaxf(v[4 * j] + b4[j].x, 0.f);
-      v[4 * j + 1] = fmaxf(v[4 * j + 1] + b4[j].y, 0.f);
-      v[4 * j + 2] = fmaxf(v[4 * j + 2] + b4[j].z, 0.f);
-      v[4 * j + 3] = fmaxf(v[4 * j + 3] + b4[j].w, 0.f);
+      float a0, a1, a2, a3;
+      unpack2(add2(pack2(v[4 * j], v[4 * j + 1]), pack2(b4[j].x, b4[j].y)), a0, a1);
+      unpack2(add2(pack2(v[4 * j + 2], v[4 * j + 3]), pack2(b4[j].z, b4[j].w)), a2, a3);
+      h[2 * j] = pack2(fmaxf(a0, 0.f), fmaxf(a1, 0.f));
+      h[2 * j + 1] = pack2(fmaxf(a2, 0.f), fmaxf(a3, 0.f));
     }
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    float4 w[NCT];
+    uint64_t w[NCT][2];
 #pragma unroll
     for (int k = 0; k < NCT; ++k)
-      asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(w[k].x), "=f"(w[k].y), "=f"(w[k].z), "=f"(w[k].w) : "r"(evs + 4u * (256 + k * 256 + C0 + 4 * j)));
+      asm("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(w[k][0]), "=l"(w[k][1]) : "r"(evs + 4u * (256 + k * 256 + C0 + 4 * j)));
 #pragma unroll
     for (int k = 0; k < NCT; ++k) {
-      float a = lg[k][j & 1];
-      a = fmaf(v[4 * j], w[k].x, a);
-      a = fmaf(v[4 * j + 1], w[k].y, a);
-      a = fmaf(v[4 * j + 2], w[k].z, a);
-      a = fmaf(v[4 * j + 3], w[k].w, a);
+      uint64_t a = lg[k][j & 1];
+      a = fma2(h[2 * j], w[k][0], a);
+      a = fma2(h[2 * j + 1], w[k][1], a);
       lg[k][j & 1] = a;
     }
   }
@@ -126,7 +148,7 @@ __device__ __forceinline__ void mask_tail_chunk(float (&v)[32], uint32_t evs, in
 // columns [cb, ce) of one accumulator row (a multiple of 64 wide); the TMEM load of the next chunk is in flight while
 // a chunk is processed
 template <int NCT>
-__device__ __forceinline__ void mask_tail_row(uint32_t taddr, uint32_t evs, float* ypos, float (&lg)[8][2], int cb, int ce) {
+__device__ __forceinline__ void mask_tail_row(uint32_t taddr, uint32_t evs, float* ypos, uint64_t (&lg)[8][2], int cb, int ce) {
   float va[32], vb[32];
   tmem_ld32_issue(taddr + (uint32_t)cb, va);
   tmem_ld_wait(va);
@@ -413,6 +435,7 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       __syncwarp();
     };
     const uint32_t evs = smem_u32(evec);
+    const PfDiv pfd = make_pfdiv(ep.pf_w1, ep.pf_blk);
     const int actk = ep.act & 0xff;
     const bool rnd = (ep.act & MYOLO_ROUND_TF32) != 0;
     uint32_t it = 0, nst = 0, actn = 0;
@@ -436,7 +459,7 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       uint4 ahp[4];
       if (EL == 2 && NACC == 1 && ep.bn_a && (dbg & 64)) {
         const long long mp = (long long)tile * WBM + q * 32 + lane;
-        const bool vp = (mp < M) && pf_valid(mp, ep.pf_w1, ep.pf_blk);
+        const bool vp = (mp < M) && pf_valid(mp, pfd);
         const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(ep.bn_a_h) + (size_t)mp * N + half * WBN + cbeg);
 #pragma unroll
         for (int j = 0; j < 4; ++j) ahp[j] = vp ? __ldg(ap + j) : make_uint4(0u, 0u, 0u, 0u);
@@ -451,14 +474,12 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       if (WBN == 256 && NACC == 1 && mt.masks && mt.tc) {
         // ---- tensor-core mask tail.  This thread's row = input pixel (roi, hh, ww) of sub-pixel (a, b) = item's slice.
         const long long m = (long long)tile * WBM + q * 32 + lane;
-        const bool valid = (m < M) && pf_valid(m, ep.pf_w1, ep.pf_blk);
         int roi = 0, hh = 0, ww = 0;
+        const bool valid = (m < M) && pf_decode(m, pfd, roi, hh, ww);
         bool pos = false;
         if (valid) {
-          roi = (int)(m / ep.pf_blk);
-          const int r = (int)(m - (long long)roi * ep.pf_blk);
-          hh = r / ep.pf_w1 - 1;
-          ww = r % ep.pf_w1 - 1;
+          hh -= 1;
+          ww -= 1;
           pos = mt.ids && __ldg(mt.ids + roi) > 0;
         }
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + ts * TSTRIDE;
@@ -555,19 +576,17 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // its partial logits over through shared memory (one named barrier per item, double-buffered by item parity)
         for (int acc = 0; acc < NACC; ++acc) {
           const long long m = (long long)tile * WBM + acc * 128 + q * 32 + lane;
-          const bool valid = (m < M) && pf_valid(m, ep.pf_w1, ep.pf_blk);
           int roi = 0, hh = 0, ww = 0;
+          const bool valid = (m < M) && pf_decode(m, pfd, roi, hh, ww);
           bool pos = false;
           if (valid) {
-            roi = (int)(m / ep.pf_blk);
-            const int r = (int)(m - (long long)roi * ep.pf_blk);
-            hh = r / ep.pf_w1 - 1;
-            ww = r % ep.pf_w1 - 1;
+            hh -= 1;
+            ww -= 1;
             pos = mt.ids && __ldg(mt.ids + roi) > 0;
           }
-          float lg[8][2];
+          uint64_t lg[8][2];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) lg[k][0] = lg[k][1] = 0.f;
+          for (int k = 0; k < 8; ++k) lg[k][0] = lg[k][1] = 0ull;
           {
             const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + ts * TSTRIDE + (uint32_t)(acc * 256);
             float* ypos = pos ? mt.y4 + (size_t)m * N + half * 256 : nullptr;
@@ -584,7 +603,12 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           }
           float lgs[8];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) lgs[k] = lg[k][0] + lg[k][1];
+          for (int k = 0; k < 8; ++k) {
+            float e0, o0, e1, o1;
+            unpack2(lg[k][0], e0, o0);
+            unpack2(lg[k][1], e1, o1);
+            lgs[k] = (e0 + o0) + (e1 + o1);
+          }
           if (EL == 2) {
             const uint32_t xbuf = stg0 + (uint32_t)(q + 4) * 4096u + (((it * NACC + acc) & 1u) ? 1024u : 0u) + (uint32_t)lane * 32u;
             if (eh == 1) {
@@ -613,7 +637,7 @@ tc_conv_win_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       for (int acc = 0; acc < NACC; ++acc) {
         const int mrow0 = tile * WBM + acc * 128 + q * 32;
         const long long m = (long long)mrow0 + lane;
-        const bool valid = (m < M) && pf_valid(m, ep.pf_w1, ep.pf_blk);
+        const bool valid = (m < M) && pf_valid(m, pfd);
         // half flavour of the fused BN backward: the activation chunk of the NEXT 32 columns is fetched while the
         // current one is processed (the global-load latency was the longest stall of this epilogue)
         const uint4* arow_h0 = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(ep.bn_a_h) + (size_t)m * N + half * WBN);

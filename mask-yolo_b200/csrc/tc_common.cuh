@@ -167,6 +167,46 @@ __device__ __forceinline__ bool pf_valid(long long m, int pf_w1, int pf_blk) {
   return (r / pf_w1) >= 1 && (r % pf_w1) >= 1;
 }
 
+// The same test with the two divisions by the (run-time constant) tile geometry as multiply-high + shift: built once per
+// thread at kernel start, used once per work item by every epilogue thread (the 64-bit div / mod chains above were ~10 %
+// of the instructions of the mask-tail epilogue).  Rows are below 2^31 (checked on the host).
+struct PfDiv {
+  uint32_t mb, sb, mw, sw;   // magic multiplier / shift for pf_blk and pf_w1
+  int w1, blk;
+};
+__device__ __forceinline__ void pf_magic(uint32_t d, uint32_t& mul, uint32_t& shr) {
+  const uint32_t l = d > 1u ? 32u - (uint32_t)__clz((int)(d - 1u)) : 0u;
+  mul = (uint32_t)((((unsigned long long)1 << 32) * (((unsigned long long)1 << l) - d)) / d + 1ull);
+  shr = l;
+}
+__device__ __forceinline__ PfDiv make_pfdiv(int pf_w1, int pf_blk) {
+  PfDiv d{0u, 0u, 0u, 0u, pf_w1, pf_blk};
+  if (pf_w1 > 0) {
+    pf_magic((uint32_t)pf_blk, d.mb, d.sb);
+    pf_magic((uint32_t)pf_w1, d.mw, d.sw);
+  }
+  return d;
+}
+// row m of a padded-flat tensor -> tile (roi / image) index, line and column inside the tile; false for pad rows
+__device__ __forceinline__ bool pf_decode(long long m, const PfDiv& d, int& tile, int& line, int& col) {
+  if (d.w1 <= 0) {
+    tile = line = col = 0;
+    return true;
+  }
+  const uint32_t mm = (uint32_t)m;
+  const uint32_t t = (__umulhi(d.mb, mm) + mm) >> d.sb;
+  const uint32_t r = mm - t * (uint32_t)d.blk;
+  const uint32_t ln = (__umulhi(d.mw, r) + r) >> d.sw;
+  tile = (int)t;
+  line = (int)ln;
+  col = (int)(r - ln * (uint32_t)d.w1);
+  return line >= 1 && col >= 1;
+}
+__device__ __forceinline__ bool pf_valid(long long m, const PfDiv& d) {
+  int t, l, c;
+  return pf_decode(m, d, t, l, c);
+}
+
 // x[c] = this lane's (row's) value of column c.  Returns, in lane l, the sum over the 32 rows of column l
 // (butterfly transpose-reduce: 31 shuffles, no shared memory).
 __device__ __forceinline__ float warp_colsum32(float (&x)[32], int lane) {
