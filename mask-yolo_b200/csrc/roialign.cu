@@ -29,7 +29,11 @@ __device__ __forceinline__ uint32_t pack_half2_sat(float lo, float hi) {
 
 // HALF: the pooled values are (also) stored as IEEE half into `outh` (operand of the kind::f16 mask conv1);
 // out.p may then be null.
-template <bool HALF>
+// NQ > 0 (C == 128 * NQ): the feature columns a sample row touches are kept in registers and re-used by the next sample
+// when it falls on the same columns -- 14 samples over a 3..10 pixel wide box read 28 column quads per row otherwise,
+// most of them twice or more (the kernel was bound by these L1 / L2 gathers, not by its 0.4 GB of output).  The values
+// and their arithmetic are unchanged, so the result stays bit-exact.  NQ == 0: any C, one load per sample and corner.
+template <bool HALF, int NQ>
 __global__ void __launch_bounds__(256)
 roialign_fwd_kernel(V feat, const float* __restrict__ boxes, int n_roi, int rois_per_img, int pool, V out, int rnd, V outh) {
   const int lane = threadIdx.x & 31;
@@ -45,6 +49,9 @@ roialign_fwd_kernel(V feat, const float* __restrict__ boxes, int n_roi, int rois
     const float* fb = feat.p + (size_t)b * feat.sn;
     float* orow = out.p ? out.p + (size_t)r * out.sn + (size_t)y * out.sh : nullptr;
     uint16_t* hrow = HALF ? reinterpret_cast<uint16_t*>(outh.p) + (size_t)r * outh.sn + (size_t)y * outh.sh : nullptr;
+    constexpr int NQR = NQ > 0 ? NQ : 1;
+    float4 ct[2][NQR], cb[2][NQR];     // cached column pair: [0] = column c_lo, [1] = column c_hi; top / bottom feature row
+    int c_lo = -1, c_hi = -1;
     for (int x = 0; x < pool; ++x) {
       const Sample sx = crop_coord(bx.y, bx.w, x, pool, feat.w);
       float4* op = reinterpret_cast<float4*>(orow + (size_t)x * out.c);
@@ -56,10 +63,71 @@ roialign_fwd_kernel(V feat, const float* __restrict__ boxes, int n_roi, int rois
         }
         continue;
       }
-      const float4* tl = reinterpret_cast<const float4*>(fb + (size_t)sy.lo * feat.sh + (size_t)sx.lo * feat.c);
-      const float4* tr = reinterpret_cast<const float4*>(fb + (size_t)sy.lo * feat.sh + (size_t)sx.hi * feat.c);
-      const float4* bl = reinterpret_cast<const float4*>(fb + (size_t)sy.hi * feat.sh + (size_t)sx.lo * feat.c);
-      const float4* br = reinterpret_cast<const float4*>(fb + (size_t)sy.hi * feat.sh + (size_t)sx.hi * feat.c);
+      const float4* rowt = reinterpret_cast<const float4*>(fb + (size_t)sy.lo * feat.sh);
+      const float4* rowb = reinterpret_cast<const float4*>(fb + (size_t)sy.hi * feat.sh);
+      if (NQ > 0) {
+        // bring (sx.lo, sx.hi) into the two cache slots, loading only the columns that are not there yet
+        auto load_col = [&](int slot, int col) {
+#pragma unroll
+          for (int qq = 0; qq < NQR; ++qq) {
+            ct[slot][qq] = __ldg(rowt + (size_t)col * C4 + qq * 32 + lane);
+            cb[slot][qq] = __ldg(rowb + (size_t)col * C4 + qq * 32 + lane);
+          }
+        };
+        auto move_col = [&](int dst, int src) {
+#pragma unroll
+          for (int qq = 0; qq < NQR; ++qq) {
+            ct[dst][qq] = ct[src][qq];
+            cb[dst][qq] = cb[src][qq];
+          }
+        };
+        if (sx.lo != c_lo) {
+          if (sx.lo == c_hi) {
+            if (sx.hi == c_lo) {          // swapped pair (a reversed box stepping back by one column)
+#pragma unroll
+              for (int qq = 0; qq < NQR; ++qq) {
+                const float4 t0 = ct[0][qq], t1 = cb[0][qq];
+                ct[0][qq] = ct[1][qq]; cb[0][qq] = cb[1][qq];
+                ct[1][qq] = t0; cb[1][qq] = t1;
+              }
+              c_hi = c_lo;
+            } else {
+              move_col(0, 1);
+              c_hi = -1;
+            }
+          } else if (sx.hi == c_lo && sx.hi != sx.lo) {
+            move_col(1, 0);
+            c_hi = c_lo;
+            load_col(0, sx.lo);
+          } else {
+            load_col(0, sx.lo);
+          }
+          c_lo = sx.lo;
+        }
+        if (sx.hi != c_hi) {
+          if (sx.hi == c_lo) move_col(1, 0);
+          else load_col(1, sx.hi);
+          c_hi = sx.hi;
+        }
+#pragma unroll
+        for (int qq = 0; qq < NQR; ++qq) {
+          const float4 a = ct[0][qq], bq = ct[1][qq], c = cb[0][qq], d = cb[1][qq];
+          float4 o;
+          o.x = lerp_rn(lerp_rn(a.x, bq.x, sx.lerp), lerp_rn(c.x, d.x, sx.lerp), sy.lerp);
+          o.y = lerp_rn(lerp_rn(a.y, bq.y, sx.lerp), lerp_rn(c.y, d.y, sx.lerp), sy.lerp);
+          o.z = lerp_rn(lerp_rn(a.z, bq.z, sx.lerp), lerp_rn(c.z, d.z, sx.lerp), sy.lerp);
+          o.w = lerp_rn(lerp_rn(a.w, bq.w, sx.lerp), lerp_rn(c.w, d.w, sx.lerp), sy.lerp);
+          if (rnd) o = make_float4(round_tf32(o.x), round_tf32(o.y), round_tf32(o.z), round_tf32(o.w));
+          const int q = qq * 32 + lane;
+          if (orow) op[q] = o;
+          if (HALF) hp[q] = make_uint2(pack_half2_sat(o.x, o.y), pack_half2_sat(o.z, o.w));
+        }
+        continue;
+      }
+      const float4* tl = rowt + (size_t)sx.lo * C4;
+      const float4* tr = rowt + (size_t)sx.hi * C4;
+      const float4* bl = rowb + (size_t)sx.lo * C4;
+      const float4* br = rowb + (size_t)sx.hi * C4;
       for (int q = lane; q < C4; q += 32) {
         const float4 a = __ldg(tl + q), bq = __ldg(tr + q), c = __ldg(bl + q), d = __ldg(br + q);
         float4 o;
@@ -223,7 +291,12 @@ extern "C" int myolo_roialign_fwd(const myolo_view* feat, const float* boxes, in
   MYOLO_CHECK_ARG((n_roi + rois_per_img - 1) / rois_per_img <= feat->n);
   const long long items = (long long)n_roi * pool;
   const int blocks = (int)max(1LL, min(ceil_div(items, 8), (long long)kNumSMs * 8));
-  roialign_fwd_kernel<false><<<blocks, 256, 0, as_stream(stream)>>>(to_v(feat), boxes, n_roi, rois_per_img, pool, to_v(out), round_tf32, to_v(out));
+  if (feat->c == 256)
+    roialign_fwd_kernel<false, 2><<<blocks, 256, 0, as_stream(stream)>>>(to_v(feat), boxes, n_roi, rois_per_img, pool, to_v(out), round_tf32, to_v(out));
+  else if (feat->c == 128)
+    roialign_fwd_kernel<false, 1><<<blocks, 256, 0, as_stream(stream)>>>(to_v(feat), boxes, n_roi, rois_per_img, pool, to_v(out), round_tf32, to_v(out));
+  else
+    roialign_fwd_kernel<false, 0><<<blocks, 256, 0, as_stream(stream)>>>(to_v(feat), boxes, n_roi, rois_per_img, pool, to_v(out), round_tf32, to_v(out));
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }
@@ -237,7 +310,12 @@ extern "C" int myolo_roialign_fwd_h(const myolo_view* feat, const float* boxes, 
   const long long items = (long long)n_roi * pool;
   const int blocks = (int)max(1LL, min(ceil_div(items, 8), (long long)kNumSMs * 8));
   V vo = out ? to_v(out) : V{nullptr, 0, 0, n_roi, pool, pool, feat->c};
-  roialign_fwd_kernel<true><<<blocks, 256, 0, as_stream(stream)>>>(to_v(feat), boxes, n_roi, rois_per_img, pool, vo, 0, to_v(out_half));
+  if (feat->c == 256)
+    roialign_fwd_kernel<true, 2><<<blocks, 256, 0, as_stream(stream)>>>(to_v(feat), boxes, n_roi, rois_per_img, pool, vo, 0, to_v(out_half));
+  else if (feat->c == 128)
+    roialign_fwd_kernel<true, 1><<<blocks, 256, 0, as_stream(stream)>>>(to_v(feat), boxes, n_roi, rois_per_img, pool, vo, 0, to_v(out_half));
+  else
+    roialign_fwd_kernel<true, 0><<<blocks, 256, 0, as_stream(stream)>>>(to_v(feat), boxes, n_roi, rois_per_img, pool, vo, 0, to_v(out_half));
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }

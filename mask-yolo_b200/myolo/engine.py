@@ -131,6 +131,8 @@ class Engine:
         self._side = torch.cuda.Stream(device=self.dev) if os.environ.get("MYOLO_BWD_STREAMS", "1") != "0" else None
         # third stream: the YOLO branch's backward next to the mask head's (Engine.backward)
         self._ystream = torch.cuda.Stream(device=self.dev) if os.environ.get("MYOLO_Y_OVERLAP", "1") != "0" else None
+        # ... started already behind the yolo loss, i.e. next to the mask head's forward as well (A/B switch)
+        self._y_early = os.environ.get("MYOLO_Y_EARLY", "1") != "0"
         # fourth stream: the mask head's filter gradients, off the data-gradient chain (Engine._backward_mask_h16)
         self._wstream = torch.cuda.Stream(device=self.dev) if (os.environ.get("MYOLO_W_OVERLAP", "0") != "0" and precision == "h16") else None
         self._w_used = False
@@ -797,7 +799,7 @@ class Engine:
             torch.cuda.current_stream().wait_event(self.inputs_ready)
             self.inputs_ready = None
 
-    def forward_training(self, inputs, learning_phase: bool = True):
+    def forward_training(self, inputs, learning_phase: bool = True, start_backward: bool = False):
         """mode='training' graph (model.py:844-901); learning_phase=False evaluates the same graph the way Keras
         validates (every BN on its moving statistics).  inputs as BatchGenerator yields them:
         [image, true_boxes [B,1,1,1,TB,4], yolo_target [B,G,G,NB,5+NC], gt_class_ids [B,M] i32,
@@ -814,6 +816,12 @@ class Engine:
         C.call("myolo_yolo_loss", yolo_target, A["yolo"], true_boxes, self.anchors, self.class_w, B, G, G, NB, NC, TB,
                self.scales, warm, float(lw.get("yolo_sum_loss", 1.0)), self.loss_yolo, A["dyolo"], self.ws_loss, st)
         out = dict(yolo_output=yolo, yolo_proposals=A["proposals"], yolo_sum_loss=self.loss_yolo[0])
+        self._y_started = False
+        if start_backward and learning_phase and self.with_mask and self._ystream is not None and self._y_early:
+            # train_step: the YOLO branch's backward (conv_23, blocks 14..7) needs nothing but the yolo loss, so it starts
+            # HERE on its own stream, next to the mask head's FORWARD and backward (12 ms of persistent tensor-core kernels)
+            # instead of next to the backward alone; Engine.backward picks the chain up again at block 6
+            self._start_yolo_branch_backward()
         if self.with_mask:
             gt_ids, gt_boxes, gt_masks = inputs[3], inputs[4], inputs[5]
             M = gt_ids.shape[1]
@@ -841,23 +849,22 @@ class Engine:
         chains meet at block 6, where d(C4) of the feature_map branch is added.  The filter-gradient kernels of blocks
         6..1 run on the side stream next to the data-gradient chain, as before."""
         A, B = self.A, self.B
-        C.record_py(self.grads.zero_)
         main, side, ys = torch.cuda.current_stream(), self._side, self._ystream
         overlap = self.with_mask and ys is not None
         blocks = list(reversed(BACKBONE_BLOCKS + YOLO_BLOCKS))
         n_y = len(YOLO_BLOCKS)
         if overlap:
-            e0, e1 = self._ev("y_fork"), self._ev("y_done")
-            C.record_py(lambda: (e0.record(main), ys.wait_event(e0)))          # after grads.zero_()
-            self._backward_conv23(ys, None, self.ws_y)
-            self._backward_blocks(blocks[:n_y], ys, None, self.ws_y)
-            C.record_py(lambda: e1.record(ys))
+            if not getattr(self, "_y_started", False):
+                self._start_yolo_branch_backward()
+            self._y_started = False
+            e1 = self._ev("y_done")
             self._backward_mask()
             if on_tail_ready is not None and not self._w_used:
                 C.record_py(on_tail_ready)
             C.record_py(lambda: main.wait_event(e1))
             self._backward_blocks(blocks[n_y:], main, side, self.ws)
         else:
+            C.record_py(self.grads.zero_)
             if self.with_mask:
                 self._backward_mask()
             if on_tail_ready is not None and not self._w_used:
@@ -877,6 +884,19 @@ class Engine:
             C.record_py(lambda: (ew.record(W), main.wait_event(ew)))
             if on_tail_ready is not None:
                 C.record_py(on_tail_ready)
+
+    def _start_yolo_branch_backward(self):
+        """Zeroes the flat gradient buffer and issues conv_23's and blocks 14..7's backward on the Y stream, behind
+        everything issued on the current stream so far (the yolo loss gradient)."""
+        main, ys = torch.cuda.current_stream(), self._ystream
+        blocks = list(reversed(BACKBONE_BLOCKS + YOLO_BLOCKS))
+        C.record_py(self.grads.zero_)
+        e0, e1 = self._ev("y_fork"), self._ev("y_done")
+        C.record_py(lambda: (e0.record(main), ys.wait_event(e0)))          # after grads.zero_()
+        self._backward_conv23(ys, None, self.ws_y)
+        self._backward_blocks(blocks[:len(YOLO_BLOCKS)], ys, None, self.ws_y)
+        C.record_py(lambda: e1.record(ys))
+        self._y_started = True
 
     def _ev(self, name):        # events are created once and re-recorded every step
         e = self._evs.get(name)
@@ -1268,7 +1288,7 @@ class Engine:
             else:
                 out = self._record_step(inputs, allreduce, key)
         else:
-            out = self.forward_training(inputs)
+            out = self.forward_training(inputs, start_backward=True)
             if allreduce is None:
                 self.backward()
             else:
@@ -1281,7 +1301,7 @@ class Engine:
         self._plan = None
         C.start_recording()
         try:
-            out = self.forward_training(inputs)
+            out = self.forward_training(inputs, start_backward=True)
             if allreduce is None:
                 self.backward()
             else:
