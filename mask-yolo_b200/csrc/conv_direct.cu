@@ -516,46 +516,73 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict_
   }
 }
 
-// stem conv wgrad (Cout == 32): lane = output channel, warp = pixel slot; the 27 input taps of a
-// pixel are warp-uniform broadcast loads.
+// stem conv wgrad (Cout == 32).  lane = output pixel, warp w of the block = output channels 4w .. 4w+3, 27 x 4 accumulators
+// per thread: one pixel costs a thread 27 scalar loads of x (neighbouring lanes 24 bytes apart) and one 16-byte load of
+// dy for 108 FMAs (54 packed FFMA2).  The first version (lane = output channel, one pixel per warp trip) issued 28 loads
+// and three 64-bit div / mod per 27 FMAs and took 155 us at the very end of the backward pass, after the last kernel it
+// could overlap with; the sums are reduced across the 32 pixels of a warp by shuffles at the end, one atomic per
+// (block, tap, channel).
 __global__ void __launch_bounds__(256) conv1_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
-                                                          float* __restrict__ dw, int B, int S, long long chunk) {
-  __shared__ float red[8 * 27 * 32];
+                                                          float* __restrict__ dw, int B, int S, unsigned chunks_per_block) {
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-  const int So = S / 2;
-  const long long total = (long long)B * So * So;
-  const long long p0 = blockIdx.x * chunk, p1 = min(total, p0 + chunk);
-  float acc[27];
+  const unsigned So = (unsigned)S / 2u;
+  const unsigned total = (unsigned)B * So * So;          // < 2^31 (checked on the host)
+  const unsigned c_beg = blockIdx.x * chunks_per_block, c_end = c_beg + chunks_per_block;
+  float acc[27][4];
 #pragma unroll
-  for (int i = 0; i < 27; ++i) acc[i] = 0.f;
-  for (long long p = p0 + wp; p < p1; p += 8) {
-    const int ox = (int)(p % So);
-    const long long t = p / So;
-    const int oy = (int)(t % So);
-    const int b = (int)(t / So);
-    const float g = __ldg(dy + (size_t)p * 32 + lane);
+  for (int t = 0; t < 27; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
+  // every load of a trip (TWO chunks of 32 pixels: 54 x values and two dy quads per thread) is issued before the first
+  // FMA: with one block of eight warps per SM the kernel lives on loads in flight (one chunk per trip: 129 us)
+  auto load_chunk = [&](unsigned ch, float (&xv)[27], float4& g) {
+    const unsigned p = ch * 32u + (unsigned)lane;
+    const bool live = ch < c_end && p < total;
+    const unsigned pp = live ? p : 0u;
+    const unsigned ox = pp % So, t2 = pp / So;
+    const unsigned oy = t2 % So, b = t2 / So;
+    g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) g = __ldg(reinterpret_cast<const float4*>(dy + (size_t)p * 32) + wp);
+    const float* xb = x + (size_t)b * S * S * 3;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
-      const int iy = oy * 2 + ky - 1;
-      if (iy < 0 || iy >= S) continue;
+      const int iy = (int)oy * 2 + ky - 1;
+      const bool vy = live && iy >= 0 && iy < S;
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
-        const int ix = ox * 2 + kx - 1;
-        if (ix < 0 || ix >= S) continue;
-        const float* px = x + (((size_t)b * S + iy) * S + ix) * 3;
+        const int ix = (int)ox * 2 + kx - 1;
+        const bool v = vy && ix >= 0 && ix < S;
+        const float* px = xb + ((size_t)(v ? iy : 0) * S + (v ? ix : 0)) * 3;
 #pragma unroll
-        for (int ci = 0; ci < 3; ++ci) acc[(ky * 3 + kx) * 3 + ci] = fmaf(__ldg(px + ci), g, acc[(ky * 3 + kx) * 3 + ci]);
+        for (int ci = 0; ci < 3; ++ci) xv[(ky * 3 + kx) * 3 + ci] = v ? __ldg(px + ci) : 0.f;
       }
     }
+  };
+  auto fma_chunk = [&](const float (&xv)[27], const float4& g) {
+#pragma unroll
+    for (int t = 0; t < 27; ++t) {
+      acc[t][0] = fmaf(xv[t], g.x, acc[t][0]);
+      acc[t][1] = fmaf(xv[t], g.y, acc[t][1]);
+      acc[t][2] = fmaf(xv[t], g.z, acc[t][2]);
+      acc[t][3] = fmaf(xv[t], g.w, acc[t][3]);
+    }
+  };
+  for (unsigned ch = c_beg; ch < c_end && ch * 32u < total; ch += 2) {
+    float xa[27], xb2[27];
+    float4 ga, gb;
+    load_chunk(ch, xa, ga);
+    load_chunk(ch + 1, xb2, gb);
+    fma_chunk(xa, ga);
+    fma_chunk(xb2, gb);
   }
+  // sum over the 32 pixels of the warp; lane 0 adds the block's share into dw[t][4*wp + c]
 #pragma unroll
-  for (int i = 0; i < 27; ++i) red[(wp * 27 + i) * 32 + lane] = acc[i];
-  __syncthreads();
-  for (int i = threadIdx.x; i < 27 * 32; i += 256) {
-    float s = 0.f;
+  for (int t = 0; t < 27; ++t) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s += red[j * 27 * 32 + i];
-    atomicAdd(dw + i, s);
+    for (int c = 0; c < 4; ++c) {
+      float v = acc[t][c];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0 && v != 0.f) atomicAdd(dw + t * 32 + wp * 4 + c, v);
+    }
   }
 }
 
@@ -577,10 +604,12 @@ extern "C" int myolo_conv1_wgrad(const float* x, const float* dy, float* dw, int
   MYOLO_CHECK_ARG(x && dy && dw && B > 0 && S > 0 && (S % 2) == 0);
   MYOLO_CHECK_ARG(Cout == 32);
   const long long total = (long long)B * (S / 2) * (S / 2);
-  const int blocks = (int)min(ceil_div(total, 64), (long long)kNumSMs * 4);
-  const long long chunk = ceil_div(total, blocks);
+  MYOLO_CHECK_ARG(total < (1LL << 31) - 64);
+  const long long chunks = ceil_div(total, 32);                       // 32 output pixels per warp trip
+  const int blocks = (int)max(1LL, min(chunks, (long long)kNumSMs));     // 173 registers: one block per SM
+  const unsigned per_block = (unsigned)ceil_div(chunks, blocks);
   MYOLO_CUDA(cudaMemsetAsync(dw, 0, 27 * 32 * sizeof(float), as_stream(stream)));
-  conv1_wgrad_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x, dy, dw, B, S, chunk);
+  conv1_wgrad_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x, dy, dw, B, S, per_block);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }
