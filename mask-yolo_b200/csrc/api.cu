@@ -1,9 +1,19 @@
+#include <stdlib.h>
 // api.cu -- library-level entry points (version, error string, device check).
 #include <stdarg.h>
 #include <string.h>
 #include "common.cuh"
 
 namespace myolo {
+
+int pdl_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("MYOLO_PDL");       // default on; MYOLO_PDL=0 launches every kernel fully serialised
+    mode = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return mode;
+}
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...) {
   va_list ap;

@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(256)
 colreduce_kernel(V x, V dy, const float* __restrict__ mean, const float* __restrict__ var,
                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int act,
                  double* __restrict__ out0, double* __restrict__ out1, long long chunk, Fin fin) {
+  pdl_entry();
   __shared__ float red[2][32][33];
   __shared__ int s_last;
   const int tid = threadIdx.x;
@@ -176,6 +177,7 @@ colreduce_kernel(V x, V dy, const float* __restrict__ mean, const float* __restr
 
 // arbitrary (small) C: one thread per channel, serial over pixels.  Only used for tiny tensors.
 __global__ void colsum_generic_kernel(V x, double* __restrict__ out) {
+  pdl_entry();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= x.c) return;
   const long long total = (long long)x.n * x.h * x.w;
@@ -185,6 +187,7 @@ __global__ void colsum_generic_kernel(V x, double* __restrict__ out) {
 }
 
 __global__ void finalize_div_kernel(double* __restrict__ s, float* __restrict__ out, int C, double inv, int accumulate) {
+  pdl_entry();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) {
     out[c] = (accumulate ? out[c] : 0.f) + (float)(s[c] * inv);
@@ -215,6 +218,7 @@ template <bool SPLIT>
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(V x, V y, V ylo, const float* __restrict__ mean, const float* __restrict__ var,
                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int act) {
+  pdl_entry();
   const int C4 = x.c >> 2;
   const FastDiv x_fc4 = x.fc4;
   const long long total = (long long)x.n * x.h * x.w * C4;
@@ -261,6 +265,7 @@ template <bool XH>
 __global__ void __launch_bounds__(256)
 bn_apply_h_kernel(V x, V y, V yh, const float* __restrict__ mean, const float* __restrict__ var,
                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int act, int same_geo) {
+  pdl_entry();
   const int C4 = x.c >> 2;
   const FastDiv x_fc4 = x.fc4;
   const long long total = (long long)x.n * x.h * x.w * C4;
@@ -289,6 +294,7 @@ bn_apply_h_kernel(V x, V y, V yh, const float* __restrict__ mean, const float* _
 }
 
 __global__ void __launch_bounds__(256) split_tf32_kernel(V src, V hi, V lo) {
+  pdl_entry();
   const int C4 = src.c >> 2;
   const FastDiv x_fc4 = src.fc4;
   const long long total = (long long)src.n * src.h * src.w * C4;
@@ -311,6 +317,7 @@ __global__ void __launch_bounds__(256)
 bn_bwd_dx_kernel(V x, V dy, V dx, const float* __restrict__ mean, const float* __restrict__ gamma,
                  const float* __restrict__ beta, int act, const float* __restrict__ coef, const float* __restrict__ oscale,
                  int same_geo) {
+  pdl_entry();
   const float os = (HALF && oscale) ? __ldg(oscale) : 1.f;
   const int C = x.c, C4 = C >> 2;
   const FastDiv x_fc4 = x.fc4;
@@ -363,6 +370,7 @@ bn_bwd_dx_kernel(V x, V dy, V dx, const float* __restrict__ mean, const float* _
 __global__ void bn_batch_coef_kernel(double* __restrict__ sums, const float* __restrict__ gamma, const float* __restrict__ var,
                                      float eps, double inv_count, const float* __restrict__ unscale, float* __restrict__ dgamma,
                                      float* __restrict__ dbeta, float* __restrict__ coef, int C) {
+  pdl_entry();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double S0 = sums[c], S1 = sums[C + c];
@@ -378,6 +386,7 @@ __global__ void bn_batch_coef_kernel(double* __restrict__ sums, const float* __r
 
 __global__ void __launch_bounds__(256)
 bn_batch_fix_hh_kernel(V z, V g, const float* __restrict__ mean, const float* __restrict__ coef, int same_geo) {
+  pdl_entry();
   const int C = z.c, C4 = C >> 2;
   const FastDiv x_fc4 = z.fc4;
   const long long total = (long long)z.n * z.h * z.w * C4;
@@ -421,6 +430,7 @@ __device__ __forceinline__ uint4 pack_half8(const float (&f)[8]) {
 __global__ void __launch_bounds__(256)
 bn_apply_hh8_kernel(V x, V yh, const float* __restrict__ mean, const float* __restrict__ var, const float* __restrict__ gamma,
                     const float* __restrict__ beta, float eps, int act, int same_geo, FastDiv fc8) {
+  pdl_entry();
   const int C8 = x.c >> 3;
   const long long total = (long long)x.n * x.h * x.w * C8;
   const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
@@ -462,6 +472,7 @@ bn_apply_hh8_kernel(V x, V yh, const float* __restrict__ mean, const float* __re
 
 __global__ void __launch_bounds__(256)
 bn_batch_fix_hh8_kernel(V z, V g, const float* __restrict__ mean, const float* __restrict__ coef, int same_geo, FastDiv fc8) {
+  pdl_entry();
   const int C = z.c, C8 = C >> 3;
   const long long total = (long long)z.n * z.h * z.w * C8;
   const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
@@ -500,6 +511,7 @@ bn_batch_fix_hh8_kernel(V z, V g, const float* __restrict__ mean, const float* _
 
 __global__ void bn_moving_update_kernel(const float* __restrict__ value, float* __restrict__ biased,
                                         float* __restrict__ moving, int C, float momentum, float corr, float debias) {
+  pdl_entry();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) {
     const float v = value[c] * corr;
@@ -518,6 +530,7 @@ struct MovingItem {
   float corr;
 };
 __global__ void bn_moving_update_batch_kernel(const MovingItem* __restrict__ items, float momentum, float debias) {
+  pdl_entry();
   const MovingItem it = items[blockIdx.x];
   for (int c = threadIdx.x; c < it.C; c += blockDim.x) {
     const float v = it.value[c] * it.corr;
@@ -528,6 +541,7 @@ __global__ void bn_moving_update_batch_kernel(const MovingItem* __restrict__ ite
 }
 
 __global__ void __launch_bounds__(256) view_copy_kernel(V src, V dst, int accumulate) {
+  pdl_entry();
   const int C4 = src.c >> 2;
   const FastDiv x_fc4 = src.fc4;
   const long long total = (long long)src.n * src.h * src.w * C4;
@@ -551,6 +565,7 @@ __global__ void __launch_bounds__(256) view_copy_kernel(V src, V dst, int accumu
 __global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
                                const float* __restrict__ mean, const float* __restrict__ var, float eps,
                                float* __restrict__ scale, float* __restrict__ shift, int C) {
+  pdl_entry();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) {
     const float s = gamma[c] * (1.f / sqrtf(var[c] + eps));
@@ -567,6 +582,7 @@ bn_act_bwd_from_output_kernel(V a, V dy, V dx, const float* __restrict__ gamma, 
                               const float* __restrict__ var, float eps, int act, double* __restrict__ out0,
                               double* __restrict__ out1, long long chunk, float* __restrict__ dgamma,
                               float* __restrict__ dbeta, float* __restrict__ dbias, int* __restrict__ ticket) {
+  pdl_entry();
   __shared__ float red[2][32][33];
   __shared__ int s_last;
   const int tid = threadIdx.x;
@@ -676,7 +692,7 @@ extern "C" int myolo_bn_stats(const myolo_view* x, float* mean, float* var, doub
   V vx = to_v(x);
   // single pass: sum and sum of squares in fp64 (per-thread fp32 partials over <= chunk/32 pixels)
   Fin fin{mean, var, nullptr, ws_ticket(ws, C), 1.0 / (double)total, 1, C};
-  colreduce_kernel<3><<<grid, 256, 0, st>>>(vx, vx, nullptr, nullptr, nullptr, nullptr, 0.f, 0, ws + kWsSums, ws + kWsSums + C, chunk, fin);
+  MYOLO_LAUNCH(colreduce_kernel<3>, grid, 256, 0, st, vx, vx, nullptr, nullptr, nullptr, nullptr, 0.f, 0, ws + kWsSums, ws + kWsSums + C, chunk, fin);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }
@@ -685,7 +701,7 @@ extern "C" int myolo_bn_apply(const myolo_view* x, const myolo_view* y, const fl
                               const float* gamma, const float* beta, float eps, int act, myolo_stream stream) {
   MYOLO_CHECK_ARG(view_ok(x) && view_ok(y) && same_shape(x, y) && mean && var && gamma && beta);
   const long long total = (long long)x->n * x->h * x->w * (x->c / 4);
-  bn_apply_kernel<false><<<ew_blocks(total), 256, 0, as_stream(stream)>>>(to_v(x), to_v(y), to_v(y), mean, var, gamma, beta, eps, act);
+  MYOLO_LAUNCH(bn_apply_kernel<false>, ew_blocks(total), 256, 0, as_stream(stream), to_v(x), to_v(y), to_v(y), mean, var, gamma, beta, eps, act);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }
@@ -696,7 +712,7 @@ extern "C" int myolo_bn_apply_split(const myolo_view* x, const myolo_view* y_hi,
   MYOLO_CHECK_ARG(view_ok(x) && view_ok(y_hi) && view_ok(y_lo) && same_shape(x, y_hi) && same_shape(x, y_lo));
   MYOLO_CHECK_ARG(mean && var && gamma && beta);
   const long long total = (long long)x->n * x->h * x->w * (x->c / 4);
-  bn_apply_kernel<true><<<ew_blocks(total), 256, 0, as_stream(stream)>>>(to_v(x), to_v(y_hi), to_v(y_lo), mean, var, gamma, beta, eps, act);
+  MYOLO_LAUNCH(bn_apply_kernel<true>, ew_blocks(total), 256, 0, as_stream(stream), to_v(x), to_v(y_hi), to_v(y_lo), mean, var, gamma, beta, eps, act);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }
@@ -710,7 +726,7 @@ extern "C" int myolo_bn_apply_h(const myolo_view* x, const myolo_view* y, const 
   V vy = y ? to_v(y) : to_v(x);
   if (!y) vy.p = nullptr;
   const int same_geo = x->sn == y_half->sn && x->sh == y_half->sh && (!y || (y->sn == x->sn && y->sh == x->sh));
-  bn_apply_h_kernel<false><<<ew_blocks(total), 256, 0, as_stream(stream)>>>(to_v(x), vy, to_v(y_half), mean, var, gamma, beta, eps, act, same_geo);
+  MYOLO_LAUNCH(bn_apply_h_kernel<false>, ew_blocks(total), 256, 0, as_stream(stream), to_v(x), vy, to_v(y_half), mean, var, gamma, beta, eps, act, same_geo);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }
@@ -726,12 +742,12 @@ extern "C" int myolo_bn_apply_hh(const myolo_view* x_half, const myolo_view* y_h
   const int same_geo = x_half->sn == y_half->sn && x_half->sh == y_half->sh;
   if (half8_ok(x_half) && half8_ok(y_half)) {
     const long long t8 = total / 2;
-    bn_apply_hh8_kernel<<<ew_blocks(t8 / 2 + 1), 256, 0, as_stream(stream)>>>(to_v(x_half), to_v(y_half), mean, var, gamma, beta, eps, act,
+    MYOLO_LAUNCH(bn_apply_hh8_kernel, ew_blocks(t8 / 2 + 1), 256, 0, as_stream(stream), to_v(x_half), to_v(y_half), mean, var, gamma, beta, eps, act,
                                                                            same_geo, make_fd((uint32_t)(x_half->c / 8)));
     MYOLO_CHECK_LAUNCH();
     return MYOLO_OK;
   }
-  bn_apply_h_kernel<true><<<ew_blocks(total), 256, 0, as_stream(stream)>>>(to_v(x_half), vy, to_v(y_half), mean, var, gamma, beta, eps, act, same_geo);
+  MYOLO_LAUNCH(bn_apply_h_kernel<true>, ew_blocks(total), 256, 0, as_stream(stream), to_v(x_half), vy, to_v(y_half), mean, var, gamma, beta, eps, act, same_geo);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }
@@ -749,15 +765,15 @@ extern "C" int myolo_bn_bwd_batch_fix_hh(const myolo_view* z_half, const myolo_v
   const int C = z_half->c;
   const long long total = (long long)z_half->n * z_half->h * z_half->w;
   float* coef = reinterpret_cast<float*>(ws + kWsCoef);
-  bn_batch_coef_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws + kWsSums, gamma, var, eps, 1.0 / (double)total, grad_unscale, dgamma, dbeta, coef, C);
+  MYOLO_LAUNCH(bn_batch_coef_kernel, (C + 127) / 128, 128, 0, st, ws + kWsSums, gamma, var, eps, 1.0 / (double)total, grad_unscale, dgamma, dbeta, coef, C);
   const int same_geo = z_half->sn == g_half->sn && z_half->sh == g_half->sh;
   if (half8_ok(z_half) && half8_ok(g_half)) {
-    bn_batch_fix_hh8_kernel<<<ew_blocks(total * (C / 8)), 256, 0, st>>>(to_v(z_half), to_v(g_half), mean, coef, same_geo,
+    MYOLO_LAUNCH(bn_batch_fix_hh8_kernel, ew_blocks(total * (C / 8)), 256, 0, st, to_v(z_half), to_v(g_half), mean, coef, same_geo,
                                                                         make_fd((uint32_t)(C / 8)));
     MYOLO_CHECK_LAUNCH();
     return MYOLO_OK;
   }
-  bn_batch_fix_hh_kernel<<<ew_blocks(total * (C / 4)), 256, 0, st>>>(to_v(z_half), to_v(g_half), mean, coef, same_geo);
+  MYOLO_LAUNCH(bn_batch_fix_hh_kernel, ew_blocks(total * (C / 4)), 256, 0, st, to_v(z_half), to_v(g_half), mean, coef, same_geo);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }
@@ -765,7 +781,7 @@ extern "C" int myolo_bn_bwd_batch_fix_hh(const myolo_view* z_half, const myolo_v
 extern "C" int myolo_split_tf32(const myolo_view* src, const myolo_view* hi, const myolo_view* lo, myolo_stream stream) {
   MYOLO_CHECK_ARG(view_ok(src) && view_ok(hi) && view_ok(lo) && same_shape(src, hi) && same_shape(src, lo));
   const long long total = (long long)src->n * src->h * src->w * (src->c / 4);
-  split_tf32_kernel<<<ew_blocks(total), 256, 0, as_stream(stream)>>>(to_v(src), to_v(hi), to_v(lo));
+  MYOLO_LAUNCH(split_tf32_kernel, ew_blocks(total), 256, 0, as_stream(stream), to_v(src), to_v(hi), to_v(lo));
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }
@@ -783,9 +799,9 @@ extern "C" int myolo_bn_bwd(const myolo_view* x, const myolo_view* dy, const myo
   reduce_grid(total, C, &grid, &chunk);
   float* coef = reinterpret_cast<float*>(ws + kWsCoef);   // 4*C floats
   Fin fin{dbeta, dgamma, coef, ws_ticket(ws, C), 1.0 / (double)total, train, C};
-  colreduce_kernel<2><<<grid, 256, 0, st>>>(to_v(x), to_v(dy), mean, var, gamma, beta, eps, act, ws + kWsSums, ws + kWsSums + C, chunk, fin);
+  MYOLO_LAUNCH(colreduce_kernel<2>, grid, 256, 0, st, to_v(x), to_v(dy), mean, var, gamma, beta, eps, act, ws + kWsSums, ws + kWsSums + C, chunk, fin);
   const int same_geo = x->sn == dy->sn && x->sh == dy->sh && x->sn == dx->sn && x->sh == dx->sh;
-  bn_bwd_dx_kernel<false><<<ew_blocks(total * (C / 4)), 256, 0, st>>>(to_v(x), to_v(dy), to_v(dx), mean, gamma, beta, act, coef, nullptr, same_geo);
+  MYOLO_LAUNCH(bn_bwd_dx_kernel<false>, ew_blocks(total * (C / 4)), 256, 0, st, to_v(x), to_v(dy), to_v(dx), mean, gamma, beta, act, coef, nullptr, same_geo);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }
@@ -804,9 +820,9 @@ extern "C" int myolo_bn_bwd_h(const myolo_view* x, const myolo_view* dy, const m
   reduce_grid(total, C, &grid, &chunk);
   float* coef = reinterpret_cast<float*>(ws + kWsCoef);
   Fin fin{dbeta, dgamma, coef, ws_ticket(ws, C), 1.0 / (double)total, train, C};
-  colreduce_kernel<2><<<grid, 256, 0, st>>>(to_v(x), to_v(dy), mean, var, gamma, beta, eps, act, ws + kWsSums, ws + kWsSums + C, chunk, fin);
+  MYOLO_LAUNCH(colreduce_kernel<2>, grid, 256, 0, st, to_v(x), to_v(dy), mean, var, gamma, beta, eps, act, ws + kWsSums, ws + kWsSums + C, chunk, fin);
   const int same_geo = x->sn == dy->sn && x->sh == dy->sh && x->sn == dx_half->sn && x->sh == dx_half->sh;
-  bn_bwd_dx_kernel<true><<<ew_blocks(total * (C / 4)), 256, 0, st>>>(to_v(x), to_v(dy), to_v(dx_half), mean, gamma, beta, act, coef, out_scale, same_geo);
+  MYOLO_LAUNCH(bn_bwd_dx_kernel<true>, ew_blocks(total * (C / 4)), 256, 0, st, to_v(x), to_v(dy), to_v(dx_half), mean, gamma, beta, act, coef, out_scale, same_geo);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }
@@ -825,9 +841,9 @@ extern "C" int myolo_bn_bwd_hh(const myolo_view* x, const myolo_view* dy_half, c
   reduce_grid(total, C, &grid, &chunk);
   float* coef = reinterpret_cast<float*>(ws + kWsCoef);
   Fin fin{dbeta, dgamma, coef, ws_ticket(ws, C), 1.0 / (double)total, train, C, grad_unscale};
-  colreduce_kernel<2, true><<<grid, 256, 0, st>>>(to_v(x), to_v(dy_half), mean, var, gamma, beta, eps, act, ws + kWsSums, ws + kWsSums + C, chunk, fin);
+  MYOLO_LAUNCH((colreduce_kernel<2, true>), grid, 256, 0, st, to_v(x), to_v(dy_half), mean, var, gamma, beta, eps, act, ws + kWsSums, ws + kWsSums + C, chunk, fin);
   const int same_geo = x->sn == dy_half->sn && x->sh == dy_half->sh && x->sn == dx_half->sn && x->sh == dx_half->sh;
-  bn_bwd_dx_kernel<true, true><<<ew_blocks(total * (C / 4)), 256, 0, st>>>(to_v(x), to_v(dy_half), to_v(dx_half), mean, gamma, beta, act, coef,
+  MYOLO_LAUNCH((bn_bwd_dx_kernel<true, true>), ew_blocks(total * (C / 4)), 256, 0, st, to_v(x), to_v(dy_half), to_v(dx_half), mean, gamma, beta, act, coef,
                                                                          nullptr, same_geo);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
@@ -844,7 +860,7 @@ extern "C" int myolo_bn_moving_update(const float* value, float* biased, float* 
     for (int i = 0; i < step && pw > 1e-300; ++i) pw *= (double)momentum;
     debias = 1.0 - pw;
   }
-  bn_moving_update_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(value, biased, moving, C, momentum, (float)corr, (float)debias);
+  MYOLO_LAUNCH(bn_moving_update_kernel, (C + 127) / 128, 128, 0, as_stream(stream), value, biased, moving, C, momentum, (float)corr, (float)debias);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }
@@ -860,11 +876,11 @@ extern "C" int myolo_colsum(const myolo_view* x, float* out, double* ws, myolo_s
     long long chunk;
     reduce_grid(total, C, &grid, &chunk);
     Fin fin{out, nullptr, nullptr, ws_ticket(ws, C), 1.0, 0, C};
-    colreduce_kernel<0><<<grid, 256, 0, st>>>(vx, vx, nullptr, nullptr, nullptr, nullptr, 0.f, 0, ws + kWsSums, nullptr, chunk, fin);
+    MYOLO_LAUNCH(colreduce_kernel<0>, grid, 256, 0, st, vx, vx, nullptr, nullptr, nullptr, nullptr, 0.f, 0, ws + kWsSums, nullptr, chunk, fin);
   } else {
     dim3 grid((C + 63) / 64, (unsigned)min(total, 256LL));
-    colsum_generic_kernel<<<grid, 64, 0, st>>>(vx, ws + kWsSums);
-    finalize_div_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws + kWsSums, out, C, 1.0, 0);
+    MYOLO_LAUNCH(colsum_generic_kernel, grid, 64, 0, st, vx, ws + kWsSums);
+    MYOLO_LAUNCH(finalize_div_kernel, (C + 127) / 128, 128, 0, st, ws + kWsSums, out, C, 1.0, 0);
   }
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
@@ -873,7 +889,7 @@ extern "C" int myolo_colsum(const myolo_view* x, float* out, double* ws, myolo_s
 extern "C" int myolo_view_copy(const myolo_view* src, const myolo_view* dst, int accumulate, myolo_stream stream) {
   MYOLO_CHECK_ARG(view_ok(src) && view_ok(dst) && same_shape(src, dst));
   const long long total = (long long)src->n * src->h * src->w * (src->c / 4);
-  view_copy_kernel<<<ew_blocks(total), 256, 0, as_stream(stream)>>>(to_v(src), to_v(dst), accumulate);
+  MYOLO_LAUNCH(view_copy_kernel, ew_blocks(total), 256, 0, as_stream(stream), to_v(src), to_v(dst), accumulate);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }
@@ -881,7 +897,7 @@ extern "C" int myolo_view_copy(const myolo_view* src, const myolo_view* dst, int
 extern "C" int myolo_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
                              float* scale, float* shift, int C, myolo_stream stream) {
   MYOLO_CHECK_ARG(gamma && beta && mean && var && scale && shift && C > 0);
-  bn_fold_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(gamma, beta, mean, var, eps, scale, shift, C);
+  MYOLO_LAUNCH(bn_fold_kernel, (C + 127) / 128, 128, 0, as_stream(stream), gamma, beta, mean, var, eps, scale, shift, C);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }
@@ -897,7 +913,7 @@ extern "C" int myolo_bn_act_bwd_from_output(const myolo_view* a, const myolo_vie
   dim3 grid;
   long long chunk;
   reduce_grid(total, C, &grid, &chunk);
-  bn_act_bwd_from_output_kernel<<<grid, 256, 0, st>>>(to_v(a), to_v(dy), to_v(dx), gamma, beta, var, eps, act, ws + kWsSums, ws + kWsSums + C, chunk,
+  MYOLO_LAUNCH(bn_act_bwd_from_output_kernel, grid, 256, 0, st, to_v(a), to_v(dy), to_v(dx), gamma, beta, var, eps, act, ws + kWsSums, ws + kWsSums + C, chunk,
                                                       dgamma, dbeta, dbias, ws_ticket(ws, C));
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
@@ -907,7 +923,7 @@ extern "C" int myolo_bn_moving_update_batch(const void* items_dev, int n_items, 
   MYOLO_CHECK_ARG(items_dev && n_items > 0 && step >= 1);
   double pw = 1.0;
   for (int i = 0; i < step && pw > 1e-300; ++i) pw *= (double)momentum;
-  bn_moving_update_batch_kernel<<<n_items, 256, 0, as_stream(stream)>>>(reinterpret_cast<const MovingItem*>(items_dev), momentum,
+  MYOLO_LAUNCH(bn_moving_update_batch_kernel, n_items, 256, 0, as_stream(stream), reinterpret_cast<const MovingItem*>(items_dev), momentum,
                                                                          (float)(1.0 - pw));
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
@@ -917,6 +933,7 @@ namespace myolo {
 __global__ void bn_epi_finalize_kernel(double* __restrict__ sums, const float* __restrict__ gamma, const float* __restrict__ var,
                                        float eps, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
                                        int C, const float* __restrict__ unscale) {
+  pdl_entry();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) {
     const double us = unscale ? (double)__ldg(unscale) : 1.0;   // the gradient tensor carried a loss scale
@@ -934,7 +951,7 @@ __global__ void bn_epi_finalize_kernel(double* __restrict__ sums, const float* _
 extern "C" int myolo_bn_epi_finalize_s(double* sums, const float* gamma, const float* var, float eps, float* dgamma,
                                        float* dbeta, float* dbias, int C, const float* unscale, myolo_stream stream) {
   MYOLO_CHECK_ARG(sums && gamma && var && dgamma && dbeta && C > 0);
-  myolo::bn_epi_finalize_kernel<<<(C + 127) / 128, 128, 0, myolo::as_stream(stream)>>>(sums, gamma, var, eps, dgamma, dbeta, dbias, C, unscale);
+  MYOLO_LAUNCH(myolo::bn_epi_finalize_kernel, (C + 127) / 128, 128, 0, myolo::as_stream(stream), sums, gamma, var, eps, dgamma, dbeta, dbias, C, unscale);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }

@@ -40,6 +40,33 @@ static inline long long ceil_div(long long a, long long b) { return (a + b - 1) 
 
 constexpr int kNumSMs = 148;  // B200
 
+// ---- programmatic dependent launch (default; MYOLO_PDL=0 switches it off): the ~170 small kernels of the backbone form a serial chain on one
+// stream; with the attribute below a kernel's CTAs are dispatched while its predecessor drains, and pdl_entry() -- the
+// first statement of every kernel launched this way -- holds them until the predecessor has completed and its memory
+// is visible.  Same results, same ordering; what is saved is the launch latency between dependent kernels.  Without the
+// attribute (MYOLO_PDL=0) both instructions of pdl_entry() are no-ops.  Measured: +0.6 % on the step (profiles/r02_pdl_ab.txt).
+int pdl_mode();
+template <typename... KP, typename... A>
+static inline void launch_k(void (*kernel)(KP...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_mode() ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KP>(args)...);   // a failure is picked up by MYOLO_CHECK_LAUNCH
+}
+#define MYOLO_LAUNCH(kernel, grid, block, smem, st, ...) \
+  myolo::launch_k(kernel, dim3(grid), dim3(block), (size_t)(smem), st, __VA_ARGS__)
+__device__ __forceinline__ void pdl_entry() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // round-to-nearest fp32 -> tf32 (10-bit mantissa, low 13 bits zero).  tcgen05 kind::tf32 reads fp32
 // words and ignores the low mantissa bits, so producers of tensor-core operands round here to keep
 // the error unbiased.

@@ -59,6 +59,7 @@ template <int S, bool INBN, bool STATS>
 __global__ void __launch_bounds__(256) dw_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                      float* __restrict__ y, int H, int W, int C, int Ho, int Wo,
                                                      int ntx, long long xsn, long long xsh, DwBn bn, DwStats st) {
+  pdl_entry();
   constexpr int IT = 7 * S + 3;
   constexpr int kTile = IT * IT * 32, kRed = 2 * 32 * 33;
   __shared__ __align__(16) float tile[kTile > kRed ? kTile : kRed];
@@ -180,6 +181,7 @@ template <int S, int TY, bool INBN, bool STATS, bool FLIP>
 __global__ void __launch_bounds__(256, MYOLO_DW_MINBLK) dw_strip_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                        float* __restrict__ y, int B, int H, int W, int C, int Ho, int Wo,
                                                        long long xsn, long long xsh, DwBn bn, DwStats st) {
+  pdl_entry();
   __shared__ float red[STATS ? 2 * 32 * 33 : 1];
   __shared__ int s_last;
   const int tid = threadIdx.x;
@@ -286,6 +288,7 @@ template <int S, bool INBN>
 __global__ void __launch_bounds__(256) dw_bwd_filter_strip_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                                   float* __restrict__ dw, int B, int H, int W, int C, int Ho,
                                                                   int Wo, int rows, long long xsn, long long xsh, DwBn bn) {
+  pdl_entry();
   __shared__ float red[9 * 32 * 33];
   const int tid = threadIdx.x;
   const int cq = tid & 7, pg = tid >> 3;
@@ -365,6 +368,7 @@ template <int S>
 __global__ void __launch_bounds__(256) dw_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ w,
                                                           float* __restrict__ dx, int B, int H, int W, int C, int Ho,
                                                           int Wo) {
+  pdl_entry();
   const unsigned C4 = C >> 2;
   const unsigned total = (unsigned)B * H * W * C4;   // < 2^31 (checked by the caller): 32-bit index math
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -406,6 +410,7 @@ template <int S, bool INBN>
 __global__ void __launch_bounds__(256) dw_bwd_filter_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                             float* __restrict__ dw, int B, int H, int W, int C, int Ho,
                                                             int Wo, long long chunk, long long xsn, long long xsh, DwBn bn) {
+  pdl_entry();
   __shared__ float red[9 * 32 * 33];
   const int tid = threadIdx.x;
   const int cq = tid & 7, pg = tid >> 3;
@@ -468,6 +473,7 @@ __global__ void __launch_bounds__(256) dw_bwd_filter_kernel(const float* __restr
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         float* __restrict__ y, int B, int S, int Cout) {
+  pdl_entry();
   extern __shared__ __align__(16) float ws[];  // [27][Cout]
   for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) ws[i] = w[i];
   __syncthreads();
@@ -524,6 +530,7 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict_
 // (block, tap, channel).
 __global__ void __launch_bounds__(256) conv1_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                           float* __restrict__ dw, int B, int S, unsigned chunks_per_block) {
+  pdl_entry();
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
   const unsigned So = (unsigned)S / 2u;
   const unsigned total = (unsigned)B * So * So;          // < 2^31 (checked on the host)
@@ -595,7 +602,7 @@ extern "C" int myolo_conv1_fwd(const float* x, const float* w, float* y, int B, 
   MYOLO_CHECK_ARG((long long)B * (S / 2) * (S / 2) * (Cout / 8) < (1LL << 31));
   const long long total = (long long)B * (S / 2) * (S / 2) * (Cout / 8);
   const int blocks = (int)min(ceil_div(total, 256), (long long)kNumSMs * 16);
-  conv1_fwd_kernel<<<blocks, 256, 27 * Cout * sizeof(float), as_stream(stream)>>>(x, w, y, B, S, Cout);
+  MYOLO_LAUNCH(conv1_fwd_kernel, blocks, 256, 27 * Cout * sizeof(float), as_stream(stream), x, w, y, B, S, Cout);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }
@@ -609,7 +616,7 @@ extern "C" int myolo_conv1_wgrad(const float* x, const float* dy, float* dw, int
   const int blocks = (int)max(1LL, min(chunks, (long long)kNumSMs));     // 173 registers: one block per SM
   const unsigned per_block = (unsigned)ceil_div(chunks, blocks);
   MYOLO_CUDA(cudaMemsetAsync(dw, 0, 27 * 32 * sizeof(float), as_stream(stream)));
-  conv1_wgrad_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x, dy, dw, B, S, per_block);
+  MYOLO_LAUNCH(conv1_wgrad_kernel, blocks, 256, 0, as_stream(stream), x, dy, dw, B, S, per_block);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }
@@ -644,7 +651,7 @@ extern "C" int myolo_dwconv3x3_fwd_bn(const myolo_view* xv, const float* w, floa
     use_tile = (e && atoi(e)) ? 1 : 0;
   }
   if (use_tile) {
-#define MYOLO_DW_FWD(S_, I_, T_) dw_fwd_kernel<S_, I_, T_><<<grid, 256, 0, cs>>>(x, w, y, H, W, C, Ho, Wo, ntx, xv->sn, xv->sh, bn, st)
+#define MYOLO_DW_FWD(S_, I_, T_) MYOLO_LAUNCH((dw_fwd_kernel<S_, I_, T_>), grid, 256, 0, cs, x, w, y, H, W, C, Ho, Wo, ntx, xv->sn, xv->sh, bn, st)
     if (stride == 1) {
       if (inbn && stats) MYOLO_DW_FWD(1, true, true);
       else if (inbn) MYOLO_DW_FWD(1, true, false);
@@ -661,7 +668,7 @@ extern "C" int myolo_dwconv3x3_fwd_bn(const myolo_view* xv, const float* w, floa
     constexpr int TY1 = MYOLO_DW_TY1, TY2 = 4;
     dim3 g1((unsigned)ceil_div((long long)B * Wo, 32), C / 32, (unsigned)ceil_div(Ho, stride == 1 ? TY1 : TY2));
 #define MYOLO_DW_STRIP(S_, T_, I_, ST_) \
-  dw_strip_kernel<S_, T_, I_, ST_, false><<<g1, 256, 0, cs>>>(x, w, y, B, H, W, C, Ho, Wo, xv->sn, xv->sh, bn, st)
+  MYOLO_LAUNCH((dw_strip_kernel<S_, T_, I_, ST_, false>), g1, 256, 0, cs, x, w, y, B, H, W, C, Ho, Wo, xv->sn, xv->sh, bn, st)
     if (stride == 1) {
       if (inbn && stats) MYOLO_DW_STRIP(1, TY1, true, true);
       else if (inbn) MYOLO_DW_STRIP(1, TY1, true, false);
@@ -701,12 +708,12 @@ extern "C" int myolo_dwconv3x3_bwd_data(const float* dy, const float* w, float* 
     dim3 grid((unsigned)ceil_div((long long)B * W, 32), C / 32, (unsigned)ceil_div(H, TY));
     DwBn bn{};
     DwStats st{};
-    dw_strip_kernel<1, TY, false, false, true><<<grid, 256, 0, as_stream(stream)>>>(dy, w, dx, B, H, W, C, H, W,
+    MYOLO_LAUNCH((dw_strip_kernel<1, TY, false, false, true>), grid, 256, 0, as_stream(stream), dy, w, dx, B, H, W, C, H, W,
                                                                                      (long long)H * W * C, (long long)W * C, bn, st);
   } else if (stride == 1)
-    dw_bwd_data_kernel<1><<<blocks, 256, 0, as_stream(stream)>>>(dy, w, dx, B, H, W, C, Ho, Wo);
+    MYOLO_LAUNCH(dw_bwd_data_kernel<1>, blocks, 256, 0, as_stream(stream), dy, w, dx, B, H, W, C, Ho, Wo);
   else
-    dw_bwd_data_kernel<2><<<blocks, 256, 0, as_stream(stream)>>>(dy, w, dx, B, H, W, C, Ho, Wo);
+    MYOLO_LAUNCH(dw_bwd_data_kernel<2>, blocks, 256, 0, as_stream(stream), dy, w, dx, B, H, W, C, Ho, Wo);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }
@@ -742,21 +749,21 @@ extern "C" int myolo_dwconv3x3_bwd_filter_bn(const myolo_view* xv, const float* 
     nstrips = ceil_div(Ho, rows);
     dim3 g2((unsigned)coltiles, cgroups, (unsigned)nstrips);
     if (stride == 1) {
-      if (inbn) dw_bwd_filter_strip_kernel<1, true><<<g2, 256, 0, cs>>>(x, dy, dw, B, H, W, C, Ho, Wo, rows, xv->sn, xv->sh, bn);
-      else dw_bwd_filter_strip_kernel<1, false><<<g2, 256, 0, cs>>>(x, dy, dw, B, H, W, C, Ho, Wo, rows, xv->sn, xv->sh, bn);
+      if (inbn) MYOLO_LAUNCH((dw_bwd_filter_strip_kernel<1, true>), g2, 256, 0, cs, x, dy, dw, B, H, W, C, Ho, Wo, rows, xv->sn, xv->sh, bn);
+      else MYOLO_LAUNCH((dw_bwd_filter_strip_kernel<1, false>), g2, 256, 0, cs, x, dy, dw, B, H, W, C, Ho, Wo, rows, xv->sn, xv->sh, bn);
     } else {
-      if (inbn) dw_bwd_filter_strip_kernel<2, true><<<g2, 256, 0, cs>>>(x, dy, dw, B, H, W, C, Ho, Wo, rows, xv->sn, xv->sh, bn);
-      else dw_bwd_filter_strip_kernel<2, false><<<g2, 256, 0, cs>>>(x, dy, dw, B, H, W, C, Ho, Wo, rows, xv->sn, xv->sh, bn);
+      if (inbn) MYOLO_LAUNCH((dw_bwd_filter_strip_kernel<2, true>), g2, 256, 0, cs, x, dy, dw, B, H, W, C, Ho, Wo, rows, xv->sn, xv->sh, bn);
+      else MYOLO_LAUNCH((dw_bwd_filter_strip_kernel<2, false>), g2, 256, 0, cs, x, dy, dw, B, H, W, C, Ho, Wo, rows, xv->sn, xv->sh, bn);
     }
     MYOLO_CHECK_LAUNCH();
     return MYOLO_OK;
   }
   if (stride == 1) {
-    if (inbn) dw_bwd_filter_kernel<1, true><<<grid, 256, 0, cs>>>(x, dy, dw, B, H, W, C, Ho, Wo, chunk, xv->sn, xv->sh, bn);
-    else dw_bwd_filter_kernel<1, false><<<grid, 256, 0, cs>>>(x, dy, dw, B, H, W, C, Ho, Wo, chunk, xv->sn, xv->sh, bn);
+    if (inbn) MYOLO_LAUNCH((dw_bwd_filter_kernel<1, true>), grid, 256, 0, cs, x, dy, dw, B, H, W, C, Ho, Wo, chunk, xv->sn, xv->sh, bn);
+    else MYOLO_LAUNCH((dw_bwd_filter_kernel<1, false>), grid, 256, 0, cs, x, dy, dw, B, H, W, C, Ho, Wo, chunk, xv->sn, xv->sh, bn);
   } else {
-    if (inbn) dw_bwd_filter_kernel<2, true><<<grid, 256, 0, cs>>>(x, dy, dw, B, H, W, C, Ho, Wo, chunk, xv->sn, xv->sh, bn);
-    else dw_bwd_filter_kernel<2, false><<<grid, 256, 0, cs>>>(x, dy, dw, B, H, W, C, Ho, Wo, chunk, xv->sn, xv->sh, bn);
+    if (inbn) MYOLO_LAUNCH((dw_bwd_filter_kernel<2, true>), grid, 256, 0, cs, x, dy, dw, B, H, W, C, Ho, Wo, chunk, xv->sn, xv->sh, bn);
+    else MYOLO_LAUNCH((dw_bwd_filter_kernel<2, false>), grid, 256, 0, cs, x, dy, dw, B, H, W, C, Ho, Wo, chunk, xv->sn, xv->sh, bn);
   }
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;

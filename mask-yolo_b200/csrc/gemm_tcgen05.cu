@@ -34,6 +34,7 @@ template <int BN>
 __global__ void __launch_bounds__(kThreads)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C,
                long long ldc, long long M, int N, int K, int ntaps, TapShifts sh, Epi ep, int stages) {
+  pdl_entry();
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * 8 + 1];
   __shared__ uint32_t tmem_slot;
@@ -189,6 +190,7 @@ __global__ void __launch_bounds__(kThreads)
 tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmD,
                 float* __restrict__ dW, long long M, int N, int K, TapShifts sh, long long chunk, int ntn,
                 int transpose_out, int stages) {
+  pdl_entry();
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * 8 + 1];
   __shared__ uint32_t tmem_slot;
@@ -303,6 +305,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // copies [hi | hi | lo], each `total` floats, matching the tap triple (A_hi,B_hi) (A_lo,B_hi) (A_hi,B_lo).
 __global__ void prep_weights_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols,
                                     int transpose, int round, size_t total) {
+  pdl_entry();
   __shared__ float t[32][33];
   const float* ip = in + (size_t)blockIdx.z * rows * cols;
   float* op = out + (size_t)blockIdx.z * rows * cols;
@@ -488,7 +491,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, float* C, l
     attr_set = true;
   }
   dim3 grid((unsigned)ceil_div(M, BM), (unsigned)(N / BN));
-  tc_gemm_kernel<BN><<<grid, kThreads, smem, st>>>(ta, tb, C, ldc, M, N, K, ntaps, sh, ep, stages);
+  MYOLO_LAUNCH(tc_gemm_kernel<BN>, grid, kThreads, smem, st, ta, tb, C, ldc, M, N, K, ntaps, sh, ep, stages);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }
@@ -522,7 +525,7 @@ static int launch_wgrad_n(const CUtensorMap& ta, const CUtensorMap& td, float* d
     attr_set = true;
   }
   dim3 grid((unsigned)nsplit, (unsigned)(ntk * ntn), (unsigned)ntaps);
-  tc_wgrad_kernel<BN, NACC><<<grid, kThreads, smem, st>>>(ta, td, dW, M, N, K, sh, chunk, ntn, transpose_out, stages);
+  MYOLO_LAUNCH((tc_wgrad_kernel<BN, NACC>), grid, kThreads, smem, st, ta, td, dW, M, N, K, sh, chunk, ntn, transpose_out, stages);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }
@@ -643,6 +646,7 @@ struct PrepJob {
   int out_total;   // elements between the hi / hi / lo copies of mode 2 (0 = ntaps*rows*cols)
 };
 __global__ void prep_weights_batch_kernel(const PrepJob* __restrict__ jobs, int n_jobs) {
+  pdl_entry();
   __shared__ float t[32][33];
   int lo = 0, hi = n_jobs - 1;
   while (lo < hi) {
@@ -691,6 +695,7 @@ __global__ void prep_weights_batch_kernel(const PrepJob* __restrict__ jobs, int 
 // dst[r][0..cols) = src[r][0..cols) for two row pitches (columns of dst beyond `cols` are left alone)
 __global__ void copy_cols_kernel(const float* __restrict__ src, long long src_ld, float* __restrict__ dst, long long dst_ld,
                                  long long rows, int cols) {
+  pdl_entry();
   const long long total = rows * cols;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / cols;
@@ -706,6 +711,7 @@ namespace tc {
 // tile i of the compact buffer <-> tile list[i] of the full buffer, 16 bytes per thread and step
 __global__ void __launch_bounds__(256) copy_tiles_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst,
                                                          const int* __restrict__ list, long long tile_vec, int scatter) {
+  pdl_entry();
   const long long t = __ldg(list + blockIdx.y);
   const uint4* s = src + (scatter ? (long long)blockIdx.y : t) * tile_vec;
   uint4* d = dst + (scatter ? t : (long long)blockIdx.y) * tile_vec;
@@ -720,7 +726,7 @@ extern "C" int myolo_copy_tiles(const void* src, void* dst, const int* list, int
   MYOLO_CHECK_ARG(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0);
   const long long tv = tile_bytes / 16;
   dim3 grid((unsigned)max(1LL, min(ceil_div(tv, 256), 64LL)), (unsigned)n_list);
-  copy_tiles_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), list,
+  MYOLO_LAUNCH(copy_tiles_kernel, grid, 256, 0, as_stream(stream), reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), list,
                                                          tv, scatter);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
@@ -730,14 +736,14 @@ extern "C" int myolo_copy_cols(const float* src, long long src_ld, float* dst, l
                                myolo_stream stream) {
   MYOLO_CHECK_ARG(src && dst && rows > 0 && cols > 0 && src_ld >= cols && dst_ld >= cols);
   const int blocks = (int)max(1LL, min(ceil_div(rows * cols, 256), (long long)kNumSMs * 8));
-  copy_cols_kernel<<<blocks, 256, 0, as_stream(stream)>>>(src, src_ld, dst, dst_ld, rows, cols);
+  MYOLO_LAUNCH(copy_cols_kernel, blocks, 256, 0, as_stream(stream), src, src_ld, dst, dst_ld, rows, cols);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }
 
 extern "C" int myolo_prep_weights_batch(const void* jobs_dev, int n_jobs, int total_tiles, myolo_stream stream) {
   MYOLO_CHECK_ARG(jobs_dev && n_jobs > 0 && total_tiles > 0);
-  prep_weights_batch_kernel<<<total_tiles, dim3(32, 8), 0, as_stream(stream)>>>(reinterpret_cast<const PrepJob*>(jobs_dev), n_jobs);
+  MYOLO_LAUNCH(prep_weights_batch_kernel, total_tiles, dim3(32, 8), 0, as_stream(stream), reinterpret_cast<const PrepJob*>(jobs_dev), n_jobs);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }
@@ -747,6 +753,7 @@ namespace tc {
 // half staging of a weight block: out[t][c][r] = half(in[t][r][c]) (transpose) or out = half(in)
 __global__ void prep_weights_h_kernel(const float* __restrict__ in, uint16_t* __restrict__ out, int rows, int cols,
                                       int transpose) {
+  pdl_entry();
   __shared__ float t[32][33];
   const float* ip = in + (size_t)blockIdx.z * rows * cols;
   uint16_t* op = out + (size_t)blockIdx.z * rows * cols;
@@ -775,7 +782,7 @@ extern "C" int myolo_prep_weights_h(const float* in, void* out_half, int ntaps, 
                                     myolo_stream stream) {
   MYOLO_CHECK_ARG(in && out_half && (const void*)in != out_half && ntaps > 0 && rows > 0 && cols > 0);
   dim3 grid((cols + 31) / 32, (rows + 31) / 32, ntaps), block(32, 8);
-  prep_weights_h_kernel<<<grid, block, 0, as_stream(stream)>>>(in, reinterpret_cast<uint16_t*>(out_half), rows, cols, transpose);
+  MYOLO_LAUNCH(prep_weights_h_kernel, grid, block, 0, as_stream(stream), in, reinterpret_cast<uint16_t*>(out_half), rows, cols, transpose);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
 }
@@ -784,7 +791,7 @@ extern "C" int myolo_prep_weights(const float* in, float* out, int ntaps, int ro
                                   int round_tf32, myolo_stream stream) {
   MYOLO_CHECK_ARG(in && out && in != out && ntaps > 0 && rows > 0 && cols > 0 && round_tf32 >= 0 && round_tf32 <= 2);
   dim3 grid((cols + 31) / 32, (rows + 31) / 32, ntaps), block(32, 8);
-  prep_weights_kernel<<<grid, block, 0, as_stream(stream)>>>(in, out, rows, cols, transpose, round_tf32,
+  MYOLO_LAUNCH(prep_weights_kernel, grid, block, 0, as_stream(stream), in, out, rows, cols, transpose, round_tf32,
                                                              (size_t)ntaps * rows * cols);
   MYOLO_CHECK_LAUNCH();
   return MYOLO_OK;
