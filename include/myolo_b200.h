@@ -434,6 +434,17 @@ int myolo_shapes_raster(const int* specs, int B, int S, int MS, int M, int TB, i
                         unsigned char* image_u8, unsigned char* gt_masks, int* gt_class_ids, int* gt_boxes,
                         float* gt_boxes_f, myolo_stream stream);
 
+/* ---- VIA polygon annotations on the device: RiceDataset.load_mask, example/rice/rice_dataset.py:135-159
+ * (`rr, cc = skimage.draw.polygon(all_points_y, all_points_x); mask[rr, cc, i] = 1` per instance) for all instances of
+ * one image in one launch.  verts_y / verts_x: the concatenated float64 vertex rows / columns of the instances,
+ * offsets [n_inst + 1] int32 (instance i owns vertices offsets[i] .. offsets[i+1]-1), all device pointers.
+ * masks [H, W, M] bytes (the reference's layout), channels >= n_inst zero; n_inst <= M <= 128, masks 4-byte aligned.
+ * Inclusion rule: skimage's float64 crossing-number test, restated in csrc/polygon_pip.h (scikit-image is absent here:
+ * parity pinned to the oracle's restatement, not to the library).  Pixels outside the image are clipped; the reference
+ * raises IndexError there, which the Python wrapper (myolo.rice) reproduces before the launch. */
+int myolo_polygon_masks(const double* verts_y, const double* verts_x, const int* offsets, int n_inst, int H, int W, int M,
+                        unsigned char* masks, myolo_stream stream);
+
 /* ---- the data-parallel exchange step: ONE sum all-reduce of the flat fp32 gradient buffer per step, issued
  * as two slices (mask-head tail first, overlapping the backbone backward).  The reference has no distributed code; this
  * is the NCCL communicator behind the C ABI (bound at run time to the libnccl.so.2 PyTorch ships and has loaded).
