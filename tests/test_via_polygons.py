@@ -270,3 +270,51 @@ def test_rice_dataset_device_masks_equal_host_masks(tmp_path):
     boxes = torch.zeros((1, m.shape[-1], 4), dtype=torch.int32, device="cuda")
     C.call("myolo_extract_bboxes", m.unsqueeze(0).contiguous(), 1, s, m.shape[-1], boxes, None)
     assert np.array_equal(boxes[0].cpu().numpy(), mutils.extract_bboxes(m.cpu().numpy().astype(bool)))
+
+
+# ------------------------------------------------------------------------------------------------ live: the reference's own class
+def test_rice_dataset_equals_the_references_own_class_live(tmp_path):
+    """The reference's example/rice/rice_dataset.py, UNMODIFIED, imported here over this package (myolo.config, myolo.model,
+    mrcnn.utils) with a stand-in for the two scikit-image calls it makes (`skimage.io.imread` -> cv2, `skimage.draw.polygon`
+    -> the oracle): its RiceConfig / RiceDataset.load_rice / load_mask / image_reference against myolo.rice on the same VIA
+    project, both region encodings.  Pins everything but the polygon primitive (container-only: needs /root/reference)."""
+    import sys
+    import types
+    ex = "/root/reference/example/rice"
+    if not os.path.isdir(ex):
+        pytest.skip("reference checkout not present on this box")
+    cv2 = pytest.importorskip("cv2")
+    sk, sk_draw, sk_io, sk_color = (types.ModuleType(n) for n in ("skimage", "skimage.draw", "skimage.io", "skimage.color"))
+    sk_draw.polygon = VO.polygon
+    sk_io.imread = lambda path: cv2.imread(path)[:, :, ::-1]
+    sk.draw, sk.io, sk.color = sk_draw, sk_io, sk_color
+    saved = {k: sys.modules.get(k) for k in ("skimage", "skimage.draw", "skimage.io", "skimage.color", "rice_dataset")}
+    sys.modules.update({"skimage": sk, "skimage.draw": sk_draw, "skimage.io": sk_io, "skimage.color": sk_color})
+    sys.path.insert(0, ex)
+    try:
+        import rice_dataset as ref                      # the reference's own file
+        rc, mc = ref.RiceConfig(), rice.RiceConfig()
+        for k in ("NAME", "IMAGES_PER_GPU", "GPU_COUNT", "NUM_CLASSES", "BATCH_SIZE"):
+            assert getattr(rc, k) == getattr(mc, k), k
+        images = [(im["polygons"],) + _size_for(im["polygons"], margin=5) for im in _fixture_images()[12:16]]
+        for v1 in (False, True):
+            root = _write_via_dataset(str(tmp_path / ("v1" if v1 else "v2")), images, v1)
+            a, b = ref.RiceDataset(), rice.RiceDataset()
+            a.load_rice(root, "train")
+            b.load_rice(root, "train")
+            a.prepare()
+            b.prepare()
+            assert a.class_info == b.class_info and len(a.image_info) == len(b.image_info) == len(images)
+            for ia, ib in zip(a.image_info, b.image_info):
+                assert ia == ib                          # id, source, path, width, height, polygons
+            for k in a.image_ids:
+                (ma, ca), (mb, cb) = a.load_mask(k), b.load_mask(k)
+                assert ma.dtype == mb.dtype and np.array_equal(ma, mb) and ca.dtype == cb.dtype and np.array_equal(ca, cb)
+                assert a.image_reference(k) == b.image_reference(k)
+    finally:
+        sys.path.remove(ex)
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
