@@ -345,6 +345,7 @@ def time_precision(args, precision, cfg, host_batches, world, rank, local, with_
     res["n_roi"] = eng.n_roi
     res["cfg"] = c
     res["sparse_stats"] = dict(eng.sparse_stats)
+    res["phases"] = eng.phase_times() if eng._phases_on else None      # MYOLO_PHASES=1: main-stream phase boundaries of the last step
     del model, eng, dev_batches, out
     import gc
     gc.collect()                      # MaskYOLO <-> keras_model handle is a reference cycle: without this the engine's
@@ -485,6 +486,9 @@ def main():
                 "fp32_class": fp32, "sparse_backward": sparse, "parity": parity,
                 "model_tflops_per_s": value * fl / 1e12, "frac_of_conv_roofline": value * fl / 1e12 / pk["bf16_tflops_sustained"],
                 "loss": main_res["loss"]}
+        if main_res.get("phases"):       # diagnostic (MYOLO_PHASES=1): the extra events cost launch-chain overlap, not a benchmark line
+            line["phases_ms"] = main_res["phases"]
+            line["invalid"] = "MYOLO_PHASES=1 (diagnostic timing events inside the step)"
         from myolo import _cabi
         if _cabi.WHATIF_SKIP:       # profiling run with entry points switched off: timing experiment, not a benchmark
             line["invalid"] = "MYOLO_WHATIF_SKIP=" + ",".join(sorted(_cabi.WHATIF_SKIP))

@@ -336,6 +336,12 @@ int myolo_mask_out_bwd_h(const float* y4, const float* bd, const float* w1, cons
 int myolo_gemm_taps_wgrad_h(const void* A, long long lda, const void* D, long long ldd, float* dW, long long M,
                             int N, int K, int ntaps, const int* shifts_host, int transpose_out,
                             const float* out_scale, myolo_stream stream);
+/* Width of the following myolo_gemm_taps_wgrad_h launches: their split-M CTAs are sized for n SMs (32..148, default 148 = one
+ * CTA per SM).  A filter-gradient launch issued on its own stream next to the backbone's backward leaves 148 - n SMs to
+ * that chain's kernels (the persistent CTAs hold 197 KB of shared memory each, so nothing tensor-core-sized fits beside
+ * them).  Process-global, takes effect in issue order like every other entry point; no reference counterpart. */
+int myolo_set_wgrad_sms(int n);
+
 int myolo_gemm_taps_wgrad_h_supported(long long lda, long long ldd, long long M, int N, int K, int ntaps);
 /* myolo_bn_bwd (fp32 x, fp32 UNSCALED dy) whose dx is stored as half * (*out_scale) in the half view dx_half. */
 int myolo_bn_bwd_h(const myolo_view* x, const myolo_view* dy, const myolo_view* dx_half, const float* mean,
@@ -439,11 +445,12 @@ int myolo_shapes_raster(const int* specs, int B, int S, int MS, int M, int TB, i
  * one image in one launch.  verts_y / verts_x: the concatenated float64 vertex rows / columns of the instances,
  * offsets [n_inst + 1] int32 (instance i owns vertices offsets[i] .. offsets[i+1]-1), all device pointers.
  * masks [H, W, M] bytes (the reference's layout), channels >= n_inst zero; n_inst <= M <= 128, masks 4-byte aligned.
+ * ws: 4*M ints, 16-byte aligned (the instances' candidate boxes, written by the first of the two launches).
  * Inclusion rule: skimage's float64 crossing-number test, restated in csrc/polygon_pip.h (scikit-image is absent here:
  * parity pinned to the oracle's restatement, not to the library).  Pixels outside the image are clipped; the reference
  * raises IndexError there, which the Python wrapper (myolo.rice) reproduces before the launch. */
 int myolo_polygon_masks(const double* verts_y, const double* verts_x, const int* offsets, int n_inst, int H, int W, int M,
-                        unsigned char* masks, myolo_stream stream);
+                        int* ws, unsigned char* masks, myolo_stream stream);
 
 /* ---- the data-parallel exchange step: ONE sum all-reduce of the flat fp32 gradient buffer per step, issued
  * as two slices (mask-head tail first, overlapping the backbone backward).  The reference has no distributed code; this

@@ -17,6 +17,7 @@ namespace myolo {
 namespace tc {
 
 constexpr int kRBH = 64;  // reduction rows per stage
+static int g_wgrad_sms = kNumSMs;   // CTAs per launch are sized for this many SMs (myolo_set_wgrad_sms)
 
 template <int BN, int NACC>
 __global__ void __launch_bounds__(kThreads)
@@ -136,7 +137,8 @@ static int launch_wgrad_h(const CUtensorMap& ta, const CUtensorMap& td, float* d
                           const TapShifts& sh, int transpose_out, const float* out_scale, cudaStream_t st) {
   const int ntk = (K + BM * NACC - 1) / (BM * NACC), ntn = N / BN;
   const long long tiles = (long long)ntk * ntn * ntaps;
-  long long nsplit = max(1LL, min(ceil_div(M, kRBH * 8), (long long)kNumSMs / tiles));
+  // g_wgrad_sms < 148 (myolo_set_wgrad_sms): the launch leaves SMs to the kernels of other streams
+  long long nsplit = max(1LL, min(ceil_div(M, kRBH * 8), (long long)g_wgrad_sms / tiles));
   long long chunk = ceil_div(ceil_div(M, nsplit), kRBH) * kRBH;
   nsplit = ceil_div(M, chunk);
   const size_t per_stage = (size_t)(BM * NACC + BN) * kRBH * 2;
@@ -158,6 +160,12 @@ static int launch_wgrad_h(const CUtensorMap& ta, const CUtensorMap& td, float* d
 
 using namespace myolo;
 using namespace myolo::tc;
+
+extern "C" int myolo_set_wgrad_sms(int n) {
+  MYOLO_CHECK_ARG(n >= 32 && n <= kNumSMs);
+  g_wgrad_sms = n;
+  return MYOLO_OK;
+}
 
 extern "C" int myolo_gemm_taps_wgrad_h_supported(long long lda, long long ldd, long long M, int N, int K, int ntaps) {
   return M >= 64 && M < (1LL << 31) - 4096 && (K % 64) == 0 && (N % 64) == 0 && (lda % 8) == 0 && (ldd % 8) == 0 &&

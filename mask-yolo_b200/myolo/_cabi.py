@@ -106,8 +106,8 @@ def _conv(x):
 KERNELS_PER_CALL = {"myolo_bn_stats": 1, "myolo_bn_bwd": 2, "myolo_bn_bwd_h": 2, "myolo_bn_bwd_hh": 2, "myolo_grad_scale": 2,
                     "myolo_gemm_taps_bnbwd": 2, "myolo_gemm_taps_bnbwd_h": 2, "myolo_gemm_taps_h_stats": 2, "myolo_gemm_taps_hh_stats": 2, "myolo_bn_bwd_batch_fix_hh": 2, "myolo_gemm_segs_win": 2, "myolo_gemm_segs_win_supported": 0, "myolo_gemm_taps_h_supported": 0,
                     "myolo_gemm_taps_wgrad_h_supported": 0, "myolo_colsum": 1, "myolo_detect_mask_targets": 2,
-                    "myolo_mask_loss": 3, "myolo_yolo_loss": 3, "myolo_shapes_raster": 2, "myolo_version": 0, "myolo_last_error": 0,
-                    "myolo_device_check": 0, "myolo_set_precision": 0, "myolo_get_precision": 0,
+                    "myolo_mask_loss": 3, "myolo_yolo_loss": 3, "myolo_shapes_raster": 2, "myolo_polygon_masks": 2, "myolo_version": 0, "myolo_last_error": 0,
+                    "myolo_device_check": 0, "myolo_set_precision": 0, "myolo_get_precision": 0, "myolo_set_wgrad_sms": 0,
                     "myolo_gemm_taps_tc_supported": 0, "myolo_gemm_taps_wgrad_tc_supported": 0}
 launch_count = 0
 

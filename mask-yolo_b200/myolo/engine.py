@@ -126,6 +126,8 @@ class Engine:
         self._shift_cache = {}
         self.inputs_ready = None       # optional CUDA event: inputs[1:] of forward_training are complete
         self.kernel_events = None      # bench.py: list collecting (start, end) CUDA events of the dominant kernel
+        self._phases_on = os.environ.get("MYOLO_PHASES", "0") != "0"
+        self._phase_evs, self._phase_order = {}, []
         # backbone backward: the two filter-gradient kernels of a block (pointwise wgrad, depthwise bwd_filter) run on a
         # side stream next to the data-gradient chain (they are 20-70 us kernels that fill a fraction of the SMs)
         self._side = torch.cuda.Stream(device=self.dev) if os.environ.get("MYOLO_BWD_STREAMS", "1") != "0" else None
@@ -133,9 +135,13 @@ class Engine:
         self._ystream = torch.cuda.Stream(device=self.dev) if os.environ.get("MYOLO_Y_OVERLAP", "1") != "0" else None
         # ... started already behind the yolo loss, i.e. next to the mask head's forward as well (A/B switch)
         self._y_early = os.environ.get("MYOLO_Y_EARLY", "1") != "0"
+        self._yside = torch.cuda.Stream(device=self.dev) if (self._ystream is not None and os.environ.get("MYOLO_Y_SIDE", "1") != "0") else None
         # fourth stream: the mask head's filter gradients, off the data-gradient chain (Engine._backward_mask_h16)
-        self._wstream = torch.cuda.Stream(device=self.dev) if (os.environ.get("MYOLO_W_OVERLAP", "0") != "0" and precision == "h16") else None
+        self._wstream = torch.cuda.Stream(device=self.dev) if (os.environ.get("MYOLO_W_OVERLAP", "1") != "0" and precision == "h16") else None
         self._w_used = False
+        # ... only the last MYOLO_W_DEFER of the five (issue order deconv, conv4, conv3, conv2, conv1), sized for MYOLO_W_SMS SMs
+        self._w_defer = max(0, min(5, int(os.environ.get("MYOLO_W_DEFER", "3"))))
+        self._w_sms = max(32, min(148, int(os.environ.get("MYOLO_W_SMS", "110"))))
         # exact sparse backward of the mask head (h16 mode; OFF by default, never the headline number): above
         # myolo_mask_bn1 only the rois with a target class carry gradient, see _sparse_mask_middle
         if sparse_backward is None:
@@ -523,6 +529,24 @@ class Engine:
         C.call("myolo_gemm_taps_tc_stats", a_rows, K, self.wt[name], out_rows, N, M, N, K, len(sh), arr, 0, 0, b.mean, b.var,
                self.ws, M, self._st())
 
+    def _phase(self, name):
+        """Diagnostic (MYOLO_PHASES=1, scripts/phase_timeline.sh): a timing event on the step's main stream at a phase
+        boundary; recorded as a host action, so it is re-recorded at every replay.  phase_times() reads the last step's."""
+        if not self._phases_on:
+            return
+        e = self._phase_evs.get(name)
+        if e is None:
+            e = self._phase_evs[name] = torch.cuda.Event(enable_timing=True)
+            self._phase_order.append(name)
+        main = torch.cuda.current_stream()
+        C.record_py(lambda: e.record(main))
+
+    def phase_times(self):
+        """[(phase, ms since the previous boundary)] of the last completed step (synchronises)."""
+        torch.cuda.synchronize()
+        ev = [(n, self._phase_evs[n]) for n in self._phase_order]
+        return [(n1, e0.elapsed_time(e1)) for (_, e0), (n1, e1) in zip(ev[:-1], ev[1:])]
+
     def _ke_begin(self):
         """bench.py hook: CUDA events around the dominant kernel (only while kernel_events is a list)"""
         if self.kernel_events is not None:
@@ -807,7 +831,9 @@ class Engine:
         image, true_boxes, yolo_target = inputs[0], inputs[1], inputs[2]
         A, B, st, cfg = self.A, self.B, self._st(), self.cfg
         G, NB, NC, TB, R = cfg["G"], self.NB, self.NC, self.TB, self.R
+        self._phase("start")
         yolo = self.forward(image, training=learning_phase)
+        self._phase("backbone + yolo branch forward, decode")
         C.record_py(self._wait_inputs)         # ground-truth tensors still in flight on the caller's copy stream
         self.seen += 1
         warm = 1 if self.seen < cfg.get("WARM_UP_BATCHES", 0) else 0
@@ -830,9 +856,11 @@ class Engine:
             C.call("myolo_detect_mask_targets", A["proposals"], gt_ids, gt_boxes, gt_masks, B, R, M, gt_masks.shape[3],
                    cfg["S"], mh, mw,
                    A["rois"], self.target_ids, A["target_masks"], self.n_pos, self.roi_src, self.roi_gt, st)
+            self._phase("yolo loss, mask targets (+ yolo-branch backward issued on its stream)")
             masks = self.mask_head(A["rois"], training=learning_phase)
             C.call("myolo_mask_loss", A["masks"], A["target_masks"], self.target_ids, self.n_roi, mh, mw, NC,
                    float(lw.get("myolo_mask_loss", 1.0)), self.loss_mask, A["dlogit"], self.ws_loss, st)
+            self._phase("ROIAlign + mask head forward + mask loss")
             out.update(output_rois=A["rois"], myolo_mask=masks, mask_loss=self.loss_mask[0],
                        target_class_ids=self.target_ids, target_mask=A["target_masks"])
         return out
@@ -862,6 +890,7 @@ class Engine:
             if on_tail_ready is not None and not self._w_used:
                 C.record_py(on_tail_ready)
             C.record_py(lambda: main.wait_event(e1))
+            self._phase("join of the yolo-branch backward")
             self._backward_blocks(blocks[n_y:], main, side, self.ws)
         else:
             C.record_py(self.grads.zero_)
@@ -876,6 +905,7 @@ class Engine:
         st = main.cuda_stream
         self._bn_bwd("conv1_bn", self._v(A["y0"]), C.view(self.gx, B, H0, H0, 32), C.ACT_RELU6, True)
         C.call("myolo_conv1_wgrad", self._image, self.gx, self.g["conv1/kernel"], B, S, 32, st)
+        self._phase("backbone blocks 6..1 + conv1 backward (data-gradient chain)")
         if side is not None and "f_done" in self._evs:
             e = self._evs["f_done"]
             C.record_py(lambda: main.wait_event(e))     # every gradient is in the flat buffer once main passes this point
@@ -884,6 +914,7 @@ class Engine:
             C.record_py(lambda: (ew.record(W), main.wait_event(ew)))
             if on_tail_ready is not None:
                 C.record_py(on_tail_ready)
+        self._phase("join of the filter-gradient streams")
 
     def _start_yolo_branch_backward(self):
         """Zeroes the flat gradient buffer and issues conv_23's and blocks 14..7's backward on the Y stream, behind
@@ -893,8 +924,15 @@ class Engine:
         C.record_py(self.grads.zero_)
         e0, e1 = self._ev("y_fork"), self._ev("y_done")
         C.record_py(lambda: (e0.record(main), ys.wait_event(e0)))          # after grads.zero_()
-        self._backward_conv23(ys, None, self.ws_y)
-        self._backward_blocks(blocks[:len(YOLO_BLOCKS)], ys, None, self.ws_y)
+        # The chain only advances in the gaps between the persistent mask-head kernels (its GEMMs need the shared memory those
+        # hold): with its filter gradients on a stream of their own (MYOLO_Y_SIDE=1) a gap starts two of its kernels instead
+        # of one, and the chain needs half as many gaps.
+        yside = self._yside
+        self._backward_conv23(ys, yside, self.ws_y)
+        self._backward_blocks(blocks[:len(YOLO_BLOCKS)], ys, yside, self.ws_y)
+        if yside is not None:
+            ef = self._evs["f_done"]                      # the chain's last filter-gradient kernel
+            C.record_py(lambda: ys.wait_event(ef))
         C.record_py(lambda: e1.record(ys))
         self._y_started = True
 
@@ -1010,10 +1048,15 @@ class Engine:
         self._w_used = W is not None
 
         deferred = []
+        n_seen = [0]
 
-        def wgrad(*args):       # args end with the stream handle
-            if W is not None:
+        def wgrad(*args):       # args end with the stream handle; issue order: deconv, conv4, conv3, conv2, conv1
+            k = n_seen[0]
+            n_seen[0] += 1
+            if W is not None and k >= 5 - self._w_defer:
                 deferred.append(args)
+            elif W is not None:     # not deferred: inline on the main stream, full width
+                C.call("myolo_gemm_taps_wgrad_h", *(args[:-1] + (st,)))
             else:
                 C.call("myolo_gemm_taps_wgrad_h", *args)
 
@@ -1050,8 +1093,12 @@ class Engine:
         if W is not None:       # the data-gradient chain of the mask head is issued: the filter gradients start behind it
             e = self._ev("w_start")
             C.record_py(lambda: (e.record(main), W.wait_event(e)))
+            if self._w_sms < 148:
+                C.call("myolo_set_wgrad_sms", self._w_sms)
             for args in deferred:
                 C.call("myolo_gemm_taps_wgrad_h", *args)
+            if self._w_sms < 148:
+                C.call("myolo_set_wgrad_sms", 148)
         return self.mg[1]
 
     def _dense_mask_middle(self, G, wgrad, M, pfw, pfb, sh3, shn, ugs, st):
@@ -1159,7 +1206,10 @@ class Engine:
         pfw, pfb = P_ + 1, (P_ + 1) * (P_ + 1)
         if self.h16:
             g0 = self._backward_mask_h16()
-            return self._backward_feature_map(g0)
+            self._phase("mask head backward (loss .. d(x0))")
+            self._backward_feature_map(g0)
+            self._phase("ROIAlign backward + feature_map backward")
+            return
         a4 = self.ma[4]
         C.call("myolo_mask_out_bwd", self.y4d.rows, self.p["myolo_mask_deconv/bias"], self.p["myolo_mask/kernel"],
                A["dlogit"], self.dy4d.rows, self.g["myolo_mask/kernel"], self.g["myolo_mask/bias"],
@@ -1270,6 +1320,7 @@ class Engine:
         self._bn_touched = []
         self.version += 1
         self.refresh_weights()
+        self._phase("Adam + BN moving update + weight staging")
 
     def train_step(self, inputs, lr: float = 1e-3, allreduce=None):
         """One fit step.  `allreduce(flat_grads, lo, hi)` (optional) sums gradient slices across

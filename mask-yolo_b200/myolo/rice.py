@@ -97,7 +97,8 @@ class DevicePolygons(object):
         d_vy, d_vx = torch.from_numpy(vy).to(self.dev), torch.from_numpy(vx).to(self.dev)
         d_off = torch.from_numpy(off).to(self.dev)
         out = torch.empty((height, width, n), dtype=torch.uint8, device=self.dev)
-        C.call("myolo_polygon_masks", d_vy, d_vx, d_off, n, height, width, n, out,
+        ws = torch.empty(4 * n, dtype=torch.int32, device=self.dev)
+        C.call("myolo_polygon_masks", d_vy, d_vx, d_off, n, height, width, n, ws, out,
                torch.cuda.current_stream(self.dev).cuda_stream)
         return out
 

@@ -34,9 +34,10 @@ for (H, W) in ((608, 800), (2048, 2048)):
     vx = torch.from_numpy(np.concatenate([np.asarray(p["all_points_x"], np.float64) for p in ps])).cuda()
     d_off = torch.from_numpy(off).cuda()
     out = torch.empty((H, W, n), dtype=torch.uint8, device="cuda")
+    ws = torch.empty(4 * n, dtype=torch.int32, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
     for _ in range(3):
-        C.call("myolo_polygon_masks", vy, vx, d_off, n, H, W, n, out, st)
+        C.call("myolo_polygon_masks", vy, vx, d_off, n, H, W, n, ws, out, st)
     torch.cuda.synchronize()
     assert np.array_equal(out.cpu().numpy(), host)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -45,7 +46,7 @@ for (H, W) in ((608, 800), (2048, 2048)):
     for _ in range(reps):
         flush.zero_()
         e0.record()
-        C.call("myolo_polygon_masks", vy, vx, d_off, n, H, W, n, out, st)
+        C.call("myolo_polygon_masks", vy, vx, d_off, n, H, W, n, ws, out, st)
         e1.record()
         e1.synchronize()
         tot += e0.elapsed_time(e1)

@@ -235,11 +235,12 @@ def test_device_entry_point_contract():
     vy, vx = torch.tensor(p["all_points_y"], dtype=torch.float64).cuda(), torch.tensor(p["all_points_x"], dtype=torch.float64).cuda()
     off = torch.tensor([0, 4], dtype=torch.int32).cuda()
     out = torch.full((7, 9, 4), 255, dtype=torch.uint8, device="cuda")
-    C.call("myolo_polygon_masks", vy, vx, off, 1, 7, 9, 4, out, None)
+    ws = torch.empty(16, dtype=torch.int32, device="cuda")
+    C.call("myolo_polygon_masks", vy, vx, off, 1, 7, 9, 4, ws, out, None)
     o = out.cpu().numpy()
     assert o[:, :, 1:].sum() == 0 and np.array_equal(o[:, :, 0].astype(bool), _oracle_mask([p], 7, 9)[:, :, 0])
     with pytest.raises(C.MyoloError, match="argument check failed"):
-        C.call("myolo_polygon_masks", vy, vx, off, 5, 7, 9, 4, out, None)          # more instances than channels
+        C.call("myolo_polygon_masks", vy, vx, off, 5, 7, 9, 4, ws, out, None)          # more instances than channels
     with pytest.raises(IndexError):                                                # the reference's error, before the launch
         dp.masks([{"all_points_y": [0, 0, 12, 12], "all_points_x": [0, 4, 4, 0]}], 9, 10)
     assert tuple(dp.masks([], 5, 6).shape) == (5, 6, 0)
