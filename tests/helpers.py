@@ -93,13 +93,15 @@ def box_iou_pairs(a, b):
     return torch.where(union > 0, inter / union.clamp(min=1e-300), torch.ones_like(union))
 
 
-def mask_iou(a, b, thr=0.5):
+def mask_iou(a, b, thr=0.5, return_union=False):
     """IoU of the masks binarised at `thr`, per (roi, class): inputs [..., H, W, NC] -> [..., NC]; two empty masks
-    count as identical (1)."""
+    count as identical (1).  With return_union also the pixel count of the union (a mask of a few pixels turns one
+    probability on either side of `thr` into an IoU of 0 or 1/2)."""
     a, b = a.detach().cpu() >= thr, b.detach().cpu() >= thr
     inter = (a & b).sum(dim=(-3, -2)).double()
     union = (a | b).sum(dim=(-3, -2)).double()
-    return torch.where(union > 0, inter / union.clamp(min=1), torch.ones_like(union))
+    iou = torch.where(union > 0, inter / union.clamp(min=1), torch.ones_like(union))
+    return (iou, union) if return_union else iou
 
 
 def sample_validity(rois, F_, pool=14):
@@ -136,9 +138,13 @@ def step_parity(dev, ref, F_):
     keep = same_img[:, None].expand(B, R).reshape(-1) & ~flips
     dm = (dev["myolo_mask"].detach().cpu().reshape(B * R, -1, NC) - ref["myolo_mask"].float().reshape(B * R, -1, NC)).abs()
     mh = int(round(dm.shape[1] ** 0.5))
-    miou = mask_iou(dev["myolo_mask"].detach().cpu().reshape(B * R, mh, mh, NC)[keep], ref["myolo_mask"].reshape(B * R, mh, mh, NC)[keep])
+    miou, munion = mask_iou(dev["myolo_mask"].detach().cpu().reshape(B * R, mh, mh, NC)[keep],
+                            ref["myolo_mask"].reshape(B * R, mh, mh, NC)[keep], return_union=True)
+    big = munion >= 16          # binarised masks of fewer pixels: one probability within the error of 0.5 decides the IoU
     out.update(box_iou_mean=biou.mean().item(), box_iou_min=biou.min().item(),
                mask_iou_mean=miou.mean().item(), mask_iou_min=miou.min().item(),
+               mask_iou_min_union_ge_16px=miou[big].min().item() if bool(big.any()) else None,
+               masks_with_union_lt_16px=int((~big & (munion > 0)).sum()),
                max_abs_mask_err=dm[keep].max().item() if bool(keep.any()) else None,
                rois_compared=int(keep.sum()), rois_total=B * R, rois_with_flipped_border_sample=int(flips.sum()),
                images_with_identical_roi_selection=int(same_img.sum()), images=B,
