@@ -339,7 +339,8 @@ int myolo_gemm_taps_wgrad_h(const void* A, long long lda, const void* D, long lo
 /* Width of the following myolo_gemm_taps_wgrad_h launches: their split-M CTAs are sized for n SMs (32..148, default 148 = one
  * CTA per SM).  A filter-gradient launch issued on its own stream next to the backbone's backward leaves 148 - n SMs to
  * that chain's kernels (the persistent CTAs hold 197 KB of shared memory each, so nothing tensor-core-sized fits beside
- * them).  Process-global, takes effect in issue order like every other entry point; no reference counterpart. */
+ * them).  Process-global, takes effect in issue order like every other entry point; it changes the launch geometry only
+ * (how the reduction over rows is split), never which sums are formed; no reference counterpart. */
 int myolo_set_wgrad_sms(int n);
 
 int myolo_gemm_taps_wgrad_h_supported(long long lda, long long ldd, long long M, int N, int K, int ntaps);

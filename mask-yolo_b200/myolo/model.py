@@ -671,6 +671,13 @@ class MaskYOLO:
         masks = pm[0, :n].permute(1, 2, 0).bool().cpu().numpy() if n else np.zeros(tuple(image.shape[:2]) + (0,), bool)
         return DetectResults(boxes[0, :n].cpu().numpy(), cls[0, :n].cpu().numpy(), score[0, :n].cpu().numpy(), masks)
 
+    def detect_for_one(self, images, verbose=0):
+        """The call the reference's example scripts make (example/shapes/infer_shapes.py:52, example/rice/rice_dataset.py:232)
+        although myolo/model.py defines no such method at HEAD: detect() on a one-element list of images, same
+        result list (`results[0]['rois' | 'masks' | 'class_ids' | 'scores']`)."""
+        assert len(images) == 1, "only detect for one image per time"
+        return self.detect(images[0])
+
     def decode_masks(self, detections, myolo_mask, image_shape):
         """Network outputs of ONE image -> (boxes [N,4] normalised (x1,y1,x2,y2), class_ids [N], scores [N], full-size
         boolean masks [H,W,N])  (model.py:1330-1391): class-specific 28x28 masks, zero-area boxes dropped, each mask

@@ -305,3 +305,15 @@ def test_padded_flat_layout_turns_a_3x3_same_conv_into_nine_shifted_gemms():
     v = A.view()
     assert (v.n, v.h, v.w, v.c, v.sh, v.sn) == (n, H, W, C, (W + 1) * C, (H + 1) * (W + 1) * C)
     assert v.p == A.rows.data_ptr() + 8 * ((W + 1) + 1) * C                     # first valid pixel, float64 here
+
+
+def test_detect_for_one_is_detect_on_a_one_element_list():
+    """the example scripts call model.detect_for_one([image], verbose=1); the reference defines no such method."""
+    from myolo.model import MaskYOLO
+    m = MaskYOLO.__new__(MaskYOLO)              # no engine: only the delegation is checked here
+    seen = []
+    m.detect = lambda image: (seen.append(image), ["result"])[1]
+    img = np.zeros((4, 4, 3), np.uint8)
+    assert m.detect_for_one([img], verbose=1) == ["result"] and seen[0] is img
+    with pytest.raises(AssertionError):
+        m.detect_for_one([img, img])
