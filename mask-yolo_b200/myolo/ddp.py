@@ -1,7 +1,8 @@
 """Data parallelism for Mask-YOLO training: one process per GPU, batch sharded across ranks, ONE
 gradient exchange per step.  The flat gradient buffer is all-reduced (sum) in two
 buckets -- the feature_map + mask-head tail as soon as the mask-branch backward has produced it
-(asynchronously, overlapping the backbone backward), the backbone/yolo head at the end -- and the
+(asynchronously; under the backbone backward when every filter gradient is issued in line, at the join of the
+filter-gradient stream in the default h16 schedule, Engine.backward), the backbone/yolo head at the end -- and the
 1/world factor is folded into the fused Adam kernel.  BatchNorm statistics and the loss normalisers
 stay per replica, so an N-rank step is the mean of N single-replica reference steps.
 The reference has no distributed code.  Two transports carry the exchange: `torch.distributed` (NCCL over NVLink on
