@@ -1,4 +1,6 @@
 #!/bin/bash
+# NOTE: MYOLO_BENCH_HIPRI / MYOLO_WGRAD_SPLIT_MUL / MYOLO_CARVEOUT were switches of this experiment only (all negative,
+# profiles/r02_wgrad_overlap_priority_split_ab_negative.txt); they are not in the tree any more.
 # (1) GPU tests of the VIA polygon rasteriser + its timing; (2) A/B: main chain on a high-priority stream, mask-head filter
 # gradients deferred to their own stream (MYOLO_W_OVERLAP) as shorter CTAs (MYOLO_WGRAD_SPLIT_MUL), max-shared carve-out
 mkdir -p gpurun_out

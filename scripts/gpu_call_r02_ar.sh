@@ -1,4 +1,6 @@
 #!/bin/bash
+# NOTE: MYOLO_WGRAD_SMS was this experiment's process-wide form of what became myolo_set_wgrad_sms / MYOLO_W_SMS
+# (profiles/r02_wgrad_sm_subset_ab.txt); with the current tree use MYOLO_W_DEFER=5 MYOLO_W_SMS=<n> for the same runs.
 # (1) GPU tests + timing of the two-launch polygon rasteriser; (2) A/B: mask-head filter gradients deferred to their own stream
 # (MYOLO_W_OVERLAP=1) on a SUBSET of the SMs (MYOLO_WGRAD_SMS), so that the backbone's backward finds free SMs next to them
 mkdir -p gpurun_out
