@@ -21,11 +21,16 @@ from .config import Config
 
 
 class RiceConfig(Config):
-    """example/rice/rice_dataset.py:60-82."""
+    """example/rice/rice_dataset.py:60-82 (that file names its configuration, source and class "food")."""
     NAME = "food"
     IMAGES_PER_GPU = 2
     GPU_COUNT = 0
     NUM_CLASSES = 1 + 1
+
+
+class FoodExampleRiceConfig(RiceConfig):
+    """The RiceConfig of example/food/rice_dataset.py:60-82: the same file with the two words swapped (NAME "rice")."""
+    NAME = "rice"
 
 
 def polygon(r, c, shape=None):
@@ -104,12 +109,20 @@ class DevicePolygons(object):
 
 
 class RiceDataset(utils.Dataset):
-    """example/rice/rice_dataset.py:89-168."""
+    """example/rice/rice_dataset.py:89-168.  `source` is the word that file uses for its dataset source, its one class and
+    its annotation file (`via_<source>_annotation.json`): "food" in example/rice (the default), "rice" in the otherwise
+    identical example/food/rice_dataset.py."""
 
-    def load_rice(self, dataset_dir, subset, annotation_file="via_food_annotation.json"):
+    def __init__(self, source="food", class_map=None):
+        super().__init__(class_map)
+        self.source = source
+
+    def load_rice(self, dataset_dir, subset, annotation_file=None):
         """VIA json -> one image record per annotated file, with its polygons (`shape_attributes` dicts).  The reference
-        hard-codes the file name `via_food_annotation.json` (rice_dataset.py:102); it stays the default."""
-        self.add_class("food", 1, "food")
+        hard-codes the file name (rice_dataset.py:102); it is the default here."""
+        src = self.source
+        annotation_file = annotation_file or "via_%s_annotation.json" % src
+        self.add_class(src, 1, src)
         assert subset in ["train", "val"]
         dataset_dir = os.path.join(dataset_dir, subset)
         with open(os.path.join(dataset_dir, annotation_file)) as fh:
@@ -122,7 +135,7 @@ class RiceDataset(utils.Dataset):
                 polygons = [r['shape_attributes'] for r in a['regions']]
             image_path = os.path.join(dataset_dir, a['filename'])
             height, width = self._image_size(image_path)
-            self.add_image("food", image_id=a['filename'], path=image_path, width=width, height=height, polygons=polygons)
+            self.add_image(src, image_id=a['filename'], path=image_path, width=width, height=height, polygons=polygons)
 
     @staticmethod
     def _image_size(path):
@@ -135,7 +148,7 @@ class RiceDataset(utils.Dataset):
     def load_mask(self, image_id):
         """(bool [height, width, instances], int32 ones [instances]); rice_dataset.py:135-159."""
         info = self.image_info[image_id]
-        if info["source"] != "food":
+        if info["source"] != self.source:
             return super().load_mask(image_id)
         mask = np.zeros([info["height"], info["width"], len(info["polygons"])], dtype=np.uint8)
         for i, p in enumerate(info["polygons"]):
@@ -151,6 +164,6 @@ class RiceDataset(utils.Dataset):
 
     def image_reference(self, image_id):
         info = self.image_info[image_id]
-        if info["source"] == "food":
+        if info["source"] == self.source:
             return info["path"]
         return super().image_reference(image_id)

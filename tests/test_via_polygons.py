@@ -162,8 +162,8 @@ def test_device_rule_compiled_for_the_host_equals_oracle(pip_host):
             assert np.array_equal(pip_host(p, h, w).astype(bool), want[:, :, i])
 
 
-def _write_via_dataset(root, images, v1=False):
-    """A VIA project on disk: <root>/train/*.png + via_food_annotation.json (2.x list regions, or 1.x dict regions)."""
+def _write_via_dataset(root, images, v1=False, word="food"):
+    """A VIA project on disk: <root>/train/*.png + via_<word>_annotation.json (2.x list regions, or 1.x dict regions)."""
     cv2 = pytest.importorskip("cv2")
     d = os.path.join(root, "train")
     os.makedirs(d, exist_ok=True)
@@ -175,7 +175,7 @@ def _write_via_dataset(root, images, v1=False):
         ann[name + "123"] = {"filename": name, "size": 123, "file_attributes": {},
                              "regions": {str(i): r for i, r in enumerate(regs)} if v1 else regs}
     ann["empty.png9"] = {"filename": "empty.png", "size": 9, "regions": [] if not v1 else {}, "file_attributes": {}}
-    json.dump(ann, open(os.path.join(d, "via_food_annotation.json"), "w"))
+    json.dump(ann, open(os.path.join(d, "via_%s_annotation.json" % word), "w"))
     return root
 
 
@@ -274,14 +274,15 @@ def test_rice_dataset_device_masks_equal_host_masks(tmp_path):
 
 
 # ------------------------------------------------------------------------------------------------ live: the reference's own class
-def test_rice_dataset_equals_the_references_own_class_live(tmp_path):
+@pytest.mark.parametrize("example,word", [("rice", "food"), ("food", "rice")])
+def test_rice_dataset_equals_the_references_own_class_live(tmp_path, example, word):
     """The reference's example/rice/rice_dataset.py, UNMODIFIED, imported here over this package (myolo.config, myolo.model,
     mrcnn.utils) with a stand-in for the two scikit-image calls it makes (`skimage.io.imread` -> cv2, `skimage.draw.polygon`
     -> the oracle): its RiceConfig / RiceDataset.load_rice / load_mask / image_reference against myolo.rice on the same VIA
     project, both region encodings.  Pins everything but the polygon primitive (container-only: needs /root/reference)."""
     import sys
     import types
-    ex = "/root/reference/example/rice"
+    ex = "/root/reference/example/" + example        # example/rice says "food" everywhere, example/food says "rice"
     if not os.path.isdir(ex):
         pytest.skip("reference checkout not present on this box")
     cv2 = pytest.importorskip("cv2")
@@ -294,13 +295,13 @@ def test_rice_dataset_equals_the_references_own_class_live(tmp_path):
     sys.path.insert(0, ex)
     try:
         import rice_dataset as ref                      # the reference's own file
-        rc, mc = ref.RiceConfig(), rice.RiceConfig()
+        rc, mc = ref.RiceConfig(), (rice.RiceConfig() if word == "food" else rice.FoodExampleRiceConfig())
         for k in ("NAME", "IMAGES_PER_GPU", "GPU_COUNT", "NUM_CLASSES", "BATCH_SIZE"):
             assert getattr(rc, k) == getattr(mc, k), k
         images = [(im["polygons"],) + _size_for(im["polygons"], margin=5) for im in _fixture_images()[12:16]]
         for v1 in (False, True):
-            root = _write_via_dataset(str(tmp_path / ("v1" if v1 else "v2")), images, v1)
-            a, b = ref.RiceDataset(), rice.RiceDataset()
+            root = _write_via_dataset(str(tmp_path / ("v1" if v1 else "v2")), images, v1, word)
+            a, b = ref.RiceDataset(), rice.RiceDataset(source=word)
             a.load_rice(root, "train")
             b.load_rice(root, "train")
             a.prepare()
@@ -314,6 +315,7 @@ def test_rice_dataset_equals_the_references_own_class_live(tmp_path):
                 assert a.image_reference(k) == b.image_reference(k)
     finally:
         sys.path.remove(ex)
+        sys.modules.pop("rice_dataset", None)
         for k, v in saved.items():
             if v is None:
                 sys.modules.pop(k, None)
